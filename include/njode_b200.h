@@ -1,0 +1,182 @@
+/* njode_b200 -- C ABI of the B200-native NJ-ODE hot path (libnjode_b200.so).
+ *
+ * Plain C, raw device pointers and sizes, no torch types.  Every entry point returns 0 on success
+ * and a negative code on failure; njode_last_error() returns a human-readable message for the last
+ * failure of the calling thread.  Kernels never allocate: the caller owns every buffer (sizes come
+ * from njode_plan()).  All work is enqueued on the given CUDA stream (cudaStream_t passed as void*).
+ *
+ * The reference (HerreraKrachTeichmann/NJODE) is pure Python and has no FFI; these entry points
+ * replace, as a unit, the Python functions named next to each of them (paths relative to the
+ * reference tree).  The reference-side binding is the ctypes stub in INTEGRATION.md /
+ * njode_b200/_ext.py.
+ */
+#ifndef NJODE_B200_H
+#define NJODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NJODE_ABI_VERSION 1
+#define NJODE_MAX_LINEAR 8          /* max number of Linear layers per network */
+
+enum { NJODE_ACT_NONE = 0, NJODE_ACT_TANH = 1, NJODE_ACT_RELU = 2 };
+enum { NJODE_LOSS_STANDARD = 0, NJODE_LOSS_EASY = 1 };     /* NJODE/models.py:129-132 LOSS_FUN_DICT */
+enum { NJODE_NET_ODE = 0, NJODE_NET_ENC = 1, NJODE_NET_RO = 2 };
+
+/* one feed-forward network as built by get_ffnn (NJODE/models.py:140-166): n_linear Linear layers,
+ * an activation (+dropout) after every layer but the last.  Weights are nn.Linear layout
+ * [out, in] row-major fp32 at float offset w_off[l] of the flat parameter buffer; b_off[l] = -1
+ * when bias=False. */
+typedef struct njode_mlp {
+    int32_t n_linear;
+    int32_t dims[NJODE_MAX_LINEAR + 1];
+    int32_t act[NJODE_MAX_LINEAR];
+    int64_t w_off[NJODE_MAX_LINEAR];
+    int64_t b_off[NJODE_MAX_LINEAR];
+} njode_mlp_t;
+
+/* constructor state of NJODE (NJODE/models.py:284-362) that the kernels need */
+typedef struct njode_model {
+    int32_t input_size, hidden_size, output_size;
+    int32_t masked;            /* options['masked']            NJODE/models.py:339-341 */
+    int32_t input_current_t;   /* options['input_current_t']   NJODE/models.py:334-337 */
+    int32_t loss_kind;         /* options['which_loss']        NJODE/models.py:322-326 */
+    int32_t residual;          /* options['residual_enc_dec']  NJODE/models.py:329-332 */
+    int32_t training;          /* module.training (dropout on) */
+    float   weight;            /* model.weight, NJODE/models.py:316,364-367 */
+    float   dropout_p;
+    uint64_t dropout_seed;     /* counter-based masks keyed (seed, path, event, net, layer, neuron) */
+    int64_t n_params;          /* floats in the flat parameter / gradient buffer */
+    njode_mlp_t net[3];        /* NJODE_NET_ODE / ENC / RO */
+} njode_model_t;
+
+/* one batch in the reference's collate contract (NJODE/data_utils.py:311-315) plus the host-built
+ * event schedule (restating the float64 loop conditions of NJODE/models.py:430-439,497-505) and the
+ * per-path CSR of observation rows.  All pointers are DEVICE pointers. */
+typedef struct njode_batch {
+    int32_t B;                 /* paths on this rank */
+    int32_t N;                 /* observation rows  = time_ptr[-1] */
+    int32_t K;                 /* observation times = len(times) */
+    int32_t S;                 /* Euler steps the reference executes for this batch */
+    int32_t E;                 /* recorded events (len(path_t)) when return_path, else 0 */
+    int32_t batch_size_norm;   /* batch size used in the loss normalisation (global B under DP) */
+    int32_t path_id_offset;    /* global id of local path 0 (dropout keys are rank-invariant) */
+    int32_t n_units;           /* work units, see unit_desc */
+    const float*   X;          /* [N, input_size] */
+    const float*   M;          /* [N, input_size] or NULL */
+    const float*   start_X;    /* [B, input_size] */
+    const float*   n_obs_ot;   /* [B] as float, or NULL when no loss is requested */
+    const int32_t* path_ptr;   /* [B+1]  CSR over paths ... */
+    const int32_t* path_rows;  /* [N]    ... row ids of each path in time order */
+    const int32_t* row_jump;   /* [N]    observation-time index i of each row */
+    const float*   step_dt;    /* [S]    fl32(delta_t_) of Euler step k */
+    const float*   step_t;     /* [S]    fl32(current_time) at the start of step k */
+    const int32_t* jump_step;  /* [K]    number of Euler steps executed before jump i */
+    const float*   jump_tau;   /* [K]    fl32(times[i]) */
+    const int32_t* step_event; /* [S]    index into path_t of the record after step k (return_path) */
+    const int32_t* jump_event; /* [K]    index into path_t of the record after jump i  (return_path) */
+    /* work units: 6 int32 each = {path, s0, s1, c0, c1, start_code}; a unit integrates path `path`
+     * over Euler steps [s0, s1), applying the path's jumps path_rows[c0..c1) where they fall,
+     * starting from enc(X[start_row]) or, when start_row = -1, enc(start_X[path]).
+     * start_code = (start_row + 1) | NJODE_UNIT_WRITES_HT if the unit ends its path (writes hT). */
+    const int32_t* unit_desc;  /* [n_units, 6], sorted by length (longest first) */
+} njode_batch_t;
+
+#define NJODE_UNIT_WRITES_HT (1 << 30)
+
+/* launch plan / buffer sizes for one (model, batch-shape) pair */
+typedef struct njode_plan {
+    int32_t tile_paths;        /* units marched in lockstep by one CTA */
+    int32_t threads;
+    int32_t grid_fwd, grid_bwd;
+    int32_t weights_in_smem, grads_in_smem;
+    int64_t smem_fwd_bytes, smem_bwd_bytes;
+    int64_t image_floats;      /* padded parameter image (also the per-CTA gradient partial) */
+    int64_t workspace_bytes;   /* scratch the caller must provide to forward/backward */
+} njode_plan_t;
+
+/* buffers produced by the forward pass that the backward pass re-reads */
+typedef struct njode_saved {
+    float* h_hist;             /* [S, B, hidden]  h at the start of every Euler step, or NULL (no grad) */
+    float* h_before;           /* [N, hidden]     h just before the jump of row r, or NULL */
+    float* y_after;            /* [N, output]     Y = readout(h after jump) of row r, or NULL */
+} njode_saved_t;
+
+const char* njode_last_error(void);
+int njode_abi_version(void);
+
+/* sizes and launch geometry.  `device` = CUDA ordinal. */
+int njode_plan(const njode_model_t* model, const njode_batch_t* batch_shape, int device,
+               njode_plan_t* plan_out);
+
+/* NJODE.forward (NJODE/models.py:379-518) incl. ode_step (369-377), ODEFunc.forward (188-199),
+ * FFNN.forward (261-276), the jump scatter (449-489), compute_loss / compute_loss_2 (71-126).
+ *   params    [n_params] flat fp32 parameters (layout given by model->net[*].w_off/b_off)
+ *   hT        [B, hidden]             out
+ *   loss      [1]                     out (sum over rows / batch_size_norm), or NULL (get_loss=False)
+ *   path_h    [E, B, hidden] / path_y [E, B, output]   out when batch->E > 0 (return_path=True)
+ *   saved     history for njode_backward, members may be NULL when no gradient is needed
+ *   workspace [plan.workspace_bytes] */
+int njode_forward(const njode_model_t* model, const njode_batch_t* batch, const float* params,
+                  float* hT, float* loss, float* path_h, float* path_y,
+                  const njode_saved_t* saved, void* workspace, void* stream);
+
+/* reverse pass of the same computation = the autograd tape replay of loss.backward()
+ * (NJODE/train.py:522) for all parameter tensors.
+ *   grad_loss [1] device scalar dL/dloss ; grad_hT [B, hidden] or NULL
+ *   grads     [n_params] out (overwritten), same layout as params */
+int njode_backward(const njode_model_t* model, const njode_batch_t* batch, const float* params,
+                   const njode_saved_t* saved, const float* grad_loss, const float* grad_hT,
+                   float* grads, void* workspace, void* stream);
+
+/* Euler-Maruyama generators + Bernoulli observation mask (NJODE/stock_model.py:181-221, 288-335,
+ * 356-375, 397-418 and NJODE/data_utils.py:73-81), one Philox-4x32-10 subsequence per global path id. */
+enum { NJODE_SDE_BLACK_SCHOLES = 0, NJODE_SDE_ORNSTEIN_UHLENBECK = 1, NJODE_SDE_HESTON = 2,
+       NJODE_SDE_HESTON_WO_FELLER = 3 };
+
+typedef struct njode_sde {
+    int32_t model;             /* NJODE_SDE_* */
+    int32_t dimension;         /* independent copies per path (np.size(S0), stock_model.py:28) */
+    int32_t nb_steps;
+    int32_t return_vol;        /* HestonWOFeller: append variance coordinates (stock_model.py:329-330) */
+    double  drift, volatility, mean, speed, correlation, v0, maturity;
+    double  sine_coeff;        /* periodic_coeff(t) = 1 + sin(sine_coeff t); NaN = constant 1 (stock_model.py:29-32) */
+    double  obs_perc;
+    double  t0;                /* time of column 0 (combined datasets chain models, data_utils.py:141-157) */
+    uint64_t seed;
+} njode_sde_t;
+
+/*   first_path  global id of path 0 of this call (data are identical for any sharding)
+ *   S0          [dimension] start values, or start_X [n_paths, dimension] when per_path_start != 0
+ *   paths       [n_paths, out_dim, nb_steps+1] float64 out (out_dim = dimension * (1 + return_vol))
+ *   observed    [n_paths, nb_steps+1] int32 out or NULL; nb_obs [n_paths] int32 out or NULL */
+int njode_sde_generate(const njode_sde_t* sde, int64_t first_path, int64_t n_paths,
+                       const double* S0, int per_path_start, double* paths, int32_t* observed,
+                       int32_t* nb_obs, void* stream);
+
+/* on-device restatement of custom_collate_fn (NJODE/data_utils.py:278-316) for a set of paths of a
+ * device-resident dataset: rows ordered (time ascending, batch position ascending).
+ *   sel [B] dataset indices of the batch; outputs sized for the worst case N <= B * nb_steps.
+ *   counts_out [2] = {K, N} (device) */
+int njode_collate(const double* paths, const int32_t* observed, int64_t n_paths_total, int32_t dim,
+                  int32_t nb_steps, const int64_t* sel, int32_t B, float* X, int32_t* obs_idx,
+                  int32_t* time_ptr, int32_t* time_idx, float* start_X, int32_t* n_obs_ot,
+                  int32_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- measurement helpers (bench.py) -------------------------------------------------------- */
+/* device-side timing of the main forward / backward kernel of the most recent call (cudaEvents on
+ * the launching stream); enable with njode_set_timing(1) or NJODE_TIMING=1. */
+void njode_set_timing(int on);
+int njode_get_timing(float* fwd_ms, float* bwd_ms);
+/* fp32 FMA-pipe microbenchmark: dependent chains of FFMA on every SM; *fmas = lane-FMAs issued */
+int njode_fma_peak_launch(float* scratch, int iters, double* fmas, void* stream);
+/* writes `bytes` of buf (size it > L2) so the next kernel starts with a cold L2 */
+int njode_l2_flush(void* buf, int64_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NJODE_B200_H */

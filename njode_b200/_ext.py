@@ -1,0 +1,274 @@
+"""ctypes binding of libnjode_b200.so (C ABI in include/njode_b200.h) and the per-batch staging
+logic.  There is no CPU fallback: ``cuda_lib()`` raises when the CUDA library is missing and the
+runner refuses non-CUDA devices.  (``Lib`` can be pointed at another build of the same ABI; the
+test-suite uses that to run the host *simulation* of the kernel source, never the product.)"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import schedule as _sched
+
+MAX_LINEAR = 8
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB_PATH = os.path.join(_HERE, "libnjode_b200.so")
+
+
+class MlpT(C.Structure):
+    _fields_ = [("n_linear", C.c_int32), ("dims", C.c_int32 * (MAX_LINEAR + 1)),
+                ("act", C.c_int32 * MAX_LINEAR), ("w_off", C.c_int64 * MAX_LINEAR),
+                ("b_off", C.c_int64 * MAX_LINEAR)]
+
+
+class ModelT(C.Structure):
+    _fields_ = [("input_size", C.c_int32), ("hidden_size", C.c_int32), ("output_size", C.c_int32),
+                ("masked", C.c_int32), ("input_current_t", C.c_int32), ("loss_kind", C.c_int32),
+                ("residual", C.c_int32), ("training", C.c_int32), ("weight", C.c_float),
+                ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("n_params", C.c_int64),
+                ("net", MlpT * 3)]
+
+
+class BatchT(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("S", C.c_int32),
+                ("E", C.c_int32), ("batch_size_norm", C.c_int32), ("path_id_offset", C.c_int32),
+                ("n_units", C.c_int32),
+                ("X", C.c_void_p), ("M", C.c_void_p), ("start_X", C.c_void_p), ("n_obs_ot", C.c_void_p),
+                ("path_ptr", C.c_void_p), ("path_rows", C.c_void_p), ("row_jump", C.c_void_p),
+                ("step_dt", C.c_void_p), ("step_t", C.c_void_p), ("jump_step", C.c_void_p),
+                ("jump_tau", C.c_void_p), ("step_event", C.c_void_p), ("jump_event", C.c_void_p),
+                ("unit_desc", C.c_void_p)]
+
+
+class PlanT(C.Structure):
+    _fields_ = [("tile_paths", C.c_int32), ("threads", C.c_int32), ("grid_fwd", C.c_int32),
+                ("grid_bwd", C.c_int32), ("weights_in_smem", C.c_int32), ("grads_in_smem", C.c_int32),
+                ("smem_fwd_bytes", C.c_int64), ("smem_bwd_bytes", C.c_int64),
+                ("image_floats", C.c_int64), ("workspace_bytes", C.c_int64)]
+
+
+class SavedT(C.Structure):
+    _fields_ = [("h_hist", C.c_void_p), ("h_before", C.c_void_p), ("y_after", C.c_void_p)]
+
+
+class SdeT(C.Structure):
+    _fields_ = [("model", C.c_int32), ("dimension", C.c_int32), ("nb_steps", C.c_int32),
+                ("return_vol", C.c_int32), ("drift", C.c_double), ("volatility", C.c_double),
+                ("mean", C.c_double), ("speed", C.c_double), ("correlation", C.c_double),
+                ("v0", C.c_double), ("maturity", C.c_double), ("sine_coeff", C.c_double),
+                ("obs_perc", C.c_double), ("t0", C.c_double), ("seed", C.c_uint64)]
+
+
+ACT_CODES = {"tanh": 1, "relu": 2}
+LOSS_CODES = {"standard": 0, "easy": 1}
+
+
+class NjodeError(RuntimeError):
+    pass
+
+
+class Lib:
+    """one loaded build of the njode_b200 C ABI"""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise NjodeError(
+                "njode_b200: native library %s not found -- build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)" % path)
+        self.path = path
+        self.dll = C.CDLL(path)
+        d = self.dll
+        d.njode_last_error.restype = C.c_char_p
+        d.njode_abi_version.restype = C.c_int
+        d.njode_plan.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT), C.c_int, C.POINTER(PlanT)]
+        d.njode_forward.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT), C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SavedT),
+                                    C.c_void_p, C.c_void_p]
+        d.njode_backward.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT), C.c_void_p,
+                                     C.POINTER(SavedT), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+        for f in (d.njode_plan, d.njode_forward, d.njode_backward):
+            f.restype = C.c_int
+        if d.njode_abi_version() != 1:
+            raise NjodeError("njode_b200: ABI version mismatch in %s" % path)
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise NjodeError("%s failed (%d): %s" % (what, rc, self.dll.njode_last_error().decode()))
+
+
+_cuda_lib = None
+
+
+def cuda_lib():
+    global _cuda_lib
+    if _cuda_lib is None:
+        _cuda_lib = Lib(CUDA_LIB_PATH)
+    return _cuda_lib
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class PreparedBatch:
+    """device-resident inputs of one forward call + the ctypes batch structs (fwd / bwd)."""
+    __slots__ = ("sched", "B", "N", "dev", "keep", "fwd", "bwd_loss", "bwd_all", "n_units",
+                 "n_loss_units", "h2d_bytes", "get_loss", "return_path", "runner")
+
+
+class Runner:
+    """stages one batch on `device`, launches forward / backward through `lib`."""
+
+    def __init__(self, lib, device):
+        self.lib = lib
+        self.device = torch.device(device)
+        self.is_cuda = self.device.type == "cuda"
+        self._ws = None
+        self._pin = None
+        self._pin_event = None
+
+    # -- buffers ----------------------------------------------------------------------------
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _staging(self, nbytes):
+        if self._pin_event is not None:
+            self._pin_event.synchronize()       # previous async copy out of the pinned block is done
+        if self._pin is None or self._pin.numel() < nbytes:
+            cap = int(nbytes * 1.5) + 4096
+            self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=self.is_cuda)
+        # a fresh device block per batch: the autograd graph may keep several batches alive
+        return self._pin, torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.is_cuda else None
+
+    # -- batch staging ----------------------------------------------------------------------
+    def prepare(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, M, until_T,
+                return_path, segments, d, batch_size_norm=None, path_id_offset=0):
+        sched = _sched.build_schedule(times, delta_t, T, until_T, return_path)
+        B = int(start_X.shape[0])
+        oi = obs_idx.detach().cpu().numpy() if torch.is_tensor(obs_idx) else np.asarray(obs_idx)
+        path_ptr, path_rows, row_jump = _sched.build_csr(time_ptr, oi, B)
+        N = len(path_rows)
+        units, n_loss = _sched.build_units(sched, path_ptr, path_rows, row_jump, B, segments)
+
+        def host_f32(t, shape):
+            if t is None:
+                return None
+            if torch.is_tensor(t):
+                if t.device.type != "cpu":
+                    return t.detach().to(self.device, torch.float32).contiguous().reshape(shape)
+                return np.ascontiguousarray(t.detach().numpy().astype(np.float32, copy=False)).reshape(shape)
+            return np.ascontiguousarray(np.asarray(t, dtype=np.float32)).reshape(shape)
+
+        arrays = {"X": host_f32(X, (N, d)), "M": host_f32(M, (N, d)),
+                  "start_X": host_f32(start_X, (B, d)), "n_obs_ot": host_f32(n_obs_ot, (B,)),
+                  "path_ptr": path_ptr, "path_rows": path_rows, "row_jump": row_jump,
+                  "step_dt": sched.step_dt, "step_t": sched.step_t, "jump_step": sched.jump_step,
+                  "jump_tau": sched.jump_tau, "step_event": sched.step_event,
+                  "jump_event": sched.jump_event, "unit_desc": units.reshape(-1)}
+        # one pinned staging block, one host->device copy
+        offs, total = {}, 0
+        for k, a in arrays.items():
+            if a is None or torch.is_tensor(a):
+                continue
+            offs[k] = total
+            total += (a.nbytes + 15) & ~15
+        pin, dev = self._staging(max(total, 16))
+        pin_np = pin.numpy()
+        for k, o in offs.items():
+            a = arrays[k]
+            pin_np[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+        dev.copy_(pin[:dev.numel()], non_blocking=True)
+        if self.is_cuda:
+            self._pin_event = torch.cuda.Event()
+            self._pin_event.record(torch.cuda.current_stream(self.device))
+        base = dev.data_ptr()
+        keep = [dev]
+
+        def p(k):
+            a = arrays[k]
+            if a is None:
+                return None
+            if torch.is_tensor(a):
+                keep.append(a)
+                return C.c_void_p(a.data_ptr())
+            return C.c_void_p(base + offs[k])
+
+        def make(n_units):
+            return BatchT(B=B, N=N, K=sched.K, S=sched.S, E=sched.E,
+                          batch_size_norm=int(batch_size_norm or B), path_id_offset=int(path_id_offset),
+                          n_units=int(n_units), X=p("X"), M=p("M"), start_X=p("start_X"),
+                          n_obs_ot=p("n_obs_ot"), path_ptr=p("path_ptr"), path_rows=p("path_rows"),
+                          row_jump=p("row_jump"), step_dt=p("step_dt"), step_t=p("step_t"),
+                          jump_step=p("jump_step"), jump_tau=p("jump_tau"), step_event=p("step_event"),
+                          jump_event=p("jump_event"), unit_desc=p("unit_desc"))
+
+        pb = PreparedBatch()
+        pb.sched, pb.B, pb.N, pb.dev, pb.keep = sched, B, N, self.device, keep
+        pb.n_units, pb.n_loss_units = len(units), n_loss
+        pb.fwd = make(len(units))
+        pb.bwd_loss = make(n_loss)       # backward without a gradient into hT: tails contribute nothing
+        pb.bwd_all = pb.fwd
+        pb.h2d_bytes = total
+        return pb
+
+    # -- launches ---------------------------------------------------------------------------
+    def plan(self, model_t, batch_t):
+        pl = PlanT()
+        dev = self.device.index if self.is_cuda and self.device.index is not None else 0
+        self.lib.check(self.lib.dll.njode_plan(C.byref(model_t), C.byref(batch_t), dev, C.byref(pl)), "njode_plan")
+        return pl
+
+    def forward(self, model_t, pb, params, H, dout, get_loss, need_grad):
+        f32 = dict(dtype=torch.float32, device=self.device)
+        pl = self.plan(model_t, pb.fwd)
+        ws = self._workspace(pl.workspace_bytes)
+        hT = torch.empty(pb.B, H, **f32)
+        loss = torch.zeros((), **f32) if get_loss else None
+        E = pb.sched.E
+        path_h = torch.empty(E, pb.B, H, **f32) if E else None
+        path_y = torch.empty(E, pb.B, dout, **f32) if E else None
+        saved_t, saved = SavedT(), None
+        if need_grad:
+            saved = (torch.empty(max(pb.sched.S, 1) * pb.B * H, **f32),
+                     torch.empty(max(pb.N, 1) * H, **f32), torch.empty(max(pb.N, 1) * dout, **f32))
+            saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved])
+        rc = self.lib.dll.njode_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT),
+                                        _ptr(loss), _ptr(path_h), _ptr(path_y), C.byref(saved_t),
+                                        _ptr(ws), self._stream())
+        self.lib.check(rc, "njode_forward")
+        return hT, loss, path_h, path_y, saved
+
+    def backward(self, model_t, pb, params, saved, grad_loss, grad_hT):
+        pl = self.plan(model_t, pb.fwd)
+        ws = self._workspace(pl.workspace_bytes)
+        grads = torch.empty_like(params)
+        saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved])
+        bt = pb.bwd_all if grad_hT is not None else pb.bwd_loss
+        rc = self.lib.dll.njode_backward(C.byref(model_t), C.byref(bt), _ptr(params), C.byref(saved_t),
+                                         _ptr(grad_loss), _ptr(grad_hT), _ptr(grads), _ptr(ws),
+                                         self._stream())
+        self.lib.check(rc, "njode_backward")
+        return grads
+
+
+_runners = {}
+
+
+def cuda_runner(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise NjodeError("njode_b200 runs on CUDA devices only; model parameters are on %s "
+                         "(call model.to('cuda')) -- there is no CPU fallback" % device)
+    if not torch.cuda.is_available():
+        raise NjodeError("njode_b200: no CUDA device available")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    r = _runners.get(idx)
+    if r is None:
+        r = _runners[idx] = Runner(cuda_lib(), torch.device("cuda", idx))
+    return r

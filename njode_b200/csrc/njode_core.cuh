@@ -1,0 +1,1061 @@
+// njode_core.cuh -- CTA-level NJ-ODE forward / backward for sm_100a (generic fp32 path).
+//
+// One CTA marches a tile of P work units (paths, or (path, inter-observation segment) pairs) in
+// lockstep through the batch-global Euler schedule.  All state lives in shared memory as row-major
+// [unit][feature] matrices; every Linear layer is a register-tiled shared-memory GEMM over the tile
+// (4x4 micro-tiles, float4 loads along the reduction dimension), the parameter image stays
+// resident in shared memory for the whole launch when it fits, and parameter gradients accumulate
+// in a thread-owned shared-memory image that is flushed once per CTA.
+//
+// Semantics restated from the reference (paths relative to /root/reference):
+//   NJODE.forward            NJODE/models.py:379-518      ode_step     NJODE/models.py:369-377
+//   ODEFunc.forward          NJODE/models.py:188-199      FFNN.forward NJODE/models.py:261-276
+//   compute_loss(_2)         NJODE/models.py:71-126       get_ffnn     NJODE/models.py:140-166
+//
+// The file is written as barrier-separated phases (NJ_THREADS ... NJ_SYNC) with all cross-thread
+// state in "shared" arrays, so that the identical source also compiles as a sequential host
+// simulation (-DNJODE_HOST_SIM, tests only; the product never loads that build).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+#include "../../include/njode_b200.h"
+
+#if defined(NJODE_HOST_SIM)
+#define NJ_HD inline
+#define NJ_HDN inline
+#define NJ_THREADS(tid, nt) for (int tid = 0; tid < (nt); ++tid)
+#define NJ_SYNC() ((void)0)
+#define NJ_LDG(p) (*(p))
+struct nj_f4 { float x, y, z, w; };
+static inline nj_f4 nj_ld4(const float* p) { nj_f4 v; memcpy(&v, p, 16); return v; }
+static inline void nj_st4(float* p, const nj_f4& v) { memcpy(p, &v, 16); }
+#else
+#define NJ_HD __device__ __forceinline__
+#define NJ_HDN __device__ __noinline__
+#define NJ_THREADS(tid, nt) for (int tid = threadIdx.x, _nj_e = threadIdx.x + 1; tid < _nj_e; ++tid)
+#define NJ_SYNC() __syncthreads()
+#define NJ_LDG(p) __ldg(p)
+typedef float4 nj_f4;
+__device__ __forceinline__ nj_f4 nj_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void nj_st4(float* p, const nj_f4& v) { *reinterpret_cast<float4*>(p) = v; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// static configuration of one launch (passed to the kernels by value)
+// ------------------------------------------------------------------------------------------------
+struct NjNet {
+    int n;                              // Linear layers
+    int dim[NJODE_MAX_LINEAR + 1];
+    int act[NJODE_MAX_LINEAR];
+    int ks[NJODE_MAX_LINEAR];           // padded row stride of W_l inside the image
+    int og[NJODE_MAX_LINEAR];           // ceil(out/4): the image holds 4*og rows (zero padded)
+    int w_img[NJODE_MAX_LINEAR];        // float offsets inside the image
+    int b_img[NJODE_MAX_LINEAR];
+    long long w_src[NJODE_MAX_LINEAR];  // float offsets inside the flat parameter buffer
+    long long b_src[NJODE_MAX_LINEAR];  // -1: no bias
+};
+
+struct NjCfg {
+    NjNet net[3];
+    int d, H, dout, inf, enc_in;
+    int masked, curt, loss_kind, residual, training, has_drop;
+    float w, keep_scale, one_minus_p;
+    unsigned thr, seed_lo, seed_hi;
+    int P, nt;
+    int img_floats;
+    int w_smem, dw_smem;
+    // strides (floats) of the shared-memory matrices
+    int sIN, sACT, nACT, sOUT, sH, sD, sDO, sG;
+    // offsets (floats) into dynamic shared memory
+    int o_img, o_dimg, o_IN, o_ACT, o_OUT, o_H, o_LX, o_XI, o_YBJ, o_YY, o_XH, o_EE;
+    int o_GOUT, o_GTMP, o_GA, o_GB, o_GH, o_GX, o_GYBJ, o_F, o_I;
+    int smem_floats_fwd, smem_floats_bwd;
+};
+
+// per-unit float scalars (row-major [slot][P]) and int scalars
+enum { NJ_F_TAU = 0, NJ_F_DT, NJ_F_T, NJ_F_CA, NJ_F_CB, NJ_F_COUNT };
+enum { NJ_I_PATH = 0, NJ_I_S0, NJ_I_LEN, NJ_I_CUR, NJ_I_C0, NJ_I_C1, NJ_I_START, NJ_I_FLAG, NJ_I_RK,
+       NJ_I_JMAP, NJ_I_JROW, NJ_I_JJMP, NJ_I_PEND, NJ_I_COUNT };
+enum { NJ_CTL_NJ = 0, NJ_CTL_MAXLEN, NJ_CTL_COUNT = 4 };
+
+static inline int nj_stride_host(int n) {
+    int s = (n + 3) & ~3;
+    if (s == 0) s = 4;
+    if ((s & 7) == 0) s += 4;      // stride == 4 (mod 8): float4 row accesses of 8 consecutive rows
+    return s;                       // hit 8 distinct 16-byte bank groups
+}
+
+// ------------------------------------------------------------------------------------------------
+// dropout: counter-based keep-mask (murmur3 finaliser chain); restated in oracle/njode_oracle.py
+// ------------------------------------------------------------------------------------------------
+NJ_HD unsigned nj_fmix32(unsigned h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+NJ_HD unsigned nj_row_key(unsigned seed_lo, unsigned seed_hi, unsigned path, unsigned event) {
+    return nj_fmix32(nj_fmix32(path ^ seed_lo) + event * 0x9E3779B9u) ^ seed_hi;
+}
+NJ_HD unsigned nj_layer_key(unsigned row_key, unsigned tag) { return nj_fmix32(row_key + tag * 0x85EBCA77u); }
+NJ_HD bool nj_keep(unsigned layer_key, unsigned neuron, unsigned thr) {
+    return nj_fmix32(layer_key + neuron * 0xC2B2AE3Du) >= thr;
+}
+#define NJ_EVENT_JUMP_BASE 0x40000000u
+#define NJ_EVENT_PATH_RO_BASE 0x20000000u
+#define NJ_EVENT_INIT 0x7FFFFFFFu
+
+NJ_HD float nj_act(float v, int act) {
+    if (act == NJODE_ACT_TANH) return tanhf(v);
+    if (act == NJODE_ACT_RELU) return v > 0.f ? v : 0.f;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile GEMMs.  All matrices row-major, rows 16-byte aligned, padding columns/rows zero (weights) or
+// finite (activations; they only ever meet zero weights).
+// ------------------------------------------------------------------------------------------------
+struct NjLin {
+    const float* in; int in_s;      // [nrows][in_s]
+    int K4;                         // float4 chunks along the reduction dimension
+    const float* W; int w_s;        // image rows [4*OG][w_s]
+    const float* bias;              // [4*OG] or nullptr
+    int O, OG;
+    float* out; int out_s;
+    int nrows;
+    int act;                        // activation applied in the epilogue (NONE for the last layer)
+    int drop; unsigned thr; float keep_scale; const int* rk; unsigned tag;
+};
+
+// out[r][o] = act(bias[o] + sum_k in[r][k] W[o][k]) (* dropout)
+template <int MR>
+NJ_HD void nj_tile_fwd(const NjLin& L, int tid, int nt) {
+    const int RG = (L.nrows + MR - 1) / MR;
+    const int ntiles = RG * L.OG;
+    for (int tile = tid; tile < ntiles; tile += nt) {
+        const int rg = tile % RG, og = tile / RG;
+        float acc[MR][4];
+        const float* ap[MR];
+        const float* wp[4];
+#pragma unroll
+        for (int i = 0; i < MR; ++i) {
+            int r = rg + RG * i; if (r >= L.nrows) r = L.nrows - 1;
+            ap[i] = L.in + (size_t)r * L.in_s;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wp[j] = L.W + (size_t)(og + L.OG * j) * L.w_s;
+        for (int k4 = 0; k4 < L.K4; ++k4) {
+            nj_f4 a[MR], w[4];
+#pragma unroll
+            for (int i = 0; i < MR; ++i) a[i] = nj_ld4(ap[i] + 4 * k4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = nj_ld4(wp[j] + 4 * k4);
+#pragma unroll
+            for (int i = 0; i < MR; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < MR; ++i) {
+            const int r = rg + RG * i;
+            if (r >= L.nrows) continue;
+            unsigned lk = 0;
+            if (L.drop) lk = nj_layer_key((unsigned)L.rk[r], L.tag);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = og + L.OG * j;
+                if (o >= L.O) continue;
+                float v = acc[i][j] + (L.bias ? L.bias[o] : 0.f);
+                v = nj_act(v, L.act);
+                if (L.drop) v = nj_keep(lk, (unsigned)o, L.thr) ? v * L.keep_scale : 0.f;
+                L.out[(size_t)r * L.out_s + o] = v;
+            }
+        }
+    }
+}
+
+struct NjDx {
+    const float* g; int g_s;        // gradient wrt the layer's pre-activation output [nrows][g_s]
+    int O4;                         // float4 chunks along out (= OG of the layer)
+    const float* W; int w_s;
+    int Kin;                        // true input width
+    float* gin; int gin_s;
+    int nrows;
+    const float* aprev; int a_s; int act_prev;    // activations feeding this layer (nullptr: network input)
+    int drop; unsigned thr; float keep_scale, one_minus_p; const int* rk; unsigned tag_prev;
+};
+
+// gin[r][k] = (sum_o g[r][o] W[o][k]) * act'(aprev[r][k]) * dropout factor
+template <int MR>
+NJ_HD void nj_tile_dx(const NjDx& L, int tid, int nt) {
+    const int RG = (L.nrows + MR - 1) / MR;
+    const int KG = (L.Kin + 3) >> 2;
+    const int ntiles = RG * KG;
+    for (int tile = tid; tile < ntiles; tile += nt) {
+        const int rg = tile % RG, kg = tile / RG;
+        float acc[MR][4];
+        const float* gp[MR];
+#pragma unroll
+        for (int i = 0; i < MR; ++i) {
+            int r = rg + RG * i; if (r >= L.nrows) r = L.nrows - 1;
+            gp[i] = L.g + (size_t)r * L.g_s;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        }
+        const float* wp = L.W + 4 * kg;
+        for (int o4 = 0; o4 < L.O4; ++o4) {
+            nj_f4 g[MR], w[4];
+#pragma unroll
+            for (int i = 0; i < MR; ++i) g[i] = nj_ld4(gp[i] + 4 * o4);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) w[jj] = nj_ld4(wp + (size_t)(4 * o4 + jj) * L.w_s);
+#pragma unroll
+            for (int i = 0; i < MR; ++i) {
+                acc[i][0] = fmaf(g[i].x, w[0].x, fmaf(g[i].y, w[1].x, fmaf(g[i].z, w[2].x, fmaf(g[i].w, w[3].x, acc[i][0]))));
+                acc[i][1] = fmaf(g[i].x, w[0].y, fmaf(g[i].y, w[1].y, fmaf(g[i].z, w[2].y, fmaf(g[i].w, w[3].y, acc[i][1]))));
+                acc[i][2] = fmaf(g[i].x, w[0].z, fmaf(g[i].y, w[1].z, fmaf(g[i].z, w[2].z, fmaf(g[i].w, w[3].z, acc[i][2]))));
+                acc[i][3] = fmaf(g[i].x, w[0].w, fmaf(g[i].y, w[1].w, fmaf(g[i].z, w[2].w, fmaf(g[i].w, w[3].w, acc[i][3]))));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MR; ++i) {
+            const int r = rg + RG * i;
+            if (r >= L.nrows) continue;
+            unsigned lk = 0;
+            if (L.drop && L.aprev) lk = nj_layer_key((unsigned)L.rk[r], L.tag_prev);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * kg + j;
+                if (k >= L.Kin) continue;
+                float v = acc[i][j];
+                if (L.aprev) {
+                    float a = L.aprev[(size_t)r * L.a_s + k];
+                    if (L.drop) {
+                        if (nj_keep(lk, (unsigned)k, L.thr)) { a *= L.one_minus_p; v *= L.keep_scale; }
+                        else { v = 0.f; a = 0.f; }
+                    }
+                    if (L.act_prev == NJODE_ACT_TANH) v *= (1.f - a * a);
+                    else if (L.act_prev == NJODE_ACT_RELU) v = a > 0.f ? v : 0.f;
+                }
+                L.gin[(size_t)r * L.gin_s + k] = v;
+            }
+        }
+    }
+}
+
+// dW[o][k] += sum_r g[r][o] a[r][k] ; db[o] += sum_r g[r][o]   (thread-owned 4x4 blocks of the image)
+NJ_HD void nj_tile_dw(const float* g, int g_s, int OG, const float* a, int a_s, int K4, int nrows,
+                      float* dW, int w_s, float* db, int tid, int nt) {
+    const int ntiles = OG * K4;
+    for (int tile = tid; tile < ntiles; tile += nt) {
+        const int kg = tile % K4, og = tile / K4;
+        float acc[4][4];
+        float bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        const float* gp = g + 4 * og;
+        const float* apx = a + 4 * kg;
+        for (int r = 0; r < nrows; ++r) {
+            const nj_f4 gv = nj_ld4(gp + (size_t)r * g_s);
+            const nj_f4 av = nj_ld4(apx + (size_t)r * a_s);
+            acc[0][0] = fmaf(gv.x, av.x, acc[0][0]); acc[0][1] = fmaf(gv.x, av.y, acc[0][1]);
+            acc[0][2] = fmaf(gv.x, av.z, acc[0][2]); acc[0][3] = fmaf(gv.x, av.w, acc[0][3]);
+            acc[1][0] = fmaf(gv.y, av.x, acc[1][0]); acc[1][1] = fmaf(gv.y, av.y, acc[1][1]);
+            acc[1][2] = fmaf(gv.y, av.z, acc[1][2]); acc[1][3] = fmaf(gv.y, av.w, acc[1][3]);
+            acc[2][0] = fmaf(gv.z, av.x, acc[2][0]); acc[2][1] = fmaf(gv.z, av.y, acc[2][1]);
+            acc[2][2] = fmaf(gv.z, av.z, acc[2][2]); acc[2][3] = fmaf(gv.z, av.w, acc[2][3]);
+            acc[3][0] = fmaf(gv.w, av.x, acc[3][0]); acc[3][1] = fmaf(gv.w, av.y, acc[3][1]);
+            acc[3][2] = fmaf(gv.w, av.z, acc[3][2]); acc[3][3] = fmaf(gv.w, av.w, acc[3][3]);
+            if (kg == 0) { bs[0] += gv.x; bs[1] += gv.y; bs[2] += gv.z; bs[3] += gv.w; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float* p = dW + (size_t)(4 * og + i) * w_s + 4 * kg;
+            nj_f4 v = nj_ld4(p);
+            v.x += acc[i][0]; v.y += acc[i][1]; v.z += acc[i][2]; v.w += acc[i][3];
+            nj_st4(p, v);
+        }
+        if (kg == 0 && db) {
+            nj_f4 v = nj_ld4(db + 4 * og);
+            v.x += bs[0]; v.y += bs[1]; v.z += bs[2]; v.w += bs[3];
+            nj_st4(db + 4 * og, v);
+        }
+    }
+}
+
+NJ_HD int nj_pick_mr(int nrows, int groups, int nt) {
+    if (((nrows + 3) >> 2) * groups >= (nt >> 1)) return 4;
+    if (((nrows + 1) >> 1) * groups >= (nt >> 1)) return 2;
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the CTA context: pointers into shared memory + launch arguments
+// ------------------------------------------------------------------------------------------------
+struct NjArgs {
+    njode_batch_t b;
+    const float* image;        // padded parameter image in global memory
+    float* hT; float* row_loss; float* path_h; float* path_y;
+    float* h_hist; float* h_before; float* y_after;      // forward: written; backward: read
+    const float* grad_loss; const float* grad_hT;
+    float* partials;           // [grid][img_floats] gradient partial images (backward)
+    int n_tiles;
+    int get_loss;
+};
+
+struct NjCta {
+    const NjCfg* c;
+    const float* wimg;         // parameter image (shared or global)
+    float* dimg;               // gradient image (shared or this CTA's global partial)
+    float *IN, *ACT, *OUT, *Hs, *LX, *XI, *YBJ, *YY, *XH, *EE, *GOUT, *GTMP, *GA, *GB, *GH, *GX, *GYBJ, *F;
+    int *I, *CTL;
+    int tid0, nt;              // nt: threads; (tid comes from NJ_THREADS)
+};
+
+NJ_HD void nj_cta_bind(NjCta& t, const NjCfg& c, float* smem, bool bwd) {
+    t.c = &c; t.nt = c.nt;
+    t.IN = smem + c.o_IN; t.ACT = smem + c.o_ACT; t.OUT = smem + c.o_OUT; t.Hs = smem + c.o_H;
+    t.LX = smem + c.o_LX; t.XI = smem + c.o_XI; t.YBJ = smem + c.o_YBJ; t.YY = smem + c.o_YY;
+    t.XH = smem + c.o_XH; t.EE = smem + c.o_EE; t.F = smem + c.o_F;
+    t.I = reinterpret_cast<int*>(smem + c.o_I); t.CTL = t.I + NJ_I_COUNT * c.P;
+    t.GOUT = t.GTMP = t.GA = t.GB = t.GH = t.GX = t.GYBJ = nullptr;
+    if (bwd) {
+        t.GOUT = smem + c.o_GOUT; t.GTMP = smem + c.o_GTMP; t.GA = smem + c.o_GA; t.GB = smem + c.o_GB;
+        t.GH = smem + c.o_GH; t.GX = smem + c.o_GX; t.GYBJ = smem + c.o_GYBJ;
+    }
+}
+
+#define NJ_IU(t, slot, u) ((t).I[(slot) * (t).c->P + (u)])
+#define NJ_FU(t, slot, u) ((t).F[(slot) * (t).c->P + (u)])
+
+// residual connections of FFNN.forward (NJODE/models.py:268-276)
+NJ_HD float nj_resid(const float* x, int in_sz, int out_sz, int c) {
+    if (in_sz <= out_sz) return x[c % in_sz];
+    const int mult = in_sz / out_sz;
+    float s = 0.f;
+    for (int k = 0; k < mult; ++k) s += x[k * out_sz + c];
+    return s / (float)mult;
+}
+// d(residual)/d x[cp] contracted with g (width out_sz)
+NJ_HD float nj_resid_bwd(const float* g, int in_sz, int out_sz, int cp) {
+    if (in_sz <= out_sz) {
+        float s = 0.f;
+        for (int k = 0; k < out_sz / in_sz; ++k) s += g[k * in_sz + cp];
+        return s;
+    }
+    return g[cp % out_sz] / (float)(in_sz / out_sz);
+}
+
+// MLP forward over rows [0, nrows) of IN -> OUT (raw output of the last Linear); hidden activations
+// are kept in ACT[l].  skip_last: backward-side recompute that only needs the hidden activations.
+NJ_HDN void nj_mlp_forward(NjCta& t, int netid, int nrows, bool skip_last) {
+    const NjCfg& c = *t.c;
+    const NjNet& N = c.net[netid];
+    const float* in = t.IN; int in_s = c.sIN;
+    for (int l = 0; l < N.n; ++l) {
+        const bool last = (l == N.n - 1);
+        if (last && skip_last) break;
+        NjLin L;
+        L.in = in; L.in_s = in_s; L.K4 = (N.dim[l] + 3) >> 2;
+        L.W = t.wimg + N.w_img[l]; L.w_s = N.ks[l];
+        L.bias = N.b_src[l] >= 0 ? t.wimg + N.b_img[l] : nullptr;
+        L.O = N.dim[l + 1]; L.OG = N.og[l];
+        L.out = last ? t.OUT : t.ACT + (size_t)l * c.P * c.sACT; L.out_s = last ? c.sOUT : c.sACT;
+        L.nrows = nrows; L.act = last ? NJODE_ACT_NONE : N.act[l];
+        L.drop = (!last) && c.has_drop; L.thr = c.thr; L.keep_scale = c.keep_scale;
+        L.rk = t.I + NJ_I_RK * c.P; L.tag = (unsigned)(netid * 16 + l + 1);
+        const int mr = nj_pick_mr(nrows, L.OG, t.nt);
+        NJ_THREADS(tid, t.nt) {
+            if (mr == 4) nj_tile_fwd<4>(L, tid, t.nt);
+            else if (mr == 2) nj_tile_fwd<2>(L, tid, t.nt);
+            else nj_tile_fwd<1>(L, tid, t.nt);
+        }
+        NJ_SYNC();
+        in = L.out; in_s = L.out_s;
+    }
+}
+
+// MLP backward: gradient wrt the raw output in GOUT (width = out dim); accumulates dW/db into the
+// gradient image; returns the buffer holding the gradient wrt the network input (already multiplied
+// by nothing: the caller applies the derivative of its own input transform), or nullptr.
+NJ_HDN float* nj_mlp_backward(NjCta& t, int netid, int nrows, bool need_in_grad) {
+    const NjCfg& c = *t.c;
+    const NjNet& N = c.net[netid];
+    const float* g = t.GOUT; int g_s = c.sOUT;
+    float* nxt = t.GA;
+    float* res = nullptr;
+    for (int l = N.n - 1; l >= 0; --l) {
+        const float* inp = l > 0 ? t.ACT + (size_t)(l - 1) * c.P * c.sACT : t.IN;
+        const int inp_s = l > 0 ? c.sACT : c.sIN;
+        const bool dx = (l > 0) || need_in_grad;
+        NjDx D;
+        D.g = g; D.g_s = g_s; D.O4 = N.og[l]; D.W = t.wimg + N.w_img[l]; D.w_s = N.ks[l];
+        D.Kin = N.dim[l]; D.gin = nxt; D.gin_s = c.sG; D.nrows = nrows;
+        D.aprev = l > 0 ? inp : nullptr; D.a_s = inp_s; D.act_prev = l > 0 ? N.act[l - 1] : NJODE_ACT_NONE;
+        D.drop = c.has_drop; D.thr = c.thr; D.keep_scale = c.keep_scale; D.one_minus_p = c.one_minus_p;
+        D.rk = t.I + NJ_I_RK * c.P; D.tag_prev = (unsigned)(netid * 16 + l);
+        const int mr = nj_pick_mr(nrows, (N.dim[l] + 3) >> 2, t.nt);
+        float* dW = t.dimg + N.w_img[l];
+        float* db = N.b_src[l] >= 0 ? t.dimg + N.b_img[l] : nullptr;
+        NJ_THREADS(tid, t.nt) {
+            nj_tile_dw(g, g_s, N.og[l], inp, inp_s, (N.dim[l] + 3) >> 2, nrows, dW, N.ks[l], db, tid, t.nt);
+            if (dx) {
+                if (mr == 4) nj_tile_dx<4>(D, tid, t.nt);
+                else if (mr == 2) nj_tile_dx<2>(D, tid, t.nt);
+                else nj_tile_dx<1>(D, tid, t.nt);
+            }
+        }
+        NJ_SYNC();
+        if (dx) { res = nxt; g = nxt; g_s = c.sG; nxt = (nxt == t.GA) ? t.GB : t.GA; }
+    }
+    return need_in_grad ? res : nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared helpers of forward and backward
+// ------------------------------------------------------------------------------------------------
+NJ_HDN void nj_load_units(NjCta& t, const NjArgs& a, int tile, bool reverse) {
+    const NjCfg& c = *t.c;
+    const int u0 = tile * c.P;
+    NJ_THREADS(tid, t.nt) {
+        if (tid < c.P) {
+            const int u = u0 + tid;
+            if (u < a.b.n_units) {
+                const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                NJ_IU(t, NJ_I_PATH, tid) = dsc[0]; NJ_IU(t, NJ_I_S0, tid) = dsc[1];
+                NJ_IU(t, NJ_I_LEN, tid) = dsc[2] - dsc[1];
+                NJ_IU(t, NJ_I_C0, tid) = dsc[3]; NJ_IU(t, NJ_I_C1, tid) = dsc[4];
+                NJ_IU(t, NJ_I_CUR, tid) = reverse ? dsc[4] : dsc[3];
+                const int sc = dsc[5];      // (start_row + 1) | NJODE_UNIT_WRITES_HT
+                NJ_IU(t, NJ_I_FLAG, tid) = (sc & NJODE_UNIT_WRITES_HT) ? 1 : 0;
+                NJ_IU(t, NJ_I_START, tid) = (sc & ~NJODE_UNIT_WRITES_HT) - 1;
+            } else {
+                NJ_IU(t, NJ_I_PATH, tid) = -1; NJ_IU(t, NJ_I_S0, tid) = 0; NJ_IU(t, NJ_I_LEN, tid) = -1;
+                NJ_IU(t, NJ_I_C0, tid) = 0; NJ_IU(t, NJ_I_C1, tid) = 0; NJ_IU(t, NJ_I_CUR, tid) = 0;
+                NJ_IU(t, NJ_I_FLAG, tid) = 0; NJ_IU(t, NJ_I_START, tid) = -1;
+            }
+        }
+    }
+    NJ_SYNC();
+    NJ_THREADS(tid, t.nt) {
+        if (tid == 0) {
+            int m = 0;
+            for (int u = 0; u < c.P; ++u) m = NJ_IU(t, NJ_I_LEN, u) > m ? NJ_IU(t, NJ_I_LEN, u) : m;
+            t.CTL[NJ_CTL_MAXLEN] = m;
+        }
+    }
+    NJ_SYNC();
+}
+
+// (last_X, tau) valid after the jump of row `prev` (or at the path start when prev < 0)
+NJ_HD void nj_state_from_row(NjCta& t, const NjArgs& a, int u, int c_, int prev) {
+    const NjCfg& c = *t.c;
+    const int p = NJ_IU(t, NJ_I_PATH, u);
+    float v;
+    if (prev < 0) v = NJ_LDG(a.b.start_X + (size_t)p * c.d + c_);
+    else if (c.masked) v = a.y_after[(size_t)prev * c.dout + c_];
+    else v = NJ_LDG(a.b.X + (size_t)prev * c.d + c_);
+    t.LX[u * c.sD + c_] = v;
+    if (c_ == 0) NJ_FU(t, NJ_F_TAU, u) = prev < 0 ? 0.f : NJ_LDG(a.b.jump_tau + NJ_LDG(a.b.row_jump + prev));
+}
+
+// ODE network input row (ODEFunc.forward, NJODE/models.py:192-197) for unit u at Euler step k
+NJ_HD void nj_build_ode_input(NjCta& t, int u, int c_, float hval, float tcur) {
+    const NjCfg& c = *t.c;
+    float* row = t.IN + (size_t)u * c.sIN;
+    const float tau = NJ_FU(t, NJ_F_TAU, u);
+    if (c_ < c.d) row[c_] = tanhf(t.LX[u * c.sD + c_]);
+    else if (c_ < c.d + c.H) row[c_] = tanhf(hval);
+    else if (c_ == c.d + c.H) row[c_] = tau;
+    else if (c_ == c.d + c.H + 1) row[c_] = tcur - tau;
+    else row[c_] = tau + (tcur - tau);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+NJ_HDN void nj_record(NjCta& t, const NjArgs& a, int nu, int e, unsigned event_key) {
+    const NjCfg& c = *t.c;
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nu * c.H; idx += t.nt) {
+            const int u = idx / c.H, c_ = idx % c.H;
+            const int p = NJ_IU(t, NJ_I_PATH, u);
+            const float h = t.Hs[u * c.sH + c_];
+            t.IN[(size_t)u * c.sIN + c_] = tanhf(h);
+            a.path_h[((size_t)e * a.b.B + p) * c.H + c_] = h;
+            if (c_ == 0) NJ_IU(t, NJ_I_RK, u) = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), event_key);
+        }
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_RO, nu, false);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nu * c.dout; idx += t.nt) {
+            const int u = idx / c.dout, c_ = idx % c.dout;
+            const int p = NJ_IU(t, NJ_I_PATH, u);
+            float y = t.OUT[u * c.sOUT + c_];
+            if (c.residual) y += nj_resid(t.Hs + u * c.sH, c.H, c.dout, c_);
+            a.path_y[((size_t)e * a.b.B + p) * c.dout + c_] = y;
+        }
+    }
+    NJ_SYNC();
+}
+
+// find the units that jump now; compacts them into JMAP/JROW/JJMP, CTL[NJ]=count.
+//   j: lockstep iteration; only_jump >= 0: restrict to that observation-time index (return_path)
+NJ_HDN void nj_find_jumps(NjCta& t, const NjArgs& a, int j, int only_jump, bool reverse) {
+    const NjCfg& c = *t.c;
+    NJ_THREADS(tid, t.nt) {
+        if (tid < c.P) {
+            int pend = -1;
+            const int len = NJ_IU(t, NJ_I_LEN, tid);
+            if (len >= 0 && j <= len) {
+                const int cur = NJ_IU(t, NJ_I_CUR, tid);
+                const int idx = reverse ? cur - 1 : cur;
+                const bool has = reverse ? (idx >= NJ_IU(t, NJ_I_C0, tid)) : (idx < NJ_IU(t, NJ_I_C1, tid));
+                if (has) {
+                    const int r = NJ_LDG(a.b.path_rows + idx);
+                    const int i = NJ_LDG(a.b.row_jump + r);
+                    if (NJ_LDG(a.b.jump_step + i) == NJ_IU(t, NJ_I_S0, tid) + j && (only_jump < 0 || i == only_jump))
+                        pend = r;
+                }
+            }
+            NJ_IU(t, NJ_I_PEND, tid) = pend;
+        }
+    }
+    NJ_SYNC();
+    NJ_THREADS(tid, t.nt) {
+        if (tid == 0) {
+            int n = 0;
+            for (int u = 0; u < c.P; ++u) {
+                const int r = NJ_IU(t, NJ_I_PEND, u);
+                if (r >= 0) { NJ_IU(t, NJ_I_JMAP, n) = u; NJ_IU(t, NJ_I_JROW, n) = r; NJ_IU(t, NJ_I_JJMP, n) = NJ_LDG(a.b.row_jump + r); ++n; }
+            }
+            t.CTL[NJ_CTL_NJ] = n;
+        }
+    }
+    NJ_SYNC();
+}
+
+NJ_HD void nj_set_jump_keys(NjCta& t, const NjArgs& a, int nj, int which, int tid) {
+    const NjCfg& c = *t.c;
+    if (tid < nj) {
+        const int u = NJ_IU(t, NJ_I_JMAP, tid);
+        const unsigned ev = NJ_EVENT_JUMP_BASE + 3u * (unsigned)NJ_IU(t, NJ_I_JJMP, tid) + (unsigned)which;
+        NJ_IU(t, NJ_I_RK, tid) = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(NJ_IU(t, NJ_I_PATH, u) + a.b.path_id_offset), ev);
+    }
+}
+
+// the jump of NJODE/models.py:449-489 for the compacted rows [0, nj)
+NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
+    const NjCfg& c = *t.c;
+    // (a) readout input = tanh(h before the jump)
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+            const int jr = idx / c.H, c_ = idx % c.H;
+            const int u = NJ_IU(t, NJ_I_JMAP, jr);
+            const float h = t.Hs[u * c.sH + c_];
+            t.IN[(size_t)jr * c.sIN + c_] = tanhf(h);
+            t.XH[jr * c.sH + c_] = h;
+            if (a.h_before) a.h_before[(size_t)NJ_IU(t, NJ_I_JROW, jr) * c.H + c_] = h;
+        }
+        nj_set_jump_keys(t, a, nj, 0, tid);
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_RO, nj, false);
+    // (c) Y_bj, imputation, encoder input
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
+            const int jr = idx / c.dout, c_ = idx % c.dout;
+            float y = t.OUT[jr * c.sOUT + c_];
+            if (c.residual) y += nj_resid(t.XH + jr * c.sH, c.H, c.dout, c_);
+            t.YBJ[jr * c.sDO + c_] = y;
+        }
+    }
+    NJ_SYNC();
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.d; idx += t.nt) {
+            const int jr = idx / c.d, c_ = idx % c.d;
+            const int r = NJ_IU(t, NJ_I_JROW, jr);
+            float x = NJ_LDG(a.b.X + (size_t)r * c.d + c_);
+            if (c.masked) {
+                const float m = NJ_LDG(a.b.M + (size_t)r * c.d + c_);
+                x = x * m + (1.f - m) * t.YBJ[jr * c.sDO + c_];
+                t.IN[(size_t)jr * c.sIN + c.d + c_] = m;
+            }
+            t.XI[jr * c.sD + c_] = x;
+            t.IN[(size_t)jr * c.sIN + c_] = tanhf(x);
+        }
+        nj_set_jump_keys(t, a, nj, 1, tid);
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_ENC, nj, false);
+    // (e) new hidden state, readout input
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+            const int jr = idx / c.H, c_ = idx % c.H;
+            const int u = NJ_IU(t, NJ_I_JMAP, jr);
+            float e = t.OUT[jr * c.sOUT + c_];
+            if (c.residual) e += nj_resid(t.XI + jr * c.sD, c.d, c.H, c_);
+            t.Hs[u * c.sH + c_] = e;
+            t.IN[(size_t)jr * c.sIN + c_] = tanhf(e);
+        }
+        nj_set_jump_keys(t, a, nj, 2, tid);
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_RO, nj, false);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
+            const int jr = idx / c.dout, c_ = idx % c.dout;
+            const int u = NJ_IU(t, NJ_I_JMAP, jr);
+            float y = t.OUT[jr * c.sOUT + c_];
+            if (c.residual) y += nj_resid(t.Hs + u * c.sH, c.H, c.dout, c_);
+            t.YY[jr * c.sDO + c_] = y;
+            if (a.y_after) a.y_after[(size_t)NJ_IU(t, NJ_I_JROW, jr) * c.dout + c_] = y;
+        }
+    }
+    NJ_SYNC();
+    // (g) loss term of the row, last_X / tau update, cursor advance
+    NJ_THREADS(tid, t.nt) {
+        if (tid < nj) {
+            const int jr = tid, u = NJ_IU(t, NJ_I_JMAP, jr), r = NJ_IU(t, NJ_I_JROW, jr);
+            if (a.get_loss) {
+                float sa = 0.f, sb = 0.f;
+                for (int c_ = 0; c_ < c.dout; ++c_) {
+                    const float x = NJ_LDG(a.b.X + (size_t)r * c.d + c_);
+                    const float m = c.masked ? NJ_LDG(a.b.M + (size_t)r * c.d + c_) : 1.f;
+                    const float y = t.YY[jr * c.sDO + c_], yb = t.YBJ[jr * c.sDO + c_];
+                    const float da = x - y, db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y) : (yb - x);
+                    sa = fmaf(m * da, da, sa); sb = fmaf(m * db, db, sb);
+                }
+                const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+                const float s = (c.loss_kind == NJODE_LOSS_STANDARD) ? (2.f * c.w * ra + 2.f * (1.f - c.w) * rb)
+                                                                     : (c.w * ra + (1.f - c.w) * rb);
+                a.row_loss[r] = s * s / NJ_LDG(a.b.n_obs_ot + NJ_IU(t, NJ_I_PATH, u));
+            }
+            NJ_FU(t, NJ_F_TAU, u) = NJ_LDG(a.b.jump_tau + NJ_IU(t, NJ_I_JJMP, jr));
+            NJ_IU(t, NJ_I_CUR, u) += 1;
+        }
+        for (int idx = tid; idx < nj * c.d; idx += t.nt) {
+            const int jr = idx / c.d, c_ = idx % c.d;
+            const int u = NJ_IU(t, NJ_I_JMAP, jr);
+            t.LX[u * c.sD + c_] = c.masked ? t.YY[jr * c.sDO + c_] : NJ_LDG(a.b.X + (size_t)NJ_IU(t, NJ_I_JROW, jr) * c.d + c_);
+        }
+    }
+    NJ_SYNC();
+}
+
+NJ_HD void nj_zero(float* p, int n, int nt) {
+    NJ_THREADS(tid, nt) { for (int i = tid; i < n; i += nt) p[i] = 0.f; }
+}
+
+NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta, int ncta) {
+    NjCta t;
+    nj_cta_bind(t, c, smem, false);
+    if (c.w_smem) {
+        float* simg = smem + c.o_img;
+        NJ_THREADS(tid, t.nt) { for (int i = tid; i < c.img_floats / 4; i += t.nt) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
+        t.wimg = simg;
+    } else t.wimg = a.image;
+    t.dimg = nullptr;
+    nj_zero(smem + c.o_IN, c.o_I - c.o_IN, t.nt);
+    NJ_SYNC();
+    const bool rec = a.b.E > 0;
+    for (int tile = cta; tile < a.n_tiles; tile += ncta) {
+        nj_load_units(t, a, tile, false);
+        const int nu = (a.b.n_units - tile * c.P) < c.P ? (a.b.n_units - tile * c.P) : c.P;
+        const int maxlen = t.CTL[NJ_CTL_MAXLEN];
+        // ---- start: h = encoder(start value)  (NJODE/models.py:411-419) ----
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nu * c.d; idx += t.nt) {
+                const int u = idx / c.d, c_ = idx % c.d;
+                nj_state_from_row(t, a, u, c_, NJ_IU(t, NJ_I_START, u));
+                // the start value of a segment is the *observation* X[row] (non-masked only)
+                const int sr = NJ_IU(t, NJ_I_START, u);
+                const float x = sr < 0 ? NJ_LDG(a.b.start_X + (size_t)NJ_IU(t, NJ_I_PATH, u) * c.d + c_)
+                                       : NJ_LDG(a.b.X + (size_t)sr * c.d + c_);
+                t.XI[u * c.sD + c_] = x;
+                t.IN[(size_t)u * c.sIN + c_] = tanhf(x);
+                if (c.masked) t.IN[(size_t)u * c.sIN + c.d + c_] = 0.f;
+            }
+            if (tid < nu) {
+                const int sr = NJ_IU(t, NJ_I_START, tid);
+                const unsigned ev = sr < 0 ? NJ_EVENT_INIT : NJ_EVENT_JUMP_BASE + 3u * (unsigned)NJ_LDG(a.b.row_jump + sr) + 1u;
+                NJ_IU(t, NJ_I_RK, tid) = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(NJ_IU(t, NJ_I_PATH, tid) + a.b.path_id_offset), ev);
+            }
+        }
+        NJ_SYNC();
+        nj_mlp_forward(t, NJODE_NET_ENC, nu, false);
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nu * c.H; idx += t.nt) {
+                const int u = idx / c.H, c_ = idx % c.H;
+                float e = t.OUT[u * c.sOUT + c_];
+                if (c.residual) e += nj_resid(t.XI + u * c.sD, c.d, c.H, c_);
+                t.Hs[u * c.sH + c_] = e;
+            }
+        }
+        NJ_SYNC();
+        if (rec) nj_record(t, a, nu, 0, NJ_EVENT_INIT);
+        int gi = 0;    // global jump cursor (return_path: all units are whole paths with s0 = 0)
+        for (int j = 0; j <= maxlen; ++j) {
+            // ---- jumps that fall before Euler step s0 + j ----
+            for (;;) {
+                int only = -1;
+                if (rec) {
+                    if (!(gi < a.b.K && NJ_LDG(a.b.jump_step + gi) == j)) break;
+                    only = gi;
+                }
+                nj_find_jumps(t, a, j, only, false);
+                const int nj = t.CTL[NJ_CTL_NJ];
+                if (nj > 0) nj_jump_forward(t, a, nj);
+                if (rec) { nj_record(t, a, nu, NJ_LDG(a.b.jump_event + gi), NJ_EVENT_JUMP_BASE + 3u * (unsigned)gi + 2u); ++gi; }
+                else if (nj == 0) break;
+                NJ_SYNC();
+            }
+            if (j == maxlen) break;
+            // ---- Euler step k = s0 + j of every unit that still has one  (NJODE/models.py:369-377) ----
+            NJ_THREADS(tid, t.nt) {
+                for (int idx = tid; idx < nu * c.inf; idx += t.nt) {
+                    const int u = idx / c.inf, c_ = idx % c.inf;
+                    const bool active = j < NJ_IU(t, NJ_I_LEN, u);
+                    const int k = NJ_IU(t, NJ_I_S0, u) + j;
+                    float hval = 0.f;
+                    if (c_ >= c.d && c_ < c.d + c.H) {
+                        hval = t.Hs[u * c.sH + c_ - c.d];
+                        if (active && a.h_hist) a.h_hist[((size_t)k * a.b.B + NJ_IU(t, NJ_I_PATH, u)) * c.H + c_ - c.d] = hval;
+                    }
+                    nj_build_ode_input(t, u, c_, hval, active ? NJ_LDG(a.b.step_t + k) : 0.f);
+                    if (c_ == 0) {
+                        NJ_FU(t, NJ_F_DT, u) = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
+                        NJ_IU(t, NJ_I_RK, u) = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(NJ_IU(t, NJ_I_PATH, u) + a.b.path_id_offset), (unsigned)k);
+                    }
+                }
+            }
+            NJ_SYNC();
+            nj_mlp_forward(t, NJODE_NET_ODE, nu, false);
+            NJ_THREADS(tid, t.nt) {
+                for (int idx = tid; idx < nu * c.H; idx += t.nt) {
+                    const int u = idx / c.H, c_ = idx % c.H;
+                    if (j < NJ_IU(t, NJ_I_LEN, u))
+                        t.Hs[u * c.sH + c_] = fmaf(NJ_FU(t, NJ_F_DT, u), t.OUT[u * c.sOUT + c_], t.Hs[u * c.sH + c_]);
+                }
+            }
+            NJ_SYNC();
+            if (rec) nj_record(t, a, nu, NJ_LDG(a.b.step_event + j), NJ_EVENT_PATH_RO_BASE + (unsigned)j);
+        }
+        // ---- hT ----
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nu * c.H; idx += t.nt) {
+                const int u = idx / c.H, c_ = idx % c.H;
+                if (NJ_IU(t, NJ_I_FLAG, u)) a.hT[(size_t)NJ_IU(t, NJ_I_PATH, u) * c.H + c_] = t.Hs[u * c.sH + c_];
+            }
+        }
+        NJ_SYNC();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+NJ_HDN void nj_reload_state(NjCta& t, const NjArgs& a, int nu) {
+    const NjCfg& c = *t.c;
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nu * c.d; idx += t.nt) {
+            const int u = idx / c.d, c_ = idx % c.d;
+            const int cur = NJ_IU(t, NJ_I_CUR, u);
+            const int p = NJ_IU(t, NJ_I_PATH, u);
+            const int prev = (cur - 1 >= NJ_LDG(a.b.path_ptr + p)) ? NJ_LDG(a.b.path_rows + cur - 1) : -1;
+            nj_state_from_row(t, a, u, c_, prev);
+        }
+    }
+    NJ_SYNC();
+}
+
+NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
+    const NjCfg& c = *t.c;
+    const float gl = NJ_LDG(a.grad_loss);
+    // 1. readout at h_before -> Y_bj
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+            const int jr = idx / c.H, c_ = idx % c.H;
+            const float h = a.h_before[(size_t)NJ_IU(t, NJ_I_JROW, jr) * c.H + c_];
+            t.XH[jr * c.sH + c_] = h;
+            t.IN[(size_t)jr * c.sIN + c_] = tanhf(h);
+        }
+        nj_set_jump_keys(t, a, nj, 0, tid);
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_RO, nj, false);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
+            const int jr = idx / c.dout, c_ = idx % c.dout;
+            float y = t.OUT[jr * c.sOUT + c_];
+            if (c.residual) y += nj_resid(t.XH + jr * c.sH, c.H, c.dout, c_);
+            t.YBJ[jr * c.sDO + c_] = y;
+        }
+    }
+    NJ_SYNC();
+    // 2. encoder at the (imputed) observation -> E
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.d; idx += t.nt) {
+            const int jr = idx / c.d, c_ = idx % c.d;
+            const int r = NJ_IU(t, NJ_I_JROW, jr);
+            float x = NJ_LDG(a.b.X + (size_t)r * c.d + c_);
+            if (c.masked) {
+                const float m = NJ_LDG(a.b.M + (size_t)r * c.d + c_);
+                x = x * m + (1.f - m) * t.YBJ[jr * c.sDO + c_];
+                t.IN[(size_t)jr * c.sIN + c.d + c_] = m;
+            }
+            t.XI[jr * c.sD + c_] = x;
+            t.IN[(size_t)jr * c.sIN + c_] = tanhf(x);
+        }
+        nj_set_jump_keys(t, a, nj, 1, tid);
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_ENC, nj, false);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+            const int jr = idx / c.H, c_ = idx % c.H;
+            float e = t.OUT[jr * c.sOUT + c_];
+            if (c.residual) e += nj_resid(t.XI + jr * c.sD, c.d, c.H, c_);
+            t.EE[jr * c.sH + c_] = e;
+            t.IN[(size_t)jr * c.sIN + c_] = tanhf(e);
+        }
+        nj_set_jump_keys(t, a, nj, 2, tid);
+    }
+    NJ_SYNC();
+    // 3. readout at E -> Y (activations kept for its backward)
+    nj_mlp_forward(t, NJODE_NET_RO, nj, false);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
+            const int jr = idx / c.dout, c_ = idx % c.dout;
+            float y = t.OUT[jr * c.sOUT + c_];
+            if (c.residual) y += nj_resid(t.EE + jr * c.sH, c.H, c.dout, c_);
+            t.YY[jr * c.sDO + c_] = y;
+        }
+    }
+    NJ_SYNC();
+    // loss derivative coefficients per row (compute_loss / compute_loss_2, NJODE/models.py:71-126)
+    NJ_THREADS(tid, t.nt) {
+        if (tid < nj) {
+            const int jr = tid, u = NJ_IU(t, NJ_I_JMAP, jr), r = NJ_IU(t, NJ_I_JROW, jr);
+            float sa = 0.f, sb = 0.f;
+            for (int c_ = 0; c_ < c.dout; ++c_) {
+                const float x = NJ_LDG(a.b.X + (size_t)r * c.d + c_);
+                const float m = c.masked ? NJ_LDG(a.b.M + (size_t)r * c.d + c_) : 1.f;
+                const float y = t.YY[jr * c.sDO + c_], yb = t.YBJ[jr * c.sDO + c_];
+                const float da = x - y, db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y) : (yb - x);
+                sa = fmaf(m * da, da, sa); sb = fmaf(m * db, db, sb);
+            }
+            const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+            const float wa = (c.loss_kind == NJODE_LOSS_STANDARD) ? 2.f * c.w : c.w;
+            const float wb = (c.loss_kind == NJODE_LOSS_STANDARD) ? 2.f * (1.f - c.w) : (1.f - c.w);
+            const float s = wa * ra + wb * rb;
+            const float cf = gl * 2.f * s / (NJ_LDG(a.b.n_obs_ot + NJ_IU(t, NJ_I_PATH, u)) * (float)a.b.batch_size_norm);
+            NJ_FU(t, NJ_F_CA, jr) = cf * wa / ra;
+            NJ_FU(t, NJ_F_CB, jr) = cf * wb / rb;
+        }
+    }
+    NJ_SYNC();
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
+            const int jr = idx / c.dout, c_ = idx % c.dout;
+            const int u = NJ_IU(t, NJ_I_JMAP, jr), r = NJ_IU(t, NJ_I_JROW, jr);
+            const float x = NJ_LDG(a.b.X + (size_t)r * c.d + c_);
+            const float m = c.masked ? NJ_LDG(a.b.M + (size_t)r * c.d + c_) : 1.f;
+            const float y = t.YY[jr * c.sDO + c_], yb = t.YBJ[jr * c.sDO + c_];
+            const float ca = NJ_FU(t, NJ_F_CA, jr), cb = NJ_FU(t, NJ_F_CB, jr);
+            float gy, gyb;
+            if (c.loss_kind == NJODE_LOSS_STANDARD) { gy = -ca * m * (x - y) - cb * m * (yb - y); gyb = cb * m * (yb - y); }
+            else { gy = -ca * m * (x - y); gyb = cb * m * (yb - x); }
+            if (c.masked) gy += t.GX[u * c.sD + c_];          // last_X = Y[i_obs]  (NJODE/models.py:483-484)
+            t.GOUT[jr * c.sOUT + c_] = gy;
+            t.GYBJ[jr * c.sDO + c_] = gyb;
+        }
+    }
+    NJ_SYNC();
+    // 4. readout backward at E
+    float* gin = nj_mlp_backward(t, NJODE_NET_RO, nj, true);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+            const int jr = idx / c.H, c_ = idx % c.H;
+            const int u = NJ_IU(t, NJ_I_JMAP, jr);
+            const float th = t.IN[(size_t)jr * c.sIN + c_];
+            float ge = t.GH[u * c.sH + c_] + gin[jr * c.sG + c_] * (1.f - th * th);
+            if (c.residual) ge += nj_resid_bwd(t.GOUT + jr * c.sOUT, c.H, c.dout, c_);
+            t.GTMP[jr * c.sOUT + c_] = ge;
+        }
+    }
+    NJ_SYNC();
+    // 5. encoder recompute + backward
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.d; idx += t.nt) {
+            const int jr = idx / c.d, c_ = idx % c.d;
+            t.IN[(size_t)jr * c.sIN + c_] = tanhf(t.XI[jr * c.sD + c_]);
+            if (c.masked) t.IN[(size_t)jr * c.sIN + c.d + c_] = NJ_LDG(a.b.M + (size_t)NJ_IU(t, NJ_I_JROW, jr) * c.d + c_);
+        }
+        for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+            const int jr = idx / c.H, c_ = idx % c.H;
+            t.GOUT[jr * c.sOUT + c_] = t.GTMP[jr * c.sOUT + c_];
+        }
+        nj_set_jump_keys(t, a, nj, 1, tid);
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_ENC, nj, true);
+    gin = nj_mlp_backward(t, NJODE_NET_ENC, nj, c.masked != 0);
+    if (c.masked) {
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nj * c.d; idx += t.nt) {
+                const int jr = idx / c.d, c_ = idx % c.d;
+                const float tx = t.IN[(size_t)jr * c.sIN + c_];
+                float gx = gin[jr * c.sG + c_] * (1.f - tx * tx);
+                if (c.residual) gx += nj_resid_bwd(t.GOUT + jr * c.sOUT, c.d, c.H, c_);
+                const float m = NJ_LDG(a.b.M + (size_t)NJ_IU(t, NJ_I_JROW, jr) * c.d + c_);
+                t.GYBJ[jr * c.sDO + c_] += (1.f - m) * gx;
+            }
+        }
+        NJ_SYNC();
+    }
+    // 6. readout recompute at h_before + backward -> gradient wrt h before the jump
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+            const int jr = idx / c.H, c_ = idx % c.H;
+            t.IN[(size_t)jr * c.sIN + c_] = tanhf(t.XH[jr * c.sH + c_]);
+        }
+        for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
+            const int jr = idx / c.dout, c_ = idx % c.dout;
+            t.GOUT[jr * c.sOUT + c_] = t.GYBJ[jr * c.sDO + c_];
+        }
+        nj_set_jump_keys(t, a, nj, 0, tid);
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_RO, nj, true);
+    gin = nj_mlp_backward(t, NJODE_NET_RO, nj, true);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+            const int jr = idx / c.H, c_ = idx % c.H;
+            const int u = NJ_IU(t, NJ_I_JMAP, jr);
+            const float th = t.IN[(size_t)jr * c.sIN + c_];
+            float gh = gin[jr * c.sG + c_] * (1.f - th * th);
+            if (c.residual) gh += nj_resid_bwd(t.GOUT + jr * c.sOUT, c.H, c.dout, c_);
+            t.GH[u * c.sH + c_] = gh;
+        }
+        for (int idx = tid; idx < nj * c.d; idx += t.nt) {
+            const int jr = idx / c.d, c_ = idx % c.d;
+            t.GX[NJ_IU(t, NJ_I_JMAP, jr) * c.sD + c_] = 0.f;
+        }
+        if (tid < nj) NJ_IU(t, NJ_I_CUR, NJ_IU(t, NJ_I_JMAP, tid)) -= 1;
+    }
+    NJ_SYNC();
+}
+
+NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta, int ncta) {
+    NjCta t;
+    nj_cta_bind(t, c, smem, true);
+    if (c.w_smem) {
+        float* simg = smem + c.o_img;
+        NJ_THREADS(tid, t.nt) { for (int i = tid; i < c.img_floats / 4; i += t.nt) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
+        t.wimg = simg;
+    } else t.wimg = a.image;
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    t.dimg = c.dw_smem ? smem + c.o_dimg : gpart;
+    nj_zero(t.dimg, c.img_floats, t.nt);
+    nj_zero(smem + c.o_IN, c.o_I - c.o_IN, t.nt);
+    NJ_SYNC();
+    for (int tile = cta; tile < a.n_tiles; tile += ncta) {
+        nj_load_units(t, a, tile, true);
+        const int nu = (a.b.n_units - tile * c.P) < c.P ? (a.b.n_units - tile * c.P) : c.P;
+        const int maxlen = t.CTL[NJ_CTL_MAXLEN];
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nu * c.H; idx += t.nt) {
+                const int u = idx / c.H, c_ = idx % c.H;
+                t.GH[u * c.sH + c_] = (NJ_IU(t, NJ_I_FLAG, u) && a.grad_hT) ? NJ_LDG(a.grad_hT + (size_t)NJ_IU(t, NJ_I_PATH, u) * c.H + c_) : 0.f;
+            }
+            for (int idx = tid; idx < nu * c.d; idx += t.nt) t.GX[(idx / c.d) * c.sD + idx % c.d] = 0.f;
+        }
+        NJ_SYNC();
+        nj_reload_state(t, a, nu);
+        for (int j = maxlen; j >= 0; --j) {
+            if (j < maxlen) {
+                // ---- reverse of Euler step k = s0 + j ----
+                NJ_THREADS(tid, t.nt) {
+                    for (int idx = tid; idx < nu * c.inf; idx += t.nt) {
+                        const int u = idx / c.inf, c_ = idx % c.inf;
+                        const bool active = j < NJ_IU(t, NJ_I_LEN, u);
+                        const int k = NJ_IU(t, NJ_I_S0, u) + j;
+                        float hval = 0.f;
+                        if (active && c_ >= c.d && c_ < c.d + c.H)
+                            hval = a.h_hist[((size_t)k * a.b.B + NJ_IU(t, NJ_I_PATH, u)) * c.H + c_ - c.d];
+                        nj_build_ode_input(t, u, c_, hval, active ? NJ_LDG(a.b.step_t + k) : 0.f);
+                        if (c_ == 0) {
+                            NJ_FU(t, NJ_F_DT, u) = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
+                            NJ_IU(t, NJ_I_RK, u) = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(NJ_IU(t, NJ_I_PATH, u) + a.b.path_id_offset), (unsigned)k);
+                        }
+                    }
+                }
+                NJ_SYNC();
+                NJ_THREADS(tid, t.nt) {
+                    for (int idx = tid; idx < nu * c.H; idx += t.nt) {
+                        const int u = idx / c.H, c_ = idx % c.H;
+                        t.GOUT[u * c.sOUT + c_] = NJ_FU(t, NJ_F_DT, u) * t.GH[u * c.sH + c_];
+                    }
+                }
+                NJ_SYNC();
+                nj_mlp_forward(t, NJODE_NET_ODE, nu, true);
+                float* gin = nj_mlp_backward(t, NJODE_NET_ODE, nu, true);
+                NJ_THREADS(tid, t.nt) {
+                    for (int idx = tid; idx < nu * (c.d + c.H); idx += t.nt) {
+                        const int u = idx / (c.d + c.H), c_ = idx % (c.d + c.H);
+                        if (j >= NJ_IU(t, NJ_I_LEN, u)) continue;
+                        const float th = t.IN[(size_t)u * c.sIN + c_];
+                        const float g = gin[u * c.sG + c_] * (1.f - th * th);
+                        if (c_ >= c.d) t.GH[u * c.sH + c_ - c.d] += g;
+                        else if (c.masked) t.GX[u * c.sD + c_] += g;
+                    }
+                }
+                NJ_SYNC();
+            }
+            // ---- reverse of the jumps that fall before step s0 + j ----
+            for (;;) {
+                nj_find_jumps(t, a, j, -1, true);
+                const int nj = t.CTL[NJ_CTL_NJ];
+                if (nj == 0) break;
+                nj_jump_backward(t, a, nj);
+                nj_reload_state(t, a, nu);
+            }
+        }
+        // ---- reverse of the start encoder ----
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nu * c.d; idx += t.nt) {
+                const int u = idx / c.d, c_ = idx % c.d;
+                const int sr = NJ_IU(t, NJ_I_START, u);
+                const float x = sr < 0 ? NJ_LDG(a.b.start_X + (size_t)NJ_IU(t, NJ_I_PATH, u) * c.d + c_)
+                                       : NJ_LDG(a.b.X + (size_t)sr * c.d + c_);
+                t.IN[(size_t)u * c.sIN + c_] = tanhf(x);
+                if (c.masked) t.IN[(size_t)u * c.sIN + c.d + c_] = 0.f;
+            }
+            for (int idx = tid; idx < nu * c.H; idx += t.nt) {
+                const int u = idx / c.H, c_ = idx % c.H;
+                t.GOUT[u * c.sOUT + c_] = t.GH[u * c.sH + c_];
+            }
+            if (tid < nu) {
+                const int sr = NJ_IU(t, NJ_I_START, tid);
+                const unsigned ev = sr < 0 ? NJ_EVENT_INIT : NJ_EVENT_JUMP_BASE + 3u * (unsigned)NJ_LDG(a.b.row_jump + sr) + 1u;
+                NJ_IU(t, NJ_I_RK, tid) = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(NJ_IU(t, NJ_I_PATH, tid) + a.b.path_id_offset), ev);
+            }
+        }
+        NJ_SYNC();
+        nj_mlp_forward(t, NJODE_NET_ENC, nu, true);
+        nj_mlp_backward(t, NJODE_NET_ENC, nu, false);
+    }
+    if (c.dw_smem) {
+        NJ_THREADS(tid, t.nt) { for (int i = tid; i < c.img_floats / 4; i += t.nt) nj_st4(gpart + 4 * i, nj_ld4(t.dimg + 4 * i)); }
+    }
+}

@@ -1,0 +1,162 @@
+// njode_plan.h -- host-side launch planning: validates the model description, lays out the padded
+// parameter image and the shared-memory matrices of njode_core.cuh, picks the tile size.
+#pragma once
+#include <string>
+#include <algorithm>
+#include "njode_core.cuh"
+
+struct NjPlanOut {
+    NjCfg fwd, bwd;
+    int n_tiles;
+    int grid_fwd, grid_bwd;
+    size_t smem_fwd_bytes, smem_bwd_bytes;
+    size_t ws_image_off, ws_rowloss_off, ws_partials_off, ws_bytes;
+};
+
+static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, std::string& err) {
+    int off = 0;
+    for (int n = 0; n < 3; ++n) {
+        const njode_mlp_t& s = m.net[n];
+        NjNet& N = c.net[n];
+        if (s.n_linear < 1 || s.n_linear > NJODE_MAX_LINEAR) { err = "n_linear out of range"; return false; }
+        N.n = s.n_linear;
+        for (int l = 0; l <= s.n_linear; ++l) {
+            N.dim[l] = s.dims[l];
+            if (s.dims[l] < 1) { err = "layer width < 1"; return false; }
+        }
+        for (int l = 0; l < s.n_linear; ++l) {
+            N.act[l] = s.act[l];
+            if (l < s.n_linear - 1 && s.act[l] != NJODE_ACT_TANH && s.act[l] != NJODE_ACT_RELU) { err = "unknown activation"; return false; }
+            N.ks[l] = nj_stride_host(s.dims[l]);
+            N.og[l] = (s.dims[l + 1] + 3) / 4;
+            N.w_img[l] = off; off += 4 * N.og[l] * N.ks[l];
+            N.b_img[l] = off; off += 4 * N.og[l];
+            N.w_src[l] = s.w_off[l]; N.b_src[l] = s.b_off[l];
+        }
+    }
+    c.img_floats = off;
+    return true;
+}
+
+// lays out shared memory for tile size P; returns the number of floats needed
+static inline void nj_layout(NjCfg& c, int P, int nt, bool bwd, bool w_smem, bool dw_smem) {
+    c.P = P; c.nt = nt; c.w_smem = w_smem; c.dw_smem = dw_smem && bwd;
+    int o = 0;
+    c.o_img = o; if (w_smem) o += c.img_floats;
+    c.o_dimg = o; if (c.dw_smem) o += c.img_floats;
+    c.o_IN = o; o += P * c.sIN;
+    c.o_ACT = o; o += c.nACT * P * c.sACT;
+    c.o_OUT = o; o += P * c.sOUT;
+    c.o_H = o; o += P * c.sH;
+    c.o_LX = o; o += P * c.sD;
+    c.o_XI = o; o += P * c.sD;
+    c.o_YBJ = o; o += P * c.sDO;
+    c.o_YY = o; o += P * c.sDO;
+    c.o_XH = o; o += P * c.sH;
+    c.o_EE = o; o += P * c.sH;
+    c.o_GOUT = c.o_GTMP = c.o_GA = c.o_GB = c.o_GH = c.o_GX = c.o_GYBJ = o;
+    if (bwd) {
+        c.o_GOUT = o; o += P * c.sOUT;
+        c.o_GTMP = o; o += P * c.sOUT;
+        c.o_GA = o; o += P * c.sG;
+        c.o_GB = o; o += P * c.sG;
+        c.o_GH = o; o += P * c.sH;
+        c.o_GX = o; o += P * c.sD;
+        c.o_GYBJ = o; o += P * c.sDO;
+    }
+    c.o_F = o; o += NJ_F_COUNT * P;
+    o = (o + 3) & ~3;
+    c.o_I = o; o += NJ_I_COUNT * P + NJ_CTL_COUNT;
+    o = (o + 3) & ~3;
+    if (bwd) c.smem_floats_bwd = o; else c.smem_floats_fwd = o;
+}
+
+static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, std::string& err) {
+    memset(&c, 0, sizeof(c));
+    if (!nj_fill_nets(m, c, err)) return false;
+    c.d = m.input_size; c.H = m.hidden_size; c.dout = m.output_size;
+    c.masked = m.masked; c.curt = m.input_current_t; c.loss_kind = m.loss_kind; c.residual = m.residual;
+    c.training = m.training;
+    c.inf = c.net[NJODE_NET_ODE].dim[0]; c.enc_in = c.net[NJODE_NET_ENC].dim[0];
+    const NjNet &O = c.net[NJODE_NET_ODE], &E = c.net[NJODE_NET_ENC], &R = c.net[NJODE_NET_RO];
+    if (c.inf != c.d + c.H + 2 + (c.curt ? 1 : 0)) { err = "ode_f input width != input+hidden+2(+1)"; return false; }
+    if (O.dim[O.n] != c.H) { err = "ode_f output width != hidden_size"; return false; }
+    if (c.enc_in != c.d * (c.masked ? 2 : 1)) { err = "encoder input width mismatch"; return false; }
+    if (E.dim[E.n] != c.H) { err = "encoder output width != hidden_size"; return false; }
+    if (R.dim[0] != c.H || R.dim[R.n] != c.dout) { err = "readout widths mismatch"; return false; }
+    if (c.dout != c.d) { err = "output_size must equal input_size (loss compares X with Y)"; return false; }
+    if (c.residual) {
+        // FFNN.__init__ residual cases, NJODE/models.py:240-257
+        if ((c.d <= c.H && c.H % c.d) || (c.d > c.H && c.d % c.H)) { err = "for residual: encoder sizes must be multiples"; return false; }
+        if ((c.H <= c.dout && c.dout % c.H) || (c.H > c.dout && c.H % c.dout)) { err = "for residual: readout sizes must be multiples"; return false; }
+    }
+    c.w = m.weight;
+    const float p = m.dropout_p;
+    c.has_drop = (m.training && p > 0.f) ? 1 : 0;
+    c.one_minus_p = 1.f - p;
+    c.keep_scale = (p < 1.f) ? 1.f / (1.f - p) : 0.f;
+    double thr = (double)p * 4294967296.0;
+    c.thr = thr >= 4294967295.0 ? 4294967295u : (unsigned)thr;
+    c.seed_lo = (unsigned)(m.dropout_seed & 0xFFFFFFFFull); c.seed_hi = (unsigned)(m.dropout_seed >> 32);
+    int maxhid = 1, maxin = 1, maxn = 1;
+    for (int n = 0; n < 3; ++n) {
+        const NjNet& N = c.net[n];
+        maxn = std::max(maxn, N.n);
+        for (int l = 0; l < N.n; ++l) maxin = std::max(maxin, N.dim[l]);
+        for (int l = 1; l < N.n; ++l) maxhid = std::max(maxhid, N.dim[l]);
+    }
+    c.sIN = nj_stride_host(std::max(std::max(c.inf, c.enc_in), c.H));
+    c.sACT = nj_stride_host(maxhid);
+    c.nACT = std::max(1, maxn - 1);
+    c.sOUT = nj_stride_host(std::max(c.H, c.dout));
+    c.sH = nj_stride_host(c.H); c.sD = nj_stride_host(c.d); c.sDO = nj_stride_host(c.dout);
+    c.sG = nj_stride_host(maxin);
+    return true;
+}
+
+// choose tile size / residency so that both kernels fit `smem_limit` bytes per CTA
+static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_units_bwd, int N_rows,
+                                int num_sms, size_t smem_limit, int force_P, NjPlanOut& out, std::string& err) {
+    NjCfg base;
+    if (!nj_make_cfg(m, base, err)) return false;
+    static const int cand[4] = {64, 32, 16, 8};
+    int P = 8;
+    for (int i = 0; i < 4; ++i)
+        if ((n_units_fwd + cand[i] - 1) / cand[i] >= num_sms) { P = cand[i]; break; }
+    if (force_P > 0) P = force_P;
+    for (;;) {
+        const int nt = std::max(64, std::min(256, 4 * P));
+        bool ok_f = false, ok_b = false;
+        out.fwd = base; out.bwd = base;
+        for (int w = 1; w >= 0 && !ok_f; --w) {
+            nj_layout(out.fwd, P, nt, false, w != 0, false);
+            ok_f = (size_t)out.fwd.smem_floats_fwd * 4 <= smem_limit;
+        }
+        static const int opts[3][2] = {{1, 1}, {1, 0}, {0, 0}};
+        for (int k = 0; k < 3 && !ok_b; ++k) {
+            nj_layout(out.bwd, P, nt, true, opts[k][0] != 0, opts[k][1] != 0);
+            ok_b = (size_t)out.bwd.smem_floats_bwd * 4 <= smem_limit;
+        }
+        if (ok_f && ok_b) break;
+        if (P <= 4) { err = "model too wide for the shared-memory tile kernels"; return false; }
+        P /= 2;
+    }
+    out.smem_fwd_bytes = (size_t)out.fwd.smem_floats_fwd * 4;
+    out.smem_bwd_bytes = (size_t)out.bwd.smem_floats_bwd * 4;
+    const int P_ = out.fwd.P;
+    out.n_tiles = (n_units_fwd + P_ - 1) / P_;
+    const int tiles_b = (n_units_bwd + P_ - 1) / P_;
+    auto per_sm = [&](size_t bytes, int nt) {
+        int k = (int)((smem_limit + 1024) / (bytes + 1024));
+        k = std::min(k, 2048 / nt);
+        return std::max(1, std::min(k, 8));
+    };
+    out.grid_fwd = std::max(1, std::min(out.n_tiles, num_sms * per_sm(out.smem_fwd_bytes, out.fwd.nt)));
+    out.grid_bwd = std::max(1, std::min(tiles_b, num_sms * per_sm(out.smem_bwd_bytes, out.bwd.nt)));
+    size_t o = 0;
+    out.ws_image_off = o; o += (size_t)base.img_floats * 4; o = (o + 255) & ~(size_t)255;
+    out.ws_rowloss_off = o; o += (size_t)std::max(N_rows, 1) * 4; o = (o + 255) & ~(size_t)255;
+    out.ws_partials_off = o; o += (size_t)out.grid_bwd * base.img_floats * 4;
+    out.ws_bytes = o;
+    return true;
+}

@@ -1,0 +1,144 @@
+"""Host-side schedule and work-unit builder.
+
+The reference decides *on the host, in float64* (float32 when ``times`` is float32, NumPy >= 2
+weak-scalar promotion) how many Euler steps every batch takes and how long each one is
+(NJODE/models.py:430-439 and 497-505).  ``build_schedule`` executes exactly those expressions, so
+the step list -- and therefore ``path_t`` -- is equal to the reference's by construction; the
+device only ever sees the fp32-rounded scalars the reference's tensor ops would see.
+
+``build_units`` turns the collate contract's (time_ptr, obs_idx) (NJODE/data_utils.py:292-315)
+into a per-path CSR of observation rows and the list of work units the kernels march:
+whole paths (masked model / return_path), or (path, inter-observation segment) pairs for the
+non-masked model, where the state after a jump does not depend on the state before it
+(NJODE/models.py:463-470) so every segment is independent.
+"""
+import collections
+
+import numpy as np
+
+UNIT_WRITES_HT = 1 << 30
+
+_Schedule = collections.namedtuple(
+    "_Schedule", "S K E step_dt step_t jump_step jump_tau step_event jump_event path_t")
+_cache = collections.OrderedDict()
+_CACHE_MAX = 16
+
+
+def build_schedule(times, delta_t, T, until_T, return_path):
+    """event list of one forward call.  step k: dt = step_dt[k] (fl32 of delta_t_), time at the
+    start = step_t[k]; jump i happens after jump_step[i] steps; *_event = index into path_t."""
+    times = np.asarray(times)
+    key = (times.tobytes(), times.dtype.str, float(delta_t), float(T), bool(until_T), bool(return_path))
+    hit = _cache.get(key)
+    if hit is not None:
+        _cache.move_to_end(key)
+        return hit
+    step_dt, step_t, step_event, jump_step, jump_event = [], [], [], [], []
+    path_t = [0]
+    current_time = 0.0
+    for obs_time in times:
+        # NJODE/models.py:432-439 (expressions kept verbatim, incl. operand types)
+        while current_time < (obs_time - 1e-10 * delta_t):
+            if current_time < obs_time - delta_t:
+                delta_t_ = delta_t
+            else:
+                delta_t_ = obs_time - current_time
+            step_t.append(current_time)
+            step_dt.append(delta_t_)
+            current_time = current_time + delta_t_          # ode_step, NJODE/models.py:376
+            step_event.append(len(path_t))
+            path_t.append(current_time)
+        jump_step.append(len(step_dt))
+        jump_event.append(len(path_t))
+        path_t.append(obs_time)
+    if until_T:                                              # NJODE/models.py:497-505
+        while current_time < T - 1e-10 * delta_t:
+            if current_time < T - delta_t:
+                delta_t_ = delta_t
+            else:
+                delta_t_ = T - current_time
+            step_t.append(current_time)
+            step_dt.append(delta_t_)
+            current_time = current_time + delta_t_
+            step_event.append(len(path_t))
+            path_t.append(current_time)
+    sched = _Schedule(
+        S=len(step_dt), K=len(times), E=len(path_t) if return_path else 0,
+        step_dt=np.array(step_dt, dtype=np.float64).astype(np.float32),
+        step_t=np.array(step_t, dtype=np.float64).astype(np.float32),
+        jump_step=np.array(jump_step, dtype=np.int32),
+        jump_tau=times.astype(np.float64).astype(np.float32),     # NJODE/models.py:487
+        step_event=np.array(step_event, dtype=np.int32),
+        jump_event=np.array(jump_event, dtype=np.int32),
+        path_t=np.array(path_t) if return_path else None)
+    _cache[key] = sched
+    if len(_cache) > _CACHE_MAX:
+        _cache.popitem(last=False)
+    return sched
+
+
+def build_csr(time_ptr, obs_idx, B):
+    """rows of every path in time order.  obs_idx: int64 numpy [N]; rows are time-major already
+    (NJODE/data_utils.py:298-307), so a stable sort by path keeps each path's rows time-ordered."""
+    time_ptr = np.asarray(time_ptr, dtype=np.int64)
+    obs_idx = np.asarray(obs_idx, dtype=np.int64)
+    K = len(time_ptr) - 1
+    N = int(time_ptr[-1]) if K >= 0 and len(time_ptr) else 0
+    if len(obs_idx) != N:
+        raise AssertionError("len(obs_idx) != time_ptr[-1]")
+    if N and (obs_idx.min() < 0 or obs_idx.max() >= B):
+        raise IndexError("obs_idx out of range")
+    row_jump = np.repeat(np.arange(K, dtype=np.int32), np.diff(time_ptr))
+    path_rows = np.argsort(obs_idx, kind="stable").astype(np.int32)
+    path_ptr = np.zeros(B + 1, dtype=np.int32)
+    np.cumsum(np.bincount(obs_idx, minlength=B), out=path_ptr[1:])
+    if N:
+        # the contract has at most one row per (time, path) (NJODE/data_utils.py:302-306)
+        pj = row_jump[path_rows].astype(np.int64) + obs_idx[path_rows] * (K + 1)
+        if np.any(np.diff(pj) == 0):
+            raise ValueError("a path has two observation rows at the same observation time")
+    return path_ptr, path_rows, row_jump
+
+
+def build_units(sched, path_ptr, path_rows, row_jump, B, segments):
+    """returns (units [n,6] int32, n_loss_units).  Layout of a unit: see include/njode_b200.h.
+    The first n_loss_units units are the ones that contribute to the loss (sorted longest first);
+    the remaining ones only produce hT (the tail after a path's last observation)."""
+    S = sched.S
+    N = len(path_rows)
+    if not segments:
+        units = np.empty((B, 6), dtype=np.int32)
+        units[:, 0] = np.arange(B)
+        units[:, 1] = 0
+        units[:, 2] = S
+        units[:, 3] = path_ptr[:-1]
+        units[:, 4] = path_ptr[1:]
+        units[:, 5] = UNIT_WRITES_HT
+        return units, B
+    q = np.arange(N, dtype=np.int64)
+    sorted_path = np.repeat(np.arange(B, dtype=np.int32), np.diff(path_ptr))
+    js = sched.jump_step[row_jump[path_rows]] if N else np.zeros(0, dtype=np.int32)
+    first = np.ones(N, dtype=bool)
+    if N:
+        first[1:] = sorted_path[1:] != sorted_path[:-1]
+    prev_js = np.where(first, 0, np.concatenate(([0], js[:-1]))) if N else js
+    prev_row = np.where(first, -1, np.concatenate(([-1], path_rows[:-1]))) if N else path_rows
+    loss_units = np.empty((N, 6), dtype=np.int32)
+    loss_units[:, 0] = sorted_path
+    loss_units[:, 1] = prev_js
+    loss_units[:, 2] = js
+    loss_units[:, 3] = q
+    loss_units[:, 4] = q + 1
+    loss_units[:, 5] = prev_row + 1
+    tails = np.empty((B, 6), dtype=np.int32)
+    has = path_ptr[1:] > path_ptr[:-1]
+    last_q = np.maximum(path_ptr[1:] - 1, 0)
+    tails[:, 0] = np.arange(B)
+    tails[:, 1] = np.where(has, js[last_q] if N else 0, 0)
+    tails[:, 2] = S
+    tails[:, 3] = path_ptr[1:]
+    tails[:, 4] = path_ptr[1:]
+    tails[:, 5] = (np.where(has, path_rows[last_q] + 1 if N else 0, 0)) | UNIT_WRITES_HT
+    o1 = np.argsort(-(loss_units[:, 2] - loss_units[:, 1]), kind="stable")
+    o2 = np.argsort(-(tails[:, 2] - tails[:, 1]), kind="stable")
+    return np.concatenate((loss_units[o1], tails[o2]), axis=0), N

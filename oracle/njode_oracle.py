@@ -61,22 +61,29 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def dropout_keep_mask(seed, path_ids, event_id, net_id, layer_id, width, p):
-    """keep-mask [len(path_ids), width] (float32 0/1) for one MLP hidden layer.
+def _fmix32(h):
+    h = np.asarray(h, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        h = h ^ (h >> np.uint32(16)); h = h * np.uint32(0x85EBCA6B)
+        h = h ^ (h >> np.uint32(13)); h = h * np.uint32(0xC2B2AE35)
+        h = h ^ (h >> np.uint32(16))
+    return h
 
-    counter = (path, event, net<<8 | layer, neuron>>2), key = (seed_lo, seed_hi); neuron j uses
-    output word j&3; keep iff word >= floor(p * 2^32).
-    """
-    path_ids = np.asarray(path_ids, dtype=np.uint32)[:, None]
-    neuron = np.arange(width, dtype=np.uint32)[None, :]
-    thr = np.uint32(min(int(p * 4294967296.0), 4294967295))
-    words = philox4x32_10(path_ids, np.uint32(event_id), np.uint32((net_id << 8) | layer_id),
-                          neuron >> np.uint32(2),
-                          np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
-    sel = neuron & np.uint32(3)
-    w = np.where(sel == 0, words[0], np.where(sel == 1, words[1],
-                                               np.where(sel == 2, words[2], words[3])))
-    return (w >= thr).astype(np.float32)
+
+def dropout_keep_mask(seed, path_ids, event_id, net_id, layer_id, width, p):
+    """keep-mask [len(path_ids), width] (float32 0/1) of one MLP hidden layer; restates
+    nj_row_key / nj_layer_key / nj_keep of njode_b200/csrc/njode_core.cuh (murmur3 finaliser chain
+    keyed by seed, path, event, net, layer, neuron); keep iff hash >= floor(p * 2^32)."""
+    path_ids = np.asarray(path_ids, dtype=np.uint32)
+    seed_lo, seed_hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    thr = np.uint32(min(int(np.float32(p).astype(np.float64) * 4294967296.0), 4294967295))
+    with np.errstate(over="ignore"):
+        rk = _fmix32(_fmix32(path_ids ^ seed_lo) + np.uint32(event_id & 0xFFFFFFFF) * np.uint32(0x9E3779B9)) ^ seed_hi
+        tag = np.uint32(net_id * 16 + layer_id + 1)
+        lk = _fmix32(rk + tag * np.uint32(0x85EBCA77))
+        neuron = np.arange(width, dtype=np.uint32)[None, :]
+        el = _fmix32(lk[:, None] + neuron * np.uint32(0xC2B2AE3D))
+    return (el >= thr).astype(np.float32)
 
 
 NET_ODE, NET_ENC, NET_RO = 0, 1, 2
@@ -206,7 +213,7 @@ def forward(cfg, sd, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
 
         def f(layer, width):
             keep = dropout_keep_mask(dropout_seed, rows, event, net, layer, width, p)
-            return torch.as_tensor(keep, dtype=dt_) * (1.0 / (1.0 - p))
+            return torch.as_tensor(keep, dtype=dt_) * float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
         return f
 
     def enc(x, mask, event, rows):

@@ -1,0 +1,127 @@
+// TEST INFRASTRUCTURE ONLY -- sequential host simulation of njode_b200/csrc/njode_core.cuh.
+// The kernel source is written as barrier-separated phases over shared arrays, so compiling it with
+// -DNJODE_HOST_SIM runs every "thread" of a CTA in turn between barriers.  This lets the CPU test
+// suite exercise the exact index/stride/cursor/gradient logic of the CUDA kernels without a GPU.
+// It exports the same C ABI as libnjode_b200.so but takes HOST pointers.  The product package never
+// loads this library (njode_b200/_ext.py only ever opens libnjode_b200.so and refuses to run
+// without a CUDA device).
+#define NJODE_HOST_SIM 1
+#include <stdlib.h>
+#include <vector>
+#include "../../njode_b200/csrc/njode_plan.h"
+
+static thread_local std::string g_err;
+extern "C" const char* njode_last_error(void) { return g_err.c_str(); }
+extern "C" int njode_abi_version(void) { return NJODE_ABI_VERSION; }
+
+static const int kSimSMs = 4;
+static const size_t kSimSmem = 227 * 1024;
+
+static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& out) {
+    std::string err;
+    const char* fp = getenv("NJODE_FORCE_TILE");
+    if (!nj_make_plan(*m, b->n_units, b->n_units, b->N, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
+    const size_t cap = (size_t)kSimSMs * 2;
+    out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
+    out.ws_bytes = out.ws_partials_off + cap * out.fwd.img_floats * sizeof(float);
+    return 0;
+}
+
+extern "C" int njode_plan(const njode_model_t* model, const njode_batch_t* bs, int, njode_plan_t* p) {
+    NjPlanOut o;
+    if (int rc = plan_for(model, bs, o)) return rc;
+    p->tile_paths = o.fwd.P; p->threads = o.fwd.nt; p->grid_fwd = o.grid_fwd; p->grid_bwd = o.grid_bwd;
+    p->weights_in_smem = o.fwd.w_smem; p->grads_in_smem = o.bwd.dw_smem;
+    p->smem_fwd_bytes = (int64_t)o.smem_fwd_bytes; p->smem_bwd_bytes = (int64_t)o.smem_bwd_bytes;
+    p->image_floats = o.fwd.img_floats; p->workspace_bytes = (int64_t)o.ws_bytes;
+    return 0;
+}
+
+static void pack(const NjCfg& c, const float* params, float* image) {
+    for (int i = 0; i < c.img_floats; ++i) image[i] = 0.f;
+    for (int n = 0; n < 3; ++n) {
+        const NjNet& N = c.net[n];
+        for (int l = 0; l < N.n; ++l) {
+            const int K = N.dim[l], O = N.dim[l + 1];
+            for (int o = 0; o < O; ++o) {
+                for (int k = 0; k < K; ++k) image[N.w_img[l] + o * N.ks[l] + k] = params[N.w_src[l] + (long long)o * K + k];
+                if (N.b_src[l] >= 0) image[N.b_img[l] + o] = params[N.b_src[l] + o];
+            }
+        }
+    }
+}
+
+static void fill_args(NjArgs& a, const njode_batch_t* b, const NjPlanOut& pl, char* ws) {
+    memset(&a, 0, sizeof(a));
+    a.b = *b;
+    a.image = reinterpret_cast<const float*>(ws + pl.ws_image_off);
+    a.row_loss = reinterpret_cast<float*>(ws + pl.ws_rowloss_off);
+    a.partials = reinterpret_cast<float*>(ws + pl.ws_partials_off);
+}
+
+extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* batch, const float* params,
+                             float* hT, float* loss, float* path_h, float* path_y,
+                             const njode_saved_t* saved, void* workspace, void*) {
+    NjPlanOut pl;
+    if (int rc = plan_for(model, batch, pl)) return rc;
+    NjArgs a;
+    fill_args(a, batch, pl, (char*)workspace);
+    a.hT = hT; a.path_h = path_h; a.path_y = path_y;
+    a.h_hist = saved ? saved->h_hist : nullptr;
+    a.h_before = saved ? saved->h_before : nullptr;
+    a.y_after = saved ? saved->y_after : nullptr;
+    a.get_loss = loss ? 1 : 0;
+    a.n_tiles = pl.n_tiles;
+    pack(pl.fwd, params, const_cast<float*>(a.image));
+    for (int i = 0; i < batch->N; ++i) a.row_loss[i] = 0.f;
+    std::vector<float> smem(pl.fwd.smem_floats_fwd);
+    for (int cta = 0; cta < pl.grid_fwd && batch->n_units > 0; ++cta) {
+        std::fill(smem.begin(), smem.end(), NAN);       // uninitialised shared memory must never matter
+        nj_cta_forward(pl.fwd, a, smem.data(), cta, pl.grid_fwd);
+    }
+    if (loss) {
+        double s = 0.0;
+        for (int i = 0; i < batch->N; ++i) s += a.row_loss[i];
+        loss[0] = (float)(s * (double)(1.f / (float)batch->batch_size_norm));
+    }
+    return 0;
+}
+
+extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* batch, const float* params,
+                              const njode_saved_t* saved, const float* grad_loss, const float* grad_hT,
+                              float* grads, void* workspace, void*) {
+    NjPlanOut pl;
+    if (int rc = plan_for(model, batch, pl)) return rc;
+    NjArgs a;
+    fill_args(a, batch, pl, (char*)workspace);
+    a.h_hist = saved->h_hist; a.h_before = saved->h_before; a.y_after = saved->y_after;
+    a.grad_loss = grad_loss; a.grad_hT = grad_hT; a.get_loss = 1; a.n_tiles = pl.n_tiles;
+    pack(pl.bwd, params, const_cast<float*>(a.image));
+    std::vector<float> smem(pl.bwd.smem_floats_bwd);
+    int nparts = 0;
+    for (int cta = 0; cta < pl.grid_bwd && batch->n_units > 0; ++cta) {
+        std::fill(smem.begin(), smem.end(), NAN);
+        nj_cta_backward(pl.bwd, a, smem.data(), cta, pl.grid_bwd);
+        nparts = pl.grid_bwd;
+    }
+    const NjCfg& c = pl.bwd;
+    for (int n = 0; n < 3; ++n) {
+        const NjNet& N = c.net[n];
+        for (int l = 0; l < N.n; ++l) {
+            const int K = N.dim[l], O = N.dim[l + 1];
+            for (int o = 0; o < O; ++o) {
+                for (int k = 0; k < K; ++k) {
+                    float s = 0.f;
+                    for (int p = 0; p < nparts; ++p) s += a.partials[(size_t)p * c.img_floats + N.w_img[l] + o * N.ks[l] + k];
+                    grads[N.w_src[l] + (long long)o * K + k] = s;
+                }
+                if (N.b_src[l] >= 0) {
+                    float s = 0.f;
+                    for (int p = 0; p < nparts; ++p) s += a.partials[(size_t)p * c.img_floats + N.b_img[l] + o];
+                    grads[N.b_src[l] + o] = s;
+                }
+            }
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,32 @@
+"""builds (g++) and loads the sequential HOST SIMULATION of the CUDA kernel source
+(tests/hostsim/njode_hostsim.cpp) -- test infrastructure for the CPU-only suite."""
+import os
+import subprocess
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "hostsim", "njode_hostsim.cpp")
+OUT_DIR = os.path.join(ROOT, "tests", "_hostsim")
+OUT = os.path.join(OUT_DIR, "libnjode_hostsim.so")
+DEPS = [SRC] + [os.path.join(ROOT, "njode_b200", "csrc", f) for f in ("njode_core.cuh", "njode_plan.h")] + \
+       [os.path.join(ROOT, "include", "njode_b200.h")]
+
+_runner = None
+
+
+def build():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+        return OUT
+    subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                           "-o", OUT, SRC])
+    return OUT
+
+
+def runner():
+    global _runner
+    if _runner is None:
+        from njode_b200 import _ext
+        _runner = _ext.Runner(_ext.Lib(build()), torch.device("cpu"))
+    return _runner

@@ -1,0 +1,103 @@
+"""GPU parity tests proper: njode_b200.models.NJODE on cuda:0 (libnjode_b200.so through the C ABI)
+against the committed outputs of the real reference and against the oracle on fresh seeded inputs.
+Tolerance: rtol 1e-4 (fp32) as stated in BASELINE.json; path_t / schedule handling exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import parity_util
+import oracle.njode_oracle as orc
+from njode_b200 import models
+
+pytestmark = pytest.mark.gpu
+NAMES = cases.golden_names()
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def no_test_runner():
+    models._TEST_RUNNER = None
+    yield
+    os.environ.pop("NJODE_FORCE_TILE", None)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_training_call(name):
+    parity_util.check_training_call(name, DEV)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_training_call_with_hT_gradient(name):
+    parity_util.check_training_call(name, DEV, with_hT_grad=True)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_path_call(name):
+    parity_util.check_path_call(name, DEV)
+
+
+@pytest.mark.parametrize("tile", [8, 16, 32, 64])
+@pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small"])
+def test_tile_size_invariance(name, tile):
+    os.environ["NJODE_FORCE_TILE"] = str(tile)
+    parity_util.check_training_call(name, DEV, with_hT_grad=True)
+    parity_util.check_path_call(name, DEV)
+
+
+def _oracle_vs_cuda(cfg, batch, dt, T, seed, train=False, rtol=1e-4):
+    parity_util.check_against_oracle(cfg, batch, dt, T, seed, DEV, train=train, rtol=rtol)
+
+
+def test_demo_batch_200_against_oracle():
+    """BASELINE config 1 shape: d=1, H=10, 2x50, 100 steps, B=200, obs_perc 0.1"""
+    batch = cases.grid_batch(200, 1, 100, 0.1, seed=5)
+    _oracle_vs_cuda(cases.CONFIGS["demo"], batch, 0.01, 1.0, seed=1)
+
+
+def test_demo_batch_train_mode_dropout_against_oracle():
+    """train mode: the oracle replays the device's counter-based keep-masks"""
+    cfg = cases.demo_cfg(dropout_rate=0.1)
+    batch = cases.grid_batch(64, 1, 50, 0.15, seed=6)
+    _oracle_vs_cuda(cfg, batch, 0.02, 1.0, seed=2, train=True)
+
+
+def test_masked_physionet_shape_against_oracle():
+    batch = cases.irregular_batch(12, 41, 40, seed=7, masked=True, times_f32=True, obs_at_zero=True,
+                                  row_prob=0.2, feat_prob=0.12)
+    _oracle_vs_cuda(cases.CONFIGS["masked_physio"], batch, 0.01, 1 + 1e-12, seed=3)
+
+
+def test_wide_model_global_weights_against_oracle():
+    """weights too large for shared memory -> global-memory parameter image path"""
+    cfg = cases.demo_cfg(input_size=4, output_size=4, hidden_size=128,
+                         ode_nn=[[256, "tanh"], [256, "tanh"]], enc_nn=[[256, "tanh"]],
+                         readout_nn=[[256, "tanh"]])
+    batch = cases.grid_batch(48, 4, 12, 0.3, seed=8)
+    _oracle_vs_cuda(cfg, batch, 1.0 / 12, 1.0, seed=4)
+
+
+def test_empty_batch_edges():
+    """no observation rows at all / zero Euler steps"""
+    cfg = cases.CONFIGS["demo"]
+    sd = orc.init_state_dict(orc.Config(**cfg), seed=9)
+    m = parity_util.build_model(cfg, sd, DEV).eval()
+    B = 5
+    batch = {"times": np.zeros(0), "time_ptr": np.array([0]), "X": torch.zeros(0, 1),
+             "obs_idx": torch.zeros(0, dtype=torch.long), "start_X": torch.ones(B, 1),
+             "n_obs_ot": torch.zeros(B, dtype=torch.long)}
+    with torch.no_grad():
+        hT, loss = parity_util.call(m, batch, {"delta_t": 0.1, "T": 1.0}, DEV, until_T=True)
+        o_hT, o_loss = orc.forward(orc.Config(**cfg), sd, batch["times"], batch["time_ptr"], batch["X"],
+                                   batch["obs_idx"], 0.1, 1.0, batch["start_X"], batch["n_obs_ot"], until_T=True)
+    assert float(loss) == 0.0
+    assert parity_util.rel_err(hT.cpu().numpy(), o_hT.numpy()) < 1e-4
+
+
+def test_native_library_is_loaded():
+    from njode_b200 import _ext
+    with open("/proc/self/maps") as f:
+        assert "libnjode_b200.so" in f.read()
+    assert _ext.cuda_lib().dll.njode_abi_version() == 1

@@ -1,0 +1,83 @@
+"""CPU-only: the kernel source (njode_b200/csrc/njode_core.cuh) compiled as a sequential host
+simulation, driven through the product's Python layer (schedule, staging, autograd bridge), against
+the golden outputs of the real reference.  Exercises the exact device logic without a GPU; the GPU
+parity tests proper are tests/test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import hostsim_util
+import parity_util
+from njode_b200 import models
+
+NAMES = cases.golden_names()
+
+
+@pytest.fixture(autouse=True)
+def sim_runner():
+    models._TEST_RUNNER = hostsim_util.runner()
+    yield
+    models._TEST_RUNNER = None
+    os.environ.pop("NJODE_FORCE_TILE", None)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_training_call(name):
+    parity_util.check_training_call(name, "cpu")
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_training_call_with_hT_gradient(name):
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_path_call(name):
+    parity_util.check_path_call(name, "cpu")
+
+
+@pytest.mark.parametrize("tile", [8, 16, 64])
+@pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small", "curt_nobias_relu"])
+def test_tile_size_invariance(name, tile):
+    os.environ["NJODE_FORCE_TILE"] = str(tile)
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    parity_util.check_path_call(name, "cpu")
+
+
+def test_no_cpu_fallback_without_test_runner():
+    models._TEST_RUNNER = None
+    cfg, meta, sd, batch, outs = cases.load_case("bs_ckpt1")
+    m = parity_util.build_model(cfg, sd, "cpu")
+    with pytest.raises(Exception) as ei:
+        parity_util.call(m, batch, meta, "cpu")
+    assert "CUDA" in str(ei.value)
+
+
+def test_train_mode_dropout_masks_replayed_by_oracle():
+    cfg = cases.demo_cfg(dropout_rate=0.1)
+    batch = cases.grid_batch(24, 1, 20, 0.2, seed=6)
+    parity_util.check_against_oracle(cfg, batch, 0.05, 1.0, seed=2, device="cpu", train=True, grad_hT=True)
+
+
+def test_train_mode_dropout_masked_model():
+    cfg = dict(cases.CONFIGS["masked_small"], dropout_rate=0.25)
+    batch = cases.irregular_batch(6, 5, 10, seed=21, masked=True, times_f32=True)
+    parity_util.check_against_oracle(cfg, batch, 0.05, 1 + 1e-12, seed=3, device="cpu", train=True)
+
+
+def test_physionet_shape_masked():
+    batch = cases.irregular_batch(5, 41, 12, seed=7, masked=True, times_f32=True, obs_at_zero=True,
+                                  row_prob=0.3, feat_prob=0.12)
+    parity_util.check_against_oracle(cases.CONFIGS["masked_physio"], batch, 0.02, 1 + 1e-12, seed=3, device="cpu")
+
+
+def test_global_weight_image_path():
+    """weights too large for shared memory -> parameter / gradient images stay in global memory"""
+    cfg = cases.demo_cfg(input_size=4, output_size=4, hidden_size=128,
+                         ode_nn=[[256, "tanh"], [256, "tanh"]], enc_nn=[[256, "tanh"]],
+                         readout_nn=[[256, "tanh"]])
+    batch = cases.grid_batch(6, 4, 5, 0.4, seed=8)
+    parity_util.check_against_oracle(cfg, batch, 0.2, 1.0, seed=4, device="cpu")
