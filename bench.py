@@ -1,0 +1,455 @@
+#!/usr/bin/env python
+"""bench.py -- NJ-ODE training hot path throughput (train paths x Euler-steps / s, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one forward + backward of the NJ-ODE over one batch (+ the gradient all-reduce when
+N > 1).  Workload at every N (weak scaling, per-GPU work fixed): BASELINE.json configs[1] -- the
+demo architecture (d=1, H=10, 2x50 tanh ode/enc/readout, dropout 0.1, train mode) on Heston paths,
+100 Euler steps, obs_perc 0.1, 20 000 paths per GPU in one batch.  Data are synthetic (seeded
+Euler-Maruyama Heston, NJODE/stock_model.py:181-221 restated), weights random-init (Xavier, seed 0).
+
+Printed JSON (rank 0, one line):
+  value        whole-job paths*steps/s with the collated batch already resident in HBM
+               (CUDA events around every step, max over ranks, L2 flushed between steps)
+  e2e          same metric through the public API `model(times, time_ptr, X, obs_idx, ...)` with
+               HOST tensors: host schedule/CSR build + one pinned H2D copy + fwd + bwd + D2H of the
+               loss inside the timed region
+  roofline     dominant kernel (nj_bwd_kernel): algorithmic fp32 flops / CUDA-event duration over
+               the measured fp32-FMA peak of this GPU (narrow nets are FMA-pipe bound, not HBM /
+               tensor bound: SURVEY.md §8d); the HBM view of the same launch is in roofline.hbm
+  cpu_baseline the oracle port of the reference (oracle/njode_oracle.py, same ATen op sequence as
+               NJODE/models.py) timed on this box's host cores on a bounded sample (N=1 only)
+`--impl reference` times only that CPU port with all host threads (one step = the bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "train_paths_x_euler_steps_per_sec_fwd_bwd"
+UNIT = "paths*steps/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: Heston demo config, same architecture as the BS demo, 20k paths
+    "heston_demo_20k": dict(sde="Heston", paths=20000, steps=100, d=1, H=10, width=50, layers=2,
+                            obs_perc=0.1, dropout=0.1, cpu_sample_paths=2000),
+    "ou_demo_20k": dict(sde="OrnsteinUhlenbeck", paths=20000, steps=100, d=1, H=10, width=50,
+                        layers=2, obs_perc=0.1, dropout=0.1, cpu_sample_paths=2000),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable demo batch
+    "bs_demo_200": dict(sde="BlackScholes", paths=200, steps=100, d=1, H=10, width=50, layers=2,
+                        obs_perc=0.1, dropout=0.1, cpu_sample_paths=200),
+    # BASELINE.json configs[4] architecture on a batch that fits the generic fp32 kernels
+    "bs_scaled_d16_h256": dict(sde="BlackScholes", paths=8192, steps=1000, d=16, H=256, width=256,
+                               layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128,
+                               cpu_sample_steps=100),
+}
+
+SDE_PARAMS = dict(drift=2.0, volatility=0.3, mean=4.0, speed=2.0, correlation=0.5, S0=1.0,
+                  maturity=1.0)          # NJODE/data_utils.py:25-31 (hyperparam_default)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data (host, seeded, vectorised over paths): restates the generators' update rules
+# ------------------------------------------------------------------------------------------------
+def synth_paths(sde, n_paths, steps, d, seed, first_path=0):
+    """f64 [n_paths, d, steps+1]; path i depends only on (seed, first_path + i)."""
+    p = SDE_PARAMS
+    dt = p["maturity"] / steps
+    out = np.empty((n_paths, d, steps + 1))
+    out[:, :, 0] = p["S0"]
+    # one generator per block of 1024 global path ids: identical data for any sharding
+    blk = 1024
+    for b0 in range((first_path // blk) * blk, first_path + n_paths, blk):
+        rng = np.random.default_rng([seed, b0 // blk])
+        z = rng.standard_normal((blk, steps, 2, d))
+        lo, hi = max(b0, first_path), min(b0 + blk, first_path + n_paths)
+        zz = z[lo - b0:hi - b0]
+        S = np.full((hi - lo, d), p["S0"])
+        v = np.full((hi - lo, d), p["mean"])
+        sl = slice(lo - first_path, hi - first_path)
+        for k in range(steps):
+            n1, n2 = zz[:, k, 0], zz[:, k, 1]
+            if sde == "BlackScholes":            # NJODE/stock_model.py:356-375
+                S = S + p["drift"] * S * dt + p["volatility"] * S * n1 * np.sqrt(dt)
+            elif sde == "OrnsteinUhlenbeck":     # NJODE/stock_model.py:397-418
+                S = S - p["speed"] * (S - p["mean"]) * dt + p["volatility"] * n1 * np.sqrt(dt)
+            elif sde == "Heston":                # NJODE/stock_model.py:181-221 (spot uses the NEW variance)
+                dW = n1 * np.sqrt(dt)
+                dZ = (p["correlation"] * n1 + np.sqrt(1 - p["correlation"] ** 2) * n2) * np.sqrt(dt)
+                v = v - p["speed"] * (v - p["mean"]) * dt + p["volatility"] * np.sqrt(np.abs(v)) * dZ
+                S = S + p["drift"] * S * dt + np.sqrt(np.abs(v)) * S * dW
+            else:
+                raise ValueError(sde)
+            out[sl, :, k + 1] = S
+    return out, dt
+
+
+def synth_batch(wl, seed, first_path, n_paths):
+    from njode_b200 import data_utils
+    paths, dt = synth_paths(wl["sde"], n_paths, wl["steps"], wl["d"], seed, first_path)
+    blk = 1024
+    obs = np.empty((n_paths, wl["steps"] + 1), dtype=np.int64)
+    for b0 in range((first_path // blk) * blk, first_path + n_paths, blk):
+        rng = np.random.default_rng([seed + 7919, b0 // blk])
+        u = rng.random((blk, wl["steps"] + 1))
+        lo, hi = max(b0, first_path), min(b0 + blk, first_path + n_paths)
+        obs[lo - first_path:hi - first_path] = (u[lo - b0:hi - b0] < wl["obs_perc"]) * 1
+    obs[:, 0] = 1                                     # NJODE/data_utils.py:80
+    nb_obs = obs[:, 1:].sum(axis=1)
+    b = data_utils.collate_paths(paths, obs, nb_obs, dt)
+    return b, dt
+
+
+def model_cfg(wl):
+    nn_desc = [[wl["width"], "tanh"]] * wl["layers"]
+    return dict(input_size=wl["d"], hidden_size=wl["H"], output_size=wl["d"], ode_nn=nn_desc,
+                readout_nn=nn_desc, enc_nn=nn_desc, use_rnn=False, bias=True,
+                dropout_rate=wl["dropout"], solver="euler", weight=0.5, weight_decay=1.0, options={})
+
+
+def flops_per_unit(wl):
+    """algorithmic fp32 flops: F_ode per path-step, F_enc / F_ro per row; fwd+bwd
+    = 3x fwd (recompute not counted)."""
+    d, H, W, L = wl["d"], wl["H"], wl["width"], wl["layers"]
+    inf = d + H + 2
+    F_ode = 2 * (inf * W + (L - 1) * W * W + W * H)
+    F_enc = 2 * (d * W + (L - 1) * W * W + W * H)
+    F_ro = 2 * (H * W + (L - 1) * W * W + W * d)
+    return F_ode, F_enc, F_ro
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the CPU arm: oracle port of the reference (test infrastructure, used here only as the baseline)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_step_fn(wl, seed, threads):
+    import torch
+    import oracle.njode_oracle as orc
+    torch.set_num_threads(threads)
+    n = wl["cpu_sample_paths"]
+    wl_s = dict(wl)
+    if "cpu_sample_steps" in wl:
+        wl_s["steps"] = wl["cpu_sample_steps"]
+    batch, dt = synth_batch(wl_s, seed, 0, n)
+    cfg = model_cfg(wl)
+    ocfg = orc.Config(**cfg)
+    sd = orc.init_state_dict(ocfg, seed=0)
+    S = len(__import__("njode_b200.schedule", fromlist=["x"]).build_schedule(
+        batch["times"], dt, 1.0, False, False).step_dt)
+
+    def step():
+        orc.loss_and_grads(ocfg, sd, batch, dt, 1.0, dropout_seed="native")
+    sample = "%d of the workload's paths x %d Euler steps, fwd+bwd, train mode (aten dropout), %d threads" % (
+        n, S, threads)
+    return step, n * S, sample
+
+
+def run_reference(args, wl_name, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    step, units, sample = cpu_port_step_fn(wl, 1234, threads)
+    for _ in range(args.warmup):
+        step()
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(ts))
+    val = units / (ms * 1e-3)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl_name, **{k: v for k, v in wl.items() if not k.startswith("cpu_")}},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "torch_threads": torch.get_num_threads()}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, wl_name, wl):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from njode_b200 import models, _ext
+    from njode_b200 import dist as njdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _ext.cuda_lib().dll
+    lib.njode_launch_count.restype = C.c_longlong
+    lib.njode_get_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.njode_fma_peak_launch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    lib.njode_l2_flush.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+
+    B = wl["paths"]                      # per GPU (weak scaling)
+    first = rank * B
+    batch, dt = synth_batch(wl, 1234, first, B)
+    # the Euler grid is batch-global (NJODE/models.py:430-439): all ranks use the union of times.
+    # On the regular grid with >= 20k paths per rank every grid time is observed on every rank.
+    T = SDE_PARAMS["maturity"]
+    torch.manual_seed(0)
+    model = models.NJODE(**model_cfg(wl)).to(dev)
+    model.train()
+    dp = None
+    if world > 1:
+        dp = njdist.DataParallel(model, global_batch_size=B * world)
+        dp.set_batch(B * world, first)
+    params = [p for p in model.parameters()]
+    stream = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def flush():
+        lib.njode_l2_flush(C.c_void_p(flush_buf.data_ptr()), flush_buf.numel(), stream())
+
+    def args_of(b):
+        return (b["times"], b["time_ptr"], b["X"], b["obs_idx"], dt, T, b["start_X"], b["n_obs_ot"])
+
+    # ---- resident-input arm -----------------------------------------------------------------
+    model.output_device = "cuda"
+    pb = model.prepare_batch(*args_of(batch))
+    S = pb.sched.S
+    units_per_step = B * S * world
+
+    def step_resident():
+        for p in params:
+            p.grad = None
+        hT, loss = model.forward_prepared(pb)
+        loss.backward()
+        return loss
+
+    lib.njode_set_timing(1)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.njode_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kf, kb = [], []
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush()
+        ev[i][0].record()
+        step_resident()
+        ev[i][1].record()
+        if i < 8:                       # per-kernel CUDA-event durations (C ABI, launching stream)
+            f, b_ = C.c_float(), C.c_float()
+            lib.njode_get_timing(C.byref(f), C.byref(b_))
+            kf.append(f.value); kb.append(b_.value)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = lib.njode_launch_count() - launches0
+    step_ms = [a.elapsed_time(b_) for a, b_ in ev]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = units_per_step / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: public API, host tensors ---------------------------------------------
+    model.output_device = "cpu"
+    nb = 3
+    host_batches = [synth_batch(wl, 4321 + j, first, B)[0] for j in range(nb)]
+
+    def step_e2e(b):
+        for p in params:
+            p.grad = None
+        hT, loss = model(*args_of(b))
+        loss.backward()
+        return float(loss)                # D2H of the step's result
+
+    for j in range(2):
+        step_e2e(host_batches[j % nb])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    h2d = 0
+    for j in range(n_e2e):
+        step_e2e(host_batches[j % nb])
+        h2d += model.last_h2d_bytes
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_val = units_per_step * n_e2e / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    N_rows = pb.N
+    F_ode, F_enc, F_ro = flops_per_unit(wl)
+    fwd_flops = B * S * F_ode + N_rows * (F_enc + 2 * F_ro) + B * F_enc
+    bwd_flops = 2 * fwd_flops
+    # measured fp32 FMA peak of this GPU (dependent FFMA chains on every SM)
+    scratch = torch.empty(148 * 8 * 256 * 2, dtype=torch.float32, device=dev)
+    fm = C.c_double()
+    peak = 0.0
+    for it in range(4):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        lib.njode_fma_peak_launch(C.c_void_p(scratch.data_ptr()), 4096, C.byref(fm), stream())
+        b_.record()
+        torch.cuda.synchronize()
+        peak = max(peak, 2.0 * fm.value / (a.elapsed_time(b_) * 1e-3) / 1e12)
+    bwd_ms = float(np.median(kb)) if kb else float("nan")
+    fwd_ms = float(np.median(kf)) if kf else float("nan")
+    achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12
+    H = wl["H"]
+    alg_bytes_bwd = 4 * (S * B * H + N_rows * (H + 2 * wl["d"]) + B * wl["d"]) + 4 * model._flat.numel()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"kernel": "nj_bwd_kernel", "bound": "fp32_fma", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": "measured in this run (njode_fma_peak_launch: FFMA chains on all SMs)",
+                "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
+                "fwd_achieved": fwd_flops / (fwd_ms * 1e-3) / 1e12,
+                "flops_per_launch": bwd_flops,
+                "hbm": {"bound": "hbm", "achieved": alg_bytes_bwd / (bwd_ms * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes_bwd / (bwd_ms * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl_name, "sde": wl["sde"], "paths_per_gpu": B, "euler_steps": S,
+                      "obs_rows_per_gpu": N_rows, "input_size": wl["d"], "hidden_size": H,
+                      "mlp": "%dx%d tanh" % (wl["layers"], wl["width"]), "dropout": wl["dropout"],
+                      "mode": "train", "parallelism": "dp%d" % world,
+                      "l2": "flushed between timed steps (256 MiB write)"},
+           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d / n_e2e),
+                   "d2h_bytes_per_step": 4, "steps": n_e2e},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+           "wall_s_timed_region": wall}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        step, units, sample = cpu_port_step_fn(wl, 1234, threads)
+        step()
+        ts = []
+        t_end = time.perf_counter() + 20.0
+        while len(ts) < 3 or (time.perf_counter() < t_end and len(ts) < 8):
+            t0 = time.perf_counter()
+            step()
+            ts.append(time.perf_counter() - t0)
+        out["cpu_baseline"] = {"value": units / float(np.median(ts)), "unit": UNIT, "cores": threads,
+                               "kind": "port", "sample": sample}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="heston_demo_20k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, args.workload, wl)
+    else:
+        run_b200(args, args.workload, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,8 @@ int njode_collate(const double* paths, const int32_t* observed, int64_t n_paths_
  * the launching stream); enable with njode_set_timing(1) or NJODE_TIMING=1. */
 void njode_set_timing(int on);
 int njode_get_timing(float* fwd_ms, float* bwd_ms);
+/* kernels launched by this library since it was loaded (bench.py: gpu_launches) */
+long long njode_launch_count(void);
 /* fp32 FMA-pipe microbenchmark: dependent chains of FFMA on every SM; *fmas = lane-FMAs issued */
 int njode_fma_peak_launch(float* scratch, int iters, double* fmas, void* stream);
 /* writes `bytes` of buf (size it > L2) so the next kernel starts with a cold L2 */

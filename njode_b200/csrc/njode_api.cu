@@ -17,6 +17,11 @@ static int nj_fail(int code, const std::string& msg) { g_err = msg; return code;
 extern "C" const char* njode_last_error(void) { return g_err.c_str(); }
 extern "C" int njode_abi_version(void) { return NJODE_ABI_VERSION; }
 
+// number of kernels this library has launched (bench.py reports it as gpu_launches)
+static long long g_launches = 0;
+extern "C" long long njode_launch_count(void) { return g_launches; }
+#define NJ_LAUNCHED(n) (g_launches += (n))
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
@@ -172,6 +177,7 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     a.get_loss = loss ? 1 : 0;
     a.n_tiles = pl.n_tiles;
     nj_pack_kernel<<<3 * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.fwd, params, const_cast<float*>(a.image));
+    NJ_LAUNCHED(1 + (batch->n_units > 0 ? 1 : 0) + (loss ? 1 : 0));
     if (loss && batch->N > 0) NJ_CUDA(cudaMemsetAsync(a.row_loss, 0, (size_t)batch->N * 4, st));
     NJ_CUDA(cudaFuncSetAttribute(nj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd_bytes));
     const bool tm = nj_timing_on();
@@ -203,6 +209,7 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     a.n_tiles = pl.n_tiles;
     // the image is rebuilt: backward may run after an optimizer that shares the workspace
     nj_pack_kernel<<<3 * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.bwd, params, const_cast<float*>(a.image));
+    NJ_LAUNCHED(2 + (batch->n_units > 0 ? 1 : 0));
     NJ_CUDA(cudaFuncSetAttribute(nj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd_bytes));
     int nparts = 0;
     const bool tm = nj_timing_on();

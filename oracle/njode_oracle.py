@@ -199,7 +199,8 @@ def forward(cfg, sd, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
     (fp32 = the reference's arithmetic; fp64 = high-precision evaluation of the same function; the
     scalars the reference rounds to fp32 -- delta_t_, current_time, obs_time -- are rounded here
     too so both precisions evaluate the same function).
-    ``dropout_seed``: None = eval mode; int = train mode with the device's counter-based masks.
+    ``dropout_seed``: None = eval mode; int = train mode with the device's counter-based masks;
+    "native" = train mode with torch's own dropout stream (as the reference draws it).
     """
     dt_ = start_X.dtype
     p = cfg.dropout_rate
@@ -210,6 +211,11 @@ def forward(cfg, sd, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
     def dropper(net, event, rows):
         if dropout_seed is None or p == 0.0:
             return None
+        if dropout_seed == "native":
+            # the reference's own masks: torch.nn.Dropout -> aten::bernoulli_ (NJODE/models.py:160,164);
+            # used by bench.py's CPU baseline so the port runs the reference's op sequence
+            return lambda layer, width: torch.nn.functional.dropout(
+                torch.ones(len(rows), width, dtype=dt_), p, True)
 
         def f(layer, width):
             keep = dropout_keep_mask(dropout_seed, rows, event, net, layer, width, p)
