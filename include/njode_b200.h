@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define NJODE_ABI_VERSION 1
+#define NJODE_ABI_VERSION 2
 #define NJODE_MAX_LINEAR 8          /* max number of Linear layers per network */
 
 enum { NJODE_ACT_NONE = 0, NJODE_ACT_TANH = 1, NJODE_ACT_RELU = 2 };
@@ -65,6 +65,10 @@ typedef struct njode_batch {
     int32_t batch_size_norm;   /* batch size used in the loss normalisation (global B under DP) */
     int32_t path_id_offset;    /* global id of local path 0 (dropout keys are rank-invariant) */
     int32_t n_units;           /* work units, see unit_desc */
+    int32_t unit_kind;         /* 0: whole paths; 1: (path, inter-observation segment) units -- each loss
+                                  unit ends with exactly one jump (c1 = c0 + 1, s1 = jump_step of its row),
+                                  tail units have none; enables the segment fast path (non-masked model) */
+    int32_t reserved0;
     const float*   X;          /* [N, input_size] */
     const float*   M;          /* [N, input_size] or NULL */
     const float*   start_X;    /* [B, input_size] */

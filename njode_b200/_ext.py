@@ -32,7 +32,7 @@ class ModelT(C.Structure):
 class BatchT(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("S", C.c_int32),
                 ("E", C.c_int32), ("batch_size_norm", C.c_int32), ("path_id_offset", C.c_int32),
-                ("n_units", C.c_int32),
+                ("n_units", C.c_int32), ("unit_kind", C.c_int32), ("reserved0", C.c_int32),
                 ("X", C.c_void_p), ("M", C.c_void_p), ("start_X", C.c_void_p), ("n_obs_ot", C.c_void_p),
                 ("path_ptr", C.c_void_p), ("path_rows", C.c_void_p), ("row_jump", C.c_void_p),
                 ("step_dt", C.c_void_p), ("step_t", C.c_void_p), ("jump_step", C.c_void_p),
@@ -89,7 +89,7 @@ class Lib:
                                      C.c_void_p, C.c_void_p]
         for f in (d.njode_plan, d.njode_forward, d.njode_backward):
             f.restype = C.c_int
-        if d.njode_abi_version() != 1:
+        if d.njode_abi_version() != 2:
             raise NjodeError("njode_b200: ABI version mismatch in %s" % path)
 
     def check(self, rc, what):
@@ -202,7 +202,7 @@ class Runner:
         def make(n_units):
             return BatchT(B=B, N=N, K=sched.K, S=sched.S, E=sched.E,
                           batch_size_norm=int(batch_size_norm or B), path_id_offset=int(path_id_offset),
-                          n_units=int(n_units), X=p("X"), M=p("M"), start_X=p("start_X"),
+                          n_units=int(n_units), unit_kind=1 if segments else 0, X=p("X"), M=p("M"), start_X=p("start_X"),
                           n_obs_ot=p("n_obs_ot"), path_ptr=p("path_ptr"), path_rows=p("path_rows"),
                           row_jump=p("row_jump"), step_dt=p("step_dt"), step_t=p("step_t"),
                           jump_step=p("jump_step"), jump_tau=p("jump_tau"), step_event=p("step_event"),

@@ -35,12 +35,39 @@ __global__ void __launch_bounds__(256) nj_bwd_kernel(const __grid_constant__ NjC
     nj_cta_backward(cfg, args, nj_smem, blockIdx.x, gridDim.x);
 }
 
+template <int TR>
+__global__ void __launch_bounds__(TR == 4 ? 384 : 512) nj_seg_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+                                                         const __grid_constant__ NjArgs args) {
+    nj_seg_cta_forward_t<TR>(cfg, seg, args, nj_smem);
+}
+
+template <int TR>
+__global__ void __launch_bounds__(384) nj_seg_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+                                                         const __grid_constant__ NjArgs args) {
+    nj_seg_cta_backward_t<TR>(cfg, seg, args, nj_smem, blockIdx.x);
+}
+
+template <int TR>
+static cudaError_t nj_launch_seg_fwd(const NjPlanOut& pl, const NjArgs& a, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(nj_seg_fwd_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes);
+    if (e != cudaSuccess) return e;
+    nj_seg_fwd_kernel<TR><<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
+    return cudaSuccess;
+}
+template <int TR>
+static cudaError_t nj_launch_seg_bwd(const NjPlanOut& pl, const NjArgs& a, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(nj_seg_bwd_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes);
+    if (e != cudaSuccess) return e;
+    nj_seg_bwd_kernel<TR><<<pl.seg_grid_b, pl.seg.nw_b * 32, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
+    return cudaSuccess;
+}
+
 // flat parameters -> zero-padded image; one block per (net, layer)
 __global__ void nj_pack_kernel(const __grid_constant__ NjCfg cfg, const float* __restrict__ params, float* __restrict__ image) {
     const int n = blockIdx.x / NJODE_MAX_LINEAR, l = blockIdx.x % NJODE_MAX_LINEAR;
     const NjNet& N = cfg.net[n];
     if (l >= N.n) return;
-    const int K = N.dim[l], O = N.dim[l + 1], ks = N.ks[l], rows = 4 * N.og[l];
+    const int K = N.dim[l], O = N.dim[l + 1], ks = N.ks[l], rows = N.rp[l];
     for (int i = threadIdx.x; i < rows * ks; i += blockDim.x) {
         const int o = i / ks, k = i % ks;
         image[N.w_img[l] + i] = (o < O && k < K) ? params[N.w_src[l] + (long long)o * K + k] : 0.f;
@@ -130,6 +157,7 @@ static int nj_plan_for(const njode_model_t* model, const njode_batch_t* b, int d
     const char* fp = getenv("NJODE_FORCE_TILE");
     if (!nj_make_plan(*model, b->n_units, b->n_units, b->N, di.sms, di.smem_optin, fp ? atoi(fp) : 0, out, err))
         return nj_fail(-3, err);
+    nj_make_seg(out.fwd, b->unit_kind, b->E, b->n_units, di.sms, di.smem_optin, out);
     // gradient partials: sized for the largest grid any backward launch of this model may use
     const size_t cap = (size_t)di.sms * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
@@ -154,6 +182,7 @@ static void nj_fill_args(NjArgs& a, const njode_batch_t* b, const NjPlanOut& pl,
     a.image = reinterpret_cast<const float*>(ws + pl.ws_image_off);
     a.row_loss = reinterpret_cast<float*>(ws + pl.ws_rowloss_off);
     a.partials = reinterpret_cast<float*>(ws + pl.ws_partials_off);
+    a.counter = reinterpret_cast<int*>(ws + pl.ws_counter_off);
 }
 
 extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* batch, const float* params,
@@ -179,11 +208,19 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     nj_pack_kernel<<<3 * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.fwd, params, const_cast<float*>(a.image));
     NJ_LAUNCHED(1 + (batch->n_units > 0 ? 1 : 0) + (loss ? 1 : 0));
     if (loss && batch->N > 0) NJ_CUDA(cudaMemsetAsync(a.row_loss, 0, (size_t)batch->N * 4, st));
-    NJ_CUDA(cudaFuncSetAttribute(nj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd_bytes));
     const bool tm = nj_timing_on();
-    if (tm) cudaEventRecord(g_ev[0], st);
-    if (batch->n_units > 0)
-        nj_fwd_kernel<<<pl.grid_fwd, pl.fwd.nt, pl.smem_fwd_bytes, st>>>(pl.fwd, a);
+    if (pl.seg.ok) {
+        NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
+        if (tm) cudaEventRecord(g_ev[0], st);
+        if (pl.seg.tr_f == 4) NJ_CUDA(nj_launch_seg_fwd<4>(pl, a, st));
+        else if (pl.seg.tr_f == 2) NJ_CUDA(nj_launch_seg_fwd<2>(pl, a, st));
+        else NJ_CUDA(nj_launch_seg_fwd<1>(pl, a, st));
+    } else {
+        NJ_CUDA(cudaFuncSetAttribute(nj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd_bytes));
+        if (tm) cudaEventRecord(g_ev[0], st);
+        if (batch->n_units > 0)
+            nj_fwd_kernel<<<pl.grid_fwd, pl.fwd.nt, pl.smem_fwd_bytes, st>>>(pl.fwd, a);
+    }
     if (tm) { cudaEventRecord(g_ev[1], st); g_ev_rec[0] = true; }
     if (loss) nj_loss_reduce_kernel<<<1, 256, 0, st>>>(a.row_loss, batch->N, 1.f / (float)batch->batch_size_norm, loss);
     NJ_CUDA(cudaGetLastError());
@@ -210,13 +247,21 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     // the image is rebuilt: backward may run after an optimizer that shares the workspace
     nj_pack_kernel<<<3 * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.bwd, params, const_cast<float*>(a.image));
     NJ_LAUNCHED(2 + (batch->n_units > 0 ? 1 : 0));
-    NJ_CUDA(cudaFuncSetAttribute(nj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd_bytes));
     int nparts = 0;
     const bool tm = nj_timing_on();
-    if (tm) cudaEventRecord(g_ev[2], st);
-    if (batch->n_units > 0) {
-        nparts = pl.grid_bwd;
-        nj_bwd_kernel<<<pl.grid_bwd, pl.bwd.nt, pl.smem_bwd_bytes, st>>>(pl.bwd, a);
+    if (pl.seg.ok) {
+        NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
+        if (tm) cudaEventRecord(g_ev[2], st);
+        nparts = pl.seg_grid_b;
+        if (pl.seg.tr_b == 2) NJ_CUDA(nj_launch_seg_bwd<2>(pl, a, st));
+        else NJ_CUDA(nj_launch_seg_bwd<1>(pl, a, st));
+    } else {
+        NJ_CUDA(cudaFuncSetAttribute(nj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd_bytes));
+        if (tm) cudaEventRecord(g_ev[2], st);
+        if (batch->n_units > 0) {
+            nparts = pl.grid_bwd;
+            nj_bwd_kernel<<<pl.grid_bwd, pl.bwd.nt, pl.smem_bwd_bytes, st>>>(pl.bwd, a);
+        }
     }
     if (tm) { cudaEventRecord(g_ev[3], st); g_ev_rec[1] = true; }
     dim3 g((unsigned)std::max(1, std::min(64, (int)((model->n_params + 255) / 256))), 3 * NJODE_MAX_LINEAR);

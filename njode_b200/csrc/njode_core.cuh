@@ -49,7 +49,10 @@ struct NjNet {
     int dim[NJODE_MAX_LINEAR + 1];
     int act[NJODE_MAX_LINEAR];
     int ks[NJODE_MAX_LINEAR];           // padded row stride of W_l inside the image
-    int og[NJODE_MAX_LINEAR];           // ceil(out/4): the image holds 4*og rows (zero padded)
+    int og[NJODE_MAX_LINEAR];           // ceil(out/4)
+    int rp[NJODE_MAX_LINEAR];           // rows of W_l held by the image (zero padded) = nch * 8 * to >= out
+    int to[NJODE_MAX_LINEAR];           // outputs per lane and chunk of the warp GEMM (njode_seg.cuh), 1..8
+    int nch[NJODE_MAX_LINEAR];          // output chunks of 8 * to rows
     int w_img[NJODE_MAX_LINEAR];        // float offsets inside the image
     int b_img[NJODE_MAX_LINEAR];
     long long w_src[NJODE_MAX_LINEAR];  // float offsets inside the flat parameter buffer
@@ -97,15 +100,31 @@ NJ_HD unsigned nj_row_key(unsigned seed_lo, unsigned seed_hi, unsigned path, uns
     return nj_fmix32(nj_fmix32(path ^ seed_lo) + event * 0x9E3779B9u) ^ seed_hi;
 }
 NJ_HD unsigned nj_layer_key(unsigned row_key, unsigned tag) { return nj_fmix32(row_key + tag * 0x85EBCA77u); }
-NJ_HD bool nj_keep(unsigned layer_key, unsigned neuron, unsigned thr) {
-    return nj_fmix32(layer_key + neuron * 0xC2B2AE3Du) >= thr;
+// one 32-bit hash word serves the two neurons o and o ^ 8 (16-bit fields): word index
+// (o & 7) | ((o >> 4) << 3), field (o >> 3) & 1; keep iff field >= thr16 = floor(p * 65536).
+NJ_HD unsigned nj_keep_word(unsigned layer_key, unsigned widx) { return nj_fmix32(layer_key + widx * 0xC2B2AE3Du); }
+NJ_HD bool nj_keep(unsigned layer_key, unsigned neuron, unsigned thr16) {
+    const unsigned w = nj_keep_word(layer_key, (neuron & 7u) | ((neuron >> 4) << 3));
+    return (((neuron >> 3) & 1u) ? (w >> 16) : (w & 0xFFFFu)) >= thr16;
 }
 #define NJ_EVENT_JUMP_BASE 0x40000000u
 #define NJ_EVENT_PATH_RO_BASE 0x20000000u
 #define NJ_EVENT_INIT 0x7FFFFFFFu
 
+// tanh(x) = 1 - 2 / (exp(2x) + 1): two MUFU ops (ex2, rcp) + three FMA-pipe ops; absolute error
+// <= ~2e-7 over the whole range (saturates correctly at +-1), versus ~20 instructions for tanhf.
+NJ_HD float nj_tanh(float x) {
+#if defined(NJODE_HOST_SIM)
+    return 1.f - 2.f / (exp2f(x * 2.8853900817779268f) + 1.f);
+#else
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return fmaf(-2.f, r, 1.f);
+#endif
+}
 NJ_HD float nj_act(float v, int act) {
-    if (act == NJODE_ACT_TANH) return tanhf(v);
+    if (act == NJODE_ACT_TANH) return nj_tanh(v);
     if (act == NJODE_ACT_RELU) return v > 0.f ? v : 0.f;
     return v;
 }
@@ -307,6 +326,7 @@ struct NjArgs {
     float* h_hist; float* h_before; float* y_after;      // forward: written; backward: read
     const float* grad_loss; const float* grad_hT;
     float* partials;           // [grid][img_floats] gradient partial images (backward)
+    int* counter;              // tile counter of the segment kernels (zeroed before every launch)
     int n_tiles;
     int get_loss;
 };
@@ -472,8 +492,8 @@ NJ_HD void nj_build_ode_input(NjCta& t, int u, int c_, float hval, float tcur) {
     const NjCfg& c = *t.c;
     float* row = t.IN + (size_t)u * c.sIN;
     const float tau = NJ_FU(t, NJ_F_TAU, u);
-    if (c_ < c.d) row[c_] = tanhf(t.LX[u * c.sD + c_]);
-    else if (c_ < c.d + c.H) row[c_] = tanhf(hval);
+    if (c_ < c.d) row[c_] = nj_tanh(t.LX[u * c.sD + c_]);
+    else if (c_ < c.d + c.H) row[c_] = nj_tanh(hval);
     else if (c_ == c.d + c.H) row[c_] = tau;
     else if (c_ == c.d + c.H + 1) row[c_] = tcur - tau;
     else row[c_] = tau + (tcur - tau);
@@ -489,7 +509,7 @@ NJ_HDN void nj_record(NjCta& t, const NjArgs& a, int nu, int e, unsigned event_k
             const int u = idx / c.H, c_ = idx % c.H;
             const int p = NJ_IU(t, NJ_I_PATH, u);
             const float h = t.Hs[u * c.sH + c_];
-            t.IN[(size_t)u * c.sIN + c_] = tanhf(h);
+            t.IN[(size_t)u * c.sIN + c_] = nj_tanh(h);
             a.path_h[((size_t)e * a.b.B + p) * c.H + c_] = h;
             if (c_ == 0) NJ_IU(t, NJ_I_RK, u) = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), event_key);
         }
@@ -562,7 +582,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
             const int jr = idx / c.H, c_ = idx % c.H;
             const int u = NJ_IU(t, NJ_I_JMAP, jr);
             const float h = t.Hs[u * c.sH + c_];
-            t.IN[(size_t)jr * c.sIN + c_] = tanhf(h);
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(h);
             t.XH[jr * c.sH + c_] = h;
             if (a.h_before) a.h_before[(size_t)NJ_IU(t, NJ_I_JROW, jr) * c.H + c_] = h;
         }
@@ -591,7 +611,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
                 t.IN[(size_t)jr * c.sIN + c.d + c_] = m;
             }
             t.XI[jr * c.sD + c_] = x;
-            t.IN[(size_t)jr * c.sIN + c_] = tanhf(x);
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(x);
         }
         nj_set_jump_keys(t, a, nj, 1, tid);
     }
@@ -605,7 +625,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
             float e = t.OUT[jr * c.sOUT + c_];
             if (c.residual) e += nj_resid(t.XI + jr * c.sD, c.d, c.H, c_);
             t.Hs[u * c.sH + c_] = e;
-            t.IN[(size_t)jr * c.sIN + c_] = tanhf(e);
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(e);
         }
         nj_set_jump_keys(t, a, nj, 2, tid);
     }
@@ -682,7 +702,7 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
                 const float x = sr < 0 ? NJ_LDG(a.b.start_X + (size_t)NJ_IU(t, NJ_I_PATH, u) * c.d + c_)
                                        : NJ_LDG(a.b.X + (size_t)sr * c.d + c_);
                 t.XI[u * c.sD + c_] = x;
-                t.IN[(size_t)u * c.sIN + c_] = tanhf(x);
+                t.IN[(size_t)u * c.sIN + c_] = nj_tanh(x);
                 if (c.masked) t.IN[(size_t)u * c.sIN + c.d + c_] = 0.f;
             }
             if (tid < nu) {
@@ -787,7 +807,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
             const int jr = idx / c.H, c_ = idx % c.H;
             const float h = a.h_before[(size_t)NJ_IU(t, NJ_I_JROW, jr) * c.H + c_];
             t.XH[jr * c.sH + c_] = h;
-            t.IN[(size_t)jr * c.sIN + c_] = tanhf(h);
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(h);
         }
         nj_set_jump_keys(t, a, nj, 0, tid);
     }
@@ -814,7 +834,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
                 t.IN[(size_t)jr * c.sIN + c.d + c_] = m;
             }
             t.XI[jr * c.sD + c_] = x;
-            t.IN[(size_t)jr * c.sIN + c_] = tanhf(x);
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(x);
         }
         nj_set_jump_keys(t, a, nj, 1, tid);
     }
@@ -826,7 +846,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
             float e = t.OUT[jr * c.sOUT + c_];
             if (c.residual) e += nj_resid(t.XI + jr * c.sD, c.d, c.H, c_);
             t.EE[jr * c.sH + c_] = e;
-            t.IN[(size_t)jr * c.sIN + c_] = tanhf(e);
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(e);
         }
         nj_set_jump_keys(t, a, nj, 2, tid);
     }
@@ -898,7 +918,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
             const int jr = idx / c.d, c_ = idx % c.d;
-            t.IN[(size_t)jr * c.sIN + c_] = tanhf(t.XI[jr * c.sD + c_]);
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.XI[jr * c.sD + c_]);
             if (c.masked) t.IN[(size_t)jr * c.sIN + c.d + c_] = NJ_LDG(a.b.M + (size_t)NJ_IU(t, NJ_I_JROW, jr) * c.d + c_);
         }
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
@@ -927,7 +947,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
             const int jr = idx / c.H, c_ = idx % c.H;
-            t.IN[(size_t)jr * c.sIN + c_] = tanhf(t.XH[jr * c.sH + c_]);
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.XH[jr * c.sH + c_]);
         }
         for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
             const int jr = idx / c.dout, c_ = idx % c.dout;
@@ -1038,7 +1058,7 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
                 const int sr = NJ_IU(t, NJ_I_START, u);
                 const float x = sr < 0 ? NJ_LDG(a.b.start_X + (size_t)NJ_IU(t, NJ_I_PATH, u) * c.d + c_)
                                        : NJ_LDG(a.b.X + (size_t)sr * c.d + c_);
-                t.IN[(size_t)u * c.sIN + c_] = tanhf(x);
+                t.IN[(size_t)u * c.sIN + c_] = nj_tanh(x);
                 if (c.masked) t.IN[(size_t)u * c.sIN + c.d + c_] = 0.f;
             }
             for (int idx = tid; idx < nu * c.H; idx += t.nt) {

@@ -4,13 +4,17 @@
 #include <string>
 #include <algorithm>
 #include "njode_core.cuh"
+#include "njode_seg.cuh"
 
 struct NjPlanOut {
     NjCfg fwd, bwd;
+    NjSeg seg;                      // seg.ok: the segment fast path (njode_seg.cuh) serves this call
+    int seg_grid_f, seg_grid_b;
+    size_t seg_smem_f_bytes, seg_smem_b_bytes;
     int n_tiles;
     int grid_fwd, grid_bwd;
     size_t smem_fwd_bytes, smem_bwd_bytes;
-    size_t ws_image_off, ws_rowloss_off, ws_partials_off, ws_bytes;
+    size_t ws_image_off, ws_rowloss_off, ws_counter_off, ws_partials_off, ws_bytes;
 };
 
 static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, std::string& err) {
@@ -29,8 +33,13 @@ static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, std::string& e
             if (l < s.n_linear - 1 && s.act[l] != NJODE_ACT_TANH && s.act[l] != NJODE_ACT_RELU) { err = "unknown activation"; return false; }
             N.ks[l] = nj_stride_host(s.dims[l]);
             N.og[l] = (s.dims[l + 1] + 3) / 4;
-            N.w_img[l] = off; off += 4 * N.og[l] * N.ks[l];
-            N.b_img[l] = off; off += 4 * N.og[l];
+            const int o8 = (s.dims[l + 1] + 7) / 8;
+            N.nch[l] = (o8 + 7) / 8;
+            N.to[l] = (o8 + N.nch[l] - 1) / N.nch[l];
+            if (N.nch[l] > 1 && (N.to[l] & 1)) N.to[l] += 1;      // chunk bases stay multiples of 16 (hash pairs)
+            N.rp[l] = N.nch[l] * 8 * N.to[l];
+            N.w_img[l] = off; off += N.rp[l] * N.ks[l];
+            N.b_img[l] = off; off += N.rp[l];
             N.w_src[l] = s.w_off[l]; N.b_src[l] = s.b_off[l];
         }
     }
@@ -95,8 +104,8 @@ static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, std::string& er
     c.has_drop = (m.training && p > 0.f) ? 1 : 0;
     c.one_minus_p = 1.f - p;
     c.keep_scale = (p < 1.f) ? 1.f / (1.f - p) : 0.f;
-    double thr = (double)p * 4294967296.0;
-    c.thr = thr >= 4294967295.0 ? 4294967295u : (unsigned)thr;
+    double thr = (double)p * 65536.0;
+    c.thr = thr >= 65536.0 ? 65536u : (unsigned)thr;          // 16-bit fields, see nj_keep
     c.seed_lo = (unsigned)(m.dropout_seed & 0xFFFFFFFFull); c.seed_hi = (unsigned)(m.dropout_seed >> 32);
     int maxhid = 1, maxin = 1, maxn = 1;
     for (int n = 0; n < 3; ++n) {
@@ -156,7 +165,126 @@ static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_u
     size_t o = 0;
     out.ws_image_off = o; o += (size_t)base.img_floats * 4; o = (o + 255) & ~(size_t)255;
     out.ws_rowloss_off = o; o += (size_t)std::max(N_rows, 1) * 4; o = (o + 255) & ~(size_t)255;
+    out.ws_counter_off = o; o += 256;
     out.ws_partials_off = o; o += (size_t)out.grid_bwd * base.img_floats * 4;
     out.ws_bytes = o;
     return true;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// segment fast path (njode_seg.cuh): eligibility + shared-memory layout
+// ------------------------------------------------------------------------------------------------
+static inline int nj_seg_fwd_region(const NjCfg& c, NjSeg& s, int R) {
+    (void)c;
+    int o = 0;
+    s.f_IN = o; o += R * s.sI;
+    s.f_A0 = o; o += R * s.sA;
+    s.f_A1 = o; o += R * s.sA;
+    s.f_OUT = o; o += R * s.sO;
+    s.f_HS = o; o += R * s.sH;
+    s.f_LX = o; o += R * s.sD;
+    s.f_TX = o; o += R * s.sD;
+    s.f_XI = o; o += R * s.sD;
+    s.f_YBJ = o; o += R * s.sD;
+    s.f_F = o; o += NJS_F_COUNT * R;
+    s.f_I = o; o += NJS_I_COUNT * R + 4;
+    return (o + 3) & ~3;
+}
+
+static inline int nj_seg_bwd_layout(const NjCfg& c, NjSeg& s, int P) {
+    int o = c.img_floats;
+    s.b_img = 0;
+    s.b_IN = o; o += P * s.sI;
+    s.b_A = o; o += s.nA * P * s.sA;
+    s.b_G = o; o += s.nA * P * s.sA;
+    s.b_GOUT = o; o += P * s.sO;
+    s.b_GZ = o; o += P * s.sI;
+    s.b_OUT = o; o += P * s.sO;
+    s.b_GH = o; o += P * s.sH;
+    s.b_HB = o; o += P * s.sH;
+    s.b_EE = o; o += P * s.sH;
+    s.b_GE = o; o += P * s.sH;
+    s.b_XI = o; o += P * s.sD;
+    s.b_LX = o; o += P * s.sD;
+    s.b_TX = o; o += P * s.sD;
+    s.b_YBJ = o; o += P * s.sD;
+    s.b_YY = o; o += P * s.sD;
+    s.b_GYBJ = o; o += P * s.sD;
+    s.b_F = o; o += NJS_F_COUNT * P;
+    s.b_I = o; o += NJS_I_COUNT * P + 4;
+    return (o + 3) & ~3;
+}
+
+static inline void nj_make_seg(const NjCfg& c, int unit_kind, int E, int n_units, int num_sms, size_t smem_limit,
+                               NjPlanOut& out) {
+    NjSeg& s = out.seg;
+    memset(&s, 0, sizeof(s));
+    const char* off = getenv("NJODE_NO_SEG");
+    if (off && atoi(off)) return;
+    if (unit_kind != 1 || c.masked || E > 0 || n_units <= 0) return;
+    int maxhid = 1, maxn = 1, maxlast = 1;
+    for (int n = 0; n < 3; ++n) {
+        const NjNet& N = c.net[n];
+        maxn = std::max(maxn, N.n);
+        for (int l = 0; l < N.n - 1; ++l) maxhid = std::max(maxhid, N.rp[l]);
+        maxlast = std::max(maxlast, N.rp[N.n - 1]);
+    }
+    s.sI = nj_stride_act(std::max(std::max(c.inf, c.enc_in), c.H));
+    s.sA = nj_stride_act(maxhid);
+    s.sO = nj_stride_act(maxlast);
+    s.sH = (c.H + 3) & ~3; s.sD = (std::max(c.d, c.dout) + 3) & ~3;
+    s.nA = std::max(1, maxn - 1);
+    // dW tiles: order ODE, RO, ENC
+    static const int order[3] = {NJODE_NET_ODE, NJODE_NET_RO, NJODE_NET_ENC};
+    int tiles = 0;
+    for (int oi = 0; oi < 3; ++oi) {
+        const NjNet& N = c.net[order[oi]];
+        for (int l = 0; l < NJODE_MAX_LINEAR; ++l) {
+            s.tile_base[order[oi]][l] = tiles;
+            if (l < N.n) tiles += ((N.dim[l] + 3) / 4) * ((N.dim[l + 1] + 3) / 4);
+        }
+    }
+    s.tiles_total = tiles;
+    const char* ftr = getenv("NJODE_FORCE_TR");
+    const int force_tr = ftr ? atoi(ftr) : 0;
+    // ---- forward: per-warp regions of R = 4*TR rows; smaller tiles when the batch cannot fill the GPU ----
+    {
+        int tr = 4;
+        while (tr > 1 && (n_units + 4 * tr - 1) / (4 * tr) < num_sms * 8) tr >>= 1;
+        if (force_tr) tr = std::min(4, force_tr);
+        s.tr_f = tr;
+        const int R = 4 * tr;
+        s.f_region = nj_seg_fwd_region(c, s, R);
+        s.f_img = 0; s.f_warp0 = c.img_floats;
+        int nw = 0;
+        for (int cand = (tr == 4 ? 12 : 16); cand >= 2; --cand)          // launch bounds: 384 (TR=4) / 512 threads
+            if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
+        if (!nw) return;
+        s.nw_f = nw;
+        s.f_smem_floats = c.img_floats + nw * s.f_region;
+        s.n_tiles_f = (n_units + R - 1) / R;
+    }
+    // ---- backward: CTA-level arrays of P = R * nw rows ----
+    {
+        const int min_nw = (tiles + NJ_SEG_NT_MAX * 32 - 1) / (NJ_SEG_NT_MAX * 32);
+        int tr = 2, nw = 0;
+        if (force_tr) tr = std::min(2, force_tr);
+        for (; tr >= 1 && !nw; tr >>= 1) {
+            for (int cand = 12; cand >= std::max(2, min_nw); --cand) {       // launch bounds: 384 threads
+                const int fl = nj_seg_bwd_layout(c, s, 4 * tr * cand);
+                if ((size_t)fl * 4 <= smem_limit) { nw = cand; s.b_smem_floats = fl; s.P_b = 4 * tr * cand; s.tr_b = tr; break; }
+            }
+            if (nw && tr == 2 && !force_tr && (n_units + s.P_b - 1) / s.P_b < num_sms) nw = 0;   // too few CTA tiles: halve the rows
+        }
+        if (!nw) return;
+        s.nw_b = nw;
+        s.nt_slots = (tiles + nw * 32 - 1) / (nw * 32);
+        s.n_tiles_b = (n_units + s.P_b - 1) / s.P_b;
+    }
+    out.seg_smem_f_bytes = (size_t)s.f_smem_floats * 4;
+    out.seg_smem_b_bytes = (size_t)s.b_smem_floats * 4;
+    out.seg_grid_f = std::max(1, std::min((s.n_tiles_f + s.nw_f - 1) / s.nw_f, num_sms));
+    out.seg_grid_b = std::max(1, std::min(s.n_tiles_b, num_sms));
+    s.ok = 1;
 }

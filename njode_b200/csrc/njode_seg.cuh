@@ -1,0 +1,960 @@
+// njode_seg.cuh -- fast path for the non-masked training call: every (path, inter-observation
+// segment) is an independent work unit (NJODE/models.py:463-470: h after a jump = enc(X_obs) does not
+// depend on h before it), so units are marched as dense tiles without any jump compaction.
+//
+// Design (sm_100a, fp32 FMA pipe; the demo nets are 13->50->50->10, far below a tensor-core tile):
+//   * every Linear layer over a warp's R = 4*TR rows is a register-tiled GEMM: lane (rg, og) owns the
+//     TR x TO accumulators of rows {rg + 4i} x outputs {og + 8j}; operands come from shared memory as
+//     float4 along the reduction dimension (TR + TO LDS.128 per 4*TR*TO FFMA).  Activation rows use
+//     a stride = 8 (mod 16) floats and weight rows a stride = 4 (mod 8) floats, which makes every
+//     LDS.128 of the inner loop a single conflict-free wavefront.
+//   * forward: warp-autonomous.  A warp owns R units from the start encoder to the loss row; there
+//     is no CTA barrier after the weight image is in shared memory.  Tiles (sorted longest first)
+//     are handed out by an atomic counter, i.e. greedy longest-processing-time scheduling.
+//   * backward: a CTA owns P = NW*R units.  Per Euler step every warp recomputes the hidden
+//     activations of its R rows and back-propagates through the layers (warp-local phase A), then
+//     all threads accumulate dW += G^T A over the P rows of the CTA into 4x4 tiles that stay in
+//     REGISTERS for the whole launch (phase B) -- two CTA barriers per step.
+//   * dropout: a dropped activation is stored as -0.0f, so the backward pass reads the keep bit
+//     from the recomputed activation instead of hashing again.
+//
+// Same dual-compilation scheme as njode_core.cuh: phases separated by NJ_SYNC / NJ_SYNCWARP with all
+// cross-lane state in shared arrays, so -DNJODE_HOST_SIM runs it sequentially on the host (tests).
+#pragma once
+#include "njode_core.cuh"
+
+#if defined(NJODE_HOST_SIM)
+#define NJ_WARPS(w, nw) for (int w = 0; w < (nw); ++w)
+#define NJ_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+#define NJ_SYNCWARP() ((void)0)
+static inline int nj_atomic_inc(int* p) { return (*p)++; }
+static inline unsigned nj_f2u(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float nj_u2f(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+#else
+#define NJ_WARPS(w, nw) for (int w = (int)(threadIdx.x >> 5), _nj_we = w + 1; w < _nj_we; ++w)
+#define NJ_LANES(lane) for (int lane = (int)(threadIdx.x & 31), _nj_le = lane + 1; lane < _nj_le; ++lane)
+#define NJ_SYNCWARP() __syncwarp()
+__device__ __forceinline__ int nj_atomic_inc(int* p) { return atomicAdd(p, 1); }
+__device__ __forceinline__ unsigned nj_f2u(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ float nj_u2f(unsigned u) { return __uint_as_float(u); }
+#endif
+
+#define NJ_SEG_NT_MAX 2            // dW tiles (4x4 + bias) a thread may own in registers
+#define NJ_SEG_ACC (NJ_SEG_NT_MAX * 20)
+#define NJ_DROPPED 0x80000000u     // bit pattern (-0.0f) of a dropped activation
+
+// launch-constant layout of the segment kernels (floats unless noted)
+struct NjSeg {
+    int ok;                         // 0: not eligible, use the generic kernels
+    int tr_f, tr_b;                 // rows per lane group: a warp owns 4*tr rows (forward / backward)
+    int nw_f, nw_b;                 // warps per CTA (forward / backward)
+    int sI, sA, sO, sH, sD;         // strides: first-layer input, hidden activations, last-layer output, H, d
+    int nA;                         // hidden-activation buffers kept in backward (max n_linear - 1)
+    // forward: per-warp region
+    int f_region, f_IN, f_A0, f_A1, f_OUT, f_HS, f_LX, f_TX, f_XI, f_YBJ, f_F, f_I;
+    int f_img, f_warp0, f_smem_floats;
+    // backward: CTA-level [P][stride] arrays
+    int b_img, b_IN, b_A, b_G, b_GOUT, b_GZ, b_OUT, b_GH, b_HB, b_EE, b_GE, b_XI, b_LX, b_TX, b_YBJ, b_YY, b_GYBJ, b_F, b_I;
+    int b_smem_floats;
+    int P_b;                        // rows per backward CTA
+    int n_tiles_f, n_tiles_b;       // warp tiles (forward), CTA tiles (backward)
+    int tile_base[3][NJODE_MAX_LINEAR];   // first dW tile id of (net, layer); order ODE, RO, ENC
+    int tiles_total, nt_slots;
+};
+
+enum { NJS_I_PATH = 0, NJS_I_S0, NJS_I_LEN, NJS_I_ROW, NJS_I_START, NJS_I_FLAG, NJS_I_RK, NJS_I_COUNT };
+enum { NJS_F_TAU = 0, NJS_F_DT, NJS_F_CA, NJS_F_CB, NJS_F_COUNT };
+
+static inline int nj_stride_act(int n) { return ((n + 7) / 16) * 16 + 8; }    // = 8 (mod 16), >= n
+
+// ------------------------------------------------------------------------------------------------
+// warp GEMM primitives
+// ------------------------------------------------------------------------------------------------
+struct NjWL {                       // one Linear layer evaluated by a warp
+    const float* in; int in_s; int K4;
+    const float* W; int w_s; const float* bias;
+    int o_base;
+    float* out; int out_s;
+    int act; int drop; unsigned thr; float keep_scale; const int* rk; unsigned tag;
+};
+
+// out[r][o] = act(b[o] + sum_k in[r][k] W[o][k]) (* dropout), rows r = rg + 4i, outputs o = o_base + og + 8j.
+// Every o < o_base + 8*TO is stored: the image rows >= O are zero and the out stride covers them.
+template <int TR, int TO>
+NJ_HD void nj_wg_fwd(const NjWL& L, int lane) {
+    const int rg = lane >> 3, og = lane & 7;
+    float acc[TR][TO];
+#pragma unroll
+    for (int j = 0; j < TO; ++j) {
+        const float b = L.bias ? L.bias[L.o_base + og + 8 * j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < TR; ++i) acc[i][j] = b;
+    }
+    const float* ap[TR];
+    const float* wp[TO];
+#pragma unroll
+    for (int i = 0; i < TR; ++i) ap[i] = L.in + (size_t)(rg + 4 * i) * L.in_s;
+#pragma unroll
+    for (int j = 0; j < TO; ++j) wp[j] = L.W + (size_t)(L.o_base + og + 8 * j) * L.w_s;
+#pragma unroll 2
+    for (int k4 = 0; k4 < L.K4; ++k4) {
+        nj_f4 a[TR], w[TO];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) a[i] = nj_ld4(ap[i] + 4 * k4);
+#pragma unroll
+        for (int j = 0; j < TO; ++j) w[j] = nj_ld4(wp[j] + 4 * k4);
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int j = 0; j < TO; ++j) {
+                acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
+                acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
+                acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
+                acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
+            }
+    }
+    const unsigned obase16 = (unsigned)(L.o_base + og);
+#pragma unroll
+    for (int i = 0; i < TR; ++i) {
+        const int r = rg + 4 * i;
+        float* orow = L.out + (size_t)r * L.out_s + L.o_base + og;
+        if (L.drop) {
+            const unsigned lk = nj_layer_key((unsigned)L.rk[r], L.tag);
+#pragma unroll
+            for (int j = 0; j < TO; j += 2) {
+                // neurons o and o ^ 8 share a hash word (nj_keep); o_base is a multiple of 16 (planner),
+                // so outputs j (even) and j + 1 of this lane are such a pair
+                const unsigned o = obase16 + 8u * j;
+                const unsigned word = nj_keep_word(lk, (o & 7u) | ((o >> 4) << 3));
+                const float v0 = nj_act(acc[i][j], L.act) * L.keep_scale;
+                orow[8 * j] = (word & 0xFFFFu) >= L.thr ? v0 : nj_u2f(NJ_DROPPED);
+                if (j + 1 < TO) {
+                    const float v1 = nj_act(acc[i][j + 1], L.act) * L.keep_scale;
+                    orow[8 * j + 8] = (word >> 16) >= L.thr ? v1 : nj_u2f(NJ_DROPPED);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TO; ++j) orow[8 * j] = nj_act(acc[i][j], L.act);
+        }
+    }
+}
+
+#if defined(NJODE_HOST_SIM)
+#define NJ_ASSUME_SHARED(p) ((void)0)
+#else
+#define NJ_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#endif
+
+// one layer over the warp's rows: all output chunks.  Not inlined: one copy of the TO variants per TR.
+template <int TR>
+NJ_HDN void nj_seg_layer_fwd(NjWL L, int to, int nch) {
+    NJ_ASSUME_SHARED(L.in); NJ_ASSUME_SHARED(L.W); NJ_ASSUME_SHARED(L.out); NJ_ASSUME_SHARED(L.rk);
+    if (L.bias) NJ_ASSUME_SHARED(L.bias);
+    for (int ch = 0; ch < nch; ++ch) {
+        L.o_base = ch * 8 * to;
+        NJ_LANES(lane) {
+            switch (to) {
+                case 1: nj_wg_fwd<TR, 1>(L, lane); break;
+                case 2: nj_wg_fwd<TR, 2>(L, lane); break;
+                case 3: nj_wg_fwd<TR, 3>(L, lane); break;
+                case 4: nj_wg_fwd<TR, 4>(L, lane); break;
+                case 5: nj_wg_fwd<TR, 5>(L, lane); break;
+                case 6: nj_wg_fwd<TR, 6>(L, lane); break;
+                case 7: nj_wg_fwd<TR, 7>(L, lane); break;
+                default: nj_wg_fwd<TR, 8>(L, lane); break;
+            }
+        }
+    }
+}
+
+struct NjWD {                       // input-gradient of one Linear layer evaluated by a warp
+    const float* g; int g_s; int O4;
+    const float* W; int w_s;
+    int kg_base, K4in;
+    float* gin; int gin_s;
+    const float* aprev; int a_s; int act_prev;
+    int drop; float keep_scale, one_minus_p;
+};
+
+// gin[r][k] = (sum_o g[r][o] W[o][k]) * act'(aprev[r][k]) * dropout factor; rows rg + 4i,
+// k-groups (float4) kg = kg_base + kq + 8*jk
+template <int TR, int TK>
+NJ_HD void nj_wg_dx(const NjWD& L, int lane) {
+    const int rg = lane >> 3, kq = lane & 7;
+    float acc[TR][TK][4];
+#pragma unroll
+    for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int jk = 0; jk < TK; ++jk)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][jk][c] = 0.f;
+    const float* wp[TK];
+#pragma unroll
+    for (int jk = 0; jk < TK; ++jk) {
+        int kg = L.kg_base + kq + 8 * jk;
+        kg = kg < L.K4in ? kg : L.K4in - 1;          // clamped lanes compute a duplicate, never store
+        wp[jk] = L.W + 4 * kg;
+    }
+    const float* gp[TR];
+#pragma unroll
+    for (int i = 0; i < TR; ++i) gp[i] = L.g + (size_t)(rg + 4 * i) * L.g_s;
+    const int ws = L.w_s;
+    for (int o4 = 0; o4 < L.O4; ++o4) {
+        nj_f4 gv[TR];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) gv[i] = nj_ld4(gp[i] + 4 * o4);
+#pragma unroll
+        for (int jk = 0; jk < TK; ++jk) {
+            const float* q = wp[jk] + (size_t)(4 * o4) * ws;
+            const nj_f4 w0 = nj_ld4(q), w1 = nj_ld4(q + ws), w2 = nj_ld4(q + 2 * ws), w3 = nj_ld4(q + 3 * ws);
+#pragma unroll
+            for (int i = 0; i < TR; ++i) {
+                acc[i][jk][0] = fmaf(gv[i].x, w0.x, fmaf(gv[i].y, w1.x, fmaf(gv[i].z, w2.x, fmaf(gv[i].w, w3.x, acc[i][jk][0]))));
+                acc[i][jk][1] = fmaf(gv[i].x, w0.y, fmaf(gv[i].y, w1.y, fmaf(gv[i].z, w2.y, fmaf(gv[i].w, w3.y, acc[i][jk][1]))));
+                acc[i][jk][2] = fmaf(gv[i].x, w0.z, fmaf(gv[i].y, w1.z, fmaf(gv[i].z, w2.z, fmaf(gv[i].w, w3.z, acc[i][jk][2]))));
+                acc[i][jk][3] = fmaf(gv[i].x, w0.w, fmaf(gv[i].y, w1.w, fmaf(gv[i].z, w2.w, fmaf(gv[i].w, w3.w, acc[i][jk][3]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TR; ++i) {
+        const int r = rg + 4 * i;
+#pragma unroll
+        for (int jk = 0; jk < TK; ++jk) {
+            const int kg = L.kg_base + kq + 8 * jk;
+            if (kg >= L.K4in) continue;
+            float v[4] = {acc[i][jk][0], acc[i][jk][1], acc[i][jk][2], acc[i][jk][3]};
+            if (L.aprev) {
+                const nj_f4 av = nj_ld4(L.aprev + (size_t)r * L.a_s + 4 * kg);
+                const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float a = a4[c];
+                    if (L.drop) {
+                        if (nj_f2u(a) == NJ_DROPPED) v[c] = 0.f;
+                        else { a *= L.one_minus_p; v[c] *= L.keep_scale; }
+                    }
+                    if (L.act_prev == NJODE_ACT_TANH) v[c] *= (1.f - a * a);
+                    else if (L.act_prev == NJODE_ACT_RELU) v[c] = a > 0.f ? v[c] : 0.f;
+                }
+            }
+            nj_f4 o; o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3];
+            nj_st4(L.gin + (size_t)r * L.gin_s + 4 * kg, o);
+        }
+    }
+}
+
+template <int TR>
+NJ_HDN void nj_seg_layer_dx(NjWD D) {
+    NJ_ASSUME_SHARED(D.g); NJ_ASSUME_SHARED(D.W); NJ_ASSUME_SHARED(D.gin);
+    if (D.aprev) NJ_ASSUME_SHARED(D.aprev);
+    for (int kb = 0; kb < D.K4in; kb += 16) {
+        D.kg_base = kb;
+        const bool two = (D.K4in - kb) > 8;
+        NJ_LANES(lane) {
+            if (two) nj_wg_dx<TR, 2>(D, lane); else nj_wg_dx<TR, 1>(D, lane);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-warp views
+// ------------------------------------------------------------------------------------------------
+struct NjSegW {
+    const NjCfg* c; const NjSeg* s;
+    const float* wimg;
+    float *IN, *A0, *A1, *OUT;          // forward: A0/A1 ping-pong; backward: A0 = first hidden buffer
+    float *G0, *GOUT, *GZ;              // backward only
+    int a_buf_stride, g_buf_stride;     // distance (floats) between consecutive hidden buffers
+    int* RK;                            // dropout row keys of this warp's rows
+};
+
+// MLP forward over the warp's rows.  keep_all: hidden activations of layer l go to A0 + l*a_buf_stride
+// (backward); otherwise they ping-pong between A0 and A1.  skip_last: stop after the hidden layers.
+template <int TR>
+NJ_HD void nj_seg_mlp_fwd(const NjSegW& w, int netid, bool keep_all, bool skip_last) {
+    const NjCfg& c = *w.c;
+    const NjNet& N = c.net[netid];
+    const float* in = w.IN; int in_s = w.s->sI;
+    for (int l = 0; l < N.n; ++l) {
+        const bool last = (l == N.n - 1);
+        if (last && skip_last) break;
+        NjWL L;
+        L.in = in; L.in_s = in_s; L.K4 = (N.dim[l] + 3) >> 2;
+        L.W = w.wimg + N.w_img[l]; L.w_s = N.ks[l];
+        L.bias = N.b_src[l] >= 0 ? w.wimg + N.b_img[l] : nullptr;
+        if (last) { L.out = w.OUT; L.out_s = w.s->sO; }
+        else { L.out = keep_all ? w.A0 + (size_t)l * w.a_buf_stride : ((l & 1) ? w.A1 : w.A0); L.out_s = w.s->sA; }
+        L.act = last ? NJODE_ACT_NONE : N.act[l];
+        L.drop = (!last) && c.has_drop; L.thr = c.thr; L.keep_scale = c.keep_scale;
+        L.rk = w.RK; L.tag = (unsigned)(netid * 16 + l + 1);
+        L.o_base = 0;
+        nj_seg_layer_fwd<TR>(L, N.to[l], N.nch[l]);
+        NJ_SYNCWARP();
+        in = L.out; in_s = L.out_s;
+    }
+}
+
+// MLP backward (input gradients only; dW is phase B).  g wrt the raw output is in GOUT; hidden
+// activations in A0 + l*a_buf_stride; g wrt hidden pre-activation l goes to G0 + l*g_buf_stride;
+// the gradient wrt the network input goes to GZ when need_in_grad.
+template <int TR>
+NJ_HD void nj_seg_mlp_dx(const NjSegW& w, int netid, bool need_in_grad) {
+    const NjCfg& c = *w.c;
+    const NjNet& N = c.net[netid];
+    for (int l = N.n - 1; l >= 0; --l) {
+        if (l == 0 && !need_in_grad) break;
+        NjWD D;
+        if (l == N.n - 1) { D.g = w.GOUT; D.g_s = w.s->sO; } else { D.g = w.G0 + (size_t)l * w.g_buf_stride; D.g_s = w.s->sA; }
+        D.O4 = (N.dim[l + 1] + 3) >> 2;
+        D.W = w.wimg + N.w_img[l]; D.w_s = N.ks[l];
+        D.K4in = (N.dim[l] + 3) >> 2;
+        if (l > 0) {
+            D.gin = w.G0 + (size_t)(l - 1) * w.g_buf_stride; D.gin_s = w.s->sA;
+            D.aprev = w.A0 + (size_t)(l - 1) * w.a_buf_stride; D.a_s = w.s->sA; D.act_prev = N.act[l - 1];
+        } else {
+            D.gin = w.GZ; D.gin_s = w.s->sI; D.aprev = nullptr; D.a_s = 0; D.act_prev = NJODE_ACT_NONE;
+        }
+        D.drop = c.has_drop; D.keep_scale = c.keep_scale; D.one_minus_p = c.one_minus_p;
+        D.kg_base = 0;
+        nj_seg_layer_dx<TR>(D);
+        NJ_SYNCWARP();
+    }
+}
+
+NJ_HD unsigned nj_seg_event_of_start(const NjArgs& a, int sr) {
+    return sr < 0 ? NJ_EVENT_INIT : NJ_EVENT_JUMP_BASE + 3u * (unsigned)NJ_LDG(a.b.row_jump + sr) + 1u;
+}
+NJ_HD unsigned nj_seg_event_of_jump(const NjArgs& a, int row, unsigned which) {
+    return NJ_EVENT_JUMP_BASE + 3u * (unsigned)NJ_LDG(a.b.row_jump + row) + which;
+}
+
+// lane -> (row, first column, column step) of the elementwise phases: 32/R lanes per row
+#define NJ_ROWMAP(R)                                              \
+    const int LPR = 32 / (R);                                     \
+    const int er = lane / LPR, ec0 = lane % LPR;                  \
+    (void)er; (void)ec0
+
+// ------------------------------------------------------------------------------------------------
+// forward: one warp = R = 4*TR units
+// ------------------------------------------------------------------------------------------------
+template <int TR>
+NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* reg, const float* wimg, int wtile) {
+    constexpr int R = 4 * TR;
+    NjSegW w;
+    w.c = &c; w.s = &s; w.wimg = wimg;
+    w.IN = reg + s.f_IN; w.A0 = reg + s.f_A0; w.A1 = reg + s.f_A1; w.OUT = reg + s.f_OUT;
+    w.G0 = w.GOUT = w.GZ = nullptr; w.a_buf_stride = 0; w.g_buf_stride = 0;
+    float* HS = reg + s.f_HS; float* LX = reg + s.f_LX; float* TX = reg + s.f_TX; float* XI = reg + s.f_XI;
+    float* YBJ = reg + s.f_YBJ; float* F = reg + s.f_F;
+    int* I = reinterpret_cast<int*>(reg + s.f_I);
+    w.RK = I + NJS_I_RK * R;
+    const int u0 = wtile * R;
+    const int d4 = ((c.d + 3) >> 2) << 2, H4 = ((c.H + 3) >> 2) << 2, inf4 = ((c.inf + 3) >> 2) << 2;
+    const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
+    // ---- unit descriptors ----
+    NJ_LANES(lane) {
+        if (lane < R) {
+            const int u = u0 + lane;
+            if (u < a.b.n_units) {
+                const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                const int sc = dsc[5];
+                I[NJS_I_PATH * R + lane] = dsc[0]; I[NJS_I_S0 * R + lane] = dsc[1]; I[NJS_I_LEN * R + lane] = dsc[2] - dsc[1];
+                I[NJS_I_ROW * R + lane] = dsc[4] > dsc[3] ? NJ_LDG(a.b.path_rows + dsc[3]) : -1;
+                I[NJS_I_FLAG * R + lane] = (sc & NJODE_UNIT_WRITES_HT) ? 1 : 0;
+                I[NJS_I_START * R + lane] = (sc & ~NJODE_UNIT_WRITES_HT) - 1;
+            } else {
+                I[NJS_I_PATH * R + lane] = -1; I[NJS_I_S0 * R + lane] = 0; I[NJS_I_LEN * R + lane] = 0;
+                I[NJS_I_ROW * R + lane] = -1; I[NJS_I_FLAG * R + lane] = 0; I[NJS_I_START * R + lane] = -1;
+            }
+        }
+    }
+    NJ_SYNCWARP();
+    int maxlen = 0, any_jump = 0;
+    for (int r = 0; r < R; ++r) {
+        maxlen = I[NJS_I_LEN * R + r] > maxlen ? I[NJS_I_LEN * R + r] : maxlen;
+        any_jump |= (I[NJS_I_ROW * R + r] >= 0);
+    }
+    // ---- start: h = encoder(start value); last_X, tanh(last_X), tau stay fixed for the whole unit ----
+    NJ_LANES(lane) {
+        NJ_ROWMAP(R);
+        const int p = I[NJS_I_PATH * R + er], sr = I[NJS_I_START * R + er];
+        for (int c_ = ec0; c_ < d4; c_ += LPR) {
+            float x = 0.f;
+            if (p >= 0 && c_ < c.d) x = sr < 0 ? NJ_LDG(a.b.start_X + (size_t)p * c.d + c_) : NJ_LDG(a.b.X + (size_t)sr * c.d + c_);
+            const float tx = c_ < c.d ? nj_tanh(x) : 0.f;
+            XI[er * sD + c_] = x; LX[er * sD + c_] = x; TX[er * sD + c_] = tx;
+            w.IN[(size_t)er * sI + c_] = tx;
+        }
+        if (ec0 == 0) {
+            F[NJS_F_TAU * R + er] = (p >= 0 && sr >= 0) ? NJ_LDG(a.b.jump_tau + NJ_LDG(a.b.row_jump + sr)) : 0.f;
+            w.RK[er] = p >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), nj_seg_event_of_start(a, sr)) : 0;
+        }
+    }
+    NJ_SYNCWARP();
+    nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, false, false);
+    NJ_LANES(lane) {
+        NJ_ROWMAP(R);
+        for (int c_ = ec0; c_ < c.H; c_ += LPR) {
+            float e = w.OUT[er * sO + c_];
+            if (c.residual) e += nj_resid(XI + er * sD, c.d, c.H, c_);
+            HS[er * sH + c_] = e;
+        }
+    }
+    NJ_SYNCWARP();
+    // ---- Euler steps ----
+    for (int j = 0; j < maxlen; ++j) {
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const bool active = j < I[NJS_I_LEN * R + er];
+            const int k = I[NJS_I_S0 * R + er] + j;
+            const int p = I[NJS_I_PATH * R + er];
+            const float tau = F[NJS_F_TAU * R + er];
+            float* hh = (active && a.h_hist) ? a.h_hist + ((size_t)k * a.b.B + p) * c.H : nullptr;
+            for (int c_ = ec0; c_ < inf4; c_ += LPR) {
+                float v = 0.f;
+                if (c_ < c.d) v = TX[er * sD + c_];
+                else if (c_ < c.d + c.H) {
+                    const float h = HS[er * sH + c_ - c.d];
+                    if (hh) hh[c_ - c.d] = h;
+                    v = nj_tanh(h);
+                } else if (c_ < c.inf) {
+                    const float tcur = active ? NJ_LDG(a.b.step_t + k) : 0.f;
+                    if (c_ == c.d + c.H) v = tau;
+                    else if (c_ == c.d + c.H + 1) v = tcur - tau;
+                    else v = tau + (tcur - tau);
+                }
+                w.IN[(size_t)er * sI + c_] = v;
+            }
+            if (ec0 == 0) {
+                F[NJS_F_DT * R + er] = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
+                w.RK[er] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
+            }
+        }
+        NJ_SYNCWARP();
+        nj_seg_mlp_fwd<TR>(w, NJODE_NET_ODE, false, false);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            if (j < I[NJS_I_LEN * R + er]) {
+                const float dt = F[NJS_F_DT * R + er];
+                for (int c_ = ec0; c_ < c.H; c_ += LPR)
+                    HS[er * sH + c_] = fmaf(dt, w.OUT[er * sO + c_], HS[er * sH + c_]);
+            }
+        }
+        NJ_SYNCWARP();
+    }
+    // ---- hT of the units that end their path ----
+    NJ_LANES(lane) {
+        NJ_ROWMAP(R);
+        if (I[NJS_I_FLAG * R + er]) {
+            float* dst = a.hT + (size_t)I[NJS_I_PATH * R + er] * c.H;
+            for (int c_ = ec0; c_ < c.H; c_ += LPR) dst[c_] = HS[er * sH + c_];
+        }
+    }
+    if (!any_jump) { NJ_SYNCWARP(); return; }
+    // ---- the jump that ends the segment (NJODE/models.py:449-489) ----
+    NJ_LANES(lane) {
+        NJ_ROWMAP(R);
+        const int row = I[NJS_I_ROW * R + er], p = I[NJS_I_PATH * R + er];
+        for (int c_ = ec0; c_ < H4; c_ += LPR) {
+            float h = 0.f;
+            if (row >= 0 && c_ < c.H) {
+                h = HS[er * sH + c_];
+                if (a.h_before) a.h_before[(size_t)row * c.H + c_] = h;
+            }
+            w.IN[(size_t)er * sI + c_] = c_ < c.H ? nj_tanh(h) : 0.f;
+        }
+        if (ec0 == 0)
+            w.RK[er] = row >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), nj_seg_event_of_jump(a, row, 0u)) : 0;
+    }
+    NJ_SYNCWARP();
+    nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, false, false);
+    NJ_LANES(lane) {
+        NJ_ROWMAP(R);
+        const int row = I[NJS_I_ROW * R + er], p = I[NJS_I_PATH * R + er];
+        for (int c_ = ec0; c_ < c.dout; c_ += LPR) {
+            float y = w.OUT[er * sO + c_];
+            if (c.residual) y += nj_resid(HS + er * sH, c.H, c.dout, c_);
+            YBJ[er * sD + c_] = y;
+        }
+        for (int c_ = ec0; c_ < d4; c_ += LPR) {
+            float x = 0.f;
+            if (row >= 0 && c_ < c.d) x = NJ_LDG(a.b.X + (size_t)row * c.d + c_);
+            XI[er * sD + c_] = x;
+            w.IN[(size_t)er * sI + c_] = c_ < c.d ? nj_tanh(x) : 0.f;
+        }
+        if (ec0 == 0)
+            w.RK[er] = row >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), nj_seg_event_of_jump(a, row, 1u)) : 0;
+    }
+    NJ_SYNCWARP();
+    nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, false, false);
+    NJ_LANES(lane) {
+        NJ_ROWMAP(R);
+        const int row = I[NJS_I_ROW * R + er], p = I[NJS_I_PATH * R + er];
+        for (int c_ = ec0; c_ < H4; c_ += LPR) {
+            float e = 0.f;
+            if (c_ < c.H) {
+                e = w.OUT[er * sO + c_];
+                if (c.residual) e += nj_resid(XI + er * sD, c.d, c.H, c_);
+                HS[er * sH + c_] = e;             // the unit is finished: HS now holds enc(X_obs)
+            }
+            w.IN[(size_t)er * sI + c_] = c_ < c.H ? nj_tanh(e) : 0.f;
+        }
+        if (ec0 == 0)
+            w.RK[er] = row >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), nj_seg_event_of_jump(a, row, 2u)) : 0;
+    }
+    NJ_SYNCWARP();
+    nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, false, false);
+    NJ_LANES(lane) {
+        if (lane < R) {
+            const int r = lane, row = I[NJS_I_ROW * R + r];
+            if (row >= 0) {
+                float sa = 0.f, sb = 0.f;
+                for (int c_ = 0; c_ < c.dout; ++c_) {
+                    float y = w.OUT[r * sO + c_];
+                    if (c.residual) y += nj_resid(HS + r * sH, c.H, c.dout, c_);
+                    if (a.y_after) a.y_after[(size_t)row * c.dout + c_] = y;
+                    const float x = XI[r * sD + c_], yb = YBJ[r * sD + c_];
+                    const float da = x - y, db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y) : (yb - x);
+                    sa = fmaf(da, da, sa); sb = fmaf(db, db, sb);
+                }
+                if (a.get_loss) {
+                    const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+                    const float sm = (c.loss_kind == NJODE_LOSS_STANDARD) ? (2.f * c.w * ra + 2.f * (1.f - c.w) * rb)
+                                                                          : (c.w * ra + (1.f - c.w) * rb);
+                    a.row_loss[row] = sm * sm / NJ_LDG(a.b.n_obs_ot + I[NJS_I_PATH * R + r]);
+                }
+            }
+        }
+    }
+    NJ_SYNCWARP();
+}
+
+template <int TR>
+NJ_HD void nj_seg_cta_forward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
+    float* simg = smem + s.f_img;
+    NJ_THREADS(tid, s.nw_f * 32) { for (int i = tid; i < c.img_floats / 4; i += s.nw_f * 32) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
+    nj_zero(smem + s.f_warp0, s.nw_f * s.f_region, s.nw_f * 32);
+    NJ_SYNC();
+    NJ_WARPS(wp, s.nw_f) {
+        float* reg = smem + s.f_warp0 + (size_t)wp * s.f_region;
+        int* slot = reinterpret_cast<int*>(reg + s.f_I) + NJS_I_COUNT * 4 * TR;
+        for (;;) {
+            NJ_LANES(lane) { if (lane == 0) *slot = nj_atomic_inc(a.counter); }
+            NJ_SYNCWARP();
+            const int wt = *slot;
+            NJ_SYNCWARP();
+            if (wt >= s.n_tiles_f) break;
+            nj_seg_forward_warp<TR>(c, s, a, reg, simg, wt);
+        }
+    }
+}
+
+NJ_HD void nj_seg_cta_forward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
+    if (s.tr_f == 4) nj_seg_cta_forward_t<4>(c, s, a, smem);
+    else if (s.tr_f == 2) nj_seg_cta_forward_t<2>(c, s, a, smem);
+    else nj_seg_cta_forward_t<1>(c, s, a, smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct NjSegB {                      // CTA-level views
+    float *IN, *A, *G, *GOUT, *GZ, *OUT, *GH, *HB, *EE, *GE, *XI, *LX, *TX, *YBJ, *YY, *GYBJ, *F;
+    int* I;
+};
+
+NJ_HD void nj_segb_bind(NjSegB& t, const NjSeg& s, float* smem) {
+    t.IN = smem + s.b_IN; t.A = smem + s.b_A; t.G = smem + s.b_G; t.GOUT = smem + s.b_GOUT; t.GZ = smem + s.b_GZ;
+    t.OUT = smem + s.b_OUT; t.GH = smem + s.b_GH; t.HB = smem + s.b_HB; t.EE = smem + s.b_EE; t.GE = smem + s.b_GE;
+    t.XI = smem + s.b_XI; t.LX = smem + s.b_LX; t.TX = smem + s.b_TX; t.YBJ = smem + s.b_YBJ; t.YY = smem + s.b_YY;
+    t.GYBJ = smem + s.b_GYBJ; t.F = smem + s.b_F; t.I = reinterpret_cast<int*>(smem + s.b_I);
+}
+
+// phase B: dW[o][k] += sum_r g[r][o] a[r][k] over the P rows of the CTA, thread-owned 4x4 tiles
+// (+ bias sums in the kg == 0 tiles) held in `acc` (registers) for the whole launch.
+NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, float* acc, int tid, int nt) {
+    const NjNet& N = c.net[netid];
+    const int P = s.P_b;
+#pragma unroll
+    for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
+        if (slot >= s.nt_slots) break;
+        const int T = slot * nt + tid;
+        if (T < s.tile_base[netid][0]) continue;
+        int l = 0;
+        for (int ll = N.n - 1; ll > 0; --ll) if (T >= s.tile_base[netid][ll]) { l = ll; break; }
+        const int K4 = (N.dim[l] + 3) >> 2, O4 = (N.dim[l + 1] + 3) >> 2;
+        const int tl = T - s.tile_base[netid][l];
+        if (tl >= K4 * O4) continue;
+        const int kg = tl % K4, og = tl / K4;
+        const float* g; int g_s;
+        if (l == N.n - 1) { g = t.GOUT; g_s = s.sO; } else { g = t.G + (size_t)l * P * s.sA; g_s = s.sA; }
+        const float* av; int a_s;
+        if (l == 0) { av = t.IN; a_s = s.sI; } else { av = t.A + (size_t)(l - 1) * P * s.sA; a_s = s.sA; }
+        g += 4 * og; av += 4 * kg;
+        float* q = acc + slot * 20;
+        float r00 = q[0], r01 = q[1], r02 = q[2], r03 = q[3], r10 = q[4], r11 = q[5], r12 = q[6], r13 = q[7];
+        float r20 = q[8], r21 = q[9], r22 = q[10], r23 = q[11], r30 = q[12], r31 = q[13], r32 = q[14], r33 = q[15];
+        float b0 = q[16], b1 = q[17], b2 = q[18], b3 = q[19];
+#pragma unroll 4
+        for (int r = 0; r < P; ++r) {
+            const nj_f4 gv = nj_ld4(g);
+            const nj_f4 x = nj_ld4(av);
+            g += g_s; av += a_s;
+            r00 = fmaf(gv.x, x.x, r00); r01 = fmaf(gv.x, x.y, r01); r02 = fmaf(gv.x, x.z, r02); r03 = fmaf(gv.x, x.w, r03);
+            r10 = fmaf(gv.y, x.x, r10); r11 = fmaf(gv.y, x.y, r11); r12 = fmaf(gv.y, x.z, r12); r13 = fmaf(gv.y, x.w, r13);
+            r20 = fmaf(gv.z, x.x, r20); r21 = fmaf(gv.z, x.y, r21); r22 = fmaf(gv.z, x.z, r22); r23 = fmaf(gv.z, x.w, r23);
+            r30 = fmaf(gv.w, x.x, r30); r31 = fmaf(gv.w, x.y, r31); r32 = fmaf(gv.w, x.z, r32); r33 = fmaf(gv.w, x.w, r33);
+            b0 += gv.x; b1 += gv.y; b2 += gv.z; b3 += gv.w;
+        }
+        q[0] = r00; q[1] = r01; q[2] = r02; q[3] = r03; q[4] = r10; q[5] = r11; q[6] = r12; q[7] = r13;
+        q[8] = r20; q[9] = r21; q[10] = r22; q[11] = r23; q[12] = r30; q[13] = r31; q[14] = r32; q[15] = r33;
+        q[16] = b0; q[17] = b1; q[18] = b2; q[19] = b3;
+    }
+}
+
+// writes the register tiles into this CTA's partial gradient image (pre-zeroed by the caller)
+NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, float* gpart, int tid, int nt) {
+#pragma unroll
+    for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
+        if (slot >= s.nt_slots) break;
+        const int T = slot * nt + tid;
+        if (T >= s.tiles_total) continue;
+        int netid = NJODE_NET_ODE, l = 0;
+        bool found = false;
+        for (int oi = 2; oi >= 0 && !found; --oi) {
+            const int n_ = oi == 0 ? NJODE_NET_ODE : (oi == 1 ? NJODE_NET_RO : NJODE_NET_ENC);
+            const NjNet& N = c.net[n_];
+            for (int ll = N.n - 1; ll >= 0; --ll) if (T >= s.tile_base[n_][ll]) { netid = n_; l = ll; found = true; break; }
+        }
+        const NjNet& N = c.net[netid];
+        const int K4 = (N.dim[l] + 3) >> 2, O4 = (N.dim[l + 1] + 3) >> 2;
+        const int tl = T - s.tile_base[netid][l];
+        if (tl >= K4 * O4) continue;
+        const int kg = tl % K4, og = tl / K4;
+        const float* q = acc + slot * 20;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            nj_f4 v; v.x = q[4 * i]; v.y = q[4 * i + 1]; v.z = q[4 * i + 2]; v.w = q[4 * i + 3];
+            nj_st4(gpart + N.w_img[l] + (size_t)(4 * og + i) * N.ks[l] + 4 * kg, v);
+        }
+        if (kg == 0 && N.b_src[l] >= 0) {
+            nj_f4 v; v.x = q[16]; v.y = q[17]; v.z = q[18]; v.w = q[19];
+            nj_st4(gpart + N.b_img[l] + 4 * og, v);
+        }
+    }
+}
+
+#if defined(NJODE_HOST_SIM)
+#define NJ_ACC_DECL(nt) std::vector<float> nj_acc_store((size_t)(nt) * NJ_SEG_ACC, 0.f)
+#define NJ_ACC(tid) (nj_acc_store.data() + (size_t)(tid) * NJ_SEG_ACC)
+#else
+#define NJ_ACC_DECL(nt) float nj_acc_store[NJ_SEG_ACC]; _Pragma("unroll") for (int _i = 0; _i < NJ_SEG_ACC; ++_i) nj_acc_store[_i] = 0.f
+#define NJ_ACC(tid) (nj_acc_store)
+#endif
+
+#define NJ_SEGB_WARP_VIEW()                                                                                        \
+    const int r0 = wp * R;                                                                                         \
+    NjSegW w;                                                                                                      \
+    w.c = &c; w.s = &s; w.wimg = simg;                                                                             \
+    w.IN = t.IN + (size_t)r0 * sI; w.A0 = t.A + (size_t)r0 * s.sA; w.A1 = nullptr; w.OUT = t.OUT + (size_t)r0 * sO; \
+    w.G0 = t.G + (size_t)r0 * s.sA; w.GOUT = t.GOUT + (size_t)r0 * sO; w.GZ = t.GZ + (size_t)r0 * sI;             \
+    w.a_buf_stride = wa; w.g_buf_stride = wa; w.RK = t.I + NJS_I_RK * P + r0
+
+#define NJ_SEGB_KEY(r, valid, ev)                                                                                  \
+    t.I[NJS_I_RK * P + (r)] = (valid) ? (int)nj_row_key(c.seed_lo, c.seed_hi,                                      \
+        (unsigned)(t.I[NJS_I_PATH * P + (r)] + a.b.path_id_offset), (ev)) : 0
+
+template <int TR>
+NJ_HD void nj_seg_cta_backward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
+    constexpr int R = 4 * TR;
+    const int P = s.P_b, nt = s.nw_b * 32;
+    float* simg = smem + s.b_img;
+    NJ_THREADS(tid, nt) { for (int i = tid; i < c.img_floats / 4; i += nt) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
+    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
+    NJ_SYNC();
+    NjSegB t;
+    nj_segb_bind(t, s, smem);
+    NJ_ACC_DECL(nt);
+    const float gl = NJ_LDG(a.grad_loss);
+    const int d4 = ((c.d + 3) >> 2) << 2, H4 = ((c.H + 3) >> 2) << 2, inf4 = ((c.inf + 3) >> 2) << 2, do4 = ((c.dout + 3) >> 2) << 2;
+    const int wa = P * s.sA;
+    const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
+    int* ctl = t.I + NJS_I_COUNT * P;
+    for (;;) {
+        NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int tile = ctl[0];
+        if (tile >= s.n_tiles_b) break;
+        const int u0 = tile * P;
+        NJ_THREADS(tid, nt) {
+            if (tid < P) {
+                const int u = u0 + tid;
+                if (u < a.b.n_units) {
+                    const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                    const int sc = dsc[5];
+                    t.I[NJS_I_PATH * P + tid] = dsc[0]; t.I[NJS_I_S0 * P + tid] = dsc[1]; t.I[NJS_I_LEN * P + tid] = dsc[2] - dsc[1];
+                    t.I[NJS_I_ROW * P + tid] = dsc[4] > dsc[3] ? NJ_LDG(a.b.path_rows + dsc[3]) : -1;
+                    t.I[NJS_I_FLAG * P + tid] = (sc & NJODE_UNIT_WRITES_HT) ? 1 : 0;
+                    t.I[NJS_I_START * P + tid] = (sc & ~NJODE_UNIT_WRITES_HT) - 1;
+                } else {
+                    t.I[NJS_I_PATH * P + tid] = -1; t.I[NJS_I_S0 * P + tid] = 0; t.I[NJS_I_LEN * P + tid] = 0;
+                    t.I[NJS_I_ROW * P + tid] = -1; t.I[NJS_I_FLAG * P + tid] = 0; t.I[NJS_I_START * P + tid] = -1;
+                }
+            }
+        }
+        NJ_SYNC();
+        int maxlen = 0, any_jump = 0;
+        for (int r = 0; r < P; ++r) {
+            maxlen = t.I[NJS_I_LEN * P + r] > maxlen ? t.I[NJS_I_LEN * P + r] : maxlen;
+            any_jump |= (t.I[NJS_I_ROW * P + r] >= 0);
+        }
+        // ================= the jump at the end of the segment, reversed =================
+        // J1-J4 (warp-local): Y_bj = ro(h_before), E = enc(X_obs), Y = ro(E); loss gradients; ro backward at E
+        NJ_WARPS(wp, s.nw_b) {
+            NJ_SEGB_WARP_VIEW();
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er;
+                const int p = t.I[NJS_I_PATH * P + r], sr = t.I[NJS_I_START * P + r];
+                // gh starts from grad_hT for the units that end their path, else 0
+                const float* ght = (t.I[NJS_I_FLAG * P + r] && a.grad_hT) ? a.grad_hT + (size_t)p * c.H : nullptr;
+                for (int c_ = ec0; c_ < c.H; c_ += LPR) t.GH[r * sH + c_] = ght ? NJ_LDG(ght + c_) : 0.f;
+                for (int c_ = ec0; c_ < d4; c_ += LPR) {      // (last_X, tau) of the segment = its start observation
+                    float x = 0.f;
+                    if (p >= 0 && c_ < c.d) x = sr < 0 ? NJ_LDG(a.b.start_X + (size_t)p * c.d + c_) : NJ_LDG(a.b.X + (size_t)sr * c.d + c_);
+                    t.LX[r * sD + c_] = x; t.TX[r * sD + c_] = c_ < c.d ? nj_tanh(x) : 0.f;
+                }
+                if (ec0 == 0) t.F[NJS_F_TAU * P + r] = (p >= 0 && sr >= 0) ? NJ_LDG(a.b.jump_tau + NJ_LDG(a.b.row_jump + sr)) : 0.f;
+            }
+            NJ_SYNCWARP();
+            if (any_jump) {
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er, row = t.I[NJS_I_ROW * P + r];
+                    for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                        const float h = (row >= 0 && c_ < c.H) ? a.h_before[(size_t)row * c.H + c_] : 0.f;
+                        if (c_ < c.H) t.HB[r * sH + c_] = h;
+                        t.IN[(size_t)r * sI + c_] = c_ < c.H ? nj_tanh(h) : 0.f;
+                    }
+                    if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 0u)); }
+                }
+                NJ_SYNCWARP();
+                nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, true, false);
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er, row = t.I[NJS_I_ROW * P + r];
+                    for (int c_ = ec0; c_ < c.dout; c_ += LPR) {
+                        float y = t.OUT[r * sO + c_];
+                        if (c.residual) y += nj_resid(t.HB + r * sH, c.H, c.dout, c_);
+                        t.YBJ[r * sD + c_] = y;
+                    }
+                    for (int c_ = ec0; c_ < d4; c_ += LPR) {
+                        const float x = (row >= 0 && c_ < c.d) ? NJ_LDG(a.b.X + (size_t)row * c.d + c_) : 0.f;
+                        t.XI[r * sD + c_] = x;
+                        t.IN[(size_t)r * sI + c_] = c_ < c.d ? nj_tanh(x) : 0.f;
+                    }
+                    if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 1u)); }
+                }
+                NJ_SYNCWARP();
+                nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, true, false);
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er, row = t.I[NJS_I_ROW * P + r];
+                    for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                        float e = 0.f;
+                        if (c_ < c.H) {
+                            e = t.OUT[r * sO + c_];
+                            if (c.residual) e += nj_resid(t.XI + r * sD, c.d, c.H, c_);
+                            t.EE[r * sH + c_] = e;
+                        }
+                        t.IN[(size_t)r * sI + c_] = c_ < c.H ? nj_tanh(e) : 0.f;
+                    }
+                    if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 2u)); }
+                }
+                NJ_SYNCWARP();
+                nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, true, false);
+                // loss derivative (compute_loss / compute_loss_2, NJODE/models.py:71-126)
+                NJ_LANES(lane) {
+                    if (lane < R) {
+                        const int r = r0 + lane, row = t.I[NJS_I_ROW * P + r];
+                        float ca = 0.f, cb = 0.f;
+                        if (row >= 0) {
+                            float sa = 0.f, sb = 0.f;
+                            for (int c_ = 0; c_ < c.dout; ++c_) {
+                                float y = t.OUT[r * sO + c_];
+                                if (c.residual) y += nj_resid(t.EE + r * sH, c.H, c.dout, c_);
+                                t.YY[r * sD + c_] = y;
+                                const float x = t.XI[r * sD + c_], yb = t.YBJ[r * sD + c_];
+                                const float da = x - y, db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y) : (yb - x);
+                                sa = fmaf(da, da, sa); sb = fmaf(db, db, sb);
+                            }
+                            const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+                            const float wa_ = (c.loss_kind == NJODE_LOSS_STANDARD) ? 2.f * c.w : c.w;
+                            const float wb_ = (c.loss_kind == NJODE_LOSS_STANDARD) ? 2.f * (1.f - c.w) : (1.f - c.w);
+                            const float sm = wa_ * ra + wb_ * rb;
+                            const float cf = gl * 2.f * sm / (NJ_LDG(a.b.n_obs_ot + t.I[NJS_I_PATH * P + r]) * (float)a.b.batch_size_norm);
+                            ca = cf * wa_ / ra; cb = cf * wb_ / rb;
+                        }
+                        t.F[NJS_F_CA * P + r] = ca; t.F[NJS_F_CB * P + r] = cb;
+                    }
+                }
+                NJ_SYNCWARP();
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er;
+                    const bool has = t.I[NJS_I_ROW * P + r] >= 0;
+                    for (int c_ = ec0; c_ < do4; c_ += LPR) {
+                        float gy = 0.f, gyb = 0.f;
+                        if (c_ < c.dout && has) {
+                            const float x = t.XI[r * sD + c_], y = t.YY[r * sD + c_], yb = t.YBJ[r * sD + c_];
+                            const float ca = t.F[NJS_F_CA * P + r], cb = t.F[NJS_F_CB * P + r];
+                            if (c.loss_kind == NJODE_LOSS_STANDARD) { gy = -ca * (x - y) - cb * (yb - y); gyb = cb * (yb - y); }
+                            else { gy = -ca * (x - y); gyb = cb * (yb - x); }
+                        }
+                        t.GOUT[(size_t)r * sO + c_] = gy;
+                        t.GYBJ[r * sD + c_] = gyb;
+                    }
+                }
+                NJ_SYNCWARP();
+                nj_seg_mlp_dx<TR>(w, NJODE_NET_RO, true);
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er;
+                    for (int c_ = ec0; c_ < c.H; c_ += LPR) {
+                        const float th = t.IN[(size_t)r * sI + c_];
+                        float ge = t.GZ[(size_t)r * sI + c_] * (1.f - th * th);
+                        if (c.residual) ge += nj_resid_bwd(t.GOUT + (size_t)r * sO, c.H, c.dout, c_);
+                        t.GE[r * sH + c_] = ge;
+                    }
+                }
+            }
+        }
+        if (any_jump) {
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), tid, nt); }
+            NJ_SYNC();
+            // J5: encoder at X_obs, backward with g = dL/dE (from Y only)
+            NJ_WARPS(wp, s.nw_b) {
+                NJ_SEGB_WARP_VIEW();
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er, row = t.I[NJS_I_ROW * P + r];
+                    for (int c_ = ec0; c_ < d4; c_ += LPR) t.IN[(size_t)r * sI + c_] = c_ < c.d ? nj_tanh(t.XI[r * sD + c_]) : 0.f;
+                    for (int c_ = ec0; c_ < H4; c_ += LPR) t.GOUT[(size_t)r * sO + c_] = c_ < c.H ? t.GE[r * sH + c_] : 0.f;
+                    if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 1u)); }
+                }
+                NJ_SYNCWARP();
+                nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, true, true);
+                nj_seg_mlp_dx<TR>(w, NJODE_NET_ENC, false);
+            }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), tid, nt); }
+            NJ_SYNC();
+            // J6: readout at h_before, backward with g = dL/dY_bj -> gradient wrt h at the segment end
+            NJ_WARPS(wp, s.nw_b) {
+                NJ_SEGB_WARP_VIEW();
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er, row = t.I[NJS_I_ROW * P + r];
+                    for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                        t.IN[(size_t)r * sI + c_] = c_ < c.H ? nj_tanh(t.HB[r * sH + c_]) : 0.f;
+                        t.GOUT[(size_t)r * sO + c_] = c_ < c.dout ? t.GYBJ[r * sD + c_] : 0.f;     // also clears J5's H4 columns
+                    }
+                    if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 0u)); }
+                }
+                NJ_SYNCWARP();
+                nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, true, true);
+                nj_seg_mlp_dx<TR>(w, NJODE_NET_RO, true);
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er;
+                    if (t.I[NJS_I_ROW * P + r] >= 0) {
+                        for (int c_ = ec0; c_ < c.H; c_ += LPR) {
+                            const float th = t.IN[(size_t)r * sI + c_];
+                            float gh = t.GZ[(size_t)r * sI + c_] * (1.f - th * th);
+                            if (c.residual) gh += nj_resid_bwd(t.GOUT + (size_t)r * sO, c.H, c.dout, c_);
+                            t.GH[r * sH + c_] = gh;
+                        }
+                    }
+                }
+            }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), tid, nt); }
+            NJ_SYNC();
+        }
+        // ================= Euler steps, reversed =================
+        for (int j = maxlen - 1; j >= 0; --j) {
+            NJ_WARPS(wp, s.nw_b) {
+                NJ_SEGB_WARP_VIEW();
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er;
+                    const bool active = j < t.I[NJS_I_LEN * P + r];
+                    const int k = t.I[NJS_I_S0 * P + r] + j;
+                    const float tau = t.F[NJS_F_TAU * P + r];
+                    const float dt = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
+                    const float* hh = active ? a.h_hist + ((size_t)k * a.b.B + t.I[NJS_I_PATH * P + r]) * c.H : nullptr;
+                    for (int c_ = ec0; c_ < inf4; c_ += LPR) {
+                        float v = 0.f;
+                        if (c_ < c.d) v = t.TX[r * sD + c_];
+                        else if (c_ < c.d + c.H) v = nj_tanh(hh ? hh[c_ - c.d] : 0.f);
+                        else if (c_ < c.inf) {
+                            const float tcur = active ? NJ_LDG(a.b.step_t + k) : 0.f;
+                            if (c_ == c.d + c.H) v = tau;
+                            else if (c_ == c.d + c.H + 1) v = tcur - tau;
+                            else v = tau + (tcur - tau);
+                        }
+                        t.IN[(size_t)r * sI + c_] = v;
+                    }
+                    for (int c_ = ec0; c_ < H4; c_ += LPR) t.GOUT[(size_t)r * sO + c_] = c_ < c.H ? dt * t.GH[r * sH + c_] : 0.f;
+                    if (ec0 == 0) { NJ_SEGB_KEY(r, true, (unsigned)k); }
+                }
+                NJ_SYNCWARP();
+                nj_seg_mlp_fwd<TR>(w, NJODE_NET_ODE, true, true);
+                nj_seg_mlp_dx<TR>(w, NJODE_NET_ODE, true);
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er;
+                    if (j < t.I[NJS_I_LEN * P + r]) {
+                        for (int c_ = ec0; c_ < c.H; c_ += LPR) {
+                            const float th = t.IN[(size_t)r * sI + c.d + c_];
+                            t.GH[r * sH + c_] += t.GZ[(size_t)r * sI + c.d + c_] * (1.f - th * th);
+                        }
+                    }
+                }
+            }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ODE, NJ_ACC(tid), tid, nt); }
+            NJ_SYNC();
+        }
+        // ================= the start encoder, reversed =================
+        NJ_WARPS(wp, s.nw_b) {
+            NJ_SEGB_WARP_VIEW();
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er;
+                const bool valid = t.I[NJS_I_PATH * P + r] >= 0;
+                for (int c_ = ec0; c_ < d4; c_ += LPR) t.IN[(size_t)r * sI + c_] = t.TX[r * sD + c_];
+                for (int c_ = ec0; c_ < H4; c_ += LPR) t.GOUT[(size_t)r * sO + c_] = (c_ < c.H && valid) ? t.GH[r * sH + c_] : 0.f;
+                if (ec0 == 0) { NJ_SEGB_KEY(r, valid, nj_seg_event_of_start(a, t.I[NJS_I_START * P + r])); }
+            }
+            NJ_SYNCWARP();
+            nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, true, true);
+            nj_seg_mlp_dx<TR>(w, NJODE_NET_ENC, false);
+        }
+        NJ_SYNC();
+        NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), tid, nt); }
+        NJ_SYNC();
+    }
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    nj_zero(gpart, c.img_floats, nt);
+    NJ_SYNC();
+    NJ_THREADS(tid, nt) { nj_seg_dw_flush(c, s, NJ_ACC(tid), gpart, tid, nt); }
+}
+
+NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
+    if (s.tr_b == 2) nj_seg_cta_backward_t<2>(c, s, a, smem, cta);
+    else nj_seg_cta_backward_t<1>(c, s, a, smem, cta);
+}

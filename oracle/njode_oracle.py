@@ -73,17 +73,20 @@ def _fmix32(h):
 def dropout_keep_mask(seed, path_ids, event_id, net_id, layer_id, width, p):
     """keep-mask [len(path_ids), width] (float32 0/1) of one MLP hidden layer; restates
     nj_row_key / nj_layer_key / nj_keep of njode_b200/csrc/njode_core.cuh (murmur3 finaliser chain
-    keyed by seed, path, event, net, layer, neuron); keep iff hash >= floor(p * 2^32)."""
+    keyed by seed, path, event, net, layer, neuron pair); keep iff 16-bit field >= floor(p * 2^16)."""
     path_ids = np.asarray(path_ids, dtype=np.uint32)
     seed_lo, seed_hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
-    thr = np.uint32(min(int(np.float32(p).astype(np.float64) * 4294967296.0), 4294967295))
+    thr16 = np.uint32(min(int(np.float32(p).astype(np.float64) * 65536.0), 65536))
     with np.errstate(over="ignore"):
         rk = _fmix32(_fmix32(path_ids ^ seed_lo) + np.uint32(event_id & 0xFFFFFFFF) * np.uint32(0x9E3779B9)) ^ seed_hi
         tag = np.uint32(net_id * 16 + layer_id + 1)
         lk = _fmix32(rk + tag * np.uint32(0x85EBCA77))
         neuron = np.arange(width, dtype=np.uint32)[None, :]
-        el = _fmix32(lk[:, None] + neuron * np.uint32(0xC2B2AE3D))
-    return (el >= thr).astype(np.float32)
+        # one 32-bit word per neuron pair (o, o ^ 8): 16-bit fields (nj_keep in njode_core.cuh)
+        widx = (neuron & np.uint32(7)) | ((neuron >> np.uint32(4)) << np.uint32(3))
+        word = _fmix32(lk[:, None] + widx * np.uint32(0xC2B2AE3D))
+        field = np.where(((neuron >> np.uint32(3)) & np.uint32(1)) == 1, word >> np.uint32(16), word & np.uint32(0xFFFF))
+    return (field >= thr16).astype(np.float32)
 
 
 NET_ODE, NET_ENC, NET_RO = 0, 1, 2

@@ -21,6 +21,7 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
     std::string err;
     const char* fp = getenv("NJODE_FORCE_TILE");
     if (!nj_make_plan(*m, b->n_units, b->n_units, b->N, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
+    nj_make_seg(out.fwd, b->unit_kind, b->E, b->n_units, kSimSMs, kSimSmem, out);
     const size_t cap = (size_t)kSimSMs * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
     out.ws_bytes = out.ws_partials_off + cap * out.fwd.img_floats * sizeof(float);
@@ -57,6 +58,7 @@ static void fill_args(NjArgs& a, const njode_batch_t* b, const NjPlanOut& pl, ch
     a.image = reinterpret_cast<const float*>(ws + pl.ws_image_off);
     a.row_loss = reinterpret_cast<float*>(ws + pl.ws_rowloss_off);
     a.partials = reinterpret_cast<float*>(ws + pl.ws_partials_off);
+    a.counter = reinterpret_cast<int*>(ws + pl.ws_counter_off);
 }
 
 extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* batch, const float* params,
@@ -74,10 +76,19 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     a.n_tiles = pl.n_tiles;
     pack(pl.fwd, params, const_cast<float*>(a.image));
     for (int i = 0; i < batch->N; ++i) a.row_loss[i] = 0.f;
-    std::vector<float> smem(pl.fwd.smem_floats_fwd);
-    for (int cta = 0; cta < pl.grid_fwd && batch->n_units > 0; ++cta) {
-        std::fill(smem.begin(), smem.end(), NAN);       // uninitialised shared memory must never matter
-        nj_cta_forward(pl.fwd, a, smem.data(), cta, pl.grid_fwd);
+    if (pl.seg.ok) {
+        std::vector<float> smem(pl.seg.f_smem_floats);
+        for (int cta = 0; cta < pl.seg_grid_f; ++cta) {
+            std::fill(smem.begin(), smem.end(), NAN);
+            if (cta == 0) *a.counter = 0;
+            nj_seg_cta_forward(pl.fwd, pl.seg, a, smem.data());
+        }
+    } else {
+        std::vector<float> smem(pl.fwd.smem_floats_fwd);
+        for (int cta = 0; cta < pl.grid_fwd && batch->n_units > 0; ++cta) {
+            std::fill(smem.begin(), smem.end(), NAN);       // uninitialised shared memory must never matter
+            nj_cta_forward(pl.fwd, a, smem.data(), cta, pl.grid_fwd);
+        }
     }
     if (loss) {
         double s = 0.0;
@@ -97,12 +108,22 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     a.h_hist = saved->h_hist; a.h_before = saved->h_before; a.y_after = saved->y_after;
     a.grad_loss = grad_loss; a.grad_hT = grad_hT; a.get_loss = 1; a.n_tiles = pl.n_tiles;
     pack(pl.bwd, params, const_cast<float*>(a.image));
-    std::vector<float> smem(pl.bwd.smem_floats_bwd);
     int nparts = 0;
-    for (int cta = 0; cta < pl.grid_bwd && batch->n_units > 0; ++cta) {
-        std::fill(smem.begin(), smem.end(), NAN);
-        nj_cta_backward(pl.bwd, a, smem.data(), cta, pl.grid_bwd);
-        nparts = pl.grid_bwd;
+    if (pl.seg.ok) {
+        std::vector<float> smem(pl.seg.b_smem_floats);
+        for (int cta = 0; cta < pl.seg_grid_b; ++cta) {
+            std::fill(smem.begin(), smem.end(), NAN);
+            if (cta == 0) *a.counter = 0;
+            nj_seg_cta_backward(pl.bwd, pl.seg, a, smem.data(), cta);
+        }
+        nparts = pl.seg_grid_b;
+    } else {
+        std::vector<float> smem(pl.bwd.smem_floats_bwd);
+        for (int cta = 0; cta < pl.grid_bwd && batch->n_units > 0; ++cta) {
+            std::fill(smem.begin(), smem.end(), NAN);
+            nj_cta_backward(pl.bwd, a, smem.data(), cta, pl.grid_bwd);
+            nparts = pl.grid_bwd;
+        }
     }
     const NjCfg& c = pl.bwd;
     for (int n = 0; n < 3; ++n) {

@@ -22,6 +22,8 @@ def sim_runner():
     yield
     models._TEST_RUNNER = None
     os.environ.pop("NJODE_FORCE_TILE", None)
+    os.environ.pop("NJODE_FORCE_TR", None)
+    os.environ.pop("NJODE_NO_SEG", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -81,3 +83,38 @@ def test_global_weight_image_path():
                          readout_nn=[[256, "tanh"]])
     batch = cases.grid_batch(6, 4, 5, 0.4, seed=8)
     parity_util.check_against_oracle(cfg, batch, 0.2, 1.0, seed=4, device="cpu")
+
+
+# ---- segment fast path (njode_b200/csrc/njode_seg.cuh): every tile height, train and eval ----
+SEG_NAMES = [n for n in NAMES if "masked" not in n]
+
+
+@pytest.mark.parametrize("tr", [1, 2, 4])
+@pytest.mark.parametrize("name", SEG_NAMES)
+def test_segment_path_tile_heights(name, tr):
+    os.environ["NJODE_FORCE_TR"] = str(tr)
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    parity_util.check_training_call(name, "cpu")
+
+
+@pytest.mark.parametrize("name", ["bs_ckpt1", "curt_nobias_relu"])
+def test_generic_kernels_still_serve_segment_units(name):
+    os.environ["NJODE_NO_SEG"] = "1"
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+
+
+@pytest.mark.parametrize("tr", [1, 2, 4])
+def test_segment_path_dropout_masks_replayed_by_oracle(tr):
+    os.environ["NJODE_FORCE_TR"] = str(tr)
+    cfg = cases.demo_cfg(dropout_rate=0.2)
+    batch = cases.grid_batch(40, 1, 25, 0.2, seed=16)
+    parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
+
+
+def test_segment_path_wide_layers_use_output_chunks():
+    """hidden width 100 > 64: two output chunks per layer in the warp GEMM"""
+    cfg = cases.demo_cfg(input_size=2, output_size=2, hidden_size=6, dropout_rate=0.1,
+                         ode_nn=[[100, "tanh"], [70, "relu"]], enc_nn=[[100, "tanh"]], readout_nn=[[33, "tanh"]])
+    batch = cases.grid_batch(20, 2, 10, 0.3, seed=18)
+    parity_util.check_against_oracle(cfg, batch, 0.1, 1.0, seed=14, device="cpu", train=True, grad_hT=True)
+    parity_util.check_against_oracle(cfg, batch, 0.1, 1.0, seed=14, device="cpu", train=False)
