@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define NJODE_ABI_VERSION 2
+#define NJODE_ABI_VERSION 3
 #define NJODE_MAX_LINEAR 8          /* max number of Linear layers per network */
 
 enum { NJODE_ACT_NONE = 0, NJODE_ACT_TANH = 1, NJODE_ACT_RELU = 2 };
@@ -68,6 +68,12 @@ typedef struct njode_batch {
     int32_t unit_kind;         /* 0: whole paths; 1: (path, inter-observation segment) units -- each loss
                                   unit ends with exactly one jump (c1 = c0 + 1, s1 = jump_step of its row),
                                   tail units have none; enables the segment fast path (non-masked model) */
+    int32_t n_loss_units;      /* unit_kind 1: units [0, n_loss_units) end with a jump (sorted longest first),
+                                  units [n_loss_units, n_units) are the tails (sorted longest first) */
+    int32_t seg_n1[2];         /* per run (loss, tail): number of units with length >= T1 ... */
+    int32_t seg_n2[2];         /* ... and >= T2 (T1 >= T2, chosen by the host from the batch's total work):
+                                  long units are marched in lower tiles so that no tile's sequential chain
+                                  of Euler steps dominates the makespan */
     int32_t reserved0;
     const float*   X;          /* [N, input_size] */
     const float*   M;          /* [N, input_size] or NULL */

@@ -32,7 +32,8 @@ class ModelT(C.Structure):
 class BatchT(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("S", C.c_int32),
                 ("E", C.c_int32), ("batch_size_norm", C.c_int32), ("path_id_offset", C.c_int32),
-                ("n_units", C.c_int32), ("unit_kind", C.c_int32), ("reserved0", C.c_int32),
+                ("n_units", C.c_int32), ("unit_kind", C.c_int32), ("n_loss_units", C.c_int32),
+                ("seg_n1", C.c_int32 * 2), ("seg_n2", C.c_int32 * 2), ("reserved0", C.c_int32),
                 ("X", C.c_void_p), ("M", C.c_void_p), ("start_X", C.c_void_p), ("n_obs_ot", C.c_void_p),
                 ("path_ptr", C.c_void_p), ("path_rows", C.c_void_p), ("row_jump", C.c_void_p),
                 ("step_dt", C.c_void_p), ("step_t", C.c_void_p), ("jump_step", C.c_void_p),
@@ -89,7 +90,7 @@ class Lib:
                                      C.c_void_p, C.c_void_p]
         for f in (d.njode_plan, d.njode_forward, d.njode_backward):
             f.restype = C.c_int
-        if d.njode_abi_version() != 2:
+        if d.njode_abi_version() != 3:
             raise NjodeError("njode_b200: ABI version mismatch in %s" % path)
 
     def check(self, rc, what):
@@ -124,6 +125,7 @@ class Runner:
         self.lib = lib
         self.device = torch.device(device)
         self.is_cuda = self.device.type == "cuda"
+        self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.is_cuda else 4
         self._ws = None
         self._pin = None
         self._pin_event = None
@@ -199,8 +201,20 @@ class Runner:
                 return C.c_void_p(a.data_ptr())
             return C.c_void_p(base + offs[k])
 
+        # tile-height classes of the segment kernels: units at least T1 (T2) Euler steps long are marched
+        # in the lowest (middle) tiles; thresholds follow the per-warp share of the batch's total work
+        seg_n1, seg_n2 = (C.c_int32 * 2)(0, 0), (C.c_int32 * 2)(0, 0)
+        if segments and len(units):
+            lens = (units[:, 2] - units[:, 1]).astype(np.int64)
+            budget = float(lens.sum()) / (16.0 * self.sms * 12)
+            T1, T2 = max(8, int(0.75 * budget)), max(4, int(0.4 * budget))
+            for r, run in enumerate((lens[:n_loss], lens[n_loss:])):
+                seg_n1[r] = int(np.count_nonzero(run >= T1))
+                seg_n2[r] = int(np.count_nonzero(run >= T2))
+
         def make(n_units):
-            return BatchT(B=B, N=N, K=sched.K, S=sched.S, E=sched.E,
+            return BatchT(B=B, N=N, K=sched.K, S=sched.S, E=sched.E, n_loss_units=int(n_loss),
+                          seg_n1=seg_n1, seg_n2=seg_n2,
                           batch_size_norm=int(batch_size_norm or B), path_id_offset=int(path_id_offset),
                           n_units=int(n_units), unit_kind=1 if segments else 0, X=p("X"), M=p("M"), start_X=p("start_X"),
                           n_obs_ot=p("n_obs_ot"), path_ptr=p("path_ptr"), path_rows=p("path_rows"),

@@ -35,31 +35,14 @@ __global__ void __launch_bounds__(256) nj_bwd_kernel(const __grid_constant__ NjC
     nj_cta_backward(cfg, args, nj_smem, blockIdx.x, gridDim.x);
 }
 
-template <int TR>
-__global__ void __launch_bounds__(TR == 4 ? 384 : 512) nj_seg_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+__global__ void __launch_bounds__(384) nj_seg_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
                                                          const __grid_constant__ NjArgs args) {
-    nj_seg_cta_forward_t<TR>(cfg, seg, args, nj_smem);
+    nj_seg_cta_forward(cfg, seg, args, nj_smem);
 }
 
-template <int TR>
 __global__ void __launch_bounds__(384) nj_seg_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
                                                          const __grid_constant__ NjArgs args) {
-    nj_seg_cta_backward_t<TR>(cfg, seg, args, nj_smem, blockIdx.x);
-}
-
-template <int TR>
-static cudaError_t nj_launch_seg_fwd(const NjPlanOut& pl, const NjArgs& a, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(nj_seg_fwd_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes);
-    if (e != cudaSuccess) return e;
-    nj_seg_fwd_kernel<TR><<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
-    return cudaSuccess;
-}
-template <int TR>
-static cudaError_t nj_launch_seg_bwd(const NjPlanOut& pl, const NjArgs& a, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(nj_seg_bwd_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes);
-    if (e != cudaSuccess) return e;
-    nj_seg_bwd_kernel<TR><<<pl.seg_grid_b, pl.seg.nw_b * 32, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
-    return cudaSuccess;
+    nj_seg_cta_backward(cfg, seg, args, nj_smem, blockIdx.x);
 }
 
 // flat parameters -> zero-padded image; one block per (net, layer)
@@ -157,7 +140,7 @@ static int nj_plan_for(const njode_model_t* model, const njode_batch_t* b, int d
     const char* fp = getenv("NJODE_FORCE_TILE");
     if (!nj_make_plan(*model, b->n_units, b->n_units, b->N, di.sms, di.smem_optin, fp ? atoi(fp) : 0, out, err))
         return nj_fail(-3, err);
-    nj_make_seg(out.fwd, b->unit_kind, b->E, b->n_units, di.sms, di.smem_optin, out);
+    nj_make_seg(out.fwd, *b, di.sms, di.smem_optin, out);
     // gradient partials: sized for the largest grid any backward launch of this model may use
     const size_t cap = (size_t)di.sms * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
@@ -212,9 +195,8 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     if (pl.seg.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[0], st);
-        if (pl.seg.tr_f == 4) NJ_CUDA(nj_launch_seg_fwd<4>(pl, a, st));
-        else if (pl.seg.tr_f == 2) NJ_CUDA(nj_launch_seg_fwd<2>(pl, a, st));
-        else NJ_CUDA(nj_launch_seg_fwd<1>(pl, a, st));
+        NJ_CUDA(cudaFuncSetAttribute(nj_seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
+        nj_seg_fwd_kernel<<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
     } else {
         NJ_CUDA(cudaFuncSetAttribute(nj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd_bytes));
         if (tm) cudaEventRecord(g_ev[0], st);
@@ -253,8 +235,8 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.seg_grid_b;
-        if (pl.seg.tr_b == 2) NJ_CUDA(nj_launch_seg_bwd<2>(pl, a, st));
-        else NJ_CUDA(nj_launch_seg_bwd<1>(pl, a, st));
+        NJ_CUDA(cudaFuncSetAttribute(nj_seg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
+        nj_seg_bwd_kernel<<<pl.seg_grid_b, pl.seg.nw_b * 32, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
     } else {
         NJ_CUDA(cudaFuncSetAttribute(nj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd_bytes));
         if (tm) cudaEventRecord(g_ev[2], st);

@@ -216,13 +216,37 @@ static inline int nj_seg_bwd_layout(const NjCfg& c, NjSeg& s, int P) {
     return (o + 3) & ~3;
 }
 
-static inline void nj_make_seg(const NjCfg& c, int unit_kind, int E, int n_units, int num_sms, size_t smem_limit,
-                               NjPlanOut& out) {
+// classes of tile heights over the two sorted unit runs (loss units, tail units); see NjSeg
+static inline int nj_seg_classes(const int run_b[2], const int run_e[2], const int n1[2], const int n2[2],
+                                 const int* trs, int ntr, int rows_per_tr, int* t0, int* u0, int* u1, int* trc) {
+    // trs: tile heights from lowest to tallest, e.g. {1, 2, 4}; cut points: n1 (-> trs[0]), n2 (-> trs[1]), rest
+    int ncls = 0, tiles = 0;
+    for (int k = 0; k < ntr; ++k) {
+        for (int r = 0; r < 2; ++r) {
+            const int len = run_e[r] - run_b[r];
+            int cut[4] = {0, std::min(n1[r], len), std::min(std::max(n2[r], n1[r]), len), len};
+            int lo, hi;
+            if (ntr == 3) { lo = cut[k]; hi = cut[k + 1]; }
+            else if (ntr == 2) { lo = k == 0 ? 0 : cut[1]; hi = k == 0 ? cut[1] : len; }
+            else { lo = 0; hi = len; }
+            if (hi <= lo) continue;
+            const int rows = rows_per_tr * trs[k];
+            t0[ncls] = tiles; u0[ncls] = run_b[r] + lo; u1[ncls] = run_b[r] + hi; trc[ncls] = trs[k];
+            tiles += (hi - lo + rows - 1) / rows;
+            ++ncls;
+        }
+    }
+    t0[ncls] = tiles;
+    return ncls;
+}
+
+static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_sms, size_t smem_limit, NjPlanOut& out) {
     NjSeg& s = out.seg;
     memset(&s, 0, sizeof(s));
+    const int n_units = b.n_units;
     const char* off = getenv("NJODE_NO_SEG");
     if (off && atoi(off)) return;
-    if (unit_kind != 1 || c.masked || E > 0 || n_units <= 0) return;
+    if (b.unit_kind != 1 || c.masked || b.E > 0 || n_units <= 0) return;
     int maxhid = 1, maxn = 1, maxlast = 1;
     for (int n = 0; n < 3; ++n) {
         const NjNet& N = c.net[n];
@@ -248,39 +272,39 @@ static inline void nj_make_seg(const NjCfg& c, int unit_kind, int E, int n_units
     s.tiles_total = tiles;
     const char* ftr = getenv("NJODE_FORCE_TR");
     const int force_tr = ftr ? atoi(ftr) : 0;
-    // ---- forward: per-warp regions of R = 4*TR rows; smaller tiles when the batch cannot fill the GPU ----
+    const int n_loss = std::max(0, std::min(b.n_loss_units, n_units));
+    const int run_b[2] = {0, n_loss}, run_e[2] = {n_loss, n_units};
+    int n1[2] = {b.seg_n1[0], b.seg_n1[1]}, n2[2] = {b.seg_n2[0], b.seg_n2[1]};
+    // ---- forward: per-warp regions sized for the tallest tile (16 rows) ----
     {
-        int tr = 4;
-        while (tr > 1 && (n_units + 4 * tr - 1) / (4 * tr) < num_sms * 8) tr >>= 1;
-        if (force_tr) tr = std::min(4, force_tr);
-        s.tr_f = tr;
-        const int R = 4 * tr;
-        s.f_region = nj_seg_fwd_region(c, s, R);
+        s.f_region = nj_seg_fwd_region(c, s, 16);
         s.f_img = 0; s.f_warp0 = c.img_floats;
         int nw = 0;
-        for (int cand = (tr == 4 ? 12 : 16); cand >= 2; --cand)          // launch bounds: 384 (TR=4) / 512 threads
+        for (int cand = 12; cand >= 2; --cand)          // launch bounds: 384 threads
             if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
         if (!nw) return;
         s.nw_f = nw;
         s.f_smem_floats = c.img_floats + nw * s.f_region;
-        s.n_tiles_f = (n_units + R - 1) / R;
+        static const int trs3[3] = {1, 2, 4};
+        if (force_tr) { const int one[1] = {std::min(4, force_tr)}; s.f_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr); }
+        else s.f_ncls = nj_seg_classes(run_b, run_e, n1, n2, trs3, 3, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr);
+        s.n_tiles_f = s.f_t0[s.f_ncls];
     }
-    // ---- backward: CTA-level arrays of P = R * nw rows ----
+    // ---- backward: CTA-level arrays of P = 8 * nw rows (tallest tile) ----
     {
         const int min_nw = (tiles + NJ_SEG_NT_MAX * 32 - 1) / (NJ_SEG_NT_MAX * 32);
-        int tr = 2, nw = 0;
-        if (force_tr) tr = std::min(2, force_tr);
-        for (; tr >= 1 && !nw; tr >>= 1) {
-            for (int cand = 12; cand >= std::max(2, min_nw); --cand) {       // launch bounds: 384 threads
-                const int fl = nj_seg_bwd_layout(c, s, 4 * tr * cand);
-                if ((size_t)fl * 4 <= smem_limit) { nw = cand; s.b_smem_floats = fl; s.P_b = 4 * tr * cand; s.tr_b = tr; break; }
-            }
-            if (nw && tr == 2 && !force_tr && (n_units + s.P_b - 1) / s.P_b < num_sms) nw = 0;   // too few CTA tiles: halve the rows
+        int nw = 0;
+        for (int cand = 12; cand >= std::max(2, min_nw); --cand) {       // launch bounds: 384 threads
+            const int fl = nj_seg_bwd_layout(c, s, 8 * cand);
+            if ((size_t)fl * 4 <= smem_limit) { nw = cand; s.b_smem_floats = fl; s.P_b = 8 * cand; break; }
         }
         if (!nw) return;
         s.nw_b = nw;
         s.nt_slots = (tiles + nw * 32 - 1) / (nw * 32);
-        s.n_tiles_b = (n_units + s.P_b - 1) / s.P_b;
+        static const int trs2[2] = {1, 2};
+        if (force_tr) { const int one[1] = {std::min(2, force_tr)}; s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr); }
+        else s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, trs2, 2, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr);
+        s.n_tiles_b = s.b_t0[s.b_ncls];
     }
     out.seg_smem_f_bytes = (size_t)s.f_smem_floats * 4;
     out.seg_smem_b_bytes = (size_t)s.b_smem_floats * 4;

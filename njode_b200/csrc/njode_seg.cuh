@@ -39,6 +39,25 @@ __device__ __forceinline__ unsigned nj_f2u(float f) { return __float_as_uint(f);
 __device__ __forceinline__ float nj_u2f(unsigned u) { return __uint_as_float(u); }
 #endif
 
+// shared-memory operand pointers of the GEMM inner loops: on the device a 32-bit shared-window address read
+// with ld.shared.v4.f32 (the generic-pointer path lost the 128-bit vector width behind the non-inlined
+// layer functions); on the host simulation a plain pointer.
+#if defined(NJODE_HOST_SIM)
+typedef const float* nj_sp;
+static inline nj_sp nj_sp_of(const float* p) { return p; }
+static inline nj_f4 nj_sp_ld4(nj_sp p) { return nj_ld4(p); }
+#define NJ_SP_ADD(p, nfloats) ((p) + (nfloats))
+#else
+typedef unsigned nj_sp;
+__device__ __forceinline__ nj_sp nj_sp_of(const float* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ nj_f4 nj_sp_ld4(nj_sp p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(p) : "memory");
+    return v;
+}
+#define NJ_SP_ADD(p, nfloats) ((p) + 4u * (unsigned)(nfloats))
+#endif
+
 #define NJ_SEG_NT_MAX 2            // dW tiles (4x4 + bias) a thread may own in registers
 #define NJ_SEG_ACC (NJ_SEG_NT_MAX * 20)
 #define NJ_DROPPED 0x80000000u     // bit pattern (-0.0f) of a dropped activation
@@ -60,7 +79,23 @@ struct NjSeg {
     int n_tiles_f, n_tiles_b;       // warp tiles (forward), CTA tiles (backward)
     int tile_base[3][NJODE_MAX_LINEAR];   // first dW tile id of (net, layer); order ODE, RO, ENC
     int tiles_total, nt_slots;
+    // work tiles come in classes of equal height: long units get low tiles (TR = 1), short ones tall tiles,
+    // so that no tile's sequential chain of Euler steps dominates the makespan.  Class i serves the units
+    // [u0, u1) in tiles of 4*tr (forward, per warp) or 4*tr*nw_b (backward, per CTA) rows; t0 = first tile id.
+    int f_ncls, f_t0[7], f_u0[6], f_u1[6], f_tr[6];
+    int b_ncls, b_t0[7], b_u0[6], b_u1[6], b_tr[6];
 };
+
+// tile id -> (class, first unit, one-past-last unit)
+NJ_HD int nj_seg_tile_lookup(int ncls, const int* t0, const int* u0, const int* u1, const int* tr, int rows_per_tr,
+                             int tile, int& ub, int& ue) {
+    int ci = 0;
+    for (int i = 1; i < ncls; ++i) if (tile >= t0[i]) ci = i;
+    const int rows = rows_per_tr * tr[ci];
+    ub = u0[ci] + (tile - t0[ci]) * rows;
+    ue = ub + rows < u1[ci] ? ub + rows : u1[ci];
+    return tr[ci];
+}
 
 enum { NJS_I_PATH = 0, NJS_I_S0, NJS_I_LEN, NJS_I_ROW, NJS_I_START, NJS_I_FLAG, NJS_I_RK, NJS_I_COUNT };
 enum { NJS_F_TAU = 0, NJS_F_DT, NJS_F_CA, NJS_F_CB, NJS_F_COUNT };
@@ -90,19 +125,18 @@ NJ_HD void nj_wg_fwd(const NjWL& L, int lane) {
 #pragma unroll
         for (int i = 0; i < TR; ++i) acc[i][j] = b;
     }
-    const float* ap[TR];
-    const float* wp[TO];
+    nj_sp ap[TR], wp[TO];
 #pragma unroll
-    for (int i = 0; i < TR; ++i) ap[i] = L.in + (size_t)(rg + 4 * i) * L.in_s;
+    for (int i = 0; i < TR; ++i) ap[i] = nj_sp_of(L.in + (size_t)(rg + 4 * i) * L.in_s);
 #pragma unroll
-    for (int j = 0; j < TO; ++j) wp[j] = L.W + (size_t)(L.o_base + og + 8 * j) * L.w_s;
+    for (int j = 0; j < TO; ++j) wp[j] = nj_sp_of(L.W + (size_t)(L.o_base + og + 8 * j) * L.w_s);
 #pragma unroll 2
     for (int k4 = 0; k4 < L.K4; ++k4) {
         nj_f4 a[TR], w[TO];
 #pragma unroll
-        for (int i = 0; i < TR; ++i) a[i] = nj_ld4(ap[i] + 4 * k4);
+        for (int i = 0; i < TR; ++i) a[i] = nj_sp_ld4(NJ_SP_ADD(ap[i], 4 * k4));
 #pragma unroll
-        for (int j = 0; j < TO; ++j) w[j] = nj_ld4(wp[j] + 4 * k4);
+        for (int j = 0; j < TO; ++j) w[j] = nj_sp_ld4(NJ_SP_ADD(wp[j], 4 * k4));
 #pragma unroll
         for (int i = 0; i < TR; ++i)
 #pragma unroll
@@ -189,25 +223,24 @@ NJ_HD void nj_wg_dx(const NjWD& L, int lane) {
         for (int jk = 0; jk < TK; ++jk)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[i][jk][c] = 0.f;
-    const float* wp[TK];
+    nj_sp wp[TK], gp[TR];
 #pragma unroll
     for (int jk = 0; jk < TK; ++jk) {
         int kg = L.kg_base + kq + 8 * jk;
         kg = kg < L.K4in ? kg : L.K4in - 1;          // clamped lanes compute a duplicate, never store
-        wp[jk] = L.W + 4 * kg;
+        wp[jk] = nj_sp_of(L.W + 4 * kg);
     }
-    const float* gp[TR];
 #pragma unroll
-    for (int i = 0; i < TR; ++i) gp[i] = L.g + (size_t)(rg + 4 * i) * L.g_s;
+    for (int i = 0; i < TR; ++i) gp[i] = nj_sp_of(L.g + (size_t)(rg + 4 * i) * L.g_s);
     const int ws = L.w_s;
     for (int o4 = 0; o4 < L.O4; ++o4) {
         nj_f4 gv[TR];
 #pragma unroll
-        for (int i = 0; i < TR; ++i) gv[i] = nj_ld4(gp[i] + 4 * o4);
+        for (int i = 0; i < TR; ++i) gv[i] = nj_sp_ld4(NJ_SP_ADD(gp[i], 4 * o4));
 #pragma unroll
         for (int jk = 0; jk < TK; ++jk) {
-            const float* q = wp[jk] + (size_t)(4 * o4) * ws;
-            const nj_f4 w0 = nj_ld4(q), w1 = nj_ld4(q + ws), w2 = nj_ld4(q + 2 * ws), w3 = nj_ld4(q + 3 * ws);
+            const nj_sp q = NJ_SP_ADD(wp[jk], 4 * o4 * ws);
+            const nj_f4 w0 = nj_sp_ld4(q), w1 = nj_sp_ld4(NJ_SP_ADD(q, ws)), w2 = nj_sp_ld4(NJ_SP_ADD(q, 2 * ws)), w3 = nj_sp_ld4(NJ_SP_ADD(q, 3 * ws));
 #pragma unroll
             for (int i = 0; i < TR; ++i) {
                 acc[i][jk][0] = fmaf(gv[i].x, w0.x, fmaf(gv[i].y, w1.x, fmaf(gv[i].z, w2.x, fmaf(gv[i].w, w3.x, acc[i][jk][0]))));
@@ -226,7 +259,7 @@ NJ_HD void nj_wg_dx(const NjWD& L, int lane) {
             if (kg >= L.K4in) continue;
             float v[4] = {acc[i][jk][0], acc[i][jk][1], acc[i][jk][2], acc[i][jk][3]};
             if (L.aprev) {
-                const nj_f4 av = nj_ld4(L.aprev + (size_t)r * L.a_s + 4 * kg);
+                const nj_f4 av = nj_sp_ld4(nj_sp_of(L.aprev + (size_t)r * L.a_s + 4 * kg));
                 const float a4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -340,8 +373,9 @@ NJ_HD unsigned nj_seg_event_of_jump(const NjArgs& a, int row, unsigned which) {
 // forward: one warp = R = 4*TR units
 // ------------------------------------------------------------------------------------------------
 template <int TR>
-NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* reg, const float* wimg, int wtile) {
+NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* reg, const float* wimg, int u0, int u1) {
     constexpr int R = 4 * TR;
+    constexpr int RS = 16;             // row-slot stride of the per-warp scalar arrays (tallest tile)
     NjSegW w;
     w.c = &c; w.s = &s; w.wimg = wimg;
     w.IN = reg + s.f_IN; w.A0 = reg + s.f_A0; w.A1 = reg + s.f_A1; w.OUT = reg + s.f_OUT;
@@ -349,37 +383,36 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     float* HS = reg + s.f_HS; float* LX = reg + s.f_LX; float* TX = reg + s.f_TX; float* XI = reg + s.f_XI;
     float* YBJ = reg + s.f_YBJ; float* F = reg + s.f_F;
     int* I = reinterpret_cast<int*>(reg + s.f_I);
-    w.RK = I + NJS_I_RK * R;
-    const int u0 = wtile * R;
+    w.RK = I + NJS_I_RK * RS;
     const int d4 = ((c.d + 3) >> 2) << 2, H4 = ((c.H + 3) >> 2) << 2, inf4 = ((c.inf + 3) >> 2) << 2;
     const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
     // ---- unit descriptors ----
     NJ_LANES(lane) {
         if (lane < R) {
             const int u = u0 + lane;
-            if (u < a.b.n_units) {
+            if (u < u1) {
                 const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
                 const int sc = dsc[5];
-                I[NJS_I_PATH * R + lane] = dsc[0]; I[NJS_I_S0 * R + lane] = dsc[1]; I[NJS_I_LEN * R + lane] = dsc[2] - dsc[1];
-                I[NJS_I_ROW * R + lane] = dsc[4] > dsc[3] ? NJ_LDG(a.b.path_rows + dsc[3]) : -1;
-                I[NJS_I_FLAG * R + lane] = (sc & NJODE_UNIT_WRITES_HT) ? 1 : 0;
-                I[NJS_I_START * R + lane] = (sc & ~NJODE_UNIT_WRITES_HT) - 1;
+                I[NJS_I_PATH * RS + lane] = dsc[0]; I[NJS_I_S0 * RS + lane] = dsc[1]; I[NJS_I_LEN * RS + lane] = dsc[2] - dsc[1];
+                I[NJS_I_ROW * RS + lane] = dsc[4] > dsc[3] ? NJ_LDG(a.b.path_rows + dsc[3]) : -1;
+                I[NJS_I_FLAG * RS + lane] = (sc & NJODE_UNIT_WRITES_HT) ? 1 : 0;
+                I[NJS_I_START * RS + lane] = (sc & ~NJODE_UNIT_WRITES_HT) - 1;
             } else {
-                I[NJS_I_PATH * R + lane] = -1; I[NJS_I_S0 * R + lane] = 0; I[NJS_I_LEN * R + lane] = 0;
-                I[NJS_I_ROW * R + lane] = -1; I[NJS_I_FLAG * R + lane] = 0; I[NJS_I_START * R + lane] = -1;
+                I[NJS_I_PATH * RS + lane] = -1; I[NJS_I_S0 * RS + lane] = 0; I[NJS_I_LEN * RS + lane] = 0;
+                I[NJS_I_ROW * RS + lane] = -1; I[NJS_I_FLAG * RS + lane] = 0; I[NJS_I_START * RS + lane] = -1;
             }
         }
     }
     NJ_SYNCWARP();
     int maxlen = 0, any_jump = 0;
     for (int r = 0; r < R; ++r) {
-        maxlen = I[NJS_I_LEN * R + r] > maxlen ? I[NJS_I_LEN * R + r] : maxlen;
-        any_jump |= (I[NJS_I_ROW * R + r] >= 0);
+        maxlen = I[NJS_I_LEN * RS + r] > maxlen ? I[NJS_I_LEN * RS + r] : maxlen;
+        any_jump |= (I[NJS_I_ROW * RS + r] >= 0);
     }
     // ---- start: h = encoder(start value); last_X, tanh(last_X), tau stay fixed for the whole unit ----
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
-        const int p = I[NJS_I_PATH * R + er], sr = I[NJS_I_START * R + er];
+        const int p = I[NJS_I_PATH * RS + er], sr = I[NJS_I_START * RS + er];
         for (int c_ = ec0; c_ < d4; c_ += LPR) {
             float x = 0.f;
             if (p >= 0 && c_ < c.d) x = sr < 0 ? NJ_LDG(a.b.start_X + (size_t)p * c.d + c_) : NJ_LDG(a.b.X + (size_t)sr * c.d + c_);
@@ -388,7 +421,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
             w.IN[(size_t)er * sI + c_] = tx;
         }
         if (ec0 == 0) {
-            F[NJS_F_TAU * R + er] = (p >= 0 && sr >= 0) ? NJ_LDG(a.b.jump_tau + NJ_LDG(a.b.row_jump + sr)) : 0.f;
+            F[NJS_F_TAU * RS + er] = (p >= 0 && sr >= 0) ? NJ_LDG(a.b.jump_tau + NJ_LDG(a.b.row_jump + sr)) : 0.f;
             w.RK[er] = p >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), nj_seg_event_of_start(a, sr)) : 0;
         }
     }
@@ -407,10 +440,10 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     for (int j = 0; j < maxlen; ++j) {
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
-            const bool active = j < I[NJS_I_LEN * R + er];
-            const int k = I[NJS_I_S0 * R + er] + j;
-            const int p = I[NJS_I_PATH * R + er];
-            const float tau = F[NJS_F_TAU * R + er];
+            const bool active = j < I[NJS_I_LEN * RS + er];
+            const int k = I[NJS_I_S0 * RS + er] + j;
+            const int p = I[NJS_I_PATH * RS + er];
+            const float tau = F[NJS_F_TAU * RS + er];
             float* hh = (active && a.h_hist) ? a.h_hist + ((size_t)k * a.b.B + p) * c.H : nullptr;
             for (int c_ = ec0; c_ < inf4; c_ += LPR) {
                 float v = 0.f;
@@ -428,7 +461,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
                 w.IN[(size_t)er * sI + c_] = v;
             }
             if (ec0 == 0) {
-                F[NJS_F_DT * R + er] = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
+                F[NJS_F_DT * RS + er] = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
                 w.RK[er] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
             }
         }
@@ -436,8 +469,8 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
         nj_seg_mlp_fwd<TR>(w, NJODE_NET_ODE, false, false);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
-            if (j < I[NJS_I_LEN * R + er]) {
-                const float dt = F[NJS_F_DT * R + er];
+            if (j < I[NJS_I_LEN * RS + er]) {
+                const float dt = F[NJS_F_DT * RS + er];
                 for (int c_ = ec0; c_ < c.H; c_ += LPR)
                     HS[er * sH + c_] = fmaf(dt, w.OUT[er * sO + c_], HS[er * sH + c_]);
             }
@@ -447,8 +480,8 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     // ---- hT of the units that end their path ----
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
-        if (I[NJS_I_FLAG * R + er]) {
-            float* dst = a.hT + (size_t)I[NJS_I_PATH * R + er] * c.H;
+        if (I[NJS_I_FLAG * RS + er]) {
+            float* dst = a.hT + (size_t)I[NJS_I_PATH * RS + er] * c.H;
             for (int c_ = ec0; c_ < c.H; c_ += LPR) dst[c_] = HS[er * sH + c_];
         }
     }
@@ -456,7 +489,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     // ---- the jump that ends the segment (NJODE/models.py:449-489) ----
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
-        const int row = I[NJS_I_ROW * R + er], p = I[NJS_I_PATH * R + er];
+        const int row = I[NJS_I_ROW * RS + er], p = I[NJS_I_PATH * RS + er];
         for (int c_ = ec0; c_ < H4; c_ += LPR) {
             float h = 0.f;
             if (row >= 0 && c_ < c.H) {
@@ -472,7 +505,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, false, false);
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
-        const int row = I[NJS_I_ROW * R + er], p = I[NJS_I_PATH * R + er];
+        const int row = I[NJS_I_ROW * RS + er], p = I[NJS_I_PATH * RS + er];
         for (int c_ = ec0; c_ < c.dout; c_ += LPR) {
             float y = w.OUT[er * sO + c_];
             if (c.residual) y += nj_resid(HS + er * sH, c.H, c.dout, c_);
@@ -491,7 +524,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, false, false);
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
-        const int row = I[NJS_I_ROW * R + er], p = I[NJS_I_PATH * R + er];
+        const int row = I[NJS_I_ROW * RS + er], p = I[NJS_I_PATH * RS + er];
         for (int c_ = ec0; c_ < H4; c_ += LPR) {
             float e = 0.f;
             if (c_ < c.H) {
@@ -508,7 +541,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, false, false);
     NJ_LANES(lane) {
         if (lane < R) {
-            const int r = lane, row = I[NJS_I_ROW * R + r];
+            const int r = lane, row = I[NJS_I_ROW * RS + r];
             if (row >= 0) {
                 float sa = 0.f, sb = 0.f;
                 for (int c_ = 0; c_ < c.dout; ++c_) {
@@ -523,7 +556,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
                     const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
                     const float sm = (c.loss_kind == NJODE_LOSS_STANDARD) ? (2.f * c.w * ra + 2.f * (1.f - c.w) * rb)
                                                                           : (c.w * ra + (1.f - c.w) * rb);
-                    a.row_loss[row] = sm * sm / NJ_LDG(a.b.n_obs_ot + I[NJS_I_PATH * R + r]);
+                    a.row_loss[row] = sm * sm / NJ_LDG(a.b.n_obs_ot + I[NJS_I_PATH * RS + r]);
                 }
             }
         }
@@ -531,30 +564,27 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     NJ_SYNCWARP();
 }
 
-template <int TR>
-NJ_HD void nj_seg_cta_forward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
+NJ_HD void nj_seg_cta_forward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
     float* simg = smem + s.f_img;
     NJ_THREADS(tid, s.nw_f * 32) { for (int i = tid; i < c.img_floats / 4; i += s.nw_f * 32) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
     nj_zero(smem + s.f_warp0, s.nw_f * s.f_region, s.nw_f * 32);
     NJ_SYNC();
     NJ_WARPS(wp, s.nw_f) {
         float* reg = smem + s.f_warp0 + (size_t)wp * s.f_region;
-        int* slot = reinterpret_cast<int*>(reg + s.f_I) + NJS_I_COUNT * 4 * TR;
+        int* slot = reinterpret_cast<int*>(reg + s.f_I) + NJS_I_COUNT * 16;
         for (;;) {
             NJ_LANES(lane) { if (lane == 0) *slot = nj_atomic_inc(a.counter); }
             NJ_SYNCWARP();
             const int wt = *slot;
             NJ_SYNCWARP();
             if (wt >= s.n_tiles_f) break;
-            nj_seg_forward_warp<TR>(c, s, a, reg, simg, wt);
+            int ub, ue;
+            const int tr = nj_seg_tile_lookup(s.f_ncls, s.f_t0, s.f_u0, s.f_u1, s.f_tr, 4, wt, ub, ue);
+            if (tr == 4) nj_seg_forward_warp<4>(c, s, a, reg, simg, ub, ue);
+            else if (tr == 2) nj_seg_forward_warp<2>(c, s, a, reg, simg, ub, ue);
+            else nj_seg_forward_warp<1>(c, s, a, reg, simg, ub, ue);
         }
     }
-}
-
-NJ_HD void nj_seg_cta_forward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
-    if (s.tr_f == 4) nj_seg_cta_forward_t<4>(c, s, a, smem);
-    else if (s.tr_f == 2) nj_seg_cta_forward_t<2>(c, s, a, smem);
-    else nj_seg_cta_forward_t<1>(c, s, a, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,7 +604,7 @@ NJ_HD void nj_segb_bind(NjSegB& t, const NjSeg& s, float* smem) {
 
 // phase B: dW[o][k] += sum_r g[r][o] a[r][k] over the P rows of the CTA, thread-owned 4x4 tiles
 // (+ bias sums in the kg == 0 tiles) held in `acc` (registers) for the whole launch.
-NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, float* acc, int tid, int nt) {
+NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, float* acc, int tid, int nt, int Pt) {
     const NjNet& N = c.net[netid];
     const int P = s.P_b;
 #pragma unroll
@@ -592,16 +622,16 @@ NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid,
         if (l == N.n - 1) { g = t.GOUT; g_s = s.sO; } else { g = t.G + (size_t)l * P * s.sA; g_s = s.sA; }
         const float* av; int a_s;
         if (l == 0) { av = t.IN; a_s = s.sI; } else { av = t.A + (size_t)(l - 1) * P * s.sA; a_s = s.sA; }
-        g += 4 * og; av += 4 * kg;
+        nj_sp gq = nj_sp_of(g + 4 * og), aq = nj_sp_of(av + 4 * kg);
         float* q = acc + slot * 20;
         float r00 = q[0], r01 = q[1], r02 = q[2], r03 = q[3], r10 = q[4], r11 = q[5], r12 = q[6], r13 = q[7];
         float r20 = q[8], r21 = q[9], r22 = q[10], r23 = q[11], r30 = q[12], r31 = q[13], r32 = q[14], r33 = q[15];
         float b0 = q[16], b1 = q[17], b2 = q[18], b3 = q[19];
 #pragma unroll 4
-        for (int r = 0; r < P; ++r) {
-            const nj_f4 gv = nj_ld4(g);
-            const nj_f4 x = nj_ld4(av);
-            g += g_s; av += a_s;
+        for (int r = 0; r < Pt; ++r) {
+            const nj_f4 gv = nj_sp_ld4(gq);
+            const nj_f4 x = nj_sp_ld4(aq);
+            gq = NJ_SP_ADD(gq, g_s); aq = NJ_SP_ADD(aq, a_s);
             r00 = fmaf(gv.x, x.x, r00); r01 = fmaf(gv.x, x.y, r01); r02 = fmaf(gv.x, x.z, r02); r03 = fmaf(gv.x, x.w, r03);
             r10 = fmaf(gv.y, x.x, r10); r11 = fmaf(gv.y, x.y, r11); r12 = fmaf(gv.y, x.z, r12); r13 = fmaf(gv.y, x.w, r13);
             r20 = fmaf(gv.z, x.x, r20); r21 = fmaf(gv.z, x.y, r21); r22 = fmaf(gv.z, x.z, r22); r23 = fmaf(gv.z, x.w, r23);
@@ -646,13 +676,15 @@ NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, flo
     }
 }
 
+// thread-owned dW accumulators: registers on the device, one slice per simulated thread on the host
 #if defined(NJODE_HOST_SIM)
-#define NJ_ACC_DECL(nt) std::vector<float> nj_acc_store((size_t)(nt) * NJ_SEG_ACC, 0.f)
-#define NJ_ACC(tid) (nj_acc_store.data() + (size_t)(tid) * NJ_SEG_ACC)
+#define NJ_ACC_DECL(nt) std::vector<float> nj_acc_store((size_t)(nt) * NJ_SEG_ACC, 0.f); float* nj_acc_base = nj_acc_store.data()
+#define NJ_ACC_OFF(tid) ((size_t)(tid) * NJ_SEG_ACC)
 #else
-#define NJ_ACC_DECL(nt) float nj_acc_store[NJ_SEG_ACC]; _Pragma("unroll") for (int _i = 0; _i < NJ_SEG_ACC; ++_i) nj_acc_store[_i] = 0.f
-#define NJ_ACC(tid) (nj_acc_store)
+#define NJ_ACC_DECL(nt) float nj_acc_store[NJ_SEG_ACC]; _Pragma("unroll") for (int _i = 0; _i < NJ_SEG_ACC; ++_i) nj_acc_store[_i] = 0.f; float* nj_acc_base = nj_acc_store
+#define NJ_ACC_OFF(tid) 0
 #endif
+#define NJ_ACC(tid) (nj_acc_base + NJ_ACC_OFF(tid))
 
 #define NJ_SEGB_WARP_VIEW()                                                                                        \
     const int r0 = wp * R;                                                                                         \
@@ -667,31 +699,20 @@ NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, flo
         (unsigned)(t.I[NJS_I_PATH * P + (r)] + a.b.path_id_offset), (ev)) : 0
 
 template <int TR>
-NJ_HD void nj_seg_cta_backward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
+NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, const NjSegB& t, float* nj_acc_base,
+                           int u0, int u1) {
     constexpr int R = 4 * TR;
-    const int P = s.P_b, nt = s.nw_b * 32;
+    const int P = s.P_b, nt = s.nw_b * 32, Pt = R * s.nw_b;
     float* simg = smem + s.b_img;
-    NJ_THREADS(tid, nt) { for (int i = tid; i < c.img_floats / 4; i += nt) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
-    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
-    NJ_SYNC();
-    NjSegB t;
-    nj_segb_bind(t, s, smem);
-    NJ_ACC_DECL(nt);
     const float gl = NJ_LDG(a.grad_loss);
     const int d4 = ((c.d + 3) >> 2) << 2, H4 = ((c.H + 3) >> 2) << 2, inf4 = ((c.inf + 3) >> 2) << 2, do4 = ((c.dout + 3) >> 2) << 2;
     const int wa = P * s.sA;
     const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
-    int* ctl = t.I + NJS_I_COUNT * P;
-    for (;;) {
-        NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
-        NJ_SYNC();
-        const int tile = ctl[0];
-        if (tile >= s.n_tiles_b) break;
-        const int u0 = tile * P;
+    {
         NJ_THREADS(tid, nt) {
-            if (tid < P) {
+            if (tid < Pt) {
                 const int u = u0 + tid;
-                if (u < a.b.n_units) {
+                if (u < u1) {
                     const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
                     const int sc = dsc[5];
                     t.I[NJS_I_PATH * P + tid] = dsc[0]; t.I[NJS_I_S0 * P + tid] = dsc[1]; t.I[NJS_I_LEN * P + tid] = dsc[2] - dsc[1];
@@ -706,7 +727,7 @@ NJ_HD void nj_seg_cta_backward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a
         }
         NJ_SYNC();
         int maxlen = 0, any_jump = 0;
-        for (int r = 0; r < P; ++r) {
+        for (int r = 0; r < Pt; ++r) {
             maxlen = t.I[NJS_I_LEN * P + r] > maxlen ? t.I[NJS_I_LEN * P + r] : maxlen;
             any_jump |= (t.I[NJS_I_ROW * P + r] >= 0);
         }
@@ -833,7 +854,7 @@ NJ_HD void nj_seg_cta_backward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a
         }
         if (any_jump) {
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), tid, nt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), tid, nt, Pt); }
             NJ_SYNC();
             // J5: encoder at X_obs, backward with g = dL/dE (from Y only)
             NJ_WARPS(wp, s.nw_b) {
@@ -850,7 +871,7 @@ NJ_HD void nj_seg_cta_backward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a
                 nj_seg_mlp_dx<TR>(w, NJODE_NET_ENC, false);
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), tid, nt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), tid, nt, Pt); }
             NJ_SYNC();
             // J6: readout at h_before, backward with g = dL/dY_bj -> gradient wrt h at the segment end
             NJ_WARPS(wp, s.nw_b) {
@@ -881,7 +902,7 @@ NJ_HD void nj_seg_cta_backward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a
                 }
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), tid, nt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), tid, nt, Pt); }
             NJ_SYNC();
         }
         // ================= Euler steps, reversed =================
@@ -926,7 +947,7 @@ NJ_HD void nj_seg_cta_backward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a
                 }
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ODE, NJ_ACC(tid), tid, nt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ODE, NJ_ACC(tid), tid, nt, Pt); }
             NJ_SYNC();
         }
         // ================= the start encoder, reversed =================
@@ -945,16 +966,34 @@ NJ_HD void nj_seg_cta_backward_t(const NjCfg& c, const NjSeg& s, const NjArgs& a
             nj_seg_mlp_dx<TR>(w, NJODE_NET_ENC, false);
         }
         NJ_SYNC();
-        NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), tid, nt); }
+        NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), tid, nt, Pt); }
         NJ_SYNC();
+    }
+}
+
+NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
+    const int nt = s.nw_b * 32;
+    float* simg = smem + s.b_img;
+    NJ_THREADS(tid, nt) { for (int i = tid; i < c.img_floats / 4; i += nt) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
+    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
+    NJ_SYNC();
+    NjSegB t;
+    nj_segb_bind(t, s, smem);
+    NJ_ACC_DECL(nt);
+    int* ctl = t.I + NJS_I_COUNT * s.P_b;
+    for (;;) {
+        NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int tile = ctl[0];
+        NJ_SYNC();
+        if (tile >= s.n_tiles_b) break;
+        int ub, ue;
+        const int tr = nj_seg_tile_lookup(s.b_ncls, s.b_t0, s.b_u0, s.b_u1, s.b_tr, 4 * s.nw_b, tile, ub, ue);
+        if (tr == 2) nj_seg_bwd_tile<2>(c, s, a, smem, t, nj_acc_base, ub, ue);
+        else nj_seg_bwd_tile<1>(c, s, a, smem, t, nj_acc_base, ub, ue);
     }
     float* gpart = a.partials + (size_t)cta * c.img_floats;
     nj_zero(gpart, c.img_floats, nt);
     NJ_SYNC();
     NJ_THREADS(tid, nt) { nj_seg_dw_flush(c, s, NJ_ACC(tid), gpart, tid, nt); }
-}
-
-NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
-    if (s.tr_b == 2) nj_seg_cta_backward_t<2>(c, s, a, smem, cta);
-    else nj_seg_cta_backward_t<1>(c, s, a, smem, cta);
 }

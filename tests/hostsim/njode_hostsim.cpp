@@ -21,7 +21,7 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
     std::string err;
     const char* fp = getenv("NJODE_FORCE_TILE");
     if (!nj_make_plan(*m, b->n_units, b->n_units, b->N, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
-    nj_make_seg(out.fwd, b->unit_kind, b->E, b->n_units, kSimSMs, kSimSmem, out);
+    nj_make_seg(out.fwd, *b, kSimSMs, kSimSmem, out);
     const size_t cap = (size_t)kSimSMs * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
     out.ws_bytes = out.ws_partials_off + cap * out.fwd.img_floats * sizeof(float);
