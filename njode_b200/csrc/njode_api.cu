@@ -7,6 +7,7 @@
 
 static thread_local std::string g_err;
 static int nj_fail(int code, const std::string& msg) { g_err = msg; return code; }
+int nj_set_error(int code, const char* msg) { g_err = msg; return code; }      // used by njode_sde.cu
 #define NJ_CUDA(call)                                                                         \
     do {                                                                                      \
         cudaError_t _e = (call);                                                              \

@@ -89,15 +89,26 @@ def build_csr(time_ptr, obs_idx, B):
     if N and (obs_idx.min() < 0 or obs_idx.max() >= B):
         raise IndexError("obs_idx out of range")
     row_jump = np.repeat(np.arange(K, dtype=np.int32), np.diff(time_ptr))
-    path_rows = np.argsort(obs_idx, kind="stable").astype(np.int32)
+    path_rows = _stable_argsort_small(obs_idx, B).astype(np.int32)
     path_ptr = np.zeros(B + 1, dtype=np.int32)
     np.cumsum(np.bincount(obs_idx, minlength=B), out=path_ptr[1:])
-    if N:
-        # the contract has at most one row per (time, path) (NJODE/data_utils.py:302-306)
-        pj = row_jump[path_rows].astype(np.int64) + obs_idx[path_rows] * (K + 1)
-        if np.any(np.diff(pj) == 0):
+    if N > 1:
+        # the contract has at most one row per (time, path) (NJODE/data_utils.py:302-306): inside a
+        # path the observation-time index must strictly increase
+        rj = row_jump[path_rows]
+        same_path = np.ones(N - 1, dtype=bool)
+        same_path[path_ptr[1:-1][(path_ptr[1:-1] > 0) & (path_ptr[1:-1] < N)] - 1] = False
+        if np.any((rj[1:] == rj[:-1]) & same_path):
             raise ValueError("a path has two observation rows at the same observation time")
     return path_ptr, path_rows, row_jump
+
+
+def _stable_argsort_small(keys, bound):
+    """stable argsort of non-negative integer keys < bound; numpy's stable sort is an O(N) radix sort
+    for 16-bit keys, so use it whenever the keys fit"""
+    if bound <= 65536:
+        return np.argsort(keys.astype(np.uint16), kind="stable")
+    return np.argsort(keys, kind="stable")
 
 
 def build_units(sched, path_ptr, path_rows, row_jump, B, segments):
@@ -139,6 +150,7 @@ def build_units(sched, path_ptr, path_rows, row_jump, B, segments):
     tails[:, 3] = path_ptr[1:]
     tails[:, 4] = path_ptr[1:]
     tails[:, 5] = (np.where(has, path_rows[last_q] + 1 if N else 0, 0)) | UNIT_WRITES_HT
-    o1 = np.argsort(-(loss_units[:, 2] - loss_units[:, 1]), kind="stable")
-    o2 = np.argsort(-(tails[:, 2] - tails[:, 1]), kind="stable")
+    # longest first (descending length, stable): ascending sort of (S - length)
+    o1 = _stable_argsort_small(S - (loss_units[:, 2] - loss_units[:, 1]), S + 1)
+    o2 = _stable_argsort_small(S - (tails[:, 2] - tails[:, 1]), S + 1)
     return np.concatenate((loss_units[o1], tails[o2]), axis=0), N

@@ -1,0 +1,382 @@
+"""Drop-in for the part of the reference's ``NJODE/stock_model.py`` that sits on the hot path:
+
+* ``generate_paths`` of BlackScholes / OrnsteinUhlenbeck / Heston / HestonWOFeller
+  (NJODE/stock_model.py:356-375, 397-418, 181-221, 288-335) runs as ONE CUDA kernel
+  (``njode_sde_generate`` in njode_b200/csrc/njode_sde.cu, Philox-4x32-10, one subsequence per global
+  path id) instead of a Python loop over paths x steps.  ``generate_paths()`` keeps the reference's
+  return contract ``(paths float64 numpy [nb_paths, dim, nb_steps+1], dt)``;
+  ``generate_paths_device()`` returns device tensors (paths, observed, nb_obs) without a host copy.
+* ``next_cond_exp`` / ``compute_cond_exp`` / ``get_optimal_loss`` (NJODE/stock_model.py:50-158 and the
+  per-model formulas) stay host NumPy: they are the cheap analytic oracle of the training loop
+  (SURVEY.md §8 a15), O(B x steps) element-wise work.
+
+There is no CPU generator: without the CUDA library / a CUDA device ``generate_paths`` raises.
+"""
+import copy
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _ext
+
+SDE_CODES = {"BlackScholes": 0, "OrnsteinUhlenbeck": 1, "Heston": 2, "HestonWOFeller": 3}
+
+
+def _bind(lib):
+    d = lib.dll
+    if getattr(d, "_sde_bound", False):
+        return d
+    d.njode_sde_generate.argtypes = [C.POINTER(_ext.SdeT), C.c_int64, C.c_int64, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    d.njode_sde_generate.restype = C.c_int
+    d.njode_collate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    d.njode_collate.restype = C.c_int
+    d._sde_bound = True
+    return d
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def compute_loss(X_obs, Y_obs, Y_obs_bj, n_obs_ot, batch_size, eps=1e-10, weight=0.5):
+    """NJODE/stock_model.py:471-481"""
+    inner = (2 * weight * np.sqrt(np.sum((X_obs - Y_obs) ** 2, axis=1) + eps) +
+             2 * (1 - weight) * np.sqrt(np.sum((Y_obs_bj - Y_obs) ** 2, axis=1) + eps)) ** 2
+    return np.sum(inner / n_obs_ot) / batch_size
+
+
+def _gen_kw(kwargs):
+    """generator-only knobs of this implementation; every other extra kwarg is ignored like in the reference"""
+    return {k: kwargs[k] for k in ("seed", "first_path", "device") if k in kwargs}
+
+
+class StockModel:
+    """NJODE/stock_model.py:15-158"""
+    model_name = None
+
+    def __init__(self, drift, volatility, S0, nb_paths, nb_steps, maturity, sine_coeff, **kwargs):
+        self.drift = drift
+        self.volatility = volatility
+        self.S0 = S0
+        self.nb_paths = nb_paths
+        self.nb_steps = nb_steps
+        self.maturity = maturity
+        self.dimensions = np.size(S0)
+        self.sine_coeff = sine_coeff
+        if sine_coeff is None:
+            self.periodic_coeff = lambda t: 1
+        else:
+            self.periodic_coeff = lambda t: (1 + np.sin(sine_coeff * t))
+        # generator-only knobs of this implementation (not in the reference's constructor)
+        self.seed = int(kwargs.get("seed", 0))
+        self.first_path = int(kwargs.get("first_path", 0))
+        self.device = kwargs.get("device", "cuda")
+
+    # ---- generators --------------------------------------------------------------------------
+    def _sde_struct(self, obs_perc=0.0):
+        p = _ext.SdeT()
+        p.model = SDE_CODES[self.model_name]
+        p.dimension = int(self.dimensions)
+        p.nb_steps = int(self.nb_steps)
+        p.return_vol = int(bool(getattr(self, "retur_vol", False)))
+        p.drift = float(self.drift) if self.drift is not None else 0.0
+        p.volatility = float(self.volatility)
+        p.mean = float(getattr(self, "mean", 0.0))
+        p.speed = float(getattr(self, "speed", 0.0))
+        p.correlation = float(getattr(self, "correlation", 0.0))
+        p.v0 = float(getattr(self, "v0", 0.0))
+        p.maturity = float(self.maturity)
+        p.sine_coeff = float("nan") if self.sine_coeff is None else float(self.sine_coeff)
+        p.obs_perc = float(obs_perc)
+        p.t0 = 0.0
+        p.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF
+        return p
+
+    def generate_paths_device(self, start_X=None, obs_perc=None, nb_paths=None, first_path=None, device=None):
+        """-> (paths f64 [n, out_dim, steps+1], observed i32 [n, steps+1] or None, nb_obs i32 [n] or None, dt),
+        all on the device.  ``observed``/``nb_obs`` are produced when ``obs_perc`` is given
+        (NJODE/data_utils.py:79-81: observed[:, 0] = 1, nb_obs counts columns >= 1)."""
+        device = torch.device(device or self.device)
+        if device.type != "cuda" or not torch.cuda.is_available():
+            raise _ext.NjodeError("njode_b200.stock_model: the generators run on CUDA devices only (no CPU fallback)")
+        d = _bind(_ext.cuda_lib())
+        n = int(self.nb_paths if nb_paths is None else nb_paths)
+        first = int(self.first_path if first_path is None else first_path)
+        dim = int(self.dimensions)
+        out_dim = dim * (2 if getattr(self, "retur_vol", False) else 1)
+        with torch.cuda.device(device):
+            if start_X is not None:
+                s0 = torch.as_tensor(np.asarray(start_X, dtype=np.float64).reshape(n, dim)).to(device)
+                per_path = 1
+            else:
+                s0 = torch.as_tensor(np.broadcast_to(np.asarray(self.S0, dtype=np.float64).reshape(-1), (dim,)).copy()).to(device)
+                per_path = 0
+            paths = torch.empty(n, out_dim, self.nb_steps + 1, dtype=torch.float64, device=device)
+            observed = nb_obs = None
+            if obs_perc is not None:
+                observed = torch.empty(n, self.nb_steps + 1, dtype=torch.int32, device=device)
+                nb_obs = torch.empty(n, dtype=torch.int32, device=device)
+            p = self._sde_struct(0.0 if obs_perc is None else obs_perc)
+            rc = d.njode_sde_generate(C.byref(p), first, n, C.c_void_p(s0.data_ptr()), per_path,
+                                      C.c_void_p(paths.data_ptr()),
+                                      None if observed is None else C.c_void_p(observed.data_ptr()),
+                                      None if nb_obs is None else C.c_void_p(nb_obs.data_ptr()), _stream(device))
+            _ext.cuda_lib().check(rc, "njode_sde_generate")
+        return paths, observed, nb_obs, self.maturity / self.nb_steps
+
+    def generate_paths(self, start_X=None):
+        """reference contract: (np.float64 [nb_paths, data_dim, nb_steps+1], dt)"""
+        paths, _, _, dt = self.generate_paths_device(start_X=start_X)
+        return paths.cpu().numpy(), dt
+
+    # ---- analytic conditional expectation (host) ------------------------------------------------
+    def next_cond_exp(self, *args, **kwargs):
+        raise ValueError("not implemented yet")
+
+    def compute_cond_exp(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
+                         return_path=True, get_loss=False, weight=0.5, start_time=None, **kwargs):
+        """NJODE/stock_model.py:50-151 (same event loop as NJODE.forward, NumPy).  One deviation: the
+        tail loop passes ``current_time`` to ``next_cond_exp`` -- the reference omits the argument
+        (stock_model.py:139) and raises TypeError whenever time remains after the last observation."""
+        y = start_X
+        batch_size = start_X.shape[0]
+        current_time = 0.0
+        if start_time:
+            current_time = start_time
+        loss = 0
+        if return_path:
+            if start_time:
+                path_t, path_y = [], []
+            else:
+                path_t, path_y = [0.], [y]
+        for i, obs_time in enumerate(times):
+            if obs_time > T + 1e-10:
+                break
+            if obs_time <= current_time:
+                continue
+            while current_time < (obs_time - 1e-10 * delta_t):
+                if current_time < obs_time - delta_t:
+                    delta_t_ = delta_t
+                else:
+                    delta_t_ = obs_time - current_time
+                y = self.next_cond_exp(y, delta_t_, current_time)
+                current_time = current_time + delta_t_
+                if return_path:
+                    path_t.append(current_time)
+                    path_y.append(y)
+            start, end = time_ptr[i], time_ptr[i + 1]
+            X_obs = X[start:end]
+            i_obs = obs_idx[start:end]
+            Y_bj = y
+            temp = copy.copy(y)
+            temp[i_obs] = X_obs
+            y = temp
+            Y = y
+            if get_loss:
+                loss = loss + compute_loss(X_obs=X_obs, Y_obs=Y[i_obs], Y_obs_bj=Y_bj[i_obs],
+                                           n_obs_ot=n_obs_ot[i_obs], batch_size=batch_size, weight=weight)
+            if return_path:
+                path_t.append(obs_time)
+                path_y.append(y)
+        while current_time < T - 1e-10 * delta_t:
+            if current_time < T - delta_t:
+                delta_t_ = delta_t
+            else:
+                delta_t_ = T - current_time
+            y = self.next_cond_exp(y, delta_t_, current_time)
+            current_time = current_time + delta_t_
+            if return_path:
+                path_t.append(current_time)
+                path_y.append(y)
+        if return_path:
+            return loss, np.array(path_t), np.array(path_y)
+        return loss
+
+    def get_optimal_loss(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, weight=0.5):
+        """NJODE/stock_model.py:153-158"""
+        return self.compute_cond_exp(times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
+                                     return_path=False, get_loss=True, weight=weight)
+
+
+class Heston(StockModel):
+    """NJODE/stock_model.py:161-221"""
+    model_name = "Heston"
+
+    def __init__(self, drift, volatility, mean, speed, correlation, nb_paths, nb_steps, S0, maturity,
+                 sine_coeff=None, **kwargs):
+        super().__init__(drift=drift, volatility=volatility, nb_paths=nb_paths, nb_steps=nb_steps, S0=S0,
+                         maturity=maturity, sine_coeff=sine_coeff, **_gen_kw(kwargs))
+        self.mean = mean
+        self.speed = speed
+        self.correlation = correlation
+
+    def next_cond_exp(self, y, delta_t, current_t):
+        return y * np.exp(self.drift * self.periodic_coeff(current_t) * delta_t)
+
+
+class HestonWOFeller(StockModel):
+    """NJODE/stock_model.py:250-335"""
+    model_name = "HestonWOFeller"
+
+    def __init__(self, drift, volatility, mean, speed, correlation, nb_paths, nb_steps, S0, maturity,
+                 scheme='euler', return_vol=False, v0=None, sine_coeff=None, **kwargs):
+        super().__init__(drift=drift, volatility=volatility, nb_paths=nb_paths, nb_steps=nb_steps, S0=S0,
+                         maturity=maturity, sine_coeff=sine_coeff, **_gen_kw(kwargs))
+        self.mean = mean
+        self.speed = speed
+        self.correlation = correlation
+        if scheme != 'euler':
+            raise ValueError('unknown sampling scheme')
+        self.scheme = scheme
+        self.retur_vol = return_vol
+        self.v0 = self.mean if v0 is None else v0
+
+    def next_cond_exp(self, y, delta_t, current_t):
+        if self.retur_vol:
+            s, v = np.split(y, indices_or_sections=2, axis=1)
+            s = s * np.exp(self.drift * self.periodic_coeff(current_t) * delta_t)
+            exp_delta = np.exp(-self.speed * delta_t)
+            v = v * exp_delta + self.mean * (1 - exp_delta)
+            return np.concatenate([s, v], axis=1)
+        return y * np.exp(self.drift * self.periodic_coeff(current_t) * delta_t)
+
+
+class BlackScholes(StockModel):
+    """NJODE/stock_model.py:340-375"""
+    model_name = "BlackScholes"
+
+    def __init__(self, drift, volatility, nb_paths, nb_steps, S0, maturity, sine_coeff=None, **kwargs):
+        super().__init__(drift=drift, volatility=volatility, nb_paths=nb_paths, nb_steps=nb_steps, S0=S0,
+                         maturity=maturity, sine_coeff=sine_coeff, **_gen_kw(kwargs))
+
+    def next_cond_exp(self, y, delta_t, current_t):
+        return y * np.exp(self.drift * self.periodic_coeff(current_t) * delta_t)
+
+
+class OrnsteinUhlenbeck(StockModel):
+    """NJODE/stock_model.py:378-418"""
+    model_name = "OrnsteinUhlenbeck"
+
+    def __init__(self, volatility, nb_paths, nb_steps, S0, mean, speed, maturity, sine_coeff=None, **kwargs):
+        super().__init__(volatility=volatility, nb_paths=nb_paths, drift=None, nb_steps=nb_steps, S0=S0,
+                         maturity=maturity, sine_coeff=sine_coeff, **_gen_kw(kwargs))
+        self.mean = mean
+        self.speed = speed
+
+    def next_cond_exp(self, y, delta_t, current_t):
+        exp_delta = np.exp(-self.speed * self.periodic_coeff(current_t) * delta_t)
+        return y * exp_delta + self.mean * (1 - exp_delta)
+
+
+class Combined(StockModel):
+    """NJODE/stock_model.py:421-468"""
+
+    def __init__(self, stock_model_names, hyperparam_dicts, **kwargs):
+        self.stock_model_names = stock_model_names
+        self.hyperparam_dicts = hyperparam_dicts
+
+    def compute_cond_exp(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
+                         return_path=True, get_loss=False, weight=0.5, **kwargs):
+        stockmodel = STOCK_MODELS[self.stock_model_names[0]](**self.hyperparam_dicts[0])
+        T = self.hyperparam_dicts[0]['maturity']
+        loss, path_t, path_y = stockmodel.compute_cond_exp(
+            times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, return_path=True,
+            get_loss=get_loss, weight=weight)
+        for i in range(1, len(self.stock_model_names)):
+            start_X = path_y[-1, :, :]
+            start_time = path_t[-1]
+            T += self.hyperparam_dicts[i]['maturity']
+            stockmodel = STOCK_MODELS[self.stock_model_names[i]](**self.hyperparam_dicts[i])
+            _loss, _path_t, _path_y = stockmodel.compute_cond_exp(
+                times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, return_path=True,
+                get_loss=get_loss, weight=weight, start_time=start_time)
+            loss += _loss
+            path_t = np.concatenate([path_t, _path_t])
+            path_y = np.concatenate([path_y, _path_y], axis=0)
+        if return_path:
+            return loss, np.array(path_t), np.array(path_y)
+        return loss
+
+    def get_optimal_loss(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, weight=0.5):
+        return self.compute_cond_exp(times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
+                                     return_path=False, get_loss=True, weight=weight)
+
+
+STOCK_MODELS = {                           # NJODE/stock_model.py:486-495
+    "BlackScholes": BlackScholes,
+    "Heston": Heston,
+    "OrnsteinUhlenbeck": OrnsteinUhlenbeck,
+    "HestonWOFeller": HestonWOFeller,
+    "combined": Combined,
+    "sine_BlackScholes": BlackScholes,
+    "sine_Heston": Heston,
+    "sine_OrnsteinUhlenbeck": OrnsteinUhlenbeck,
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident dataset + on-device collate (NJODE/data_utils.py:59-108, 278-316)
+# ------------------------------------------------------------------------------------------------
+class DeviceDataset:
+    """paths / observation mask generated on the device and kept there; ``collate(sel)`` builds one
+    batch of the reference's collate contract with ``njode_collate`` (rows ordered time ascending,
+    batch position ascending) and returns the same dict as ``custom_collate_fn`` -- ``X`` / ``start_X``
+    stay on the device, the small index arrays come back to the host because the reference contract
+    holds them there (NJODE/train.py:493-507)."""
+
+    def __init__(self, stock_model_name, hyperparam_dict, seed=0, first_path=0, device="cuda"):
+        hp = dict(hyperparam_dict)
+        self.obs_perc = hp['obs_perc']
+        self.hyperparam_dict = hp
+        self.model = STOCK_MODELS[stock_model_name](**hp, seed=seed, first_path=first_path, device=device)
+        self.paths, self.observed, self.nb_obs, self.dt = self.model.generate_paths_device(obs_perc=self.obs_perc)
+        self.device = self.paths.device
+        self.n, self.dim, n1 = self.paths.shape
+        self.nb_steps = n1 - 1
+        self._ws = None
+
+    def __len__(self):
+        return self.n
+
+    def collate_device(self, sel):
+        """device-side batch: dict of device tensors (X, obs_idx i32, time_ptr i32, time_idx i32, start_X,
+        n_obs_ot i32) sized for the worst case plus ``counts`` = [K, N] (device)."""
+        d = _bind(_ext.cuda_lib())
+        sel = torch.as_tensor(sel, dtype=torch.int64, device=self.device).contiguous()
+        B = int(sel.numel())
+        nw = (B + 31) // 32
+        need = (self.nb_steps * nw + 3 * self.nb_steps + 16) * 4
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        nmax = B * self.nb_steps
+        i32 = dict(dtype=torch.int32, device=self.device)
+        out = {"X": torch.empty(nmax, self.dim, dtype=torch.float32, device=self.device),
+               "obs_idx": torch.empty(nmax, **i32), "time_ptr": torch.empty(self.nb_steps + 1, **i32),
+               "time_idx": torch.empty(self.nb_steps, **i32),
+               "start_X": torch.empty(B, self.dim, dtype=torch.float32, device=self.device),
+               "n_obs_ot": torch.empty(B, **i32), "counts": torch.empty(2, **i32)}
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = d.njode_collate(p(self.paths), p(self.observed), self.n, self.dim, self.nb_steps, p(sel), B,
+                                 p(out["X"]), p(out["obs_idx"]), p(out["time_ptr"]), p(out["time_idx"]),
+                                 p(out["start_X"]), p(out["n_obs_ot"]), p(out["counts"]), p(self._ws),
+                                 self._ws.numel(), _stream(self.device))
+        _ext.cuda_lib().check(rc, "njode_collate")
+        return out
+
+    def collate(self, sel):
+        """the reference's collate dict (NJODE/data_utils.py:311-315)"""
+        o = self.collate_device(sel)
+        K, N = (int(v) for v in o["counts"].cpu())
+        tidx = o["time_idx"][:K].cpu().numpy()
+        # current_time += dt once per grid step in float64 (data_utils.py:293-296)
+        grid_t = np.cumsum(np.full(self.nb_steps, self.dt, dtype=np.float64))
+        return {"times": grid_t[tidx - 1], "time_ptr": o["time_ptr"][:K + 1].cpu().numpy().astype(np.int64),
+                "obs_idx": o["obs_idx"][:N].cpu().to(torch.int64), "start_X": o["start_X"],
+                "n_obs_ot": o["n_obs_ot"].cpu().to(torch.int64), "X": o["X"][:N],
+                "true_paths": None, "observed_dates": None}

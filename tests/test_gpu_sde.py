@@ -1,0 +1,114 @@
+"""GPU: njode_sde_generate / njode_collate (njode_b200/csrc/njode_sde.cu) through the C ABI against
+oracle/sde_oracle.py (same Philox stream: fp64 agreement to libm rounding, integer outputs exact), in
+distribution against the reference generator (committed moments) and the closed-form moments of the
+Euler scheme, and end to end: a device-collated batch drives the model to the same loss as the host path."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import sde_oracle as so
+from njode_b200 import models, stock_model
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "sde_ref.npz"))
+HP = dict(drift=2., volatility=0.3, mean=4, speed=2., correlation=0.5, nb_paths=300, nb_steps=37, S0=[1., 1.5, 0.7],
+          maturity=1., dimension=3, sine_coeff=None, v0=0.5, return_vol=False, obs_perc=0.2)
+
+
+@pytest.mark.parametrize("sine", [None, 2.5])
+@pytest.mark.parametrize("name", ["BlackScholes", "OrnsteinUhlenbeck", "Heston", "HestonWOFeller", "HestonWOFeller_vol"])
+def test_generator_matches_oracle_on_the_same_stream(name, sine):
+    model = name.split("_")[0]
+    hp = dict(HP, return_vol=name.endswith("_vol"), sine_coeff=sine)
+    m = stock_model.STOCK_MODELS[model](**hp, seed=1234567890123, first_path=1000)
+    paths, obs, nb, dt = m.generate_paths_device(obs_perc=0.2)
+    o_paths, o_obs, o_nb = so.generate(model, hp, 1234567890123, 1000, 300, obs_perc=0.2)
+    assert paths.shape == o_paths.shape
+    np.testing.assert_allclose(paths.cpu().numpy(), o_paths, rtol=1e-10, atol=1e-12)      # fp64, libm differences only
+    assert np.array_equal(obs.cpu().numpy(), o_obs) and np.array_equal(nb.cpu().numpy(), o_nb)   # integer outputs: exact
+
+
+def test_generator_is_sharding_invariant_and_honours_start_X():
+    hp = dict(HP, dimension=1, S0=1.0, nb_paths=64)
+    a, *_ = stock_model.Heston(**hp, seed=7, first_path=0).generate_paths_device(nb_paths=64)
+    b, *_ = stock_model.Heston(**hp, seed=7, first_path=40).generate_paths_device(nb_paths=24)
+    assert torch.equal(a[40:], b)
+    sx = np.linspace(0.5, 2.0, 64).reshape(64, 1)
+    c, *_ = stock_model.BlackScholes(**hp, seed=7).generate_paths_device(start_X=sx)
+    assert np.allclose(c[:, :, 0].cpu().numpy(), sx)
+    p, dt = stock_model.BlackScholes(**hp, seed=7).generate_paths()
+    assert isinstance(p, np.ndarray) and p.dtype == np.float64 and p.shape == (64, 1, 38) and dt == 1.0 / 37
+
+
+def test_moments_against_closed_forms_and_reference_generator():
+    demo = json.loads(str(GOLD["demo_hp"]))
+    n = 400000
+    k = np.arange(101)
+    dt = 0.01
+    for name in ("BlackScholes", "OrnsteinUhlenbeck", "Heston"):
+        paths, *_ = stock_model.STOCK_MODELS[name](**dict(demo, nb_paths=n), seed=99).generate_paths_device()
+        x = paths[:, 0, :]
+        mean, var = x.mean(0).cpu().numpy(), x.var(0).cpu().numpy()
+        # reference generator, 20 000 paths: agreement within its own Monte-Carlo error (5 sigma)
+        r_mean, r_var = GOLD["moments/%s/mean" % name], GOLD["moments/%s/var" % name]
+        assert np.all(np.abs(mean - r_mean) <= 5 * np.sqrt(r_var / 20000) + 1e-12), name
+        if name != "Heston":                # Heston spot (vol ~ 200 %) has no stable sample variance at 20 000 paths
+            assert np.all(np.abs(var - r_var) <= 0.08 * r_var + 1e-12), name
+        # quartiles: robust for every model; sampling error of a quantile ~ sqrt(p(1-p)/n) / density
+        q = torch.quantile(x[:100000].float(), torch.tensor([0.25, 0.5, 0.75], device=x.device), dim=0).cpu().numpy()
+        r_q = GOLD["moments/%s/quantiles" % name]
+        iqr = r_q[2] - r_q[0]
+        assert np.all(np.abs(q - r_q) <= 0.05 * iqr[None, :] + 1e-9), name
+        if name == "BlackScholes":          # E[S_k] = S0 (1 + mu dt)^k ; E[S_k^2] = S0^2 ((1 + mu dt)^2 + sigma^2 dt)^k
+            em = (1 + 2.0 * dt) ** k
+            e2 = ((1 + 2.0 * dt) ** 2 + 0.09 * dt) ** k
+            assert np.all(np.abs(mean - em) <= 5 * np.sqrt((e2 - em ** 2) / n) + 1e-12)
+            assert np.all(np.abs(var - (e2 - em ** 2)) <= 0.03 * (e2 - em ** 2) + 1e-12)
+        if name == "OrnsteinUhlenbeck":     # E[S_k] = m + (S0 - m)(1 - kappa dt)^k
+            em = 4 + (1 - 4) * (1 - 2.0 * dt) ** k
+            assert np.all(np.abs(mean - em) <= 5 * np.sqrt(var / n) + 1e-12)
+
+
+def test_mask_rate():
+    m = stock_model.BlackScholes(**dict(HP, dimension=1, S0=1.0, nb_steps=100, nb_paths=20000), seed=3)
+    _, obs, nb, _ = m.generate_paths_device(obs_perc=0.1)
+    assert torch.all(obs[:, 0] == 1)
+    rate = obs[:, 1:].float().mean().item()
+    assert abs(rate - 0.1) < 0.002
+    assert torch.equal(nb, obs[:, 1:].sum(1).to(torch.int32))
+
+
+@pytest.mark.parametrize("B", [1, 31, 200, 1000])
+def test_device_collate_matches_oracle_exactly(B):
+    hp = dict(HP, nb_paths=1500, dimension=2, S0=[1.0, 2.0], nb_steps=25, obs_perc=0.15)
+    ds = stock_model.DeviceDataset("Heston", hp, seed=11)
+    sel = np.random.default_rng(B).permutation(1500)[:B]
+    got = ds.collate(sel)
+    paths, obs, nb = ds.paths.cpu().numpy()[sel], ds.observed.cpu().numpy()[sel], ds.nb_obs.cpu().numpy()[sel]
+    want = so.collate(paths, obs, nb, ds.dt)
+    assert np.array_equal(got["times"], want["times"]) and np.array_equal(got["time_ptr"], want["time_ptr"])
+    assert np.array_equal(got["obs_idx"].numpy(), want["obs_idx"])
+    assert np.array_equal(got["X"].cpu().numpy(), want["X"]) and np.array_equal(got["start_X"].cpu().numpy(), want["start_X"])
+    assert np.array_equal(got["n_obs_ot"].numpy(), want["n_obs_ot"])
+
+
+def test_device_dataset_drives_the_model_like_the_host_collate():
+    from njode_b200 import data_utils
+    hp = dict(HP, nb_paths=600, dimension=1, S0=1.0, nb_steps=50, obs_perc=0.1)
+    ds = stock_model.DeviceDataset("BlackScholes", hp, seed=5)
+    sel = np.arange(100, 300)
+    b_dev = ds.collate(sel)
+    b_host = data_utils.collate_paths(ds.paths.cpu().numpy()[sel], ds.observed.cpu().numpy()[sel],
+                                      ds.nb_obs.cpu().numpy()[sel], ds.dt)
+    torch.manual_seed(0)
+    m = models.NJODE(**cases.CONFIGS["demo"]).to("cuda:0").eval()
+    out = []
+    for b in (b_dev, b_host):
+        with torch.no_grad():
+            hT, loss = m(b["times"], b["time_ptr"], b["X"], b["obs_idx"], ds.dt, 1.0, b["start_X"], b["n_obs_ot"])
+        out.append((hT.cpu().numpy(), float(loss)))
+    assert out[0][1] == out[1][1] and np.array_equal(out[0][0], out[1][0])
