@@ -151,14 +151,19 @@ class Runner:
     # -- batch staging ----------------------------------------------------------------------
     def prepare(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, M, until_T,
                 return_path, segments, d, batch_size_norm=None, path_id_offset=0):
+        """stages one batch of the collate contract: the host builds only the Euler schedule (float64
+        loop conditions of the reference) and ships the raw arrays in ONE pinned host->device copy; the
+        per-path CSR and the sorted work units are built on the device (schedule.build_index_torch)."""
         sched = _sched.build_schedule(times, delta_t, T, until_T, return_path)
         B = int(start_X.shape[0])
-        oi = obs_idx.detach().cpu().numpy() if torch.is_tensor(obs_idx) else np.asarray(obs_idx)
-        path_ptr, path_rows, row_jump = _sched.build_csr(time_ptr, oi, B)
-        N = len(path_rows)
-        units, n_loss = _sched.build_units(sched, path_ptr, path_rows, row_jump, B, segments)
+        tp = np.ascontiguousarray(np.asarray(time_ptr, dtype=np.int64).astype(np.int32))
+        K = len(tp) - 1
+        N = int(tp[-1]) if len(tp) else 0
+        n_idx = int(obs_idx.numel()) if torch.is_tensor(obs_idx) else len(obs_idx)
+        if n_idx != N:
+            raise AssertionError("len(obs_idx) != time_ptr[-1]")
 
-        def host_f32(t, shape):
+        def stage_f32(t, shape):
             if t is None:
                 return None
             if torch.is_tensor(t):
@@ -167,12 +172,32 @@ class Runner:
                 return np.ascontiguousarray(t.detach().numpy().astype(np.float32, copy=False)).reshape(shape)
             return np.ascontiguousarray(np.asarray(t, dtype=np.float32)).reshape(shape)
 
-        arrays = {"X": host_f32(X, (N, d)), "M": host_f32(M, (N, d)),
-                  "start_X": host_f32(start_X, (B, d)), "n_obs_ot": host_f32(n_obs_ot, (B,)),
-                  "path_ptr": path_ptr, "path_rows": path_rows, "row_jump": row_jump,
+        if torch.is_tensor(obs_idx) and obs_idx.device.type != "cpu":
+            obs_arr = obs_idx.detach().to(self.device)
+        else:
+            oi = obs_idx.detach().numpy() if torch.is_tensor(obs_idx) else np.asarray(obs_idx)
+            obs_arr = np.ascontiguousarray(oi.astype(np.int32, copy=False))
+        # small batches: the index arrays are cheaper to build with NumPy on the host (a dozen tensor-op
+        # launches cost more than sorting a few thousand rows); large ones are built on the device
+        mode = os.environ.get("NJODE_INDEX", "auto")
+        host_index = (not torch.is_tensor(obs_arr)) and (mode == "host" or (mode == "auto" and N + B < 16384))
+        budget = float(B) * sched.S / (16.0 * self.sms * 12)
+        T1, T2 = max(8, int(0.75 * budget)), max(4, int(0.4 * budget))
+        host_idx = {}
+        if host_index:
+            path_ptr, path_rows, row_jump = _sched.build_csr(tp, obs_arr, B)
+            units, n_loss = _sched.build_units(sched, path_ptr, path_rows, row_jump, B, segments)
+            host_idx = {"path_ptr": path_ptr, "path_rows": path_rows, "row_jump": row_jump, "unit_desc": units.reshape(-1)}
+            lens = (units[:, 2] - units[:, 1])
+            st = [0, 0, 0, 0, 0, 0]
+            if segments:
+                st[:4] = [int(np.count_nonzero(lens[:n_loss] >= T1)), int(np.count_nonzero(lens[:n_loss] >= T2)),
+                          int(np.count_nonzero(lens[n_loss:] >= T1)), int(np.count_nonzero(lens[n_loss:] >= T2))]
+        arrays = {"X": stage_f32(X, (N, d)), "M": stage_f32(M, (N, d)),
+                  "start_X": stage_f32(start_X, (B, d)), "n_obs_ot": stage_f32(n_obs_ot, (B,)),
+                  "obs_idx": None if host_index else obs_arr, "time_ptr": tp, **host_idx,
                   "step_dt": sched.step_dt, "step_t": sched.step_t, "jump_step": sched.jump_step,
-                  "jump_tau": sched.jump_tau, "step_event": sched.step_event,
-                  "jump_event": sched.jump_event, "unit_desc": units.reshape(-1)}
+                  "jump_tau": sched.jump_tau, "step_event": sched.step_event, "jump_event": sched.jump_event}
         # one pinned staging block, one host->device copy
         offs, total = {}, 0
         for k, a in arrays.items():
@@ -192,7 +217,32 @@ class Runner:
         base = dev.data_ptr()
         keep = [dev]
 
+        def view_i32(k, n):
+            a = arrays[k]
+            if torch.is_tensor(a):
+                return a
+            return dev[offs[k]:offs[k] + 4 * n].view(torch.int32)
+
+        # tile-height classes of the segment kernels: units at least T1 (T2) Euler steps long are marched in
+        # the lowest (middle) tiles; thresholds follow the per-warp share of the batch's total work B * S
+        index = {}
+        if not host_index:
+            path_ptr, path_rows, row_jump, unit_desc, n_loss, stats = _sched.build_index_torch(
+                view_i32("obs_idx", N), view_i32("time_ptr", K + 1), view_i32("jump_step", K), B, sched.S, segments, T1, T2)
+            index = {"path_ptr": path_ptr, "path_rows": path_rows, "row_jump": row_jump, "unit_desc": unit_desc}
+            keep.extend(index.values())
+            st = [int(v) for v in stats.cpu()]                  # the one small device->host read of staging
+        if st[5]:
+            raise IndexError("obs_idx out of range")
+        if st[4]:
+            # the contract has at most one row per (time, path) (NJODE/data_utils.py:302-306)
+            raise ValueError("a path has two observation rows at the same observation time")
+        seg_n1, seg_n2 = (C.c_int32 * 2)(st[0], st[2]), (C.c_int32 * 2)(st[1], st[3])
+        n_units = (N + B) if segments else B
+
         def p(k):
+            if k in index:
+                return C.c_void_p(index[k].data_ptr())
             a = arrays[k]
             if a is None:
                 return None
@@ -201,22 +251,11 @@ class Runner:
                 return C.c_void_p(a.data_ptr())
             return C.c_void_p(base + offs[k])
 
-        # tile-height classes of the segment kernels: units at least T1 (T2) Euler steps long are marched
-        # in the lowest (middle) tiles; thresholds follow the per-warp share of the batch's total work
-        seg_n1, seg_n2 = (C.c_int32 * 2)(0, 0), (C.c_int32 * 2)(0, 0)
-        if segments and len(units):
-            lens = (units[:, 2] - units[:, 1]).astype(np.int64)
-            budget = float(lens.sum()) / (16.0 * self.sms * 12)
-            T1, T2 = max(8, int(0.75 * budget)), max(4, int(0.4 * budget))
-            for r, run in enumerate((lens[:n_loss], lens[n_loss:])):
-                seg_n1[r] = int(np.count_nonzero(run >= T1))
-                seg_n2[r] = int(np.count_nonzero(run >= T2))
-
-        def make(n_units):
+        def make(n_units_):
             return BatchT(B=B, N=N, K=sched.K, S=sched.S, E=sched.E, n_loss_units=int(n_loss),
                           seg_n1=seg_n1, seg_n2=seg_n2,
                           batch_size_norm=int(batch_size_norm or B), path_id_offset=int(path_id_offset),
-                          n_units=int(n_units), unit_kind=1 if segments else 0, X=p("X"), M=p("M"), start_X=p("start_X"),
+                          n_units=int(n_units_), unit_kind=1 if segments else 0, X=p("X"), M=p("M"), start_X=p("start_X"),
                           n_obs_ot=p("n_obs_ot"), path_ptr=p("path_ptr"), path_rows=p("path_rows"),
                           row_jump=p("row_jump"), step_dt=p("step_dt"), step_t=p("step_t"),
                           jump_step=p("jump_step"), jump_tau=p("jump_tau"), step_event=p("step_event"),
@@ -224,8 +263,8 @@ class Runner:
 
         pb = PreparedBatch()
         pb.sched, pb.B, pb.N, pb.dev, pb.keep = sched, B, N, self.device, keep
-        pb.n_units, pb.n_loss_units = len(units), n_loss
-        pb.fwd = make(len(units))
+        pb.n_units, pb.n_loss_units = n_units, n_loss
+        pb.fwd = make(n_units)
         pb.bwd_loss = make(n_loss)       # backward without a gradient into hT: tails contribute nothing
         pb.bwd_all = pb.fwd
         pb.h2d_bytes = total

@@ -15,6 +15,7 @@ non-masked model, where the state after a jump does not depend on the state befo
 import collections
 
 import numpy as np
+import torch
 
 UNIT_WRITES_HT = 1 << 30
 
@@ -154,3 +155,62 @@ def build_units(sched, path_ptr, path_rows, row_jump, B, segments):
     o1 = _stable_argsort_small(S - (loss_units[:, 2] - loss_units[:, 1]), S + 1)
     o2 = _stable_argsort_small(S - (tails[:, 2] - tails[:, 1]), S + 1)
     return np.concatenate((loss_units[o1], tails[o2]), axis=0), N
+
+
+def build_index_torch(obs, time_ptr, jump_step, B, S, segments, T1, T2):
+    """device-side (any torch device) version of build_csr + build_units: the per-path CSR of observation
+    rows and the work units, built with a handful of tensor ops (stable radix sorts, prefix sums) right
+    where the batch lives, so the host ships only the raw collate arrays.
+
+    obs [N] path index of every row (time-major rows, NJODE/data_utils.py:298-307), time_ptr [K+1],
+    jump_step [K] (host schedule).  Returns (path_ptr, path_rows, row_jump, unit_desc) as int32 tensors,
+    n_loss_units, and ``stats`` (int64 [6] on the device): units with length >= T1 / >= T2 in the loss
+    run and in the tail run, a duplicate-(time, path) flag and an out-of-range-index flag."""
+    dev = obs.device
+    N = int(obs.numel())
+    i64 = dict(dtype=torch.int64, device=dev)
+    obs = obs.to(torch.int64)
+    zero = torch.zeros((), **i64)
+    bad = ((obs < 0) | (obs >= B)).any().to(torch.int64) if N else zero
+    obs_c = obs.clamp(0, max(B - 1, 0))
+    counts = torch.bincount(obs_c, minlength=B)[:B] if N else torch.zeros(B, **i64)
+    path_ptr = torch.zeros(B + 1, **i64)
+    torch.cumsum(counts, 0, out=path_ptr[1:])
+    sorted_path, path_rows = torch.sort(obs_c, stable=True)
+    r = torch.arange(N, **i64)
+    row_jump = torch.searchsorted(time_ptr.to(torch.int64), r, right=True) - 1
+    rj_sorted = row_jump[path_rows]
+    first = torch.ones(N, dtype=torch.bool, device=dev)
+    if N > 1:
+        first[1:] = sorted_path[1:] != sorted_path[:-1]
+        dup = ((rj_sorted[1:] == rj_sorted[:-1]) & ~first[1:]).any().to(torch.int64)
+    else:
+        dup = zero
+    ar_b = torch.arange(B, **i64)
+    if not segments:
+        units = torch.stack([ar_b, torch.zeros(B, **i64), torch.full((B,), S, **i64), path_ptr[:-1], path_ptr[1:],
+                             torch.full((B,), UNIT_WRITES_HT, **i64)], 1)
+        stats = torch.stack([zero, zero, zero, zero, dup, bad])
+        n_loss = B
+    else:
+        js = jump_step.to(torch.int64)[rj_sorted]
+        prev_js = torch.where(first, torch.zeros_like(js), torch.roll(js, 1))
+        prev_row = torch.where(first, torch.full_like(path_rows, -1), torch.roll(path_rows, 1))
+        loss_units = torch.stack([sorted_path, prev_js, js, r, r + 1, prev_row + 1], 1)
+        has = counts > 0
+        if N:
+            last_q = (path_ptr[1:] - 1).clamp(min=0)
+            tail_s0 = torch.where(has, js[last_q], torch.zeros(B, **i64))
+            tail_start = torch.where(has, path_rows[last_q] + 1, torch.zeros(B, **i64)) | UNIT_WRITES_HT
+        else:
+            tail_s0 = torch.zeros(B, **i64)
+            tail_start = torch.full((B,), UNIT_WRITES_HT, **i64)
+        tails = torch.stack([ar_b, tail_s0, torch.full((B,), S, **i64), path_ptr[1:], path_ptr[1:], tail_start], 1)
+        len_l, len_t = js - prev_js, S - tail_s0
+        o1 = torch.sort(S - len_l, stable=True).indices          # longest first, ties in path-major order
+        o2 = torch.sort(S - len_t, stable=True).indices
+        units = torch.cat((loss_units[o1], tails[o2]), 0)
+        stats = torch.stack([(len_l >= T1).sum(), (len_l >= T2).sum(), (len_t >= T1).sum(), (len_t >= T2).sum(), dup, bad])
+        n_loss = N
+    i32 = torch.int32
+    return (path_ptr.to(i32), path_rows.to(i32), row_jump.to(i32), units.to(i32).contiguous().view(-1), n_loss, stats)

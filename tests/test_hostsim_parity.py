@@ -24,6 +24,7 @@ def sim_runner():
     os.environ.pop("NJODE_FORCE_TILE", None)
     os.environ.pop("NJODE_FORCE_TR", None)
     os.environ.pop("NJODE_NO_SEG", None)
+    os.environ.pop("NJODE_INDEX", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -118,3 +119,31 @@ def test_segment_path_wide_layers_use_output_chunks():
     batch = cases.grid_batch(20, 2, 10, 0.3, seed=18)
     parity_util.check_against_oracle(cfg, batch, 0.1, 1.0, seed=14, device="cpu", train=True, grad_hT=True)
     parity_util.check_against_oracle(cfg, batch, 0.1, 1.0, seed=14, device="cpu", train=False)
+
+
+@pytest.mark.parametrize("mode", ["host", "device"])
+@pytest.mark.parametrize("name", ["bs_ckpt1", "irregular_demo", "masked_small"])
+def test_both_index_builders(name, mode):
+    """per-path CSR + work units built by NumPy on the host (small batches) or by tensor ops where the
+    batch lives (large batches): same results"""
+    os.environ["NJODE_INDEX"] = mode
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    parity_util.check_path_call(name, "cpu")
+
+
+def test_index_builders_agree_exactly():
+    from njode_b200 import schedule
+    batch = cases.grid_batch(57, 1, 30, 0.2, seed=31)
+    sched = schedule.build_schedule(batch["times"], 1.0 / 30, 1.0, False, False)
+    B = 57
+    pp, pr, rj = schedule.build_csr(batch["time_ptr"], batch["obs_idx"].numpy(), B)
+    for segments in (True, False):
+        units, n_loss = schedule.build_units(sched, pp, pr, rj, B, segments)
+        t = schedule.build_index_torch(batch["obs_idx"], torch.tensor(batch["time_ptr"]), torch.tensor(sched.jump_step),
+                                       B, sched.S, segments, 8, 4)
+        assert np.array_equal(t[0].numpy(), pp) and np.array_equal(t[1].numpy(), pr) and np.array_equal(t[2].numpy(), rj)
+        assert np.array_equal(t[3].numpy().reshape(-1, 6), units) and t[4] == n_loss
+        if segments:
+            lens = units[:, 2] - units[:, 1]
+            assert [int(v) for v in t[5][:4]] == [int((lens[:n_loss] >= 8).sum()), int((lens[:n_loss] >= 4).sum()),
+                                                   int((lens[n_loss:] >= 8).sum()), int((lens[n_loss:] >= 4).sum())]
