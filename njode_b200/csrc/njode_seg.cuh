@@ -58,6 +58,38 @@ __device__ __forceinline__ nj_f4 nj_sp_ld4(nj_sp p) {
 #define NJ_SP_ADD(p, nfloats) ((p) + 4u * (unsigned)(nfloats))
 #endif
 
+// parameter image global -> shared: one TMA bulk copy (cp.async.bulk, completion on an mbarrier) issued by
+// one thread instead of a cooperative load/store loop; the caller must NJ_SYNC() afterwards.
+#if defined(NJODE_HOST_SIM)
+static inline void nj_stage_image(float* dst, const float* src, int nfloats, int nt) {
+    (void)nt;
+    memcpy(dst, src, (size_t)nfloats * 4);
+}
+#else
+__device__ __forceinline__ void nj_stage_image(float* dst, const float* src, int nfloats, int nt) {
+    (void)nt;
+    __shared__ __align__(8) unsigned long long nj_img_bar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&nj_img_bar);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)nfloats * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        for (unsigned off = 0; off < bytes; off += 32768u) {
+            const unsigned n = bytes - off < 32768u ? bytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(d + off), "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(bar) : "memory");
+        }
+    }
+    __syncthreads();                       // the barrier is initialised and armed for every waiter
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar) : "memory");
+}
+#endif
+
 #define NJ_SEG_NT_MAX 2            // dW tiles (4x4 + bias) a thread may own in registers
 #define NJ_SEG_ACC (NJ_SEG_NT_MAX * 20)
 #define NJ_DROPPED 0x80000000u     // bit pattern (-0.0f) of a dropped activation
@@ -566,7 +598,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
 
 NJ_HD void nj_seg_cta_forward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
     float* simg = smem + s.f_img;
-    NJ_THREADS(tid, s.nw_f * 32) { for (int i = tid; i < c.img_floats / 4; i += s.nw_f * 32) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
+    nj_stage_image(simg, a.image, c.img_floats, s.nw_f * 32);
     nj_zero(smem + s.f_warp0, s.nw_f * s.f_region, s.nw_f * 32);
     NJ_SYNC();
     NJ_WARPS(wp, s.nw_f) {
@@ -974,7 +1006,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
 NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
     const int nt = s.nw_b * 32;
     float* simg = smem + s.b_img;
-    NJ_THREADS(tid, nt) { for (int i = tid; i < c.img_floats / 4; i += nt) nj_st4(simg + 4 * i, nj_ld4(a.image + 4 * i)); }
+    nj_stage_image(simg, a.image, c.img_floats, nt);
     nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
     NJ_SYNC();
     NjSegB t;
