@@ -52,6 +52,11 @@ WORKLOADS = {
     "bs_scaled_d16_h256": dict(sde="BlackScholes", paths=8192, steps=1000, d=16, H=256, width=256,
                                layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128,
                                cpu_sample_steps=100),
+    "bs_scaled_d16_h256_small": dict(sde="BlackScholes", paths=2048, steps=100, d=16, H=256, width=256,
+                                     layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128),
+    # BASELINE.json configs[2] (i): combined-dataset nets (2x100 tanh), batch 5000
+    "bs_2x100_5k": dict(sde="BlackScholes", paths=5000, steps=100, d=1, H=10, width=100, layers=2,
+                        obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
 }
 
 SDE_PARAMS = dict(drift=2.0, volatility=0.3, mean=4.0, speed=2.0, correlation=0.5, S0=1.0,
@@ -226,7 +231,9 @@ def run_reference(args, wl_name, wl):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": wl_name, **{k: v for k, v in wl.items() if not k.startswith("cpu_")}},
+           "config": {"workload": wl_name, "sde": wl["sde"], "paths_per_gpu": wl["paths"], "euler_steps": wl["steps"],
+                      "input_size": wl["d"], "hidden_size": wl["H"], "mlp": "%dx%d tanh" % (wl["layers"], wl["width"]),
+                      "dropout": wl["dropout"], "mode": "train", "parallelism": "cpu"},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "torch_threads": torch.get_num_threads()}

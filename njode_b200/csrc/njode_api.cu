@@ -78,14 +78,20 @@ __global__ void nj_grad_reduce_kernel(const __grid_constant__ NjCfg cfg, const f
     }
 }
 
-// loss = (sum_r row_loss[r]) / batch_size   (single block, fixed order, fp64 accumulation)
-__global__ void nj_loss_reduce_kernel(const float* __restrict__ row_loss, int N, float inv_b, float* __restrict__ loss) {
-    __shared__ double sh[256];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s += (double)row_loss[i];
-    sh[threadIdx.x] = s;
+// loss = (sum_r row_loss[r]) / batch_size   (single block, fixed summation order, fp64 accumulation;
+// 1024 threads x 4 independent accumulators so that the latency of the loads overlaps)
+__global__ void __launch_bounds__(1024) nj_loss_reduce_kernel(const float* __restrict__ row_loss, int N, float inv_b, float* __restrict__ loss) {
+    __shared__ double sh[1024];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = threadIdx.x;
+    for (; i + 3 * 1024 < N; i += 4 * 1024) {
+        s0 += (double)row_loss[i]; s1 += (double)row_loss[i + 1024];
+        s2 += (double)row_loss[i + 2048]; s3 += (double)row_loss[i + 3072];
+    }
+    for (; i < N; i += 1024) s0 += (double)row_loss[i];
+    sh[threadIdx.x] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
+    for (int w = 512; w > 0; w >>= 1) {
         if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
         __syncthreads();
     }
@@ -205,7 +211,7 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
             nj_fwd_kernel<<<pl.grid_fwd, pl.fwd.nt, pl.smem_fwd_bytes, st>>>(pl.fwd, a);
     }
     if (tm) { cudaEventRecord(g_ev[1], st); g_ev_rec[0] = true; }
-    if (loss) nj_loss_reduce_kernel<<<1, 256, 0, st>>>(a.row_loss, batch->N, 1.f / (float)batch->batch_size_norm, loss);
+    if (loss) nj_loss_reduce_kernel<<<1, 1024, 0, st>>>(a.row_loss, batch->N, 1.f / (float)batch->batch_size_norm, loss);
     NJ_CUDA(cudaGetLastError());
     return 0;
 }

@@ -272,6 +272,8 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
     s.tiles_total = tiles;
     const char* ftr = getenv("NJODE_FORCE_TR");
     const int force_tr = ftr ? atoi(ftr) : 0;
+    const char* fnw = getenv("NJODE_FORCE_NW");
+    const int force_nw = fnw ? atoi(fnw) : 0;
     const int n_loss = std::max(0, std::min(b.n_loss_units, n_units));
     const int run_b[2] = {0, n_loss}, run_e[2] = {n_loss, n_units};
     int n1[2] = {b.seg_n1[0], b.seg_n1[1]}, n2[2] = {b.seg_n2[0], b.seg_n2[1]};
@@ -279,28 +281,34 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
     {
         s.f_region = nj_seg_fwd_region(c, s, 16);
         s.f_img = 0; s.f_warp0 = c.img_floats;
-        int nw = 0;
-        for (int cand = 12; cand >= 2; --cand)          // launch bounds: 384 threads
-            if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
-        if (!nw) return;
-        s.nw_f = nw;
-        s.f_smem_floats = c.img_floats + nw * s.f_region;
         static const int trs3[3] = {1, 2, 4};
         if (force_tr) { const int one[1] = {std::min(4, force_tr)}; s.f_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr); }
         else s.f_ncls = nj_seg_classes(run_b, run_e, n1, n2, trs3, 3, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr);
         s.n_tiles_f = s.f_t0[s.f_ncls];
+        int nw = 0;
+        for (int cand = 12; cand >= 2; --cand)          // launch bounds: 384 threads
+            if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
+        if (!nw) return;
+        // small batches: fewer warps per CTA so that every SM gets work
+        nw = std::max(2, std::min(nw, (s.n_tiles_f + num_sms - 1) / num_sms));
+        if (force_nw) nw = std::max(2, std::min(12, force_nw));
+        s.nw_f = nw;
+        s.f_smem_floats = c.img_floats + nw * s.f_region;
     }
     // ---- backward: CTA-level arrays of P = 8 * nw rows (tallest tile) ----
     {
-        const int min_nw = (tiles + NJ_SEG_NT_MAX * 32 - 1) / (NJ_SEG_NT_MAX * 32);
+        // small batches: fewer warps (rows) per CTA so that every SM gets a tile; dW tiles beyond the register
+        // capacity of the smaller CTA go through the partial image in global memory (nj_seg_dw)
+        int want = std::max(4, std::min(12, (n_units + 8 * num_sms - 1) / (8 * num_sms)));
+        if (force_nw) want = std::max(2, std::min(12, force_nw));
         int nw = 0;
-        for (int cand = 12; cand >= std::max(2, min_nw); --cand) {       // launch bounds: 384 threads
+        for (int cand = want; cand >= 2; --cand) {       // launch bounds: 384 threads
             const int fl = nj_seg_bwd_layout(c, s, 8 * cand);
             if ((size_t)fl * 4 <= smem_limit) { nw = cand; s.b_smem_floats = fl; s.P_b = 8 * cand; break; }
         }
         if (!nw) return;
         s.nw_b = nw;
-        s.nt_slots = (tiles + nw * 32 - 1) / (nw * 32);
+        s.nt_slots = std::min(NJ_SEG_NT_MAX, (tiles + nw * 32 - 1) / (nw * 32));
         static const int trs2[2] = {1, 2};
         if (force_tr) { const int one[1] = {std::min(2, force_tr)}; s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr); }
         else s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, trs2, 2, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr);

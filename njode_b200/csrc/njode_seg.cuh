@@ -636,43 +636,85 @@ NJ_HD void nj_segb_bind(NjSegB& t, const NjSeg& s, float* smem) {
 
 // phase B: dW[o][k] += sum_r g[r][o] a[r][k] over the P rows of the CTA, thread-owned 4x4 tiles
 // (+ bias sums in the kg == 0 tiles) held in `acc` (registers) for the whole launch.
-NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, float* acc, int tid, int nt, int Pt) {
+// (net, layer, og, kg) of dW tile T inside network `netid`; false when T belongs to another network
+NJ_HD bool nj_seg_tile_decode(const NjCfg& c, const NjSeg& s, int netid, int T, int& l, int& og, int& kg) {
+    const NjNet& N = c.net[netid];
+    if (T < s.tile_base[netid][0]) return false;
+    l = 0;
+    for (int ll = N.n - 1; ll > 0; --ll) if (T >= s.tile_base[netid][ll]) { l = ll; break; }
+    const int K4 = (N.dim[l] + 3) >> 2, O4 = (N.dim[l + 1] + 3) >> 2;
+    const int tl = T - s.tile_base[netid][l];
+    if (tl >= K4 * O4) return false;
+    kg = tl % K4; og = tl / K4;
+    return true;
+}
+
+// r[0..15] += sum_r g[r][4og..] (x) a[r][4kg..],  r[16..19] += sum_r g[r][4og..]   over Pt rows
+NJ_HD void nj_seg_dw_rows(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, int l, int og, int kg, int Pt, float* q) {
     const NjNet& N = c.net[netid];
     const int P = s.P_b;
+    const float* g; int g_s;
+    if (l == N.n - 1) { g = t.GOUT; g_s = s.sO; } else { g = t.G + (size_t)l * P * s.sA; g_s = s.sA; }
+    const float* av; int a_s;
+    if (l == 0) { av = t.IN; a_s = s.sI; } else { av = t.A + (size_t)(l - 1) * P * s.sA; a_s = s.sA; }
+    nj_sp gq = nj_sp_of(g + 4 * og), aq = nj_sp_of(av + 4 * kg);
+    float r00 = q[0], r01 = q[1], r02 = q[2], r03 = q[3], r10 = q[4], r11 = q[5], r12 = q[6], r13 = q[7];
+    float r20 = q[8], r21 = q[9], r22 = q[10], r23 = q[11], r30 = q[12], r31 = q[13], r32 = q[14], r33 = q[15];
+    float b0 = q[16], b1 = q[17], b2 = q[18], b3 = q[19];
+#pragma unroll 4
+    for (int r = 0; r < Pt; ++r) {
+        const nj_f4 gv = nj_sp_ld4(gq);
+        const nj_f4 x = nj_sp_ld4(aq);
+        gq = NJ_SP_ADD(gq, g_s); aq = NJ_SP_ADD(aq, a_s);
+        r00 = fmaf(gv.x, x.x, r00); r01 = fmaf(gv.x, x.y, r01); r02 = fmaf(gv.x, x.z, r02); r03 = fmaf(gv.x, x.w, r03);
+        r10 = fmaf(gv.y, x.x, r10); r11 = fmaf(gv.y, x.y, r11); r12 = fmaf(gv.y, x.z, r12); r13 = fmaf(gv.y, x.w, r13);
+        r20 = fmaf(gv.z, x.x, r20); r21 = fmaf(gv.z, x.y, r21); r22 = fmaf(gv.z, x.z, r22); r23 = fmaf(gv.z, x.w, r23);
+        r30 = fmaf(gv.w, x.x, r30); r31 = fmaf(gv.w, x.y, r31); r32 = fmaf(gv.w, x.z, r32); r33 = fmaf(gv.w, x.w, r33);
+        b0 += gv.x; b1 += gv.y; b2 += gv.z; b3 += gv.w;
+    }
+    q[0] = r00; q[1] = r01; q[2] = r02; q[3] = r03; q[4] = r10; q[5] = r11; q[6] = r12; q[7] = r13;
+    q[8] = r20; q[9] = r21; q[10] = r22; q[11] = r23; q[12] = r30; q[13] = r31; q[14] = r32; q[15] = r33;
+    q[16] = b0; q[17] = b1; q[18] = b2; q[19] = b3;
+}
+
+// adds one 4x4 tile (+ bias sums of the kg == 0 tile) into a gradient image; `add`: read-modify-write
+NJ_HD void nj_seg_tile_store(const NjCfg& c, int netid, int l, int og, int kg, const float* q, float* gpart, bool add) {
+    const NjNet& N = c.net[netid];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float* p = gpart + N.w_img[l] + (size_t)(4 * og + i) * N.ks[l] + 4 * kg;
+        nj_f4 v; v.x = q[4 * i]; v.y = q[4 * i + 1]; v.z = q[4 * i + 2]; v.w = q[4 * i + 3];
+        if (add) { const nj_f4 o = nj_ld4(p); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        nj_st4(p, v);
+    }
+    if (kg == 0 && N.b_src[l] >= 0) {
+        float* p = gpart + N.b_img[l] + 4 * og;
+        nj_f4 v; v.x = q[16]; v.y = q[17]; v.z = q[18]; v.w = q[19];
+        if (add) { const nj_f4 o = nj_ld4(p); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        nj_st4(p, v);
+    }
+}
+
+// phase B: dW[o][k] += sum_r g[r][o] a[r][k] over the Pt rows of the tile.  Tiles are thread-owned: the first
+// NT_MAX * nt of them (the ODE network first) live in registers (`acc`) for the whole launch; the others are
+// accumulated from zero and added into this CTA's partial image in global memory (L2 resident) right away.
+NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, float* acc, float* gpart,
+                     int tid, int nt, int Pt) {
 #pragma unroll
     for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
         if (slot >= s.nt_slots) break;
-        const int T = slot * nt + tid;
-        if (T < s.tile_base[netid][0]) continue;
-        int l = 0;
-        for (int ll = N.n - 1; ll > 0; --ll) if (T >= s.tile_base[netid][ll]) { l = ll; break; }
-        const int K4 = (N.dim[l] + 3) >> 2, O4 = (N.dim[l + 1] + 3) >> 2;
-        const int tl = T - s.tile_base[netid][l];
-        if (tl >= K4 * O4) continue;
-        const int kg = tl % K4, og = tl / K4;
-        const float* g; int g_s;
-        if (l == N.n - 1) { g = t.GOUT; g_s = s.sO; } else { g = t.G + (size_t)l * P * s.sA; g_s = s.sA; }
-        const float* av; int a_s;
-        if (l == 0) { av = t.IN; a_s = s.sI; } else { av = t.A + (size_t)(l - 1) * P * s.sA; a_s = s.sA; }
-        nj_sp gq = nj_sp_of(g + 4 * og), aq = nj_sp_of(av + 4 * kg);
-        float* q = acc + slot * 20;
-        float r00 = q[0], r01 = q[1], r02 = q[2], r03 = q[3], r10 = q[4], r11 = q[5], r12 = q[6], r13 = q[7];
-        float r20 = q[8], r21 = q[9], r22 = q[10], r23 = q[11], r30 = q[12], r31 = q[13], r32 = q[14], r33 = q[15];
-        float b0 = q[16], b1 = q[17], b2 = q[18], b3 = q[19];
-#pragma unroll 4
-        for (int r = 0; r < Pt; ++r) {
-            const nj_f4 gv = nj_sp_ld4(gq);
-            const nj_f4 x = nj_sp_ld4(aq);
-            gq = NJ_SP_ADD(gq, g_s); aq = NJ_SP_ADD(aq, a_s);
-            r00 = fmaf(gv.x, x.x, r00); r01 = fmaf(gv.x, x.y, r01); r02 = fmaf(gv.x, x.z, r02); r03 = fmaf(gv.x, x.w, r03);
-            r10 = fmaf(gv.y, x.x, r10); r11 = fmaf(gv.y, x.y, r11); r12 = fmaf(gv.y, x.z, r12); r13 = fmaf(gv.y, x.w, r13);
-            r20 = fmaf(gv.z, x.x, r20); r21 = fmaf(gv.z, x.y, r21); r22 = fmaf(gv.z, x.z, r22); r23 = fmaf(gv.z, x.w, r23);
-            r30 = fmaf(gv.w, x.x, r30); r31 = fmaf(gv.w, x.y, r31); r32 = fmaf(gv.w, x.z, r32); r33 = fmaf(gv.w, x.w, r33);
-            b0 += gv.x; b1 += gv.y; b2 += gv.z; b3 += gv.w;
-        }
-        q[0] = r00; q[1] = r01; q[2] = r02; q[3] = r03; q[4] = r10; q[5] = r11; q[6] = r12; q[7] = r13;
-        q[8] = r20; q[9] = r21; q[10] = r22; q[11] = r23; q[12] = r30; q[13] = r31; q[14] = r32; q[15] = r33;
-        q[16] = b0; q[17] = b1; q[18] = b2; q[19] = b3;
+        int l, og, kg;
+        if (!nj_seg_tile_decode(c, s, netid, slot * nt + tid, l, og, kg)) continue;
+        nj_seg_dw_rows(c, s, t, netid, l, og, kg, Pt, acc + slot * 20);
+    }
+    for (int T = NJ_SEG_NT_MAX * nt + tid; T < s.tiles_total; T += nt) {
+        int l, og, kg;
+        if (!nj_seg_tile_decode(c, s, netid, T, l, og, kg)) continue;
+        float q[20];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) q[i] = 0.f;
+        nj_seg_dw_rows(c, s, t, netid, l, og, kg, Pt, q);
+        nj_seg_tile_store(c, netid, l, og, kg, q, gpart, true);
     }
 }
 
@@ -683,27 +725,9 @@ NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, flo
         if (slot >= s.nt_slots) break;
         const int T = slot * nt + tid;
         if (T >= s.tiles_total) continue;
-        int netid = NJODE_NET_ODE, l = 0;
-        bool found = false;
-        for (int oi = 2; oi >= 0 && !found; --oi) {
-            const int n_ = oi == 0 ? NJODE_NET_ODE : (oi == 1 ? NJODE_NET_RO : NJODE_NET_ENC);
-            const NjNet& N = c.net[n_];
-            for (int ll = N.n - 1; ll >= 0; --ll) if (T >= s.tile_base[n_][ll]) { netid = n_; l = ll; found = true; break; }
-        }
-        const NjNet& N = c.net[netid];
-        const int K4 = (N.dim[l] + 3) >> 2, O4 = (N.dim[l + 1] + 3) >> 2;
-        const int tl = T - s.tile_base[netid][l];
-        if (tl >= K4 * O4) continue;
-        const int kg = tl % K4, og = tl / K4;
-        const float* q = acc + slot * 20;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            nj_f4 v; v.x = q[4 * i]; v.y = q[4 * i + 1]; v.z = q[4 * i + 2]; v.w = q[4 * i + 3];
-            nj_st4(gpart + N.w_img[l] + (size_t)(4 * og + i) * N.ks[l] + 4 * kg, v);
-        }
-        if (kg == 0 && N.b_src[l] >= 0) {
-            nj_f4 v; v.x = q[16]; v.y = q[17]; v.z = q[18]; v.w = q[19];
-            nj_st4(gpart + N.b_img[l] + 4 * og, v);
+        for (int netid = 0; netid < 3; ++netid) {
+            int l, og, kg;
+            if (nj_seg_tile_decode(c, s, netid, T, l, og, kg)) { nj_seg_tile_store(c, netid, l, og, kg, acc + slot * 20, gpart, false); break; }
         }
     }
 }
@@ -732,10 +756,11 @@ NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, flo
 
 template <int TR>
 NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, const NjSegB& t, float* nj_acc_base,
-                           int u0, int u1) {
+                           int cta, int u0, int u1) {
     constexpr int R = 4 * TR;
     const int P = s.P_b, nt = s.nw_b * 32, Pt = R * s.nw_b;
     float* simg = smem + s.b_img;
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
     const float gl = NJ_LDG(a.grad_loss);
     const int d4 = ((c.d + 3) >> 2) << 2, H4 = ((c.H + 3) >> 2) << 2, inf4 = ((c.inf + 3) >> 2) << 2, do4 = ((c.dout + 3) >> 2) << 2;
     const int wa = P * s.sA;
@@ -886,7 +911,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
         }
         if (any_jump) {
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), tid, nt, Pt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), gpart, tid, nt, Pt); }
             NJ_SYNC();
             // J5: encoder at X_obs, backward with g = dL/dE (from Y only)
             NJ_WARPS(wp, s.nw_b) {
@@ -903,7 +928,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                 nj_seg_mlp_dx<TR>(w, NJODE_NET_ENC, false);
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), tid, nt, Pt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), gpart, tid, nt, Pt); }
             NJ_SYNC();
             // J6: readout at h_before, backward with g = dL/dY_bj -> gradient wrt h at the segment end
             NJ_WARPS(wp, s.nw_b) {
@@ -934,7 +959,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                 }
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), tid, nt, Pt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), gpart, tid, nt, Pt); }
             NJ_SYNC();
         }
         // ================= Euler steps, reversed =================
@@ -979,7 +1004,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                 }
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ODE, NJ_ACC(tid), tid, nt, Pt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ODE, NJ_ACC(tid), gpart, tid, nt, Pt); }
             NJ_SYNC();
         }
         // ================= the start encoder, reversed =================
@@ -998,7 +1023,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
             nj_seg_mlp_dx<TR>(w, NJODE_NET_ENC, false);
         }
         NJ_SYNC();
-        NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), tid, nt, Pt); }
+        NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), gpart, tid, nt, Pt); }
         NJ_SYNC();
     }
 }
@@ -1008,6 +1033,7 @@ NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     float* simg = smem + s.b_img;
     nj_stage_image(simg, a.image, c.img_floats, nt);
     nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
+    nj_zero(a.partials + (size_t)cta * c.img_floats, c.img_floats, nt);      // overflow tiles add into it
     NJ_SYNC();
     NjSegB t;
     nj_segb_bind(t, s, smem);
@@ -1021,11 +1047,9 @@ NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
         if (tile >= s.n_tiles_b) break;
         int ub, ue;
         const int tr = nj_seg_tile_lookup(s.b_ncls, s.b_t0, s.b_u0, s.b_u1, s.b_tr, 4 * s.nw_b, tile, ub, ue);
-        if (tr == 2) nj_seg_bwd_tile<2>(c, s, a, smem, t, nj_acc_base, ub, ue);
-        else nj_seg_bwd_tile<1>(c, s, a, smem, t, nj_acc_base, ub, ue);
+        if (tr == 2) nj_seg_bwd_tile<2>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
+        else nj_seg_bwd_tile<1>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
     }
     float* gpart = a.partials + (size_t)cta * c.img_floats;
-    nj_zero(gpart, c.img_floats, nt);
-    NJ_SYNC();
     NJ_THREADS(tid, nt) { nj_seg_dw_flush(c, s, NJ_ACC(tid), gpart, tid, nt); }
 }

@@ -79,6 +79,39 @@ def test_wide_model_global_weights_against_oracle():
     _oracle_vs_cuda(cfg, batch, 1.0 / 12, 1.0, seed=4)
 
 
+def test_config3_combined_2x100_nets_against_oracle():
+    """BASELINE config 3 (i): 2x100 tanh nets, H=10 (parallel_train.py:609-632) on a regular grid"""
+    nn100 = [[100, "tanh"], [100, "tanh"]]
+    cfg = cases.demo_cfg(ode_nn=nn100, enc_nn=nn100, readout_nn=nn100)
+    batch = cases.grid_batch(96, 1, 40, 0.1, seed=21)
+    _oracle_vs_cuda(cfg, batch, 1.0 / 40, 1.0, seed=5)
+    _oracle_vs_cuda(dict(cfg, dropout_rate=0.1), batch, 1.0 / 40, 1.0, seed=5, train=True)
+
+
+def test_config3_heston_wo_feller_two_coordinates_against_oracle():
+    """BASELINE config 3 (ii): HestonWOFeller with return_vol -> input_size 2, 2x50 nets"""
+    cfg = cases.demo_cfg(input_size=2, output_size=2)
+    batch = cases.grid_batch(300, 2, 50, 0.1, seed=22)
+    _oracle_vs_cuda(cfg, batch, 0.02, 1.0, seed=6)
+    _oracle_vs_cuda(dict(cfg, dropout_rate=0.1), batch, 0.02, 1.0, seed=6, train=True)
+
+
+def test_config5_scaled_architecture_against_oracle():
+    """BASELINE config 5 architecture (d=16, H=256, 4x256 tanh) at a size the oracle finishes in seconds"""
+    nn = [[256, "tanh"]] * 4
+    cfg = cases.demo_cfg(input_size=16, output_size=16, hidden_size=256, ode_nn=nn, enc_nn=nn, readout_nn=nn)
+    batch = cases.grid_batch(24, 16, 8, 0.25, seed=23)
+    _oracle_vs_cuda(cfg, batch, 0.125, 1.0, seed=7)
+
+
+@pytest.mark.parametrize("B", [200, 5000])
+def test_demo_batch_sweep_train_mode(B):
+    """batch sweep of config 3 on the demo nets, dropout on: segment fast path with every tile height"""
+    cfg = cases.demo_cfg(dropout_rate=0.1)
+    batch = cases.grid_batch(B, 1, 100, 0.1, seed=24)
+    _oracle_vs_cuda(cfg, batch, 0.01, 1.0, seed=8, train=True)
+
+
 def test_empty_batch_edges():
     """no observation rows at all / zero Euler steps"""
     cfg = cases.CONFIGS["demo"]

@@ -25,6 +25,7 @@ def sim_runner():
     os.environ.pop("NJODE_FORCE_TR", None)
     os.environ.pop("NJODE_NO_SEG", None)
     os.environ.pop("NJODE_INDEX", None)
+    os.environ.pop("NJODE_FORCE_NW", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -147,3 +148,18 @@ def test_index_builders_agree_exactly():
             lens = units[:, 2] - units[:, 1]
             assert [int(v) for v in t[5][:4]] == [int((lens[:n_loss] >= 8).sum()), int((lens[:n_loss] >= 4).sum()),
                                                    int((lens[n_loss:] >= 8).sum()), int((lens[n_loss:] >= 4).sum())]
+
+
+@pytest.mark.parametrize("nw", [2, 5])
+@pytest.mark.parametrize("name", ["bs_ckpt1", "easy_w07_nores"])
+def test_segment_path_small_ctas_spill_dw_tiles_to_the_partial_image(name, nw):
+    """few warps per CTA (small batches): dW tiles beyond the register capacity accumulate through global memory"""
+    os.environ["NJODE_FORCE_NW"] = str(nw)
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+
+
+def test_segment_path_small_ctas_with_dropout():
+    os.environ["NJODE_FORCE_NW"] = "3"
+    cfg = cases.demo_cfg(dropout_rate=0.2)
+    batch = cases.grid_batch(40, 1, 25, 0.2, seed=16)
+    parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
