@@ -62,7 +62,8 @@ def _worker(rank, world, port, dropout, q):
     total = dp.reduce_loss(loss)
     ok = True
     for g, p in zip(r_grads, model.parameters()):
-        ok &= bool(torch.allclose(p.grad, g, rtol=2e-5, atol=1e-7))
+        # fp32 sums in a different order (two shards): tolerance relative to the tensor's scale
+        ok &= bool(torch.allclose(p.grad, g, rtol=2e-5, atol=2e-6 * float(g.abs().max()) + 1e-7))
     lo, hi = (B * rank) // world, (B * (rank + 1)) // world
     ok &= bool(torch.allclose(hT, r_hT[lo:hi], rtol=1e-5, atol=1e-6))
     ok &= bool(abs(float(total) - float(r_loss)) <= 1e-5 * abs(float(r_loss)))
