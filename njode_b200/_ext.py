@@ -92,6 +92,19 @@ class Lib:
             f.restype = C.c_int
         if d.njode_abi_version() != 3:
             raise NjodeError("njode_b200: ABI version mismatch in %s" % path)
+        # tensor-core path (absent from the host simulation used by the CPU-only tests)
+        self.has_wide = hasattr(d, "njode_wide_forward")
+        if self.has_wide:
+            d.njode_wide_supported.argtypes = [C.POINTER(ModelT)]
+            d.njode_wide_supported.restype = C.c_int
+            d.njode_wide_workspace_bytes.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT)]
+            d.njode_wide_workspace_bytes.restype = C.c_int64
+            d.njode_wide_forward.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT), C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.POINTER(SavedT), C.c_void_p, C.c_void_p]
+            d.njode_wide_forward.restype = C.c_int
+            d.njode_wide_ws_offsets.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT), C.POINTER(C.c_int64)]
+            d.njode_wide_ws_offsets.restype = C.c_int
+            d.njode_wide_get_timing.argtypes = [C.POINTER(C.c_float)] * 3
 
     def check(self, rc, what):
         if rc != 0:
@@ -276,6 +289,34 @@ class Runner:
         dev = self.device.index if self.is_cuda and self.device.index is not None else 0
         self.lib.check(self.lib.dll.njode_plan(C.byref(model_t), C.byref(batch_t), dev, C.byref(pl)), "njode_plan")
         return pl
+
+    def wide_supported(self, model_t):
+        """True when the tcgen05 tensor-core path (njode_wide_*) can run this model"""
+        return bool(self.lib.has_wide and self.is_cuda and self.lib.dll.njode_wide_supported(C.byref(model_t)))
+
+    def _wide_workspace(self, nbytes):
+        ws = getattr(self, "_wws", None)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._wws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def forward_wide(self, model_t, pb, params, H, dout, get_loss, need_grad):
+        """same contract as ``forward`` on the tensor-core kernels (bf16 operands, fp32 accumulate / state)"""
+        f32 = dict(dtype=torch.float32, device=self.device)
+        nbytes = self.lib.dll.njode_wide_workspace_bytes(C.byref(model_t), C.byref(pb.fwd))
+        if nbytes < 0:
+            self.lib.check(int(nbytes), "njode_wide_workspace_bytes")
+        ws = self._wide_workspace(nbytes)
+        hT = torch.empty(pb.B, H, **f32)
+        loss = torch.zeros((), **f32) if get_loss else None
+        h_hist = torch.empty(max(pb.sched.S, 1) * pb.B * H, **f32) if need_grad else None
+        h_before = torch.empty(max(pb.N, 1) * H, **f32) if (need_grad or get_loss) else None
+        y_after = torch.empty(max(pb.N, 1) * dout, **f32) if need_grad else None
+        saved_t = SavedT(_ptr(h_hist), _ptr(h_before), _ptr(y_after))
+        rc = self.lib.dll.njode_wide_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT),
+                                             _ptr(loss), C.byref(saved_t), _ptr(ws), self._stream())
+        self.lib.check(rc, "njode_wide_forward")
+        return hT, loss, None, None, ((h_hist, h_before, y_after) if need_grad else None)
 
     def forward(self, model_t, pb, params, H, dout, get_loss, need_grad):
         f32 = dict(dtype=torch.float32, device=self.device)

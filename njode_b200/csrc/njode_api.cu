@@ -22,6 +22,7 @@ extern "C" int njode_abi_version(void) { return NJODE_ABI_VERSION; }
 static long long g_launches = 0;
 extern "C" long long njode_launch_count(void) { return g_launches; }
 #define NJ_LAUNCHED(n) (g_launches += (n))
+void nj_count_launches(int n) { g_launches += n; }          // used by njode_wide.cu
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -112,6 +113,7 @@ static bool nj_timing_on() {
     return g_timing != 0;
 }
 extern "C" void njode_set_timing(int on) { g_timing = on ? 1 : 0; }
+int nj_timing_flag() { if (g_timing < 0) { const char* e = getenv("NJODE_TIMING"); g_timing = (e && atoi(e)) ? 1 : 0; } return g_timing; }   // njode_wide.cu
 // elapsed milliseconds of the most recent forward / backward main kernel (-1: none recorded)
 extern "C" int njode_get_timing(float* fwd_ms, float* bwd_ms) {
     float f = -1.f, b = -1.f;

@@ -1,0 +1,638 @@
+// njode_wide.cuh -- tensor-core ("wide") path of the NJ-ODE hot path for sm_100a: tcgen05.mma with
+// TMEM accumulators, weights streamed through shared memory by TMA bulk copies, bf16 operands and
+// fp32 accumulation.  Used when the MLPs are real dense contractions (BASELINE config 5:
+// d=16, H=256, 4x256 tanh nets); the narrow demo nets stay on the fp32 FMA kernels (njode_seg.cuh).
+//
+// Same segment decomposition as njode_seg.cuh (NJODE/models.py:463-470: h after a jump = enc(X_obs)):
+// every (path, inter-observation segment) is an independent unit.  One CTA marches a tile of 128
+// units; unit r of the tile is TMEM lane r / row r of every operand tile.
+//
+//   pass ENC : h_start[u] = encoder(start value of unit u)                  (FFNN.forward, models.py:261-276)
+//   pass ODE : Euler steps of the unit, h kept in TMEM columns [256,512) in fp32; h_hist / h_before / hT
+//              written on the fly                                           (ode_step, models.py:369-377)
+//   pass RO  : Y_bj = readout(h_before[row]), Y = readout(enc(X_obs)), loss row (compute_loss, models.py:71-126)
+//
+// Every Linear layer over the tile is D[128 x N] = A[128 x K] . W[N x K]^T:
+//   * A (activations, bf16) lives in shared memory as K-blocks of 64 columns, each block [128 rows x 128 B]
+//     in the canonical K-major SWIZZLE_128B layout (16-byte chunk c of row r stored at chunk c ^ (r & 7));
+//     it is written by the epilogue threads of the previous layer (generic proxy -> fence.proxy.async).
+//   * W comes from a bf16 image in global memory that nj_wide_pack_kernel has already laid out in exactly
+//     that shared-memory image, one [n16 rows x 128 B] block per (layer, K-block), so a stage is filled by ONE
+//     cp.async.bulk (TMA, no tensor map) completing on an mbarrier.
+//   * D accumulates in TMEM columns [0,256) (tcgen05.mma.cta_group::1.kind::f16, M=128, N=n16, K=16 per
+//     instruction, issued by one thread); the epilogue warps read it with tcgen05.ld.32x32b, add the bias,
+//     apply tanh (MUFU.TANH) / relu and dropout, and write the next layer's A operand.
+// Warp roles (384 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM allocator, warps 4..11 =
+// epilogue (warp w reads TMEM lanes 32*(w%4).., column half (w-4)/4).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/njode_b200.h"
+#include "njode_hash.cuh"
+
+namespace njw {
+
+constexpr int TILE_M = 128;
+constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = 256 * 128;          // one K-block of a 256-row weight matrix
+constexpr int A_BLOCK_BYTES = TILE_M * 128;     // one K-block of the activation tile
+constexpr int A_BLOCKS = 5;                     // 4 main blocks (K <= 256) + the auxiliary block
+constexpr int AUX_BLOCK = 4;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int MAX_W = 256;                      // widest layer / hidden state
+constexpr int MAX_D = 16;                       // widest input / output
+constexpr int AUX_X0 = 8;                       // auxiliary block: columns 0..5 = tau, tdiff, tau+tdiff as bf16 hi/lo
+                                                // pairs, columns 8..8+d = tanh(x)
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_H = 256;                     // first TMEM column of the fp32 hidden state
+
+enum { MODE_ENC = 0, MODE_ODE = 1, MODE_RO = 2 };
+enum { KIND_PLAIN = 0, KIND_ODE0 = 1, KIND_ENC0 = 2 };
+
+struct WLayer {
+    int kb_main;        // K-blocks read from the main activation blocks
+    int has_aux;        // + the auxiliary block (layer 0 of the ODE / encoder nets)
+    int aux_ksteps;     // UMMA K-steps (of 16 columns) issued on the auxiliary block
+    int n, n16;         // outputs, padded to the UMMA N granularity
+    int in_dim;         // inputs of the nn.Linear
+    int act, drop, kind;
+    unsigned img_off;   // byte offset of K-block 0 inside the bf16 image (blocks are n16 * 128 B apart)
+    int bias_off;       // float offset inside the bias image
+    long long w_src, b_src;
+};
+struct WNet { int n; WLayer l[NJODE_MAX_LINEAR]; };
+struct WCfg {
+    WNet net[3];
+    int d, H, dout, curt, loss_kind, residual, training, has_drop;
+    float w, keep_scale;
+    unsigned thr, seed_lo, seed_hi;
+    unsigned img_bytes; int bias_floats;
+};
+
+struct WArgs {
+    njode_batch_t b;
+    const unsigned char* wimg;     // packed bf16 weight image
+    const float* bias;             // packed fp32 biases
+    float* h_start;                // [n_units, H]  encoder output per unit
+    int* row_unit;                 // [N] unit that starts at observation row r
+    float *hT, *row_loss, *h_hist, *h_before, *y_after;
+    int mode, n_tiles_loss, n_tiles, get_loss;
+};
+
+// dynamic shared memory map (bytes from the 1024-aligned base)
+constexpr int SM_A = 0;
+constexpr int SM_W = SM_A + A_BLOCKS * A_BLOCK_BYTES;
+constexpr int SM_BIAS = SM_W + NSTAGE * STAGE_BYTES;                 // [8][256] fp32
+constexpr int SM_RES = SM_BIAS + NJODE_MAX_LINEAR * MAX_W * 4;       // [128][16] fp32 residual partial of column half 1
+constexpr int SM_YBJ = SM_RES + TILE_M * MAX_D * 4;                  // [128][16] fp32
+constexpr int SM_BAR = SM_YBJ + TILE_M * MAX_D * 4;                  // mbarriers
+constexpr int SM_TOTAL = SM_BAR + 128;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;                          // + alignment slack
+
+#if !defined(NJODE_HOST_SIM)
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+// bounded spin: a protocol error traps (with the barrier's offset) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spins > (1u << 22)) {
+            printf("njode_wide: mbarrier wait timed out (cta %d thread %d barrier@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar & 127u, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                    "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                    "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+// bf16 hi/lo split of an fp32 scalar: hi + lo reproduces v to ~16 mantissa bits
+__device__ __forceinline__ uint32_t split_bf16(float v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+
+// shared-memory matrix descriptor of a K-major SWIZZLE_128B operand tile (rows of 128 B, 8-row groups 1024 B
+// apart); advancing along K inside the 64-column block = adding the byte offset to the start address.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);               // start address, LBO (unused) = 1
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);              // SBO = 1024 B, version 1, SWIZZLE_128B
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n16
+__device__ __forceinline__ uint32_t make_idesc(int n16) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n16 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile bookkeeping shared by the three roles
+// ------------------------------------------------------------------------------------------------
+struct Tile { int u0, u1, reps; };
+__device__ __forceinline__ Tile tile_of(const WCfg& c, const WArgs& a, int t) {
+    Tile T;
+    const int nl = a.b.n_loss_units;
+    if (t < a.n_tiles_loss) { T.u0 = t * TILE_M; T.u1 = min(T.u0 + TILE_M, nl); }
+    else { T.u0 = nl + (t - a.n_tiles_loss) * TILE_M; T.u1 = min(T.u0 + TILE_M, a.b.n_units); }
+    if (a.mode == MODE_ODE) {
+        const int32_t* dsc = a.b.unit_desc + (size_t)T.u0 * 6;       // units are sorted longest first within a run
+        T.reps = __ldg(dsc + 2) - __ldg(dsc + 1);
+    } else T.reps = (a.mode == MODE_RO) ? 2 : 1;
+    return T;
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue pieces (thread = TMEM lane r, column range of its half)
+// ------------------------------------------------------------------------------------------------
+// stores 32 consecutive bf16 activations (packed in p[16]) of row r, columns [c0, c0+32), into the A blocks
+__device__ __forceinline__ void store_a_chunk(uint32_t a_base, int r, int c0, const uint32_t* p) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int col = c0 + 8 * q;
+        const uint32_t addr = a_base + (uint32_t)(col >> 6) * A_BLOCK_BYTES + (uint32_t)r * 128u
+                            + ((uint32_t)(((col & 63) >> 3) ^ (r & 7)) << 4);
+        st_shared_v4(addr, p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+    }
+}
+
+// hidden layer: act(acc + bias) (+ dropout) of columns [c0, c0+32) -> bf16 -> A
+__device__ __forceinline__ void epi_hidden_chunk(uint32_t taddr, const float* bias_s, int c0, const WLayer& L,
+                                                 const WCfg& c, unsigned lk, uint32_t a_base, int r) {
+    uint32_t v[32];
+    tmem_ld32(taddr + (uint32_t)c0, v);
+    tmem_wait_ld();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+        x = (L.act == NJODE_ACT_TANH) ? tanh_fast(x) : (L.act == NJODE_ACT_RELU ? fmaxf(x, 0.f) : x);
+        f[j] = (c0 + j < L.n) ? x : 0.f;
+    }
+    if (L.drop) {
+        // neurons o and o ^ 8 share one hash word (nj_keep, njode_core.cuh): 16 words serve the 32 columns
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const unsigned word = nj_keep_word(lk, (unsigned)jj | ((unsigned)((c0 >> 4) + g) << 3));
+                const int j0 = g * 16 + jj, j1 = j0 + 8;
+                f[j0] = (word & 0xFFFFu) >= c.thr ? f[j0] * c.keep_scale : -0.f;
+                f[j1] = (word >> 16) >= c.thr ? f[j1] * c.keep_scale : -0.f;
+            }
+    }
+    uint32_t p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+    store_a_chunk(a_base, r, c0, p);
+}
+
+// tanh of 32 fp32 values -> bf16 -> A main blocks at columns [c0, c0+32); columns >= n are written as 0
+__device__ __forceinline__ void store_tanh_chunk(uint32_t a_base, int r, int c0, int n, const float* h) {
+    uint32_t p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float t0 = (c0 + 2 * j < n) ? tanh_fast(h[2 * j]) : 0.f;
+        const float t1 = (c0 + 2 * j + 1 < n) ? tanh_fast(h[2 * j + 1]) : 0.f;
+        p[j] = pack_bf16(t0, t1);
+    }
+    store_a_chunk(a_base, r, c0, p);
+}
+
+// 32 floats of a global row (columns [c0, c0+32) of a width-n row; n % 4 == 0), zero beyond n or when src == null
+__device__ __forceinline__ void load_row_chunk(const float* src, int c0, int n, float* h) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src && c0 + 4 * q < n) t = *reinterpret_cast<const float4*>(src + c0 + 4 * q);
+        h[4 * q] = t.x; h[4 * q + 1] = t.y; h[4 * q + 2] = t.z; h[4 * q + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store_row_chunk(float* dst, int c0, int n, const float* h) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (c0 + 4 * q < n) *reinterpret_cast<float4*>(dst + c0 + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+}
+
+// the auxiliary block row of unit r: time columns (chunk 0) and tanh(x) (columns 8..8+d)
+__device__ __forceinline__ void store_aux_time(uint32_t a_base, int r, float tau, float tdiff, int curt) {
+    const uint32_t addr = a_base + AUX_BLOCK * A_BLOCK_BYTES + (uint32_t)r * 128u + ((uint32_t)(0 ^ (r & 7)) << 4);
+    st_shared_v4(addr, split_bf16(tau), split_bf16(tdiff), curt ? split_bf16(tau + tdiff) : 0u, 0u);
+}
+__device__ __forceinline__ void store_aux_x(uint32_t a_base, int r, const float* x, int d) {
+    // columns 8..23 (chunks 1, 2) hold tanh(x[0..16)); chunks 3..7 are zero
+    uint32_t p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float t0 = (2 * j < d) ? nj_tanh(x[2 * j]) : 0.f, t1 = (2 * j + 1 < d) ? nj_tanh(x[2 * j + 1]) : 0.f;
+        p[j] = pack_bf16(t0, t1);
+    }
+    const uint32_t row = a_base + AUX_BLOCK * A_BLOCK_BYTES + (uint32_t)r * 128u;
+    st_shared_v4(row + ((uint32_t)(1 ^ (r & 7)) << 4), p[0], p[1], p[2], p[3]);
+    st_shared_v4(row + ((uint32_t)(2 ^ (r & 7)) << 4), p[4], p[5], p[6], p[7]);
+#pragma unroll
+    for (int q = 3; q < 8; ++q) st_shared_v4(row + ((uint32_t)(q ^ (r & 7)) << 4), 0u, 0u, 0u, 0u);
+}
+
+// d is a power of two <= 16.  res[m] holds the sum over the columns = m (mod 16); fold it to column mod d.
+__device__ __forceinline__ void fold_res(float* res, int d) {
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+        if (d <= w) {
+#pragma unroll
+            for (int j = 0; j < w; ++j) res[j] += res[j + w];
+        }
+}
+// xe[m] = x[m mod d]
+__device__ __forceinline__ void expand_x(const float* x, float* xe, int d) {
+#pragma unroll
+    for (int m = 0; m < MAX_D; ++m) xe[m] = x[m];
+#pragma unroll
+    for (int w = 1; w < MAX_D; w <<= 1)
+        if (d <= w) {
+#pragma unroll
+            for (int j = 0; j < w; ++j) xe[j + w] = xe[j];
+        }
+}
+
+__device__ __forceinline__ unsigned ev_start(const WArgs& a, int sr) {
+    return sr < 0 ? NJ_EVENT_INIT : NJ_EVENT_JUMP_BASE + 3u * (unsigned)__ldg(a.b.row_jump + sr) + 1u;
+}
+__device__ __forceinline__ unsigned ev_jump(const WArgs& a, int row, unsigned which) {
+    return NJ_EVENT_JUMP_BASE + 3u * (unsigned)__ldg(a.b.row_jump + row) + which;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned char* smem_raw) {
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t a_base = sbase + SM_A, w_base = sbase + SM_W;
+    float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS);
+    float* res_s = reinterpret_cast<float*>(smem + SM_RES);
+    float* ybj_s = reinterpret_cast<float*>(smem + SM_YBJ);
+    const uint32_t bar0 = sbase + SM_BAR;
+    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * NSTAGE, bar_acc = bar0 + 16 * NSTAGE, bar_a = bar_acc + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int netid = a.mode == MODE_ENC ? NJODE_NET_ENC : (a.mode == MODE_ODE ? NJODE_NET_ODE : NJODE_NET_RO);
+    const WNet& net = c.net[netid];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        mbar_init(bar_a, EPI_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < net.n * MAX_W; i += NUM_THREADS) {
+        const int l = i / MAX_W, o = i % MAX_W;
+        bias_s[i] = o < net.l[l].n16 ? __ldg(a.bias + net.l[l].bias_off + o) : 0.f;
+    }
+    // zero the activation blocks once: padding columns only ever meet zero weights but must stay finite
+    for (int i = threadIdx.x; i < A_BLOCKS * A_BLOCK_BYTES / 16; i += NUM_THREADS)
+        st_shared_v4(a_base + 16u * i, 0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const Tile T = tile_of(c, a, t);
+                for (int rep = 0; rep < T.reps; ++rep)
+                    for (int l = 0; l < net.n; ++l) {
+                        const WLayer& L = net.l[l];
+                        const uint32_t bytes = (uint32_t)L.n16 * 128u;
+                        const int nkb = L.kb_main + L.has_aux;
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+                            mbar_expect_tx(bar_full + 8 * stage, bytes);
+                            bulk_g2s(w_base + stage * STAGE_BYTES, a.wimg + L.img_off + (size_t)kb * bytes, bytes, bar_full + 8 * stage);
+                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0, pa = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const Tile T = tile_of(c, a, t);
+                for (int rep = 0; rep < T.reps; ++rep)
+                    for (int l = 0; l < net.n; ++l) {
+                        const WLayer& L = net.l[l];
+                        const uint32_t idesc = make_idesc(L.n16);
+                        const int nkb = L.kb_main + L.has_aux;
+                        mbar_wait(bar_a, pa); pa ^= 1;               // A operand written, accumulator drained
+                        tc_fence_after();
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            const bool aux = kb >= L.kb_main;
+                            const int ksteps = aux ? L.aux_ksteps : 4;
+                            mbar_wait(bar_full + 8 * stage, ph);
+                            tc_fence_after();
+                            const uint32_t ab = a_base + (uint32_t)(aux ? AUX_BLOCK : kb) * A_BLOCK_BYTES;
+                            const uint32_t wb = w_base + (uint32_t)stage * STAGE_BYTES;
+                            for (int k = 0; k < ksteps; ++k)
+                                tc_mma(tmem, make_desc(ab + 32u * k), make_desc(wb + 32u * k), idesc, (kb | k) ? 1u : 0u);
+                            tc_commit(bar_empty + 8 * stage);        // stage free once these MMAs have read it
+                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                        }
+                        tc_commit(bar_acc);                           // accumulator complete
+                    }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue warps =====================
+        const int q = warp & 3, hf = (warp - EPI_WARP0) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t pf = 0;
+        const int H = c.H, d = c.d;
+        const int hch = (H + 31) >> 5, hper = (hch + 1) >> 1;
+        const int hc_lo = hf * hper, hc_hi = min(hch, hc_lo + hper);              // this thread's chunks of an H-wide row
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+            const Tile T = tile_of(c, a, t);
+            const int u = T.u0 + r;
+            const bool valid = u < T.u1;
+            int path = 0, s0 = 0, len = 0, row = -1, flag = 0, sr = -1;
+            if (valid) {
+                const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                path = __ldg(dsc); s0 = __ldg(dsc + 1); len = __ldg(dsc + 2) - s0;
+                const int c0_ = __ldg(dsc + 3), c1_ = __ldg(dsc + 4), sc = __ldg(dsc + 5);
+                row = c1_ > c0_ ? __ldg(a.b.path_rows + c0_) : -1;
+                flag = (sc & NJODE_UNIT_WRITES_HT) ? 1 : 0;
+                sr = (sc & ~NJODE_UNIT_WRITES_HT) - 1;
+            }
+            const unsigned gpath = (unsigned)(path + a.b.path_id_offset);
+            float xr[MAX_D], xe[MAX_D];
+            float tau = 0.f;
+            float res[MAX_D];
+            unsigned rk = 0;
+            // ---------------- prologue ----------------
+            if (a.mode == MODE_ENC) {
+#pragma unroll
+                for (int j = 0; j < MAX_D; ++j)
+                    xr[j] = (valid && j < d) ? (sr < 0 ? __ldg(a.b.start_X + (size_t)path * d + j) : __ldg(a.b.X + (size_t)sr * d + j)) : 0.f;
+                if (hf == 0) {
+                    store_aux_x(a_base, r, xr, d);
+                    store_aux_time(a_base, r, 0.f, 0.f, 0);
+                    if (valid && sr >= 0) a.row_unit[sr] = u;
+                }
+                expand_x(xr, xe, d);
+                rk = nj_row_key(c.seed_lo, c.seed_hi, gpath, ev_start(a, sr));
+            } else if (a.mode == MODE_ODE) {
+#pragma unroll
+                for (int j = 0; j < MAX_D; ++j)
+                    xr[j] = (valid && j < d) ? (sr < 0 ? __ldg(a.b.start_X + (size_t)path * d + j) : __ldg(a.b.X + (size_t)sr * d + j)) : 0.f;
+                tau = (valid && sr >= 0) ? __ldg(a.b.jump_tau + __ldg(a.b.row_jump + sr)) : 0.f;
+                const float* hs = valid ? a.h_start + (size_t)u * H : nullptr;
+                for (int ch = hc_lo; ch < hc_hi; ++ch) {
+                    float h[32];
+                    load_row_chunk(hs, ch * 32, H, h);
+                    tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(h));
+                    if (valid && len == 0) {           // a unit without Euler steps (observation at t = 0)
+                        if (row >= 0 && a.h_before) store_row_chunk(a.h_before + (size_t)row * H, ch * 32, H, h);
+                        if (flag) store_row_chunk(a.hT + (size_t)path * H, ch * 32, H, h);
+                    }
+                    store_tanh_chunk(a_base, r, ch * 32, H, h);
+                }
+                tmem_wait_st();
+                if (hf == 0) {
+                    store_aux_x(a_base, r, xr, d);
+                    const float t0 = (valid && len > 0) ? __ldg(a.b.step_t + s0) : 0.f;
+                    store_aux_time(a_base, r, tau, t0 - tau, c.curt);
+                }
+                rk = nj_row_key(c.seed_lo, c.seed_hi, gpath, (unsigned)s0);
+            } else {
+#pragma unroll
+                for (int j = 0; j < MAX_D; ++j) res[j] = 0.f;
+                const float* hb = (valid && row >= 0) ? a.h_before + (size_t)row * H : nullptr;
+                for (int ch = hc_lo; ch < hc_hi; ++ch) {
+                    float h[32];
+                    load_row_chunk(hb, ch * 32, H, h);
+                    store_tanh_chunk(a_base, r, ch * 32, H, h);
+                    if (c.residual) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (ch * 32 + j < H) res[j & 15] += h[j];     // column mod 16
+                    }
+                }
+                fold_res(res, d);
+                if (hf == 1) {
+#pragma unroll
+                    for (int j = 0; j < MAX_D; ++j) res_s[r * MAX_D + j] = res[j];
+                }
+                rk = (valid && row >= 0) ? nj_row_key(c.seed_lo, c.seed_hi, gpath, ev_jump(a, row, 0u)) : 0u;
+            }
+            if (T.reps == 0) continue;
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(bar_a);
+            // ---------------- layers ----------------
+            for (int rep = 0; rep < T.reps; ++rep) {
+                for (int l = 0; l < net.n; ++l) {
+                    const WLayer& L = net.l[l];
+                    const bool last = (l == net.n - 1);
+                    mbar_wait(bar_acc, pf); pf ^= 1;
+                    tc_fence_after();
+                    const int nch = (L.n16 + 31) >> 5, per = (nch + 1) >> 1;
+                    const int c_lo = hf * per, c_hi = min(nch, c_lo + per);
+                    if (!last) {
+                        const unsigned lk = L.drop ? nj_layer_key(rk, (unsigned)(netid * 16 + l + 1)) : 0u;
+                        for (int ch = c_lo; ch < c_hi; ++ch)
+                            epi_hidden_chunk(tlane, bias_s + l * MAX_W, ch * 32, L, c, lk, a_base, r);
+                    } else if (a.mode == MODE_ENC) {
+                        for (int ch = c_lo; ch < c_hi; ++ch) {
+                            uint32_t v[32];
+                            tmem_ld32(tlane + ch * 32, v);
+                            tmem_wait_ld();
+                            float e[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                e[j] = __uint_as_float(v[j]) + bias_s[l * MAX_W + ch * 32 + j];
+                                if (c.residual) e[j] += xe[j & 15];                       // case 1: x.repeat(1, H / d)
+                            }
+                            if (valid) store_row_chunk(a.h_start + (size_t)u * H, ch * 32, H, e);
+                        }
+                    } else if (a.mode == MODE_ODE) {
+                        const int i = rep;
+                        const bool active = valid && i < len;
+                        const float dt = active ? __ldg(a.b.step_dt + s0 + i) : 0.f;
+                        const bool more = i + 1 < T.reps;
+                        for (int ch = c_lo; ch < c_hi; ++ch) {
+                            uint32_t v[32];
+                            float h[32];
+                            tmem_ld32(tlane + ch * 32, v);
+                            tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(h));
+                            tmem_wait_ld();
+                            if (active) {
+                                if (a.h_hist) store_row_chunk(a.h_hist + ((size_t)(s0 + i) * a.b.B + path) * H, ch * 32, H, h);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    h[j] = fmaf(dt, __uint_as_float(v[j]) + bias_s[l * MAX_W + ch * 32 + j], h[j]);
+                                if (i == len - 1) {
+                                    if (row >= 0 && a.h_before) store_row_chunk(a.h_before + (size_t)row * H, ch * 32, H, h);
+                                    if (flag) store_row_chunk(a.hT + (size_t)path * H, ch * 32, H, h);
+                                }
+                            }
+                            // .sync.aligned: every lane of the warp stores (finished / padding rows write h back unchanged)
+                            tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(h));
+                            if (more) store_tanh_chunk(a_base, r, ch * 32, H, h);
+                        }
+                        tmem_wait_st();
+                        if (more) {
+                            if (hf == 0) {
+                                const float tn = (valid && i + 1 < len) ? __ldg(a.b.step_t + s0 + i + 1) : 0.f;
+                                store_aux_time(a_base, r, tau, tn - tau, c.curt);
+                            }
+                            rk = nj_row_key(c.seed_lo, c.seed_hi, gpath, (unsigned)(s0 + i + 1));
+                        }
+                    } else {
+                        // readout: y = acc + bias + residual (mean over the H / d chunks of h, or h itself when H == d)
+                        if (hf == 0 && c_lo < c_hi) {
+                            uint32_t v[32];
+                            tmem_ld32(tlane, v);
+                            tmem_wait_ld();
+                            const float rmul = c.residual ? 1.f / (float)(H / d) : 0.f;
+                            float y[MAX_D];
+#pragma unroll
+                            for (int j = 0; j < MAX_D; ++j)
+                                y[j] = __uint_as_float(v[j]) + bias_s[l * MAX_W + j] + rmul * (res[j] + res_s[r * MAX_D + j]);
+                            if (rep == 0) {
+#pragma unroll
+                                for (int j = 0; j < MAX_D; ++j) ybj_s[r * MAX_D + j] = y[j];
+                            } else if (valid && row >= 0) {
+                                float sa = 0.f, sb = 0.f;
+#pragma unroll
+                                for (int j = 0; j < MAX_D; ++j) {
+                                    if (j < d) {
+                                        if (a.y_after) a.y_after[(size_t)row * d + j] = y[j];
+                                        const float x = __ldg(a.b.X + (size_t)row * d + j), yb = ybj_s[r * MAX_D + j];
+                                        const float da = x - y[j], db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y[j]) : (yb - x);
+                                        sa = fmaf(da, da, sa); sb = fmaf(db, db, sb);
+                                    }
+                                }
+                                if (a.get_loss) {
+                                    const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+                                    const float sm = (c.loss_kind == NJODE_LOSS_STANDARD) ? (2.f * c.w * ra + 2.f * (1.f - c.w) * rb)
+                                                                                          : (c.w * ra + (1.f - c.w) * rb);
+                                    a.row_loss[row] = sm * sm / __ldg(a.b.n_obs_ot + path);
+                                }
+                            }
+                        }
+                        if (rep == 0) {
+                            // second chain of the tile: Y = readout(h after the jump) with h = encoder output of the
+                            // unit that starts at this row
+                            epi_bar_sync();                       // res_s of chain 1 consumed by every row's hf-0 thread
+#pragma unroll
+                            for (int j = 0; j < MAX_D; ++j) res[j] = 0.f;
+                            const float* hs = (valid && row >= 0) ? a.h_start + (size_t)a.row_unit[row] * H : nullptr;
+                            for (int ch = hc_lo; ch < hc_hi; ++ch) {
+                                float h[32];
+                                load_row_chunk(hs, ch * 32, H, h);
+                                store_tanh_chunk(a_base, r, ch * 32, H, h);
+                                if (c.residual) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) if (ch * 32 + j < H) res[j & 15] += h[j];
+                                }
+                            }
+                            fold_res(res, d);
+                            if (hf == 1) {
+#pragma unroll
+                                for (int j = 0; j < MAX_D; ++j) res_s[r * MAX_D + j] = res[j];
+                            }
+                            rk = (valid && row >= 0) ? nj_row_key(c.seed_lo, c.seed_hi, gpath, ev_jump(a, row, 2u)) : 0u;
+                        }
+                    }
+                    const bool tile_done = last && rep + 1 == T.reps;
+                    if (a.mode == MODE_RO) epi_bar_sync();        // res_s / ybj_s written before the hf-0 threads read them
+                    if (!tile_done) {
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(bar_a);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+#endif  // !NJODE_HOST_SIM
+
+}  // namespace njw

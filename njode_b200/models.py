@@ -168,7 +168,8 @@ class _NJODEFunction(torch.autograd.Function):
     def forward(ctx, module, runner, pb, model_t, get_loss, need_grad, *params):
         flat = module._flat
         H, dout = module.hidden_size, module.output_size
-        hT, loss, path_h, path_y, saved = runner.forward(model_t, pb, flat, H, dout, get_loss, need_grad)
+        fwd = runner.forward_wide if module._use_tensor_cores(runner, pb, model_t) else runner.forward
+        hT, loss, path_h, path_y, saved = fwd(model_t, pb, flat, H, dout, get_loss, need_grad)
         ctx.module, ctx.runner, ctx.pb, ctx.model_t, ctx.saved = module, runner, pb, model_t, saved
         ctx.flat_version = module._flat_version
         ctx.mark_non_differentiable(*[t for t in (path_h, path_y) if t is not None])
@@ -237,6 +238,21 @@ class NJODE(torch.nn.Module):
         self.batch_size_norm = None      # global batch size under data parallelism
         self.path_id_offset = 0
         self.last_h2d_bytes = 0
+        # "auto": the tcgen05 tensor-core kernels (bf16 operands, fp32 accumulation and state) serve the
+        # non-masked loss/training call when every MLP is a real dense contraction (all hidden widths and
+        # hidden_size >= 128); "off": always the fp32 FMA kernels; "on": whenever the model qualifies.
+        self.tensor_cores = os.environ.get("NJODE_TENSOR_CORES", "auto")
+        self.last_forward_path = None
+
+    def _use_tensor_cores(self, runner, pb, model_t):
+        mode = self.tensor_cores
+        use = False
+        if mode != "off" and pb.fwd.unit_kind == 1 and not pb.return_path and hasattr(runner, "wide_supported"):
+            if runner.wide_supported(model_t):
+                widths = [w for desc in self._nn_desc if desc is not None for (w, _) in desc]
+                use = mode == "on" or (self.hidden_size >= 128 and len(widths) > 0 and min(widths) >= 128)
+        self.last_forward_path = "tcgen05" if use else "fp32"
+        return use
 
     # -- reference API ------------------------------------------------------------------------
     def weight_decay_step(self):

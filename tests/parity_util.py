@@ -15,9 +15,12 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
-def build_model(cfg, sd, device):
+def build_model(cfg, sd, device, tensor_cores="off"):
+    """``tensor_cores="off"``: these are the fp32 parity checks (rtol 1e-4); the bf16 tensor-core path has
+    its own tests and tolerance (tests/test_gpu_wide.py)."""
     m = models.NJODE(**cfg)
     m.load_state_dict(sd)
+    m.tensor_cores = tensor_cores
     return m.to(device)
 
 
