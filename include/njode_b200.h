@@ -146,20 +146,29 @@ int njode_backward(const njode_model_t* model, const njode_batch_t* batch, const
  * Serves the non-masked training / loss call of models whose MLPs are real dense contractions
  * (BASELINE config 5: d=16, H=256, 4x256 nets): input_size = output_size in {1,2,4,8,16}, hidden_size a
  * multiple of 16 up to 256, layer widths up to 256, segment units (batch->unit_kind == 1), no path
- * recording.  Same arguments and outputs as njode_forward; results agree with the fp32 path within the
- * bf16 tolerance stated in tests/test_gpu_wide.py.  The buffers in `saved` are written in the layout
- * njode_backward reads, so the fp32 backward can follow a tensor-core forward.
- *   njode_wide_supported      1 when the model qualifies (else 0, reason in njode_last_error())
- *   njode_wide_workspace_bytes  scratch the caller must provide
- *   saved->h_before is required whenever a loss is requested (the readout pass reads it). */
+ * recording.  Same arguments and outputs as njode_forward / njode_backward; results agree with the fp32
+ * path within the bf16 tolerance stated in tests/test_gpu_wide.py.
+ *   njode_wide_supported        1 when the model qualifies (else 0, reason in njode_last_error())
+ *   njode_wide_workspace_bytes  scratch for either call (not preserved between calls)
+ *   njode_wide_saved_bytes      size of the caller-owned blob that carries the forward's operand tiles
+ *                               (bf16 activation images per tile and chain step), h_before, Y, Y_bj and the
+ *                               encoder outputs to njode_wide_backward
+ * njode_wide_forward: `wide_saved` NULL = no gradient bookkeeping.  `saved` (may be NULL) optionally receives
+ * h_hist / h_before / y_after in the layout njode_backward reads, so the fp32 backward can follow a
+ * tensor-core forward. */
 int njode_wide_supported(const njode_model_t* model);
 int64_t njode_wide_workspace_bytes(const njode_model_t* model, const njode_batch_t* batch);
+int64_t njode_wide_saved_bytes(const njode_model_t* model, const njode_batch_t* batch);
 int njode_wide_forward(const njode_model_t* model, const njode_batch_t* batch, const float* params,
-                       float* hT, float* loss, const njode_saved_t* saved, void* workspace, void* stream);
-/* byte offsets {weight image, bias image, h_start, row_unit, row_loss} inside the workspace (tests) */
-int njode_wide_ws_offsets(const njode_model_t* model, const njode_batch_t* batch, int64_t* out5);
-/* elapsed ms of the encoder / Euler-chain / readout passes of the last njode_wide_forward (timing on) */
+                       float* hT, float* loss, const njode_saved_t* saved, void* wide_saved,
+                       void* workspace, void* stream);
+int njode_wide_backward(const njode_model_t* model, const njode_batch_t* batch, const float* params,
+                        void* wide_saved, const float* grad_loss, const float* grad_hT, float* grads,
+                        void* workspace, void* stream);
+/* elapsed ms of the encoder / Euler-chain / readout passes of the last njode_wide_forward, and of the
+ * chain passes / dW pass of the last njode_wide_backward (timing on) */
 int njode_wide_get_timing(float* enc_ms, float* ode_ms, float* ro_ms);
+int njode_wide_get_timing_bwd(float* chain_ms, float* dw_ms);
 
 /* Euler-Maruyama generators + Bernoulli observation mask (NJODE/stock_model.py:181-221, 288-335,
  * 356-375, 397-418 and NJODE/data_utils.py:73-81), one Philox-4x32-10 subsequence per global path id. */

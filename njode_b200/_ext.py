@@ -99,12 +99,16 @@ class Lib:
             d.njode_wide_supported.restype = C.c_int
             d.njode_wide_workspace_bytes.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT)]
             d.njode_wide_workspace_bytes.restype = C.c_int64
+            d.njode_wide_saved_bytes.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT)]
+            d.njode_wide_saved_bytes.restype = C.c_int64
             d.njode_wide_forward.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT), C.c_void_p, C.c_void_p,
-                                             C.c_void_p, C.POINTER(SavedT), C.c_void_p, C.c_void_p]
+                                             C.c_void_p, C.POINTER(SavedT), C.c_void_p, C.c_void_p, C.c_void_p]
             d.njode_wide_forward.restype = C.c_int
-            d.njode_wide_ws_offsets.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT), C.POINTER(C.c_int64)]
-            d.njode_wide_ws_offsets.restype = C.c_int
+            d.njode_wide_backward.argtypes = [C.POINTER(ModelT), C.POINTER(BatchT), C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            d.njode_wide_backward.restype = C.c_int
             d.njode_wide_get_timing.argtypes = [C.POINTER(C.c_float)] * 3
+            d.njode_wide_get_timing_bwd.argtypes = [C.POINTER(C.c_float)] * 2
 
     def check(self, rc, what):
         if rc != 0:
@@ -300,23 +304,43 @@ class Runner:
             ws = self._wws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=self.device)
         return ws
 
-    def forward_wide(self, model_t, pb, params, H, dout, get_loss, need_grad):
-        """same contract as ``forward`` on the tensor-core kernels (bf16 operands, fp32 accumulate / state)"""
+    def forward_wide(self, model_t, pb, params, H, dout, get_loss, need_grad, fp32_backward=False):
+        """same contract as ``forward`` on the tensor-core kernels (bf16 operands, fp32 accumulate / state).
+        ``saved`` is a ("wide", blob) pair for ``backward_wide``, or -- with ``fp32_backward`` -- the fp32
+        kernels' (h_hist, h_before, y_after) triple."""
         f32 = dict(dtype=torch.float32, device=self.device)
-        nbytes = self.lib.dll.njode_wide_workspace_bytes(C.byref(model_t), C.byref(pb.fwd))
+        dll = self.lib.dll
+        nbytes = dll.njode_wide_workspace_bytes(C.byref(model_t), C.byref(pb.fwd))
         if nbytes < 0:
             self.lib.check(int(nbytes), "njode_wide_workspace_bytes")
         ws = self._wide_workspace(nbytes)
         hT = torch.empty(pb.B, H, **f32)
         loss = torch.zeros((), **f32) if get_loss else None
-        h_hist = torch.empty(max(pb.sched.S, 1) * pb.B * H, **f32) if need_grad else None
-        h_before = torch.empty(max(pb.N, 1) * H, **f32) if (need_grad or get_loss) else None
-        y_after = torch.empty(max(pb.N, 1) * dout, **f32) if need_grad else None
-        saved_t = SavedT(_ptr(h_hist), _ptr(h_before), _ptr(y_after))
-        rc = self.lib.dll.njode_wide_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT),
-                                             _ptr(loss), C.byref(saved_t), _ptr(ws), self._stream())
+        saved_t, saved, blob = SavedT(), None, None
+        if need_grad and fp32_backward:
+            saved = (torch.empty(max(pb.sched.S, 1) * pb.B * H, **f32), torch.empty(max(pb.N, 1) * H, **f32),
+                     torch.empty(max(pb.N, 1) * dout, **f32))
+            saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved])
+        elif need_grad:
+            sbytes = dll.njode_wide_saved_bytes(C.byref(model_t), C.byref(pb.fwd))
+            if sbytes < 0:
+                self.lib.check(int(sbytes), "njode_wide_saved_bytes")
+            blob = torch.empty(int(sbytes), dtype=torch.uint8, device=self.device)
+            saved = ("wide", blob)
+        rc = dll.njode_wide_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT), _ptr(loss),
+                                    C.byref(saved_t), _ptr(blob), _ptr(ws), self._stream())
         self.lib.check(rc, "njode_wide_forward")
-        return hT, loss, None, None, ((h_hist, h_before, y_after) if need_grad else None)
+        return hT, loss, None, None, saved
+
+    def backward_wide(self, model_t, pb, params, blob, grad_loss, grad_hT):
+        dll = self.lib.dll
+        nbytes = dll.njode_wide_workspace_bytes(C.byref(model_t), C.byref(pb.fwd))
+        ws = self._wide_workspace(nbytes)
+        grads = torch.empty_like(params)
+        rc = dll.njode_wide_backward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(blob), _ptr(grad_loss),
+                                     _ptr(grad_hT), _ptr(grads), _ptr(ws), self._stream())
+        self.lib.check(rc, "njode_wide_backward")
+        return grads
 
     def forward(self, model_t, pb, params, H, dout, get_loss, need_grad):
         f32 = dict(dtype=torch.float32, device=self.device)

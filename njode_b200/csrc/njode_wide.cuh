@@ -63,6 +63,15 @@ struct WLayer {
     unsigned img_off;   // byte offset of K-block 0 inside the bf16 image (blocks are n16 * 128 B apart)
     int bias_off;       // float offset inside the bias image
     long long w_src, b_src;
+    // backward: acc[128 x k] = G_l[128 x n] . W_l[n x k]  (B operand = W_l^T, K-major over the outputs)
+    unsigned wt_off;    // byte offset of the transposed image (kt_blocks blocks of nt16 * 128 B)
+    int kt_blocks;      // K-blocks of the transposed GEMM = ceil(n16 / 64)
+    int kt_last_ksteps; // K-steps issued on the last of them
+    int nt, nt16;       // N of the transposed GEMM: main inputs of the layer (ODE layer 0: H), padded to 16
+    int act_off;        // byte offset of this layer's input image inside an activation record (forward spill)
+    int g_off;          // byte offset of this layer's output-gradient image inside a gradient record
+    int dw_slot0[2];    // first partial-accumulator slot of the (main, aux) dW items, -1 = no such item
+    int dw_J[2];        // CTAs sharing the records of the item
 };
 struct WNet { int n; WLayer l[NJODE_MAX_LINEAR]; };
 struct WCfg {
@@ -71,6 +80,9 @@ struct WCfg {
     float w, keep_scale;
     unsigned thr, seed_lo, seed_hi;
     unsigned img_bytes; int bias_floats;
+    unsigned wt_bytes;
+    int act_rec[3], g_rec[3];      // bytes per activation / gradient record of each net
+    int dw_items, dw_slots;
 };
 
 struct WArgs {
@@ -81,6 +93,19 @@ struct WArgs {
     int* row_unit;                 // [N] unit that starts at observation row r
     float *hT, *row_loss, *h_hist, *h_before, *y_after;
     int mode, n_tiles_loss, n_tiles, get_loss;
+    // training: operand tiles spilled for the backward pass (bf16 images, one record per tile and chain step)
+    float* y_before;               // [N, d] readout before the jump
+    unsigned char* act;            // activation records of the pass's net (forward: written, backward: read)
+    unsigned char* gsp;            // gradient records of the pass's net (backward: written; dW: read)
+    int* tile_base;                // [n_tiles + 1] first ODE record of every tile
+    int spill;
+    // backward
+    const unsigned char* wt;       // transposed bf16 weight image
+    float* g_before;               // [N, H]       dL/dh_before[row]
+    float* g_start;                // [n_units, H] dL/dh_start[u]
+    const float* grad_loss; const float* grad_hT;
+    float* dw_part;                // [dw_slots][256 x 256] partial dW accumulators, then [dw_slots][256] bias partials
+    int n_tiles_all;
 };
 
 // dynamic shared memory map (bytes from the 1024-aligned base)
@@ -89,7 +114,7 @@ constexpr int SM_W = SM_A + A_BLOCKS * A_BLOCK_BYTES;
 constexpr int SM_BIAS = SM_W + NSTAGE * STAGE_BYTES;                 // [8][256] fp32
 constexpr int SM_RES = SM_BIAS + NJODE_MAX_LINEAR * MAX_W * 4;       // [128][16] fp32 residual partial of column half 1
 constexpr int SM_YBJ = SM_RES + TILE_M * MAX_D * 4;                  // [128][16] fp32
-constexpr int SM_BAR = SM_YBJ + TILE_M * MAX_D * 4;                  // mbarriers
+constexpr int SM_BAR = SM_YBJ + TILE_M * MAX_D * 4;                  // mbarriers (SM_BAR is a multiple of 1024)
 constexpr int SM_TOTAL = SM_BAR + 128;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;                          // + alignment slack
 
@@ -123,6 +148,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -202,6 +233,12 @@ __device__ __forceinline__ Tile tile_of(const WCfg& c, const WArgs& a, int t) {
         T.reps = __ldg(dsc + 2) - __ldg(dsc + 1);
     } else T.reps = (a.mode == MODE_RO) ? 2 : 1;
     return T;
+}
+
+// record (spilled operand images) of chain step `rep` of tile t
+__device__ __forceinline__ size_t record_of(const WArgs& a, int t, int rep) {
+    if (a.mode == MODE_ODE) return (size_t)(__ldg(a.tile_base + t) + rep);
+    return a.mode == MODE_RO ? (size_t)(2 * t + rep) : (size_t)t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -336,7 +373,8 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
     float* ybj_s = reinterpret_cast<float*>(smem + SM_YBJ);
     const uint32_t bar0 = sbase + SM_BAR;
     const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * NSTAGE, bar_acc = bar0 + 16 * NSTAGE, bar_a = bar_acc + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 16);
+    const uint32_t bar_spill = bar_acc + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 24);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int netid = a.mode == MODE_ENC ? NJODE_NET_ENC : (a.mode == MODE_ODE ? NJODE_NET_ODE : NJODE_NET_RO);
     const WNet& net = c.net[netid];
@@ -345,6 +383,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_acc, 1);
         mbar_init(bar_a, EPI_THREADS);
+        mbar_init(bar_spill, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -413,12 +452,41 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                     }
             }
         }
+    } else if (warp == 2) {
+        // ===================== operand spill (training): every layer's A image -> its activation record =====================
+        if (lane == 0 && a.spill) {
+            uint32_t pa = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const Tile T = tile_of(c, a, t);
+                for (int rep = 0; rep < T.reps; ++rep) {
+                    unsigned char* rec = a.act + record_of(a, t, rep) * (size_t)c.act_rec[netid];
+                    for (int l = 0; l < net.n; ++l) {
+                        const WLayer& L = net.l[l];
+                        mbar_wait(bar_a, pa); pa ^= 1;
+                        for (int kb = 0; kb < L.kb_main; ++kb)
+                            bulk_s2g(rec + L.act_off + (size_t)kb * A_BLOCK_BYTES, a_base + (uint32_t)kb * A_BLOCK_BYTES, A_BLOCK_BYTES);
+                        if (L.has_aux)
+                            bulk_s2g(rec + L.act_off + (size_t)L.kb_main * A_BLOCK_BYTES, a_base + AUX_BLOCK * A_BLOCK_BYTES, A_BLOCK_BYTES);
+                        bulk_commit();
+                        bulk_wait_read();                 // the image has been read: the epilogue may overwrite it
+                        mbar_arrive(bar_spill);
+                    }
+                }
+            }
+            bulk_wait_all();
+        }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue warps =====================
         const int q = warp & 3, hf = (warp - EPI_WARP0) >> 2;
         const int r = q * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t pf = 0;
+        uint32_t pf = 0, ps = 0;
+        int n_arr = 0, n_spw = 0;          // a_ready arrivals made / spill completions consumed
+        // the A image of an arrival may be overwritten only after the spill warp has read it
+        auto spill_sync = [&]() {
+            if (a.spill)
+                while (n_spw < n_arr) { mbar_wait(bar_spill, ps); ps ^= 1; ++n_spw; }
+        };
         const int H = c.H, d = c.d;
         const int hch = (H + 31) >> 5, hper = (hch + 1) >> 1;
         const int hc_lo = hf * hper, hc_hi = min(hch, hc_lo + hper);              // this thread's chunks of an H-wide row
@@ -441,6 +509,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
             float res[MAX_D];
             unsigned rk = 0;
             // ---------------- prologue ----------------
+            spill_sync();
             if (a.mode == MODE_ENC) {
 #pragma unroll
                 for (int j = 0; j < MAX_D; ++j)
@@ -498,7 +567,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
             if (T.reps == 0) continue;
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(bar_a);
+            mbar_arrive(bar_a); ++n_arr;
             // ---------------- layers ----------------
             for (int rep = 0; rep < T.reps; ++rep) {
                 for (int l = 0; l < net.n; ++l) {
@@ -506,6 +575,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                     const bool last = (l == net.n - 1);
                     mbar_wait(bar_acc, pf); pf ^= 1;
                     tc_fence_after();
+                    spill_sync();
                     const int nch = (L.n16 + 31) >> 5, per = (nch + 1) >> 1;
                     const int c_lo = hf * per, c_hi = min(nch, c_lo + per);
                     if (!last) {
@@ -571,7 +641,10 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                                 y[j] = __uint_as_float(v[j]) + bias_s[l * MAX_W + j] + rmul * (res[j] + res_s[r * MAX_D + j]);
                             if (rep == 0) {
 #pragma unroll
-                                for (int j = 0; j < MAX_D; ++j) ybj_s[r * MAX_D + j] = y[j];
+                                for (int j = 0; j < MAX_D; ++j) {
+                                    ybj_s[r * MAX_D + j] = y[j];
+                                    if (a.y_before && valid && row >= 0 && j < d) a.y_before[(size_t)row * d + j] = y[j];
+                                }
                             } else if (valid && row >= 0) {
                                 float sa = 0.f, sb = 0.f;
 #pragma unroll
@@ -620,7 +693,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                     if (!tile_done) {
                         tc_fence_before();
                         fence_proxy_async();
-                        mbar_arrive(bar_a);
+                        mbar_arrive(bar_a); ++n_arr;
                     }
                 }
             }
@@ -633,6 +706,485 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
+
+// ================================================================================================
+// backward chain: per tile and chain step, G_{l-1} = (G_l . W_l) * act'(A_l) for l = L-1 .. 0, with the
+// forward's spilled activation images A_l supplying act' and every G_l image spilled for the dW pass.
+//   BWD_RO  : two chains per loss tile (Y_bj, Y): G_{L-1} = dLoss/dY..., ends in g_before[row] / g_start[unit]
+//   BWD_ODE : reverse Euler steps, adjoint dL/dh in TMEM (fp32): G_{L-1} = dt * adjoint,
+//             adjoint += (G_0 . W_0)[tanh(h) columns] * (1 - tanh(h)^2); ends in g_start[unit]
+//   BWD_ENC : G_{L-1} = g_start[unit]; no input gradient (layer 0 only spills G_0)
+// Same warp roles, barriers and operand layouts as the forward kernel; the B operand is the transposed weight
+// image (W_l^T, K-major over the layer's outputs).
+// ================================================================================================
+__device__ __forceinline__ float act_factor(uint32_t bits16, int act, int drop, float ks, float inv_ks) {
+    const float av = __uint_as_float(bits16 << 16);
+    if (act == NJODE_ACT_TANH) {
+        if (drop) {
+            if (bits16 == 0x8000u) return 0.f;             // dropped activations were stored as -0
+            const float t = av * inv_ks;
+            return ks * (1.f - t * t);
+        }
+        return 1.f - av * av;
+    }
+    if (act == NJODE_ACT_RELU) return av > 0.f ? (drop ? ks : 1.f) : 0.f;
+    return 1.f;
+}
+// my row's 32 columns [c0, c0+32) of a spilled image (global memory), as 16 packed bf16 pairs
+__device__ __forceinline__ void load_img_chunk(const unsigned char* img, int r, int c0, uint32_t* p) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int col = c0 + 8 * q;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)(col >> 6) * A_BLOCK_BYTES + (size_t)r * 128
+                                                              + ((((col & 63) >> 3) ^ (r & 7)) << 4)));
+        p[4 * q] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w;
+    }
+}
+// 32 fp32 gradients -> bf16 -> G image columns [c0, c0+32); columns >= n are written as 0
+__device__ __forceinline__ void store_g_chunk(uint32_t a_base, int r, int c0, int n, const float* g) {
+    uint32_t p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        p[j] = pack_bf16((c0 + 2 * j < n) ? g[2 * j] : 0.f, (c0 + 2 * j + 1 < n) ? g[2 * j + 1] : 0.f);
+    store_a_chunk(a_base, r, c0, p);
+}
+
+__device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsigned char* smem_raw) {
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t a_base = sbase + SM_A, w_base = sbase + SM_W;
+    const uint32_t bar0 = sbase + SM_BAR;
+    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * NSTAGE, bar_acc = bar0 + 16 * NSTAGE, bar_a = bar_acc + 8;
+    const uint32_t bar_spill = bar_acc + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 24);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int netid = a.mode == MODE_ENC ? NJODE_NET_ENC : (a.mode == MODE_ODE ? NJODE_NET_ODE : NJODE_NET_RO);
+    const WNet& net = c.net[netid];
+    const int l_min = a.mode == MODE_ENC ? 1 : 0;          // the encoder input needs no gradient
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        mbar_init(bar_a, EPI_THREADS);
+        mbar_init(bar_spill, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < A_BLOCKS * A_BLOCK_BYTES / 16; i += NUM_THREADS)
+        st_shared_v4(a_base + 16u * i, 0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const Tile T = tile_of(c, a, t);
+                for (int rep = 0; rep < T.reps; ++rep)
+                    for (int l = net.n - 1; l >= l_min; --l) {
+                        const WLayer& L = net.l[l];
+                        const uint32_t bytes = (uint32_t)L.nt16 * 128u;
+                        for (int kb = 0; kb < L.kt_blocks; ++kb) {
+                            mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+                            mbar_expect_tx(bar_full + 8 * stage, bytes);
+                            bulk_g2s(w_base + stage * STAGE_BYTES, a.wt + L.wt_off + (size_t)kb * bytes, bytes, bar_full + 8 * stage);
+                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0, pa = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const Tile T = tile_of(c, a, t);
+                for (int rep = 0; rep < T.reps; ++rep)
+                    for (int l = net.n - 1; l >= 0; --l) {
+                        const WLayer& L = net.l[l];
+                        mbar_wait(bar_a, pa); pa ^= 1;               // G_l written, accumulator drained
+                        if (l < l_min) continue;                     // spilled only
+                        tc_fence_after();
+                        const uint32_t idesc = make_idesc(L.nt16);
+                        for (int kb = 0; kb < L.kt_blocks; ++kb) {
+                            const int ksteps = (kb == L.kt_blocks - 1) ? L.kt_last_ksteps : 4;
+                            mbar_wait(bar_full + 8 * stage, ph);
+                            tc_fence_after();
+                            const uint32_t ab = a_base + (uint32_t)kb * A_BLOCK_BYTES;
+                            const uint32_t wb = w_base + (uint32_t)stage * STAGE_BYTES;
+                            for (int k = 0; k < ksteps; ++k)
+                                tc_mma(tmem, make_desc(ab + 32u * k), make_desc(wb + 32u * k), idesc, (kb | k) ? 1u : 0u);
+                            tc_commit(bar_empty + 8 * stage);
+                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                        }
+                        tc_commit(bar_acc);
+                    }
+            }
+        }
+    } else if (warp == 2) {
+        // every G_l image -> its gradient record (read again by the dW pass)
+        if (lane == 0) {
+            uint32_t pa = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const Tile T = tile_of(c, a, t);
+                for (int rep = 0; rep < T.reps; ++rep) {
+                    const int step = a.mode == MODE_ODE ? T.reps - 1 - rep : rep;
+                    unsigned char* rec = a.gsp + record_of(a, t, step) * (size_t)c.g_rec[netid];
+                    for (int l = net.n - 1; l >= 0; --l) {
+                        const WLayer& L = net.l[l];
+                        mbar_wait(bar_a, pa); pa ^= 1;
+                        for (int kb = 0; kb < L.kt_blocks; ++kb)
+                            bulk_s2g(rec + L.g_off + (size_t)kb * A_BLOCK_BYTES, a_base + (uint32_t)kb * A_BLOCK_BYTES, A_BLOCK_BYTES);
+                        bulk_commit();
+                        bulk_wait_read();
+                        mbar_arrive(bar_spill);
+                    }
+                }
+            }
+            bulk_wait_all();
+        }
+    } else if (warp >= EPI_WARP0) {
+        const int q = warp & 3, hf = (warp - EPI_WARP0) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t pf = 0, ps = 0;
+        int n_arr = 0, n_spw = 0;
+        auto spill_sync = [&]() { while (n_spw < n_arr) { mbar_wait(bar_spill, ps); ps ^= 1; ++n_spw; } };
+        auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(bar_a); ++n_arr; };
+        const int H = c.H, d = c.d;
+        const int hch = (H + 31) >> 5, hper = (hch + 1) >> 1;
+        const int hc_lo = hf * hper, hc_hi = min(hch, hc_lo + hper);
+        const float ks = c.keep_scale, inv_ks = c.keep_scale > 0.f ? 1.f / c.keep_scale : 0.f;
+        const float gl = a.grad_loss ? __ldg(a.grad_loss) / (float)a.b.batch_size_norm : 0.f;
+        const int Ln = net.n;
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+            const Tile T = tile_of(c, a, t);
+            const int u = T.u0 + r;
+            const bool valid = u < T.u1;
+            int path = 0, s0 = 0, len = 0, row = -1, flag = 0, sr = -1;
+            if (valid) {
+                const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                path = __ldg(dsc); s0 = __ldg(dsc + 1); len = __ldg(dsc + 2) - s0;
+                const int c0_ = __ldg(dsc + 3), c1_ = __ldg(dsc + 4), sc = __ldg(dsc + 5);
+                row = c1_ > c0_ ? __ldg(a.b.path_rows + c0_) : -1;
+                flag = (sc & NJODE_UNIT_WRITES_HT) ? 1 : 0;
+                sr = (sc & ~NJODE_UNIT_WRITES_HT) - 1;
+            }
+            float gy[MAX_D];                     // BWD_RO: dL/dy of the current chain (both halves of a row hold it)
+#pragma unroll
+            for (int j = 0; j < MAX_D; ++j) gy[j] = 0.f;
+            if (a.mode == MODE_ODE) {
+                // adjoint at the end of the unit: dL/dh_before[row] (loss units) or the caller's gradient into hT
+                const float* src = nullptr;
+                if (valid && row >= 0) src = a.g_before + (size_t)row * H;
+                else if (valid && flag && a.grad_hT) src = a.grad_hT + (size_t)path * H;
+                for (int ch = hc_lo; ch < hc_hi; ++ch) {
+                    float g[32];
+                    load_row_chunk(src, ch * 32, H, g);
+                    tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(g));
+                }
+                tmem_wait_st();
+            }
+            for (int rep = 0; rep < T.reps; ++rep) {
+                const int step = a.mode == MODE_ODE ? T.reps - 1 - rep : rep;
+                const unsigned char* arec = a.act + record_of(a, t, step) * (size_t)c.act_rec[netid];
+                // ---------------- G_{L-1}: gradient of the chain's output ----------------
+                spill_sync();
+                if (a.mode == MODE_ODE) {
+                    const bool active = valid && step < len;
+                    const float dt = active ? __ldg(a.b.step_dt + s0 + step) : 0.f;
+                    for (int ch = hc_lo; ch < hc_hi; ++ch) {
+                        float g[32];
+                        tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(g));
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) g[j] *= dt;                      // h += dt * f  (0 for finished / padding rows)
+                        store_g_chunk(a_base, r, ch * 32, H, g);
+                    }
+                } else if (a.mode == MODE_ENC) {
+                    const float* src = valid ? a.g_start + (size_t)u * H : nullptr;
+                    for (int ch = hc_lo; ch < hc_hi; ++ch) {
+                        float g[32];
+                        load_row_chunk(src, ch * 32, H, g);
+                        store_g_chunk(a_base, r, ch * 32, H, g);
+                    }
+                } else {
+                    // loss row (compute_loss / compute_loss_2, NJODE/models.py:71-126): chain 0 = Y_bj, chain 1 = Y
+                    if (valid && row >= 0) {
+                        float sa = 0.f, sb = 0.f, x[MAX_D], y[MAX_D], yb[MAX_D];
+#pragma unroll
+                        for (int j = 0; j < MAX_D; ++j) {
+                            x[j] = y[j] = yb[j] = 0.f;
+                            if (j < d) {
+                                x[j] = __ldg(a.b.X + (size_t)row * d + j); y[j] = a.y_after[(size_t)row * d + j]; yb[j] = a.y_before[(size_t)row * d + j];
+                                const float da = x[j] - y[j], db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb[j] - y[j]) : (yb[j] - x[j]);
+                                sa = fmaf(da, da, sa); sb = fmaf(db, db, sb);
+                            }
+                        }
+                        const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+                        const bool stdl = c.loss_kind == NJODE_LOSS_STANDARD;
+                        const float wa = stdl ? 2.f * c.w : c.w, wb = stdl ? 2.f * (1.f - c.w) : (1.f - c.w);
+                        const float sm = wa * ra + wb * rb;
+                        const float k0 = gl * 2.f * sm / __ldg(a.b.n_obs_ot + path);
+#pragma unroll
+                        for (int j = 0; j < MAX_D; ++j) {
+                            if (j < d) {
+                                if (rep == 0) gy[j] = k0 * wb * (stdl ? (yb[j] - y[j]) : (yb[j] - x[j])) / rb;
+                                else gy[j] = k0 * (wa * (y[j] - x[j]) / ra + (stdl ? wb * (y[j] - yb[j]) / rb : 0.f));
+                            } else gy[j] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < MAX_D; ++j) gy[j] = 0.f;
+                    }
+                    if (hf == 0) {
+                        uint32_t p[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) p[j] = pack_bf16(gy[2 * j], gy[2 * j + 1]);
+                        const uint32_t rowa = a_base + (uint32_t)r * 128u;
+                        st_shared_v4(rowa + ((uint32_t)(0 ^ (r & 7)) << 4), p[0], p[1], p[2], p[3]);
+                        st_shared_v4(rowa + ((uint32_t)(1 ^ (r & 7)) << 4), p[4], p[5], p[6], p[7]);
+                    }
+                }
+                arrive_a();
+                // ---------------- layers, last to first ----------------
+                for (int l = Ln - 1; l >= 0; --l) {
+                    const WLayer& L = net.l[l];
+                    if (l < l_min) break;
+                    // this layer's input image A_l (forward spill): prefetched before waiting for the MMAs
+                    const int ncols = L.nt;                                   // gradient width = main inputs of layer l
+                    const int nch = (L.nt16 + 31) >> 5, per = (nch + 1) >> 1;
+                    const int c_lo = hf * per, c_hi = min(nch, c_lo + per);
+                    uint32_t av[4][16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (c_lo + k < c_hi) load_img_chunk(arec + L.act_off, r, (c_lo + k) * 32, av[k]);
+                    mbar_wait(bar_acc, pf); pf ^= 1;
+                    tc_fence_after();
+                    spill_sync();
+                    const WLayer& Lp = net.l[l > 0 ? l - 1 : 0];             // layer whose activation A_l is
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int ch = c_lo + k;
+                        if (ch < c_hi) {
+                            uint32_t v[32];
+                            float g[32];
+                            tmem_ld32(tlane + ch * 32, v);
+                            if (l == 0 && a.mode == MODE_ODE) tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(g));
+                            tmem_wait_ld();
+                            if (l > 0) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const uint32_t b16 = (j & 1) ? (av[k][j >> 1] >> 16) : (av[k][j >> 1] & 0xFFFFu);
+                                    g[j] = __uint_as_float(v[j]) * act_factor(b16, Lp.act, Lp.drop, ks, inv_ks);
+                                }
+                                store_g_chunk(a_base, r, ch * 32, ncols, g);
+                            } else {
+                                // input of the net = tanh(h): d/dh = 1 - tanh(h)^2, tanh(h) from the spilled A_0
+                                float gi[32];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const uint32_t b16 = (j & 1) ? (av[k][j >> 1] >> 16) : (av[k][j >> 1] & 0xFFFFu);
+                                    const float th = __uint_as_float(b16 << 16);
+                                    gi[j] = __uint_as_float(v[j]) * (1.f - th * th);
+                                }
+                                if (a.mode == MODE_ODE) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) g[j] += gi[j];
+                                    tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(g));
+                                } else {
+                                    // readout residual (FFNN.forward, models.py:268-276): y[j] += mean_k h[k d + j]
+                                    if (c.residual) {
+                                        const float rmul = 1.f / (float)(H / d);
+                                        float ge[MAX_D];
+                                        expand_x(gy, ge, d);
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) gi[j] += rmul * ge[j & 15];
+                                    }
+                                    if (valid && row >= 0) {
+                                        float* dst = rep == 0 ? a.g_before + (size_t)row * H : a.g_start + (size_t)a.row_unit[row] * H;
+                                        store_row_chunk(dst, ch * 32, H, gi);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (l == 0 && a.mode == MODE_ODE) tmem_wait_st();
+                    if (l > 0) arrive_a();          // G_{l-1} is the next GEMM's operand (or, for l-1 < l_min, only spilled)
+                }
+            }
+            if (a.mode == MODE_ODE) {
+                // dL/dh_start[u] = adjoint at the start of the unit (+ the readout-after-jump part written by BWD_RO);
+                // every lane executes the (warp-collective) TMEM load
+                for (int ch = hc_lo; ch < hc_hi; ++ch) {
+                    float g[32], o[32];
+                    tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(g));
+                    tmem_wait_ld();
+                    if (valid) {
+                        if (sr >= 0) {
+                            load_row_chunk(a.g_start + (size_t)u * H, ch * 32, H, o);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) g[j] += o[j];
+                        }
+                        store_row_chunk(a.g_start + (size_t)u * H, ch * 32, H, g);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
+// ================================================================================================
+// dW pass: dW_l[n x k] = sum over records of G_l^T[n x 128] . A_l[128 x k], db_l = column sums of G_l.
+// The spilled images are [64-column block][128 rows x 128 B] SWIZZLE_128B tiles; read as MN-major operands
+// (64 contiguous elements of the M / N dimension per 128-byte row, K = the 128 units of the tile) they feed
+// tcgen05.mma directly: A operand = G_l (M = layer outputs, two M = 128 halves in TMEM columns [0,256) and
+// [256,512)), B operand = A_l (N = layer inputs).  One CTA owns one (net, layer, main|aux part) item and a
+// contiguous share of the net's records; half records (64 units = 4 K-steps) stream through a 3-stage ring.
+// ================================================================================================
+struct DwItem { int net, layer, part, j, J, slot; };
+constexpr int DW_STAGE_BYTES = 65536;             // [4 G half-blocks][4 A half-blocks] of 8 KB
+constexpr int DW_HALF_BLOCK = 8192;
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | ((uint32_t)(DW_HALF_BLOCK >> 4) << 16);   // LBO: next 64 elements of M / N
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);                                // SBO: next 8 units of K
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+__device__ __forceinline__ void wide_dw_cta(const WCfg& c, const WArgs& a, const DwItem& item, unsigned char* smem_raw) {
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + SM_BAR;
+    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * NSTAGE, bar_acc = bar0 + 16 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 24);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const DwItem it = item;
+    const WLayer& L = c.net[it.net].l[it.layer];
+    const int R = it.net == NJODE_NET_ENC ? a.n_tiles_all : (it.net == NJODE_NET_RO ? 2 * a.n_tiles_loss : __ldg(a.tile_base + a.n_tiles_all));
+    const int r0 = (int)((long long)R * it.j / it.J), r1 = (int)((long long)R * (it.j + 1) / it.J);
+    const int nhalf = 2 * (r1 - r0);
+    const bool aux = it.part == 1;
+    const int nb = aux ? 1 : L.kb_main;                       // B blocks
+    const int b0 = aux ? L.kb_main : 0;                       // first B block inside the activation image
+    const int Nn = aux ? 16 * L.aux_ksteps : L.nt16;
+    const int Mh = L.n16 > 128 ? 2 : 1;
+    const bool do_bias = (aux ? L.kb_main == 0 : true) && L.b_src >= 0;
+    const unsigned char* act = a.act;                         // records of it.net (set by the host per launch)
+    const unsigned char* gsp = a.gsp;
+    const size_t arec = (size_t)c.act_rec[it.net], grec = (size_t)c.g_rec[it.net];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + EPI_THREADS / 32); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < NSTAGE * DW_STAGE_BYTES / 16; i += NUM_THREADS)
+        st_shared_v4(sbase + 16u * i, 0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (int hidx = 0; hidx < nhalf; ++hidx) {
+                const int rec = r0 + (hidx >> 1), h = hidx & 1;
+                const unsigned char* gi = gsp + (size_t)rec * grec + L.g_off + (size_t)h * DW_HALF_BLOCK;
+                const unsigned char* ai = act + (size_t)rec * arec + L.act_off + (size_t)b0 * A_BLOCK_BYTES + (size_t)h * DW_HALF_BLOCK;
+                const uint32_t sb = sbase + (uint32_t)stage * DW_STAGE_BYTES;
+                mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+                mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(L.kt_blocks + nb) * DW_HALF_BLOCK);
+                for (int kb = 0; kb < L.kt_blocks; ++kb)
+                    bulk_g2s(sb + kb * DW_HALF_BLOCK, gi + (size_t)kb * A_BLOCK_BYTES, DW_HALF_BLOCK, bar_full + 8 * stage);
+                for (int b = 0; b < nb; ++b)
+                    bulk_g2s(sb + 4 * DW_HALF_BLOCK + b * DW_HALF_BLOCK, ai + (size_t)b * A_BLOCK_BYTES, DW_HALF_BLOCK, bar_full + 8 * stage);
+                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            const uint32_t idesc = make_idesc(Nn) | (1u << 15) | (1u << 16);        // both operands MN-major
+            for (int hidx = 0; hidx < nhalf; ++hidx) {
+                const uint32_t sb = sbase + (uint32_t)stage * DW_STAGE_BYTES;
+                mbar_wait(bar_full + 8 * stage, ph);
+                tc_fence_after();
+                for (int mh = 0; mh < Mh; ++mh)
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma(tmem + (uint32_t)mh * 256u, make_desc_mn(sb + (uint32_t)mh * 2 * DW_HALF_BLOCK + 2048u * k),
+                               make_desc_mn(sb + 4 * DW_HALF_BLOCK + 2048u * k), idesc, (hidx | k) ? 1u : 0u);
+                tc_commit(bar_empty + 8 * stage);
+                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+            }
+            tc_commit(bar_acc);
+        }
+    } else if (warp >= EPI_WARP0) {
+        const int q = warp & 3, hf = (warp - EPI_WARP0) >> 2;
+        const int o = threadIdx.x - EPI_WARP0 * 32;               // bias: this thread's output column
+        float bsum = 0.f;
+        {
+            int stage = 0; uint32_t ph = 0;
+            for (int hidx = 0; hidx < nhalf; ++hidx) {
+                mbar_wait(bar_full + 8 * stage, ph);
+                if (do_bias && o < L.n16) {
+                    const unsigned char* g = smem + (size_t)stage * DW_STAGE_BYTES + (size_t)(o >> 6) * DW_HALF_BLOCK + (o & 7) * 2;
+                    const int cch = (o & 63) >> 3;
+#pragma unroll 8
+                    for (int row = 0; row < 64; ++row) {
+                        const unsigned short b = *reinterpret_cast<const unsigned short*>(g + row * 128 + ((cch ^ (row & 7)) << 4));
+                        bsum += __uint_as_float((uint32_t)b << 16);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+            }
+        }
+        float* part = a.dw_part + (size_t)it.slot * (256 * 256);
+        float* bpart = a.dw_part + (size_t)c.dw_slots * (256 * 256) + (size_t)it.slot * 256;
+        bpart[o] = bsum;
+        if (nhalf > 0) { mbar_wait(bar_acc, 0); tc_fence_after(); }
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        const int nch = (Nn + 31) >> 5, per = (nch + 1) >> 1;
+        const int c_lo = hf * per, c_hi = min(nch, c_lo + per);
+        for (int mh = 0; mh < Mh; ++mh)
+            for (int ch = c_lo; ch < c_hi; ++ch) {
+                float v[32];
+                if (nhalf > 0) { tmem_ld32(tlane + (uint32_t)mh * 256u + ch * 32, reinterpret_cast<uint32_t*>(v)); tmem_wait_ld(); }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
+                store_row_chunk(part + (size_t)(mh * 128 + q * 32 + lane) * 256, ch * 32, 256, v);
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 #endif  // !NJODE_HOST_SIM
 
 }  // namespace njw

@@ -168,8 +168,11 @@ class _NJODEFunction(torch.autograd.Function):
     def forward(ctx, module, runner, pb, model_t, get_loss, need_grad, *params):
         flat = module._flat
         H, dout = module.hidden_size, module.output_size
-        fwd = runner.forward_wide if module._use_tensor_cores(runner, pb, model_t) else runner.forward
-        hT, loss, path_h, path_y, saved = fwd(model_t, pb, flat, H, dout, get_loss, need_grad)
+        if module._use_tensor_cores(runner, pb, model_t):
+            hT, loss, path_h, path_y, saved = runner.forward_wide(
+                model_t, pb, flat, H, dout, get_loss, need_grad, fp32_backward=module.tensor_core_backward == "fp32")
+        else:
+            hT, loss, path_h, path_y, saved = runner.forward(model_t, pb, flat, H, dout, get_loss, need_grad)
         ctx.module, ctx.runner, ctx.pb, ctx.model_t, ctx.saved = module, runner, pb, model_t, saved
         ctx.flat_version = module._flat_version
         ctx.mark_non_differentiable(*[t for t in (path_h, path_y) if t is not None])
@@ -189,7 +192,10 @@ class _NJODEFunction(torch.autograd.Function):
         g_loss = torch.zeros((), device=dev) if g_loss is None else g_loss.to(dev, torch.float32).contiguous()
         if g_hT is not None:
             g_hT = g_hT.to(dev, torch.float32).contiguous()
-        grads = runner.backward(ctx.model_t, ctx.pb, flat, ctx.saved, g_loss, g_hT)
+        if isinstance(ctx.saved[0], str):          # ("wide", blob): operand tiles of the tensor-core forward
+            grads = runner.backward_wide(ctx.model_t, ctx.pb, flat, ctx.saved[1], g_loss, g_hT)
+        else:
+            grads = runner.backward(ctx.model_t, ctx.pb, flat, ctx.saved, g_loss, g_hT)
         if module._grad_sync is not None:
             module._grad_sync(grads)
         views = tuple(grads[o:o + n].view(s) for (o, n, s) in module._flat_layout)
@@ -242,6 +248,9 @@ class NJODE(torch.nn.Module):
         # non-masked loss/training call when every MLP is a real dense contraction (all hidden widths and
         # hidden_size >= 128); "off": always the fp32 FMA kernels; "on": whenever the model qualifies.
         self.tensor_cores = os.environ.get("NJODE_TENSOR_CORES", "auto")
+        # backward of a tensor-core forward: "tcgen05" (chain + dW kernels on the spilled operand tiles) or
+        # "fp32" (the FMA backward kernels re-reading h_hist)
+        self.tensor_core_backward = os.environ.get("NJODE_TENSOR_CORE_BACKWARD", "tcgen05")
         self.last_forward_path = None
 
     def _use_tensor_cores(self, runner, pb, model_t):

@@ -1,6 +1,7 @@
 #!/bin/bash
-# usage: bash scripts/gpu_wide.sh case1 case2 ...
+# usage: bash scripts/gpu_wide.sh case1 case2 ...   (full logs in gpurun_out/wide_<case>.log)
 mkdir -p gpurun_out
 for c in "$@"; do
-  echo "=== $c"; timeout 70 python scripts/wide_debug.py $c 2>&1 | tail -25; echo "rc=$?"
+  echo "=== $c"; timeout 70 python scripts/wide_debug.py $c > gpurun_out/wide_$c.log 2>&1; echo "rc=$?"
+  grep -v -E "^frame|^$" gpurun_out/wide_$c.log | tail -45
 done

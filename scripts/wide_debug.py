@@ -18,6 +18,7 @@ CASES = {
     "cfg5": (16, 256, 256, 4, 300, 20, 0.2, 0.0),
     "cfg5_drop": (16, 256, 256, 4, 300, 20, 0.2, 0.1),
     "cfg5_big": (16, 256, 256, 4, 4096, 100, 0.1, 0.1),
+    "cfg5_huge": (16, 256, 256, 4, 16384, 200, 0.1, 0.1),
 }
 
 
@@ -44,7 +45,7 @@ def main(name):
     hT1, loss1, _, _, s1 = r.forward(mt, pb, m._flat, H, d, True, True)
     torch.cuda.synchronize()
     print("fp32 loss", float(loss1), flush=True)
-    hT2, loss2, _, _, s2 = r.forward_wide(mt, pb, m._flat, H, d, True, True)
+    hT2, loss2, _, _, s2 = r.forward_wide(mt, pb, m._flat, H, d, True, True, fp32_backward=True)
     torch.cuda.synchronize()
     print("tc   loss", float(loss2), "rel", abs(float(loss2) - float(loss1)) / abs(float(loss1)), flush=True)
     S = pb.sched.S
@@ -60,7 +61,19 @@ def main(name):
         print("worst at step", s_, "path", b_, "col", c_, float(hh2[s_, b_, c_]), float(hh1[s_, b_, c_]))
         print("err by column block of 8 (step 0):", [round(float(e[0][:, i:i + 8].max()), 4) for i in range(0, H, 8)][:32])
         print("err by path (step 0):", [round(float(e[0][i].max()), 4) for i in range(min(B, 16))])
-    if name.endswith("big"):
+    # gradients: tcgen05 backward vs the fp32 backward (both on this batch)
+    gl = torch.ones((), device="cuda")
+    g1 = r.backward(mt, pb, m._flat, s1, gl, None)
+    hT3, loss3, _, _, s3 = r.forward_wide(mt, pb, m._flat, H, d, True, True)
+    torch.cuda.synchronize()
+    print("tc(train) loss", float(loss3), flush=True)
+    g2 = r.backward_wide(mt, pb, m._flat, s3[1], gl, None)
+    torch.cuda.synchronize()
+    print("grad rel (all)", rel(g2, g1), "nan", int(torch.isnan(g2).sum()), flush=True)
+    for (nme, p_), (o, n_, shp) in zip(m.named_parameters(), m._flat_layout):
+        a_, b_ = g2[o:o + n_], g1[o:o + n_]
+        print("   %-28s rel %.4f  max|ref| %.3e" % (nme, rel(a_, b_), float(b_.abs().max())))
+    if name.endswith("big") or name.endswith("huge"):
         import ctypes as C
         r.lib.dll.njode_set_timing(1)
         for _ in range(3):
@@ -70,12 +83,25 @@ def main(name):
         r.lib.dll.njode_wide_get_timing(C.byref(a), C.byref(b_), C.byref(c_))
         F_ode = 2 * ((d + H + 2) * W + (L - 1) * W * W + W * H)
         print("timing ms: enc %.3f ode %.3f ro %.3f ; ode TFLOP/s %.1f" % (a.value, b_.value, c_.value, B * S * F_ode / (b_.value * 1e-3) / 1e12))
+        for _ in range(2):
+            hT3, loss3, _, _, s3 = r.forward_wide(mt, pb, m._flat, H, d, True, True)
+            g2 = r.backward_wide(mt, pb, m._flat, s3[1], gl, None)
+        torch.cuda.synchronize()
+        r.lib.dll.njode_wide_get_timing(C.byref(a), C.byref(b_), C.byref(c_))
+        ch, dw = C.c_float(), C.c_float()
+        r.lib.dll.njode_wide_get_timing_bwd(C.byref(ch), C.byref(dw))
+        tot = a.value + b_.value + c_.value + ch.value + dw.value
+        print("train: fwd enc %.3f ode %.3f ro %.3f | bwd chains %.3f dW %.3f ms ; total %.3f ms = %.1f M path-steps/s, %.1f TFLOP/s (3x fwd flops)" % (
+            a.value, b_.value, c_.value, ch.value, dw.value, tot, B * S / tot / 1e3, 3 * B * S * F_ode / (tot * 1e-3) / 1e12))
         f, bb = C.c_float(), C.c_float()
         for _ in range(2):
             r.forward(mt, pb, m._flat, H, d, True, True)
         torch.cuda.synchronize()
         r.lib.dll.njode_get_timing(C.byref(f), C.byref(bb))
-        print("fp32 fwd kernel ms %.3f" % f.value)
+        r.backward(mt, pb, m._flat, s1, gl, None)
+        torch.cuda.synchronize()
+        r.lib.dll.njode_get_timing(C.byref(f), C.byref(bb))
+        print("fp32 fwd kernel ms %.3f bwd kernel ms %.3f" % (f.value, bb.value))
 
 
 if __name__ == "__main__":
