@@ -48,12 +48,13 @@ WORKLOADS = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable demo batch
     "bs_demo_200": dict(sde="BlackScholes", paths=200, steps=100, d=1, H=10, width=50, layers=2,
                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=200),
-    # BASELINE.json configs[4] architecture on a batch that fits the generic fp32 kernels
+    # BASELINE.json configs[4]: scaled BlackScholes, d=16, H=256, 4x256 nets, 1000 Euler steps, paths generated
+    # on the device (Philox Euler-Maruyama + device collate), tcgen05 tensor-core kernels (bf16 operands)
     "bs_scaled_d16_h256": dict(sde="BlackScholes", paths=8192, steps=1000, d=16, H=256, width=256,
                                layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128,
-                               cpu_sample_steps=100),
-    "bs_scaled_d16_h256_small": dict(sde="BlackScholes", paths=2048, steps=100, d=16, H=256, width=256,
-                                     layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128),
+                               cpu_sample_steps=100, device_data=True),
+    "bs_scaled_d16_h256_small": dict(sde="BlackScholes", paths=4096, steps=100, d=16, H=256, width=256,
+                                     layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128, device_data=True),
     # BASELINE.json configs[2] (i): combined-dataset nets (2x100 tanh), batch 5000
     "bs_2x100_5k": dict(sde="BlackScholes", paths=5000, steps=100, d=1, H=10, width=100, layers=2,
                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
@@ -113,6 +114,20 @@ def synth_batch(wl, seed, first_path, n_paths):
     nb_obs = obs[:, 1:].sum(axis=1)
     b = data_utils.collate_paths(paths, obs, nb_obs, dt)
     return b, dt
+
+
+def synth_batch_device(wl, seed, first_path, n_paths, dev):
+    """paths + observation mask generated on the device (njode_sde_generate, one Philox subsequence per global
+    path id: identical data for any sharding) and collated there (njode_collate)."""
+    import torch
+    from njode_b200 import stock_model
+    p = SDE_PARAMS
+    hp = dict(drift=p["drift"], volatility=p["volatility"], mean=p["mean"], speed=p["speed"],
+              correlation=p["correlation"], S0=[p["S0"]] * wl["d"], nb_paths=n_paths, nb_steps=wl["steps"],
+              maturity=p["maturity"], sine_coeff=None, obs_perc=wl["obs_perc"])
+    ds = stock_model.DeviceDataset(wl["sde"], hp, seed=seed, first_path=first_path, device=dev)
+    b = ds.collate(torch.arange(n_paths))
+    return b, ds.dt
 
 
 def model_cfg(wl):
@@ -267,7 +282,11 @@ def run_b200(args, wl_name, wl):
 
     B = wl["paths"]                      # per GPU (weak scaling)
     first = rank * B
-    batch, dt = synth_batch(wl, 1234, first, B)
+    dev_data = bool(wl.get("device_data"))
+    if dev_data:
+        batch, dt = synth_batch_device(wl, 1234, first, B, dev)
+    else:
+        batch, dt = synth_batch(wl, 1234, first, B)
     # the Euler grid is batch-global (NJODE/models.py:430-439): all ranks use the union of times.
     # On the regular grid with >= 20k paths per rank every grid time is observed on every rank.
     T = SDE_PARAMS["maturity"]
@@ -342,7 +361,15 @@ def run_b200(args, wl_name, wl):
     # ---- end-to-end arm: public API, host tensors ---------------------------------------------
     model.output_device = "cpu"
     nb = 3
-    host_batches = [synth_batch(wl, 4321 + j, first, B)[0] for j in range(nb)]
+    if dev_data:
+        # the e2e arm still hands HOST tensors to the public API (X / start_X are copied to the host here)
+        host_batches = []
+        for j in range(nb):
+            hb = synth_batch_device(wl, 4321 + j, first, B, dev)[0]
+            hb["X"], hb["start_X"] = hb["X"].cpu(), hb["start_X"].cpu()
+            host_batches.append(hb)
+    else:
+        host_batches = [synth_batch(wl, 4321 + j, first, B)[0] for j in range(nb)]
 
     def step_e2e(b):
         for p in params:
@@ -391,6 +418,7 @@ def run_b200(args, wl_name, wl):
     fwd_ms = float(np.median(kf)) if kf else float("nan")
     achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12
     H = wl["H"]
+    tensor_path = model.last_forward_path == "tcgen05"
     alg_bytes_bwd = 4 * (S * B * H + N_rows * (H + 2 * wl["d"]) + B * wl["d"]) + 4 * model._flat.numel()
     peaks = {}
     try:
@@ -409,13 +437,31 @@ def run_b200(args, wl_name, wl):
                         "frac": alg_bytes_bwd / (bwd_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
 
+    if tensor_path:
+        # wide nets: the step runs on the tcgen05 kernels (njode_wide_*): bf16 operands, fp32 accumulation.
+        # Roofline = all MLP flops of fwd+bwd (3x forward) over the summed durations of the
+        # tensor-core kernels (CUDA events on the launching stream, last timed step), against the measured
+        # sustained bf16 GEMM peak (the kernels run inside a long step).
+        lib.njode_wide_get_timing.argtypes = [C.POINTER(C.c_float)] * 3
+        lib.njode_wide_get_timing_bwd.argtypes = [C.POINTER(C.c_float)] * 2
+        te, to, tr, tc_, td = (C.c_float() for _ in range(5))
+        lib.njode_wide_get_timing(C.byref(te), C.byref(to), C.byref(tr))
+        lib.njode_wide_get_timing_bwd(C.byref(tc_), C.byref(td))
+        k_ms = te.value + to.value + tr.value + tc_.value + td.value
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = 3.0 * fwd_flops / (k_ms * 1e-3) / 1e12
+        roofline = {"kernel": "nj_wide_kernel + nj_wide_bwd_kernel + nj_wide_dw_kernel (tcgen05)", "bound": "tensor",
+                    "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                    "kernel_ms": k_ms, "fwd_enc_ms": te.value, "fwd_ode_ms": to.value, "fwd_ro_ms": tr.value,
+                    "bwd_chain_ms": tc_.value, "bwd_dw_ms": td.value, "flops_per_launch": 3.0 * fwd_flops}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor_path else "f32", "data": "synthetic",
            "config": {"workload": wl_name, "sde": wl["sde"], "paths_per_gpu": B, "euler_steps": S,
                       "obs_rows_per_gpu": N_rows, "input_size": wl["d"], "hidden_size": H,
                       "mlp": "%dx%d tanh" % (wl["layers"], wl["width"]), "dropout": wl["dropout"],
