@@ -255,29 +255,42 @@ __device__ __forceinline__ void store_a_chunk(uint32_t a_base, int r, int c0, co
     }
 }
 
-// hidden layer: act(acc + bias) (+ dropout) of columns [c0, c0+32) -> bf16 -> A
-__device__ __forceinline__ void epi_hidden_chunk(uint32_t taddr, const float* bias_s, int c0, const WLayer& L,
-                                                 const WCfg& c, unsigned lk, uint32_t a_base, int r) {
+// hidden layer: act(acc + bias) (+ dropout) of columns [c0, c0+32) -> bf16 -> A.  ACT / DROP are compile-time so
+// that the 32-element loops are branch-free; the caller dispatches on the (warp-uniform) layer description.
+template <int ACT, bool DROP>
+__device__ __forceinline__ void epi_hidden_chunk_t(uint32_t taddr, const float* bias_s, int c0, int n,
+                                                   const WCfg& c, unsigned lk, uint32_t a_base, int r) {
     uint32_t v[32];
     tmem_ld32(taddr + (uint32_t)c0, v);
+    float b[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {                       // broadcast LDS.128 of the bias (overlaps the TMEM load)
+        const float4 t = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * q);
+        b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+    }
     tmem_wait_ld();
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]) + bias_s[c0 + j];
-        x = (L.act == NJODE_ACT_TANH) ? tanh_fast(x) : (L.act == NJODE_ACT_RELU ? fmaxf(x, 0.f) : x);
-        f[j] = (c0 + j < L.n) ? x : 0.f;
+        const float x = __uint_as_float(v[j]) + b[j];
+        f[j] = ACT == NJODE_ACT_TANH ? tanh_fast(x) : (ACT == NJODE_ACT_RELU ? fmaxf(x, 0.f) : x);
     }
-    if (L.drop) {
-        // neurons o and o ^ 8 share one hash word (nj_keep, njode_core.cuh): 16 words serve the 32 columns
+    if (c0 + 32 > n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = (c0 + j < n) ? f[j] : 0.f;
+    }
+    if (DROP) {
+        // neurons o and o ^ 8 share one hash word (nj_keep, njode_hash.cuh): 16 words serve the 32 columns
+        const float ks = c.keep_scale;
+        const unsigned thr = c.thr;
 #pragma unroll
         for (int g = 0; g < 2; ++g)
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const unsigned word = nj_keep_word(lk, (unsigned)jj | ((unsigned)((c0 >> 4) + g) << 3));
                 const int j0 = g * 16 + jj, j1 = j0 + 8;
-                f[j0] = (word & 0xFFFFu) >= c.thr ? f[j0] * c.keep_scale : -0.f;
-                f[j1] = (word >> 16) >= c.thr ? f[j1] * c.keep_scale : -0.f;
+                f[j0] = (word & 0xFFFFu) >= thr ? f[j0] * ks : -0.f;
+                f[j1] = (word >> 16) >= thr ? f[j1] * ks : -0.f;
             }
     }
     uint32_t p[16];
@@ -285,16 +298,29 @@ __device__ __forceinline__ void epi_hidden_chunk(uint32_t taddr, const float* bi
     for (int j = 0; j < 16; ++j) p[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
     store_a_chunk(a_base, r, c0, p);
 }
+__device__ __forceinline__ void epi_hidden_chunk(uint32_t taddr, const float* bias_s, int c0, const WLayer& L,
+                                                 const WCfg& c, unsigned lk, uint32_t a_base, int r) {
+    if (L.act == NJODE_ACT_TANH) {
+        if (L.drop) epi_hidden_chunk_t<NJODE_ACT_TANH, true>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
+        else epi_hidden_chunk_t<NJODE_ACT_TANH, false>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
+    } else if (L.act == NJODE_ACT_RELU) {
+        if (L.drop) epi_hidden_chunk_t<NJODE_ACT_RELU, true>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
+        else epi_hidden_chunk_t<NJODE_ACT_RELU, false>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
+    } else epi_hidden_chunk_t<NJODE_ACT_NONE, false>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
+}
 
 // tanh of 32 fp32 values -> bf16 -> A main blocks at columns [c0, c0+32); columns >= n are written as 0
 __device__ __forceinline__ void store_tanh_chunk(uint32_t a_base, int r, int c0, int n, const float* h) {
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = tanh_fast(h[j]);
+    if (c0 + 32 > n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = (c0 + j < n) ? t[j] : 0.f;
+    }
     uint32_t p[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float t0 = (c0 + 2 * j < n) ? tanh_fast(h[2 * j]) : 0.f;
-        const float t1 = (c0 + 2 * j + 1 < n) ? tanh_fast(h[2 * j + 1]) : 0.f;
-        p[j] = pack_bf16(t0, t1);
-    }
+    for (int j = 0; j < 16; ++j) p[j] = pack_bf16(t[2 * j], t[2 * j + 1]);
     store_a_chunk(a_base, r, c0, p);
 }
 
@@ -382,7 +408,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_acc, 1);
-        mbar_init(bar_a, EPI_THREADS);
+        mbar_init(bar_a, EPI_THREADS / 32);
         mbar_init(bar_spill, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -567,7 +593,9 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
             if (T.reps == 0) continue;
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(bar_a); ++n_arr;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a);
+            ++n_arr;
             // ---------------- layers ----------------
             for (int rep = 0; rep < T.reps; ++rep) {
                 for (int l = 0; l < net.n; ++l) {
@@ -693,7 +721,9 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                     if (!tile_done) {
                         tc_fence_before();
                         fence_proxy_async();
-                        mbar_arrive(bar_a); ++n_arr;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_a);
+                        ++n_arr;
                     }
                 }
             }
@@ -717,19 +747,6 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
 // Same warp roles, barriers and operand layouts as the forward kernel; the B operand is the transposed weight
 // image (W_l^T, K-major over the layer's outputs).
 // ================================================================================================
-__device__ __forceinline__ float act_factor(uint32_t bits16, int act, int drop, float ks, float inv_ks) {
-    const float av = __uint_as_float(bits16 << 16);
-    if (act == NJODE_ACT_TANH) {
-        if (drop) {
-            if (bits16 == 0x8000u) return 0.f;             // dropped activations were stored as -0
-            const float t = av * inv_ks;
-            return ks * (1.f - t * t);
-        }
-        return 1.f - av * av;
-    }
-    if (act == NJODE_ACT_RELU) return av > 0.f ? (drop ? ks : 1.f) : 0.f;
-    return 1.f;
-}
 // my row's 32 columns [c0, c0+32) of a spilled image (global memory), as 16 packed bf16 pairs
 __device__ __forceinline__ void load_img_chunk(const unsigned char* img, int r, int c0, uint32_t* p) {
 #pragma unroll
@@ -741,12 +758,36 @@ __device__ __forceinline__ void load_img_chunk(const unsigned char* img, int r, 
     }
 }
 // 32 fp32 gradients -> bf16 -> G image columns [c0, c0+32); columns >= n are written as 0
-__device__ __forceinline__ void store_g_chunk(uint32_t a_base, int r, int c0, int n, const float* g) {
+__device__ __forceinline__ void store_g_chunk(uint32_t a_base, int r, int c0, int n, float* g) {
+    if (c0 + 32 > n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = (c0 + j < n) ? g[j] : 0.f;
+    }
     uint32_t p[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-        p[j] = pack_bf16((c0 + 2 * j < n) ? g[2 * j] : 0.f, (c0 + 2 * j + 1 < n) ? g[2 * j + 1] : 0.f);
+    for (int j = 0; j < 16; ++j) p[j] = pack_bf16(g[2 * j], g[2 * j + 1]);
     store_a_chunk(a_base, r, c0, p);
+}
+// g[j] = acc[j] * act'(a_j) with the (warp-uniform) activation kind hoisted out of the element loop
+template <int ACT, bool DROP>
+__device__ __forceinline__ void apply_act_grad_t(const uint32_t* v, const uint32_t* av, float ks, float inv_ks, float* g) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t b16 = (j & 1) ? (av[j >> 1] >> 16) : (av[j >> 1] & 0xFFFFu);
+        const float a = __uint_as_float(b16 << 16);
+        float f;
+        if (ACT == NJODE_ACT_TANH) {
+            if (DROP) { const float t = a * inv_ks; f = b16 == 0x8000u ? 0.f : ks * (1.f - t * t); }   // dropped: stored as -0
+            else f = 1.f - a * a;
+        } else if (ACT == NJODE_ACT_RELU) f = a > 0.f ? (DROP ? ks : 1.f) : 0.f;
+        else f = 1.f;
+        g[j] = __uint_as_float(v[j]) * f;
+    }
+}
+__device__ __forceinline__ void apply_act_grad(const uint32_t* v, const uint32_t* av, int act, int drop, float ks, float inv_ks, float* g) {
+    if (act == NJODE_ACT_TANH) { if (drop) apply_act_grad_t<NJODE_ACT_TANH, true>(v, av, ks, inv_ks, g); else apply_act_grad_t<NJODE_ACT_TANH, false>(v, av, ks, inv_ks, g); }
+    else if (act == NJODE_ACT_RELU) { if (drop) apply_act_grad_t<NJODE_ACT_RELU, true>(v, av, ks, inv_ks, g); else apply_act_grad_t<NJODE_ACT_RELU, false>(v, av, ks, inv_ks, g); }
+    else apply_act_grad_t<NJODE_ACT_NONE, false>(v, av, ks, inv_ks, g);
 }
 
 __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsigned char* smem_raw) {
@@ -765,7 +806,7 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_acc, 1);
-        mbar_init(bar_a, EPI_THREADS);
+        mbar_init(bar_a, EPI_THREADS / 32);
         mbar_init(bar_spill, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -855,7 +896,7 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
         uint32_t pf = 0, ps = 0;
         int n_arr = 0, n_spw = 0;
         auto spill_sync = [&]() { while (n_spw < n_arr) { mbar_wait(bar_spill, ps); ps ^= 1; ++n_spw; } };
-        auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(bar_a); ++n_arr; };
+        auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(bar_a); ++n_arr; };
         const int H = c.H, d = c.d;
         const int hch = (H + 31) >> 5, hper = (hch + 1) >> 1;
         const int hc_lo = hf * hper, hc_hi = min(hch, hc_lo + hper);
@@ -960,9 +1001,9 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                     const int ncols = L.nt;                                   // gradient width = main inputs of layer l
                     const int nch = (L.nt16 + 31) >> 5, per = (nch + 1) >> 1;
                     const int c_lo = hf * per, c_hi = min(nch, c_lo + per);
-                    uint32_t av[4][16];
+                    uint32_t av[2][16];                                       // two chunks in flight
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < 2; ++k)
                         if (c_lo + k < c_hi) load_img_chunk(arec + L.act_off, r, (c_lo + k) * 32, av[k]);
                     mbar_wait(bar_acc, pf); pf ^= 1;
                     tc_fence_after();
@@ -978,18 +1019,14 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                             if (l == 0 && a.mode == MODE_ODE) tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(g));
                             tmem_wait_ld();
                             if (l > 0) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const uint32_t b16 = (j & 1) ? (av[k][j >> 1] >> 16) : (av[k][j >> 1] & 0xFFFFu);
-                                    g[j] = __uint_as_float(v[j]) * act_factor(b16, Lp.act, Lp.drop, ks, inv_ks);
-                                }
+                                apply_act_grad(v, av[k & 1], Lp.act, Lp.drop, ks, inv_ks, g);
                                 store_g_chunk(a_base, r, ch * 32, ncols, g);
                             } else {
                                 // input of the net = tanh(h): d/dh = 1 - tanh(h)^2, tanh(h) from the spilled A_0
                                 float gi[32];
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
-                                    const uint32_t b16 = (j & 1) ? (av[k][j >> 1] >> 16) : (av[k][j >> 1] & 0xFFFFu);
+                                    const uint32_t b16 = (j & 1) ? (av[k & 1][j >> 1] >> 16) : (av[k & 1][j >> 1] & 0xFFFFu);
                                     const float th = __uint_as_float(b16 << 16);
                                     gi[j] = __uint_as_float(v[j]) * (1.f - th * th);
                                 }
@@ -1012,6 +1049,7 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                                     }
                                 }
                             }
+                            if (k + 2 < 4 && ch + 2 < c_hi) load_img_chunk(arec + L.act_off, r, (ch + 2) * 32, av[k & 1]);
                         }
                     }
                     if (l == 0 && a.mode == MODE_ODE) tmem_wait_st();
