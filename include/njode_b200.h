@@ -169,6 +169,8 @@ int njode_wide_backward(const njode_model_t* model, const njode_batch_t* batch, 
  * chain passes / dW pass of the last njode_wide_backward (timing on) */
 int njode_wide_get_timing(float* enc_ms, float* ode_ms, float* ro_ms);
 int njode_wide_get_timing_bwd(float* chain_ms, float* dw_ms);
+/* debugging aid: clock64 stamps of CTA 0 of the forward Euler-chain kernel (buf: 4 x 256 uint64 device words, or NULL) */
+void njode_wide_set_profile(void* buf);
 
 /* Euler-Maruyama generators + Bernoulli observation mask (NJODE/stock_model.py:181-221, 288-335,
  * 356-375, 397-418 and NJODE/data_utils.py:73-81), one Philox-4x32-10 subsequence per global path id. */

@@ -328,6 +328,7 @@ static Wb wb_layout(const WCfg& c, const njode_batch_t& b) {
 }
 static inline char* align1k(void* p) { return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); }
 
+static unsigned long long* g_prof = nullptr;      // debugging: device buffer of clock stamps (njode_wide_set_profile)
 static cudaEvent_t g_ev[10];
 static bool g_ev_ok = false, g_ev_rec = false, g_evb_rec = false;
 
@@ -420,9 +421,11 @@ extern "C" int njode_wide_forward(const njode_model_t* model, const njode_batch_
         nj_wide_kernel<<<std::min(n_tiles_all, sms), NUM_THREADS, SMEM_BYTES, st>>>(c, a);
         if (timing) cudaEventRecord(g_ev[1], st);
         a.mode = MODE_ODE; a.act = act_base[NJODE_NET_ODE];
+        a.prof = g_prof;
         if (timing) cudaEventRecord(g_ev[2], st);
         nj_wide_kernel<<<std::min(n_tiles_all, sms), NUM_THREADS, SMEM_BYTES, st>>>(c, a);
         if (timing) cudaEventRecord(g_ev[3], st);
+        a.prof = nullptr;
         launches += 2;
     }
     if (loss) {
@@ -542,3 +545,6 @@ extern "C" int njode_wide_get_timing_bwd(float* chain_ms, float* dw_ms) {
     if (dw_ms) *dw_ms = dw;
     return 0;
 }
+
+// debugging aid: the forward Euler-chain kernel writes clock64 stamps of CTA 0 into `buf` (4 x 256 uint64) when set
+extern "C" void njode_wide_set_profile(void* buf) { njw::g_prof = reinterpret_cast<unsigned long long*>(buf); }

@@ -106,6 +106,7 @@ struct WArgs {
     const float* grad_loss; const float* grad_hT;
     float* dw_part;                // [dw_slots][256 x 256] partial dW accumulators, then [dw_slots][256] bias partials
     int n_tiles_all;
+    unsigned long long* prof;      // debugging: clock64 stamps of CTA 0 (4 per layer GEMM: a_ready seen, MMAs issued, accumulator seen, epilogue done)
 };
 
 // dynamic shared memory map (bytes from the 1024-aligned base)
@@ -453,6 +454,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
         // ===================== MMA issuer =====================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0, pa = 0;
+            int nprof = 0;
             for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
                 const Tile T = tile_of(c, a, t);
                 for (int rep = 0; rep < T.reps; ++rep)
@@ -462,6 +464,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                         const int nkb = L.kb_main + L.has_aux;
                         mbar_wait(bar_a, pa); pa ^= 1;               // A operand written, accumulator drained
                         tc_fence_after();
+                        if (a.prof && blockIdx.x == 0 && nprof < 256) a.prof[4 * nprof] = clock64();
                         for (int kb = 0; kb < nkb; ++kb) {
                             const bool aux = kb >= L.kb_main;
                             const int ksteps = aux ? L.aux_ksteps : 4;
@@ -475,6 +478,8 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                             if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
                         }
                         tc_commit(bar_acc);                           // accumulator complete
+                        if (a.prof && blockIdx.x == 0 && nprof < 256) a.prof[4 * nprof + 1] = clock64();
+                        ++nprof;
                     }
             }
         }
@@ -507,6 +512,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
         const int r = q * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t pf = 0, ps = 0;
+        int nprof = 0;
         int n_arr = 0, n_spw = 0;          // a_ready arrivals made / spill completions consumed
         // the A image of an arrival may be overwritten only after the spill warp has read it
         auto spill_sync = [&]() {
@@ -603,6 +609,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                     const bool last = (l == net.n - 1);
                     mbar_wait(bar_acc, pf); pf ^= 1;
                     tc_fence_after();
+                    if (a.prof && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && nprof < 256) a.prof[4 * nprof + 2] = clock64();
                     spill_sync();
                     const int nch = (L.n16 + 31) >> 5, per = (nch + 1) >> 1;
                     const int c_lo = hf * per, c_hi = min(nch, c_lo + per);
@@ -717,6 +724,8 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                         }
                     }
                     const bool tile_done = last && rep + 1 == T.reps;
+                    if (a.prof && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && nprof < 256) a.prof[4 * nprof + 3] = clock64();
+                    ++nprof;
                     if (a.mode == MODE_RO) epi_bar_sync();        // res_s / ybj_s written before the hf-0 threads read them
                     if (!tile_done) {
                         tc_fence_before();

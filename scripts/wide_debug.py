@@ -75,6 +75,18 @@ def main(name):
         print("   %-28s rel %.4f  max|ref| %.3e" % (nme, rel(a_, b_), float(b_.abs().max())))
     if name.endswith("big") or name.endswith("huge"):
         import ctypes as C
+        prof = torch.zeros(1024, dtype=torch.int64, device="cuda")
+        r.lib.dll.njode_wide_set_profile(C.c_void_p(prof.data_ptr()))
+        r.forward_wide(mt, pb, m._flat, H, d, True, False)
+        torch.cuda.synchronize()
+        r.lib.dll.njode_wide_set_profile(None)
+        pr = prof.cpu().numpy().reshape(256, 4)
+        t0 = pr[0, 0]
+        print("layer-GEMM stamps of CTA 0 (cycles): a_ready seen | MMAs issued | acc seen | epilogue done ; deltas")
+        for i in range(1, 16):
+            a0, a1, a2, a3 = pr[i]
+            print("  %3d: mma_start %7d  issue %5d  acc_wait %6d  epilogue %6d  -> next start %6d" % (
+                i, a0 - t0, a1 - a0, a2 - a0, a3 - a2, pr[i + 1, 0] - a3))
         r.lib.dll.njode_set_timing(1)
         for _ in range(3):
             r.forward_wide(mt, pb, m._flat, H, d, True, True)
