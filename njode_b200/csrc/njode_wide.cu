@@ -111,20 +111,26 @@ static void plan_dw(WCfg& c, const njode_batch_t& b, int sms) {
     c.dw_items = items; c.dw_slots = slot;
 }
 
-// flat fp32 parameters -> bf16 image in the shared-memory operand layout (one [n16 x 128 B] SWIZZLE_128B block per
-// K-block) + fp32 bias image.  grid = 3 nets x 8 layers x 5 K-blocks.
+// flat fp32 parameters -> bf16 image in the shared-memory operand layout: per layer, for each 128-row half of the
+// outputs, one [rows x 128 B] SWIZZLE_128B block per K-block (the order the MMA issuer consumes them) + fp32 bias
+// image.  grid = 3 nets x 8 layers x 2 halves x 5 K-blocks.
 __global__ void nj_wide_pack_kernel(const __grid_constant__ WCfg c, const float* __restrict__ params,
                                     unsigned char* __restrict__ img, float* __restrict__ bias) {
-    const int n = blockIdx.x / (NJODE_MAX_LINEAR * A_BLOCKS), l = (blockIdx.x / A_BLOCKS) % NJODE_MAX_LINEAR, kb = blockIdx.x % A_BLOCKS;
+    int b = blockIdx.x;
+    const int kb = b % 5; b /= 5;
+    const int p = b % 2; b /= 2;
+    const int l = b % NJODE_MAX_LINEAR, n = b / NJODE_MAX_LINEAR;
     const WNet& N = c.net[n];
     if (l >= N.n) return;
     const WLayer& L = N.l[l];
-    if (kb >= L.kb_main + L.has_aux) return;
+    const int nkb = L.kb_main + L.has_aux;
+    if (kb >= nkb || p * 128 >= L.n16) return;
     const bool aux = kb >= L.kb_main;
     const int d = c.d, H = c.H;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(img + L.img_off + (size_t)kb * L.n16 * 128);
-    for (int i = threadIdx.x; i < L.n16 * 64; i += blockDim.x) {
-        const int o = i >> 6, k = i & 63;
+    const int rows = min(128, L.n16 - 128 * p);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(img + L.img_off + (size_t)p * 128 * 128 * nkb + (size_t)kb * rows * 128);
+    for (int i = threadIdx.x; i < rows * 64; i += blockDim.x) {
+        const int ol = i >> 6, k = i & 63, o = 128 * p + ol;
         int col = -1;
         if (!aux) {
             const int kk = kb * 64 + k;
@@ -139,9 +145,9 @@ __global__ void nj_wide_pack_kernel(const __grid_constant__ WCfg c, const float*
         }
         float v = 0.f;
         if (o < L.n && col >= 0) v = params[L.w_src + (long long)o * L.in_dim + col];
-        dst[(size_t)o * 64 + ((((k >> 3) ^ (o & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
+        dst[(size_t)ol * 64 + ((((k >> 3) ^ (ol & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
     }
-    if (kb == 0)
+    if (kb == 0 && p == 0)
         for (int o = threadIdx.x; o < MAX_W; o += blockDim.x)
             bias[L.bias_off + o] = (o < L.n && L.b_src >= 0) ? params[L.b_src + o] : 0.f;
 }
@@ -151,19 +157,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nj_wide_kernel(const __grid_co
     wide_cta(c, a, njw_smem);
 }
 
-// W_l^T images for the backward GEMMs: rows = the layer's main inputs (ODE layer 0: the tanh(h) columns), K = outputs
+// W_l^T images for the backward GEMMs: rows = the layer's main inputs (ODE layer 0: the tanh(h) columns) in halves of
+// 128, K = outputs.  grid = 3 nets x 8 layers x 2 halves x 4 K-blocks.
 __global__ void nj_wide_pack_t_kernel(const __grid_constant__ WCfg c, const float* __restrict__ params, unsigned char* __restrict__ img) {
-    const int n = blockIdx.x / (NJODE_MAX_LINEAR * 4), l = (blockIdx.x / 4) % NJODE_MAX_LINEAR, kb = blockIdx.x % 4;
+    int b = blockIdx.x;
+    const int kb = b % 4; b /= 4;
+    const int p = b % 2; b /= 2;
+    const int l = b % NJODE_MAX_LINEAR, n = b / NJODE_MAX_LINEAR;
     const WNet& N = c.net[n];
     if (l >= N.n) return;
     const WLayer& L = N.l[l];
-    if (L.kind == KIND_ENC0 || kb >= L.kt_blocks) return;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(img + L.wt_off + (size_t)kb * L.nt16 * 128);
-    for (int i = threadIdx.x; i < L.nt16 * 64; i += blockDim.x) {
-        const int k = i >> 6, oo = i & 63, o = kb * 64 + oo;
+    if (L.kind == KIND_ENC0 || kb >= L.kt_blocks || p * 128 >= L.nt16) return;
+    const int rows = min(128, L.nt16 - 128 * p);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(img + L.wt_off + (size_t)p * 128 * 128 * L.kt_blocks + (size_t)kb * rows * 128);
+    for (int i = threadIdx.x; i < rows * 64; i += blockDim.x) {
+        const int kl = i >> 6, oo = i & 63, o = kb * 64 + oo, k = 128 * p + kl;
         float v = 0.f;
         if (o < L.n && k < L.nt) v = params[L.w_src + (long long)o * L.in_dim + (L.kind == KIND_ODE0 ? c.d + k : k)];
-        dst[(size_t)k * 64 + ((((oo >> 3) ^ (k & 7)) << 3) | (oo & 7))] = __float2bfloat16_rn(v);
+        dst[(size_t)kl * 64 + ((((oo >> 3) ^ (kl & 7)) << 3) | (oo & 7))] = __float2bfloat16_rn(v);
     }
 }
 
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nj_wide_bwd_kernel(const __gri
 }
 
 // one launch per net (a.mode = net id): CTA -> (layer, part, share) from the per-layer CTA counts
-__global__ void __launch_bounds__(NUM_THREADS, 1) nj_wide_dw_kernel(const __grid_constant__ WCfg c, const __grid_constant__ WArgs a) {
+__global__ void __launch_bounds__(DW_THREADS, 1) nj_wide_dw_kernel(const __grid_constant__ WCfg c, const __grid_constant__ WArgs a) {
     __shared__ DwItem it;
     if (threadIdx.x == 0) {
         int b = blockIdx.x;
@@ -410,7 +421,7 @@ extern "C" int njode_wide_forward(const njode_model_t* model, const njode_batch_
     const bool timing = nj_timing_flag() != 0;
     if (timing && !g_ev_ok) { for (int i = 0; i < 10; ++i) cudaEventCreate(&g_ev[i]); g_ev_ok = true; }
 
-    nj_wide_pack_kernel<<<3 * NJODE_MAX_LINEAR * A_BLOCKS, 256, 0, st>>>(c, params, const_cast<unsigned char*>(a.wimg), const_cast<float*>(a.bias));
+    nj_wide_pack_kernel<<<3 * NJODE_MAX_LINEAR * 2 * 5, 256, 0, st>>>(c, params, const_cast<unsigned char*>(a.wimg), const_cast<float*>(a.bias));
     int launches = 1;
     NJW_CUDA(cudaFuncSetAttribute(nj_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     if (loss && batch->N > 0) NJW_CUDA(cudaMemsetAsync(a.row_loss, 0, (size_t)batch->N * 4, st));
@@ -488,7 +499,7 @@ extern "C" int njode_wide_backward(const njode_model_t* model, const njode_batch
     const bool timing = nj_timing_flag() != 0;
     if (timing && !g_ev_ok) { for (int i = 0; i < 10; ++i) cudaEventCreate(&g_ev[i]); g_ev_ok = true; }
     int launches = 0;
-    nj_wide_pack_t_kernel<<<3 * NJODE_MAX_LINEAR * 4, 256, 0, st>>>(c, params, const_cast<unsigned char*>(a.wt)); ++launches;
+    nj_wide_pack_t_kernel<<<3 * NJODE_MAX_LINEAR * 2 * 4, 256, 0, st>>>(c, params, const_cast<unsigned char*>(a.wt)); ++launches;
     NJW_CUDA(cudaFuncSetAttribute(nj_wide_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     NJW_CUDA(cudaFuncSetAttribute(nj_wide_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     // rows without a loss contribution (none today) and units never reached by the readout chains start from zero
@@ -510,7 +521,7 @@ extern "C" int njode_wide_backward(const njode_model_t* model, const njode_batch
         for (int l = 0; l < c.net[n].n; ++l) ctas += c.net[n].l[l].dw_J[0] + c.net[n].l[l].dw_J[1];
         if (ctas == 0) continue;
         a.mode = n; a.act = act_base[n]; a.gsp = g_base[n];
-        nj_wide_dw_kernel<<<ctas, NUM_THREADS, SMEM_BYTES, st>>>(c, a); ++launches;
+        nj_wide_dw_kernel<<<ctas, DW_THREADS, SMEM_BYTES, st>>>(c, a); ++launches;
     }
     nj_wide_dw_reduce_kernel<<<dim3(3 * NJODE_MAX_LINEAR * 2, 16), 256, 0, st>>>(c, a.dw_part, grads); ++launches;
     if (timing) { cudaEventRecord(g_ev[8], st); g_evb_rec = true; }

@@ -35,14 +35,19 @@
 namespace njw {
 
 constexpr int TILE_M = 128;
-constexpr int NSTAGE = 3;
-constexpr int STAGE_BYTES = 256 * 128;          // one K-block of a 256-row weight matrix
+constexpr int NSTAGE = 5;
+constexpr int STAGE_BYTES = 128 * 128;          // one K-block of one 128-row half of a weight matrix
 constexpr int A_BLOCK_BYTES = TILE_M * 128;     // one K-block of the activation tile
-constexpr int A_BLOCKS = 5;                     // 4 main blocks (K <= 256) + the auxiliary block
-constexpr int AUX_BLOCK = 4;
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_THREADS = 256;
+constexpr int A_BLOCKS = 7;                     // 3 rotating pairs of main K-blocks + the auxiliary block
+constexpr int AUX_BLOCK = 6;
+#ifndef NJW_EPI_GROUPS
+#define NJW_EPI_GROUPS 2
+#endif
+constexpr int EPI_GROUPS = NJW_EPI_GROUPS;                   // column groups of the epilogue: warp w = lane quadrant w % 4, group (w - 4) / 4
+constexpr int EPI_WARPS = 4 * EPI_GROUPS;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int EPI_WARP0 = 4;
+constexpr int NUM_THREADS = 32 * EPI_WARP0 + EPI_THREADS;
 constexpr int MAX_W = 256;                      // widest layer / hidden state
 constexpr int MAX_D = 16;                       // widest input / output
 constexpr int AUX_X0 = 8;                       // auxiliary block: columns 0..5 = tau, tdiff, tau+tdiff as bf16 hi/lo
@@ -60,11 +65,12 @@ struct WLayer {
     int n, n16;         // outputs, padded to the UMMA N granularity
     int in_dim;         // inputs of the nn.Linear
     int act, drop, kind;
-    unsigned img_off;   // byte offset of K-block 0 inside the bf16 image (blocks are n16 * 128 B apart)
+    unsigned img_off;   // byte offset of the layer's bf16 image: for each 128-row half of the outputs, its K-blocks
+                        // ([rows of the half x 128 B] each, main blocks then the auxiliary block)
     int bias_off;       // float offset inside the bias image
     long long w_src, b_src;
     // backward: acc[128 x k] = G_l[128 x n] . W_l[n x k]  (B operand = W_l^T, K-major over the outputs)
-    unsigned wt_off;    // byte offset of the transposed image (kt_blocks blocks of nt16 * 128 B)
+    unsigned wt_off;    // byte offset of the transposed image: for each 128-row half of nt16, kt_blocks K-blocks
     int kt_blocks;      // K-blocks of the transposed GEMM = ceil(n16 / 64)
     int kt_last_ksteps; // K-steps issued on the last of them
     int nt, nt16;       // N of the transposed GEMM: main inputs of the layer (ODE layer 0: H), padded to 16
@@ -113,10 +119,10 @@ struct WArgs {
 constexpr int SM_A = 0;
 constexpr int SM_W = SM_A + A_BLOCKS * A_BLOCK_BYTES;
 constexpr int SM_BIAS = SM_W + NSTAGE * STAGE_BYTES;                 // [8][256] fp32
-constexpr int SM_RES = SM_BIAS + NJODE_MAX_LINEAR * MAX_W * 4;       // [128][16] fp32 residual partial of column half 1
+constexpr int SM_RES = SM_BIAS + NJODE_MAX_LINEAR * MAX_W * 4;       // [128][16] fp32 readout residual (summed over the column groups)
 constexpr int SM_YBJ = SM_RES + TILE_M * MAX_D * 4;                  // [128][16] fp32
 constexpr int SM_BAR = SM_YBJ + TILE_M * MAX_D * 4;                  // mbarriers (SM_BAR is a multiple of 1024)
-constexpr int SM_TOTAL = SM_BAR + 128;
+constexpr int SM_TOTAL = SM_BAR + 256;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;                          // + alignment slack
 
 #if !defined(NJODE_HOST_SIM)
@@ -245,13 +251,28 @@ __device__ __forceinline__ size_t record_of(const WArgs& a, int t, int rep) {
 // ------------------------------------------------------------------------------------------------
 // epilogue pieces (thread = TMEM lane r, column range of its half)
 // ------------------------------------------------------------------------------------------------
-// stores 32 consecutive bf16 activations (packed in p[16]) of row r, columns [c0, c0+32), into the A blocks
-__device__ __forceinline__ void store_a_chunk(uint32_t a_base, int r, int c0, const uint32_t* p) {
+// The A operand of consecutive layer GEMMs rotates through three pairs of K-blocks: GEMM g reads its K-blocks
+// 0-1 from pair X_g and 2-3 from pair Y_g while the epilogue of its first output half already writes the next
+// GEMM's K-blocks 0-1 into the third pair Z_g; the second half's epilogue (all MMAs of g complete) writes K-blocks
+// 2-3 into X_g.  Hence (X, Y, Z)_{g+1} = (Z, X, Y)_g.
+__device__ __forceinline__ int pair_x(int g) { return (3 - g % 3) % 3; }
+__device__ __forceinline__ int pair_y(int g) { return (pair_x(g) + 1) % 3; }
+__device__ __forceinline__ int pair_z(int g) { return (pair_x(g) + 2) % 3; }
+// physical block of logical K-block kb of GEMM g's A operand
+__device__ __forceinline__ uint32_t ablock_of(uint32_t a_base, int g, int kb) {
+    return a_base + (uint32_t)((kb < 2 ? pair_x(g) : pair_y(g)) * 2 + (kb & 1)) * A_BLOCK_BYTES;
+}
+// physical block written by the epilogue of output half p of GEMM g for columns [128 p + 64 j, +64) (= K-block 2p + j
+// of GEMM g + 1)
+__device__ __forceinline__ uint32_t wblock_of(uint32_t a_base, int g, int p, int j) {
+    return a_base + (uint32_t)((p == 0 ? pair_z(g) : pair_x(g)) * 2 + j) * A_BLOCK_BYTES;
+}
+
+// stores 32 consecutive bf16 values (packed in p[16]) of row r at columns [cin, cin+32) (cin = 0 or 32) of a 64-column block
+__device__ __forceinline__ void store_a_chunk(uint32_t block, int r, int cin, const uint32_t* p) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int col = c0 + 8 * q;
-        const uint32_t addr = a_base + (uint32_t)(col >> 6) * A_BLOCK_BYTES + (uint32_t)r * 128u
-                            + ((uint32_t)(((col & 63) >> 3) ^ (r & 7)) << 4);
+        const uint32_t addr = block + (uint32_t)r * 128u + ((uint32_t)(((cin >> 3) + q) ^ (r & 7)) << 4);
         st_shared_v4(addr, p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
     }
 }
@@ -260,7 +281,7 @@ __device__ __forceinline__ void store_a_chunk(uint32_t a_base, int r, int c0, co
 // that the 32-element loops are branch-free; the caller dispatches on the (warp-uniform) layer description.
 template <int ACT, bool DROP>
 __device__ __forceinline__ void epi_hidden_chunk_t(uint32_t taddr, const float* bias_s, int c0, int n,
-                                                   const WCfg& c, unsigned lk, uint32_t a_base, int r) {
+                                                   const WCfg& c, unsigned lk, uint32_t block, int r) {
     uint32_t v[32];
     tmem_ld32(taddr + (uint32_t)c0, v);
     float b[32];
@@ -297,21 +318,21 @@ __device__ __forceinline__ void epi_hidden_chunk_t(uint32_t taddr, const float* 
     uint32_t p[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) p[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-    store_a_chunk(a_base, r, c0, p);
+    store_a_chunk(block, r, c0 & 32, p);
 }
 __device__ __forceinline__ void epi_hidden_chunk(uint32_t taddr, const float* bias_s, int c0, const WLayer& L,
-                                                 const WCfg& c, unsigned lk, uint32_t a_base, int r) {
+                                                 const WCfg& c, unsigned lk, uint32_t block, int r) {
     if (L.act == NJODE_ACT_TANH) {
-        if (L.drop) epi_hidden_chunk_t<NJODE_ACT_TANH, true>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
-        else epi_hidden_chunk_t<NJODE_ACT_TANH, false>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
+        if (L.drop) epi_hidden_chunk_t<NJODE_ACT_TANH, true>(taddr, bias_s, c0, L.n, c, lk, block, r);
+        else epi_hidden_chunk_t<NJODE_ACT_TANH, false>(taddr, bias_s, c0, L.n, c, lk, block, r);
     } else if (L.act == NJODE_ACT_RELU) {
-        if (L.drop) epi_hidden_chunk_t<NJODE_ACT_RELU, true>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
-        else epi_hidden_chunk_t<NJODE_ACT_RELU, false>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
-    } else epi_hidden_chunk_t<NJODE_ACT_NONE, false>(taddr, bias_s, c0, L.n, c, lk, a_base, r);
+        if (L.drop) epi_hidden_chunk_t<NJODE_ACT_RELU, true>(taddr, bias_s, c0, L.n, c, lk, block, r);
+        else epi_hidden_chunk_t<NJODE_ACT_RELU, false>(taddr, bias_s, c0, L.n, c, lk, block, r);
+    } else epi_hidden_chunk_t<NJODE_ACT_NONE, false>(taddr, bias_s, c0, L.n, c, lk, block, r);
 }
 
 // tanh of 32 fp32 values -> bf16 -> A main blocks at columns [c0, c0+32); columns >= n are written as 0
-__device__ __forceinline__ void store_tanh_chunk(uint32_t a_base, int r, int c0, int n, const float* h) {
+__device__ __forceinline__ void store_tanh_chunk(uint32_t block, int r, int c0, int n, const float* h) {
     float t[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) t[j] = tanh_fast(h[j]);
@@ -322,7 +343,7 @@ __device__ __forceinline__ void store_tanh_chunk(uint32_t a_base, int r, int c0,
     uint32_t p[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) p[j] = pack_bf16(t[2 * j], t[2 * j + 1]);
-    store_a_chunk(a_base, r, c0, p);
+    store_a_chunk(block, r, c0 & 32, p);
 }
 
 // 32 floats of a global row (columns [c0, c0+32) of a width-n row; n % 4 == 0), zero beyond n or when src == null
@@ -389,8 +410,38 @@ __device__ __forceinline__ unsigned ev_jump(const WArgs& a, int row, unsigned wh
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the forward kernel
 // ------------------------------------------------------------------------------------------------
+// Every layer GEMM is issued as two output halves of <= 128 columns (TMEM columns [0,128) and [128,256)), each
+// committed to its own mbarrier, so that the epilogue of half 0 overlaps the MMAs of half 1 and the MMAs of the
+// next layer's half 0 (which only need K-blocks 0-1 = the columns half 0's epilogue has just written) overlap the
+// epilogue of half 1.  Barriers: full/empty per weight stage, acc[2] (MMA -> epilogue), a_ready[2] (epilogue ->
+// MMA: "columns of half p written and TMEM half p drained"), spill (spill warp -> epilogue).
+struct Bars { uint32_t full, empty, acc, a, spill; };
+__device__ __forceinline__ Bars bars_of(uint32_t bar0) {
+    Bars b;
+    b.full = bar0; b.empty = bar0 + 8 * NSTAGE; b.acc = bar0 + 16 * NSTAGE; b.a = b.acc + 16; b.spill = b.a + 16;
+    return b;
+}
+constexpr int SM_TMEM_SLOT = SM_BAR + 16 * NSTAGE + 48;
+
+__device__ __forceinline__ void cta_setup(const Bars& B, uint32_t* tmem_slot, uint32_t zero_base, int zero_bytes) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(B.full + 8 * s, 1); mbar_init(B.empty + 8 * s, 1); }
+        mbar_init(B.acc, 1); mbar_init(B.acc + 8, 1);
+        mbar_init(B.a, EPI_WARPS); mbar_init(B.a + 8, EPI_WARPS);
+        mbar_init(B.spill, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((threadIdx.x >> 5) == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // zero the operand blocks once: padding columns only ever meet zero weights but must stay finite
+    for (int i = threadIdx.x; i < zero_bytes / 16; i += blockDim.x)
+        st_shared_v4(zero_base + 16u * i, 0u, 0u, 0u, 0u);
+}
+
 __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned char* smem_raw) {
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
@@ -398,32 +449,17 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
     float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS);
     float* res_s = reinterpret_cast<float*>(smem + SM_RES);
     float* ybj_s = reinterpret_cast<float*>(smem + SM_YBJ);
-    const uint32_t bar0 = sbase + SM_BAR;
-    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * NSTAGE, bar_acc = bar0 + 16 * NSTAGE, bar_a = bar_acc + 8;
-    const uint32_t bar_spill = bar_acc + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 24);
+    const Bars B = bars_of(sbase + SM_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM_SLOT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int netid = a.mode == MODE_ENC ? NJODE_NET_ENC : (a.mode == MODE_ODE ? NJODE_NET_ODE : NJODE_NET_RO);
     const WNet& net = c.net[netid];
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_a, EPI_THREADS / 32);
-        mbar_init(bar_spill, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    cta_setup(B, tmem_slot, a_base, A_BLOCKS * A_BLOCK_BYTES);
     for (int i = threadIdx.x; i < net.n * MAX_W; i += NUM_THREADS) {
         const int l = i / MAX_W, o = i % MAX_W;
         bias_s[i] = o < net.l[l].n16 ? __ldg(a.bias + net.l[l].bias_off + o) : 0.f;
     }
-    // zero the activation blocks once: padding columns only ever meet zero weights but must stay finite
-    for (int i = threadIdx.x; i < A_BLOCKS * A_BLOCK_BYTES / 16; i += NUM_THREADS)
-        st_shared_v4(a_base + 16u * i, 0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -431,7 +467,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== weight producer =====================
+        // ===================== weight producer: (half, K-block) tiles in the order the MMAs consume them =====================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
@@ -439,13 +475,17 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                 for (int rep = 0; rep < T.reps; ++rep)
                     for (int l = 0; l < net.n; ++l) {
                         const WLayer& L = net.l[l];
-                        const uint32_t bytes = (uint32_t)L.n16 * 128u;
                         const int nkb = L.kb_main + L.has_aux;
-                        for (int kb = 0; kb < nkb; ++kb) {
-                            mbar_wait(bar_empty + 8 * stage, ph ^ 1);
-                            mbar_expect_tx(bar_full + 8 * stage, bytes);
-                            bulk_g2s(w_base + stage * STAGE_BYTES, a.wimg + L.img_off + (size_t)kb * bytes, bytes, bar_full + 8 * stage);
-                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                        const unsigned char* src = a.wimg + L.img_off;
+                        for (int p = 0; p * 128 < L.n16; ++p) {
+                            const uint32_t bytes = (uint32_t)min(128, L.n16 - 128 * p) * 128u;
+                            for (int kb = 0; kb < nkb; ++kb) {
+                                mbar_wait(B.empty + 8 * stage, ph ^ 1);
+                                mbar_expect_tx(B.full + 8 * stage, bytes);
+                                bulk_g2s(w_base + stage * STAGE_BYTES, src, bytes, B.full + 8 * stage);
+                                src += bytes;
+                                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                            }
                         }
                     }
             }
@@ -453,54 +493,61 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            int stage = 0; uint32_t ph = 0, pa = 0;
-            int nprof = 0;
+            int stage = 0, g = 0; uint32_t ph = 0, pa0 = 0, pa1 = 0;
             for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
                 const Tile T = tile_of(c, a, t);
                 for (int rep = 0; rep < T.reps; ++rep)
-                    for (int l = 0; l < net.n; ++l) {
+                    for (int l = 0; l < net.n; ++l, ++g) {
                         const WLayer& L = net.l[l];
-                        const uint32_t idesc = make_idesc(L.n16);
                         const int nkb = L.kb_main + L.has_aux;
-                        mbar_wait(bar_a, pa); pa ^= 1;               // A operand written, accumulator drained
+                        bool got1 = false;
+                        mbar_wait(B.a, pa0); pa0 ^= 1;               // K-blocks 0-1 written, TMEM half 0 drained
                         tc_fence_after();
-                        if (a.prof && blockIdx.x == 0 && nprof < 256) a.prof[4 * nprof] = clock64();
-                        for (int kb = 0; kb < nkb; ++kb) {
-                            const bool aux = kb >= L.kb_main;
-                            const int ksteps = aux ? L.aux_ksteps : 4;
-                            mbar_wait(bar_full + 8 * stage, ph);
-                            tc_fence_after();
-                            const uint32_t ab = a_base + (uint32_t)(aux ? AUX_BLOCK : kb) * A_BLOCK_BYTES;
-                            const uint32_t wb = w_base + (uint32_t)stage * STAGE_BYTES;
-                            for (int k = 0; k < ksteps; ++k)
-                                tc_mma(tmem, make_desc(ab + 32u * k), make_desc(wb + 32u * k), idesc, (kb | k) ? 1u : 0u);
-                            tc_commit(bar_empty + 8 * stage);        // stage free once these MMAs have read it
-                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                        if (a.prof && blockIdx.x == 0 && g < 256) a.prof[4 * g] = clock64();
+                        for (int p = 0; p * 128 < L.n16; ++p) {
+                            const uint32_t idesc = make_idesc(min(128, L.n16 - 128 * p));
+                            for (int kb = 0; kb < nkb; ++kb) {
+                                const bool aux = kb >= L.kb_main;
+                                if ((aux || kb >= 2) && !got1) {     // K-blocks 2-3 / the auxiliary block, TMEM half 1 drained
+                                    mbar_wait(B.a + 8, pa1); pa1 ^= 1; got1 = true;
+                                    tc_fence_after();
+                                }
+                                const int ksteps = aux ? L.aux_ksteps : 4;
+                                mbar_wait(B.full + 8 * stage, ph);
+                                tc_fence_after();
+                                const uint32_t ab = aux ? a_base + AUX_BLOCK * A_BLOCK_BYTES : ablock_of(a_base, g, kb);
+                                const uint32_t wb = w_base + (uint32_t)stage * STAGE_BYTES;
+                                for (int k = 0; k < ksteps; ++k)
+                                    tc_mma(tmem + 128u * p, make_desc(ab + 32u * k), make_desc(wb + 32u * k), idesc, (kb | k) ? 1u : 0u);
+                                tc_commit(B.empty + 8 * stage);      // stage free once these MMAs have read it
+                                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                            }
+                            if (p == 0 && !got1) { mbar_wait(B.a + 8, pa1); pa1 ^= 1; got1 = true; tc_fence_after(); }
+                            tc_commit(B.acc + 8 * p);                // output half p complete
                         }
-                        tc_commit(bar_acc);                           // accumulator complete
-                        if (a.prof && blockIdx.x == 0 && nprof < 256) a.prof[4 * nprof + 1] = clock64();
-                        ++nprof;
+                        if (L.n16 <= 128) tc_commit(B.acc + 8);      // no second half: keep the barrier phases in step
+                        if (a.prof && blockIdx.x == 0 && g < 256) a.prof[4 * g + 1] = clock64();
                     }
             }
         }
     } else if (warp == 2) {
         // ===================== operand spill (training): every layer's A image -> its activation record =====================
         if (lane == 0 && a.spill) {
-            uint32_t pa = 0;
+            uint32_t pa1 = 0; int g = 0;
             for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
                 const Tile T = tile_of(c, a, t);
                 for (int rep = 0; rep < T.reps; ++rep) {
                     unsigned char* rec = a.act + record_of(a, t, rep) * (size_t)c.act_rec[netid];
-                    for (int l = 0; l < net.n; ++l) {
+                    for (int l = 0; l < net.n; ++l, ++g) {
                         const WLayer& L = net.l[l];
-                        mbar_wait(bar_a, pa); pa ^= 1;
+                        mbar_wait(B.a + 8, pa1); pa1 ^= 1;           // the whole image is written (half 1 arrives last)
                         for (int kb = 0; kb < L.kb_main; ++kb)
-                            bulk_s2g(rec + L.act_off + (size_t)kb * A_BLOCK_BYTES, a_base + (uint32_t)kb * A_BLOCK_BYTES, A_BLOCK_BYTES);
+                            bulk_s2g(rec + L.act_off + (size_t)kb * A_BLOCK_BYTES, ablock_of(a_base, g, kb), A_BLOCK_BYTES);
                         if (L.has_aux)
                             bulk_s2g(rec + L.act_off + (size_t)L.kb_main * A_BLOCK_BYTES, a_base + AUX_BLOCK * A_BLOCK_BYTES, A_BLOCK_BYTES);
                         bulk_commit();
                         bulk_wait_read();                 // the image has been read: the epilogue may overwrite it
-                        mbar_arrive(bar_spill);
+                        mbar_arrive(B.spill);
                     }
                 }
             }
@@ -508,20 +555,25 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue warps =====================
-        const int q = warp & 3, hf = (warp - EPI_WARP0) >> 2;
+        const int q = warp & 3, cg = (warp - EPI_WARP0) >> 2;
         const int r = q * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t pf = 0, ps = 0;
-        int nprof = 0;
-        int n_arr = 0, n_spw = 0;          // a_ready arrivals made / spill completions consumed
+        uint32_t pf0 = 0, pf1 = 0, ps = 0;
+        int g = 0;                         // layer GEMMs issued so far (all roles count alike)
+        int n_arr = 0, n_spw = 0;          // complete a_ready arrivals made / spill completions consumed
         // the A image of an arrival may be overwritten only after the spill warp has read it
         auto spill_sync = [&]() {
             if (a.spill)
-                while (n_spw < n_arr) { mbar_wait(bar_spill, ps); ps ^= 1; ++n_spw; }
+                while (n_spw < n_arr) { mbar_wait(B.spill, ps); ps ^= 1; ++n_spw; }
+        };
+        auto arrive = [&](int p) {
+            tc_fence_before(); fence_proxy_async(); __syncwarp();
+            if (lane == 0) mbar_arrive(B.a + 8 * p);
         };
         const int H = c.H, d = c.d;
-        const int hch = (H + 31) >> 5, hper = (hch + 1) >> 1;
-        const int hc_lo = hf * hper, hc_hi = min(hch, hc_lo + hper);              // this thread's chunks of an H-wide row
+        const int hch = (H + 31) >> 5;
+        // chunk c (32 columns) of an H-wide row belongs to the column group (c % 4) % EPI_GROUPS
+        auto mine = [&](int ch) { return ((ch & 3) % EPI_GROUPS) == cg; };
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
             const Tile T = tile_of(c, a, t);
             const int u = T.u0 + r;
@@ -538,15 +590,43 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
             const unsigned gpath = (unsigned)(path + a.b.path_id_offset);
             float xr[MAX_D], xe[MAX_D];
             float tau = 0.f;
-            float res[MAX_D];
             unsigned rk = 0;
-            // ---------------- prologue ----------------
+            // tanh of my chunks of an H-wide fp32 row -> A image of GEMM `gg`; optionally the readout residual sums
+            auto stage_h_row = [&](const float* src, int gg, bool to_tmem, bool with_res) {
+                float res[MAX_D];
+#pragma unroll
+                for (int j = 0; j < MAX_D; ++j) res[j] = 0.f;
+                for (int ch = 0; ch < hch; ++ch) {
+                    if (!mine(ch)) continue;
+                    float h[32];
+                    load_row_chunk(src, ch * 32, H, h);
+                    if (to_tmem) tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(h));
+                    store_tanh_chunk(ablock_of(a_base, gg, ch >> 1), r, ch * 32, H, h);
+                    if (with_res) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (ch * 32 + j < H) res[j & 15] += h[j];     // column mod 16
+                    }
+                }
+                if (with_res) {
+                    fold_res(res, d);
+#pragma unroll
+                    for (int j = 0; j < MAX_D; ++j) if (j < d) atomicAdd(res_s + r * MAX_D + j, res[j]);
+                }
+            };
+            auto zero_res = [&]() {
+                if (cg == 0) {
+#pragma unroll
+                    for (int j = 0; j < MAX_D; ++j) res_s[r * MAX_D + j] = 0.f;
+                }
+                epi_bar_sync();
+            };
+            // ---------------- prologue: the A image of the tile's first GEMM ----------------
             spill_sync();
             if (a.mode == MODE_ENC) {
 #pragma unroll
                 for (int j = 0; j < MAX_D; ++j)
                     xr[j] = (valid && j < d) ? (sr < 0 ? __ldg(a.b.start_X + (size_t)path * d + j) : __ldg(a.b.X + (size_t)sr * d + j)) : 0.f;
-                if (hf == 0) {
+                if (cg == 0) {
                     store_aux_x(a_base, r, xr, d);
                     store_aux_time(a_base, r, 0.f, 0.f, 0);
                     if (valid && sr >= 0) a.row_unit[sr] = u;
@@ -559,180 +639,150 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                     xr[j] = (valid && j < d) ? (sr < 0 ? __ldg(a.b.start_X + (size_t)path * d + j) : __ldg(a.b.X + (size_t)sr * d + j)) : 0.f;
                 tau = (valid && sr >= 0) ? __ldg(a.b.jump_tau + __ldg(a.b.row_jump + sr)) : 0.f;
                 const float* hs = valid ? a.h_start + (size_t)u * H : nullptr;
-                for (int ch = hc_lo; ch < hc_hi; ++ch) {
-                    float h[32];
-                    load_row_chunk(hs, ch * 32, H, h);
-                    tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(h));
-                    if (valid && len == 0) {           // a unit without Euler steps (observation at t = 0)
+                stage_h_row(hs, g, true, false);
+                tmem_wait_st();
+                if (valid && len == 0) {               // a unit without Euler steps (observation at t = 0)
+                    for (int ch = 0; ch < hch; ++ch) {
+                        if (!mine(ch)) continue;
+                        float h[32];
+                        load_row_chunk(hs, ch * 32, H, h);
                         if (row >= 0 && a.h_before) store_row_chunk(a.h_before + (size_t)row * H, ch * 32, H, h);
                         if (flag) store_row_chunk(a.hT + (size_t)path * H, ch * 32, H, h);
                     }
-                    store_tanh_chunk(a_base, r, ch * 32, H, h);
                 }
-                tmem_wait_st();
-                if (hf == 0) {
+                if (cg == 0) {
                     store_aux_x(a_base, r, xr, d);
                     const float t0 = (valid && len > 0) ? __ldg(a.b.step_t + s0) : 0.f;
                     store_aux_time(a_base, r, tau, t0 - tau, c.curt);
                 }
                 rk = nj_row_key(c.seed_lo, c.seed_hi, gpath, (unsigned)s0);
             } else {
-#pragma unroll
-                for (int j = 0; j < MAX_D; ++j) res[j] = 0.f;
-                const float* hb = (valid && row >= 0) ? a.h_before + (size_t)row * H : nullptr;
-                for (int ch = hc_lo; ch < hc_hi; ++ch) {
-                    float h[32];
-                    load_row_chunk(hb, ch * 32, H, h);
-                    store_tanh_chunk(a_base, r, ch * 32, H, h);
-                    if (c.residual) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (ch * 32 + j < H) res[j & 15] += h[j];     // column mod 16
-                    }
-                }
-                fold_res(res, d);
-                if (hf == 1) {
-#pragma unroll
-                    for (int j = 0; j < MAX_D; ++j) res_s[r * MAX_D + j] = res[j];
-                }
+                zero_res();
+                stage_h_row((valid && row >= 0) ? a.h_before + (size_t)row * H : nullptr, g, false, c.residual != 0);
+                epi_bar_sync();                        // residual sums complete before a group-0 thread reads them
                 rk = (valid && row >= 0) ? nj_row_key(c.seed_lo, c.seed_hi, gpath, ev_jump(a, row, 0u)) : 0u;
             }
             if (T.reps == 0) continue;
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a);
-            ++n_arr;
+            arrive(0); arrive(1); ++n_arr;
             // ---------------- layers ----------------
             for (int rep = 0; rep < T.reps; ++rep) {
-                for (int l = 0; l < net.n; ++l) {
+                for (int l = 0; l < net.n; ++l, ++g) {
                     const WLayer& L = net.l[l];
                     const bool last = (l == net.n - 1);
-                    mbar_wait(bar_acc, pf); pf ^= 1;
-                    tc_fence_after();
-                    if (a.prof && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && nprof < 256) a.prof[4 * nprof + 2] = clock64();
-                    spill_sync();
-                    const int nch = (L.n16 + 31) >> 5, per = (nch + 1) >> 1;
-                    const int c_lo = hf * per, c_hi = min(nch, c_lo + per);
-                    if (!last) {
-                        const unsigned lk = L.drop ? nj_layer_key(rk, (unsigned)(netid * 16 + l + 1)) : 0u;
-                        for (int ch = c_lo; ch < c_hi; ++ch)
-                            epi_hidden_chunk(tlane, bias_s + l * MAX_W, ch * 32, L, c, lk, a_base, r);
-                    } else if (a.mode == MODE_ENC) {
-                        for (int ch = c_lo; ch < c_hi; ++ch) {
-                            uint32_t v[32];
-                            tmem_ld32(tlane + ch * 32, v);
-                            tmem_wait_ld();
-                            float e[32];
+                    const bool tile_done = last && rep + 1 == T.reps;
+                    const bool ro_chain1_end = a.mode == MODE_RO && last && rep == 0;
+                    const unsigned lk = (!last && L.drop) ? nj_layer_key(rk, (unsigned)(netid * 16 + l + 1)) : 0u;
+                    // ODE: per-step scalars of the last layer
+                    const int i = rep;
+                    const bool active = valid && i < len;
+                    const float dt = (a.mode == MODE_ODE && last && active) ? __ldg(a.b.step_dt + s0 + i) : 0.f;
+                    const bool more = i + 1 < T.reps;
+                    for (int p = 0; p < 2; ++p) {
+                        if (p == 0) { mbar_wait(B.acc, pf0); pf0 ^= 1; }
+                        else { mbar_wait(B.acc + 8, pf1); pf1 ^= 1; }
+                        tc_fence_after();
+                        if (p == 0 && a.prof && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && g < 256) a.prof[4 * g + 2] = clock64();
+                        if (p == 1) spill_sync();                 // half 1 overwrites K-blocks 0-1 of this GEMM's own A image
+                        const int ncols = min(128, L.n16 - 128 * p);              // <= 0: no such half
+                        const int nchp = ncols > 0 ? (ncols + 31) >> 5 : 0;
+                        for (int ch = cg; ch < nchp; ch += EPI_GROUPS) {
+                            const int c0 = 128 * p + 32 * ch;                     // first output column of the chunk
+                            const uint32_t tcol = tlane + (uint32_t)c0;
+                            if (!last) {
+                                epi_hidden_chunk(tcol - c0, bias_s + l * MAX_W, c0, L, c, lk, wblock_of(a_base, g, p, ch >> 1), r);
+                            } else if (a.mode == MODE_ENC) {
+                                uint32_t v[32];
+                                tmem_ld32(tcol, v);
+                                tmem_wait_ld();
+                                float e[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                e[j] = __uint_as_float(v[j]) + bias_s[l * MAX_W + ch * 32 + j];
-                                if (c.residual) e[j] += xe[j & 15];                       // case 1: x.repeat(1, H / d)
-                            }
-                            if (valid) store_row_chunk(a.h_start + (size_t)u * H, ch * 32, H, e);
-                        }
-                    } else if (a.mode == MODE_ODE) {
-                        const int i = rep;
-                        const bool active = valid && i < len;
-                        const float dt = active ? __ldg(a.b.step_dt + s0 + i) : 0.f;
-                        const bool more = i + 1 < T.reps;
-                        for (int ch = c_lo; ch < c_hi; ++ch) {
-                            uint32_t v[32];
-                            float h[32];
-                            tmem_ld32(tlane + ch * 32, v);
-                            tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(h));
-                            tmem_wait_ld();
-                            if (active) {
-                                if (a.h_hist) store_row_chunk(a.h_hist + ((size_t)(s0 + i) * a.b.B + path) * H, ch * 32, H, h);
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    h[j] = fmaf(dt, __uint_as_float(v[j]) + bias_s[l * MAX_W + ch * 32 + j], h[j]);
-                                if (i == len - 1) {
-                                    if (row >= 0 && a.h_before) store_row_chunk(a.h_before + (size_t)row * H, ch * 32, H, h);
-                                    if (flag) store_row_chunk(a.hT + (size_t)path * H, ch * 32, H, h);
+                                for (int j = 0; j < 32; ++j) {
+                                    e[j] = __uint_as_float(v[j]) + bias_s[l * MAX_W + c0 + j];
+                                    if (c.residual) e[j] += xe[j & 15];                       // case 1: x.repeat(1, H / d)
                                 }
-                            }
-                            // .sync.aligned: every lane of the warp stores (finished / padding rows write h back unchanged)
-                            tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(h));
-                            if (more) store_tanh_chunk(a_base, r, ch * 32, H, h);
-                        }
-                        tmem_wait_st();
-                        if (more) {
-                            if (hf == 0) {
-                                const float tn = (valid && i + 1 < len) ? __ldg(a.b.step_t + s0 + i + 1) : 0.f;
-                                store_aux_time(a_base, r, tau, tn - tau, c.curt);
-                            }
-                            rk = nj_row_key(c.seed_lo, c.seed_hi, gpath, (unsigned)(s0 + i + 1));
-                        }
-                    } else {
-                        // readout: y = acc + bias + residual (mean over the H / d chunks of h, or h itself when H == d)
-                        if (hf == 0 && c_lo < c_hi) {
-                            uint32_t v[32];
-                            tmem_ld32(tlane, v);
-                            tmem_wait_ld();
-                            const float rmul = c.residual ? 1.f / (float)(H / d) : 0.f;
-                            float y[MAX_D];
+                                if (valid) store_row_chunk(a.h_start + (size_t)u * H, c0, H, e);
+                            } else if (a.mode == MODE_ODE) {
+                                uint32_t v[32];
+                                float h[32];
+                                tmem_ld32(tcol, v);
+                                tmem_ld32(tlane + TMEM_H + c0, reinterpret_cast<uint32_t*>(h));
+                                tmem_wait_ld();
+                                if (active) {
+                                    if (a.h_hist) store_row_chunk(a.h_hist + ((size_t)(s0 + i) * a.b.B + path) * H, c0, H, h);
 #pragma unroll
-                            for (int j = 0; j < MAX_D; ++j)
-                                y[j] = __uint_as_float(v[j]) + bias_s[l * MAX_W + j] + rmul * (res[j] + res_s[r * MAX_D + j]);
-                            if (rep == 0) {
-#pragma unroll
-                                for (int j = 0; j < MAX_D; ++j) {
-                                    ybj_s[r * MAX_D + j] = y[j];
-                                    if (a.y_before && valid && row >= 0 && j < d) a.y_before[(size_t)row * d + j] = y[j];
-                                }
-                            } else if (valid && row >= 0) {
-                                float sa = 0.f, sb = 0.f;
-#pragma unroll
-                                for (int j = 0; j < MAX_D; ++j) {
-                                    if (j < d) {
-                                        if (a.y_after) a.y_after[(size_t)row * d + j] = y[j];
-                                        const float x = __ldg(a.b.X + (size_t)row * d + j), yb = ybj_s[r * MAX_D + j];
-                                        const float da = x - y[j], db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y[j]) : (yb - x);
-                                        sa = fmaf(da, da, sa); sb = fmaf(db, db, sb);
+                                    for (int j = 0; j < 32; ++j)
+                                        h[j] = fmaf(dt, __uint_as_float(v[j]) + bias_s[l * MAX_W + c0 + j], h[j]);
+                                    if (i == len - 1) {
+                                        if (row >= 0 && a.h_before) store_row_chunk(a.h_before + (size_t)row * H, c0, H, h);
+                                        if (flag) store_row_chunk(a.hT + (size_t)path * H, c0, H, h);
                                     }
                                 }
-                                if (a.get_loss) {
-                                    const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
-                                    const float sm = (c.loss_kind == NJODE_LOSS_STANDARD) ? (2.f * c.w * ra + 2.f * (1.f - c.w) * rb)
-                                                                                          : (c.w * ra + (1.f - c.w) * rb);
-                                    a.row_loss[row] = sm * sm / __ldg(a.b.n_obs_ot + path);
+                                // .sync.aligned: every lane of the warp stores (finished / padding rows write h back unchanged)
+                                tmem_st32(tlane + TMEM_H + c0, reinterpret_cast<const uint32_t*>(h));
+                                if (more) store_tanh_chunk(wblock_of(a_base, g, p, ch >> 1), r, c0, H, h);
+                            } else if (p == 0 && ch == 0) {
+                                // readout: y = acc + bias + residual (mean over the H / d chunks of h, or h itself when H == d)
+                                uint32_t v[32];
+                                tmem_ld32(tcol, v);
+                                tmem_wait_ld();
+                                const float rmul = c.residual ? 1.f / (float)(H / d) : 0.f;
+                                float y[MAX_D];
+#pragma unroll
+                                for (int j = 0; j < MAX_D; ++j)
+                                    y[j] = __uint_as_float(v[j]) + bias_s[l * MAX_W + j] + rmul * res_s[r * MAX_D + j];
+                                if (rep == 0) {
+#pragma unroll
+                                    for (int j = 0; j < MAX_D; ++j) {
+                                        ybj_s[r * MAX_D + j] = y[j];
+                                        if (a.y_before && valid && row >= 0 && j < d) a.y_before[(size_t)row * d + j] = y[j];
+                                    }
+                                } else if (valid && row >= 0) {
+                                    float sa = 0.f, sb = 0.f;
+#pragma unroll
+                                    for (int j = 0; j < MAX_D; ++j) {
+                                        if (j < d) {
+                                            if (a.y_after) a.y_after[(size_t)row * d + j] = y[j];
+                                            const float x = __ldg(a.b.X + (size_t)row * d + j), yb = ybj_s[r * MAX_D + j];
+                                            const float da = x - y[j], db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y[j]) : (yb - x);
+                                            sa = fmaf(da, da, sa); sb = fmaf(db, db, sb);
+                                        }
+                                    }
+                                    if (a.get_loss) {
+                                        const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+                                        const float sm = (c.loss_kind == NJODE_LOSS_STANDARD) ? (2.f * c.w * ra + 2.f * (1.f - c.w) * rb)
+                                                                                              : (c.w * ra + (1.f - c.w) * rb);
+                                        a.row_loss[row] = sm * sm / __ldg(a.b.n_obs_ot + path);
+                                    }
                                 }
                             }
                         }
-                        if (rep == 0) {
-                            // second chain of the tile: Y = readout(h after the jump) with h = encoder output of the
-                            // unit that starts at this row
-                            epi_bar_sync();                       // res_s of chain 1 consumed by every row's hf-0 thread
-#pragma unroll
-                            for (int j = 0; j < MAX_D; ++j) res[j] = 0.f;
-                            const float* hs = (valid && row >= 0) ? a.h_start + (size_t)a.row_unit[row] * H : nullptr;
-                            for (int ch = hc_lo; ch < hc_hi; ++ch) {
-                                float h[32];
-                                load_row_chunk(hs, ch * 32, H, h);
-                                store_tanh_chunk(a_base, r, ch * 32, H, h);
-                                if (c.residual) {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) if (ch * 32 + j < H) res[j & 15] += h[j];
+                        if (p == 1) {
+                            if (a.mode == MODE_ODE && last) {
+                                tmem_wait_st();
+                                if (more) {
+                                    if (cg == 0) {
+                                        const float tn = (valid && i + 1 < len) ? __ldg(a.b.step_t + s0 + i + 1) : 0.f;
+                                        store_aux_time(a_base, r, tau, tn - tau, c.curt);
+                                    }
+                                    rk = nj_row_key(c.seed_lo, c.seed_hi, gpath, (unsigned)(s0 + i + 1));
                                 }
                             }
-                            fold_res(res, d);
-                            if (hf == 1) {
-#pragma unroll
-                                for (int j = 0; j < MAX_D; ++j) res_s[r * MAX_D + j] = res[j];
+                            if (ro_chain1_end) {
+                                // second chain of the tile: Y = readout(h after the jump), h = encoder output of the unit that
+                                // starts at this row.  All MMAs of this GEMM are complete: both block pairs may be written.
+                                epi_bar_sync();                       // chain 1's residual sums are consumed
+                                zero_res();
+                                stage_h_row((valid && row >= 0) ? a.h_start + (size_t)a.row_unit[row] * H : nullptr, g + 1, false, c.residual != 0);
+                                epi_bar_sync();
+                                rk = (valid && row >= 0) ? nj_row_key(c.seed_lo, c.seed_hi, gpath, ev_jump(a, row, 2u)) : 0u;
                             }
-                            rk = (valid && row >= 0) ? nj_row_key(c.seed_lo, c.seed_hi, gpath, ev_jump(a, row, 2u)) : 0u;
+                            if (a.prof && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && g < 256) a.prof[4 * g + 3] = clock64();
                         }
-                    }
-                    const bool tile_done = last && rep + 1 == T.reps;
-                    if (a.prof && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && nprof < 256) a.prof[4 * nprof + 3] = clock64();
-                    ++nprof;
-                    if (a.mode == MODE_RO) epi_bar_sync();        // res_s / ybj_s written before the hf-0 threads read them
-                    if (!tile_done) {
-                        tc_fence_before();
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_a);
-                        ++n_arr;
+                        if (!tile_done) {
+                            // chain 1 of the readout writes the next image only in its second phase: both arrivals then
+                            if (p == 0 && !ro_chain1_end) arrive(0);
+                            if (p == 1) { if (ro_chain1_end) arrive(0); arrive(1); ++n_arr; }
+                        }
                     }
                 }
             }
@@ -767,7 +817,7 @@ __device__ __forceinline__ void load_img_chunk(const unsigned char* img, int r, 
     }
 }
 // 32 fp32 gradients -> bf16 -> G image columns [c0, c0+32); columns >= n are written as 0
-__device__ __forceinline__ void store_g_chunk(uint32_t a_base, int r, int c0, int n, float* g) {
+__device__ __forceinline__ void store_g_chunk(uint32_t block, int r, int c0, int n, float* g) {
     if (c0 + 32 > n) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) g[j] = (c0 + j < n) ? g[j] : 0.f;
@@ -775,7 +825,7 @@ __device__ __forceinline__ void store_g_chunk(uint32_t a_base, int r, int c0, in
     uint32_t p[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) p[j] = pack_bf16(g[2 * j], g[2 * j + 1]);
-    store_a_chunk(a_base, r, c0, p);
+    store_a_chunk(block, r, c0 & 32, p);
 }
 // g[j] = acc[j] * act'(a_j) with the (warp-uniform) activation kind hoisted out of the element loop
 template <int ACT, bool DROP>
@@ -803,28 +853,14 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t a_base = sbase + SM_A, w_base = sbase + SM_W;
-    const uint32_t bar0 = sbase + SM_BAR;
-    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * NSTAGE, bar_acc = bar0 + 16 * NSTAGE, bar_a = bar_acc + 8;
-    const uint32_t bar_spill = bar_acc + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 24);
+    const Bars B = bars_of(sbase + SM_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM_SLOT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int netid = a.mode == MODE_ENC ? NJODE_NET_ENC : (a.mode == MODE_ODE ? NJODE_NET_ODE : NJODE_NET_RO);
     const WNet& net = c.net[netid];
     const int l_min = a.mode == MODE_ENC ? 1 : 0;          // the encoder input needs no gradient
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_a, EPI_THREADS / 32);
-        mbar_init(bar_spill, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    for (int i = threadIdx.x; i < A_BLOCKS * A_BLOCK_BYTES / 16; i += NUM_THREADS)
-        st_shared_v4(a_base + 16u * i, 0u, 0u, 0u, 0u);
+    cta_setup(B, tmem_slot, a_base, A_BLOCKS * A_BLOCK_BYTES);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -839,76 +875,89 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                 for (int rep = 0; rep < T.reps; ++rep)
                     for (int l = net.n - 1; l >= l_min; --l) {
                         const WLayer& L = net.l[l];
-                        const uint32_t bytes = (uint32_t)L.nt16 * 128u;
-                        for (int kb = 0; kb < L.kt_blocks; ++kb) {
-                            mbar_wait(bar_empty + 8 * stage, ph ^ 1);
-                            mbar_expect_tx(bar_full + 8 * stage, bytes);
-                            bulk_g2s(w_base + stage * STAGE_BYTES, a.wt + L.wt_off + (size_t)kb * bytes, bytes, bar_full + 8 * stage);
-                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                        const unsigned char* src = a.wt + L.wt_off;
+                        for (int p = 0; p * 128 < L.nt16; ++p) {
+                            const uint32_t bytes = (uint32_t)min(128, L.nt16 - 128 * p) * 128u;
+                            for (int kb = 0; kb < L.kt_blocks; ++kb) {
+                                mbar_wait(B.empty + 8 * stage, ph ^ 1);
+                                mbar_expect_tx(B.full + 8 * stage, bytes);
+                                bulk_g2s(w_base + stage * STAGE_BYTES, src, bytes, B.full + 8 * stage);
+                                src += bytes;
+                                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                            }
                         }
                     }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            int stage = 0; uint32_t ph = 0, pa = 0;
+            int stage = 0, g = 0; uint32_t ph = 0, pa0 = 0, pa1 = 0;
             for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
                 const Tile T = tile_of(c, a, t);
                 for (int rep = 0; rep < T.reps; ++rep)
-                    for (int l = net.n - 1; l >= 0; --l) {
+                    for (int l = net.n - 1; l >= 0; --l, ++g) {
                         const WLayer& L = net.l[l];
-                        mbar_wait(bar_a, pa); pa ^= 1;               // G_l written, accumulator drained
-                        if (l < l_min) continue;                     // spilled only
+                        mbar_wait(B.a, pa0); pa0 ^= 1;               // G_l K-blocks 0-1 written, TMEM half 0 drained
+                        if (l < l_min) { mbar_wait(B.a + 8, pa1); pa1 ^= 1; continue; }     // spilled only, no GEMM
                         tc_fence_after();
-                        const uint32_t idesc = make_idesc(L.nt16);
-                        for (int kb = 0; kb < L.kt_blocks; ++kb) {
-                            const int ksteps = (kb == L.kt_blocks - 1) ? L.kt_last_ksteps : 4;
-                            mbar_wait(bar_full + 8 * stage, ph);
-                            tc_fence_after();
-                            const uint32_t ab = a_base + (uint32_t)kb * A_BLOCK_BYTES;
-                            const uint32_t wb = w_base + (uint32_t)stage * STAGE_BYTES;
-                            for (int k = 0; k < ksteps; ++k)
-                                tc_mma(tmem, make_desc(ab + 32u * k), make_desc(wb + 32u * k), idesc, (kb | k) ? 1u : 0u);
-                            tc_commit(bar_empty + 8 * stage);
-                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                        bool got1 = false;
+                        for (int p = 0; p * 128 < L.nt16; ++p) {
+                            const uint32_t idesc = make_idesc(min(128, L.nt16 - 128 * p));
+                            for (int kb = 0; kb < L.kt_blocks; ++kb) {
+                                if (kb >= 2 && !got1) { mbar_wait(B.a + 8, pa1); pa1 ^= 1; got1 = true; tc_fence_after(); }
+                                const int ksteps = (kb == L.kt_blocks - 1) ? L.kt_last_ksteps : 4;
+                                mbar_wait(B.full + 8 * stage, ph);
+                                tc_fence_after();
+                                const uint32_t ab = ablock_of(a_base, g, kb);
+                                const uint32_t wb = w_base + (uint32_t)stage * STAGE_BYTES;
+                                for (int k = 0; k < ksteps; ++k)
+                                    tc_mma(tmem + 128u * p, make_desc(ab + 32u * k), make_desc(wb + 32u * k), idesc, (kb | k) ? 1u : 0u);
+                                tc_commit(B.empty + 8 * stage);
+                                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                            }
+                            if (p == 0 && !got1) { mbar_wait(B.a + 8, pa1); pa1 ^= 1; got1 = true; tc_fence_after(); }
+                            tc_commit(B.acc + 8 * p);
                         }
-                        tc_commit(bar_acc);
+                        if (L.nt16 <= 128) tc_commit(B.acc + 8);
                     }
             }
         }
     } else if (warp == 2) {
         // every G_l image -> its gradient record (read again by the dW pass)
         if (lane == 0) {
-            uint32_t pa = 0;
+            uint32_t pa1 = 0; int g = 0;
             for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
                 const Tile T = tile_of(c, a, t);
                 for (int rep = 0; rep < T.reps; ++rep) {
                     const int step = a.mode == MODE_ODE ? T.reps - 1 - rep : rep;
                     unsigned char* rec = a.gsp + record_of(a, t, step) * (size_t)c.g_rec[netid];
-                    for (int l = net.n - 1; l >= 0; --l) {
+                    for (int l = net.n - 1; l >= 0; --l, ++g) {
                         const WLayer& L = net.l[l];
-                        mbar_wait(bar_a, pa); pa ^= 1;
+                        mbar_wait(B.a + 8, pa1); pa1 ^= 1;
                         for (int kb = 0; kb < L.kt_blocks; ++kb)
-                            bulk_s2g(rec + L.g_off + (size_t)kb * A_BLOCK_BYTES, a_base + (uint32_t)kb * A_BLOCK_BYTES, A_BLOCK_BYTES);
+                            bulk_s2g(rec + L.g_off + (size_t)kb * A_BLOCK_BYTES, ablock_of(a_base, g, kb), A_BLOCK_BYTES);
                         bulk_commit();
                         bulk_wait_read();
-                        mbar_arrive(bar_spill);
+                        mbar_arrive(B.spill);
                     }
                 }
             }
             bulk_wait_all();
         }
     } else if (warp >= EPI_WARP0) {
-        const int q = warp & 3, hf = (warp - EPI_WARP0) >> 2;
+        const int q = warp & 3, cg = (warp - EPI_WARP0) >> 2;
         const int r = q * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t pf = 0, ps = 0;
-        int n_arr = 0, n_spw = 0;
-        auto spill_sync = [&]() { while (n_spw < n_arr) { mbar_wait(bar_spill, ps); ps ^= 1; ++n_spw; } };
-        auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(bar_a); ++n_arr; };
+        uint32_t pf0 = 0, pf1 = 0, ps = 0;
+        int g = 0, n_arr = 0, n_spw = 0;
+        auto spill_sync = [&]() { while (n_spw < n_arr) { mbar_wait(B.spill, ps); ps ^= 1; ++n_spw; } };
+        auto arrive = [&](int p) {
+            tc_fence_before(); fence_proxy_async(); __syncwarp();
+            if (lane == 0) mbar_arrive(B.a + 8 * p);
+        };
         const int H = c.H, d = c.d;
-        const int hch = (H + 31) >> 5, hper = (hch + 1) >> 1;
-        const int hc_lo = hf * hper, hc_hi = min(hch, hc_lo + hper);
+        const int hch = (H + 31) >> 5;
+        auto mine = [&](int ch) { return ((ch & 3) % EPI_GROUPS) == cg; };
         const float ks = c.keep_scale, inv_ks = c.keep_scale > 0.f ? 1.f / c.keep_scale : 0.f;
         const float gl = a.grad_loss ? __ldg(a.grad_loss) / (float)a.b.batch_size_norm : 0.f;
         const int Ln = net.n;
@@ -925,7 +974,7 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                 flag = (sc & NJODE_UNIT_WRITES_HT) ? 1 : 0;
                 sr = (sc & ~NJODE_UNIT_WRITES_HT) - 1;
             }
-            float gy[MAX_D];                     // BWD_RO: dL/dy of the current chain (both halves of a row hold it)
+            float gy[MAX_D];                     // BWD_RO: dL/dy of the current chain (every thread of the row holds it)
 #pragma unroll
             for (int j = 0; j < MAX_D; ++j) gy[j] = 0.f;
             if (a.mode == MODE_ODE) {
@@ -933,35 +982,38 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                 const float* src = nullptr;
                 if (valid && row >= 0) src = a.g_before + (size_t)row * H;
                 else if (valid && flag && a.grad_hT) src = a.grad_hT + (size_t)path * H;
-                for (int ch = hc_lo; ch < hc_hi; ++ch) {
-                    float g[32];
-                    load_row_chunk(src, ch * 32, H, g);
-                    tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(g));
+                for (int ch = 0; ch < hch; ++ch) {
+                    if (!mine(ch)) continue;
+                    float gv[32];
+                    load_row_chunk(src, ch * 32, H, gv);
+                    tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(gv));
                 }
                 tmem_wait_st();
             }
             for (int rep = 0; rep < T.reps; ++rep) {
                 const int step = a.mode == MODE_ODE ? T.reps - 1 - rep : rep;
                 const unsigned char* arec = a.act + record_of(a, t, step) * (size_t)c.act_rec[netid];
-                // ---------------- G_{L-1}: gradient of the chain's output ----------------
+                // ---------------- G_{L-1}: gradient of the chain's output = the A image of this step's first GEMM ----------------
                 spill_sync();
                 if (a.mode == MODE_ODE) {
                     const bool active = valid && step < len;
                     const float dt = active ? __ldg(a.b.step_dt + s0 + step) : 0.f;
-                    for (int ch = hc_lo; ch < hc_hi; ++ch) {
-                        float g[32];
-                        tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(g));
+                    for (int ch = 0; ch < hch; ++ch) {
+                        if (!mine(ch)) continue;
+                        float gv[32];
+                        tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(gv));
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) g[j] *= dt;                      // h += dt * f  (0 for finished / padding rows)
-                        store_g_chunk(a_base, r, ch * 32, H, g);
+                        for (int j = 0; j < 32; ++j) gv[j] *= dt;                     // h += dt * f  (0 for finished / padding rows)
+                        store_g_chunk(ablock_of(a_base, g, ch >> 1), r, ch * 32, H, gv);
                     }
                 } else if (a.mode == MODE_ENC) {
                     const float* src = valid ? a.g_start + (size_t)u * H : nullptr;
-                    for (int ch = hc_lo; ch < hc_hi; ++ch) {
-                        float g[32];
-                        load_row_chunk(src, ch * 32, H, g);
-                        store_g_chunk(a_base, r, ch * 32, H, g);
+                    for (int ch = 0; ch < hch; ++ch) {
+                        if (!mine(ch)) continue;
+                        float gv[32];
+                        load_row_chunk(src, ch * 32, H, gv);
+                        store_g_chunk(ablock_of(a_base, g, ch >> 1), r, ch * 32, H, gv);
                     }
                 } else {
                     // loss row (compute_loss / compute_loss_2, NJODE/models.py:71-126): chain 0 = Y_bj, chain 1 = Y
@@ -992,93 +1044,95 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
 #pragma unroll
                         for (int j = 0; j < MAX_D; ++j) gy[j] = 0.f;
                     }
-                    if (hf == 0) {
+                    if (cg == 0) {
                         uint32_t p[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) p[j] = pack_bf16(gy[2 * j], gy[2 * j + 1]);
-                        const uint32_t rowa = a_base + (uint32_t)r * 128u;
+                        const uint32_t rowa = ablock_of(a_base, g, 0) + (uint32_t)r * 128u;
                         st_shared_v4(rowa + ((uint32_t)(0 ^ (r & 7)) << 4), p[0], p[1], p[2], p[3]);
                         st_shared_v4(rowa + ((uint32_t)(1 ^ (r & 7)) << 4), p[4], p[5], p[6], p[7]);
                     }
                 }
-                arrive_a();
+                arrive(0); arrive(1); ++n_arr;
                 // ---------------- layers, last to first ----------------
-                for (int l = Ln - 1; l >= 0; --l) {
+                for (int l = Ln - 1; l >= 0; --l, ++g) {
                     const WLayer& L = net.l[l];
-                    if (l < l_min) break;
-                    // this layer's input image A_l (forward spill): prefetched before waiting for the MMAs
-                    const int ncols = L.nt;                                   // gradient width = main inputs of layer l
-                    const int nch = (L.nt16 + 31) >> 5, per = (nch + 1) >> 1;
-                    const int c_lo = hf * per, c_hi = min(nch, c_lo + per);
-                    uint32_t av[2][16];                                       // two chunks in flight
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        if (c_lo + k < c_hi) load_img_chunk(arec + L.act_off, r, (c_lo + k) * 32, av[k]);
-                    mbar_wait(bar_acc, pf); pf ^= 1;
-                    tc_fence_after();
-                    spill_sync();
+                    if (l < l_min) continue;                                 // G_0 of the encoder chain is only spilled (counts as a GEMM slot)
+                    const int ncol = L.nt;                                    // gradient width = main inputs of layer l
                     const WLayer& Lp = net.l[l > 0 ? l - 1 : 0];             // layer whose activation A_l is
+                    // my chunks of this layer's input image A_l (forward spill), one per output half: prefetched before the
+                    // accumulator waits
+                    uint32_t av[2][16];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int ch = c_lo + k;
-                        if (ch < c_hi) {
+                    for (int p = 0; p < 2; ++p) {
+                        const int c0 = 128 * p + 32 * cg;
+                        if (EPI_GROUPS == 4 && c0 < L.nt16) load_img_chunk(arec + L.act_off, r, c0, av[p]);
+                    }
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        if (p == 0) { mbar_wait(B.acc, pf0); pf0 ^= 1; }
+                        else { mbar_wait(B.acc + 8, pf1); pf1 ^= 1; }
+                        tc_fence_after();
+                        if (p == 1) spill_sync();
+                        const int ncols = min(128, L.nt16 - 128 * p);
+                        const int nchp = ncols > 0 ? (ncols + 31) >> 5 : 0;
+                        for (int ch = cg; ch < nchp; ch += EPI_GROUPS) {
+                            const int c0 = 128 * p + 32 * ch;
                             uint32_t v[32];
-                            float g[32];
-                            tmem_ld32(tlane + ch * 32, v);
-                            if (l == 0 && a.mode == MODE_ODE) tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(g));
+                            float gv[32];
+                            if (EPI_GROUPS != 4) load_img_chunk(arec + L.act_off, r, c0, av[p]);
+                            tmem_ld32(tlane + (uint32_t)c0, v);
+                            if (l == 0 && a.mode == MODE_ODE) tmem_ld32(tlane + TMEM_H + c0, reinterpret_cast<uint32_t*>(gv));
                             tmem_wait_ld();
                             if (l > 0) {
-                                apply_act_grad(v, av[k & 1], Lp.act, Lp.drop, ks, inv_ks, g);
-                                store_g_chunk(a_base, r, ch * 32, ncols, g);
-                            } else {
+                                apply_act_grad(v, av[p], Lp.act, Lp.drop, ks, inv_ks, gv);
+                                store_g_chunk(wblock_of(a_base, g, p, ch >> 1), r, c0, ncol, gv);
+                            } else if (a.mode == MODE_ODE) {
                                 // input of the net = tanh(h): d/dh = 1 - tanh(h)^2, tanh(h) from the spilled A_0
-                                float gi[32];
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
-                                    const uint32_t b16 = (j & 1) ? (av[k & 1][j >> 1] >> 16) : (av[k & 1][j >> 1] & 0xFFFFu);
+                                    const uint32_t b16 = (j & 1) ? (av[p][j >> 1] >> 16) : (av[p][j >> 1] & 0xFFFFu);
                                     const float th = __uint_as_float(b16 << 16);
-                                    gi[j] = __uint_as_float(v[j]) * (1.f - th * th);
+                                    gv[j] = fmaf(__uint_as_float(v[j]), 1.f - th * th, gv[j]);
                                 }
-                                if (a.mode == MODE_ODE) {
+                                tmem_st32(tlane + TMEM_H + c0, reinterpret_cast<const uint32_t*>(gv));
+                            } else {
+                                // readout residual (FFNN.forward, models.py:268-276): y[j] += mean_k h[k d + j]
+                                float ge[MAX_D];
+                                expand_x(gy, ge, d);
+                                const float rmul = c.residual ? 1.f / (float)(H / d) : 0.f;
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) g[j] += gi[j];
-                                    tmem_st32(tlane + TMEM_H + ch * 32, reinterpret_cast<const uint32_t*>(g));
-                                } else {
-                                    // readout residual (FFNN.forward, models.py:268-276): y[j] += mean_k h[k d + j]
-                                    if (c.residual) {
-                                        const float rmul = 1.f / (float)(H / d);
-                                        float ge[MAX_D];
-                                        expand_x(gy, ge, d);
-#pragma unroll
-                                        for (int j = 0; j < 32; ++j) gi[j] += rmul * ge[j & 15];
-                                    }
-                                    if (valid && row >= 0) {
-                                        float* dst = rep == 0 ? a.g_before + (size_t)row * H : a.g_start + (size_t)a.row_unit[row] * H;
-                                        store_row_chunk(dst, ch * 32, H, gi);
-                                    }
+                                for (int j = 0; j < 32; ++j) {
+                                    const uint32_t b16 = (j & 1) ? (av[p][j >> 1] >> 16) : (av[p][j >> 1] & 0xFFFFu);
+                                    const float th = __uint_as_float(b16 << 16);
+                                    gv[j] = __uint_as_float(v[j]) * (1.f - th * th) + rmul * ge[j & 15];
+                                }
+                                if (valid && row >= 0) {
+                                    float* dst = rep == 0 ? a.g_before + (size_t)row * H : a.g_start + (size_t)a.row_unit[row] * H;
+                                    store_row_chunk(dst, c0, H, gv);
                                 }
                             }
-                            if (k + 2 < 4 && ch + 2 < c_hi) load_img_chunk(arec + L.act_off, r, (ch + 2) * 32, av[k & 1]);
                         }
+                        if (l == 0 && a.mode == MODE_ODE && p == 1) tmem_wait_st();
+                        if (l > 0) { arrive(p); if (p == 1) ++n_arr; }        // G_{l-1} is the next GEMM's operand (or only spilled)
                     }
-                    if (l == 0 && a.mode == MODE_ODE) tmem_wait_st();
-                    if (l > 0) arrive_a();          // G_{l-1} is the next GEMM's operand (or, for l-1 < l_min, only spilled)
                 }
             }
             if (a.mode == MODE_ODE) {
                 // dL/dh_start[u] = adjoint at the start of the unit (+ the readout-after-jump part written by BWD_RO);
                 // every lane executes the (warp-collective) TMEM load
-                for (int ch = hc_lo; ch < hc_hi; ++ch) {
-                    float g[32], o[32];
-                    tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(g));
+                for (int ch = 0; ch < hch; ++ch) {
+                    if (!mine(ch)) continue;
+                    float gv[32], o[32];
+                    tmem_ld32(tlane + TMEM_H + ch * 32, reinterpret_cast<uint32_t*>(gv));
                     tmem_wait_ld();
                     if (valid) {
                         if (sr >= 0) {
                             load_row_chunk(a.g_start + (size_t)u * H, ch * 32, H, o);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) g[j] += o[j];
+                            for (int j = 0; j < 32; ++j) gv[j] += o[j];
                         }
-                        store_row_chunk(a.g_start + (size_t)u * H, ch * 32, H, g);
+                        store_row_chunk(a.g_start + (size_t)u * H, ch * 32, H, gv);
                     }
                 }
             }
@@ -1092,7 +1146,6 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
     }
 }
 
-
 // ================================================================================================
 // dW pass: dW_l[n x k] = sum over records of G_l^T[n x 128] . A_l[128 x k], db_l = column sums of G_l.
 // The spilled images are [64-column block][128 rows x 128 B] SWIZZLE_128B tiles; read as MN-major operands
@@ -1102,6 +1155,9 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
 // contiguous share of the net's records; half records (64 units = 4 K-steps) stream through a 3-stage ring.
 // ================================================================================================
 struct DwItem { int net, layer, part, j, J, slot; };
+constexpr int DW_NSTAGE = 3;
+constexpr int DW_THREADS = 384;                   // producer, MMA, 2 idle, 8 bias / write-out warps
+constexpr int DW_EPI_WARPS = 8;
 constexpr int DW_STAGE_BYTES = 65536;             // [4 G half-blocks][4 A half-blocks] of 8 KB
 constexpr int DW_HALF_BLOCK = 8192;
 
@@ -1115,8 +1171,8 @@ __device__ __forceinline__ void wide_dw_cta(const WCfg& c, const WArgs& a, const
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + SM_BAR;
-    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * NSTAGE, bar_acc = bar0 + 16 * NSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 24);
+    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * DW_NSTAGE, bar_acc = bar0 + 16 * DW_NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM_SLOT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const DwItem it = item;
     const WLayer& L = c.net[it.net].l[it.layer];
@@ -1134,7 +1190,7 @@ __device__ __forceinline__ void wide_dw_cta(const WCfg& c, const WArgs& a, const
     const size_t arec = (size_t)c.act_rec[it.net], grec = (size_t)c.g_rec[it.net];
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + EPI_THREADS / 32); }
+        for (int s = 0; s < DW_NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + DW_EPI_WARPS); }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1142,7 +1198,7 @@ __device__ __forceinline__ void wide_dw_cta(const WCfg& c, const WArgs& a, const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < NSTAGE * DW_STAGE_BYTES / 16; i += NUM_THREADS)
+    for (int i = threadIdx.x; i < DW_NSTAGE * DW_STAGE_BYTES / 16; i += DW_THREADS)
         st_shared_v4(sbase + 16u * i, 0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
@@ -1164,7 +1220,7 @@ __device__ __forceinline__ void wide_dw_cta(const WCfg& c, const WArgs& a, const
                     bulk_g2s(sb + kb * DW_HALF_BLOCK, gi + (size_t)kb * A_BLOCK_BYTES, DW_HALF_BLOCK, bar_full + 8 * stage);
                 for (int b = 0; b < nb; ++b)
                     bulk_g2s(sb + 4 * DW_HALF_BLOCK + b * DW_HALF_BLOCK, ai + (size_t)b * A_BLOCK_BYTES, DW_HALF_BLOCK, bar_full + 8 * stage);
-                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                if (++stage == DW_NSTAGE) { stage = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -1180,7 +1236,7 @@ __device__ __forceinline__ void wide_dw_cta(const WCfg& c, const WArgs& a, const
                         tc_mma(tmem + (uint32_t)mh * 256u, make_desc_mn(sb + (uint32_t)mh * 2 * DW_HALF_BLOCK + 2048u * k),
                                make_desc_mn(sb + 4 * DW_HALF_BLOCK + 2048u * k), idesc, (hidx | k) ? 1u : 0u);
                 tc_commit(bar_empty + 8 * stage);
-                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                if (++stage == DW_NSTAGE) { stage = 0; ph ^= 1; }
             }
             tc_commit(bar_acc);
         }
@@ -1203,7 +1259,7 @@ __device__ __forceinline__ void wide_dw_cta(const WCfg& c, const WArgs& a, const
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
-                if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
+                if (++stage == DW_NSTAGE) { stage = 0; ph ^= 1; }
             }
         }
         float* part = a.dw_part + (size_t)it.slot * (256 * 256);

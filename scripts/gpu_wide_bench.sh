@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_wide.py -x -q 2>&1 | tail -4
-for w in bs_scaled_d16_h256 bs_scaled_d16_h256_small; do
-timeout 400 python bench.py --steps 5 --warmup 3 --workload $w --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; tail -3 gpurun_out/bench_$w.err | grep -v Warn; python - <<PY
+for w in bs_scaled_d16_h256_small bs_scaled_d16_h256; do
+timeout 400 python bench.py --steps 5 --warmup 3 --workload $w --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; tail -3 gpurun_out/bench_$w.err | grep -v -i warn | grep -v "return float"; python - <<PY
 import json
 try:
     d=json.load(open("gpurun_out/bench_$w.json")); r=d["roofline"]
