@@ -139,15 +139,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
-// bounded spin: a protocol error traps (with the barrier's offset) instead of hanging the device
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// bounded spin: a protocol error traps (with the barrier's offset) instead of hanging the device.  `sleep_ns` > 0
+// backs the polling off: the single-thread roles (producer, MMA issuer, spill) share their scheduler with an
+// epilogue warp and must not take its issue slots while they wait.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned sleep_ns = 0) {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && spins > (1u << 22)) {
-            printf("njode_wide: mbarrier wait timed out (cta %d thread %d barrier@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar & 127u, parity);
-            __trap();
+        if (!done) {
+            if (sleep_ns) __nanosleep(sleep_ns);
+            if (spins > (1u << 22)) {
+                printf("njode_wide: mbarrier wait timed out (cta %d thread %d barrier@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar & 255u, parity);
+                __trap();
+            }
         }
     }
 }
@@ -480,7 +485,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                         for (int p = 0; p * 128 < L.n16; ++p) {
                             const uint32_t bytes = (uint32_t)min(128, L.n16 - 128 * p) * 128u;
                             for (int kb = 0; kb < nkb; ++kb) {
-                                mbar_wait(B.empty + 8 * stage, ph ^ 1);
+                                mbar_wait(B.empty + 8 * stage, ph ^ 1, 128);
                                 mbar_expect_tx(B.full + 8 * stage, bytes);
                                 bulk_g2s(w_base + stage * STAGE_BYTES, src, bytes, B.full + 8 * stage);
                                 src += bytes;
@@ -501,7 +506,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                         const WLayer& L = net.l[l];
                         const int nkb = L.kb_main + L.has_aux;
                         bool got1 = false;
-                        mbar_wait(B.a, pa0); pa0 ^= 1;               // K-blocks 0-1 written, TMEM half 0 drained
+                        mbar_wait(B.a, pa0, 32); pa0 ^= 1;               // K-blocks 0-1 written, TMEM half 0 drained
                         tc_fence_after();
                         if (a.prof && blockIdx.x == 0 && g < 256) a.prof[4 * g] = clock64();
                         for (int p = 0; p * 128 < L.n16; ++p) {
@@ -509,11 +514,11 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                             for (int kb = 0; kb < nkb; ++kb) {
                                 const bool aux = kb >= L.kb_main;
                                 if ((aux || kb >= 2) && !got1) {     // K-blocks 2-3 / the auxiliary block, TMEM half 1 drained
-                                    mbar_wait(B.a + 8, pa1); pa1 ^= 1; got1 = true;
+                                    mbar_wait(B.a + 8, pa1, 32); pa1 ^= 1; got1 = true;
                                     tc_fence_after();
                                 }
                                 const int ksteps = aux ? L.aux_ksteps : 4;
-                                mbar_wait(B.full + 8 * stage, ph);
+                                mbar_wait(B.full + 8 * stage, ph, 32);
                                 tc_fence_after();
                                 const uint32_t ab = aux ? a_base + AUX_BLOCK * A_BLOCK_BYTES : ablock_of(a_base, g, kb);
                                 const uint32_t wb = w_base + (uint32_t)stage * STAGE_BYTES;
@@ -522,7 +527,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                                 tc_commit(B.empty + 8 * stage);      // stage free once these MMAs have read it
                                 if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
                             }
-                            if (p == 0 && !got1) { mbar_wait(B.a + 8, pa1); pa1 ^= 1; got1 = true; tc_fence_after(); }
+                            if (p == 0 && !got1) { mbar_wait(B.a + 8, pa1, 32); pa1 ^= 1; got1 = true; tc_fence_after(); }
                             tc_commit(B.acc + 8 * p);                // output half p complete
                         }
                         if (L.n16 <= 128) tc_commit(B.acc + 8);      // no second half: keep the barrier phases in step
@@ -540,7 +545,7 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                     unsigned char* rec = a.act + record_of(a, t, rep) * (size_t)c.act_rec[netid];
                     for (int l = 0; l < net.n; ++l, ++g) {
                         const WLayer& L = net.l[l];
-                        mbar_wait(B.a + 8, pa1); pa1 ^= 1;           // the whole image is written (half 1 arrives last)
+                        mbar_wait(B.a + 8, pa1, 128); pa1 ^= 1;      // the whole image is written (half 1 arrives last)
                         for (int kb = 0; kb < L.kb_main; ++kb)
                             bulk_s2g(rec + L.act_off + (size_t)kb * A_BLOCK_BYTES, ablock_of(a_base, g, kb), A_BLOCK_BYTES);
                         if (L.has_aux)
@@ -678,8 +683,8 @@ __device__ __forceinline__ void wide_cta(const WCfg& c, const WArgs& a, unsigned
                     const float dt = (a.mode == MODE_ODE && last && active) ? __ldg(a.b.step_dt + s0 + i) : 0.f;
                     const bool more = i + 1 < T.reps;
                     for (int p = 0; p < 2; ++p) {
-                        if (p == 0) { mbar_wait(B.acc, pf0); pf0 ^= 1; }
-                        else { mbar_wait(B.acc + 8, pf1); pf1 ^= 1; }
+                        if (p == 0) { mbar_wait(B.acc, pf0, 32); pf0 ^= 1; }
+                        else { mbar_wait(B.acc + 8, pf1, 32); pf1 ^= 1; }
                         tc_fence_after();
                         if (p == 0 && a.prof && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32 && g < 256) a.prof[4 * g + 2] = clock64();
                         if (p == 1) spill_sync();                 // half 1 overwrites K-blocks 0-1 of this GEMM's own A image
@@ -879,7 +884,7 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                         for (int p = 0; p * 128 < L.nt16; ++p) {
                             const uint32_t bytes = (uint32_t)min(128, L.nt16 - 128 * p) * 128u;
                             for (int kb = 0; kb < L.kt_blocks; ++kb) {
-                                mbar_wait(B.empty + 8 * stage, ph ^ 1);
+                                mbar_wait(B.empty + 8 * stage, ph ^ 1, 128);
                                 mbar_expect_tx(B.full + 8 * stage, bytes);
                                 bulk_g2s(w_base + stage * STAGE_BYTES, src, bytes, B.full + 8 * stage);
                                 src += bytes;
@@ -897,16 +902,16 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                 for (int rep = 0; rep < T.reps; ++rep)
                     for (int l = net.n - 1; l >= 0; --l, ++g) {
                         const WLayer& L = net.l[l];
-                        mbar_wait(B.a, pa0); pa0 ^= 1;               // G_l K-blocks 0-1 written, TMEM half 0 drained
-                        if (l < l_min) { mbar_wait(B.a + 8, pa1); pa1 ^= 1; continue; }     // spilled only, no GEMM
+                        mbar_wait(B.a, pa0, 32); pa0 ^= 1;               // G_l K-blocks 0-1 written, TMEM half 0 drained
+                        if (l < l_min) { mbar_wait(B.a + 8, pa1, 32); pa1 ^= 1; continue; }     // spilled only, no GEMM
                         tc_fence_after();
                         bool got1 = false;
                         for (int p = 0; p * 128 < L.nt16; ++p) {
                             const uint32_t idesc = make_idesc(min(128, L.nt16 - 128 * p));
                             for (int kb = 0; kb < L.kt_blocks; ++kb) {
-                                if (kb >= 2 && !got1) { mbar_wait(B.a + 8, pa1); pa1 ^= 1; got1 = true; tc_fence_after(); }
+                                if (kb >= 2 && !got1) { mbar_wait(B.a + 8, pa1, 32); pa1 ^= 1; got1 = true; tc_fence_after(); }
                                 const int ksteps = (kb == L.kt_blocks - 1) ? L.kt_last_ksteps : 4;
-                                mbar_wait(B.full + 8 * stage, ph);
+                                mbar_wait(B.full + 8 * stage, ph, 32);
                                 tc_fence_after();
                                 const uint32_t ab = ablock_of(a_base, g, kb);
                                 const uint32_t wb = w_base + (uint32_t)stage * STAGE_BYTES;
@@ -915,7 +920,7 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                                 tc_commit(B.empty + 8 * stage);
                                 if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
                             }
-                            if (p == 0 && !got1) { mbar_wait(B.a + 8, pa1); pa1 ^= 1; got1 = true; tc_fence_after(); }
+                            if (p == 0 && !got1) { mbar_wait(B.a + 8, pa1, 32); pa1 ^= 1; got1 = true; tc_fence_after(); }
                             tc_commit(B.acc + 8 * p);
                         }
                         if (L.nt16 <= 128) tc_commit(B.acc + 8);
@@ -933,7 +938,7 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                     unsigned char* rec = a.gsp + record_of(a, t, step) * (size_t)c.g_rec[netid];
                     for (int l = net.n - 1; l >= 0; --l, ++g) {
                         const WLayer& L = net.l[l];
-                        mbar_wait(B.a + 8, pa1); pa1 ^= 1;
+                        mbar_wait(B.a + 8, pa1, 128); pa1 ^= 1;
                         for (int kb = 0; kb < L.kt_blocks; ++kb)
                             bulk_s2g(rec + L.g_off + (size_t)kb * A_BLOCK_BYTES, ablock_of(a_base, g, kb), A_BLOCK_BYTES);
                         bulk_commit();
@@ -1070,8 +1075,8 @@ __device__ __forceinline__ void wide_bwd_cta(const WCfg& c, const WArgs& a, unsi
                     }
 #pragma unroll
                     for (int p = 0; p < 2; ++p) {
-                        if (p == 0) { mbar_wait(B.acc, pf0); pf0 ^= 1; }
-                        else { mbar_wait(B.acc + 8, pf1); pf1 ^= 1; }
+                        if (p == 0) { mbar_wait(B.acc, pf0, 32); pf0 ^= 1; }
+                        else { mbar_wait(B.acc + 8, pf1, 32); pf1 ^= 1; }
                         tc_fence_after();
                         if (p == 1) spill_sync();
                         const int ncols = min(128, L.nt16 - 128 * p);
