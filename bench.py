@@ -55,6 +55,19 @@ WORKLOADS = {
                                cpu_sample_steps=100, device_data=True),
     "bs_scaled_d16_h256_small": dict(sde="BlackScholes", paths=4096, steps=100, d=16, H=256, width=256,
                                      layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128, device_data=True),
+    # BASELINE.json configs[3]: PhysioNet-shaped synthetic irregular series: 41 masked features,
+    # 3000-tick grid (delta_t = 0.016/48, T = 1 + 1e-12), 40..110 stamps per record, Bernoulli(0.12) feature masks,
+    # float32 times, start_X = 0; masked model d = H = 41, 2x50 nets.  B = 50 is the reference's batch size
+    # (parallel_train.py:656); the 2000-record variant shows the throughput of the generic masked kernels.
+    "physionet_synth_b50": dict(sde="physionet_synth", paths=50, steps=3000, d=41, H=41, width=50, layers=2,
+                                obs_perc=None, dropout=0.1, masked=True, cpu_sample_paths=50),
+    "physionet_synth_b2000": dict(sde="physionet_synth", paths=2000, steps=3000, d=41, H=41, width=50, layers=2,
+                                  obs_perc=None, dropout=0.1, masked=True, cpu_sample_paths=50),
+    # BASELINE.json configs[2] (ii): Heston without Feller condition (parallel_train.py:525-537), demo nets, batch sweep
+    "hestonwof_demo_1k": dict(sde="HestonWOFeller", paths=1000, steps=100, d=1, H=10, width=50, layers=2,
+                              obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
+    "hestonwof_demo_20k": dict(sde="HestonWOFeller", paths=20000, steps=100, d=1, H=10, width=50, layers=2,
+                               obs_perc=0.1, dropout=0.1, cpu_sample_paths=2000),
     # BASELINE.json configs[2] (i): combined-dataset nets (2x100 tanh), batch 5000
     "bs_2x100_5k": dict(sde="BlackScholes", paths=5000, steps=100, d=1, H=10, width=100, layers=2,
                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
@@ -94,6 +107,14 @@ def synth_paths(sde, n_paths, steps, d, seed, first_path=0):
                 dZ = (p["correlation"] * n1 + np.sqrt(1 - p["correlation"] ** 2) * n2) * np.sqrt(dt)
                 v = v - p["speed"] * (v - p["mean"]) * dt + p["volatility"] * np.sqrt(np.abs(v)) * dZ
                 S = S + p["drift"] * S * dt + np.sqrt(np.abs(v)) * S * dW
+            elif sde == "HestonWOFeller":        # NJODE/stock_model.py:288-335 (drift 2, volatility 3, mean 1, speed 2, v0 0.5)
+                if k == 0:
+                    v = np.full((hi - lo, d), 0.5)
+                dW = n1 * np.sqrt(dt)
+                dZ = (p["correlation"] * n1 + np.sqrt(1 - p["correlation"] ** 2) * n2) * np.sqrt(dt)
+                vp = np.maximum(v, 0.0)
+                S = S * np.exp((p["drift"] - 0.5 * vp) * dt + np.sqrt(vp) * dW)
+                v = v + 2.0 * (1.0 - v) * dt + 3.0 * np.sqrt(vp) * dZ
             else:
                 raise ValueError(sde)
             out[sl, :, k + 1] = S
@@ -102,6 +123,8 @@ def synth_paths(sde, n_paths, steps, d, seed, first_path=0):
 
 def synth_batch(wl, seed, first_path, n_paths):
     from njode_b200 import data_utils
+    if wl["sde"] == "physionet_synth":
+        return synth_batch_physio(wl, seed, first_path, n_paths)
     paths, dt = synth_paths(wl["sde"], n_paths, wl["steps"], wl["d"], seed, first_path)
     blk = 1024
     obs = np.empty((n_paths, wl["steps"] + 1), dtype=np.int64)
@@ -114,6 +137,34 @@ def synth_batch(wl, seed, first_path, n_paths):
     nb_obs = obs[:, 1:].sum(axis=1)
     b = data_utils.collate_paths(paths, obs, nb_obs, dt)
     return b, dt
+
+
+def synth_batch_physio(wl, seed, first_path, n_paths):
+    """PhysioNet-shaped synthetic records in the masked collate contract (latent_ODE/physionet_LODE.py:428-544 flavour):
+    float32 ``times`` = union of the records' ticks, rows = (time, record) pairs ordered time-major, ``M`` = feature masks."""
+    import torch
+    d, grid = wl["d"], wl["steps"]
+    rows = []                                          # (tick, record, values, mask)
+    for p_ in range(n_paths):
+        rng = np.random.default_rng([seed, first_path + p_])
+        n_st = int(rng.integers(40, 111))
+        ticks = np.concatenate(([0], 1 + np.sort(rng.choice(grid - 1, size=n_st, replace=False))))
+        m = rng.random((len(ticks), d)) < 0.12
+        m[0, :5] = True
+        empty = ~m.any(axis=1)
+        m[empty, rng.integers(d, size=int(empty.sum()))] = True
+        x = rng.random((len(ticks), d)) * m
+        rows.append((ticks, np.full(len(ticks), p_), x, m))
+    ticks = np.concatenate([r[0] for r in rows]); rec = np.concatenate([r[1] for r in rows])
+    X = np.concatenate([r[2] for r in rows]).astype(np.float32); M = np.concatenate([r[3] for r in rows]).astype(np.float32)
+    order = np.lexsort((rec, ticks))
+    ticks, rec, X, M = ticks[order], rec[order], X[order], M[order]
+    ut, counts = np.unique(ticks, return_counts=True)
+    times = (ut.astype(np.float32) * np.float32(0.016)) / np.float32(48.0)
+    batch = {"times": times.astype(np.float32), "time_ptr": np.concatenate(([0], np.cumsum(counts))),
+             "obs_idx": torch.from_numpy(rec.astype(np.int64)), "X": torch.from_numpy(X), "M": torch.from_numpy(M),
+             "start_X": torch.zeros(n_paths, d), "n_obs_ot": torch.from_numpy(np.bincount(rec, minlength=n_paths).astype(np.int64))}
+    return batch, 0.016 / 48
 
 
 def synth_batch_device(wl, seed, first_path, n_paths, dev):
@@ -134,7 +185,13 @@ def model_cfg(wl):
     nn_desc = [[wl["width"], "tanh"]] * wl["layers"]
     return dict(input_size=wl["d"], hidden_size=wl["H"], output_size=wl["d"], ode_nn=nn_desc,
                 readout_nn=nn_desc, enc_nn=nn_desc, use_rnn=False, bias=True,
-                dropout_rate=wl["dropout"], solver="euler", weight=0.5, weight_decay=1.0, options={})
+                dropout_rate=wl["dropout"], solver="euler", weight=0.5, weight_decay=1.0,
+                options={"masked": True} if wl.get("masked") else {})
+
+
+def horizon(wl):
+    """T passed to NJODE.forward (physionet_train.py:192-193 uses 1 + 1e-12)"""
+    return 1.0 + 1e-12 if wl.get("masked") else SDE_PARAMS["maturity"]
 
 
 def flops_per_unit(wl):
@@ -143,7 +200,7 @@ def flops_per_unit(wl):
     d, H, W, L = wl["d"], wl["H"], wl["width"], wl["layers"]
     inf = d + H + 2
     F_ode = 2 * (inf * W + (L - 1) * W * W + W * H)
-    F_enc = 2 * (d * W + (L - 1) * W * W + W * H)
+    F_enc = 2 * ((2 * d if wl.get("masked") else d) * W + (L - 1) * W * W + W * H)
     F_ro = 2 * (H * W + (L - 1) * W * W + W * d)
     return F_ode, F_enc, F_ro
 
@@ -218,10 +275,10 @@ def cpu_port_step_fn(wl, seed, threads):
     ocfg = orc.Config(**cfg)
     sd = orc.init_state_dict(ocfg, seed=0)
     S = len(__import__("njode_b200.schedule", fromlist=["x"]).build_schedule(
-        batch["times"], dt, 1.0, False, False).step_dt)
+        batch["times"], dt, horizon(wl), False, False).step_dt)
 
     def step():
-        orc.loss_and_grads(ocfg, sd, batch, dt, 1.0, dropout_seed="native")
+        orc.loss_and_grads(ocfg, sd, batch, dt, horizon(wl), dropout_seed="native")
     sample = "%d of the workload's paths x %d Euler steps, fwd+bwd, train mode (aten dropout), %d threads" % (
         n, S, threads)
     return step, n * S, sample
@@ -289,7 +346,7 @@ def run_b200(args, wl_name, wl):
         batch, dt = synth_batch(wl, 1234, first, B)
     # the Euler grid is batch-global (NJODE/models.py:430-439): all ranks use the union of times.
     # On the regular grid with >= 20k paths per rank every grid time is observed on every rank.
-    T = SDE_PARAMS["maturity"]
+    T = horizon(wl)
     torch.manual_seed(0)
     model = models.NJODE(**model_cfg(wl)).to(dev)
     model.train()
@@ -310,7 +367,8 @@ def run_b200(args, wl_name, wl):
 
     # ---- resident-input arm -----------------------------------------------------------------
     model.output_device = "cuda"
-    pb = model.prepare_batch(*args_of(batch))
+    kw_of = lambda b: ({"M": b["M"]} if "M" in b else {})
+    pb = model.prepare_batch(*args_of(batch), **kw_of(batch))
     S = pb.sched.S
     units_per_step = B * S * world
 
@@ -374,9 +432,9 @@ def run_b200(args, wl_name, wl):
     def step_e2e(b):
         for p in params:
             p.grad = None
-        hT, loss = model(*args_of(b))
+        hT, loss = model(*args_of(b), **kw_of(b))
         loss.backward()
-        return float(loss)                # D2H of the step's result
+        return float(loss.detach())       # D2H of the step's result
 
     for j in range(2):
         step_e2e(host_batches[j % nb])
