@@ -19,12 +19,15 @@
 extern "C" {
 #endif
 
-#define NJODE_ABI_VERSION 3
+#define NJODE_ABI_VERSION 4
 #define NJODE_MAX_LINEAR 8          /* max number of Linear layers per network */
 
 enum { NJODE_ACT_NONE = 0, NJODE_ACT_TANH = 1, NJODE_ACT_RELU = 2 };
 enum { NJODE_LOSS_STANDARD = 0, NJODE_LOSS_EASY = 1 };     /* NJODE/models.py:129-132 LOSS_FUN_DICT */
-enum { NJODE_NET_ODE = 0, NJODE_NET_ENC = 1, NJODE_NET_RO = 2 };
+enum { NJODE_NET_ODE = 0, NJODE_NET_ENC = 1, NJODE_NET_RO = 2,
+       /* use_rnn=True only: the two affine maps of torch.nn.GRUCell (NJODE/models.py:202-217), one Linear each:
+        * weight_ih [3H, input] / bias_ih and weight_hh [3H, H] / bias_hh, gate order (r, z, n) */
+       NJODE_NET_GRU_IH = 3, NJODE_NET_GRU_HH = 4, NJODE_NUM_NETS = 5 };
 
 /* one feed-forward network as built by get_ffnn (NJODE/models.py:140-166): n_linear Linear layers,
  * an activation (+dropout) after every layer but the last.  Weights are nn.Linear layout
@@ -50,7 +53,10 @@ typedef struct njode_model {
     float   dropout_p;
     uint64_t dropout_seed;     /* counter-based masks keyed (seed, path, event, net, layer, neuron) */
     int64_t n_params;          /* floats in the flat parameter / gradient buffer */
-    njode_mlp_t net[3];        /* NJODE_NET_ODE / ENC / RO */
+    int32_t use_rnn;           /* use_rnn=True: the jump is h[i_obs] = GRUCell(tanh(X_obs), tanh(h[i_obs]))
+                                  (NJODE/models.py:202-217,460-461) instead of the encoder */
+    int32_t reserved1;
+    njode_mlp_t net[NJODE_NUM_NETS];   /* NJODE_NET_ODE / ENC / RO (/ GRU_IH / GRU_HH when use_rnn) */
 } njode_model_t;
 
 /* one batch in the reference's collate contract (NJODE/data_utils.py:311-315) plus the host-built

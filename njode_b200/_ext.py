@@ -26,7 +26,7 @@ class ModelT(C.Structure):
                 ("masked", C.c_int32), ("input_current_t", C.c_int32), ("loss_kind", C.c_int32),
                 ("residual", C.c_int32), ("training", C.c_int32), ("weight", C.c_float),
                 ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("n_params", C.c_int64),
-                ("net", MlpT * 3)]
+                ("use_rnn", C.c_int32), ("reserved1", C.c_int32), ("net", MlpT * 5)]
 
 
 class BatchT(C.Structure):
@@ -90,7 +90,7 @@ class Lib:
                                      C.c_void_p, C.c_void_p]
         for f in (d.njode_plan, d.njode_forward, d.njode_backward):
             f.restype = C.c_int
-        if d.njode_abi_version() != 3:
+        if d.njode_abi_version() != 4:
             raise NjodeError("njode_b200: ABI version mismatch in %s" % path)
         # tensor-core path (absent from the host simulation used by the CPU-only tests)
         self.has_wide = hasattr(d, "njode_wide_forward")

@@ -197,7 +197,7 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     a.y_after = saved ? saved->y_after : nullptr;
     a.get_loss = loss ? 1 : 0;
     a.n_tiles = pl.n_tiles;
-    nj_pack_kernel<<<3 * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.fwd, params, const_cast<float*>(a.image));
+    nj_pack_kernel<<<NJODE_NUM_NETS * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.fwd, params, const_cast<float*>(a.image));
     NJ_LAUNCHED(1 + (batch->n_units > 0 ? 1 : 0) + (loss ? 1 : 0));
     if (loss && batch->N > 0) NJ_CUDA(cudaMemsetAsync(a.row_loss, 0, (size_t)batch->N * 4, st));
     const bool tm = nj_timing_on();
@@ -236,7 +236,7 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     a.get_loss = 1;
     a.n_tiles = pl.n_tiles;
     // the image is rebuilt: backward may run after an optimizer that shares the workspace
-    nj_pack_kernel<<<3 * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.bwd, params, const_cast<float*>(a.image));
+    nj_pack_kernel<<<NJODE_NUM_NETS * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.bwd, params, const_cast<float*>(a.image));
     NJ_LAUNCHED(2 + (batch->n_units > 0 ? 1 : 0));
     int nparts = 0;
     const bool tm = nj_timing_on();
@@ -255,7 +255,7 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         }
     }
     if (tm) { cudaEventRecord(g_ev[3], st); g_ev_rec[1] = true; }
-    dim3 g((unsigned)std::max(1, std::min(64, (int)((model->n_params + 255) / 256))), 3 * NJODE_MAX_LINEAR);
+    dim3 g((unsigned)std::max(1, std::min(64, (int)((model->n_params + 255) / 256))), NJODE_NUM_NETS * NJODE_MAX_LINEAR);
     nj_grad_reduce_kernel<<<g, 256, 0, st>>>(pl.bwd, a.partials, nparts, grads);
     NJ_CUDA(cudaGetLastError());
     return 0;

@@ -60,19 +60,20 @@ struct NjNet {
 };
 
 struct NjCfg {
-    NjNet net[3];
+    NjNet net[NJODE_NUM_NETS];          // ODE, ENC, RO (, GRU_IH, GRU_HH when use_rnn; n = 0 otherwise)
     int d, H, dout, inf, enc_in;
-    int masked, curt, loss_kind, residual, training, has_drop;
+    int masked, curt, loss_kind, residual, training, has_drop, use_rnn;
     float w, keep_scale, one_minus_p;
     unsigned thr, seed_lo, seed_hi;
     int P, nt;
     int img_floats;
     int w_smem, dw_smem;
     // strides (floats) of the shared-memory matrices
-    int sIN, sACT, nACT, sOUT, sH, sD, sDO, sG;
+    int sIN, sACT, nACT, sOUT, sH, sD, sDO, sG, s3H;
     // offsets (floats) into dynamic shared memory
     int o_img, o_dimg, o_IN, o_ACT, o_OUT, o_H, o_LX, o_XI, o_YBJ, o_YY, o_XH, o_EE;
     int o_GOUT, o_GTMP, o_GA, o_GB, o_GH, o_GX, o_GYBJ, o_F, o_I;
+    int o_GI, o_GHH;                    // use_rnn: [P][s3H] gate buffers of the GRU jump
     int smem_floats_fwd, smem_floats_bwd;
 };
 
@@ -304,6 +305,7 @@ struct NjCta {
     const float* wimg;         // parameter image (shared or global)
     float* dimg;               // gradient image (shared or this CTA's global partial)
     float *IN, *ACT, *OUT, *Hs, *LX, *XI, *YBJ, *YY, *XH, *EE, *GOUT, *GTMP, *GA, *GB, *GH, *GX, *GYBJ, *F;
+    float *GI, *GHH;
     int *I, *CTL;
     int tid0, nt;              // nt: threads; (tid comes from NJ_THREADS)
 };
@@ -313,6 +315,7 @@ NJ_HD void nj_cta_bind(NjCta& t, const NjCfg& c, float* smem, bool bwd) {
     t.IN = smem + c.o_IN; t.ACT = smem + c.o_ACT; t.OUT = smem + c.o_OUT; t.Hs = smem + c.o_H;
     t.LX = smem + c.o_LX; t.XI = smem + c.o_XI; t.YBJ = smem + c.o_YBJ; t.YY = smem + c.o_YY;
     t.XH = smem + c.o_XH; t.EE = smem + c.o_EE; t.F = smem + c.o_F;
+    t.GI = smem + c.o_GI; t.GHH = smem + c.o_GHH;
     t.I = reinterpret_cast<int*>(smem + c.o_I); t.CTL = t.I + NJ_I_COUNT * c.P;
     t.GOUT = t.GTMP = t.GA = t.GB = t.GH = t.GX = t.GYBJ = nullptr;
     if (bwd) {
@@ -541,6 +544,57 @@ NJ_HD void nj_set_jump_keys(NjCta& t, const NjArgs& a, int nj, int which, int ti
     }
 }
 
+NJ_HD float nj_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+// GRU jump (use_rnn=True; NJODE/models.py:202-217 -> torch.nn.GRUCell, gate order r, z, n) for the compacted
+// rows [0, nj); h_old = XH[jr]:
+//   gi = W_ih tanh(X_obs) + b_ih ; gh = W_hh tanh(h_old) + b_hh
+//   r = sig(gi_r + gh_r), z = sig(gi_z + gh_z), n = tanh(gi_n + r gh_n), h' = (1 - z) n + z tanh(h_old)
+// leaves (r, z, n) in GI, tanh(h_old) in GHH[0, H), gh_n in GHH[2H, 3H), h' in EE, X_obs in XI
+NJ_HDN void nj_gru_forward(NjCta& t, const NjArgs& a, int nj) {
+    const NjCfg& c = *t.c;
+    const int H = c.H;
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * c.d; idx += t.nt) {
+            const int jr = idx / c.d, c_ = idx % c.d;
+            const float x = NJ_LDG(a.b.X + (size_t)NJ_IU(t, NJ_I_JROW, jr) * c.d + c_);
+            t.XI[jr * c.sD + c_] = x;
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(x);
+        }
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_GRU_IH, nj, false);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * 3 * H; idx += t.nt) {
+            const int jr = idx / (3 * H), k = idx % (3 * H);
+            t.GI[jr * c.s3H + k] = t.OUT[jr * c.sOUT + k];
+        }
+        for (int idx = tid; idx < nj * H; idx += t.nt) {
+            const int jr = idx / H, c_ = idx % H;
+            t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.XH[jr * c.sH + c_]);
+        }
+    }
+    NJ_SYNC();
+    nj_mlp_forward(t, NJODE_NET_GRU_HH, nj, false);
+    NJ_THREADS(tid, t.nt) {
+        for (int idx = tid; idx < nj * H; idx += t.nt) {
+            const int jr = idx / H, c_ = idx % H;
+            float* gi = t.GI + jr * c.s3H;
+            float* gh = t.GHH + jr * c.s3H;
+            const float* o = t.OUT + jr * c.sOUT;
+            const float hh = t.IN[(size_t)jr * c.sIN + c_];
+            const float r = nj_sigmoid(gi[c_] + o[c_]);
+            const float z = nj_sigmoid(gi[H + c_] + o[H + c_]);
+            const float ghn = o[2 * H + c_];
+            const float n = nj_tanh(fmaf(r, ghn, gi[2 * H + c_]));
+            gi[c_] = r; gi[H + c_] = z; gi[2 * H + c_] = n;
+            gh[c_] = hh; gh[2 * H + c_] = ghn;
+            t.EE[jr * c.sH + c_] = fmaf(z, hh - n, n);
+        }
+    }
+    NJ_SYNC();
+}
+
 // the jump of NJODE/models.py:449-489 for the compacted rows [0, nj)
 NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
     const NjCfg& c = *t.c;
@@ -568,6 +622,20 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
         }
     }
     NJ_SYNC();
+    if (c.use_rnn) {
+        // (d') h[i_obs] = GRUCell(tanh(X_obs), tanh(h[i_obs]))  (NJODE/models.py:460-461)
+        nj_gru_forward(t, a, nj);
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+                const int jr = idx / c.H, c_ = idx % c.H;
+                const float e = t.EE[jr * c.sH + c_];
+                t.Hs[NJ_IU(t, NJ_I_JMAP, jr) * c.sH + c_] = e;
+                t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(e);
+            }
+            nj_set_jump_keys(t, a, nj, 2, tid);
+        }
+        NJ_SYNC();
+    } else {
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
             const int jr = idx / c.d, c_ = idx % c.d;
@@ -598,6 +666,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
         nj_set_jump_keys(t, a, nj, 2, tid);
     }
     NJ_SYNC();
+    }
     nj_mlp_forward(t, NJODE_NET_RO, nj, false);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
@@ -790,7 +859,18 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
         }
     }
     NJ_SYNC();
-    // 2. encoder at the (imputed) observation -> E
+    // 2. encoder at the (imputed) observation -> E   (use_rnn: the GRU cell at (X_obs, h_before) -> E)
+    if (c.use_rnn) {
+        nj_gru_forward(t, a, nj);
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nj * c.H; idx += t.nt) {
+                const int jr = idx / c.H, c_ = idx % c.H;
+                t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.EE[jr * c.sH + c_]);
+            }
+            nj_set_jump_keys(t, a, nj, 2, tid);
+        }
+        NJ_SYNC();
+    } else {
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
             const int jr = idx / c.d, c_ = idx % c.d;
@@ -819,6 +899,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
         nj_set_jump_keys(t, a, nj, 2, tid);
     }
     NJ_SYNC();
+    }
     // 3. readout at E -> Y (activations kept for its backward)
     nj_mlp_forward(t, NJODE_NET_RO, nj, false);
     NJ_THREADS(tid, t.nt) {
@@ -882,7 +963,49 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
         }
     }
     NJ_SYNC();
-    // 5. encoder recompute + backward
+    // 5. encoder recompute + backward   (use_rnn: backward of the GRU cell; EE <- gradient wrt h_before through it)
+    if (c.use_rnn) {
+        const int H = c.H;
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nj * H; idx += t.nt) {
+                const int jr = idx / H, c_ = idx % H;
+                float* gi = t.GI + jr * c.s3H;
+                const float* gh = t.GHH + jr * c.s3H;
+                float* go = t.GOUT + jr * c.sOUT;
+                const float ge = t.GTMP[jr * c.sOUT + c_];
+                const float r = gi[c_], z = gi[H + c_], n = gi[2 * H + c_], hh = gh[c_], ghn = gh[2 * H + c_];
+                const float dpn = ge * (1.f - z) * (1.f - n * n);          // wrt the pre-activation of n
+                const float dpr = dpn * ghn * r * (1.f - r);
+                const float dpz = ge * (hh - n) * z * (1.f - z);
+                go[c_] = dpr; go[H + c_] = dpz; go[2 * H + c_] = dpn * r;  // wrt gh = W_hh tanh(h_old) + b_hh
+                gi[c_] = dpr; gi[H + c_] = dpz; gi[2 * H + c_] = dpn;      // wrt gi = W_ih tanh(x) + b_ih
+                t.EE[jr * c.sH + c_] = ge * z;                             // direct path h' = ... + z tanh(h_old)
+                t.IN[(size_t)jr * c.sIN + c_] = hh;
+            }
+        }
+        NJ_SYNC();
+        gin = nj_mlp_backward(t, NJODE_NET_GRU_HH, nj, true);
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nj * H; idx += t.nt) {
+                const int jr = idx / H, c_ = idx % H;
+                const float hh = t.GHH[jr * c.s3H + c_];
+                t.EE[jr * c.sH + c_] = (t.EE[jr * c.sH + c_] + gin[jr * c.sG + c_]) * (1.f - hh * hh);
+            }
+            for (int idx = tid; idx < nj * 3 * H; idx += t.nt) {
+                const int jr = idx / (3 * H), k = idx % (3 * H);
+                t.GOUT[jr * c.sOUT + k] = t.GI[jr * c.s3H + k];
+            }
+        }
+        NJ_SYNC();
+        NJ_THREADS(tid, t.nt) {
+            for (int idx = tid; idx < nj * c.d; idx += t.nt) {
+                const int jr = idx / c.d, c_ = idx % c.d;
+                t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.XI[jr * c.sD + c_]);
+            }
+        }
+        NJ_SYNC();
+        nj_mlp_backward(t, NJODE_NET_GRU_IH, nj, false);
+    } else {
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
             const int jr = idx / c.d, c_ = idx % c.d;
@@ -911,6 +1034,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
         }
         NJ_SYNC();
     }
+    }
     // 6. readout recompute at h_before + backward -> gradient wrt h before the jump
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
@@ -933,6 +1057,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
             const float th = t.IN[(size_t)jr * c.sIN + c_];
             float gh = gin[jr * c.sG + c_] * (1.f - th * th);
             if (c.residual) gh += nj_resid_bwd(t.GOUT + jr * c.sOUT, c.H, c.dout, c_);
+            if (c.use_rnn) gh += t.EE[jr * c.sH + c_];
             t.GH[u * c.sH + c_] = gh;
         }
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {

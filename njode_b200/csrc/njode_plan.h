@@ -19,7 +19,8 @@ struct NjPlanOut {
 
 static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, std::string& err) {
     int off = 0;
-    for (int n = 0; n < 3; ++n) {
+    const int nnets = m.use_rnn ? NJODE_NUM_NETS : 3;
+    for (int n = 0; n < nnets; ++n) {
         const njode_mlp_t& s = m.net[n];
         NjNet& N = c.net[n];
         if (s.n_linear < 1 || s.n_linear > NJODE_MAX_LINEAR) { err = "n_linear out of range"; return false; }
@@ -63,6 +64,8 @@ static inline void nj_layout(NjCfg& c, int P, int nt, bool bwd, bool w_smem, boo
     c.o_YY = o; o += P * c.sDO;
     c.o_XH = o; o += P * c.sH;
     c.o_EE = o; o += P * c.sH;
+    c.o_GI = o; if (c.use_rnn) o += P * c.s3H;
+    c.o_GHH = o; if (c.use_rnn) o += P * c.s3H;
     c.o_GOUT = c.o_GTMP = c.o_GA = c.o_GB = c.o_GH = c.o_GX = c.o_GYBJ = o;
     if (bwd) {
         c.o_GOUT = o; o += P * c.sOUT;
@@ -85,7 +88,7 @@ static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, std::string& er
     if (!nj_fill_nets(m, c, err)) return false;
     c.d = m.input_size; c.H = m.hidden_size; c.dout = m.output_size;
     c.masked = m.masked; c.curt = m.input_current_t; c.loss_kind = m.loss_kind; c.residual = m.residual;
-    c.training = m.training;
+    c.training = m.training; c.use_rnn = m.use_rnn ? 1 : 0;
     c.inf = c.net[NJODE_NET_ODE].dim[0]; c.enc_in = c.net[NJODE_NET_ENC].dim[0];
     const NjNet &O = c.net[NJODE_NET_ODE], &E = c.net[NJODE_NET_ENC], &R = c.net[NJODE_NET_RO];
     if (c.inf != c.d + c.H + 2 + (c.curt ? 1 : 0)) { err = "ode_f input width != input+hidden+2(+1)"; return false; }
@@ -94,6 +97,13 @@ static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, std::string& er
     if (E.dim[E.n] != c.H) { err = "encoder output width != hidden_size"; return false; }
     if (R.dim[0] != c.H || R.dim[R.n] != c.dout) { err = "readout widths mismatch"; return false; }
     if (c.dout != c.d) { err = "output_size must equal input_size (loss compares X with Y)"; return false; }
+    if (c.use_rnn) {
+        // torch.nn.GRUCell(input_size, hidden_size): weight_ih [3H, d], weight_hh [3H, H]  (NJODE/models.py:208)
+        const NjNet &GI = c.net[NJODE_NET_GRU_IH], &GH = c.net[NJODE_NET_GRU_HH];
+        if (GI.n != 1 || GH.n != 1 || GI.dim[0] != c.d || GH.dim[0] != c.H || GI.dim[1] != 3 * c.H || GH.dim[1] != 3 * c.H) {
+            err = "use_rnn: GRU maps must be single Linear layers input->3*hidden and hidden->3*hidden"; return false;
+        }
+    }
     if (c.residual) {
         // FFNN.__init__ residual cases, NJODE/models.py:240-257
         if ((c.d <= c.H && c.H % c.d) || (c.d > c.H && c.d % c.H)) { err = "for residual: encoder sizes must be multiples"; return false; }
@@ -108,7 +118,7 @@ static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, std::string& er
     c.thr = thr >= 65536.0 ? 65536u : (unsigned)thr;          // 16-bit fields, see nj_keep
     c.seed_lo = (unsigned)(m.dropout_seed & 0xFFFFFFFFull); c.seed_hi = (unsigned)(m.dropout_seed >> 32);
     int maxhid = 1, maxin = 1, maxn = 1;
-    for (int n = 0; n < 3; ++n) {
+    for (int n = 0; n < NJODE_NUM_NETS; ++n) {
         const NjNet& N = c.net[n];
         maxn = std::max(maxn, N.n);
         for (int l = 0; l < N.n; ++l) maxin = std::max(maxin, N.dim[l]);
@@ -117,7 +127,8 @@ static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, std::string& er
     c.sIN = nj_stride_host(std::max(std::max(c.inf, c.enc_in), c.H));
     c.sACT = nj_stride_host(maxhid);
     c.nACT = std::max(1, maxn - 1);
-    c.sOUT = nj_stride_host(std::max(c.H, c.dout));
+    c.sOUT = nj_stride_host(std::max(std::max(c.H, c.dout), c.use_rnn ? 3 * c.H : 0));
+    c.s3H = nj_stride_host(3 * c.H);
     c.sH = nj_stride_host(c.H); c.sD = nj_stride_host(c.d); c.sDO = nj_stride_host(c.dout);
     c.sG = nj_stride_host(maxin);
     return true;
@@ -246,7 +257,7 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
     const int n_units = b.n_units;
     const char* off = getenv("NJODE_NO_SEG");
     if (off && atoi(off)) return;
-    if (b.unit_kind != 1 || c.masked || b.E > 0 || n_units <= 0) return;
+    if (b.unit_kind != 1 || c.masked || c.use_rnn || b.E > 0 || n_units <= 0) return;
     int maxhid = 1, maxn = 1, maxlast = 1;
     for (int n = 0; n < 3; ++n) {
         const NjNet& N = c.net[n];

@@ -28,6 +28,7 @@ static bool make_cfg(const njode_model_t& m, WCfg& c, std::string& why) {
     memset(&c, 0, sizeof(c));
     const int d = m.input_size, H = m.hidden_size;
     if (m.masked) { why = "masked model"; return false; }
+    if (m.use_rnn) { why = "use_rnn (GRU jump) runs on the fp32 whole-path kernels"; return false; }
     if (m.output_size != d) { why = "output_size != input_size"; return false; }
     if (!(d == 1 || d == 2 || d == 4 || d == 8 || d == 16)) { why = "input_size must be a power of two <= 16"; return false; }
     if (H < 16 || H > MAX_W || (H % 16)) { why = "hidden_size must be a multiple of 16 in [16, 256]"; return false; }

@@ -272,21 +272,26 @@ class NJODE(torch.nn.Module):
 
     # -- parameter flattening -------------------------------------------------------------------
     def _kernel_params(self):
+        """per kernel network (ODE, ENC, RO[, GRU_IH, GRU_HH]) the list of its affine layers as
+        (weight, bias or None) parameter pairs, nn.Linear layout [out, in]"""
         nets = (self.ode_f.f, self.encoder_map.ffnn, self.readout_map.ffnn)
         out = []
         for seq in nets:
-            lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
-            out.append(lin)
+            out.append([(m.weight, m.bias) for m in seq if isinstance(m, torch.nn.Linear)])
+        if self.use_rnn:
+            g = self.obs_c.gru_d          # torch.nn.GRUCell: weight_ih [3H, d], weight_hh [3H, H], gates (r, z, n)
+            out.append([(g.weight_ih, g.bias_ih if g.bias else None)])
+            out.append([(g.weight_hh, g.bias_hh if g.bias else None)])
         return out
 
     def _ensure_flat(self):
         """all MLP parameters alias one contiguous fp32 buffer (re-established after .to(device))"""
         plist = []
         for lin in self._kernel_params():
-            for m in lin:
-                plist.append(m.weight)
-                if m.bias is not None:
-                    plist.append(m.bias)
+            for w, b in lin:
+                plist.append(w)
+                if b is not None:
+                    plist.append(b)
         ok = self._flat is not None and self._flat.device == plist[0].device
         if ok:
             base = self._flat.data_ptr()
@@ -319,18 +324,19 @@ class NJODE(torch.nn.Module):
         mt.weight = float(self.weight)
         mt.dropout_p = self.dropout_rate
         mt.dropout_seed = int(seed)
+        mt.use_rnn = int(bool(self.use_rnn))
         it = iter(self._flat_layout)
-        for n, (lin, desc) in enumerate(zip(self._kernel_params(), (ode_nn, enc_nn, readout_nn))):
+        for n, (lin, desc) in enumerate(zip(self._kernel_params(), (ode_nn, enc_nn, readout_nn, None, None))):
             net = mt.net[n]
             if len(lin) > _ext.MAX_LINEAR:
                 raise ValueError("at most %d Linear layers per network are supported" % _ext.MAX_LINEAR)
             net.n_linear = len(lin)
-            net.dims[0] = lin[0].in_features
-            for l, m in enumerate(lin):
-                net.dims[l + 1] = m.out_features
+            net.dims[0] = lin[0][0].shape[1]
+            for l, (w, b) in enumerate(lin):
+                net.dims[l + 1] = w.shape[0]
                 net.act[l] = _ext.ACT_CODES[desc[l][1]] if l < len(lin) - 1 else 0
                 net.w_off[l] = next(it)[0]
-                net.b_off[l] = next(it)[0] if m.bias is not None else -1
+                net.b_off[l] = next(it)[0] if b is not None else -1
         mt.n_params = self._flat.numel()
         return mt
 
@@ -342,10 +348,6 @@ class NJODE(torch.nn.Module):
         ``forward_prepared`` any number of times (inputs then stay resident in HBM)."""
         if self.solver != "euler":
             raise ValueError("Unknown solver '{}'.".format(self.solver))      # NJODE/models.py:374
-        if self.use_rnn:
-            raise NotImplementedError(
-                "use_rnn=True (GRU jump, NJODE/models.py:202-217) is not implemented by the B200 "
-                "kernels yet; every shipped configuration of the reference uses use_rnn=False")
         assert len(times) + 1 == len(time_ptr)                                  # NJODE/models.py:428
         if self.masked:
             assert M is not None                                                # NJODE/models.py:263
@@ -353,7 +355,9 @@ class NJODE(torch.nn.Module):
             raise ValueError("get_loss=True needs n_obs_ot")
         self._ensure_flat()
         runner = _TEST_RUNNER if _TEST_RUNNER is not None else _ext.cuda_runner(self._flat.device)
-        segments = (not self.masked) and (not return_path)
+        # the encoder jump forgets the old hidden state -> (path, segment) units; the masked imputation and the
+        # GRU jump (use_rnn) carry h through the jump -> whole-path units
+        segments = (not self.masked) and (not return_path) and (not self.use_rnn)
         pb = runner.prepare(times, time_ptr, X, obs_idx, delta_t, T, start_X,
                             n_obs_ot if get_loss else None, M if self.masked else None, until_T,
                             return_path, segments, self.input_size,

@@ -155,6 +155,20 @@ def ffnn(x, sd, prefix, nn_desc, bias, residual, in_size, out_size, mask=None, d
     return ident + out
 
 
+def gru_cell(x, h, sd, prefix, bias):
+    """torch.nn.GRUCell as used by GRUCell.forward (NJODE/models.py:202-217): gates in (r, z, n) order,
+    r = sig(W_ir x + b_ir + W_hr h + b_hr), z likewise, n = tanh(W_in x + b_in + r (W_hn h + b_hn)),
+    h' = (1 - z) n + z h.  The caller passes x = tanh(X_obs), h = tanh(h[i_obs])."""
+    gi = torch.nn.functional.linear(x, sd[prefix + ".weight_ih"], sd[prefix + ".bias_ih"] if bias else None)
+    gh = torch.nn.functional.linear(h, sd[prefix + ".weight_hh"], sd[prefix + ".bias_hh"] if bias else None)
+    i_r, i_z, i_n = gi.chunk(3, dim=1)
+    h_r, h_z, h_n = gh.chunk(3, dim=1)
+    r = torch.sigmoid(i_r + h_r)
+    z = torch.sigmoid(i_z + h_z)
+    n = torch.tanh(i_n + r * h_n)
+    return (1 - z) * n + z * h
+
+
 def loss_term(which, X_obs, Y_obs, Y_obs_bj, n_obs_ot, batch_size, weight, M_obs=None, eps=1e-10):
     """compute_loss / compute_loss_2 (NJODE/models.py:71-126)."""
     m = 1.0 if M_obs is None else M_obs
@@ -190,7 +204,6 @@ class Config:
         self.input_current_t = o.get("input_current_t", False)
         self.masked = o.get("masked", False)
         assert self.which_loss in ("standard", "easy")
-        assert not use_rnn, "oracle restates the use_rnn=False path"
 
 
 def forward(cfg, sd, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
@@ -284,7 +297,9 @@ def forward(cfg, sd, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
         M_obs = M[start:end] if cfg.masked else None
         Y_bj = ro(h, jump_event_id(i, 0), path_ids)              # NJODE/models.py:459
         temp = h.clone()                                           # NJODE/models.py:463-470
-        if cfg.masked:
+        if cfg.use_rnn:                                            # NJODE/models.py:460-461, 213-217
+            temp[i_obs] = gru_cell(torch.tanh(X_obs), torch.tanh(h[i_obs]), sd, "obs_c.gru_d", cfg.bias)
+        elif cfg.masked:
             X_imp = X_obs * M_obs + (torch.ones_like(M_obs) - M_obs) * Y_bj[i_obs]
             temp[i_obs] = enc(X_imp, M_obs, jump_event_id(i, 1), rows)
         else:
@@ -330,6 +345,16 @@ def init_state_dict(cfg, seed=0, dtype=torch.float32):
     add("ode_f.f", cfg.input_size + cfg.hidden_size + add_t, cfg.hidden_size, cfg.ode_nn)
     add("encoder_map.ffnn", cfg.input_size * (2 if cfg.masked else 1), cfg.hidden_size, cfg.enc_nn)
     add("readout_map.ffnn", cfg.hidden_size, cfg.output_size, cfg.readout_nn)
+    if cfg.use_rnn:
+        # torch.nn.GRUCell default init: U(-1/sqrt(H), 1/sqrt(H)) for all four tensors (init_weights only
+        # touches nn.Linear, NJODE/models.py:21-26)
+        k = 1.0 / math.sqrt(cfg.hidden_size)
+        H3 = 3 * cfg.hidden_size
+        sd["obs_c.gru_d.weight_ih"] = ((torch.rand(H3, cfg.input_size, generator=g) * 2 - 1) * k).to(dtype)
+        sd["obs_c.gru_d.weight_hh"] = ((torch.rand(H3, cfg.hidden_size, generator=g) * 2 - 1) * k).to(dtype)
+        if cfg.bias:
+            sd["obs_c.gru_d.bias_ih"] = ((torch.rand(H3, generator=g) * 2 - 1) * k).to(dtype)
+            sd["obs_c.gru_d.bias_hh"] = ((torch.rand(H3, generator=g) * 2 - 1) * k).to(dtype)
     return sd
 
 

@@ -38,6 +38,14 @@ CONFIGS = {
                              ode_nn=[[24, "tanh"], [24, "tanh"]], enc_nn=[[24, "tanh"], [24, "tanh"]],
                              readout_nn=[[24, "tanh"], [24, "tanh"]], options={"masked": True}),
     "masked_physio": demo_cfg(input_size=41, output_size=41, hidden_size=41, options={"masked": True}),
+    # use_rnn=True: GRU jump (NJODE/models.py:202-217); never enabled in a shipped config, built for coverage
+    "gru_demo": demo_cfg(use_rnn=True, hidden_size=10),
+    "gru_d3_nores": demo_cfg(input_size=3, output_size=3, hidden_size=7, use_rnn=True, weight=0.6,
+                             ode_nn=[[18, "tanh"]], enc_nn=[[12, "relu"]], readout_nn=[[16, "tanh"], [9, "tanh"]],
+                             options={"residual_enc_dec": False, "which_loss": "easy"}),
+    "gru_masked": demo_cfg(input_size=4, output_size=4, hidden_size=8, use_rnn=True,
+                           ode_nn=[[20, "tanh"]], enc_nn=[[20, "tanh"]], readout_nn=[[20, "tanh"]],
+                           options={"masked": True}),
     "wide_small": demo_cfg(input_size=16, output_size=16, hidden_size=64,
                            ode_nn=[[64, "tanh"]] * 4, enc_nn=[[64, "tanh"]] * 4,
                            readout_nn=[[64, "tanh"]] * 4),

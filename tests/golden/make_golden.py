@@ -91,8 +91,18 @@ def main():
     b = cases.irregular_batch(8, 1, 12, seed=15)
     todo.append(("irregular_demo", cases.CONFIGS["demo"], b, 0.05, 1.0, None))
 
+    b = cases.grid_batch(14, 1, 20, 0.25, seed=16)
+    todo.append(("gru_demo", cases.CONFIGS["gru_demo"], b, 0.05, 1.0, None))
+    b = cases.irregular_batch(9, 3, 14, seed=17)
+    todo.append(("gru_d3_nores", cases.CONFIGS["gru_d3_nores"], b, 0.04, 1.0, None))
+    b = cases.irregular_batch(7, 4, 15, seed=18, masked=True, times_f32=True, obs_at_zero=True)
+    todo.append(("gru_masked", cases.CONFIGS["gru_masked"], b, 0.03, 1 + 1e-12, None))
+
     import oracle.njode_oracle as orc
+    only = set(sys.argv[1:])            # optional: regenerate only the named cases
     for i, (name, cfg, batch, dt, T, sd) in enumerate(todo):
+        if only and name not in only:
+            continue
         sd, outs = run_reference(ref, cfg, sd, batch, dt, T, seed=100 + i)
         meta = {"delta_t": dt, "T": T}
         cases.save_case(os.path.join(HERE, name + ".npz"), cfg, meta, sd, batch, outs)

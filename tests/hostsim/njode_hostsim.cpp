@@ -40,7 +40,7 @@ extern "C" int njode_plan(const njode_model_t* model, const njode_batch_t* bs, i
 
 static void pack(const NjCfg& c, const float* params, float* image) {
     for (int i = 0; i < c.img_floats; ++i) image[i] = 0.f;
-    for (int n = 0; n < 3; ++n) {
+    for (int n = 0; n < NJODE_NUM_NETS; ++n) {
         const NjNet& N = c.net[n];
         for (int l = 0; l < N.n; ++l) {
             const int K = N.dim[l], O = N.dim[l + 1];
@@ -126,7 +126,7 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         }
     }
     const NjCfg& c = pl.bwd;
-    for (int n = 0; n < 3; ++n) {
+    for (int n = 0; n < NJODE_NUM_NETS; ++n) {
         const NjNet& N = c.net[n];
         for (int l = 0; l < N.n; ++l) {
             const int K = N.dim[l], O = N.dim[l + 1];

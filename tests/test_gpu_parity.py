@@ -40,7 +40,7 @@ def test_path_call(name):
 
 
 @pytest.mark.parametrize("tile", [8, 16, 32, 64])
-@pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small"])
+@pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small", "gru_demo"])
 def test_tile_size_invariance(name, tile):
     os.environ["NJODE_FORCE_TILE"] = str(tile)
     parity_util.check_training_call(name, DEV, with_hT_grad=True)
@@ -104,6 +104,14 @@ def test_config5_scaled_architecture_against_oracle():
     _oracle_vs_cuda(cfg, batch, 0.125, 1.0, seed=7)
 
 
+def test_gru_jump_train_mode_dropout_against_oracle():
+    """use_rnn=True (GRU jump, NJODE/models.py:202-217) on the demo nets, dropout on, batch 200"""
+    cfg = cases.demo_cfg(use_rnn=True, dropout_rate=0.1)
+    batch = cases.grid_batch(200, 1, 50, 0.1, seed=25)
+    parity_util.check_against_oracle(cfg, batch, 0.02, 1.0, seed=9, device=DEV, train=True, grad_hT=True)
+    parity_util.check_against_oracle(cfg, batch, 0.02, 1.0, seed=9, device=DEV, train=False)
+
+
 @pytest.mark.parametrize("B", [200, 5000])
 def test_demo_batch_sweep_train_mode(B):
     """batch sweep of config 3 on the demo nets, dropout on: segment fast path with every tile height"""
@@ -133,4 +141,4 @@ def test_native_library_is_loaded():
     from njode_b200 import _ext
     with open("/proc/self/maps") as f:
         assert "libnjode_b200.so" in f.read()
-    assert _ext.cuda_lib().dll.njode_abi_version() == 3
+    assert _ext.cuda_lib().dll.njode_abi_version() == 4

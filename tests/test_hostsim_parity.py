@@ -44,7 +44,7 @@ def test_path_call(name):
 
 
 @pytest.mark.parametrize("tile", [8, 16, 64])
-@pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small", "curt_nobias_relu"])
+@pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small", "curt_nobias_relu", "gru_masked"])
 def test_tile_size_invariance(name, tile):
     os.environ["NJODE_FORCE_TILE"] = str(tile)
     parity_util.check_training_call(name, "cpu", with_hT_grad=True)
@@ -72,6 +72,13 @@ def test_train_mode_dropout_masked_model():
     parity_util.check_against_oracle(cfg, batch, 0.05, 1 + 1e-12, seed=3, device="cpu", train=True)
 
 
+def test_gru_jump_train_mode_dropout():
+    """use_rnn=True: the GRU cell replaces the encoder at the jumps (NJODE/models.py:202-217,460-461)"""
+    cfg = cases.demo_cfg(use_rnn=True, dropout_rate=0.2, bias=False, hidden_size=6)
+    batch = cases.grid_batch(30, 1, 20, 0.25, seed=26)
+    parity_util.check_against_oracle(cfg, batch, 0.05, 1.0, seed=5, device="cpu", train=True, grad_hT=True)
+
+
 def test_physionet_shape_masked():
     batch = cases.irregular_batch(5, 41, 12, seed=7, masked=True, times_f32=True, obs_at_zero=True,
                                   row_prob=0.3, feat_prob=0.12)
@@ -88,7 +95,7 @@ def test_global_weight_image_path():
 
 
 # ---- segment fast path (njode_b200/csrc/njode_seg.cuh): every tile height, train and eval ----
-SEG_NAMES = [n for n in NAMES if "masked" not in n]
+SEG_NAMES = [n for n in NAMES if "masked" not in n and "gru" not in n]
 
 
 @pytest.mark.parametrize("tr", [1, 2, 4])
