@@ -484,8 +484,19 @@ def run_b200(args, wl_name, wl):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    roofline = {"kernel": "nj_bwd_kernel", "bound": "fp32_fma", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/ncu_traffic.json names the capture), else null
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(wl_name, {})
+    except Exception:
+        pass
+    seg_path = (not wl.get("masked")) and pb.fwd.unit_kind == 1 and wl["width"] <= 64
+    kname = "nj_seg_bwd_kernel" if seg_path else "nj_bwd_kernel"
+    roofline = {"kernel": kname, "bound": "fp32_fma", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": traffic.get(kname, {}).get("dram_bytes"), "traffic_source": traffic.get(kname, {}).get("source"),
+                "algorithmic_bytes": alg_bytes_bwd,
                 "peak_source": "measured in this run (njode_fma_peak_launch: FFMA chains on all SMs)",
                 "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
                 "fwd_achieved": fwd_flops / (fwd_ms * 1e-3) / 1e12,
@@ -509,7 +520,8 @@ def run_b200(args, wl_name, wl):
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = 3.0 * fwd_flops / (k_ms * 1e-3) / 1e12
         roofline = {"kernel": "nj_wide_kernel + nj_wide_bwd_kernel + nj_wide_dw_kernel (tcgen05)", "bound": "tensor",
-                    "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                    "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                    "traffic": traffic.get("nj_wide", {}).get("dram_bytes"), "traffic_source": traffic.get("nj_wide", {}).get("source"),
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                     "kernel_ms": k_ms, "fwd_enc_ms": te.value, "fwd_ode_ms": to.value, "fwd_ro_ms": tr.value,
                     "bwd_chain_ms": tc_.value, "bwd_dw_ms": td.value, "flops_per_launch": 3.0 * fwd_flops}

@@ -147,9 +147,8 @@ static int nj_plan_for(const njode_model_t* model, const njode_batch_t* b, int d
     if (int rc = nj_device_info(dev, di)) return rc;
     std::string err;
     const char* fp = getenv("NJODE_FORCE_TILE");
-    if (!nj_make_plan(*model, b->n_units, b->n_units, b->N, di.sms, di.smem_optin, fp ? atoi(fp) : 0, out, err))
+    if (!nj_plan_all(*model, *b, di.sms, di.smem_optin, fp ? atoi(fp) : 0, out, err))
         return nj_fail(-3, err);
-    nj_make_seg(out.fwd, *b, di.sms, di.smem_optin, out);
     // gradient partials: sized for the largest grid any backward launch of this model may use
     const size_t cap = (size_t)di.sms * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);

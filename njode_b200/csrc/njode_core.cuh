@@ -62,12 +62,13 @@ struct NjNet {
 struct NjCfg {
     NjNet net[NJODE_NUM_NETS];          // ODE, ENC, RO (, GRU_IH, GRU_HH when use_rnn; n = 0 otherwise)
     int d, H, dout, inf, enc_in;
-    int masked, curt, loss_kind, residual, training, has_drop, use_rnn;
+    int masked, curt, loss_kind, residual, training, has_drop, use_rnn, compact;
     float w, keep_scale, one_minus_p;
     unsigned thr, seed_lo, seed_hi;
     int P, nt;
     int img_floats;
-    int w_smem, dw_smem;
+    int w_smem, dw_smem;                // dw_smem: 0 none, 1 whole gradient image, 2 ODE network part only
+    int dimg_floats;                    // floats of the gradient image held in shared memory
     // strides (floats) of the shared-memory matrices
     int sIN, sACT, nACT, sOUT, sH, sD, sDO, sG, s3H;
     // offsets (floats) into dynamic shared memory
@@ -303,7 +304,8 @@ struct NjArgs {
 struct NjCta {
     const NjCfg* c;
     const float* wimg;         // parameter image (shared or global)
-    float* dimg;               // gradient image (shared or this CTA's global partial)
+    float* dimg;               // gradient image: shared-memory part [0, dimg_floats) ...
+    float* gpart;              // ... and this CTA's partial image in global memory for the rest
     float *IN, *ACT, *OUT, *Hs, *LX, *XI, *YBJ, *YY, *XH, *EE, *GOUT, *GTMP, *GA, *GB, *GH, *GX, *GYBJ, *F;
     float *GI, *GHH;
     int *I, *CTL;
@@ -394,8 +396,9 @@ NJ_HDN float* nj_mlp_backward(NjCta& t, int netid, int nrows, bool need_in_grad)
         D.drop = c.has_drop; D.thr = c.thr; D.keep_scale = c.keep_scale; D.one_minus_p = c.one_minus_p;
         D.rk = t.I + NJ_I_RK * c.P; D.tag_prev = (unsigned)(netid * 16 + l);
         const int mr = nj_pick_mr(nrows, (N.dim[l] + 3) >> 2, t.nt);
-        float* dW = t.dimg + N.w_img[l];
-        float* db = N.b_src[l] >= 0 ? t.dimg + N.b_img[l] : nullptr;
+        float* dbase = (N.b_img[l] + N.rp[l] <= c.dimg_floats) ? t.dimg : t.gpart;
+        float* dW = dbase + N.w_img[l];
+        float* db = N.b_src[l] >= 0 ? dbase + N.b_img[l] : nullptr;
         NJ_THREADS(tid, t.nt) {
             nj_tile_dw(g, g_s, N.og[l], inp, inp_s, (N.dim[l] + 3) >> 2, nrows, dW, N.ks[l], db, tid, t.nt);
             if (dx) {
@@ -1078,8 +1081,9 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
         t.wimg = simg;
     } else t.wimg = a.image;
     float* gpart = a.partials + (size_t)cta * c.img_floats;
-    t.dimg = c.dw_smem ? smem + c.o_dimg : gpart;
-    nj_zero(t.dimg, c.img_floats, t.nt);
+    t.dimg = smem + c.o_dimg; t.gpart = gpart;
+    nj_zero(t.dimg, c.dimg_floats, t.nt);
+    if (c.dimg_floats < c.img_floats) nj_zero(gpart + c.dimg_floats, c.img_floats - c.dimg_floats, t.nt);
     nj_zero(smem + c.o_IN, c.o_I - c.o_IN, t.nt);
     NJ_SYNC();
     for (int tile = cta; tile < a.n_tiles; tile += ncta) {
@@ -1168,7 +1172,7 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
         nj_mlp_forward(t, NJODE_NET_ENC, nu, true);
         nj_mlp_backward(t, NJODE_NET_ENC, nu, false);
     }
-    if (c.dw_smem) {
-        NJ_THREADS(tid, t.nt) { for (int i = tid; i < c.img_floats / 4; i += t.nt) nj_st4(gpart + 4 * i, nj_ld4(t.dimg + 4 * i)); }
+    if (c.dimg_floats) {
+        NJ_THREADS(tid, t.nt) { for (int i = tid; i < c.dimg_floats / 4; i += t.nt) nj_st4(gpart + 4 * i, nj_ld4(t.dimg + 4 * i)); }
     }
 }

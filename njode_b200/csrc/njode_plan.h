@@ -17,7 +17,10 @@ struct NjPlanOut {
     size_t ws_image_off, ws_rowloss_off, ws_counter_off, ws_partials_off, ws_bytes;
 };
 
-static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, std::string& err) {
+// compact: the generic kernels (njode_core.cuh) only touch rows < 4 * og of a weight block; the 8*to*nch row padding
+// is for the warp GEMMs of the segment kernels.  Wide-ish nets (2x100) that cannot take the segment path anyway get
+// the compact image so that it fits shared memory.
+static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, bool compact, std::string& err) {
     int off = 0;
     const int nnets = m.use_rnn ? NJODE_NUM_NETS : 3;
     for (int n = 0; n < nnets; ++n) {
@@ -38,7 +41,7 @@ static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, std::string& e
             N.nch[l] = (o8 + 7) / 8;
             N.to[l] = (o8 + N.nch[l] - 1) / N.nch[l];
             if (N.nch[l] > 1 && (N.to[l] & 1)) N.to[l] += 1;      // chunk bases stay multiples of 16 (hash pairs)
-            N.rp[l] = N.nch[l] * 8 * N.to[l];
+            N.rp[l] = compact ? 4 * N.og[l] : N.nch[l] * 8 * N.to[l];
             N.w_img[l] = off; off += N.rp[l] * N.ks[l];
             N.b_img[l] = off; off += N.rp[l];
             N.w_src[l] = s.w_off[l]; N.b_src[l] = s.b_off[l];
@@ -49,11 +52,13 @@ static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, std::string& e
 }
 
 // lays out shared memory for tile size P; returns the number of floats needed
-static inline void nj_layout(NjCfg& c, int P, int nt, bool bwd, bool w_smem, bool dw_smem) {
-    c.P = P; c.nt = nt; c.w_smem = w_smem; c.dw_smem = dw_smem && bwd;
+static inline void nj_layout(NjCfg& c, int P, int nt, bool bwd, bool w_smem, int dw_smem) {
+    c.P = P; c.nt = nt; c.w_smem = w_smem; c.dw_smem = bwd ? dw_smem : 0;
+    // gradient image part kept in shared memory: everything (1) or the ODE network's blocks (2; first in the image)
+    c.dimg_floats = c.dw_smem == 1 ? c.img_floats : (c.dw_smem == 2 ? c.net[NJODE_NET_ENC].w_img[0] : 0);
     int o = 0;
     c.o_img = o; if (w_smem) o += c.img_floats;
-    c.o_dimg = o; if (c.dw_smem) o += c.img_floats;
+    c.o_dimg = o; o += c.dimg_floats;
     c.o_IN = o; o += P * c.sIN;
     c.o_ACT = o; o += c.nACT * P * c.sACT;
     c.o_OUT = o; o += P * c.sOUT;
@@ -83,9 +88,10 @@ static inline void nj_layout(NjCfg& c, int P, int nt, bool bwd, bool w_smem, boo
     if (bwd) c.smem_floats_bwd = o; else c.smem_floats_fwd = o;
 }
 
-static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, std::string& err) {
+static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, bool compact, std::string& err) {
     memset(&c, 0, sizeof(c));
-    if (!nj_fill_nets(m, c, err)) return false;
+    if (!nj_fill_nets(m, c, compact, err)) return false;
+    c.compact = compact ? 1 : 0;
     c.d = m.input_size; c.H = m.hidden_size; c.dout = m.output_size;
     c.masked = m.masked; c.curt = m.input_current_t; c.loss_kind = m.loss_kind; c.residual = m.residual;
     c.training = m.training; c.use_rnn = m.use_rnn ? 1 : 0;
@@ -134,33 +140,52 @@ static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, std::string& er
     return true;
 }
 
-// choose tile size / residency so that both kernels fit `smem_limit` bytes per CTA
+// choose tile size / residency so that both kernels fit `smem_limit` bytes per CTA.
+//   * 256 threads per CTA whatever the tile height: the lockstep march is latency bound (dependent Euler steps), so
+//     every layer GEMM wants as many threads as it has 1x4 micro-tiles;
+//   * tile height P: the smallest that still covers the units in whole waves of one CTA per SM (a whole-path batch of
+//     2000 records -> P = 14, 143 CTAs; the reference's PhysioNet batch of 50 -> P = 1), at most 64;
+//   * residency: parameter image (and, if it also fits, the gradient image) in shared memory is worth a smaller P.
 static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_units_bwd, int N_rows,
-                                int num_sms, size_t smem_limit, int force_P, NjPlanOut& out, std::string& err) {
+                                int num_sms, size_t smem_limit, int force_P, bool compact, NjPlanOut& out, std::string& err) {
     NjCfg base;
-    if (!nj_make_cfg(m, base, err)) return false;
-    static const int cand[4] = {64, 32, 16, 8};
-    int P = 8;
-    for (int i = 0; i < 4; ++i)
-        if ((n_units_fwd + cand[i] - 1) / cand[i] >= num_sms) { P = cand[i]; break; }
-    if (force_P > 0) P = force_P;
-    for (;;) {
-        const int nt = std::max(64, std::min(256, 4 * P));
-        bool ok_f = false, ok_b = false;
-        out.fwd = base; out.bwd = base;
-        for (int w = 1; w >= 0 && !ok_f; --w) {
-            nj_layout(out.fwd, P, nt, false, w != 0, false);
-            ok_f = (size_t)out.fwd.smem_floats_fwd * 4 <= smem_limit;
-        }
-        static const int opts[3][2] = {{1, 1}, {1, 0}, {0, 0}};
-        for (int k = 0; k < 3 && !ok_b; ++k) {
-            nj_layout(out.bwd, P, nt, true, opts[k][0] != 0, opts[k][1] != 0);
-            ok_b = (size_t)out.bwd.smem_floats_bwd * 4 <= smem_limit;
-        }
-        if (ok_f && ok_b) break;
-        if (P <= 4) { err = "model too wide for the shared-memory tile kernels"; return false; }
-        P /= 2;
+    if (!nj_make_cfg(m, base, compact, err)) return false;
+    const int nt = 256;
+    int P_want = 64;
+    if (n_units_fwd < 64 * num_sms) {
+        const int waves = std::max(1, (n_units_fwd + 64 * num_sms - 1) / (64 * num_sms));
+        P_want = std::max(1, std::min(64, (n_units_fwd + waves * num_sms - 1) / (waves * num_sms)));
+    } else {
+        const int tiles64 = (n_units_fwd + 63) / 64;
+        const int waves = (tiles64 + num_sms - 1) / num_sms;
+        P_want = std::max(1, std::min(64, (n_units_fwd + waves * num_sms - 1) / (waves * num_sms)));
     }
+    if (force_P > 0) P_want = force_P;
+    // residency options of one kernel at tile height P, best first; dw: 1 = whole gradient image in shared memory,
+    // 2 = the ODE network's part only (the one every Euler step accumulates into), 0 = per-CTA partial in global memory
+    auto place = [&](int P, bool need_w) {
+        out.fwd = base; out.bwd = base;
+        bool okf = false, okb = false;
+        for (int w = 1; w >= (need_w ? 1 : 0) && !okf; --w) {
+            nj_layout(out.fwd, P, nt, false, w != 0, 0);
+            okf = (size_t)out.fwd.smem_floats_fwd * 4 <= smem_limit;
+        }
+        static const int opts[4][2] = {{1, 1}, {1, 2}, {1, 0}, {0, 0}};
+        const char* fdw = getenv("NJODE_FORCE_DW");          // tests: pin the gradient-image residency
+        for (int k = 0; k < (need_w ? 3 : 4) && !okb; ++k) {
+            if (fdw && opts[k][0] && opts[k][1] != atoi(fdw)) continue;
+            nj_layout(out.bwd, P, nt, true, opts[k][0] != 0, opts[k][1]);
+            okb = (size_t)out.bwd.smem_floats_bwd * 4 <= smem_limit;
+        }
+        return okf && okb;
+    };
+    bool ok = false;
+    // the parameter image in shared memory is worth a tile of half the height
+    const int cands[3] = {P_want, (3 * P_want) / 4, P_want / 2};
+    for (int i = 0; i < (force_P > 0 ? 1 : 3) && !ok; ++i)
+        if (cands[i] >= 1 && (i == 0 || cands[i] != cands[i - 1])) ok = place(cands[i], true);
+    for (int P = P_want; !ok && P >= 1; P /= 2) ok = place(P, false);
+    if (!ok) { err = "model too wide for the shared-memory tile kernels"; return false; }
     out.smem_fwd_bytes = (size_t)out.fwd.smem_floats_fwd * 4;
     out.smem_bwd_bytes = (size_t)out.bwd.smem_floats_bwd * 4;
     const int P_ = out.fwd.P;
@@ -169,7 +194,7 @@ static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_u
     auto per_sm = [&](size_t bytes, int nt) {
         int k = (int)((smem_limit + 1024) / (bytes + 1024));
         k = std::min(k, 2048 / nt);
-        return std::max(1, std::min(k, 8));
+        return std::max(1, std::min(k, 2));          // 128 registers x 256 threads: two CTAs per SM
     };
     out.grid_fwd = std::max(1, std::min(out.n_tiles, num_sms * per_sm(out.smem_fwd_bytes, out.fwd.nt)));
     out.grid_bwd = std::max(1, std::min(tiles_b, num_sms * per_sm(out.smem_bwd_bytes, out.bwd.nt)));
@@ -330,4 +355,16 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
     out.seg_grid_f = std::max(1, std::min((s.n_tiles_f + s.nw_f - 1) / s.nw_f, num_sms));
     out.seg_grid_b = std::max(1, std::min(s.n_tiles_b, num_sms));
     s.ok = 1;
+}
+
+// the whole launch plan of one (model, batch) pair: the segment fast path when it serves the call (padded parameter
+// image), else the generic kernels on the compact image
+static inline bool nj_plan_all(const njode_model_t& m, const njode_batch_t& b, int num_sms, size_t smem_limit, int force_P,
+                               NjPlanOut& out, std::string& err) {
+    if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, false, out, err)) return false;
+    nj_make_seg(out.fwd, b, num_sms, smem_limit, out);
+    if (out.seg.ok) return true;
+    if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, true, out, err)) return false;
+    memset(&out.seg, 0, sizeof(out.seg));
+    return true;
 }

@@ -20,8 +20,7 @@ static const size_t kSimSmem = 227 * 1024;
 static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& out) {
     std::string err;
     const char* fp = getenv("NJODE_FORCE_TILE");
-    if (!nj_make_plan(*m, b->n_units, b->n_units, b->N, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
-    nj_make_seg(out.fwd, *b, kSimSMs, kSimSmem, out);
+    if (!nj_plan_all(*m, *b, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
     const size_t cap = (size_t)kSimSMs * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
     out.ws_bytes = out.ws_partials_off + cap * out.fwd.img_floats * sizeof(float);

@@ -26,6 +26,7 @@ def sim_runner():
     os.environ.pop("NJODE_NO_SEG", None)
     os.environ.pop("NJODE_INDEX", None)
     os.environ.pop("NJODE_FORCE_NW", None)
+    os.environ.pop("NJODE_FORCE_DW", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -47,6 +48,26 @@ def test_path_call(name):
 @pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small", "curt_nobias_relu", "gru_masked"])
 def test_tile_size_invariance(name, tile):
     os.environ["NJODE_FORCE_TILE"] = str(tile)
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    parity_util.check_path_call(name, "cpu")
+
+
+@pytest.mark.parametrize("dw", [0, 2])
+@pytest.mark.parametrize("name", ["masked_small", "gru_d3_nores", "res_case2"])
+def test_gradient_image_residency(name, dw):
+    """gradient image: whole in shared memory (default for small nets), ODE-network part only (2), or the per-CTA
+    partial in global memory (0) -- same gradients"""
+    os.environ["NJODE_FORCE_DW"] = str(dw)
+    os.environ["NJODE_NO_SEG"] = "1"
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+
+
+@pytest.mark.parametrize("tile", [1, 3, 5])
+@pytest.mark.parametrize("name", ["heston_ckpt2", "masked_small", "gru_demo"])
+def test_small_tiles(name, tile):
+    """tile heights the planner picks for small whole-path batches (PhysioNet batch of 50 -> one path per CTA)"""
+    os.environ["NJODE_FORCE_TILE"] = str(tile)
+    os.environ["NJODE_NO_SEG"] = "1"
     parity_util.check_training_call(name, "cpu", with_hT_grad=True)
     parity_util.check_path_call(name, "cpu")
 
