@@ -206,10 +206,11 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
         NJ_CUDA(cudaFuncSetAttribute(nj_seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
         nj_seg_fwd_kernel<<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
     } else {
-        NJ_CUDA(cudaFuncSetAttribute(nj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd_bytes));
+        auto kern = nj_fwd_kernel;
+        NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd_bytes));
         if (tm) cudaEventRecord(g_ev[0], st);
         if (batch->n_units > 0)
-            nj_fwd_kernel<<<pl.grid_fwd, pl.fwd.nt, pl.smem_fwd_bytes, st>>>(pl.fwd, a);
+            kern<<<pl.grid_fwd, pl.fwd.nt, pl.smem_fwd_bytes, st>>>(pl.fwd, a);
     }
     if (tm) { cudaEventRecord(g_ev[1], st); g_ev_rec[0] = true; }
     if (loss) nj_loss_reduce_kernel<<<1, 1024, 0, st>>>(a.row_loss, batch->N, 1.f / (float)batch->batch_size_norm, loss);
@@ -246,11 +247,12 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         NJ_CUDA(cudaFuncSetAttribute(nj_seg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
         nj_seg_bwd_kernel<<<pl.seg_grid_b, pl.seg.nw_b * 32, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
     } else {
-        NJ_CUDA(cudaFuncSetAttribute(nj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd_bytes));
+        auto kern = nj_bwd_kernel;
+        NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd_bytes));
         if (tm) cudaEventRecord(g_ev[2], st);
         if (batch->n_units > 0) {
             nparts = pl.grid_bwd;
-            nj_bwd_kernel<<<pl.grid_bwd, pl.bwd.nt, pl.smem_bwd_bytes, st>>>(pl.bwd, a);
+            kern<<<pl.grid_bwd, pl.bwd.nt, pl.smem_bwd_bytes, st>>>(pl.bwd, a);
         }
     }
     if (tm) { cudaEventRecord(g_ev[3], st); g_ev_rec[1] = true; }

@@ -55,6 +55,12 @@ struct NjNet {
     int nch[NJODE_MAX_LINEAR];          // output chunks of 8 * to rows
     int w_img[NJODE_MAX_LINEAR];        // float offsets inside the image
     int b_img[NJODE_MAX_LINEAR];
+    unsigned m_in[NJODE_MAX_LINEAR], m_out[NJODE_MAX_LINEAR];   // nj_magic of dim[l] / dim[l + 1]
+    // row-loop slicing of the layer GEMMs for tiles of <= NJ_RL_MAXROWS rows (0 slices: micro-tile path); filled by the
+    // planner for the tile height of the launch: forward (slices, float4 chunks per slice), dx (first thread, slices,
+    // output groups per slice)
+    int rl_f_ns[NJODE_MAX_LINEAR], rl_f_kc[NJODE_MAX_LINEAR];
+    int rl_d_t0[NJODE_MAX_LINEAR], rl_d_ns[NJODE_MAX_LINEAR], rl_d_oc[NJODE_MAX_LINEAR];
     long long w_src[NJODE_MAX_LINEAR];  // float offsets inside the flat parameter buffer
     long long b_src[NJODE_MAX_LINEAR];  // -1: no bias
 };
@@ -66,6 +72,7 @@ struct NjCfg {
     float w, keep_scale, one_minus_p;
     unsigned thr, seed_lo, seed_hi;
     int P, nt;
+    unsigned m_H, m_d, m_dout, m_inf, m_dH, m_3H;      // nj_magic of H, d, dout, inf, d + H, 3 H
     int img_floats;
     int w_smem, dw_smem;                // dw_smem: 0 none, 1 whole gradient image, 2 ODE network part only
     int dimg_floats;                    // floats of the gradient image held in shared memory
@@ -74,6 +81,7 @@ struct NjCfg {
     // offsets (floats) into dynamic shared memory
     int o_img, o_dimg, o_IN, o_ACT, o_OUT, o_H, o_LX, o_XI, o_YBJ, o_YY, o_XH, o_EE;
     int o_GOUT, o_GTMP, o_GA, o_GB, o_GH, o_GX, o_GYBJ, o_F, o_I;
+    int o_KS;                           // [NJ_RL_SCRATCH] partial sums of the row-loop GEMMs (nj_rl_*)
     int o_GI, o_GHH;                    // use_rnn: [P][s3H] gate buffers of the GRU jump
     int smem_floats_fwd, smem_floats_bwd;
 };
@@ -81,8 +89,8 @@ struct NjCfg {
 // per-unit float scalars (row-major [slot][P]) and int scalars
 enum { NJ_F_TAU = 0, NJ_F_DT, NJ_F_T, NJ_F_CA, NJ_F_CB, NJ_F_COUNT };
 enum { NJ_I_PATH = 0, NJ_I_S0, NJ_I_LEN, NJ_I_CUR, NJ_I_C0, NJ_I_C1, NJ_I_START, NJ_I_FLAG, NJ_I_RK,
-       NJ_I_JMAP, NJ_I_JROW, NJ_I_JJMP, NJ_I_PEND, NJ_I_COUNT };
-enum { NJ_CTL_NJ = 0, NJ_CTL_MAXLEN, NJ_CTL_COUNT = 4 };
+       NJ_I_JMAP, NJ_I_JROW, NJ_I_JJMP, NJ_I_PEND, NJ_I_NEXT, NJ_I_COUNT };
+enum { NJ_CTL_NJ = 0, NJ_CTL_MAXLEN, NJ_CTL_NEXT, NJ_CTL_COUNT = 4 };
 
 static inline int nj_stride_host(int n) {
     int s = (n + 3) & ~3;
@@ -92,6 +100,18 @@ static inline int nj_stride_host(int n) {
 }
 
 #include "njode_hash.cuh"
+
+// division by a launch constant: q = umulhi(x, ceil(2^32 / d)), exact for x * d < 2^32 (indices here are < 2^16 and
+// divisors < 2^10).  The element loops of the lockstep phases decode (row, column) from a flat index; a hardware-less
+// 32-bit division costs ~20 instructions, and with few warps per SM every instruction of a phase is exposed latency.
+static inline unsigned nj_magic_host(int d) { return d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u; }
+#if defined(NJODE_HOST_SIM)
+static inline int nj_div(int x, int d, unsigned m) { return d > 1 ? (int)(((unsigned long long)(unsigned)x * m) >> 32) : x; }
+static inline unsigned nj_magic(int d) { return nj_magic_host(d); }
+#else
+__device__ __forceinline__ int nj_div(int x, int d, unsigned m) { return d > 1 ? (int)__umulhi((unsigned)x, m) : x; }
+__device__ __forceinline__ unsigned nj_magic(int d) { return d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u; }
+#endif
 
 NJ_HD float nj_act(float v, int act) {
     if (act == NJODE_ACT_TANH) return nj_tanh(v);
@@ -108,7 +128,7 @@ struct NjLin {
     int K4;                         // float4 chunks along the reduction dimension
     const float* W; int w_s;        // image rows [4*OG][w_s]
     const float* bias;              // [4*OG] or nullptr
-    int O, OG;
+    int O, OG; unsigned mO;
     float* out; int out_s;
     int nrows;
     int act;                        // activation applied in the epilogue (NONE for the last layer)
@@ -120,8 +140,10 @@ template <int MR>
 NJ_HD void nj_tile_fwd(const NjLin& L, int tid, int nt) {
     const int RG = (L.nrows + MR - 1) / MR;
     const int ntiles = RG * L.OG;
+    if (tid >= ntiles) return;
+    const unsigned mRG = nj_magic(RG);
     for (int tile = tid; tile < ntiles; tile += nt) {
-        const int rg = tile % RG, og = tile / RG;
+        const int og = nj_div(tile, RG, mRG), rg = tile - og * RG;
         float acc[MR][4];
         const float* ap[MR];
         const float* wp[4];
@@ -173,7 +195,7 @@ struct NjDx {
     const float* g; int g_s;        // gradient wrt the layer's pre-activation output [nrows][g_s]
     int O4;                         // float4 chunks along out (= OG of the layer)
     const float* W; int w_s;
-    int Kin;                        // true input width
+    int Kin; unsigned mK;           // true input width (+ nj_magic)
     float* gin; int gin_s;
     int nrows;
     const float* aprev; int a_s; int act_prev;    // activations feeding this layer (nullptr: network input)
@@ -186,8 +208,10 @@ NJ_HD void nj_tile_dx(const NjDx& L, int tid, int nt) {
     const int RG = (L.nrows + MR - 1) / MR;
     const int KG = (L.Kin + 3) >> 2;
     const int ntiles = RG * KG;
+    if (tid >= ntiles) return;
+    const unsigned mRG = nj_magic(RG);
     for (int tile = tid; tile < ntiles; tile += nt) {
-        const int rg = tile % RG, kg = tile / RG;
+        const int kg = nj_div(tile, RG, mRG), rg = tile - kg * RG;
         float acc[MR][4];
         const float* gp[MR];
 #pragma unroll
@@ -238,12 +262,116 @@ NJ_HD void nj_tile_dx(const NjDx& L, int tid, int nt) {
     }
 }
 
+// ---- row-loop variants for tiles of few rows (whole-path batches: 14 records per CTA for a PhysioNet batch of 2000,
+// one at the reference's batch size of 50).  The 1x4 micro-tiles above leave most threads idle there and every thread
+// re-reads its weights for every row.  Here a thread owns ONE output (forward) / ONE input column (dx) and a slice of
+// the reduction dimension, loads that weight slice into registers ONCE per call and then walks the rows: per row only
+// broadcast loads of the activation slice + independent FMAs, so consecutive rows pipeline.  The KS partial sums of an
+// output meet in shared memory (scratch[kq][r][o]); a second phase, one thread per output element, sums them and
+// applies the epilogue.  ----
+#define NJ_RL_MAXROWS 4             // measured on B200: from ~8 rows up the 1x4 micro-tiles are faster again
+#define NJ_RL_SCRATCH 4096          // floats
+
+// forward: thread (kq, o), lane = o.  KC = float4 chunks of the reduction dimension per slice (template bound).
+template <int KC>
+NJ_HD void nj_rl_fwd1(const NjLin& L, int KS, int kc, float* scratch, int tid) {
+    const int O = L.O;
+    if (tid >= KS * O) return;
+    const int kq = nj_div(tid, O, L.mO), o = tid - kq * O;
+    const int c0 = kq * kc;
+    int nc = L.K4 - c0; nc = nc > kc ? kc : nc;
+    nj_f4 w[KC];
+    const float* wp = L.W + (size_t)o * L.w_s + 4 * c0;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        if (c < nc) w[c] = nj_ld4(wp + 4 * c);
+        else { w[c].x = 0.f; w[c].y = 0.f; w[c].z = 0.f; w[c].w = 0.f; }
+    }
+    const float* ap = L.in + 4 * c0;
+    float* sp = scratch + (size_t)kq * L.nrows * O + o;
+    for (int r = 0; r < L.nrows; ++r) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            if (c < nc) {
+                const nj_f4 a = nj_ld4(ap + (size_t)r * L.in_s + 4 * c);
+                s0 = fmaf(a.x, w[c].x, s0); s1 = fmaf(a.y, w[c].y, s1);
+                s2 = fmaf(a.z, w[c].z, s2); s3 = fmaf(a.w, w[c].w, s3);
+            }
+        }
+        sp[(size_t)r * O] = (s0 + s1) + (s2 + s3);
+    }
+}
+
+NJ_HD void nj_rl_fwd2(const NjLin& L, int KS, const float* scratch, int tid, int nt) {
+    const int O = L.O, n = L.nrows * O;
+    for (int idx = tid; idx < n; idx += nt) {
+        const int r = nj_div(idx, O, L.mO), o = idx - r * O;
+        float v = L.bias ? L.bias[o] : 0.f;
+        for (int kq = 0; kq < KS; ++kq) v += scratch[(size_t)kq * n + idx];
+        v = nj_act(v, L.act);
+        if (L.drop) v = nj_keep(nj_layer_key((unsigned)L.rk[r], L.tag), (unsigned)o, L.thr) ? v * L.keep_scale : 0.f;
+        L.out[(size_t)r * L.out_s + o] = v;
+    }
+}
+
+// dx: thread (oq, k), lane = k.  OC = groups of 4 outputs per slice (template bound).
+template <int OC>
+NJ_HD void nj_rl_dx1(const NjDx& L, int OS, int oc, float* scratch, int tid) {
+    const int K = L.Kin;
+    if (tid >= OS * K) return;
+    const int oq = nj_div(tid, K, L.mK), k = tid - oq * K;
+    const int c0 = oq * oc;
+    int nc = L.O4 - c0; nc = nc > oc ? oc : nc;
+    float w[OC][4];
+    const float* wp = L.W + (size_t)(4 * c0) * L.w_s + k;
+#pragma unroll
+    for (int c = 0; c < OC; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[c][i] = (c < nc) ? wp[(size_t)(4 * c + i) * L.w_s] : 0.f;
+    const float* gp = L.g + 4 * c0;
+    float* sp = scratch + (size_t)oq * L.nrows * K + k;
+    for (int r = 0; r < L.nrows; ++r) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < OC; ++c) {
+            if (c < nc) {
+                const nj_f4 g = nj_ld4(gp + (size_t)r * L.g_s + 4 * c);
+                s0 = fmaf(g.x, w[c][0], s0); s1 = fmaf(g.y, w[c][1], s1);
+                s2 = fmaf(g.z, w[c][2], s2); s3 = fmaf(g.w, w[c][3], s3);
+            }
+        }
+        sp[(size_t)r * K] = (s0 + s1) + (s2 + s3);
+    }
+}
+
+NJ_HD void nj_rl_dx2(const NjDx& L, int OS, const float* scratch, int tid, int nt) {
+    const int K = L.Kin, n = L.nrows * K;
+    for (int idx = tid; idx < n; idx += nt) {
+        const int r = nj_div(idx, K, L.mK), k = idx - r * K;
+        float v = 0.f;
+        for (int oq = 0; oq < OS; ++oq) v += scratch[(size_t)oq * n + idx];
+        if (L.aprev) {
+            float a = L.aprev[(size_t)r * L.a_s + k];
+            if (L.drop) {
+                if (nj_keep(nj_layer_key((unsigned)L.rk[r], L.tag_prev), (unsigned)k, L.thr)) { a *= L.one_minus_p; v *= L.keep_scale; }
+                else { v = 0.f; a = 0.f; }
+            }
+            if (L.act_prev == NJODE_ACT_TANH) v *= (1.f - a * a);
+            else if (L.act_prev == NJODE_ACT_RELU) v = a > 0.f ? v : 0.f;
+        }
+        L.gin[(size_t)r * L.gin_s + k] = v;
+    }
+}
+
 // dW[o][k] += sum_r g[r][o] a[r][k] ; db[o] += sum_r g[r][o]   (thread-owned 4x4 blocks of the image)
 NJ_HD void nj_tile_dw(const float* g, int g_s, int OG, const float* a, int a_s, int K4, int nrows,
                       float* dW, int w_s, float* db, int tid, int nt) {
     const int ntiles = OG * K4;
+    if (tid >= ntiles) return;
+    const unsigned mK4 = nj_magic(K4);
     for (int tile = tid; tile < ntiles; tile += nt) {
-        const int kg = tile % K4, og = tile / K4;
+        const int og = nj_div(tile, K4, mK4), kg = tile - og * K4;
         float acc[4][4];
         float bs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -307,7 +435,7 @@ struct NjCta {
     float* dimg;               // gradient image: shared-memory part [0, dimg_floats) ...
     float* gpart;              // ... and this CTA's partial image in global memory for the rest
     float *IN, *ACT, *OUT, *Hs, *LX, *XI, *YBJ, *YY, *XH, *EE, *GOUT, *GTMP, *GA, *GB, *GH, *GX, *GYBJ, *F;
-    float *GI, *GHH;
+    float *GI, *GHH, *KSB;
     int *I, *CTL;
     int tid0, nt;              // nt: threads; (tid comes from NJ_THREADS)
 };
@@ -317,7 +445,7 @@ NJ_HD void nj_cta_bind(NjCta& t, const NjCfg& c, float* smem, bool bwd) {
     t.IN = smem + c.o_IN; t.ACT = smem + c.o_ACT; t.OUT = smem + c.o_OUT; t.Hs = smem + c.o_H;
     t.LX = smem + c.o_LX; t.XI = smem + c.o_XI; t.YBJ = smem + c.o_YBJ; t.YY = smem + c.o_YY;
     t.XH = smem + c.o_XH; t.EE = smem + c.o_EE; t.F = smem + c.o_F;
-    t.GI = smem + c.o_GI; t.GHH = smem + c.o_GHH;
+    t.GI = smem + c.o_GI; t.GHH = smem + c.o_GHH; t.KSB = smem + c.o_KS;
     t.I = reinterpret_cast<int*>(smem + c.o_I); t.CTL = t.I + NJ_I_COUNT * c.P;
     t.GOUT = t.GTMP = t.GA = t.GB = t.GH = t.GX = t.GYBJ = nullptr;
     if (bwd) {
@@ -360,16 +488,29 @@ NJ_HDN void nj_mlp_forward(NjCta& t, int netid, int nrows, bool skip_last) {
         L.in = in; L.in_s = in_s; L.K4 = (N.dim[l] + 3) >> 2;
         L.W = t.wimg + N.w_img[l]; L.w_s = N.ks[l];
         L.bias = N.b_src[l] >= 0 ? t.wimg + N.b_img[l] : nullptr;
-        L.O = N.dim[l + 1]; L.OG = N.og[l];
+        L.O = N.dim[l + 1]; L.OG = N.og[l]; L.mO = N.m_out[l];
         L.out = last ? t.OUT : t.ACT + (size_t)l * c.P * c.sACT; L.out_s = last ? c.sOUT : c.sACT;
         L.nrows = nrows; L.act = last ? NJODE_ACT_NONE : N.act[l];
         L.drop = (!last) && c.has_drop; L.thr = c.thr; L.keep_scale = c.keep_scale;
         L.rk = t.I + NJ_I_RK * c.P; L.tag = (unsigned)(netid * 16 + l + 1);
         const int mr = nj_pick_mr(nrows, L.OG, t.nt);
-        NJ_THREADS(tid, t.nt) {
-            if (mr == 4) nj_tile_fwd<4>(L, tid, t.nt);
-            else if (mr == 2) nj_tile_fwd<2>(L, tid, t.nt);
-            else nj_tile_fwd<1>(L, tid, t.nt);
+        const int kc = N.rl_f_kc[l];
+        const int ksl = nrows <= NJ_RL_MAXROWS ? N.rl_f_ns[l] : 0;
+        if (ksl > 0) {
+            NJ_THREADS(tid, t.nt) {
+                if (kc <= 1) nj_rl_fwd1<1>(L, ksl, kc, t.KSB, tid);
+                else if (kc <= 2) nj_rl_fwd1<2>(L, ksl, kc, t.KSB, tid);
+                else if (kc <= 4) nj_rl_fwd1<4>(L, ksl, kc, t.KSB, tid);
+                else nj_rl_fwd1<8>(L, ksl, kc, t.KSB, tid);
+            }
+            NJ_SYNC();
+            NJ_THREADS(tid, t.nt) { nj_rl_fwd2(L, ksl, t.KSB, tid, t.nt); }
+        } else {
+            NJ_THREADS(tid, t.nt) {
+                if (mr == 4) nj_tile_fwd<4>(L, tid, t.nt);
+                else if (mr == 2) nj_tile_fwd<2>(L, tid, t.nt);
+                else nj_tile_fwd<1>(L, tid, t.nt);
+            }
         }
         NJ_SYNC();
         in = L.out; in_s = L.out_s;
@@ -391,7 +532,7 @@ NJ_HDN float* nj_mlp_backward(NjCta& t, int netid, int nrows, bool need_in_grad)
         const bool dx = (l > 0) || need_in_grad;
         NjDx D;
         D.g = g; D.g_s = g_s; D.O4 = N.og[l]; D.W = t.wimg + N.w_img[l]; D.w_s = N.ks[l];
-        D.Kin = N.dim[l]; D.gin = nxt; D.gin_s = c.sG; D.nrows = nrows;
+        D.Kin = N.dim[l]; D.mK = N.m_in[l]; D.gin = nxt; D.gin_s = c.sG; D.nrows = nrows;
         D.aprev = l > 0 ? inp : nullptr; D.a_s = inp_s; D.act_prev = l > 0 ? N.act[l - 1] : NJODE_ACT_NONE;
         D.drop = c.has_drop; D.thr = c.thr; D.keep_scale = c.keep_scale; D.one_minus_p = c.one_minus_p;
         D.rk = t.I + NJ_I_RK * c.P; D.tag_prev = (unsigned)(netid * 16 + l);
@@ -399,15 +540,30 @@ NJ_HDN float* nj_mlp_backward(NjCta& t, int netid, int nrows, bool need_in_grad)
         float* dbase = (N.b_img[l] + N.rp[l] <= c.dimg_floats) ? t.dimg : t.gpart;
         float* dW = dbase + N.w_img[l];
         float* db = N.b_src[l] >= 0 ? dbase + N.b_img[l] : nullptr;
+        // small tiles: the dW micro-tiles take the first threads, the row-loop dx slices the rest of the CTA
+        const int dx_t0 = N.rl_d_t0[l], oc = N.rl_d_oc[l];
+        const int osl = (dx && nrows <= NJ_RL_MAXROWS) ? N.rl_d_ns[l] : 0;
         NJ_THREADS(tid, t.nt) {
             nj_tile_dw(g, g_s, N.og[l], inp, inp_s, (N.dim[l] + 3) >> 2, nrows, dW, N.ks[l], db, tid, t.nt);
             if (dx) {
-                if (mr == 4) nj_tile_dx<4>(D, tid, t.nt);
+                if (osl > 0) {
+                    const int tid2 = tid - dx_t0;
+                    if (tid2 < 0) { }
+                    else if (oc <= 1) nj_rl_dx1<1>(D, osl, oc, t.KSB, tid2);
+                    else if (oc <= 2) nj_rl_dx1<2>(D, osl, oc, t.KSB, tid2);
+                    else if (oc <= 4) nj_rl_dx1<4>(D, osl, oc, t.KSB, tid2);
+                    else nj_rl_dx1<8>(D, osl, oc, t.KSB, tid2);
+                }
+                else if (mr == 4) nj_tile_dx<4>(D, tid, t.nt);
                 else if (mr == 2) nj_tile_dx<2>(D, tid, t.nt);
                 else nj_tile_dx<1>(D, tid, t.nt);
             }
         }
         NJ_SYNC();
+        if (osl > 0) {
+            NJ_THREADS(tid, t.nt) { nj_rl_dx2(D, osl, t.KSB, tid, t.nt); }
+            NJ_SYNC();
+        }
         if (dx) { res = nxt; g = nxt; g_s = c.sG; nxt = (nxt == t.GA) ? t.GB : t.GA; }
     }
     return need_in_grad ? res : nullptr;
@@ -480,7 +636,7 @@ NJ_HDN void nj_record(NjCta& t, const NjArgs& a, int nu, int e, unsigned event_k
     const NjCfg& c = *t.c;
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nu * c.H; idx += t.nt) {
-            const int u = idx / c.H, c_ = idx % c.H;
+            const int u = nj_div(idx, c.H, c.m_H), c_ = idx - u * c.H;
             const int p = NJ_IU(t, NJ_I_PATH, u);
             const float h = t.Hs[u * c.sH + c_];
             t.IN[(size_t)u * c.sIN + c_] = nj_tanh(h);
@@ -492,11 +648,47 @@ NJ_HDN void nj_record(NjCta& t, const NjArgs& a, int nu, int e, unsigned event_k
     nj_mlp_forward(t, NJODE_NET_RO, nu, false);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nu * c.dout; idx += t.nt) {
-            const int u = idx / c.dout, c_ = idx % c.dout;
+            const int u = nj_div(idx, c.dout, c.m_dout), c_ = idx - u * c.dout;
             const int p = NJ_IU(t, NJ_I_PATH, u);
             float y = t.OUT[u * c.sOUT + c_];
             if (c.residual) y += nj_resid(t.Hs + u * c.sH, c.H, c.dout, c_);
             a.path_y[((size_t)e * a.b.B + p) * c.dout + c_] = y;
+        }
+    }
+    NJ_SYNC();
+}
+
+// lockstep iteration (relative Euler-step index) at which each unit meets its next pending jump, and the first such
+// iteration over the tile (forward: min, reverse: max; none: INT_MAX / -1) in CTL[NJ_CTL_NEXT].  Refreshed when a
+// tile is loaded and after every jump, so the march only looks for jumps (nj_find_jumps: compaction, dependent global
+// loads, two barriers) at the iterations that have one.
+NJ_HDN void nj_next_jump(NjCta& t, const NjArgs& a, int j, bool reverse) {
+    const NjCfg& c = *t.c;
+    NJ_THREADS(tid, t.nt) {
+        if (tid < c.P) {
+            int nxt = reverse ? -1 : 0x7FFFFFFF;
+            const int len = NJ_IU(t, NJ_I_LEN, tid);
+            if (len >= 0) {
+                const int cur = NJ_IU(t, NJ_I_CUR, tid);
+                const int idx = reverse ? cur - 1 : cur;
+                const bool has = reverse ? (idx >= NJ_IU(t, NJ_I_C0, tid)) : (idx < NJ_IU(t, NJ_I_C1, tid));
+                if (has) {
+                    const int rel = NJ_LDG(a.b.jump_step + NJ_LDG(a.b.row_jump + NJ_LDG(a.b.path_rows + idx))) - NJ_IU(t, NJ_I_S0, tid);
+                    if (rel >= 0 && rel <= len && (reverse ? rel <= j : rel >= j)) nxt = rel;
+                }
+            }
+            NJ_IU(t, NJ_I_NEXT, tid) = nxt;
+        }
+    }
+    NJ_SYNC();
+    NJ_THREADS(tid, t.nt) {
+        if (tid == 0) {
+            int m = reverse ? -1 : 0x7FFFFFFF;
+            for (int u = 0; u < c.P; ++u) {
+                const int v = NJ_IU(t, NJ_I_NEXT, u);
+                m = reverse ? (v > m ? v : m) : (v < m ? v : m);
+            }
+            t.CTL[NJ_CTL_NEXT] = m;
         }
     }
     NJ_SYNC();
@@ -559,7 +751,7 @@ NJ_HDN void nj_gru_forward(NjCta& t, const NjArgs& a, int nj) {
     const int H = c.H;
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
-            const int jr = idx / c.d, c_ = idx % c.d;
+            const int jr = nj_div(idx, c.d, c.m_d), c_ = idx - jr * c.d;
             const float x = NJ_LDG(a.b.X + (size_t)NJ_IU(t, NJ_I_JROW, jr) * c.d + c_);
             t.XI[jr * c.sD + c_] = x;
             t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(x);
@@ -569,11 +761,11 @@ NJ_HDN void nj_gru_forward(NjCta& t, const NjArgs& a, int nj) {
     nj_mlp_forward(t, NJODE_NET_GRU_IH, nj, false);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * 3 * H; idx += t.nt) {
-            const int jr = idx / (3 * H), k = idx % (3 * H);
+            const int jr = nj_div(idx, (3 * H), c.m_3H), k = idx - jr * (3 * H);
             t.GI[jr * c.s3H + k] = t.OUT[jr * c.sOUT + k];
         }
         for (int idx = tid; idx < nj * H; idx += t.nt) {
-            const int jr = idx / H, c_ = idx % H;
+            const int jr = nj_div(idx, H, c.m_H), c_ = idx - jr * H;
             t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.XH[jr * c.sH + c_]);
         }
     }
@@ -581,7 +773,7 @@ NJ_HDN void nj_gru_forward(NjCta& t, const NjArgs& a, int nj) {
     nj_mlp_forward(t, NJODE_NET_GRU_HH, nj, false);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * H; idx += t.nt) {
-            const int jr = idx / H, c_ = idx % H;
+            const int jr = nj_div(idx, H, c.m_H), c_ = idx - jr * H;
             float* gi = t.GI + jr * c.s3H;
             float* gh = t.GHH + jr * c.s3H;
             const float* o = t.OUT + jr * c.sOUT;
@@ -604,7 +796,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
     // (a) readout input = tanh(h before the jump)
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-            const int jr = idx / c.H, c_ = idx % c.H;
+            const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
             const int u = NJ_IU(t, NJ_I_JMAP, jr);
             const float h = t.Hs[u * c.sH + c_];
             t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(h);
@@ -618,7 +810,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
     // (c) Y_bj, imputation, encoder input
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
-            const int jr = idx / c.dout, c_ = idx % c.dout;
+            const int jr = nj_div(idx, c.dout, c.m_dout), c_ = idx - jr * c.dout;
             float y = t.OUT[jr * c.sOUT + c_];
             if (c.residual) y += nj_resid(t.XH + jr * c.sH, c.H, c.dout, c_);
             t.YBJ[jr * c.sDO + c_] = y;
@@ -630,7 +822,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
         nj_gru_forward(t, a, nj);
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-                const int jr = idx / c.H, c_ = idx % c.H;
+                const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
                 const float e = t.EE[jr * c.sH + c_];
                 t.Hs[NJ_IU(t, NJ_I_JMAP, jr) * c.sH + c_] = e;
                 t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(e);
@@ -641,7 +833,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
     } else {
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
-            const int jr = idx / c.d, c_ = idx % c.d;
+            const int jr = nj_div(idx, c.d, c.m_d), c_ = idx - jr * c.d;
             const int r = NJ_IU(t, NJ_I_JROW, jr);
             float x = NJ_LDG(a.b.X + (size_t)r * c.d + c_);
             if (c.masked) {
@@ -659,7 +851,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
     // (e) new hidden state, readout input
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-            const int jr = idx / c.H, c_ = idx % c.H;
+            const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
             const int u = NJ_IU(t, NJ_I_JMAP, jr);
             float e = t.OUT[jr * c.sOUT + c_];
             if (c.residual) e += nj_resid(t.XI + jr * c.sD, c.d, c.H, c_);
@@ -673,7 +865,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
     nj_mlp_forward(t, NJODE_NET_RO, nj, false);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
-            const int jr = idx / c.dout, c_ = idx % c.dout;
+            const int jr = nj_div(idx, c.dout, c.m_dout), c_ = idx - jr * c.dout;
             const int u = NJ_IU(t, NJ_I_JMAP, jr);
             float y = t.OUT[jr * c.sOUT + c_];
             if (c.residual) y += nj_resid(t.Hs + u * c.sH, c.H, c.dout, c_);
@@ -704,7 +896,7 @@ NJ_HDN void nj_jump_forward(NjCta& t, const NjArgs& a, int nj) {
             NJ_IU(t, NJ_I_CUR, u) += 1;
         }
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
-            const int jr = idx / c.d, c_ = idx % c.d;
+            const int jr = nj_div(idx, c.d, c.m_d), c_ = idx - jr * c.d;
             const int u = NJ_IU(t, NJ_I_JMAP, jr);
             t.LX[u * c.sD + c_] = c.masked ? t.YY[jr * c.sDO + c_] : NJ_LDG(a.b.X + (size_t)NJ_IU(t, NJ_I_JROW, jr) * c.d + c_);
         }
@@ -728,14 +920,18 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
     nj_zero(smem + c.o_IN, c.o_I - c.o_IN, t.nt);
     NJ_SYNC();
     const bool rec = a.b.E > 0;
+    // whole-path units jump at a few of their thousands of lockstep iterations: look for jumps only where the tile
+    // has one (nj_next_jump).  Segment units jump at almost every iteration of a tile: look every time.
+    const bool gate = !rec && a.b.unit_kind == 0;
     for (int tile = cta; tile < a.n_tiles; tile += ncta) {
         nj_load_units(t, a, tile, false);
+        if (gate) nj_next_jump(t, a, 0, false);
         const int nu = (a.b.n_units - tile * c.P) < c.P ? (a.b.n_units - tile * c.P) : c.P;
         const int maxlen = t.CTL[NJ_CTL_MAXLEN];
         // ---- start: h = encoder(start value)  (NJODE/models.py:411-419) ----
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nu * c.d; idx += t.nt) {
-                const int u = idx / c.d, c_ = idx % c.d;
+                const int u = nj_div(idx, c.d, c.m_d), c_ = idx - u * c.d;
                 nj_state_from_row(t, a, u, c_, NJ_IU(t, NJ_I_START, u));
                 // the start value of a segment is the *observation* X[row] (non-masked only)
                 const int sr = NJ_IU(t, NJ_I_START, u);
@@ -755,7 +951,7 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
         nj_mlp_forward(t, NJODE_NET_ENC, nu, false);
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nu * c.H; idx += t.nt) {
-                const int u = idx / c.H, c_ = idx % c.H;
+                const int u = nj_div(idx, c.H, c.m_H), c_ = idx - u * c.H;
                 float e = t.OUT[u * c.sOUT + c_];
                 if (c.residual) e += nj_resid(t.XI + u * c.sD, c.d, c.H, c_);
                 t.Hs[u * c.sH + c_] = e;
@@ -771,19 +967,22 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
                 if (rec) {
                     if (!(gi < a.b.K && NJ_LDG(a.b.jump_step + gi) == j)) break;
                     only = gi;
-                }
+                } else if (gate && t.CTL[NJ_CTL_NEXT] != j) break;  // no unit of the tile jumps before step s0 + j
                 nj_find_jumps(t, a, j, only, false);
                 const int nj = t.CTL[NJ_CTL_NJ];
                 if (nj > 0) nj_jump_forward(t, a, nj);
                 if (rec) { nj_record(t, a, nu, NJ_LDG(a.b.jump_event + gi), NJ_EVENT_JUMP_BASE + 3u * (unsigned)gi + 2u); ++gi; }
-                else if (nj == 0) break;
+                else {
+                    if (nj == 0) break;
+                    if (gate) nj_next_jump(t, a, j, false);
+                }
                 NJ_SYNC();
             }
             if (j == maxlen) break;
             // ---- Euler step k = s0 + j of every unit that still has one  (NJODE/models.py:369-377) ----
             NJ_THREADS(tid, t.nt) {
                 for (int idx = tid; idx < nu * c.inf; idx += t.nt) {
-                    const int u = idx / c.inf, c_ = idx % c.inf;
+                    const int u = nj_div(idx, c.inf, c.m_inf), c_ = idx - u * c.inf;
                     const bool active = j < NJ_IU(t, NJ_I_LEN, u);
                     const int k = NJ_IU(t, NJ_I_S0, u) + j;
                     float hval = 0.f;
@@ -802,7 +1001,7 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
             nj_mlp_forward(t, NJODE_NET_ODE, nu, false);
             NJ_THREADS(tid, t.nt) {
                 for (int idx = tid; idx < nu * c.H; idx += t.nt) {
-                    const int u = idx / c.H, c_ = idx % c.H;
+                    const int u = nj_div(idx, c.H, c.m_H), c_ = idx - u * c.H;
                     if (j < NJ_IU(t, NJ_I_LEN, u))
                         t.Hs[u * c.sH + c_] = fmaf(NJ_FU(t, NJ_F_DT, u), t.OUT[u * c.sOUT + c_], t.Hs[u * c.sH + c_]);
                 }
@@ -813,7 +1012,7 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
         // ---- hT ----
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nu * c.H; idx += t.nt) {
-                const int u = idx / c.H, c_ = idx % c.H;
+                const int u = nj_div(idx, c.H, c.m_H), c_ = idx - u * c.H;
                 if (NJ_IU(t, NJ_I_FLAG, u)) a.hT[(size_t)NJ_IU(t, NJ_I_PATH, u) * c.H + c_] = t.Hs[u * c.sH + c_];
             }
         }
@@ -828,7 +1027,7 @@ NJ_HDN void nj_reload_state(NjCta& t, const NjArgs& a, int nu) {
     const NjCfg& c = *t.c;
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nu * c.d; idx += t.nt) {
-            const int u = idx / c.d, c_ = idx % c.d;
+            const int u = nj_div(idx, c.d, c.m_d), c_ = idx - u * c.d;
             const int cur = NJ_IU(t, NJ_I_CUR, u);
             const int p = NJ_IU(t, NJ_I_PATH, u);
             const int prev = (cur - 1 >= NJ_LDG(a.b.path_ptr + p)) ? NJ_LDG(a.b.path_rows + cur - 1) : -1;
@@ -844,7 +1043,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     // 1. readout at h_before -> Y_bj
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-            const int jr = idx / c.H, c_ = idx % c.H;
+            const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
             const float h = a.h_before[(size_t)NJ_IU(t, NJ_I_JROW, jr) * c.H + c_];
             t.XH[jr * c.sH + c_] = h;
             t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(h);
@@ -855,7 +1054,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     nj_mlp_forward(t, NJODE_NET_RO, nj, false);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
-            const int jr = idx / c.dout, c_ = idx % c.dout;
+            const int jr = nj_div(idx, c.dout, c.m_dout), c_ = idx - jr * c.dout;
             float y = t.OUT[jr * c.sOUT + c_];
             if (c.residual) y += nj_resid(t.XH + jr * c.sH, c.H, c.dout, c_);
             t.YBJ[jr * c.sDO + c_] = y;
@@ -867,7 +1066,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
         nj_gru_forward(t, a, nj);
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-                const int jr = idx / c.H, c_ = idx % c.H;
+                const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
                 t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.EE[jr * c.sH + c_]);
             }
             nj_set_jump_keys(t, a, nj, 2, tid);
@@ -876,7 +1075,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     } else {
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
-            const int jr = idx / c.d, c_ = idx % c.d;
+            const int jr = nj_div(idx, c.d, c.m_d), c_ = idx - jr * c.d;
             const int r = NJ_IU(t, NJ_I_JROW, jr);
             float x = NJ_LDG(a.b.X + (size_t)r * c.d + c_);
             if (c.masked) {
@@ -893,7 +1092,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     nj_mlp_forward(t, NJODE_NET_ENC, nj, false);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-            const int jr = idx / c.H, c_ = idx % c.H;
+            const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
             float e = t.OUT[jr * c.sOUT + c_];
             if (c.residual) e += nj_resid(t.XI + jr * c.sD, c.d, c.H, c_);
             t.EE[jr * c.sH + c_] = e;
@@ -907,7 +1106,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     nj_mlp_forward(t, NJODE_NET_RO, nj, false);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
-            const int jr = idx / c.dout, c_ = idx % c.dout;
+            const int jr = nj_div(idx, c.dout, c.m_dout), c_ = idx - jr * c.dout;
             float y = t.OUT[jr * c.sOUT + c_];
             if (c.residual) y += nj_resid(t.EE + jr * c.sH, c.H, c.dout, c_);
             t.YY[jr * c.sDO + c_] = y;
@@ -938,7 +1137,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     NJ_SYNC();
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
-            const int jr = idx / c.dout, c_ = idx % c.dout;
+            const int jr = nj_div(idx, c.dout, c.m_dout), c_ = idx - jr * c.dout;
             const int u = NJ_IU(t, NJ_I_JMAP, jr), r = NJ_IU(t, NJ_I_JROW, jr);
             const float x = NJ_LDG(a.b.X + (size_t)r * c.d + c_);
             const float m = c.masked ? NJ_LDG(a.b.M + (size_t)r * c.d + c_) : 1.f;
@@ -957,7 +1156,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     float* gin = nj_mlp_backward(t, NJODE_NET_RO, nj, true);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-            const int jr = idx / c.H, c_ = idx % c.H;
+            const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
             const int u = NJ_IU(t, NJ_I_JMAP, jr);
             const float th = t.IN[(size_t)jr * c.sIN + c_];
             float ge = t.GH[u * c.sH + c_] + gin[jr * c.sG + c_] * (1.f - th * th);
@@ -971,7 +1170,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
         const int H = c.H;
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nj * H; idx += t.nt) {
-                const int jr = idx / H, c_ = idx % H;
+                const int jr = nj_div(idx, H, c.m_H), c_ = idx - jr * H;
                 float* gi = t.GI + jr * c.s3H;
                 const float* gh = t.GHH + jr * c.s3H;
                 float* go = t.GOUT + jr * c.sOUT;
@@ -990,19 +1189,19 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
         gin = nj_mlp_backward(t, NJODE_NET_GRU_HH, nj, true);
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nj * H; idx += t.nt) {
-                const int jr = idx / H, c_ = idx % H;
+                const int jr = nj_div(idx, H, c.m_H), c_ = idx - jr * H;
                 const float hh = t.GHH[jr * c.s3H + c_];
                 t.EE[jr * c.sH + c_] = (t.EE[jr * c.sH + c_] + gin[jr * c.sG + c_]) * (1.f - hh * hh);
             }
             for (int idx = tid; idx < nj * 3 * H; idx += t.nt) {
-                const int jr = idx / (3 * H), k = idx % (3 * H);
+                const int jr = nj_div(idx, (3 * H), c.m_3H), k = idx - jr * (3 * H);
                 t.GOUT[jr * c.sOUT + k] = t.GI[jr * c.s3H + k];
             }
         }
         NJ_SYNC();
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nj * c.d; idx += t.nt) {
-                const int jr = idx / c.d, c_ = idx % c.d;
+                const int jr = nj_div(idx, c.d, c.m_d), c_ = idx - jr * c.d;
                 t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.XI[jr * c.sD + c_]);
             }
         }
@@ -1011,12 +1210,12 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     } else {
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
-            const int jr = idx / c.d, c_ = idx % c.d;
+            const int jr = nj_div(idx, c.d, c.m_d), c_ = idx - jr * c.d;
             t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.XI[jr * c.sD + c_]);
             if (c.masked) t.IN[(size_t)jr * c.sIN + c.d + c_] = NJ_LDG(a.b.M + (size_t)NJ_IU(t, NJ_I_JROW, jr) * c.d + c_);
         }
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-            const int jr = idx / c.H, c_ = idx % c.H;
+            const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
             t.GOUT[jr * c.sOUT + c_] = t.GTMP[jr * c.sOUT + c_];
         }
         nj_set_jump_keys(t, a, nj, 1, tid);
@@ -1027,7 +1226,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     if (c.masked) {
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nj * c.d; idx += t.nt) {
-                const int jr = idx / c.d, c_ = idx % c.d;
+                const int jr = nj_div(idx, c.d, c.m_d), c_ = idx - jr * c.d;
                 const float tx = t.IN[(size_t)jr * c.sIN + c_];
                 float gx = gin[jr * c.sG + c_] * (1.f - tx * tx);
                 if (c.residual) gx += nj_resid_bwd(t.GOUT + jr * c.sOUT, c.d, c.H, c_);
@@ -1041,11 +1240,11 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     // 6. readout recompute at h_before + backward -> gradient wrt h before the jump
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-            const int jr = idx / c.H, c_ = idx % c.H;
+            const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
             t.IN[(size_t)jr * c.sIN + c_] = nj_tanh(t.XH[jr * c.sH + c_]);
         }
         for (int idx = tid; idx < nj * c.dout; idx += t.nt) {
-            const int jr = idx / c.dout, c_ = idx % c.dout;
+            const int jr = nj_div(idx, c.dout, c.m_dout), c_ = idx - jr * c.dout;
             t.GOUT[jr * c.sOUT + c_] = t.GYBJ[jr * c.sDO + c_];
         }
         nj_set_jump_keys(t, a, nj, 0, tid);
@@ -1055,7 +1254,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
     gin = nj_mlp_backward(t, NJODE_NET_RO, nj, true);
     NJ_THREADS(tid, t.nt) {
         for (int idx = tid; idx < nj * c.H; idx += t.nt) {
-            const int jr = idx / c.H, c_ = idx % c.H;
+            const int jr = nj_div(idx, c.H, c.m_H), c_ = idx - jr * c.H;
             const int u = NJ_IU(t, NJ_I_JMAP, jr);
             const float th = t.IN[(size_t)jr * c.sIN + c_];
             float gh = gin[jr * c.sG + c_] * (1.f - th * th);
@@ -1064,7 +1263,7 @@ NJ_HDN void nj_jump_backward(NjCta& t, const NjArgs& a, int nj) {
             t.GH[u * c.sH + c_] = gh;
         }
         for (int idx = tid; idx < nj * c.d; idx += t.nt) {
-            const int jr = idx / c.d, c_ = idx % c.d;
+            const int jr = nj_div(idx, c.d, c.m_d), c_ = idx - jr * c.d;
             t.GX[NJ_IU(t, NJ_I_JMAP, jr) * c.sD + c_] = 0.f;
         }
         if (tid < nj) NJ_IU(t, NJ_I_CUR, NJ_IU(t, NJ_I_JMAP, tid)) -= 1;
@@ -1086,16 +1285,18 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
     if (c.dimg_floats < c.img_floats) nj_zero(gpart + c.dimg_floats, c.img_floats - c.dimg_floats, t.nt);
     nj_zero(smem + c.o_IN, c.o_I - c.o_IN, t.nt);
     NJ_SYNC();
+    const bool gate = a.b.unit_kind == 0;          // see nj_cta_forward
     for (int tile = cta; tile < a.n_tiles; tile += ncta) {
         nj_load_units(t, a, tile, true);
         const int nu = (a.b.n_units - tile * c.P) < c.P ? (a.b.n_units - tile * c.P) : c.P;
         const int maxlen = t.CTL[NJ_CTL_MAXLEN];
+        if (gate) nj_next_jump(t, a, maxlen, true);
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nu * c.H; idx += t.nt) {
-                const int u = idx / c.H, c_ = idx % c.H;
+                const int u = nj_div(idx, c.H, c.m_H), c_ = idx - u * c.H;
                 t.GH[u * c.sH + c_] = (NJ_IU(t, NJ_I_FLAG, u) && a.grad_hT) ? NJ_LDG(a.grad_hT + (size_t)NJ_IU(t, NJ_I_PATH, u) * c.H + c_) : 0.f;
             }
-            for (int idx = tid; idx < nu * c.d; idx += t.nt) t.GX[(idx / c.d) * c.sD + idx % c.d] = 0.f;
+            for (int idx = tid; idx < nu * c.d; idx += t.nt) { const int u = nj_div(idx, c.d, c.m_d); t.GX[u * c.sD + idx - u * c.d] = 0.f; }
         }
         NJ_SYNC();
         nj_reload_state(t, a, nu);
@@ -1104,7 +1305,7 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
                 // ---- reverse of Euler step k = s0 + j ----
                 NJ_THREADS(tid, t.nt) {
                     for (int idx = tid; idx < nu * c.inf; idx += t.nt) {
-                        const int u = idx / c.inf, c_ = idx % c.inf;
+                        const int u = nj_div(idx, c.inf, c.m_inf), c_ = idx - u * c.inf;
                         const bool active = j < NJ_IU(t, NJ_I_LEN, u);
                         const int k = NJ_IU(t, NJ_I_S0, u) + j;
                         float hval = 0.f;
@@ -1120,7 +1321,7 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
                 NJ_SYNC();
                 NJ_THREADS(tid, t.nt) {
                     for (int idx = tid; idx < nu * c.H; idx += t.nt) {
-                        const int u = idx / c.H, c_ = idx % c.H;
+                        const int u = nj_div(idx, c.H, c.m_H), c_ = idx - u * c.H;
                         t.GOUT[u * c.sOUT + c_] = NJ_FU(t, NJ_F_DT, u) * t.GH[u * c.sH + c_];
                     }
                 }
@@ -1129,7 +1330,7 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
                 float* gin = nj_mlp_backward(t, NJODE_NET_ODE, nu, true);
                 NJ_THREADS(tid, t.nt) {
                     for (int idx = tid; idx < nu * (c.d + c.H); idx += t.nt) {
-                        const int u = idx / (c.d + c.H), c_ = idx % (c.d + c.H);
+                        const int u = nj_div(idx, (c.d + c.H), c.m_dH), c_ = idx - u * (c.d + c.H);
                         if (j >= NJ_IU(t, NJ_I_LEN, u)) continue;
                         const float th = t.IN[(size_t)u * c.sIN + c_];
                         const float g = gin[u * c.sG + c_] * (1.f - th * th);
@@ -1141,17 +1342,19 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
             }
             // ---- reverse of the jumps that fall before step s0 + j ----
             for (;;) {
+                if (gate && t.CTL[NJ_CTL_NEXT] != j) break;            // no unit of the tile jumped before step s0 + j
                 nj_find_jumps(t, a, j, -1, true);
                 const int nj = t.CTL[NJ_CTL_NJ];
                 if (nj == 0) break;
                 nj_jump_backward(t, a, nj);
                 nj_reload_state(t, a, nu);
+                if (gate) nj_next_jump(t, a, j, true);
             }
         }
         // ---- reverse of the start encoder ----
         NJ_THREADS(tid, t.nt) {
             for (int idx = tid; idx < nu * c.d; idx += t.nt) {
-                const int u = idx / c.d, c_ = idx % c.d;
+                const int u = nj_div(idx, c.d, c.m_d), c_ = idx - u * c.d;
                 const int sr = NJ_IU(t, NJ_I_START, u);
                 const float x = sr < 0 ? NJ_LDG(a.b.start_X + (size_t)NJ_IU(t, NJ_I_PATH, u) * c.d + c_)
                                        : NJ_LDG(a.b.X + (size_t)sr * c.d + c_);
@@ -1159,7 +1362,7 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
                 if (c.masked) t.IN[(size_t)u * c.sIN + c.d + c_] = 0.f;
             }
             for (int idx = tid; idx < nu * c.H; idx += t.nt) {
-                const int u = idx / c.H, c_ = idx % c.H;
+                const int u = nj_div(idx, c.H, c.m_H), c_ = idx - u * c.H;
                 t.GOUT[u * c.sOUT + c_] = t.GH[u * c.sH + c_];
             }
             if (tid < nu) {

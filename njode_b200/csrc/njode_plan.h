@@ -45,15 +45,50 @@ static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, bool compact, 
             N.w_img[l] = off; off += N.rp[l] * N.ks[l];
             N.b_img[l] = off; off += N.rp[l];
             N.w_src[l] = s.w_off[l]; N.b_src[l] = s.b_off[l];
+            N.m_in[l] = nj_magic_host(s.dims[l]); N.m_out[l] = nj_magic_host(s.dims[l + 1]);
         }
     }
     c.img_floats = off;
     return true;
 }
 
+// slices for the row-loop layer GEMMs (nj_rl_* in njode_core.cuh): `width` threads side by side (outputs / input
+// columns), `chunks` groups of 4 along the reduction.  Returns the number of slices (0: micro-tile path) and the chunks
+// per slice.
+static inline int nj_rl_pick(int nrows, int width, int chunks, int nt, int& per) {
+    per = 0;
+    if (nrows > NJ_RL_MAXROWS || width > nt || width < 1 || chunks < 1) return 0;
+    int ns = nt / width;
+    if (ns > chunks) ns = chunks;
+    if (ns > 16) ns = 16;
+    per = (chunks + ns - 1) / ns;
+    if (per > 8) return 0;
+    ns = (chunks + per - 1) / per;
+    if ((size_t)ns * nrows * width > NJ_RL_SCRATCH) return 0;
+    return ns;
+}
+
+static inline void nj_fill_rl(NjCfg& c) {
+    const char* off = getenv("NJODE_NO_ROWLOOP");
+    const bool on = !(off && atoi(off)) && c.P <= NJ_RL_MAXROWS;
+    for (int n = 0; n < NJODE_NUM_NETS; ++n) {
+        NjNet& N = c.net[n];
+        for (int l = 0; l < N.n; ++l) {
+            N.rl_f_ns[l] = N.rl_f_kc[l] = N.rl_d_t0[l] = N.rl_d_ns[l] = N.rl_d_oc[l] = 0;
+            if (!on) continue;
+            const int K4 = (N.dim[l] + 3) / 4;
+            N.rl_f_ns[l] = nj_rl_pick(c.P, N.dim[l + 1], K4, c.nt, N.rl_f_kc[l]);
+            const int dw_tiles = N.og[l] * K4;
+            N.rl_d_t0[l] = (dw_tiles + 2 * N.dim[l] <= c.nt) ? dw_tiles : 0;
+            N.rl_d_ns[l] = nj_rl_pick(c.P, N.dim[l], N.og[l], c.nt - N.rl_d_t0[l], N.rl_d_oc[l]);
+        }
+    }
+}
+
 // lays out shared memory for tile size P; returns the number of floats needed
 static inline void nj_layout(NjCfg& c, int P, int nt, bool bwd, bool w_smem, int dw_smem) {
     c.P = P; c.nt = nt; c.w_smem = w_smem; c.dw_smem = bwd ? dw_smem : 0;
+    nj_fill_rl(c);
     // gradient image part kept in shared memory: everything (1) or the ODE network's blocks (2; first in the image)
     c.dimg_floats = c.dw_smem == 1 ? c.img_floats : (c.dw_smem == 2 ? c.net[NJODE_NET_ENC].w_img[0] : 0);
     int o = 0;
@@ -69,6 +104,7 @@ static inline void nj_layout(NjCfg& c, int P, int nt, bool bwd, bool w_smem, int
     c.o_YY = o; o += P * c.sDO;
     c.o_XH = o; o += P * c.sH;
     c.o_EE = o; o += P * c.sH;
+    c.o_KS = o; o += NJ_RL_SCRATCH;
     c.o_GI = o; if (c.use_rnn) o += P * c.s3H;
     c.o_GHH = o; if (c.use_rnn) o += P * c.s3H;
     c.o_GOUT = c.o_GTMP = c.o_GA = c.o_GB = c.o_GH = c.o_GX = c.o_GYBJ = o;
@@ -115,6 +151,8 @@ static inline bool nj_make_cfg(const njode_model_t& m, NjCfg& c, bool compact, s
         if ((c.d <= c.H && c.H % c.d) || (c.d > c.H && c.d % c.H)) { err = "for residual: encoder sizes must be multiples"; return false; }
         if ((c.H <= c.dout && c.dout % c.H) || (c.H > c.dout && c.H % c.dout)) { err = "for residual: readout sizes must be multiples"; return false; }
     }
+    c.m_H = nj_magic_host(c.H); c.m_d = nj_magic_host(c.d); c.m_dout = nj_magic_host(c.dout);
+    c.m_inf = nj_magic_host(c.inf); c.m_dH = nj_magic_host(c.d + c.H); c.m_3H = nj_magic_host(3 * c.H);
     c.w = m.weight;
     const float p = m.dropout_p;
     c.has_drop = (m.training && p > 0.f) ? 1 : 0;
@@ -150,7 +188,6 @@ static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_u
                                 int num_sms, size_t smem_limit, int force_P, bool compact, NjPlanOut& out, std::string& err) {
     NjCfg base;
     if (!nj_make_cfg(m, base, compact, err)) return false;
-    const int nt = 256;
     int P_want = 64;
     if (n_units_fwd < 64 * num_sms) {
         const int waves = std::max(1, (n_units_fwd + 64 * num_sms - 1) / (64 * num_sms));
@@ -164,6 +201,10 @@ static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_u
     // residency options of one kernel at tile height P, best first; dw: 1 = whole gradient image in shared memory,
     // 2 = the ODE network's part only (the one every Euler step accumulates into), 0 = per-CTA partial in global memory
     auto place = [&](int P, bool need_w) {
+        // 256 threads whatever the tile height.  (Measured on B200: 1024-thread CTAs for the small tiles are 2-3x
+        // SLOWER -- the per-warp fixed cost of the ~12 barrier-separated phases of an Euler step dominates, not the
+        // arithmetic, so more warps means more issue slots spent on loop/phase boilerplate.)
+        const int nt = 256;
         out.fwd = base; out.bwd = base;
         bool okf = false, okb = false;
         for (int w = 1; w >= (need_w ? 1 : 0) && !okf; --w) {
@@ -193,7 +234,7 @@ static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_u
     const int tiles_b = (n_units_bwd + P_ - 1) / P_;
     auto per_sm = [&](size_t bytes, int nt) {
         int k = (int)((smem_limit + 1024) / (bytes + 1024));
-        k = std::min(k, 2048 / nt);
+        (void)nt;
         return std::max(1, std::min(k, 2));          // 128 registers x 256 threads: two CTAs per SM
     };
     out.grid_fwd = std::max(1, std::min(out.n_tiles, num_sms * per_sm(out.smem_fwd_bytes, out.fwd.nt)));
