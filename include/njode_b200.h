@@ -212,6 +212,20 @@ int njode_collate(const double* paths, const int32_t* observed, int64_t n_paths_
                   int32_t* time_ptr, int32_t* time_idx, float* start_X, int32_t* n_obs_ot,
                   int32_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* per-path CSR of observation rows + sorted work units of one batch (the njode_batch_t index arrays), built on the device
+ * from the raw collate arrays: replaces the per-observation-time slicing of X / obs_idx by time_ptr that NJODE.forward does
+ * in Python (NJODE/models.py:449-456) and the n_obs_ot bookkeeping of NJODE/train.py:501-507.
+ *   obs [N] path index of every row (rows time-major, path ascending inside a time: NJODE/data_utils.py:298-307),
+ *   time_ptr [K+1], jump_step [K] (host schedule); segments != 0: (path, inter-observation segment) units, else whole paths
+ *   path_ptr [B+1], path_rows [N], row_jump [N], unit_desc [(segments ? N + B : B) * 6] out
+ *   stats [6] out: units of length >= T1 / >= T2 among the loss units, among the tail units (njode_batch_t.seg_n1/seg_n2),
+ *                  duplicate (time, path) flag, index-out-of-range flag */
+int64_t njode_index_workspace_bytes(int32_t N, int32_t B);
+int njode_build_index(const int32_t* obs, int32_t N, const int32_t* time_ptr, int32_t K, const int32_t* jump_step,
+                      int32_t B, int32_t S, int32_t segments, int32_t T1, int32_t T2,
+                      int32_t* path_ptr, int32_t* path_rows, int32_t* row_jump, int32_t* unit_desc, int32_t* stats,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------- */
 /* device-side timing of the main forward / backward kernel of the most recent call (cudaEvents on
  * the launching stream); enable with njode_set_timing(1) or NJODE_TIMING=1. */

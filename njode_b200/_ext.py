@@ -92,6 +92,15 @@ class Lib:
             f.restype = C.c_int
         if d.njode_abi_version() != 4:
             raise NjodeError("njode_b200: ABI version mismatch in %s" % path)
+        # device index build (absent from the host simulation: the CPU-only tests use schedule.build_index_torch)
+        self.has_index = hasattr(d, "njode_build_index")
+        if self.has_index:
+            d.njode_index_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+            d.njode_index_workspace_bytes.restype = C.c_int64
+            d.njode_build_index.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+            d.njode_build_index.restype = C.c_int
         # tensor-core path (absent from the host simulation used by the CPU-only tests)
         self.has_wide = hasattr(d, "njode_wide_forward")
         if self.has_wide:
@@ -243,12 +252,37 @@ class Runner:
         # tile-height classes of the segment kernels: units at least T1 (T2) Euler steps long are marched in
         # the lowest (middle) tiles; thresholds follow the per-warp share of the batch's total work B * S
         index = {}
-        if not host_index:
+        if not host_index and self.is_cuda:
+            # njode_build_index: ~10 launches (histogram, scan, three stable radix sorts, unit kernels) behind one call
+            if not self.lib.has_index:
+                raise NjodeError("njode_b200: libnjode_b200.so lacks njode_build_index -- rebuild it")
+            obs_t = view_i32("obs_idx", N)
+            if obs_t.dtype != torch.int32:
+                obs_t = obs_t.to(torch.int32)
+            n_u = (N + B) if segments else B
+            out = torch.empty(B + 1 + 2 * N + 6 * n_u + 8, dtype=torch.int32, device=self.device)
+            path_ptr, path_rows, row_jump = out[:B + 1], out[B + 1:B + 1 + N], out[B + 1 + N:B + 1 + 2 * N]
+            unit_desc, stats = out[B + 1 + 2 * N:B + 1 + 2 * N + 6 * n_u], out[B + 1 + 2 * N + 6 * n_u:]
+            wsb = int(self.lib.dll.njode_index_workspace_bytes(N, B))
+            iws = getattr(self, "_iws", None)
+            if iws is None or iws.numel() < wsb:
+                iws = self._iws = torch.empty(int(wsb * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+            rc = self.lib.dll.njode_build_index(
+                _ptr(obs_t), N, _ptr(view_i32("time_ptr", K + 1)), K, _ptr(view_i32("jump_step", K)), B, sched.S,
+                1 if segments else 0, T1, T2, _ptr(path_ptr), _ptr(path_rows), _ptr(row_jump), _ptr(unit_desc), _ptr(stats),
+                _ptr(iws), iws.numel(), self._stream())
+            self.lib.check(rc, "njode_build_index")
+            index = {"path_ptr": path_ptr, "path_rows": path_rows, "row_jump": row_jump, "unit_desc": unit_desc}
+            keep.extend([out, obs_t])
+            n_loss = N if segments else B
+            st = stats[:6].tolist()                              # the one small device->host read of staging
+        elif not host_index:
+            # the host simulation used by the CPU-only tests: same arrays from a handful of tensor ops
             path_ptr, path_rows, row_jump, unit_desc, n_loss, stats = _sched.build_index_torch(
                 view_i32("obs_idx", N), view_i32("time_ptr", K + 1), view_i32("jump_step", K), B, sched.S, segments, T1, T2)
             index = {"path_ptr": path_ptr, "path_rows": path_rows, "row_jump": row_jump, "unit_desc": unit_desc}
             keep.extend(index.values())
-            st = [int(v) for v in stats.cpu()]                  # the one small device->host read of staging
+            st = [int(v) for v in stats.cpu()]
         if st[5]:
             raise IndexError("obs_idx out of range")
         if st[4]:
