@@ -709,7 +709,7 @@ NJ_HDN void nj_find_jumps(NjCta& t, const NjArgs& a, int j, int only_jump, bool 
                 if (has) {
                     const int r = NJ_LDG(a.b.path_rows + idx);
                     const int i = NJ_LDG(a.b.row_jump + r);
-                    if (NJ_LDG(a.b.jump_step + i) == NJ_IU(t, NJ_I_S0, tid) + j && (only_jump < 0 || i == only_jump))
+                    if ((j < 0 || NJ_LDG(a.b.jump_step + i) == NJ_IU(t, NJ_I_S0, tid) + j) && (only_jump < 0 || i == only_jump))
                         pend = r;
                 }
             }
@@ -923,6 +923,9 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
     // whole-path units jump at a few of their thousands of lockstep iterations: look for jumps only where the tile
     // has one (nj_next_jump).  Segment units jump at almost every iteration of a tile: look every time.
     const bool gate = !rec && a.b.unit_kind == 0;
+    // segment units end with their one jump and nothing follows it: all jumps of a tile are applied together after the
+    // march (one dense batch of rows through readout / encoder / readout) instead of one sparse event per unit
+    const bool defer = !rec && a.b.unit_kind == 1;
     for (int tile = cta; tile < a.n_tiles; tile += ncta) {
         nj_load_units(t, a, tile, false);
         if (gate) nj_next_jump(t, a, 0, false);
@@ -962,7 +965,7 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
         int gi = 0;    // global jump cursor (return_path: all units are whole paths with s0 = 0)
         for (int j = 0; j <= maxlen; ++j) {
             // ---- jumps that fall before Euler step s0 + j ----
-            for (;;) {
+            for (; !defer;) {
                 int only = -1;
                 if (rec) {
                     if (!(gi < a.b.K && NJ_LDG(a.b.jump_step + gi) == j)) break;
@@ -1008,6 +1011,12 @@ NJ_HD void nj_cta_forward(const NjCfg& c, const NjArgs& a, float* smem, int cta,
             }
             NJ_SYNC();
             if (rec) nj_record(t, a, nu, NJ_LDG(a.b.step_event + j), NJ_EVENT_PATH_RO_BASE + (unsigned)j);
+        }
+        if (defer) {
+            nj_find_jumps(t, a, -1, -1, false);
+            const int nj = t.CTL[NJ_CTL_NJ];
+            if (nj > 0) nj_jump_forward(t, a, nj);
+            NJ_SYNC();
         }
         // ---- hT ----
         NJ_THREADS(tid, t.nt) {
@@ -1286,6 +1295,7 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
     nj_zero(smem + c.o_IN, c.o_I - c.o_IN, t.nt);
     NJ_SYNC();
     const bool gate = a.b.unit_kind == 0;          // see nj_cta_forward
+    const bool defer = a.b.unit_kind == 1;
     for (int tile = cta; tile < a.n_tiles; tile += ncta) {
         nj_load_units(t, a, tile, true);
         const int nu = (a.b.n_units - tile * c.P) < c.P ? (a.b.n_units - tile * c.P) : c.P;
@@ -1300,6 +1310,12 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
         }
         NJ_SYNC();
         nj_reload_state(t, a, nu);
+        if (defer) {
+            // reverse of the deferred jumps: every unit's jump precedes (in reverse order) all of its Euler steps
+            nj_find_jumps(t, a, -1, -1, true);
+            const int nj = t.CTL[NJ_CTL_NJ];
+            if (nj > 0) { nj_jump_backward(t, a, nj); nj_reload_state(t, a, nu); }
+        }
         for (int j = maxlen; j >= 0; --j) {
             if (j < maxlen) {
                 // ---- reverse of Euler step k = s0 + j ----
@@ -1341,7 +1357,7 @@ NJ_HD void nj_cta_backward(const NjCfg& c, const NjArgs& a, float* smem, int cta
                 NJ_SYNC();
             }
             // ---- reverse of the jumps that fall before step s0 + j ----
-            for (;;) {
+            for (; !defer;) {
                 if (gate && t.CTL[NJ_CTL_NEXT] != j) break;            // no unit of the tile jumped before step s0 + j
                 nj_find_jumps(t, a, j, -1, true);
                 const int nj = t.CTL[NJ_CTL_NJ];

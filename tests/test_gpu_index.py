@@ -95,7 +95,7 @@ def test_model_call_uses_the_native_builder_and_matches_the_host_builder():
             hT, loss = m(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 1.0 / 40, 1.0, batch["start_X"],
                          batch["n_obs_ot"])
             loss.backward()
-            res[mode] = (float(loss), hT.cpu().numpy(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]).cpu().numpy())
+            res[mode] = (float(loss.detach()), hT.detach().cpu().numpy(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]).cpu().numpy())
         finally:
             os.environ.pop("NJODE_INDEX", None)
     # identical index arrays -> identical per-unit arithmetic; the gradient partials are summed per CTA and the tiles are
