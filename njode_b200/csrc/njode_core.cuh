@@ -119,6 +119,38 @@ NJ_HD float nj_act(float v, int act) {
     return v;
 }
 
+// shared-memory operand pointers of the GEMM inner loops: on the device a 32-bit shared-window address read
+// with ld.shared.v4.f32 (the generic-pointer path lost the 128-bit vector width behind the non-inlined
+// layer functions); on the host simulation a plain pointer.
+#if defined(NJODE_HOST_SIM)
+typedef const float* nj_sp;
+static inline nj_sp nj_sp_of(const float* p) { return p; }
+static inline nj_f4 nj_sp_ld4(nj_sp p) { return nj_ld4(p); }
+#define NJ_SP_ADD(p, nfloats) ((p) + (nfloats))
+#else
+typedef unsigned nj_sp;
+__device__ __forceinline__ nj_sp nj_sp_of(const float* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ nj_f4 nj_sp_ld4(nj_sp p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(p) : "memory");
+    return v;
+}
+#define NJ_SP_ADD(p, nfloats) ((p) + 4u * (unsigned)(nfloats))
+#endif
+
+// weight operand of the micro-tile GEMMs: the shared-memory image (WS) or the image in global memory
+template <bool WS> struct NjWPtr;
+template <> struct NjWPtr<true> {
+    nj_sp p;
+    NJ_HD void set(const float* q) { p = nj_sp_of(q); }
+    NJ_HD nj_f4 ld(int off) const { return nj_sp_ld4(NJ_SP_ADD(p, off)); }
+};
+template <> struct NjWPtr<false> {
+    const float* p;
+    NJ_HD void set(const float* q) { p = q; }
+    NJ_HD nj_f4 ld(int off) const { return nj_ld4(p + off); }
+};
+
 // ------------------------------------------------------------------------------------------------
 // tile GEMMs.  All matrices row-major, rows 16-byte aligned, padding columns/rows zero (weights) or
 // finite (activations; they only ever meet zero weights).
@@ -136,7 +168,7 @@ struct NjLin {
 };
 
 // out[r][o] = act(bias[o] + sum_k in[r][k] W[o][k]) (* dropout)
-template <int MR>
+template <int MR, bool WS>
 NJ_HD void nj_tile_fwd(const NjLin& L, int tid, int nt) {
     const int RG = (L.nrows + MR - 1) / MR;
     const int ntiles = RG * L.OG;
@@ -145,23 +177,24 @@ NJ_HD void nj_tile_fwd(const NjLin& L, int tid, int nt) {
     for (int tile = tid; tile < ntiles; tile += nt) {
         const int og = nj_div(tile, RG, mRG), rg = tile - og * RG;
         float acc[MR][4];
-        const float* ap[MR];
-        const float* wp[4];
+        nj_sp ap[MR];
+        NjWPtr<WS> wp[4];
 #pragma unroll
         for (int i = 0; i < MR; ++i) {
             int r = rg + RG * i; if (r >= L.nrows) r = L.nrows - 1;
-            ap[i] = L.in + (size_t)r * L.in_s;
+            ap[i] = nj_sp_of(L.in + (size_t)r * L.in_s);
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) wp[j] = L.W + (size_t)(og + L.OG * j) * L.w_s;
+        for (int j = 0; j < 4; ++j) wp[j].set(L.W + (size_t)(og + L.OG * j) * L.w_s);
+#pragma unroll 2
         for (int k4 = 0; k4 < L.K4; ++k4) {
             nj_f4 a[MR], w[4];
 #pragma unroll
-            for (int i = 0; i < MR; ++i) a[i] = nj_ld4(ap[i] + 4 * k4);
+            for (int i = 0; i < MR; ++i) a[i] = nj_sp_ld4(NJ_SP_ADD(ap[i], 4 * k4));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = nj_ld4(wp[j] + 4 * k4);
+            for (int j = 0; j < 4; ++j) w[j] = wp[j].ld(4 * k4);
 #pragma unroll
             for (int i = 0; i < MR; ++i)
 #pragma unroll
@@ -203,7 +236,7 @@ struct NjDx {
 };
 
 // gin[r][k] = (sum_o g[r][o] W[o][k]) * act'(aprev[r][k]) * dropout factor
-template <int MR>
+template <int MR, bool WS>
 NJ_HD void nj_tile_dx(const NjDx& L, int tid, int nt) {
     const int RG = (L.nrows + MR - 1) / MR;
     const int KG = (L.Kin + 3) >> 2;
@@ -213,21 +246,23 @@ NJ_HD void nj_tile_dx(const NjDx& L, int tid, int nt) {
     for (int tile = tid; tile < ntiles; tile += nt) {
         const int kg = nj_div(tile, RG, mRG), rg = tile - kg * RG;
         float acc[MR][4];
-        const float* gp[MR];
+        nj_sp gp[MR];
 #pragma unroll
         for (int i = 0; i < MR; ++i) {
             int r = rg + RG * i; if (r >= L.nrows) r = L.nrows - 1;
-            gp[i] = L.g + (size_t)r * L.g_s;
+            gp[i] = nj_sp_of(L.g + (size_t)r * L.g_s);
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
         }
-        const float* wp = L.W + 4 * kg;
+        NjWPtr<WS> wp;
+        wp.set(L.W + 4 * kg);
+#pragma unroll 2
         for (int o4 = 0; o4 < L.O4; ++o4) {
             nj_f4 g[MR], w[4];
 #pragma unroll
-            for (int i = 0; i < MR; ++i) g[i] = nj_ld4(gp[i] + 4 * o4);
+            for (int i = 0; i < MR; ++i) g[i] = nj_sp_ld4(NJ_SP_ADD(gp[i], 4 * o4));
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) w[jj] = nj_ld4(wp + (size_t)(4 * o4 + jj) * L.w_s);
+            for (int jj = 0; jj < 4; ++jj) w[jj] = wp.ld((4 * o4 + jj) * L.w_s);
 #pragma unroll
             for (int i = 0; i < MR; ++i) {
                 acc[i][0] = fmaf(g[i].x, w[0].x, fmaf(g[i].y, w[1].x, fmaf(g[i].z, w[2].x, fmaf(g[i].w, w[3].x, acc[i][0]))));
@@ -287,14 +322,14 @@ NJ_HD void nj_rl_fwd1(const NjLin& L, int KS, int kc, float* scratch, int tid) {
         if (c < nc) w[c] = nj_ld4(wp + 4 * c);
         else { w[c].x = 0.f; w[c].y = 0.f; w[c].z = 0.f; w[c].w = 0.f; }
     }
-    const float* ap = L.in + 4 * c0;
+    nj_sp ap = nj_sp_of(L.in + 4 * c0);
     float* sp = scratch + (size_t)kq * L.nrows * O + o;
-    for (int r = 0; r < L.nrows; ++r) {
+    for (int r = 0; r < L.nrows; ++r, ap = NJ_SP_ADD(ap, L.in_s)) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int c = 0; c < KC; ++c) {
             if (c < nc) {
-                const nj_f4 a = nj_ld4(ap + (size_t)r * L.in_s + 4 * c);
+                const nj_f4 a = nj_sp_ld4(NJ_SP_ADD(ap, 4 * c));
                 s0 = fmaf(a.x, w[c].x, s0); s1 = fmaf(a.y, w[c].y, s1);
                 s2 = fmaf(a.z, w[c].z, s2); s3 = fmaf(a.w, w[c].w, s3);
             }
@@ -329,14 +364,14 @@ NJ_HD void nj_rl_dx1(const NjDx& L, int OS, int oc, float* scratch, int tid) {
     for (int c = 0; c < OC; ++c)
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[c][i] = (c < nc) ? wp[(size_t)(4 * c + i) * L.w_s] : 0.f;
-    const float* gp = L.g + 4 * c0;
+    nj_sp gp = nj_sp_of(L.g + 4 * c0);
     float* sp = scratch + (size_t)oq * L.nrows * K + k;
-    for (int r = 0; r < L.nrows; ++r) {
+    for (int r = 0; r < L.nrows; ++r, gp = NJ_SP_ADD(gp, L.g_s)) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int c = 0; c < OC; ++c) {
             if (c < nc) {
-                const nj_f4 g = nj_ld4(gp + (size_t)r * L.g_s + 4 * c);
+                const nj_f4 g = nj_sp_ld4(NJ_SP_ADD(gp, 4 * c));
                 s0 = fmaf(g.x, w[c][0], s0); s1 = fmaf(g.y, w[c][1], s1);
                 s2 = fmaf(g.z, w[c][2], s2); s3 = fmaf(g.w, w[c][3], s3);
             }
@@ -378,11 +413,12 @@ NJ_HD void nj_tile_dw(const float* g, int g_s, int OG, const float* a, int a_s, 
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        const float* gp = g + 4 * og;
-        const float* apx = a + 4 * kg;
+        nj_sp gp = nj_sp_of(g + 4 * og), apx = nj_sp_of(a + 4 * kg);
+#pragma unroll 2
         for (int r = 0; r < nrows; ++r) {
-            const nj_f4 gv = nj_ld4(gp + (size_t)r * g_s);
-            const nj_f4 av = nj_ld4(apx + (size_t)r * a_s);
+            const nj_f4 gv = nj_sp_ld4(gp);
+            const nj_f4 av = nj_sp_ld4(apx);
+            gp = NJ_SP_ADD(gp, g_s); apx = NJ_SP_ADD(apx, a_s);
             acc[0][0] = fmaf(gv.x, av.x, acc[0][0]); acc[0][1] = fmaf(gv.x, av.y, acc[0][1]);
             acc[0][2] = fmaf(gv.x, av.z, acc[0][2]); acc[0][3] = fmaf(gv.x, av.w, acc[0][3]);
             acc[1][0] = fmaf(gv.y, av.x, acc[1][0]); acc[1][1] = fmaf(gv.y, av.y, acc[1][1]);
@@ -507,9 +543,15 @@ NJ_HDN void nj_mlp_forward(NjCta& t, int netid, int nrows, bool skip_last) {
             NJ_THREADS(tid, t.nt) { nj_rl_fwd2(L, ksl, t.KSB, tid, t.nt); }
         } else {
             NJ_THREADS(tid, t.nt) {
-                if (mr == 4) nj_tile_fwd<4>(L, tid, t.nt);
-                else if (mr == 2) nj_tile_fwd<2>(L, tid, t.nt);
-                else nj_tile_fwd<1>(L, tid, t.nt);
+                if (c.w_smem) {
+                    if (mr == 4) nj_tile_fwd<4, true>(L, tid, t.nt);
+                    else if (mr == 2) nj_tile_fwd<2, true>(L, tid, t.nt);
+                    else nj_tile_fwd<1, true>(L, tid, t.nt);
+                } else {
+                    if (mr == 4) nj_tile_fwd<4, false>(L, tid, t.nt);
+                    else if (mr == 2) nj_tile_fwd<2, false>(L, tid, t.nt);
+                    else nj_tile_fwd<1, false>(L, tid, t.nt);
+                }
             }
         }
         NJ_SYNC();
@@ -554,9 +596,15 @@ NJ_HDN float* nj_mlp_backward(NjCta& t, int netid, int nrows, bool need_in_grad)
                     else if (oc <= 4) nj_rl_dx1<4>(D, osl, oc, t.KSB, tid2);
                     else nj_rl_dx1<8>(D, osl, oc, t.KSB, tid2);
                 }
-                else if (mr == 4) nj_tile_dx<4>(D, tid, t.nt);
-                else if (mr == 2) nj_tile_dx<2>(D, tid, t.nt);
-                else nj_tile_dx<1>(D, tid, t.nt);
+                else if (c.w_smem) {
+                    if (mr == 4) nj_tile_dx<4, true>(D, tid, t.nt);
+                    else if (mr == 2) nj_tile_dx<2, true>(D, tid, t.nt);
+                    else nj_tile_dx<1, true>(D, tid, t.nt);
+                } else {
+                    if (mr == 4) nj_tile_dx<4, false>(D, tid, t.nt);
+                    else if (mr == 2) nj_tile_dx<2, false>(D, tid, t.nt);
+                    else nj_tile_dx<1, false>(D, tid, t.nt);
+                }
             }
         }
         NJ_SYNC();

@@ -39,25 +39,6 @@ __device__ __forceinline__ unsigned nj_f2u(float f) { return __float_as_uint(f);
 __device__ __forceinline__ float nj_u2f(unsigned u) { return __uint_as_float(u); }
 #endif
 
-// shared-memory operand pointers of the GEMM inner loops: on the device a 32-bit shared-window address read
-// with ld.shared.v4.f32 (the generic-pointer path lost the 128-bit vector width behind the non-inlined
-// layer functions); on the host simulation a plain pointer.
-#if defined(NJODE_HOST_SIM)
-typedef const float* nj_sp;
-static inline nj_sp nj_sp_of(const float* p) { return p; }
-static inline nj_f4 nj_sp_ld4(nj_sp p) { return nj_ld4(p); }
-#define NJ_SP_ADD(p, nfloats) ((p) + (nfloats))
-#else
-typedef unsigned nj_sp;
-__device__ __forceinline__ nj_sp nj_sp_of(const float* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ nj_f4 nj_sp_ld4(nj_sp p) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(p) : "memory");
-    return v;
-}
-#define NJ_SP_ADD(p, nfloats) ((p) + 4u * (unsigned)(nfloats))
-#endif
-
 // parameter image global -> shared: one TMA bulk copy (cp.async.bulk, completion on an mbarrier) issued by
 // one thread instead of a cooperative load/store loop; the caller must NJ_SYNC() afterwards.
 #if defined(NJODE_HOST_SIM)
