@@ -68,6 +68,9 @@ WORKLOADS = {
                               obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
     "hestonwof_demo_20k": dict(sde="HestonWOFeller", paths=20000, steps=100, d=1, H=10, width=50, layers=2,
                                obs_perc=0.1, dropout=0.1, cpu_sample_paths=2000),
+    # use_rnn=True (GRU jump, NJODE/models.py:202-217): whole-path units on the generic kernels
+    "bs_demo_gru_5k": dict(sde="BlackScholes", paths=5000, steps=100, d=1, H=10, width=50, layers=2,
+                           obs_perc=0.1, dropout=0.1, use_rnn=True, cpu_sample_paths=1000),
     # BASELINE.json configs[2] (i): combined-dataset nets (2x100 tanh), batch 5000
     "bs_2x100_5k": dict(sde="BlackScholes", paths=5000, steps=100, d=1, H=10, width=100, layers=2,
                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
@@ -184,7 +187,7 @@ def synth_batch_device(wl, seed, first_path, n_paths, dev):
 def model_cfg(wl):
     nn_desc = [[wl["width"], "tanh"]] * wl["layers"]
     return dict(input_size=wl["d"], hidden_size=wl["H"], output_size=wl["d"], ode_nn=nn_desc,
-                readout_nn=nn_desc, enc_nn=nn_desc, use_rnn=False, bias=True,
+                readout_nn=nn_desc, enc_nn=nn_desc, use_rnn=bool(wl.get("use_rnn")), bias=True,
                 dropout_rate=wl["dropout"], solver="euler", weight=0.5, weight_decay=1.0,
                 options={"masked": True} if wl.get("masked") else {})
 
@@ -491,7 +494,7 @@ def run_b200(args, wl_name, wl):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(wl_name, {})
     except Exception:
         pass
-    seg_path = (not wl.get("masked")) and pb.fwd.unit_kind == 1 and wl["width"] <= 64
+    seg_path = (not wl.get("masked")) and (not wl.get("use_rnn")) and pb.fwd.unit_kind == 1 and wl["width"] <= 64
     kname = "nj_seg_bwd_kernel" if seg_path else "nj_bwd_kernel"
     roofline = {"kernel": kname, "bound": "fp32_fma", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
