@@ -397,14 +397,26 @@ class NJODE(torch.nn.Module):
             times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, return_path=return_path,
             get_loss=get_loss, until_T=until_T, M=M))
 
+    def _pred_path(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, M):
+        """forward(return_path=True, get_loss=False, until_T=True) as evaluate / get_pred call it; only the predictions
+        path_y go to the host (path_h, ten times larger for the demo nets, is not used by either caller)"""
+        keep = self.output_device
+        self.output_device = "cuda"
+        try:
+            with torch.no_grad():
+                _, _, path_t, _, path_y = self.forward(
+                    times, time_ptr, X, obs_idx, delta_t, T, start_X, None, return_path=True,
+                    get_loss=False, until_T=True, M=M)
+        finally:
+            self.output_device = keep
+        return path_t, (path_y.cpu() if keep == "cpu" else path_y)
+
     def evaluate(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, stockmodel,
                  cond_exp_fun_kwargs=None, diff_fun=lambda x, y: np.mean((x - y) ** 2),
                  return_paths=False, M=None):
         """NJODE/models.py:521-562"""
         self.eval()
-        _, _, path_t, path_h, path_y = self.forward(
-            times, time_ptr, X, obs_idx, delta_t, T, start_X, None, return_path=True,
-            get_loss=False, until_T=True, M=M)
+        path_t, path_y = self._pred_path(times, time_ptr, X, obs_idx, delta_t, T, start_X, M)
         _, true_path_t, true_path_y = stockmodel.compute_cond_exp(
             times, time_ptr, X.detach().cpu().numpy(), obs_idx.detach().cpu().numpy(), delta_t, T,
             start_X.detach().cpu().numpy(), n_obs_ot.detach().cpu().numpy(), return_path=True,
@@ -417,7 +429,5 @@ class NJODE(torch.nn.Module):
     def get_pred(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, M=None):
         """NJODE/models.py:564-584"""
         self.eval()
-        _, _, path_t, path_h, path_y = self.forward(
-            times, time_ptr, X, obs_idx, delta_t, T, start_X, None, return_path=True,
-            get_loss=False, until_T=True, M=M)
+        path_t, path_y = self._pred_path(times, time_ptr, X, obs_idx, delta_t, T, start_X, M)
         return {"pred": path_y, "pred_t": path_t}
