@@ -556,6 +556,20 @@ def run_b200(args, wl_name, wl):
             ts.append(time.perf_counter() - t0)
         out["cpu_baseline"] = {"value": units / float(np.median(ts)), "unit": UNIT, "cores": threads,
                                "kind": "port", "sample": sample}
+        # the reference's own server setting is ONE torch thread (NJODE/train.py:44,209: N_CPUS = 1): same port, a quarter
+        # of the sample, one thread
+        wl1 = dict(wl, cpu_sample_paths=max(1, wl["cpu_sample_paths"] // 4))
+        step1, units1, sample1 = cpu_port_step_fn(wl1, 1234, 1)
+        step1()
+        ts1 = []
+        t_end = time.perf_counter() + 8.0
+        while len(ts1) < 2 or (time.perf_counter() < t_end and len(ts1) < 5):
+            t0 = time.perf_counter()
+            step1()
+            ts1.append(time.perf_counter() - t0)
+        out["cpu_baseline_1thread"] = {"value": units1 / float(np.median(ts1)), "unit": UNIT, "cores": 1,
+                                       "kind": "port", "sample": sample1}
+        __import__("torch").set_num_threads(threads)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
