@@ -369,9 +369,26 @@ class DeviceDataset:
         _ext.cuda_lib().check(rc, "njode_collate")
         return out
 
-    def collate(self, sel):
-        """the reference's collate dict (NJODE/data_utils.py:311-315)"""
+    @staticmethod
+    def _apply_functions(X, func_names):
+        """CustomCollateFnGen (NJODE/data_utils.py:352-416): append f(X) for every supported function name ('exp',
+        'power-x') along the feature axis -- on the device, the values never visit the host"""
+        if not func_names:
+            return X
+        cols = [X]
+        for name in func_names:
+            if name in ("exp", "exponential"):
+                cols.append(torch.exp(X.double()).float())
+            elif "power-" in name:
+                cols.append(torch.pow(X.double(), float(name.split("-")[1])).float())
+        return torch.cat(cols, dim=1)
+
+    def collate(self, sel, func_names=None):
+        """the reference's collate dict (NJODE/data_utils.py:311-315); ``func_names`` = the 'func_appl_X' option of
+        train.py (e.g. ["power-2"]: the model then also learns the conditional second moment)"""
         o = self.collate_device(sel)
+        o["X"] = self._apply_functions(o["X"], func_names)
+        o["start_X"] = self._apply_functions(o["start_X"], func_names)
         K, N = (int(v) for v in o["counts"].cpu())
         tidx = o["time_idx"][:K].cpu().numpy()
         # current_time += dt once per grid step in float64 (data_utils.py:293-296)

@@ -112,3 +112,18 @@ def test_device_dataset_drives_the_model_like_the_host_collate():
             hT, loss = m(b["times"], b["time_ptr"], b["X"], b["obs_idx"], ds.dt, 1.0, b["start_X"], b["n_obs_ot"])
         out.append((hT.cpu().numpy(), float(loss)))
     assert out[0][1] == out[1][1] and np.array_equal(out[0][0], out[1][0])
+
+
+def test_device_collate_with_func_appl_X_matches_the_host_collate_generator():
+    """'func_appl_X': ["power-2"] (NJODE/data_utils.py:352-416): X and start_X gain the squared coordinates"""
+    from njode_b200 import data_utils
+    hp = dict(HP, nb_paths=400, dimension=2, S0=[1.0, 2.0], nb_steps=20, obs_perc=0.2)
+    ds = stock_model.DeviceDataset("BlackScholes", hp, seed=7)
+    sel = np.arange(50, 150)
+    got = ds.collate(sel, func_names=["power-2"])
+    want = data_utils.collate_paths(ds.paths.cpu().numpy()[sel], ds.observed.cpu().numpy()[sel], ds.nb_obs.cpu().numpy()[sel],
+                                    ds.dt, functions=[data_utils._get_func("power-2")])
+    assert got["X"].shape[1] == 4 and got["start_X"].shape[1] == 4
+    np.testing.assert_allclose(got["X"].cpu().numpy(), want["X"].numpy(), rtol=1e-6)
+    np.testing.assert_allclose(got["start_X"].cpu().numpy(), want["start_X"].numpy(), rtol=1e-6)
+    assert np.array_equal(got["obs_idx"].numpy(), want["obs_idx"].numpy())
