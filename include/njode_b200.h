@@ -212,6 +212,13 @@ int njode_collate(const double* paths, const int32_t* observed, int64_t n_paths_
                   int32_t* time_ptr, int32_t* time_idx, float* start_X, int32_t* n_obs_ot,
                   int32_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* analytic conditional-expectation path of the data-generating model on the event schedule of a return_path batch
+ * (StockModel.compute_cond_exp, NJODE/stock_model.py:50-151 with next_cond_exp 178-179, 277-286, 353-354, 393-395):
+ * the reference target that NJODE.evaluate (NJODE/models.py:551-558) compares the model's path_y with.
+ *   batch   the prepared batch of the forward(return_path=True) call (E > 0, whole-path units)
+ *   path_y  [E, B, d] out, d = dimension * (1 + return_vol), same record order as NJODE.forward's path_t */
+int njode_cond_exp(const njode_sde_t* sde, const njode_batch_t* batch, float* path_y, void* stream);
+
 /* per-path CSR of observation rows + sorted work units of one batch (the njode_batch_t index arrays), built on the device
  * from the raw collate arrays: replaces the per-observation-time slicing of X / obs_idx by time_ptr that NJODE.forward does
  * in Python (NJODE/models.py:449-456) and the n_obs_ot bookkeeping of NJODE/train.py:501-507.

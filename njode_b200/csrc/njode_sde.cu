@@ -22,6 +22,7 @@
 
 extern "C" const char* njode_last_error(void);
 int nj_set_error(int code, const char* msg);       // njode_api.cu
+void nj_count_launches(int n);                     // njode_api.cu
 
 // ------------------------------------------------------------------------------------------------
 // Philox-4x32-10
@@ -287,6 +288,65 @@ extern "C" int njode_collate(const double* paths, const int32_t* observed, int64
     nj_collate_scan_times<<<1, 32, 0, st>>>(col_cnt, nb_steps, time_ptr, time_idx, col_slot, col_off, counts_out);
     nj_collate_scatter<<<gw, 256, 0, st>>>(paths, observed, sel, B, dim, n1, warp_cnt, col_off, X, obs_idx, start_X);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return nj_set_error(-2, cudaGetErrorString(e));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// analytic conditional expectation path (StockModel.compute_cond_exp, NJODE/stock_model.py:50-151, with the models'
+// next_cond_exp: 178-179, 277-286, 353-354, 393-395) on the event schedule of a return_path batch:
+//   y <- start_X;  every Euler step: y <- E[X_{t+dt} | X_t = y];  every observation: y[i_obs] <- X_obs;
+// one record of y for the whole batch after every step and every observation time, in the order of NJODE.forward's
+// path_t.  One thread per (path, coordinate): each coordinate evolves on its own (growth y e^{mu c(t) dt}, or mean
+// reversion y e + m (1 - e), e = e^{-kappa c(t) dt}; HestonWOFeller's variance coordinates revert without c(t)).
+// fp64 arithmetic, fp32 records.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nj_cond_exp_kernel(const __grid_constant__ njode_sde_t sde, const __grid_constant__ njode_batch_t b,
+                                                          int d, float* __restrict__ path_y) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b.B * d) return;
+    const int p = idx / d, c = idx - p * d;
+    const bool periodic = !isnan(sde.sine_coeff);
+    // coordinate kind: 0 growth, 1 mean reversion with the periodic coefficient (OU), 2 plain mean reversion (variance)
+    int kind = sde.model == NJODE_SDE_ORNSTEIN_UHLENBECK ? 1 : 0;
+    if (sde.model == NJODE_SDE_HESTON_WO_FELLER && sde.return_vol && c >= sde.dimension) kind = 2;
+    double y = (double)b.start_X[idx];
+    const size_t rec = (size_t)b.B * d;
+    path_y[idx] = (float)y;
+    int cur = b.path_ptr[p];
+    const int cend = b.path_ptr[p + 1];
+    int gi = 0;
+    for (int k = 0; k <= b.S; ++k) {
+        while (gi < b.K && b.jump_step[gi] == k) {
+            if (cur < cend) {
+                const int r = b.path_rows[cur];
+                if (b.row_jump[r] == gi) { y = (double)b.X[(size_t)r * d + c]; ++cur; }
+            }
+            path_y[(size_t)b.jump_event[gi] * rec + idx] = (float)y;
+            ++gi;
+        }
+        if (k == b.S) break;
+        const double dt = (double)b.step_dt[k], t = (double)b.step_t[k];
+        const double coef = periodic ? 1.0 + sin(sde.sine_coeff * t) : 1.0;
+        if (kind == 0) y = y * exp(sde.drift * coef * dt);
+        else {
+            const double e = exp(-sde.speed * (kind == 1 ? coef : 1.0) * dt);
+            y = y * e + sde.mean * (1.0 - e);
+        }
+        path_y[(size_t)b.step_event[k] * rec + idx] = (float)y;
+    }
+}
+
+extern "C" int njode_cond_exp(const njode_sde_t* sde, const njode_batch_t* batch, float* path_y, void* stream) {
+    if (!sde || !batch || !path_y) return nj_set_error(-1, "njode_cond_exp: null argument");
+    if (batch->E <= 0 || batch->unit_kind != 0) return nj_set_error(-1, "njode_cond_exp: needs the event schedule of a return_path batch");
+    if (sde->model < 0 || sde->model > NJODE_SDE_HESTON_WO_FELLER) return nj_set_error(-1, "njode_cond_exp: unknown model");
+    const int d = sde->dimension * (sde->return_vol ? 2 : 1);
+    const long long n = (long long)batch->B * d;
+    if (n <= 0) return 0;
+    nj_cond_exp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*sde, *batch, d, path_y);
+    nj_count_launches(1);
+    const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return nj_set_error(-2, cudaGetErrorString(e));
     return 0;
 }

@@ -72,6 +72,11 @@ def compute_loss_2(X_obs, Y_obs, Y_obs_bj, n_obs_ot, batch_size, eps=1e-10, weig
 
 
 LOSS_FUN_DICT = {"standard": compute_loss, "easy": compute_loss_2}
+
+
+def _mean_square_diff(x, y):
+    """default ``diff_fun`` of NJODE.evaluate (NJODE/models.py:523)"""
+    return np.mean((x - y) ** 2)
 nonlinears = {"tanh": torch.nn.Tanh, "relu": torch.nn.ReLU}
 
 
@@ -397,26 +402,35 @@ class NJODE(torch.nn.Module):
             times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, return_path=return_path,
             get_loss=get_loss, until_T=until_T, M=M))
 
-    def _pred_path(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, M):
+    def _pred_path(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, M, on_device=False):
         """forward(return_path=True, get_loss=False, until_T=True) as evaluate / get_pred call it; only the predictions
-        path_y go to the host (path_h, ten times larger for the demo nets, is not used by either caller)"""
+        path_y go to the host (path_h, ten times larger for the demo nets, is not used by either caller).  Returns
+        (path_t, path_y, prepared batch)."""
         keep = self.output_device
         self.output_device = "cuda"
         try:
             with torch.no_grad():
-                _, _, path_t, _, path_y = self.forward(
-                    times, time_ptr, X, obs_idx, delta_t, T, start_X, None, return_path=True,
-                    get_loss=False, until_T=True, M=M)
+                pb = self.prepare_batch(times, time_ptr, X, obs_idx, delta_t, T, start_X, None, return_path=True,
+                                        get_loss=False, until_T=True, M=M)
+                _, _, path_t, _, path_y = self.forward_prepared(pb)
         finally:
             self.output_device = keep
-        return path_t, (path_y.cpu() if keep == "cpu" else path_y)
+        return path_t, (path_y.cpu() if (keep == "cpu" and not on_device) else path_y), pb
 
     def evaluate(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, stockmodel,
-                 cond_exp_fun_kwargs=None, diff_fun=lambda x, y: np.mean((x - y) ** 2),
-                 return_paths=False, M=None):
-        """NJODE/models.py:521-562"""
+                 cond_exp_fun_kwargs=None, diff_fun=_mean_square_diff, return_paths=False, M=None):
+        """NJODE/models.py:521-562.  With the default ``diff_fun`` and a stock model that has the device kernel
+        (njode_b200.stock_model: BlackScholes / Heston / HestonWOFeller / OrnsteinUhlenbeck) the analytic conditional
+        expectation path and the mean square difference are computed on the device (one scalar comes back); any other
+        combination takes the reference's NumPy route."""
         self.eval()
-        path_t, path_y = self._pred_path(times, time_ptr, X, obs_idx, delta_t, T, start_X, M)
+        dev_ok = (diff_fun is _mean_square_diff and not return_paths and _TEST_RUNNER is None
+                  and next(self.parameters()).device.type == "cuda"
+                  and getattr(stockmodel, "supports_cond_exp_device", lambda d: False)(self.output_size))
+        path_t, path_y, pb = self._pred_path(times, time_ptr, X, obs_idx, delta_t, T, start_X, M, on_device=dev_ok)
+        if dev_ok:
+            true_y = stockmodel.compute_cond_exp_device(pb, self.output_size)
+            return float(((path_y.double() - true_y.double()) ** 2).mean())
         _, true_path_t, true_path_y = stockmodel.compute_cond_exp(
             times, time_ptr, X.detach().cpu().numpy(), obs_idx.detach().cpu().numpy(), delta_t, T,
             start_X.detach().cpu().numpy(), n_obs_ot.detach().cpu().numpy(), return_path=True,
@@ -429,5 +443,5 @@ class NJODE(torch.nn.Module):
     def get_pred(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, M=None):
         """NJODE/models.py:564-584"""
         self.eval()
-        path_t, path_y = self._pred_path(times, time_ptr, X, obs_idx, delta_t, T, start_X, M)
+        path_t, path_y, _ = self._pred_path(times, time_ptr, X, obs_idx, delta_t, T, start_X, M)
         return {"pred": path_y, "pred_t": path_t}

@@ -35,6 +35,8 @@ def _bind(lib):
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     d.njode_collate.restype = C.c_int
+    d.njode_cond_exp.argtypes = [C.POINTER(_ext.SdeT), C.POINTER(_ext.BatchT), C.c_void_p, C.c_void_p]
+    d.njode_cond_exp.restype = C.c_int
     d._sde_bound = True
     return d
 
@@ -134,7 +136,31 @@ class StockModel:
         paths, _, _, dt = self.generate_paths_device(start_X=start_X)
         return paths.cpu().numpy(), dt
 
-    # ---- analytic conditional expectation (host) ------------------------------------------------
+    # ---- analytic conditional expectation ---------------------------------------------------------
+    def supports_cond_exp_device(self, d):
+        """True when ``compute_cond_exp_device`` serves batches of data dimension ``d`` (not with func_appl_X features,
+        not for the regime-switching Combined model, whose conditional expectation restarts per regime)"""
+        if self.model_name not in SDE_CODES:
+            return False
+        return int(self.dimensions) * (2 if getattr(self, "retur_vol", False) else 1) == int(d)
+
+    def compute_cond_exp_device(self, pb, d):
+        """path_y of ``compute_cond_exp`` as a device tensor [E, B, d] (njode_cond_exp) for the prepared batch ``pb``
+        of a forward(return_path=True, until_T=True) call -- same records, same order as the model's path_y, so
+        NJODE.evaluate (NJODE/models.py:551-558) can take the mean square difference without leaving the device."""
+        lib = _ext.cuda_lib()
+        dll = _bind(lib)
+        if not pb.return_path or pb.dev.type != "cuda":
+            raise _ext.NjodeError("compute_cond_exp_device needs the prepared batch of a return_path call on a CUDA device")
+        sde = self._sde_struct()
+        if int(sde.dimension) * (2 if sde.return_vol else 1) != int(d):
+            raise ValueError("data dimension of the batch does not match the stock model")
+        out = torch.empty(pb.sched.E, pb.B, d, dtype=torch.float32, device=pb.dev)
+        with torch.cuda.device(pb.dev):
+            rc = dll.njode_cond_exp(C.byref(sde), C.byref(pb.fwd), C.c_void_p(out.data_ptr()), _stream(pb.dev))
+        lib.check(rc, "njode_cond_exp")
+        return out
+
     def next_cond_exp(self, *args, **kwargs):
         raise ValueError("not implemented yet")
 

@@ -127,3 +127,30 @@ def test_device_collate_with_func_appl_X_matches_the_host_collate_generator():
     np.testing.assert_allclose(got["X"].cpu().numpy(), want["X"].numpy(), rtol=1e-6)
     np.testing.assert_allclose(got["start_X"].cpu().numpy(), want["start_X"].numpy(), rtol=1e-6)
     assert np.array_equal(got["obs_idx"].numpy(), want["obs_idx"].numpy())
+
+
+@pytest.mark.parametrize("name,extra", [("BlackScholes", {}), ("OrnsteinUhlenbeck", {"sine_coeff": 3.0}), ("Heston", {}),
+                                        ("HestonWOFeller", {"return_vol": True, "v0": 0.5})])
+def test_cond_exp_kernel_matches_the_numpy_event_loop(name, extra):
+    """njode_cond_exp against StockModel.compute_cond_exp (the restatement of NJODE/stock_model.py:50-151) on the records
+    of a return_path call; then NJODE.evaluate: device route == NumPy route"""
+    hp = dict(HP, nb_paths=300, dimension=1, S0=1.0, nb_steps=40, obs_perc=0.15, **extra)
+    ds = stock_model.DeviceDataset(name, hp, seed=9)
+    b = ds.collate(np.arange(300))
+    d = ds.paths.shape[1]
+    cfg = cases.demo_cfg(input_size=d, output_size=d, hidden_size=10)
+    torch.manual_seed(1)
+    m = models.NJODE(**cfg).to("cuda:0").eval()
+    sm = ds.model
+    assert sm.supports_cond_exp_device(d)
+    pb = m.prepare_batch(b["times"], b["time_ptr"], b["X"], b["obs_idx"], ds.dt, 1.0, b["start_X"], None,
+                         return_path=True, get_loss=False, until_T=True)
+    got = sm.compute_cond_exp_device(pb, d).cpu().numpy()
+    _, want_t, want = sm.compute_cond_exp(b["times"], b["time_ptr"], b["X"].cpu().numpy(), b["obs_idx"].numpy(), ds.dt, 1.0,
+                                          b["start_X"].cpu().numpy(), b["n_obs_ot"].numpy(), return_path=True, get_loss=False)
+    assert got.shape == want.shape and np.array_equal(np.asarray(pb.sched.path_t, dtype=np.float64), np.asarray(want_t, dtype=np.float64))
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
+    args = (b["times"], b["time_ptr"], b["X"], b["obs_idx"], ds.dt, 1.0, b["start_X"], b["n_obs_ot"], sm)
+    on_device = m.evaluate(*args)
+    on_host = m.evaluate(*args, diff_fun=lambda x, y: np.mean((x - y) ** 2))
+    assert abs(on_device - on_host) <= 1e-5 * abs(on_host)
