@@ -152,7 +152,7 @@ static int nj_plan_for(const njode_model_t* model, const njode_batch_t* b, int d
     // gradient partials: sized for the largest grid any backward launch of this model may use
     const size_t cap = (size_t)di.sms * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
-    out.ws_bytes = out.ws_partials_off + cap * out.fwd.img_floats * sizeof(float);
+    out.ws_bytes = out.ws_partials_off + cap * std::max(out.fwd.img_floats, out.bwd.img_floats) * sizeof(float);
     return 0;
 }
 
@@ -240,7 +240,7 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     NJ_LAUNCHED(2 + (batch->n_units > 0 ? 1 : 0));
     int nparts = 0;
     const bool tm = nj_timing_on();
-    if (pl.seg.ok) {
+    if (pl.seg.ok && pl.seg_bwd) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.seg_grid_b;

@@ -52,6 +52,7 @@ struct NjNet {
     int og[NJODE_MAX_LINEAR];           // ceil(out/4)
     int rp[NJODE_MAX_LINEAR];           // rows of W_l held by the image (zero padded) = nch * 8 * to >= out
     int to[NJODE_MAX_LINEAR];           // outputs per lane and chunk of the warp GEMM (njode_seg.cuh), 1..8
+    int tol[NJODE_MAX_LINEAR];          // ... of the last chunk (<= to)
     int nch[NJODE_MAX_LINEAR];          // output chunks of 8 * to rows
     int w_img[NJODE_MAX_LINEAR];        // float offsets inside the image
     int b_img[NJODE_MAX_LINEAR];

@@ -8,7 +8,8 @@
 
 struct NjPlanOut {
     NjCfg fwd, bwd;
-    NjSeg seg;                      // seg.ok: the segment fast path (njode_seg.cuh) serves this call
+    NjSeg seg;                      // seg.ok: the segment fast path (njode_seg.cuh) serves the forward of this call
+    int seg_bwd;                    // ... and its backward (else the generic backward follows the segment forward)
     int seg_grid_f, seg_grid_b;
     size_t seg_smem_f_bytes, seg_smem_b_bytes;
     int n_tiles;
@@ -38,10 +39,12 @@ static inline bool nj_fill_nets(const njode_model_t& m, NjCfg& c, bool compact, 
             N.ks[l] = nj_stride_host(s.dims[l]);
             N.og[l] = (s.dims[l + 1] + 3) / 4;
             const int o8 = (s.dims[l + 1] + 7) / 8;
+            // warp GEMM chunks: 64 outputs (8 per lane) each, the last one 8 * tol; chunk bases stay multiples of 16
+            // (hash pairs) and the image holds exactly 8 * ceil(out / 8) rows (2x100 nets: 104 rows, not 128)
             N.nch[l] = (o8 + 7) / 8;
-            N.to[l] = (o8 + N.nch[l] - 1) / N.nch[l];
-            if (N.nch[l] > 1 && (N.to[l] & 1)) N.to[l] += 1;      // chunk bases stay multiples of 16 (hash pairs)
-            N.rp[l] = compact ? 4 * N.og[l] : N.nch[l] * 8 * N.to[l];
+            N.to[l] = N.nch[l] > 1 ? 8 : o8;
+            N.tol[l] = o8 - 8 * (N.nch[l] - 1);
+            N.rp[l] = compact ? 4 * N.og[l] : 8 * o8;
             N.w_img[l] = off; off += N.rp[l] * N.ks[l];
             N.b_img[l] = off; off += N.rp[l];
             N.w_src[l] = s.w_off[l]; N.b_src[l] = s.b_off[l];
@@ -399,13 +402,36 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
 }
 
 // the whole launch plan of one (model, batch) pair: the segment fast path when it serves the call (padded parameter
-// image), else the generic kernels on the compact image
+// image), else the generic kernels on the compact image.  The segment BACKWARD keeps its dW tiles in registers; when
+// the nets have many more tiles than a CTA has register slots (2x100 nets: 2250 tiles, <= 768 slots) almost all of them
+// go through the L2-resident partial image at every step and the generic backward is faster (measured on B200: 10.2 vs
+// 9.4 ms), so such calls pair the segment forward with the generic backward -- both read the same saved buffers.
 static inline bool nj_plan_all(const njode_model_t& m, const njode_batch_t& b, int num_sms, size_t smem_limit, int force_P,
                                NjPlanOut& out, std::string& err) {
     if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, false, out, err)) return false;
     nj_make_seg(out.fwd, b, num_sms, smem_limit, out);
-    if (out.seg.ok) return true;
-    if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, true, out, err)) return false;
-    memset(&out.seg, 0, sizeof(out.seg));
+    out.seg_bwd = out.seg.ok;
+    if (out.seg.ok && out.seg.tiles_total <= 1024) return true;
+    const char* sb = getenv("NJODE_FORCE_SEG_BWD");                 // tests: keep the segment backward whatever the size
+    if (out.seg.ok && sb && atoi(sb)) return true;
+    NjPlanOut gen;
+    if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, true, gen, err)) return false;
+    memset(&gen.seg, 0, sizeof(gen.seg));
+    gen.seg_bwd = 0;
+    if (out.seg.ok) {
+        // segment forward (padded image, out.fwd / out.seg) + generic backward (compact image, gen.bwd)
+        gen.seg = out.seg; gen.fwd = out.fwd;
+        gen.seg_grid_f = out.seg_grid_f; gen.seg_smem_f_bytes = out.seg_smem_f_bytes;
+        gen.seg_grid_b = 0; gen.seg_smem_b_bytes = 0;
+        // one workspace serves both calls: the image slot holds the larger of the two images
+        const size_t img = (size_t)std::max(out.fwd.img_floats, gen.bwd.img_floats) * 4;
+        size_t o = 0;
+        gen.ws_image_off = o; o += img; o = (o + 255) & ~(size_t)255;
+        gen.ws_rowloss_off = o; o += (size_t)std::max(b.N, 1) * 4; o = (o + 255) & ~(size_t)255;
+        gen.ws_counter_off = o; o += 256;
+        gen.ws_partials_off = o; o += (size_t)gen.grid_bwd * gen.bwd.img_floats * 4;
+        gen.ws_bytes = o;
+    }
+    out = gen;
     return true;
 }

@@ -195,11 +195,13 @@ NJ_HD void nj_wg_fwd(const NjWL& L, int lane) {
 
 // one layer over the warp's rows: all output chunks.  Not inlined: one copy of the TO variants per TR.
 template <int TR>
-NJ_HDN void nj_seg_layer_fwd(NjWL L, int to, int nch) {
+NJ_HDN void nj_seg_layer_fwd(NjWL L, int to0, int to_last, int nch) {
     NJ_ASSUME_SHARED(L.in); NJ_ASSUME_SHARED(L.W); NJ_ASSUME_SHARED(L.out); NJ_ASSUME_SHARED(L.rk);
     if (L.bias) NJ_ASSUME_SHARED(L.bias);
     for (int ch = 0; ch < nch; ++ch) {
-        L.o_base = ch * 8 * to;
+        // chunks of 8 * to0 outputs, the last one narrower: the image holds exactly 8 * ceil(out / 8) rows
+        L.o_base = ch * 8 * to0;
+        const int to = ch < nch - 1 ? to0 : to_last;
         NJ_LANES(lane) {
             switch (to) {
                 case 1: nj_wg_fwd<TR, 1>(L, lane); break;
@@ -336,7 +338,7 @@ NJ_HD void nj_seg_mlp_fwd(const NjSegW& w, int netid, bool keep_all, bool skip_l
         L.drop = (!last) && c.has_drop; L.thr = c.thr; L.keep_scale = c.keep_scale;
         L.rk = w.RK; L.tag = (unsigned)(netid * 16 + l + 1);
         L.o_base = 0;
-        nj_seg_layer_fwd<TR>(L, N.to[l], N.nch[l]);
+        nj_seg_layer_fwd<TR>(L, N.to[l], N.tol[l], N.nch[l]);
         NJ_SYNCWARP();
         in = L.out; in_s = L.out_s;
     }

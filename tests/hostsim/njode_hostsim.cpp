@@ -23,7 +23,7 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
     if (!nj_plan_all(*m, *b, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
     const size_t cap = (size_t)kSimSMs * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
-    out.ws_bytes = out.ws_partials_off + cap * out.fwd.img_floats * sizeof(float);
+    out.ws_bytes = out.ws_partials_off + cap * std::max(out.fwd.img_floats, out.bwd.img_floats) * sizeof(float);
     return 0;
 }
 
@@ -108,7 +108,7 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     a.grad_loss = grad_loss; a.grad_hT = grad_hT; a.get_loss = 1; a.n_tiles = pl.n_tiles;
     pack(pl.bwd, params, const_cast<float*>(a.image));
     int nparts = 0;
-    if (pl.seg.ok) {
+    if (pl.seg.ok && pl.seg_bwd) {
         std::vector<float> smem(pl.seg.b_smem_floats);
         for (int cta = 0; cta < pl.seg_grid_b; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
