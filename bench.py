@@ -494,7 +494,7 @@ def run_b200(args, wl_name, wl):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(wl_name, {})
     except Exception:
         pass
-    seg_path = (not wl.get("masked")) and (not wl.get("use_rnn")) and pb.fwd.unit_kind == 1 and wl["width"] <= 64
+    seg_path = (not wl.get("masked")) and (not wl.get("use_rnn")) and pb.fwd.unit_kind == 1 and wl["width"] <= 100
     kname = "nj_seg_bwd_kernel" if seg_path else "nj_bwd_kernel"
     roofline = {"kernel": kname, "bound": "fp32_fma", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None,

@@ -44,7 +44,13 @@ __global__ void __launch_bounds__(384) nj_seg_fwd_kernel(const __grid_constant__
 
 __global__ void __launch_bounds__(384) nj_seg_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
                                                          const __grid_constant__ NjArgs args) {
-    nj_seg_cta_backward(cfg, seg, args, nj_smem, blockIdx.x);
+    nj_seg_cta_backward<false>(cfg, seg, args, nj_smem, blockIdx.x);
+}
+
+// the same kernel for launches with dW helper warps (seg.nt_b > 32 * seg.nw_b), see nj_seg_cta_backward
+__global__ void __launch_bounds__(384) nj_seg_bwd_kernel_h(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+                                                           const __grid_constant__ NjArgs args) {
+    nj_seg_cta_backward<true>(cfg, seg, args, nj_smem, blockIdx.x);
 }
 
 // flat parameters -> zero-padded image; one block per (net, layer)
@@ -240,12 +246,13 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     NJ_LAUNCHED(2 + (batch->n_units > 0 ? 1 : 0));
     int nparts = 0;
     const bool tm = nj_timing_on();
-    if (pl.seg.ok && pl.seg_bwd) {
+    if (pl.seg.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.seg_grid_b;
-        NJ_CUDA(cudaFuncSetAttribute(nj_seg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
-        nj_seg_bwd_kernel<<<pl.seg_grid_b, pl.seg.nw_b * 32, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
+        auto kern = pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h : nj_seg_bwd_kernel;
+        NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
+        kern<<<pl.seg_grid_b, pl.seg.nt_b, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
     } else {
         auto kern = nj_bwd_kernel;
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd_bytes));

@@ -8,8 +8,7 @@
 
 struct NjPlanOut {
     NjCfg fwd, bwd;
-    NjSeg seg;                      // seg.ok: the segment fast path (njode_seg.cuh) serves the forward of this call
-    int seg_bwd;                    // ... and its backward (else the generic backward follows the segment forward)
+    NjSeg seg;                      // seg.ok: the segment fast path (njode_seg.cuh) serves this call
     int seg_grid_f, seg_grid_b;
     size_t seg_smem_f_bytes, seg_smem_b_bytes;
     int n_tiles;
@@ -388,7 +387,16 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
         }
         if (!nw) return;
         s.nw_b = nw;
-        s.nt_slots = std::min(NJ_SEG_NT_MAX, (tiles + nw * 32 - 1) / (nw * 32));
+        // dW tiles beyond NJ_SEG_NT_MAX per thread go through the L2-resident partial image at every step.  Nets with
+        // many more tiles than a CTA has register slots (2x100 nets: 2250 tiles; the image leaves room for 24 rows =
+        // 3 row warps = 192 slots) get helper warps that own no rows and only join the dW phases, up to the 12 warps of
+        // the launch bounds (B200, 2x100 nets: backward 11.5 -> 7.7 ms; the generic backward takes 9.6 ms).  For the
+        // demo nets (702 tiles) helpers measured neutral to 6 % slower, so small batches of small nets get none.
+        const char* fh = getenv("NJODE_SEG_HELPERS");
+        int wtot = nw;
+        if (fh ? atoi(fh) != 0 : tiles > 1024) wtot = std::max(nw, std::min(12, (tiles + 32 * NJ_SEG_NT_MAX - 1) / (32 * NJ_SEG_NT_MAX)));
+        s.nt_b = 32 * wtot;
+        s.nt_slots = std::min(NJ_SEG_NT_MAX, (tiles + s.nt_b - 1) / s.nt_b);
         static const int trs2[2] = {1, 2};
         if (force_tr) { const int one[1] = {std::min(2, force_tr)}; s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr); }
         else s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, trs2, 2, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr);
@@ -402,36 +410,13 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
 }
 
 // the whole launch plan of one (model, batch) pair: the segment fast path when it serves the call (padded parameter
-// image), else the generic kernels on the compact image.  The segment BACKWARD keeps its dW tiles in registers; when
-// the nets have many more tiles than a CTA has register slots (2x100 nets: 2250 tiles, <= 768 slots) almost all of them
-// go through the L2-resident partial image at every step and the generic backward is faster (measured on B200: 10.2 vs
-// 9.4 ms), so such calls pair the segment forward with the generic backward -- both read the same saved buffers.
+// image), else the generic kernels on the compact image
 static inline bool nj_plan_all(const njode_model_t& m, const njode_batch_t& b, int num_sms, size_t smem_limit, int force_P,
                                NjPlanOut& out, std::string& err) {
     if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, false, out, err)) return false;
     nj_make_seg(out.fwd, b, num_sms, smem_limit, out);
-    out.seg_bwd = out.seg.ok;
-    if (out.seg.ok && out.seg.tiles_total <= 1024) return true;
-    const char* sb = getenv("NJODE_FORCE_SEG_BWD");                 // tests: keep the segment backward whatever the size
-    if (out.seg.ok && sb && atoi(sb)) return true;
-    NjPlanOut gen;
-    if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, true, gen, err)) return false;
-    memset(&gen.seg, 0, sizeof(gen.seg));
-    gen.seg_bwd = 0;
-    if (out.seg.ok) {
-        // segment forward (padded image, out.fwd / out.seg) + generic backward (compact image, gen.bwd)
-        gen.seg = out.seg; gen.fwd = out.fwd;
-        gen.seg_grid_f = out.seg_grid_f; gen.seg_smem_f_bytes = out.seg_smem_f_bytes;
-        gen.seg_grid_b = 0; gen.seg_smem_b_bytes = 0;
-        // one workspace serves both calls: the image slot holds the larger of the two images
-        const size_t img = (size_t)std::max(out.fwd.img_floats, gen.bwd.img_floats) * 4;
-        size_t o = 0;
-        gen.ws_image_off = o; o += img; o = (o + 255) & ~(size_t)255;
-        gen.ws_rowloss_off = o; o += (size_t)std::max(b.N, 1) * 4; o = (o + 255) & ~(size_t)255;
-        gen.ws_counter_off = o; o += 256;
-        gen.ws_partials_off = o; o += (size_t)gen.grid_bwd * gen.bwd.img_floats * 4;
-        gen.ws_bytes = o;
-    }
-    out = gen;
+    if (out.seg.ok) return true;
+    if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, true, out, err)) return false;
+    memset(&out.seg, 0, sizeof(out.seg));
     return true;
 }

@@ -79,7 +79,8 @@ __device__ __forceinline__ void nj_stage_image(float* dst, const float* src, int
 struct NjSeg {
     int ok;                         // 0: not eligible, use the generic kernels
     int tr_f, tr_b;                 // rows per lane group: a warp owns 4*tr rows (forward / backward)
-    int nw_f, nw_b;                 // warps per CTA (forward / backward)
+    int nw_f, nw_b;                 // warps per CTA that own rows (forward / backward)
+    int nt_b;                       // threads of a backward CTA: 32 * nw_b + helper warps that only join the dW phases
     int sI, sA, sO, sH, sD;         // strides: first-layer input, hidden activations, last-layer output, H, d
     int nA;                         // hidden-activation buffers kept in backward (max n_linear - 1)
     // forward: per-warp region
@@ -741,7 +742,7 @@ template <int TR>
 NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, const NjSegB& t, float* nj_acc_base,
                            int cta, int u0, int u1) {
     constexpr int R = 4 * TR;
-    const int P = s.P_b, nt = s.nw_b * 32, Pt = R * s.nw_b;
+    const int P = s.P_b, nt = s.nt_b, Pt = R * s.nw_b;
     float* simg = smem + s.b_img;
     float* gpart = a.partials + (size_t)cta * c.img_floats;
     const float gl = NJ_LDG(a.grad_loss);
@@ -1011,8 +1012,40 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
     }
 }
 
+#if !defined(NJODE_HOST_SIM)
+// the dW helper warps (threads >= 32 * nw_b) of a backward CTA: they own no rows, so they skip the warp-local phases
+// of nj_seg_bwd_tile and only mirror its barriers and its CTA-wide dW phases.  (On the host simulation the NJ_THREADS
+// loops of nj_seg_bwd_tile already run the helper thread ids.)  Kept out of nj_seg_bwd_tile so that the row warps run
+// exactly the code they ran without helpers.
+template <int TR>
+__device__ __forceinline__ void nj_seg_bwd_tile_helper(const NjCfg& c, const NjSeg& s, const NjArgs& a, const NjSegB& t,
+                                                       float* acc, int cta) {
+    constexpr int R = 4 * TR;
+    const int P = s.P_b, nt = s.nt_b, Pt = R * s.nw_b, tid = threadIdx.x;
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    NJ_SYNC();                                               // unit descriptors are in shared memory
+    int maxlen = 0, any_jump = 0;
+    for (int r = 0; r < Pt; ++r) {
+        maxlen = t.I[NJS_I_LEN * P + r] > maxlen ? t.I[NJS_I_LEN * P + r] : maxlen;
+        any_jump |= (t.I[NJS_I_ROW * P + r] >= 0);
+    }
+    if (any_jump) {
+        NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_RO, acc, gpart, tid, nt, Pt); NJ_SYNC();
+        NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_ENC, acc, gpart, tid, nt, Pt); NJ_SYNC();
+        NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_RO, acc, gpart, tid, nt, Pt); NJ_SYNC();
+    }
+    for (int j = maxlen - 1; j >= 0; --j) {
+        NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_ODE, acc, gpart, tid, nt, Pt); NJ_SYNC();
+    }
+    NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_ENC, acc, gpart, tid, nt, Pt); NJ_SYNC();
+}
+#endif
+
+// HELP: the launch has dW helper warps (a second instantiation of the kernel, so that launches without helpers run
+// exactly the code -- and the register allocation -- they had before helpers existed)
+template <bool HELP>
 NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
-    const int nt = s.nw_b * 32;
+    const int nt = s.nt_b;
     float* simg = smem + s.b_img;
     nj_stage_image(simg, a.image, c.img_floats, nt);
     nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
@@ -1030,6 +1063,13 @@ NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
         if (tile >= s.n_tiles_b) break;
         int ub, ue;
         const int tr = nj_seg_tile_lookup(s.b_ncls, s.b_t0, s.b_u0, s.b_u1, s.b_tr, 4 * s.nw_b, tile, ub, ue);
+#if !defined(NJODE_HOST_SIM)
+        if (HELP && (int)(threadIdx.x >> 5) >= s.nw_b) {
+            if (tr == 2) nj_seg_bwd_tile_helper<2>(c, s, a, t, nj_acc_base, cta);
+            else nj_seg_bwd_tile_helper<1>(c, s, a, t, nj_acc_base, cta);
+            continue;
+        }
+#endif
         if (tr == 2) nj_seg_bwd_tile<2>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
         else nj_seg_bwd_tile<1>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
     }

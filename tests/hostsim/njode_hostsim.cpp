@@ -108,12 +108,12 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     a.grad_loss = grad_loss; a.grad_hT = grad_hT; a.get_loss = 1; a.n_tiles = pl.n_tiles;
     pack(pl.bwd, params, const_cast<float*>(a.image));
     int nparts = 0;
-    if (pl.seg.ok && pl.seg_bwd) {
+    if (pl.seg.ok) {
         std::vector<float> smem(pl.seg.b_smem_floats);
         for (int cta = 0; cta < pl.seg_grid_b; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
             if (cta == 0) *a.counter = 0;
-            nj_seg_cta_backward(pl.bwd, pl.seg, a, smem.data(), cta);
+            nj_seg_cta_backward<false>(pl.bwd, pl.seg, a, smem.data(), cta);
         }
         nparts = pl.seg_grid_b;
     } else {

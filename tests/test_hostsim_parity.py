@@ -27,7 +27,7 @@ def sim_runner():
     os.environ.pop("NJODE_INDEX", None)
     os.environ.pop("NJODE_FORCE_NW", None)
     os.environ.pop("NJODE_FORCE_DW", None)
-    os.environ.pop("NJODE_FORCE_SEG_BWD", None)
+    os.environ.pop("NJODE_SEG_HELPERS", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -142,11 +142,11 @@ def test_segment_path_dropout_masks_replayed_by_oracle(tr):
     parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
 
 
-@pytest.mark.parametrize("seg_bwd", [0, 1])
-def test_segment_path_wide_layers_use_output_chunks(seg_bwd):
-    """hidden width 100 > 64: two output chunks per layer in the warp GEMM (64 + 40 outputs); nets with more dW tiles
-    than register slots pair the segment forward with the generic backward unless the segment backward is forced"""
-    os.environ["NJODE_FORCE_SEG_BWD"] = str(seg_bwd)
+@pytest.mark.parametrize("helpers", [0, 1])
+def test_segment_path_wide_layers_use_output_chunks(helpers):
+    """hidden width 100 > 64: two output chunks per layer in the warp GEMM (64 + 40 outputs); with / without the dW
+    helper warps of the backward (threads that own no rows)"""
+    os.environ["NJODE_SEG_HELPERS"] = str(helpers)
     cfg = cases.demo_cfg(input_size=2, output_size=2, hidden_size=6, dropout_rate=0.1,
                          ode_nn=[[100, "tanh"], [70, "relu"]], enc_nn=[[100, "tanh"]], readout_nn=[[33, "tanh"]])
     batch = cases.grid_batch(20, 2, 10, 0.3, seed=18)
