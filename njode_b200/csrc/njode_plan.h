@@ -393,12 +393,18 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
         // the launch bounds (B200, 2x100 nets: backward 11.5 -> 7.7 ms; the generic backward takes 9.6 ms).  For the
         // demo nets (702 tiles) helpers measured neutral to 6 % slower, so small batches of small nets get none.
         const char* fh = getenv("NJODE_SEG_HELPERS");
+        const bool helpers = fh ? atoi(fh) != 0 : tiles > 1024;
         int wtot = nw;
-        if (fh ? atoi(fh) != 0 : tiles > 1024) wtot = std::max(nw, std::min(12, (tiles + 32 * NJ_SEG_NT_MAX - 1) / (32 * NJ_SEG_NT_MAX)));
+        if (helpers) wtot = std::max(nw, std::min(12, (tiles + 32 * NJ_SEG_NT_MAX - 1) / (32 * NJ_SEG_NT_MAX)));
+        // with spare warps in the launch the rows of the CTA are spread over twice as many row warps (4 rows each
+        // instead of 8): the warp-local phases, during which the helpers wait, take half as long
+        const bool thin = helpers && !force_tr && 2 * nw <= wtot;
+        if (thin) { nw *= 2; s.nw_b = nw; }
         s.nt_b = 32 * wtot;
         s.nt_slots = std::min(NJ_SEG_NT_MAX, (tiles + s.nt_b - 1) / s.nt_b);
         static const int trs2[2] = {1, 2};
-        if (force_tr) { const int one[1] = {std::min(2, force_tr)}; s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr); }
+        if (thin) { const int one[1] = {1}; s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr); }
+        else if (force_tr) { const int one[1] = {std::min(2, force_tr)}; s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr); }
         else s.b_ncls = nj_seg_classes(run_b, run_e, n1, n2, trs2, 2, 4 * nw, s.b_t0, s.b_u0, s.b_u1, s.b_tr);
         s.n_tiles_b = s.b_t0[s.b_ncls];
     }
