@@ -266,8 +266,9 @@ static inline int nj_seg_fwd_region(const NjCfg& c, NjSeg& s, int R) {
     s.f_TX = o; o += R * s.sD;
     s.f_XI = o; o += R * s.sD;
     s.f_YBJ = o; o += R * s.sD;
-    s.f_F = o; o += NJS_F_COUNT * R;
-    s.f_I = o; o += NJS_I_COUNT * R + 4;
+    // the per-row scalar slots keep the stride of the tallest tile (RS = 16 in nj_seg_forward_warp) whatever R is
+    s.f_F = o; o += NJS_F_COUNT * 16;
+    s.f_I = o; o += NJS_I_COUNT * 16 + 4;
     return (o + 3) & ~3;
 }
 
@@ -360,13 +361,27 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
     {
         s.f_region = nj_seg_fwd_region(c, s, 16);
         s.f_img = 0; s.f_warp0 = c.img_floats;
+        auto warps_that_fit = [&]() {
+            for (int cand = 12; cand >= 2; --cand)          // launch bounds: 384 threads
+                if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) return cand;
+            return 0;
+        };
+        int nw = warps_that_fit();
+        // big nets (2x100: the image leaves room for three 16-row regions): regions of 8 rows and tiles of at most
+        // 8 rows instead -- twice the warps to hide the latency of the warp-autonomous marches
+        bool low = false;
+        if (!force_tr && nw < 6) {
+            s.f_region = nj_seg_fwd_region(c, s, 8);
+            const int nw8 = warps_that_fit();
+            if (nw8 >= 2 * nw && nw8 >= 2) { nw = nw8; low = true; }
+            else s.f_region = nj_seg_fwd_region(c, s, 16);
+        }
         static const int trs3[3] = {1, 2, 4};
+        static const int trs2f[2] = {1, 2};
         if (force_tr) { const int one[1] = {std::min(4, force_tr)}; s.f_ncls = nj_seg_classes(run_b, run_e, n1, n2, one, 1, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr); }
+        else if (low) s.f_ncls = nj_seg_classes(run_b, run_e, n1, n2, trs2f, 2, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr);
         else s.f_ncls = nj_seg_classes(run_b, run_e, n1, n2, trs3, 3, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr);
         s.n_tiles_f = s.f_t0[s.f_ncls];
-        int nw = 0;
-        for (int cand = 12; cand >= 2; --cand)          // launch bounds: 384 threads
-            if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
         if (!nw) return;
         // small batches: fewer warps per CTA so that every SM gets work
         nw = std::max(2, std::min(nw, (s.n_tiles_f + num_sms - 1) / num_sms));
