@@ -88,6 +88,19 @@ def test_config3_combined_2x100_nets_against_oracle():
     _oracle_vs_cuda(dict(cfg, dropout_rate=0.1), batch, 1.0 / 40, 1.0, seed=5, train=True)
 
 
+@pytest.mark.parametrize("helpers", ["0", "1"])
+def test_segment_backward_helper_warps(helpers):
+    """the backward instantiation with dW helper warps (nj_seg_bwd_kernel_h) and the plain one give the oracle's
+    gradients whichever the planner would pick: demo nets at a batch whose CTAs have 4 row warps, dropout on"""
+    os.environ["NJODE_SEG_HELPERS"] = helpers
+    try:
+        cfg = cases.demo_cfg(dropout_rate=0.1)
+        batch = cases.grid_batch(300, 1, 40, 0.15, seed=27)
+        parity_util.check_against_oracle(cfg, batch, 1.0 / 40, 1.0, seed=10, device=DEV, train=True, grad_hT=True)
+    finally:
+        os.environ.pop("NJODE_SEG_HELPERS", None)
+
+
 def test_config3_heston_wo_feller_two_coordinates_against_oracle():
     """BASELINE config 3 (ii): HestonWOFeller with return_vol -> input_size 2, 2x50 nets"""
     cfg = cases.demo_cfg(input_size=2, output_size=2)
