@@ -74,6 +74,10 @@ WORKLOADS = {
     # BASELINE.json configs[2] (i): combined-dataset nets (2x100 tanh), batch 5000
     "bs_2x100_5k": dict(sde="BlackScholes", paths=5000, steps=100, d=1, H=10, width=100, layers=2,
                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
+    "bs_2x100_200": dict(sde="BlackScholes", paths=200, steps=100, d=1, H=10, width=100, layers=2,
+                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=200),
+    "bs_2x100_20k": dict(sde="BlackScholes", paths=20000, steps=100, d=1, H=10, width=100, layers=2,
+                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
 }
 
 SDE_PARAMS = dict(drift=2.0, volatility=0.3, mean=4.0, speed=2.0, correlation=0.5, S0=1.0,
