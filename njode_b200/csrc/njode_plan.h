@@ -370,10 +370,11 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
         // big nets (2x100: the image leaves room for three 16-row regions): regions of 8 rows and tiles of at most
         // 8 rows instead -- twice the warps to hide the latency of the warp-autonomous marches
         bool low = false;
-        if (!force_tr && nw < 6) {
+        const char* flow = getenv("NJODE_SEG_LOW");           // tests: take the 8-row layout whatever fits
+        if (!force_tr && (nw < 6 || (flow && atoi(flow)))) {
             s.f_region = nj_seg_fwd_region(c, s, 8);
             const int nw8 = warps_that_fit();
-            if (nw8 >= 2 * nw && nw8 >= 2) { nw = nw8; low = true; }
+            if ((nw8 >= 2 * nw || (flow && atoi(flow))) && nw8 >= 2) { nw = nw8; low = true; }
             else s.f_region = nj_seg_fwd_region(c, s, 16);
         }
         static const int trs3[3] = {1, 2, 4};

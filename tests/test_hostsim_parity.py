@@ -28,6 +28,7 @@ def sim_runner():
     os.environ.pop("NJODE_FORCE_NW", None)
     os.environ.pop("NJODE_FORCE_DW", None)
     os.environ.pop("NJODE_SEG_HELPERS", None)
+    os.environ.pop("NJODE_SEG_LOW", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -152,6 +153,16 @@ def test_segment_path_wide_layers_use_output_chunks(helpers):
     batch = cases.grid_batch(20, 2, 10, 0.3, seed=18)
     parity_util.check_against_oracle(cfg, batch, 0.1, 1.0, seed=14, device="cpu", train=True, grad_hT=True)
     parity_util.check_against_oracle(cfg, batch, 0.1, 1.0, seed=14, device="cpu", train=False)
+
+
+@pytest.mark.parametrize("name", ["bs_ckpt1", "easy_w07_nores", "curt_nobias_relu"])
+def test_segment_forward_low_regions(name):
+    """8-row warp regions / tiles of at most 8 rows (the layout big nets get when the image leaves little room)"""
+    os.environ["NJODE_SEG_LOW"] = "1"
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    cfg = cases.demo_cfg(dropout_rate=0.2)
+    batch = cases.grid_batch(40, 1, 25, 0.2, seed=16)
+    parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
 
 
 @pytest.mark.parametrize("mode", ["host", "device"])
