@@ -141,3 +141,38 @@ def test_config5_shape_shard_invariance_on_tensor_cores():
     assert abs(tot_l - loss) < 1e-4 * abs(loss)
     assert rel(np.concatenate(hs), hT) < 1e-4
     assert rel(tot_g, g) < 2e-3
+
+
+def test_training_trajectory_matches_the_oracle_under_adam():
+    """30 Adam steps on the CUDA kernels vs 30 Adam steps on the oracle (CPU, autograd), same data / weights / optimiser
+    settings as train.py (lr 1e-3, weight_decay 5e-4), dropout off: the per-step losses stay together (the difference is
+    the accumulated effect of 1e-5-level gradient differences)"""
+    import oracle.njode_oracle as orc
+    cfg = cases.demo_cfg()
+    ocfg = orc.Config(**cfg)
+    sd0 = orc.init_state_dict(ocfg, seed=21)
+    batches = [cases.grid_batch(64, 1, 25, 0.2, seed=50 + i) for i in range(3)]
+    m = models.NJODE(**cfg)
+    m.load_state_dict(sd0)
+    m.to(DEV).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0.0005)
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    oopt = torch.optim.Adam(list(osd.values()), lr=1e-3, weight_decay=0.0005)
+    ours, theirs = [], []
+    for it in range(30):
+        b = batches[it % 3]
+        opt.zero_grad()
+        hT, loss = m(b["times"], b["time_ptr"], b["X"], b["obs_idx"], 0.04, 1.0, b["start_X"], b["n_obs_ot"])
+        loss.backward()
+        opt.step()
+        ours.append(float(loss.detach()))
+        oopt.zero_grad()
+        _, oloss = orc.forward(ocfg, osd, b["times"], b["time_ptr"], b["X"], b["obs_idx"], 0.04, 1.0, b["start_X"], b["n_obs_ot"])
+        oloss.backward()
+        oopt.step()
+        theirs.append(float(oloss.detach()))
+    ours, theirs = np.array(ours), np.array(theirs)
+    assert theirs[-1] < theirs[0]                                   # it trains
+    np.testing.assert_allclose(ours, theirs, rtol=2e-3)
+    for (n, p) in m.named_parameters():
+        assert rel(p.detach().cpu().numpy(), osd[n].detach().numpy()) < 5e-3, n
