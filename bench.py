@@ -61,6 +61,8 @@ WORKLOADS = {
     # (parallel_train.py:656); the 2000-record variant shows the throughput of the generic masked kernels.
     "physionet_synth_b50": dict(sde="physionet_synth", paths=50, steps=3000, d=41, H=41, width=50, layers=2,
                                 obs_perc=None, dropout=0.1, masked=True, cpu_sample_paths=50),
+    "physionet_synth_b50_2x200": dict(sde="physionet_synth", paths=50, steps=3000, d=41, H=41, width=200, layers=2,
+                                      obs_perc=None, dropout=0.1, masked=True, cpu_sample_paths=50),
     "physionet_synth_b2000": dict(sde="physionet_synth", paths=2000, steps=3000, d=41, H=41, width=50, layers=2,
                                   obs_perc=None, dropout=0.1, masked=True, cpu_sample_paths=50),
     # BASELINE.json configs[2] (ii): Heston without Feller condition (parallel_train.py:525-537), demo nets, batch sweep
