@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""stage-wise comparison of the tcgen05 forward (njode_wide_forward) with the fp32 kernels on the same
+"""TEST INFRASTRUCTURE (developer tool, may import oracle/): stage-wise comparison of the tcgen05 forward (njode_wide_forward) with the fp32 kernels on the same
 batch: h_hist (every Euler step), h_before, y_after, hT, loss.  usage: wide_debug.py CASE"""
 import os, sys
 import numpy as np
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests/tools/ -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases
 import oracle.njode_oracle as orc
