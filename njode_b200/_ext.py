@@ -138,6 +138,19 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class _Cast:
+    """a host array that is converted to ``dtype`` while it is copied into the pinned staging block (one pass over the
+    data instead of astype + copy)"""
+    __slots__ = ("src", "dtype", "nbytes")
+
+    def __init__(self, src, dtype):
+        self.src, self.dtype = np.ascontiguousarray(src), np.dtype(dtype)
+        self.nbytes = self.src.size * self.dtype.itemsize
+
+    def copy_into(self, dst_u8):
+        np.copyto(dst_u8.view(self.dtype), self.src.reshape(-1), casting="unsafe")
+
+
 class PreparedBatch:
     """device-resident inputs of one forward call + the ctypes batch structs (fwd / bwd)."""
     __slots__ = ("sched", "B", "N", "dev", "keep", "fwd", "bwd_loss", "bwd_all", "n_units",
@@ -195,18 +208,26 @@ class Runner:
             if torch.is_tensor(t):
                 if t.device.type != "cpu":
                     return t.detach().to(self.device, torch.float32).contiguous().reshape(shape)
-                return np.ascontiguousarray(t.detach().numpy().astype(np.float32, copy=False)).reshape(shape)
-            return np.ascontiguousarray(np.asarray(t, dtype=np.float32)).reshape(shape)
+                a = t.detach().numpy()
+            else:
+                a = np.asarray(t)
+            if a.dtype != np.float32:
+                return _Cast(a, np.float32)
+            return np.ascontiguousarray(a).reshape(shape)
 
         if torch.is_tensor(obs_idx) and obs_idx.device.type != "cpu":
             obs_arr = obs_idx.detach().to(self.device)
         else:
-            oi = obs_idx.detach().numpy() if torch.is_tensor(obs_idx) else np.asarray(obs_idx)
-            obs_arr = np.ascontiguousarray(oi.astype(np.int32, copy=False))
+            obs_arr = obs_idx.detach().numpy() if torch.is_tensor(obs_idx) else np.asarray(obs_idx)
         # small batches: the index arrays are cheaper to build with NumPy on the host (a dozen tensor-op
         # launches cost more than sorting a few thousand rows); large ones are built on the device
         mode = os.environ.get("NJODE_INDEX", "auto")
         host_index = (not torch.is_tensor(obs_arr)) and (mode == "host" or (mode == "auto" and N + B < 16384))
+        if not torch.is_tensor(obs_arr):
+            if host_index:
+                obs_arr = np.ascontiguousarray(obs_arr.astype(np.int32, copy=False))
+            elif obs_arr.dtype != np.int32:
+                obs_arr = _Cast(obs_arr, np.int32)          # int64 -> int32 on the way into the staging block
         budget = float(B) * sched.S / (16.0 * self.sms * 12)
         T1, T2 = max(8, int(0.75 * budget)), max(4, int(0.4 * budget))
         host_idx = {}
@@ -235,7 +256,10 @@ class Runner:
         pin_np = pin.numpy()
         for k, o in offs.items():
             a = arrays[k]
-            pin_np[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+            if isinstance(a, _Cast):
+                a.copy_into(pin_np[o:o + a.nbytes])
+            else:
+                pin_np[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
         dev.copy_(pin[:dev.numel()], non_blocking=True)
         if self.is_cuda:
             self._pin_event = torch.cuda.Event()
