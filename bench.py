@@ -4,10 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
 One "step" = one forward + backward of the NJ-ODE over one batch (+ the gradient all-reduce when
-N > 1).  Workload at every N (weak scaling, per-GPU work fixed): BASELINE.json configs[1] -- the
+N > 1).  Headline workload at every N (weak scaling, per-GPU work fixed): BASELINE.json configs[1] -- the
 demo architecture (d=1, H=10, 2x50 tanh ode/enc/readout, dropout 0.1, train mode) on Heston paths,
 100 Euler steps, obs_perc 0.1, 20 000 paths per GPU in one batch.  Data are synthetic (seeded
 Euler-Maruyama Heston, NJODE/stock_model.py:181-221 restated), weights random-init (Xavier, seed 0).
+
+The same command also measures the two configurations BASELINE.json's targets are quoted on and reports them in
+``target_configs`` of the same JSON line ("next" #1):
+  bs_demo_200          the reference's own batch (model_overview.csv:2: BlackScholes, batch 200): value / e2e on the B200
+                       next to the CPU arm on the SAME 200 paths, one thread (the reference's server setting) and all host
+                       threads, and the resulting ratios (target: >= 50x); N = 1 only
+  bs_scaled_d16_h256   d = 16, H = 256, 4x256 nets, 1000 steps, device-generated paths, tcgen05 kernels: value / e2e /
+                       roofline at every N, so the 1 -> 8 curve of the 3.5 MB all-reduce is computable from the scaling run
+and, when N > 1, ``dp_check``: the all-reduced flat gradient is bit-identical on every rank and equals the single-GPU
+gradient of the concatenated batch (rtol 1e-5), checked outside the timed regions.
 
 Printed JSON (rank 0, one line):
   value        whole-job paths*steps/s with the collated batch already resident in HBM
@@ -15,9 +25,9 @@ Printed JSON (rank 0, one line):
   e2e          same metric through the public API `model(times, time_ptr, X, obs_idx, ...)` with
                HOST tensors: host schedule/CSR build + one pinned H2D copy + fwd + bwd + D2H of the
                loss inside the timed region
-  roofline     dominant kernel (nj_bwd_kernel): algorithmic fp32 flops / CUDA-event duration over
-               the measured fp32-FMA peak of this GPU (narrow nets are FMA-pipe bound, not HBM /
-               tensor bound: SURVEY.md §8d); the HBM view of the same launch is in roofline.hbm
+  roofline     dominant kernel (its name comes from the library: njode_last_kernel): algorithmic fp32 flops /
+               CUDA-event duration over the measured fp32-FMA peak of this GPU (narrow nets are FMA-pipe bound, not
+               HBM / tensor bound: SURVEY.md 8d); the HBM view of the same launch is in roofline.hbm
   cpu_baseline the oracle port of the reference (oracle/njode_oracle.py, same ATen op sequence as
                NJODE/models.py) timed on this box's host cores on a bounded sample (N=1 only)
 `--impl reference` times only that CPU port with all host threads (one step = the bounded sample).
@@ -271,11 +281,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the CPU arm: oracle port of the reference (test infrastructure, used here only as the baseline)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_step_fn(wl, seed, threads):
+def cpu_port_step_fn(wl, seed, threads, n=None):
     import torch
     import oracle.njode_oracle as orc
     torch.set_num_threads(threads)
-    n = wl["cpu_sample_paths"]
+    n = wl["cpu_sample_paths"] if n is None else n
     wl_s = dict(wl)
     if "cpu_sample_steps" in wl:
         wl_s["steps"] = wl["cpu_sample_steps"]
@@ -288,9 +298,44 @@ def cpu_port_step_fn(wl, seed, threads):
 
     def step():
         orc.loss_and_grads(ocfg, sd, batch, dt, horizon(wl), dropout_seed="native")
-    sample = "%d of the workload's paths x %d Euler steps, fwd+bwd, train mode (aten dropout), %d threads" % (
-        n, S, threads)
+    whole = n == wl["paths"] and "cpu_sample_steps" not in wl
+    sample = "%s%d paths x %d Euler steps, fwd+bwd, train mode (aten dropout), %d thread%s" % (
+        "the workload's batch: " if whole else "a sample of the workload: ", n, S, threads, "" if threads == 1 else "s")
     return step, n * S, sample
+
+
+def time_cpu(step, budget_s, min_reps, max_reps):
+    step()
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < min_reps or (time.perf_counter() < t_end and len(ts) < max_reps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts))
+
+
+def cpu_arms(wl, budget_all=20.0, budget_one=8.0):
+    """(all host threads, one thread) baselines of one workload; the one-thread arm (the reference's own server setting,
+    NJODE/train.py:44,209: N_CPUS = 1) runs a quarter of the sample unless the sample is the whole batch"""
+    import torch
+    threads = os.cpu_count() or 1
+    step, units, sample = cpu_port_step_fn(wl, 1234, threads)
+    all_ = {"value": units / time_cpu(step, budget_all, 3, 8), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    whole = wl["cpu_sample_paths"] == wl["paths"]
+    n1 = wl["cpu_sample_paths"] if whole else max(1, wl["cpu_sample_paths"] // 4)
+    step1, units1, sample1 = cpu_port_step_fn(wl, 1234, 1, n=n1)
+    one = {"value": units1 / time_cpu(step1, budget_one, 2, 5), "unit": UNIT, "cores": 1, "kind": "port", "sample": sample1}
+    torch.set_num_threads(threads)
+    return all_, one
+
+
+def config_of(wl_name, wl, **extra):
+    c = {"workload": wl_name, "sde": wl["sde"], "paths_per_gpu": wl["paths"], "euler_steps": wl["steps"],
+         "input_size": wl["d"], "hidden_size": wl["H"], "mlp": "%dx%d tanh" % (wl["layers"], wl["width"]),
+         "dropout": wl["dropout"], "mode": "train"}
+    c.update(extra)
+    return c
 
 
 def run_reference(args, wl_name, wl):
@@ -312,39 +357,102 @@ def run_reference(args, wl_name, wl):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": wl_name, "sde": wl["sde"], "paths_per_gpu": wl["paths"], "euler_steps": wl["steps"],
-                      "input_size": wl["d"], "hidden_size": wl["H"], "mlp": "%dx%d tanh" % (wl["layers"], wl["width"]),
-                      "dropout": wl["dropout"], "mode": "train", "parallelism": "cpu"},
+           "config": config_of(wl_name, wl, parallelism="cpu"),
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0, "torch_threads": torch.get_num_threads()}
+           "gpu_launches": 0, "torch_threads": torch.get_num_threads(),
+           "note": "ONE CPU process on rank 0 whatever --gpus says (n_gpus only echoes the launch)"}
+    if args.targets:
+        # the reference's own batch (model_overview.csv:2): the full 200 paths, all threads and one thread
+        tw = WORKLOADS["bs_demo_200"]
+        all_, one = cpu_arms(tw, budget_all=6.0, budget_one=6.0)
+        out["target_configs"] = {"bs_demo_200": {"config": config_of("bs_demo_200", tw, parallelism="cpu"),
+                                                 "cpu_baseline": all_, "cpu_baseline_1thread": one}}
     print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------
-def run_b200(args, wl_name, wl):
-    import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from njode_b200 import models, _ext
-    from njode_b200 import dist as njdist
+class Ctx:
+    """per-process state shared by the workloads of one bench command"""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _ext.cuda_lib().dll
-    lib.njode_launch_count.restype = C.c_longlong
-    lib.njode_get_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
-    lib.njode_fma_peak_launch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
-    lib.njode_l2_flush.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    def __init__(self):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from njode_b200 import _ext
+        self.C, self.torch, self.dist = C, torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        lib = self.lib = _ext.cuda_lib().dll
+        lib.njode_launch_count.restype = C.c_longlong
+        lib.njode_get_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        lib.njode_fma_peak_launch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
+        lib.njode_l2_flush.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        lib.njode_last_kernel.argtypes = [C.c_int]
+        lib.njode_last_kernel.restype = C.c_char_p
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
+        self.peaks = {}
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.traffic = {}
+        try:
+            self.traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
+        self._fma_peak = None
+
+    def stream(self):
+        return self.C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def flush(self):
+        self.lib.njode_l2_flush(self.C.c_void_p(self.flush_buf.data_ptr()), self.flush_buf.numel(), self.stream())
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def fma_peak(self):
+        """measured fp32 FMA peak of this GPU in TFLOP/s (dependent FFMA chains on every SM)"""
+        if self._fma_peak is None:
+            torch, C = self.torch, self.C
+            scratch = torch.empty(148 * 8 * 256 * 2, dtype=torch.float32, device=self.dev)
+            fm = C.c_double()
+            peak = 0.0
+            for it in range(4):
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                self.lib.njode_fma_peak_launch(C.c_void_p(scratch.data_ptr()), 4096, C.byref(fm), self.stream())
+                b_.record()
+                torch.cuda.synchronize()
+                peak = max(peak, 2.0 * fm.value / (a.elapsed_time(b_) * 1e-3) / 1e12)
+            self._fma_peak = peak
+        return self._fma_peak
+
+
+def measure_b200(ctx, wl_name, wl, steps, warmup, sample_clocks=True):
+    """resident-input arm, end-to-end arm and the roofline of one workload on this rank's GPU; returns the JSON fields
+    (rank 0) -- every rank must call it (collectives inside)."""
+    torch, C, lib = ctx.torch, ctx.C, ctx.lib
+    from njode_b200 import models
+    from njode_b200 import dist as njdist
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
 
     B = wl["paths"]                      # per GPU (weak scaling)
     first = rank * B
@@ -359,17 +467,10 @@ def run_b200(args, wl_name, wl):
     torch.manual_seed(0)
     model = models.NJODE(**model_cfg(wl)).to(dev)
     model.train()
-    dp = None
     if world > 1:
         dp = njdist.DataParallel(model, global_batch_size=B * world)
         dp.set_batch(B * world, first)
     params = [p for p in model.parameters()]
-    stream = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def flush():
-        lib.njode_l2_flush(C.c_void_p(flush_buf.data_ptr()), flush_buf.numel(), stream())
 
     def args_of(b):
         return (b["times"], b["time_ptr"], b["X"], b["obs_idx"], dt, T, b["start_X"], b["n_obs_ot"])
@@ -389,21 +490,20 @@ def run_b200(args, wl_name, wl):
         return loss
 
     lib.njode_set_timing(1)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(ctx.local)
+    if rank == 0 and sample_clocks:
         sampler.start()
-    if world > 1:
-        dist.barrier()
+    ctx.barrier()
     torch.cuda.synchronize()
     launches0 = lib.njode_launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     kf, kb = [], []
     wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush()
+    for i in range(steps):
+        ctx.flush()
         ev[i][0].record()
         step_resident()
         ev[i][1].record()
@@ -412,18 +512,14 @@ def run_b200(args, wl_name, wl):
             lib.njode_get_timing(C.byref(f), C.byref(b_))
             kf.append(f.value); kb.append(b_.value)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    ctx.barrier()
     wall = time.perf_counter() - wall0
     launches = lib.njode_launch_count() - launches0
-    step_ms = [a.elapsed_time(b_) for a, b_ in ev]
-    total_ms = float(sum(step_ms))
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    total_ms = ctx.max_over_ranks(float(sum(a.elapsed_time(b_) for a, b_ in ev)))
+    ms_per_step = total_ms / steps
     value = units_per_step / (ms_per_step * 1e-3)
+    kname_f = (lib.njode_last_kernel(0) or b"").decode()
+    kname_b = (lib.njode_last_kernel(1) or b"").decode()
 
     # ---- end-to-end arm: public API, host tensors ---------------------------------------------
     model.output_device = "cpu"
@@ -448,67 +544,44 @@ def run_b200(args, wl_name, wl):
     for j in range(2):
         step_e2e(host_batches[j % nb])
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    n_e2e = max(3, min(args.steps, 10))
+    ctx.barrier()
+    n_e2e = max(3, min(steps, 10))
     t0 = time.perf_counter()
     h2d = 0
     for j in range(n_e2e):
         step_e2e(host_batches[j % nb])
         h2d += model.last_h2d_bytes
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
     e2e_val = units_per_step * n_e2e / e2e_s
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     N_rows = pb.N
     F_ode, F_enc, F_ro = flops_per_unit(wl)
     fwd_flops = B * S * F_ode + N_rows * (F_enc + 2 * F_ro) + B * F_enc
     bwd_flops = 2 * fwd_flops
-    # measured fp32 FMA peak of this GPU (dependent FFMA chains on every SM)
-    scratch = torch.empty(148 * 8 * 256 * 2, dtype=torch.float32, device=dev)
-    fm = C.c_double()
-    peak = 0.0
-    for it in range(4):
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        lib.njode_fma_peak_launch(C.c_void_p(scratch.data_ptr()), 4096, C.byref(fm), stream())
-        b_.record()
-        torch.cuda.synchronize()
-        peak = max(peak, 2.0 * fm.value / (a.elapsed_time(b_) * 1e-3) / 1e12)
+    peak = ctx.fma_peak()
     bwd_ms = float(np.median(kb)) if kb else float("nan")
     fwd_ms = float(np.median(kf)) if kf else float("nan")
     achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12
     H = wl["H"]
     tensor_path = model.last_forward_path == "tcgen05"
-    alg_bytes_bwd = 4 * (S * B * H + N_rows * (H + 2 * wl["d"]) + B * wl["d"]) + 4 * model._flat.numel()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    alg_bytes_bwd = 4 * (N_rows * (H + 2 * wl["d"]) + B * wl["d"]) + 4 * model._flat.numel()
+    peaks = ctx.peaks
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/ncu_traffic.json names the capture), else null
-    traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(wl_name, {})
-    except Exception:
-        pass
-    seg_path = (not wl.get("masked")) and (not wl.get("use_rnn")) and pb.fwd.unit_kind == 1 and wl["width"] <= 100
-    kname = "nj_seg_bwd_kernel" if seg_path else "nj_bwd_kernel"
-    roofline = {"kernel": kname, "bound": "fp32_fma", "achieved": achieved, "peak": peak,
+    # DRAM bytes per launch of the dominant kernel: the committed `ncu --set full` capture of this workload
+    # (dram__bytes_read.sum + dram__bytes_write.sum); profiles/ncu_traffic.json names the capture and the git commit it
+    # was taken at -- null when there is no capture of this workload / kernel
+    tr = ctx.traffic.get(wl_name, {}).get(kname_b, {})
+    roofline = {"kernel": kname_b, "fwd_kernel": kname_f, "bound": "fp32_fma", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic.get(kname, {}).get("dram_bytes"), "traffic_source": traffic.get(kname, {}).get("source"),
+                "traffic": tr.get("dram_bytes"), "traffic_source": tr.get("source"), "traffic_commit": tr.get("commit"),
                 "algorithmic_bytes": alg_bytes_bwd,
                 "peak_source": "measured in this run (njode_fma_peak_launch: FFMA chains on all SMs)",
                 "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
                 "fwd_achieved": fwd_flops / (fwd_ms * 1e-3) / 1e12,
+                "step_frac": 3.0 * fwd_flops / (ms_per_step * 1e-3) / 1e12 / peak if peak else None,
                 "flops_per_launch": bwd_flops,
                 "hbm": {"bound": "hbm", "achieved": alg_bytes_bwd / (bwd_ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s",
@@ -522,63 +595,113 @@ def run_b200(args, wl_name, wl):
         # sustained bf16 GEMM peak (the kernels run inside a long step).
         lib.njode_wide_get_timing.argtypes = [C.POINTER(C.c_float)] * 3
         lib.njode_wide_get_timing_bwd.argtypes = [C.POINTER(C.c_float)] * 2
-        te, to, tr, tc_, td = (C.c_float() for _ in range(5))
-        lib.njode_wide_get_timing(C.byref(te), C.byref(to), C.byref(tr))
+        te, to, tr_, tc_, td = (C.c_float() for _ in range(5))
+        lib.njode_wide_get_timing(C.byref(te), C.byref(to), C.byref(tr_))
         lib.njode_wide_get_timing_bwd(C.byref(tc_), C.byref(td))
-        k_ms = te.value + to.value + tr.value + tc_.value + td.value
+        k_ms = te.value + to.value + tr_.value + tc_.value + td.value
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = 3.0 * fwd_flops / (k_ms * 1e-3) / 1e12
+        trw = ctx.traffic.get(wl_name, {}).get("nj_wide", {})
         roofline = {"kernel": "nj_wide_kernel + nj_wide_bwd_kernel + nj_wide_dw_kernel (tcgen05)", "bound": "tensor",
                     "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                    "traffic": traffic.get("nj_wide", {}).get("dram_bytes"), "traffic_source": traffic.get("nj_wide", {}).get("source"),
+                    "traffic": trw.get("dram_bytes"), "traffic_source": trw.get("source"), "traffic_commit": trw.get("commit"),
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                    "kernel_ms": k_ms, "fwd_enc_ms": te.value, "fwd_ode_ms": to.value, "fwd_ro_ms": tr.value,
+                    "kernel_ms": k_ms, "fwd_enc_ms": te.value, "fwd_ode_ms": to.value, "fwd_ro_ms": tr_.value,
                     "bwd_chain_ms": tc_.value, "bwd_dw_ms": td.value, "flops_per_launch": 3.0 * fwd_flops}
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    del model, pb, host_batches, batch
+    torch.cuda.empty_cache()
+    return {"value": value, "ms_per_step": ms_per_step, "steps": steps, "warmup": max(warmup, 3),
+            "dtype": "bf16" if tensor_path else "f32",
+            "config": config_of(wl_name, wl, euler_steps=S, obs_rows_per_gpu=N_rows, parallelism="dp%d" % world,
+                                l2="flushed between timed steps (256 MiB write)"),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d / n_e2e),
+                    "d2h_bytes_per_step": 4, "steps": n_e2e},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s_timed_region": wall}
+
+
+def dp_check(ctx):
+    """N > 1, outside every timed region: the NCCL-reduced flat gradient (a) is bit-identical on all ranks and (b) equals
+    the gradient rank 0 computes alone on the concatenated batch (element-wise rtol 1e-5 + 1e-7 of the tensor's max).
+    Demo nets (fp32 kernels), dropout on (keys use global path ids: rank-count invariant), 96 paths per rank."""
+    torch, dist = ctx.torch, ctx.dist
+    from njode_b200 import models
+    from njode_b200 import dist as njdist
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    wl = dict(WORKLOADS["bs_demo_200"], paths=96 * world)
+    full, dt = synth_batch(wl, 777, 0, wl["paths"])
+    shard, first = njdist.shard_batch(full, rank, world)
+
+    def grad_of(batch, bs_norm, first_id, sync):
+        torch.manual_seed(0)
+        m = models.NJODE(**model_cfg(wl)).to(dev)
+        m.train()
+        m.batch_size_norm, m.path_id_offset = bs_norm, first_id
+        if sync:
+            njdist.DataParallel(m, global_batch_size=bs_norm).set_batch(bs_norm, first_id)
+        torch.manual_seed(99)                     # the same dropout seed on every rank and in the single-GPU run
+        hT, loss = m(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], dt, 1.0, batch["start_X"], batch["n_obs_ot"])
+        loss.backward()
+        return torch.cat([p.grad.reshape(-1) for p in m.parameters()]), float(loss)
+
+    g, part_loss = grad_of(shard, wl["paths"], first, True)
+    gathered = [torch.empty_like(g) for _ in range(world)]
+    dist.all_gather(gathered, g)
+    identical = all(bool(torch.equal(gathered[0], x)) for x in gathered[1:])
+    lsum = torch.tensor([part_loss], device=dev, dtype=torch.float64)
+    dist.all_reduce(lsum)
+    out = None
+    if rank == 0:
+        g1, loss1 = grad_of(full, wl["paths"], 0, False)
+        err = (g - g1).abs()
+        lim = 1e-5 * g1.abs() + 1e-7 * float(g1.abs().max())
+        out = {"ranks": world, "paths": wl["paths"], "grad_floats": int(g.numel()),
+               "identical_across_ranks": identical,
+               "max_abs_err_vs_single_gpu": float(err.max()), "max_norm_rel_err": float(err.max() / g1.abs().max()),
+               "within_rtol_1e-5": bool((err <= lim).all()),
+               "loss_sum_over_ranks": float(lsum.item()), "loss_single_gpu": loss1}
+        assert identical, "dp_check: the all-reduced gradient differs between ranks"
+        assert out["within_rtol_1e-5"], "dp_check: data-parallel gradient != single-GPU gradient: %r" % out
+    dist.barrier()
+    return out
+
+
+def run_b200(args, wl_name, wl):
+    ctx = Ctx()
+    head = measure_b200(ctx, wl_name, wl, args.steps, args.warmup)
+    targets = {}
+    if args.targets:
+        if ctx.world == 1 and wl_name != "bs_demo_200":
+            targets["bs_demo_200"] = measure_b200(ctx, "bs_demo_200", WORKLOADS["bs_demo_200"], max(args.steps, 20), args.warmup)
+        if wl_name != "bs_scaled_d16_h256":
+            targets["bs_scaled_d16_h256"] = measure_b200(ctx, "bs_scaled_d16_h256", WORKLOADS["bs_scaled_d16_h256"],
+                                                         max(3, min(args.steps, 6)), args.warmup)
+    check = dp_check(ctx) if ctx.world > 1 else None
+    if ctx.rank != 0:
+        if ctx.world > 1:
+            ctx.dist.destroy_process_group()
         return
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor_path else "f32", "data": "synthetic",
-           "config": {"workload": wl_name, "sde": wl["sde"], "paths_per_gpu": B, "euler_steps": S,
-                      "obs_rows_per_gpu": N_rows, "input_size": wl["d"], "hidden_size": H,
-                      "mlp": "%dx%d tanh" % (wl["layers"], wl["width"]), "dropout": wl["dropout"],
-                      "mode": "train", "parallelism": "dp%d" % world,
-                      "l2": "flushed between timed steps (256 MiB write)"},
-           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d / n_e2e),
-                   "d2h_bytes_per_step": 4, "steps": n_e2e},
-           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-           "wall_s_timed_region": wall}
-    if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        step, units, sample = cpu_port_step_fn(wl, 1234, threads)
-        step()
-        ts = []
-        t_end = time.perf_counter() + 20.0
-        while len(ts) < 3 or (time.perf_counter() < t_end and len(ts) < 8):
-            t0 = time.perf_counter()
-            step()
-            ts.append(time.perf_counter() - t0)
-        out["cpu_baseline"] = {"value": units / float(np.median(ts)), "unit": UNIT, "cores": threads,
-                               "kind": "port", "sample": sample}
-        # the reference's own server setting is ONE torch thread (NJODE/train.py:44,209: N_CPUS = 1): same port, a quarter
-        # of the sample, one thread
-        wl1 = dict(wl, cpu_sample_paths=max(1, wl["cpu_sample_paths"] // 4))
-        step1, units1, sample1 = cpu_port_step_fn(wl1, 1234, 1)
-        step1()
-        ts1 = []
-        t_end = time.perf_counter() + 8.0
-        while len(ts1) < 2 or (time.perf_counter() < t_end and len(ts1) < 5):
-            t0 = time.perf_counter()
-            step1()
-            ts1.append(time.perf_counter() - t0)
-        out["cpu_baseline_1thread"] = {"value": units1 / float(np.median(ts1)), "unit": UNIT, "cores": 1,
-                                       "kind": "port", "sample": sample1}
-        __import__("torch").set_num_threads(threads)
+    out = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+           "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+           "config": head["config"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+           "roofline": head["roofline"], "wall_s_timed_region": head["wall_s_timed_region"]}
+    if check is not None:
+        out["dp_check"] = check
+    if ctx.world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"], out["cpu_baseline_1thread"] = cpu_arms(wl)
+    for name, t in targets.items():
+        t.update({"metric": METRIC, "unit": UNIT, "n_gpus": ctx.world, "scaling": "weak"})
+        if ctx.world == 1 and not args.no_cpu_baseline:
+            tw = WORKLOADS[name]
+            t["cpu_baseline"], t["cpu_baseline_1thread"] = cpu_arms(tw, budget_all=6.0, budget_one=6.0)
+            t["same_config_as_cpu_arm"] = tw["cpu_sample_paths"] == tw["paths"] and "cpu_sample_steps" not in tw
+            for k, cb in (("speedup_e2e_vs_cpu_all_threads", "cpu_baseline"), ("speedup_e2e_vs_cpu_1thread", "cpu_baseline_1thread")):
+                t[k] = t["e2e"]["value"] / t[cb]["value"]
+    if targets:
+        out["target_configs"] = targets
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -589,6 +712,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="heston_demo_20k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-targets", dest="targets", action="store_false",
+                    help="skip the target_configs sub-records (bs_demo_200, bs_scaled_d16_h256)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -240,6 +240,8 @@ void njode_set_timing(int on);
 int njode_get_timing(float* fwd_ms, float* bwd_ms);
 /* kernels launched by this library since it was loaded (bench.py: gpu_launches) */
 long long njode_launch_count(void);
+/* name of the main kernel launched by the most recent forward (which = 0) / backward (which = 1) call of either path */
+const char* njode_last_kernel(int which);
 /* fp32 FMA-pipe microbenchmark: dependent chains of FFMA on every SM; *fmas = lane-FMAs issued */
 int njode_fma_peak_launch(float* scratch, int iters, double* fmas, void* stream);
 /* writes `bytes` of buf (size it > L2) so the next kernel starts with a cold L2 */

@@ -2,6 +2,7 @@
 logic.  There is no CPU fallback: ``cuda_lib()`` raises when the CUDA library is missing and the
 runner refuses non-CUDA devices.  (``Lib`` can be pointed at another build of the same ABI; the
 test-suite uses that to run the host *simulation* of the kernel source, never the product.)"""
+import contextlib
 import ctypes as C
 import os
 
@@ -187,6 +188,11 @@ class Runner:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.is_cuda else None
 
+    def _guard(self):
+        """every C-ABI call plans and launches on the CURRENT CUDA device (cudaGetDevice): make it this runner's device
+        for the duration of the call, so a model on cuda:1 works while cuda:0 is current"""
+        return torch.cuda.device(self.device) if self.is_cuda else contextlib.nullcontext()
+
     # -- batch staging ----------------------------------------------------------------------
     def prepare(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, M, until_T,
                 return_path, segments, d, batch_size_norm=None, path_id_offset=0):
@@ -291,10 +297,11 @@ class Runner:
             iws = getattr(self, "_iws", None)
             if iws is None or iws.numel() < wsb:
                 iws = self._iws = torch.empty(int(wsb * 1.25) + 1024, dtype=torch.uint8, device=self.device)
-            rc = self.lib.dll.njode_build_index(
-                _ptr(obs_t), N, _ptr(view_i32("time_ptr", K + 1)), K, _ptr(view_i32("jump_step", K)), B, sched.S,
-                1 if segments else 0, T1, T2, _ptr(path_ptr), _ptr(path_rows), _ptr(row_jump), _ptr(unit_desc), _ptr(stats),
-                _ptr(iws), iws.numel(), self._stream())
+            with self._guard():
+                rc = self.lib.dll.njode_build_index(
+                    _ptr(obs_t), N, _ptr(view_i32("time_ptr", K + 1)), K, _ptr(view_i32("jump_step", K)), B, sched.S,
+                    1 if segments else 0, T1, T2, _ptr(path_ptr), _ptr(path_rows), _ptr(row_jump), _ptr(unit_desc),
+                    _ptr(stats), _ptr(iws), iws.numel(), self._stream())
             self.lib.check(rc, "njode_build_index")
             index = {"path_ptr": path_ptr, "path_rows": path_rows, "row_jump": row_jump, "unit_desc": unit_desc}
             keep.extend([out, obs_t])
@@ -349,7 +356,8 @@ class Runner:
     def plan(self, model_t, batch_t):
         pl = PlanT()
         dev = self.device.index if self.is_cuda and self.device.index is not None else 0
-        self.lib.check(self.lib.dll.njode_plan(C.byref(model_t), C.byref(batch_t), dev, C.byref(pl)), "njode_plan")
+        with self._guard():
+            self.lib.check(self.lib.dll.njode_plan(C.byref(model_t), C.byref(batch_t), dev, C.byref(pl)), "njode_plan")
         return pl
 
     def wide_supported(self, model_t):
@@ -385,8 +393,9 @@ class Runner:
                 self.lib.check(int(sbytes), "njode_wide_saved_bytes")
             blob = torch.empty(int(sbytes), dtype=torch.uint8, device=self.device)
             saved = ("wide", blob)
-        rc = dll.njode_wide_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT), _ptr(loss),
-                                    C.byref(saved_t), _ptr(blob), _ptr(ws), self._stream())
+        with self._guard():
+            rc = dll.njode_wide_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT), _ptr(loss),
+                                        C.byref(saved_t), _ptr(blob), _ptr(ws), self._stream())
         self.lib.check(rc, "njode_wide_forward")
         return hT, loss, None, None, saved
 
@@ -395,8 +404,9 @@ class Runner:
         nbytes = dll.njode_wide_workspace_bytes(C.byref(model_t), C.byref(pb.fwd))
         ws = self._wide_workspace(nbytes)
         grads = torch.empty_like(params)
-        rc = dll.njode_wide_backward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(blob), _ptr(grad_loss),
-                                     _ptr(grad_hT), _ptr(grads), _ptr(ws), self._stream())
+        with self._guard():
+            rc = dll.njode_wide_backward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(blob), _ptr(grad_loss),
+                                         _ptr(grad_hT), _ptr(grads), _ptr(ws), self._stream())
         self.lib.check(rc, "njode_wide_backward")
         return grads
 
@@ -414,21 +424,24 @@ class Runner:
             saved = (torch.empty(max(pb.sched.S, 1) * pb.B * H, **f32),
                      torch.empty(max(pb.N, 1) * H, **f32), torch.empty(max(pb.N, 1) * dout, **f32))
             saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved])
-        rc = self.lib.dll.njode_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT),
-                                        _ptr(loss), _ptr(path_h), _ptr(path_y), C.byref(saved_t),
-                                        _ptr(ws), self._stream())
+        with self._guard():
+            rc = self.lib.dll.njode_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT),
+                                            _ptr(loss), _ptr(path_h), _ptr(path_y), C.byref(saved_t),
+                                            _ptr(ws), self._stream())
         self.lib.check(rc, "njode_forward")
         return hT, loss, path_h, path_y, saved
 
     def backward(self, model_t, pb, params, saved, grad_loss, grad_hT):
-        pl = self.plan(model_t, pb.fwd)
+        # without a gradient into hT the tail units (after a path's last observation) contribute nothing
+        bt = pb.bwd_all if grad_hT is not None else pb.bwd_loss
+        pl = self.plan(model_t, bt)
         ws = self._workspace(pl.workspace_bytes)
         grads = torch.empty_like(params)
         saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved])
-        bt = pb.bwd_all if grad_hT is not None else pb.bwd_loss
-        rc = self.lib.dll.njode_backward(C.byref(model_t), C.byref(bt), _ptr(params), C.byref(saved_t),
-                                         _ptr(grad_loss), _ptr(grad_hT), _ptr(grads), _ptr(ws),
-                                         self._stream())
+        with self._guard():
+            rc = self.lib.dll.njode_backward(C.byref(model_t), C.byref(bt), _ptr(params), C.byref(saved_t),
+                                             _ptr(grad_loss), _ptr(grad_hT), _ptr(grads), _ptr(ws),
+                                             self._stream())
         self.lib.check(rc, "njode_backward")
         return grads
 

@@ -24,6 +24,12 @@ extern "C" long long njode_launch_count(void) { return g_launches; }
 #define NJ_LAUNCHED(n) (g_launches += (n))
 void nj_count_launches(int n) { g_launches += n; }          // used by njode_wide.cu
 
+// name of the main kernel the most recent forward (0) / backward (1) call launched: bench.py labels its roofline with
+// what actually ran instead of re-deriving the planner's dispatch
+static const char* g_last_kernel[2] = {"", ""};
+void nj_set_last_kernel(int which, const char* name) { g_last_kernel[which & 1] = name; }
+extern "C" const char* njode_last_kernel(int which) { return g_last_kernel[which & 1]; }
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
@@ -211,7 +217,9 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
         if (tm) cudaEventRecord(g_ev[0], st);
         NJ_CUDA(cudaFuncSetAttribute(nj_seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
         nj_seg_fwd_kernel<<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
+        nj_set_last_kernel(0, "nj_seg_fwd_kernel");
     } else {
+        nj_set_last_kernel(0, "nj_fwd_kernel");
         auto kern = nj_fwd_kernel;
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd_bytes));
         if (tm) cudaEventRecord(g_ev[0], st);
@@ -253,7 +261,9 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         auto kern = pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h : nj_seg_bwd_kernel;
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
         kern<<<pl.seg_grid_b, pl.seg.nt_b, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
+        nj_set_last_kernel(1, pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : "nj_seg_bwd_kernel");
     } else {
+        nj_set_last_kernel(1, "nj_bwd_kernel");
         auto kern = nj_bwd_kernel;
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd_bytes));
         if (tm) cudaEventRecord(g_ev[2], st);

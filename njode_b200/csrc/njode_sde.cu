@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(128) nj_sde_kernel(const __grid_constant__ NjS
     }
 }
 
-// observation mask: observed[p][k] = (u < obs_perc), column 0 forced to 1 (NJODE/data_utils.py:79-81)
+// observation mask: observed[p][k] = (u < obs_perc) for every column incl. column 0, which the reference also draws at
+// random and never uses as an observation (NJODE/data_utils.py:79-81; the collate starts at column 1, 292-307)
 __global__ void __launch_bounds__(256) nj_mask_kernel(const __grid_constant__ NjSdeArgs a) {
     const int n1 = a.p.nb_steps + 1;
     const unsigned k0 = (unsigned)(a.p.seed & 0xFFFFFFFFull), k1 = (unsigned)(a.p.seed >> 32);
@@ -147,7 +148,6 @@ __global__ void __launch_bounds__(256) nj_mask_kernel(const __grid_constant__ Nj
         for (int q = 0; q < 4; ++q) {
             const int k = 4 * k4 + q;
             int ob = ((double)w[q] * (1.0 / 4294967296.0)) < a.p.obs_perc ? 1 : 0;
-            if (k == 0) ob = 1;
             op[q] = ob;
             if (k >= 1 && k < n1) cnt += ob;
         }

@@ -11,6 +11,7 @@
 int nj_set_error(int code, const char* msg);        // njode_api.cu
 void nj_count_launches(int n);                      // njode_api.cu
 int nj_timing_flag();                               // njode_api.cu
+void nj_set_last_kernel(int which, const char* name);   // njode_api.cu
 
 #define NJW_CUDA(call)                                                                        \
     do {                                                                                      \
@@ -452,6 +453,7 @@ extern "C" int njode_wide_forward(const njode_model_t* model, const njode_batch_
         ++launches;
     }
     nj_count_launches(launches);
+    nj_set_last_kernel(0, "nj_wide_kernel");
     NJW_CUDA(cudaGetLastError());
     return 0;
 }
@@ -527,6 +529,7 @@ extern "C" int njode_wide_backward(const njode_model_t* model, const njode_batch
     nj_wide_dw_reduce_kernel<<<dim3(3 * NJODE_MAX_LINEAR * 2, 16), 256, 0, st>>>(c, a.dw_part, grads); ++launches;
     if (timing) { cudaEventRecord(g_ev[8], st); g_evb_rec = true; }
     nj_count_launches(launches);
+    nj_set_last_kernel(1, "nj_wide_bwd_kernel");
     NJW_CUDA(cudaGetLastError());
     return 0;
 }

@@ -83,7 +83,8 @@ def create_dataset(stock_model_name="BlackScholes", hyperparam_dict=hyperparam_d
     'model_name' and 'dt' to ``hyperparam_dict``."""
     hyperparam_dict['model_name'] = stock_model_name
     obs_perc = hyperparam_dict['obs_perc']
-    stockmodel = _STOCK_MODELS[stock_model_name](**hyperparam_dict, seed=seed)
+    kw = {k: v for k, v in hyperparam_dict.items() if k != 'seed'}          # a 'seed' entry would collide with seed=
+    stockmodel = _STOCK_MODELS[stock_model_name](**kw, seed=seed)
     paths, observed, nb_obs, dt = stockmodel.generate_paths_device(obs_perc=obs_perc)
     desc = json.dumps(hyperparam_dict, sort_keys=True)          # the overview row has no 'dt' (as in the reference)
     hyperparam_dict['dt'] = dt
@@ -222,7 +223,7 @@ def collate_paths(stock_paths, observed_dates, nb_obs, dt, functions=()):
             'obs_idx': torch.from_numpy(p_idx.astype(np.int64)),
             'start_X': torch.tensor(start, dtype=torch.float32),
             'n_obs_ot': torch.as_tensor(np.asarray(nb_obs)),
-            'X': torch.tensor(Xp, dtype=torch.float32).reshape(len(p_idx), -1),
+            'X': torch.tensor(Xp, dtype=torch.float32).reshape(len(p_idx), start.shape[1]),   # [0, d] when nothing is observed
             'true_paths': stock_paths, 'observed_dates': observed_dates}
 
 

@@ -15,10 +15,6 @@ import torch
 
 from . import _ext
 
-# a Runner injected by the test-suite to drive the *host simulation* of the kernels; never set in
-# production code (NJODE.forward then insists on CUDA).
-_TEST_RUNNER = None
-
 
 # ----------------------------------------------------------------------------------------------
 # helpers with the reference's names
@@ -179,7 +175,11 @@ class _NJODEFunction(torch.autograd.Function):
         else:
             hT, loss, path_h, path_y, saved = runner.forward(model_t, pb, flat, H, dout, get_loss, need_grad)
         ctx.module, ctx.runner, ctx.pb, ctx.model_t, ctx.saved = module, runner, pb, model_t, saved
+        # the backward re-reads the parameters: remember which buffer / which in-place versions the forward saw
         ctx.flat_version = module._flat_version
+        ctx.param_versions = tuple(p._version for p in params)
+        ctx.params = params
+        ctx.set_materialize_grads(False)      # an unused output (hT in loss.backward()) arrives as None, not zeros
         ctx.mark_non_differentiable(*[t for t in (path_h, path_y) if t is not None])
         outs = (hT, loss if loss is not None else hT.new_zeros(()))
         ctx.n_extra = 0
@@ -192,8 +192,16 @@ class _NJODEFunction(torch.autograd.Function):
         module, runner = ctx.module, ctx.runner
         if ctx.saved is None:
             raise RuntimeError("NJODE.forward ran without gradient bookkeeping")
+        if (ctx.flat_version != module._flat_version
+                or tuple(p._version for p in ctx.params) != ctx.param_versions):
+            # same contract as autograd's saved-tensor version check: the kernels would otherwise combine the NEW weights
+            # with activations saved under the old ones
+            raise RuntimeError("njode_b200: a parameter of the model was modified (optimizer.step(), load_state_dict(), "
+                               ".to()) between NJODE.forward and the backward of its outputs")
         flat = module._flat
         dev = flat.device
+        if g_loss is None and g_hT is None:
+            return (None,) * (6 + len(ctx.params))
         g_loss = torch.zeros((), device=dev) if g_loss is None else g_loss.to(dev, torch.float32).contiguous()
         if g_hT is not None:
             g_hT = g_hT.to(dev, torch.float32).contiguous()
@@ -359,7 +367,7 @@ class NJODE(torch.nn.Module):
         if get_loss and n_obs_ot is None:
             raise ValueError("get_loss=True needs n_obs_ot")
         self._ensure_flat()
-        runner = _TEST_RUNNER if _TEST_RUNNER is not None else _ext.cuda_runner(self._flat.device)
+        runner = _ext.cuda_runner(self._flat.device)      # raises off CUDA: there is no CPU path
         # the encoder jump forgets the old hidden state -> (path, segment) units; the masked imputation and the
         # GRU jump (use_rnn) carry h through the jump -> whole-path units
         segments = (not self.masked) and (not return_path) and (not self.use_rnn)
@@ -424,7 +432,7 @@ class NJODE(torch.nn.Module):
         expectation path and the mean square difference are computed on the device (one scalar comes back); any other
         combination takes the reference's NumPy route."""
         self.eval()
-        dev_ok = (diff_fun is _mean_square_diff and not return_paths and _TEST_RUNNER is None
+        dev_ok = (diff_fun is _mean_square_diff and not return_paths
                   and next(self.parameters()).device.type == "cuda"
                   and getattr(stockmodel, "supports_cond_exp_device", lambda d: False)(self.output_size))
         path_t, path_y, pb = self._pred_path(times, time_ptr, X, obs_idx, delta_t, T, start_X, M, on_device=dev_ok)

@@ -78,6 +78,50 @@ def build_schedule(times, delta_t, T, until_T, return_path):
     return sched
 
 
+_CondExpSchedule = collections.namedtuple(
+    "_CondExpSchedule", "step_dt step_t jump_index jump_step rec_t rec_step rec_jumps")
+
+
+def cond_exp_schedule(times, delta_t, T, start_time=None):
+    """event list of ``StockModel.compute_cond_exp`` (NJODE/stock_model.py:75-146).  Same Euler marching rule as
+    ``build_schedule`` but its own observation filter: an observation time beyond ``T + 1e-10`` ends the list, one at or
+    before the current time is skipped (the regime-switching ``Combined`` model restarts the loop at ``start_time``),
+    and the march always continues to ``T``.  Returns, all float64 / int64 NumPy arrays:
+      step_dt, step_t [S]     length of step k and the time at its start
+      jump_index, jump_step   [J] index into ``times`` of every processed observation time, steps done before it
+      rec_t, rec_step, rec_jumps [E]  the records of ``path_t``: time stamp, steps done, jumps applied at that record
+    """
+    current_time = start_time if start_time else 0.0
+    step_dt, step_t, jump_index, jump_step = [], [], [], []
+    rec_t, rec_step, rec_jumps = [], [], []
+    if not start_time:
+        rec_t.append(0.); rec_step.append(0); rec_jumps.append(0)
+
+    def march(target, current_time):
+        while current_time < (target - 1e-10 * delta_t):
+            delta_t_ = delta_t if current_time < target - delta_t else target - current_time
+            step_t.append(current_time)
+            step_dt.append(delta_t_)
+            current_time = current_time + delta_t_
+            rec_t.append(current_time); rec_step.append(len(step_dt)); rec_jumps.append(len(jump_step))
+        return current_time
+
+    for i, obs_time in enumerate(times):
+        if obs_time > T + 1e-10:
+            break
+        if obs_time <= current_time:
+            continue
+        current_time = march(obs_time, current_time)
+        jump_index.append(i)
+        jump_step.append(len(step_dt))
+        rec_t.append(obs_time); rec_step.append(len(step_dt)); rec_jumps.append(len(jump_step))
+    march(T, current_time)
+    f64, i64 = np.float64, np.int64
+    return _CondExpSchedule(np.array(step_dt, dtype=f64), np.array(step_t, dtype=f64), np.array(jump_index, dtype=i64),
+                            np.array(jump_step, dtype=i64), np.array(rec_t, dtype=f64), np.array(rec_step, dtype=i64),
+                            np.array(rec_jumps, dtype=i64))
+
+
 def build_csr(time_ptr, obs_idx, B):
     """rows of every path in time order.  obs_idx: int64 numpy [N]; rows are time-major already
     (NJODE/data_utils.py:298-307), so a stable sort by path keeps each path's rows time-ordered."""

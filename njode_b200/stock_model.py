@@ -12,7 +12,6 @@
 
 There is no CPU generator: without the CUDA library / a CUDA device ``generate_paths`` raises.
 """
-import copy
 import ctypes as C
 import math
 
@@ -102,7 +101,7 @@ class StockModel:
     def generate_paths_device(self, start_X=None, obs_perc=None, nb_paths=None, first_path=None, device=None):
         """-> (paths f64 [n, out_dim, steps+1], observed i32 [n, steps+1] or None, nb_obs i32 [n] or None, dt),
         all on the device.  ``observed``/``nb_obs`` are produced when ``obs_perc`` is given
-        (NJODE/data_utils.py:79-81: observed[:, 0] = 1, nb_obs counts columns >= 1)."""
+        (NJODE/data_utils.py:79-81: every column incl. column 0 is Bernoulli(obs_perc), nb_obs counts columns >= 1)."""
         device = torch.device(device or self.device)
         if device.type != "cuda" or not torch.cuda.is_available():
             raise _ext.NjodeError("njode_b200.stock_model: the generators run on CUDA devices only (no CPU fallback)")
@@ -161,70 +160,81 @@ class StockModel:
         lib.check(rc, "njode_cond_exp")
         return out
 
-    def next_cond_exp(self, *args, **kwargs):
-        raise ValueError("not implemented yet")
+    def _decay(self, step_t, step_dt, d):
+        """the analytic conditional expectation of every model moves each coordinate towards a fixed point at an exponential
+        rate: y(t + s) = fp + (y(t) - fp) exp(rate(t) s).  Returns (rate * step_dt as [S, d], fp as [d]) for Euler steps
+        starting at ``step_t`` of length ``step_dt``; subclasses define it from their ``next_cond_exp`` formula."""
+        raise ValueError("not implemented yet")          # same error as the reference's abstract next_cond_exp
+
+    def _coeff(self, t):
+        """periodic_coeff on an array of times (NJODE/stock_model.py:29-32)"""
+        t = np.asarray(t, dtype=np.float64)
+        return np.ones_like(t) if self.sine_coeff is None else 1 + np.sin(self.sine_coeff * t)
+
+    def next_cond_exp(self, y, delta_t, current_t):
+        """E[X_{t + delta_t} | X_t = y] (NJODE/stock_model.py:178-179, 277-286, 353-354, 393-395)"""
+        la, fp = self._decay(np.array([current_t], dtype=np.float64), np.array([delta_t], dtype=np.float64), np.shape(y)[1])
+        return fp + (y - fp) * np.exp(la[0])
 
     def compute_cond_exp(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
                          return_path=True, get_loss=False, weight=0.5, start_time=None, **kwargs):
-        """NJODE/stock_model.py:50-151 (same event loop as NJODE.forward, NumPy).  One deviation: the
-        tail loop passes ``current_time`` to ``next_cond_exp`` -- the reference omits the argument
-        (stock_model.py:139) and raises TypeError whenever time remains after the last observation."""
-        y = start_X
-        batch_size = start_X.shape[0]
-        current_time = 0.0
-        if start_time:
-            current_time = start_time
+        """StockModel.compute_cond_exp (NJODE/stock_model.py:50-151): the analytic counterpart of NJODE.forward --
+        between observations every path follows its model's conditional expectation, at an observation the observed
+        paths are reset to the observed value.  Returns ``loss`` or ``(loss, path_t, path_y [E, B, d])`` like the
+        reference.
+
+        Evaluated in closed form over the event list (schedule.cond_exp_schedule) instead of stepping: with
+        P[k] = sum of the first k log-factors, the value of a path at a record is
+        fp + (x_a - fp) exp(P[k_record] - P[k_a]) where (x_a, k_a) is the path's latest observation (or the start)
+        -- one gather and one exp for the whole [E, B, d] block.  One deviation from the reference: its tail loop calls
+        ``next_cond_exp`` without the current time (stock_model.py:139) and raises TypeError whenever time remains after
+        the last observation; here the tail uses the current time like every other step."""
+        from . import schedule as _sched
+        X, start_X = np.asarray(X), np.asarray(start_X)
+        obs_idx, time_ptr = np.asarray(obs_idx, dtype=np.int64), np.asarray(time_ptr, dtype=np.int64)
+        B, d = start_X.shape
+        cs = _sched.cond_exp_schedule(times, delta_t, T, start_time)
+        la, fp = self._decay(cs.step_t, cs.step_dt, d)
+        P = np.zeros((len(cs.step_dt) + 1, d))
+        np.cumsum(la, axis=0, out=P[1:])
+        # observation rows of the processed observation times, in processing order
+        J = len(cs.jump_index)
+        lo = time_ptr[cs.jump_index] if J else np.zeros(0, dtype=np.int64)
+        cnt = (time_ptr[cs.jump_index + 1] - lo) if J else lo
+        first = np.cumsum(cnt) - cnt
+        row_j = np.repeat(np.arange(J), cnt)
+        rows = np.arange(int(cnt.sum())) - first[row_j] + lo[row_j]
+        row_p = obs_idx[rows]
+        # anchor[j, b]: position (into rows) of path b's latest observation among the first j observation times, -1 = start
+        anchor = np.full((J + 1, B), -1, dtype=np.int64)
+        anchor[row_j + 1, row_p] = np.arange(len(rows))
+        np.maximum.accumulate(anchor, axis=0, out=anchor)
+
+        def value_at(pos, paths, k):
+            """conditional expectation after k Euler steps of the given paths, anchored at rows[pos] (or the start)"""
+            has = pos >= 0
+            safe = np.where(has, pos, 0)
+            xa = np.where(has[..., None], X[rows[safe]] if len(rows) else 0.0, start_X[paths]).astype(np.float64)
+            ka = np.where(has, cs.jump_step[row_j[safe]] if len(rows) else 0, 0)
+            k = np.broadcast_to(k, ka.shape)
+            y = fp + (xa - fp) * np.exp(P[k] - P[ka])
+            return np.where((k == ka)[..., None], xa, y)          # an observation is reproduced exactly
+
         loss = 0
-        if return_path:
-            if start_time:
-                path_t, path_y = [], []
-            else:
-                path_t, path_y = [0.], [y]
-        for i, obs_time in enumerate(times):
-            if obs_time > T + 1e-10:
-                break
-            if obs_time <= current_time:
-                continue
-            while current_time < (obs_time - 1e-10 * delta_t):
-                if current_time < obs_time - delta_t:
-                    delta_t_ = delta_t
-                else:
-                    delta_t_ = obs_time - current_time
-                y = self.next_cond_exp(y, delta_t_, current_time)
-                current_time = current_time + delta_t_
-                if return_path:
-                    path_t.append(current_time)
-                    path_y.append(y)
-            start, end = time_ptr[i], time_ptr[i + 1]
-            X_obs = X[start:end]
-            i_obs = obs_idx[start:end]
-            Y_bj = y
-            temp = copy.copy(y)
-            temp[i_obs] = X_obs
-            y = temp
-            Y = y
-            if get_loss:
-                loss = loss + compute_loss(X_obs=X_obs, Y_obs=Y[i_obs], Y_obs_bj=Y_bj[i_obs],
-                                           n_obs_ot=n_obs_ot[i_obs], batch_size=batch_size, weight=weight)
-            if return_path:
-                path_t.append(obs_time)
-                path_y.append(y)
-        while current_time < T - 1e-10 * delta_t:
-            if current_time < T - delta_t:
-                delta_t_ = delta_t
-            else:
-                delta_t_ = T - current_time
-            y = self.next_cond_exp(y, delta_t_, current_time)
-            current_time = current_time + delta_t_
-            if return_path:
-                path_t.append(current_time)
-                path_y.append(y)
-        if return_path:
-            return loss, np.array(path_t), np.array(path_y)
-        return loss
+        if get_loss and len(rows):
+            # compute_loss (NJODE/stock_model.py:471-481) with Y = X at the observed rows and Y_bj = value before the reset
+            ybj = value_at(anchor[row_j, row_p], row_p, cs.jump_step[row_j])
+            eps = 1e-10
+            inner = (2 * weight * np.sqrt(eps) +
+                     2 * (1 - weight) * np.sqrt(np.sum((ybj - X[rows]) ** 2, axis=1) + eps)) ** 2
+            loss = np.sum(inner / np.asarray(n_obs_ot)[row_p]) / B
+        if not return_path:
+            return loss
+        path_y = value_at(anchor[cs.rec_jumps], np.broadcast_to(np.arange(B), (len(cs.rec_t), B)), cs.rec_step[:, None])
+        return loss, cs.rec_t, path_y
 
     def get_optimal_loss(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, weight=0.5):
-        """NJODE/stock_model.py:153-158"""
+        """NJODE/stock_model.py:153-158: the loss of the true conditional expectation"""
         return self.compute_cond_exp(times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
                                      return_path=False, get_loss=True, weight=weight)
 
@@ -241,8 +251,9 @@ class Heston(StockModel):
         self.speed = speed
         self.correlation = correlation
 
-    def next_cond_exp(self, y, delta_t, current_t):
-        return y * np.exp(self.drift * self.periodic_coeff(current_t) * delta_t)
+    def _decay(self, step_t, step_dt, d):
+        """NJODE/stock_model.py:178-179: y exp(drift c(t) s)"""
+        return np.repeat((self.drift * self._coeff(step_t) * step_dt)[:, None], d, axis=1), np.zeros(d)
 
 
 class HestonWOFeller(StockModel):
@@ -262,14 +273,15 @@ class HestonWOFeller(StockModel):
         self.retur_vol = return_vol
         self.v0 = self.mean if v0 is None else v0
 
-    def next_cond_exp(self, y, delta_t, current_t):
+    def _decay(self, step_t, step_dt, d):
+        """NJODE/stock_model.py:277-286: spot coordinates y exp(drift c(t) s); with return_vol the second half of the
+        coordinates is the variance, mean reverting at ``speed`` (no periodic coefficient)"""
+        la = np.repeat((self.drift * self._coeff(step_t) * step_dt)[:, None], d, axis=1)
+        fp = np.zeros(d)
         if self.retur_vol:
-            s, v = np.split(y, indices_or_sections=2, axis=1)
-            s = s * np.exp(self.drift * self.periodic_coeff(current_t) * delta_t)
-            exp_delta = np.exp(-self.speed * delta_t)
-            v = v * exp_delta + self.mean * (1 - exp_delta)
-            return np.concatenate([s, v], axis=1)
-        return y * np.exp(self.drift * self.periodic_coeff(current_t) * delta_t)
+            la[:, d // 2:] = (-self.speed * np.asarray(step_dt, dtype=np.float64))[:, None]
+            fp[d // 2:] = self.mean
+        return la, fp
 
 
 class BlackScholes(StockModel):
@@ -280,8 +292,9 @@ class BlackScholes(StockModel):
         super().__init__(drift=drift, volatility=volatility, nb_paths=nb_paths, nb_steps=nb_steps, S0=S0,
                          maturity=maturity, sine_coeff=sine_coeff, **_gen_kw(kwargs))
 
-    def next_cond_exp(self, y, delta_t, current_t):
-        return y * np.exp(self.drift * self.periodic_coeff(current_t) * delta_t)
+    def _decay(self, step_t, step_dt, d):
+        """NJODE/stock_model.py:353-354: y exp(drift c(t) s)"""
+        return np.repeat((self.drift * self._coeff(step_t) * step_dt)[:, None], d, axis=1), np.zeros(d)
 
 
 class OrnsteinUhlenbeck(StockModel):
@@ -294,9 +307,9 @@ class OrnsteinUhlenbeck(StockModel):
         self.mean = mean
         self.speed = speed
 
-    def next_cond_exp(self, y, delta_t, current_t):
-        exp_delta = np.exp(-self.speed * self.periodic_coeff(current_t) * delta_t)
-        return y * exp_delta + self.mean * (1 - exp_delta)
+    def _decay(self, step_t, step_dt, d):
+        """NJODE/stock_model.py:393-395: mean reversion, y e + mean (1 - e) with e = exp(-speed c(t) s)"""
+        return np.repeat((-self.speed * self._coeff(step_t) * step_dt)[:, None], d, axis=1), np.full(d, float(self.mean))
 
 
 class Combined(StockModel):
@@ -308,29 +321,22 @@ class Combined(StockModel):
 
     def compute_cond_exp(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
                          return_path=True, get_loss=False, weight=0.5, **kwargs):
-        stockmodel = STOCK_MODELS[self.stock_model_names[0]](**self.hyperparam_dicts[0])
-        T = self.hyperparam_dicts[0]['maturity']
-        loss, path_t, path_y = stockmodel.compute_cond_exp(
-            times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, return_path=True,
-            get_loss=get_loss, weight=weight)
-        for i in range(1, len(self.stock_model_names)):
-            start_X = path_y[-1, :, :]
-            start_time = path_t[-1]
-            T += self.hyperparam_dicts[i]['maturity']
-            stockmodel = STOCK_MODELS[self.stock_model_names[i]](**self.hyperparam_dicts[i])
-            _loss, _path_t, _path_y = stockmodel.compute_cond_exp(
-                times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, return_path=True,
-                get_loss=get_loss, weight=weight, start_time=start_time)
-            loss += _loss
-            path_t = np.concatenate([path_t, _path_t])
-            path_y = np.concatenate([path_y, _path_y], axis=0)
+        """NJODE/stock_model.py:426-460: one regime after the other; regime i covers (end of regime i-1, + its own
+        maturity], starts from the last conditional expectation of the previous regime and only looks at the observation
+        times after its start (``start_time``)."""
+        loss, horizon, ts, ys = 0, 0., [], []
+        for name, hp in zip(self.stock_model_names, self.hyperparam_dicts):
+            regime = STOCK_MODELS[name](**hp)
+            horizon += hp['maturity']
+            part = regime.compute_cond_exp(
+                times, time_ptr, X, obs_idx, delta_t, horizon, ys[-1][-1] if ys else start_X, n_obs_ot,
+                return_path=True, get_loss=get_loss, weight=weight, start_time=ts[-1][-1] if ts else None)
+            loss += part[0]
+            ts.append(part[1])
+            ys.append(part[2])
         if return_path:
-            return loss, np.array(path_t), np.array(path_y)
+            return loss, np.concatenate(ts), np.concatenate(ys, axis=0)
         return loss
-
-    def get_optimal_loss(self, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot, weight=0.5):
-        return self.compute_cond_exp(times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
-                                     return_path=False, get_loss=True, weight=weight)
 
 
 STOCK_MODELS = {                           # NJODE/stock_model.py:486-495

@@ -33,6 +33,17 @@ _PHILOX_W0 = np.uint32(0x9E3779B9)
 _PHILOX_W1 = np.uint32(0xBB67AE85)
 
 
+# tanh of the restated computation.  ``torch.tanh`` = the reference.  tests/parity_util.py swaps in ``tanh_kernel_formula``
+# (fp32 evaluation only) to MEASURE how much fp32 noise a tanh of the kernels' accuracy class adds to each output.
+TANH = torch.tanh
+
+
+def tanh_kernel_formula(x):
+    """1 - 2 / (2^(2 x log2 e) + 1), every operation rounded to the dtype of x: the formula of nj_tanh
+    (njode_b200/csrc/njode_hash.cuh); CUDA's own tanhf uses the same expression for |x| > 0.55"""
+    return 1 - 2 / (torch.exp2(x * 2.8853900817779268) + 1)
+
+
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
     """Philox-4x32-10 on numpy uint32 arrays (Salmon et al. 2011).  Returns 4 uint32 arrays."""
     c0 = np.asarray(c0, dtype=np.uint32).copy()
@@ -108,7 +119,7 @@ def jump_event_id(i, which):
 # ----------------------------------------------------------------------------------------------
 def _act(name):
     # NJODE/models.py:134-137 (nonlinears)
-    return {"tanh": torch.tanh, "relu": torch.relu}[name]
+    return {"tanh": lambda v: TANH(v), "relu": torch.relu}[name]
 
 
 def linear_indices(nn_desc):
@@ -139,9 +150,9 @@ def ffnn(x, sd, prefix, nn_desc, bias, residual, in_size, out_size, mask=None, d
     """FFNN.forward (NJODE/models.py:261-276) incl. the residual cases set up in
     NJODE/models.py:240-259."""
     if mask is not None:
-        out = mlp(torch.cat((torch.tanh(x), mask), 1), sd, prefix, nn_desc, bias, dropout)
+        out = mlp(torch.cat((TANH(x), mask), 1), sd, prefix, nn_desc, bias, dropout)
     else:
-        out = mlp(torch.tanh(x), sd, prefix, nn_desc, bias, dropout)
+        out = mlp(TANH(x), sd, prefix, nn_desc, bias, dropout)
     if not residual:
         return out
     if in_size <= out_size:
@@ -165,7 +176,7 @@ def gru_cell(x, h, sd, prefix, bias):
     h_r, h_z, h_n = gh.chunk(3, dim=1)
     r = torch.sigmoid(i_r + h_r)
     z = torch.sigmoid(i_z + h_z)
-    n = torch.tanh(i_n + r * h_n)
+    n = TANH(i_n + r * h_n)
     return (1 - z) * n + z * h
 
 
@@ -248,7 +259,7 @@ def forward(cfg, sd, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
 
     def ode_f(x, h, tau, tdiff, event):
         # ODEFunc.forward (NJODE/models.py:188-199)
-        parts = [torch.tanh(x), torch.tanh(h), tau, tdiff]
+        parts = [TANH(x), TANH(h), tau, tdiff]
         if cfg.input_current_t:
             parts.append(tau + tdiff)
         return mlp(torch.cat(parts, dim=1), sd, "ode_f.f", cfg.ode_nn, cfg.bias,
@@ -298,7 +309,7 @@ def forward(cfg, sd, times, time_ptr, X, obs_idx, delta_t, T, start_X, n_obs_ot,
         Y_bj = ro(h, jump_event_id(i, 0), path_ids)              # NJODE/models.py:459
         temp = h.clone()                                           # NJODE/models.py:463-470
         if cfg.use_rnn:                                            # NJODE/models.py:460-461, 213-217
-            temp[i_obs] = gru_cell(torch.tanh(X_obs), torch.tanh(h[i_obs]), sd, "obs_c.gru_d", cfg.bias)
+            temp[i_obs] = gru_cell(TANH(X_obs), TANH(h[i_obs]), sd, "obs_c.gru_d", cfg.bias)
         elif cfg.masked:
             X_imp = X_obs * M_obs + (torch.ones_like(M_obs) - M_obs) * Y_bj[i_obs]
             temp[i_obs] = enc(X_imp, M_obs, jump_event_id(i, 1), rows)

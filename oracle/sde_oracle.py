@@ -39,7 +39,8 @@ def philox_normals(seed, path_ids, nb_steps, dim):
 
 def philox_mask(seed, path_ids, nb_steps, obs_perc):
     """observed int32 [n_paths, nb_steps+1]: column k uses word (k & 3) of Philox(counter = (path lo,
-    path hi, k >> 2, 0xFFFFFFFF)); column 0 forced to 1 (NJODE/data_utils.py:79-80)."""
+    path hi, k >> 2, 0xFFFFFFFF)); column 0 is drawn like every other column and never used as an
+    observation (NJODE/data_utils.py:79-81, 292-307)."""
     path_ids = np.asarray(path_ids, dtype=np.uint64)
     lo = (path_ids & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
     hi = (path_ids >> np.uint64(32)).astype(np.uint32)[:, None]
@@ -48,7 +49,6 @@ def philox_mask(seed, path_ids, nb_steps, obs_perc):
     w = philox4x32_10(lo, hi, k4, np.uint32(STREAM_MASK), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     u = np.stack(w, axis=-1).reshape(len(path_ids), -1)[:, :n1].astype(np.float64) * (1.0 / 4294967296.0)
     obs = (u < obs_perc).astype(np.int32)
-    obs[:, 0] = 1
     return obs
 
 

@@ -30,3 +30,22 @@ def runner():
         from njode_b200 import _ext
         _runner = _ext.Runner(_ext.Lib(build()), torch.device("cpu"))
     return _runner
+
+
+_saved = []
+
+
+def install():
+    """route njode_b200 to the host simulation: replaces ``_ext.cuda_runner`` (the one place the product obtains its
+    runner) for the duration of a test.  The product has no such switch of its own."""
+    from njode_b200 import _ext
+    _saved.append(_ext.cuda_runner)
+    r = runner()
+    _ext.cuda_runner = lambda device: r
+
+
+def uninstall():
+    from njode_b200 import _ext
+    if _saved:
+        _ext.cuda_runner = _saved[0]
+        del _saved[:]

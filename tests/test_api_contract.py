@@ -12,9 +12,9 @@ from njode_b200 import models
 
 @pytest.fixture(autouse=True)
 def sim_runner():
-    models._TEST_RUNNER = hostsim_util.runner()
+    hostsim_util.install()
     yield
-    models._TEST_RUNNER = None
+    hostsim_util.uninstall()
 
 
 def call(m, b, dt=0.05, T=1.0, **kw):

@@ -21,6 +21,10 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["config"]["workload"] == "bs_demo_200" and d["vs_baseline"] is None and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the reference's own batch (200 paths) on the same 200 paths, all host threads and one thread
+    t = d["target_configs"]["bs_demo_200"]
+    assert t["cpu_baseline"]["sample"].startswith("the workload's batch: 200 paths")
+    assert t["cpu_baseline_1thread"]["cores"] == 1 and t["cpu_baseline_1thread"]["value"] > 0
 
 
 def test_reference_arm_is_silent_on_other_ranks():

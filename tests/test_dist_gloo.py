@@ -32,7 +32,7 @@ def _worker(rank, world, port, dropout, q):
     import hostsim_util
     from njode_b200 import models
     from njode_b200 import dist as njdist
-    models._TEST_RUNNER = hostsim_util.runner()
+    hostsim_util.install()
     cfg = cases.demo_cfg(dropout_rate=dropout, input_size=2, output_size=2)
     batch = cases.grid_batch(37, 2, 20, 0.25, seed=3)
     B = 37

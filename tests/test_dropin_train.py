@@ -59,13 +59,13 @@ def test_reference_train_loop_drives_the_b200_models_module(workdir, use_rnn):
     try:
         want = _run(ref_train, workdir, base + 1, use_rnn)
         ref_train.models = b200_models                          # the swap a user makes
-        b200_models._TEST_RUNNER = hostsim_util.runner()        # no GPU here: host simulation of the kernels
+        hostsim_util.install()        # no GPU here: host simulation of the kernels
         got = _run(ref_train, workdir, base + 2, use_rnn)
         # resume from the checkpoint our save_checkpoint wrote, with the reference's loader logic (get_ckpt_model)
         more = _run(ref_train, workdir, base + 2, use_rnn, resume_epochs=4)
     finally:
         ref_train.models = ref_models
-        b200_models._TEST_RUNNER = None
+        hostsim_util.uninstall()
     assert list(got.columns) == list(want.columns) and len(got) == len(want) == 3
     for col in ("train_loss", "eval_loss", "optimal_eval_loss", "evaluation_mean_diff"):
         np.testing.assert_allclose(got[col].values.astype(float), want[col].values.astype(float), rtol=2e-3, err_msg=col)

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 import cases
+import hostsim_util
 import parity_util
 import oracle.njode_oracle as orc
 from njode_b200 import models
@@ -19,7 +20,7 @@ DEV = "cuda:0"
 
 @pytest.fixture(autouse=True)
 def no_test_runner():
-    models._TEST_RUNNER = None
+    hostsim_util.uninstall()
     yield
     os.environ.pop("NJODE_FORCE_TILE", None)
 

@@ -18,9 +18,9 @@ NAMES = cases.golden_names()
 
 @pytest.fixture(autouse=True)
 def sim_runner():
-    models._TEST_RUNNER = hostsim_util.runner()
+    hostsim_util.install()
     yield
-    models._TEST_RUNNER = None
+    hostsim_util.uninstall()
     os.environ.pop("NJODE_FORCE_TILE", None)
     os.environ.pop("NJODE_FORCE_TR", None)
     os.environ.pop("NJODE_NO_SEG", None)
@@ -75,7 +75,7 @@ def test_small_tiles(name, tile):
 
 
 def test_no_cpu_fallback_without_test_runner():
-    models._TEST_RUNNER = None
+    hostsim_util.uninstall()
     cfg, meta, sd, batch, outs = cases.load_case("bs_ckpt1")
     m = parity_util.build_model(cfg, sd, "cpu")
     with pytest.raises(Exception) as ei:
@@ -206,3 +206,34 @@ def test_segment_path_small_ctas_with_dropout():
     cfg = cases.demo_cfg(dropout_rate=0.2)
     batch = cases.grid_batch(40, 1, 25, 0.2, seed=16)
     parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
+
+
+@pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small"])
+def test_backward_without_hT_gradient_skips_the_tail_units(name):
+    """loss.backward() hands the Function ``None`` for the unused hT (set_materialize_grads(False)): the backward then runs
+    on the loss units only (PreparedBatch.bwd_loss) and must give the gradients of the all-units backward fed with zeros"""
+    cfg, meta, sd, batch, outs = cases.load_case(name)
+    grads = []
+    for with_zero_hT in (False, True):
+        m = parity_util.build_model(cfg, sd, "cpu")
+        m.eval()
+        hT, loss = parity_util.call(m, batch, meta, "cpu")
+        obj = loss + (hT * 0.0).sum() if with_zero_hT else loss
+        obj.backward()
+        grads.append({n: p.grad.clone() for n, p in m.named_parameters()})
+    for n in grads[0]:
+        # other tiles -> other fp32 summation orders, nothing else
+        np.testing.assert_allclose(grads[0][n].numpy(), grads[1][n].numpy(), rtol=2e-5, atol=1e-6 * float(grads[1][n].abs().max()))
+
+
+def test_backward_after_a_parameter_update_raises():
+    """the kernels' backward re-reads the parameters: changing them between forward and backward must fail loudly, as
+    autograd's saved-tensor version check does for the reference"""
+    cfg, meta, sd, batch, outs = cases.load_case("bs_ckpt1")
+    m = parity_util.build_model(cfg, sd, "cpu")
+    m.eval()
+    hT, loss = parity_util.call(m, batch, meta, "cpu")
+    with torch.no_grad():
+        next(m.parameters()).mul_(1.5)
+    with pytest.raises(RuntimeError, match="modified"):
+        loss.backward()
