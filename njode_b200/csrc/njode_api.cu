@@ -59,6 +59,31 @@ __global__ void __launch_bounds__(384) nj_seg_bwd_kernel_h(const __grid_constant
     nj_seg_cta_backward<true>(cfg, seg, args, nj_smem, blockIdx.x);
 }
 
+// whole-path units on the warp GEMMs (njode_path.cuh); one kernel per (row groups, rows per group) tile shape
+template <int RG, int TR>
+__global__ void __launch_bounds__(384) nj_path_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
+                                                          const __grid_constant__ NjArgs args) {
+    nj_path_cta_forward<RG, TR>(cfg, path, args, nj_smem);
+}
+template <int RG, int TR>
+__global__ void __launch_bounds__(384) nj_path_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
+                                                          const __grid_constant__ NjArgs args) {
+    nj_path_cta_backward<RG, TR>(cfg, path, args, nj_smem, blockIdx.x);
+}
+typedef void (*nj_path_kern_t)(const NjCfg, const NjPath, const NjArgs);
+static nj_path_kern_t nj_path_pick(int rg, int tr, bool bwd, const char** name) {
+    if (!bwd) {
+        if (rg == 1) { *name = "nj_path_fwd_kernel<1,1>"; return nj_path_fwd_kernel<1, 1>; }
+        if (rg == 2) { *name = "nj_path_fwd_kernel<2,1>"; return nj_path_fwd_kernel<2, 1>; }
+        if (tr == 1) { *name = "nj_path_fwd_kernel<4,1>"; return nj_path_fwd_kernel<4, 1>; }
+        *name = "nj_path_fwd_kernel<4,2>"; return nj_path_fwd_kernel<4, 2>;
+    }
+    if (rg == 1) { *name = "nj_path_bwd_kernel<1,1>"; return nj_path_bwd_kernel<1, 1>; }
+    if (rg == 2) { *name = "nj_path_bwd_kernel<2,1>"; return nj_path_bwd_kernel<2, 1>; }
+    if (tr == 1) { *name = "nj_path_bwd_kernel<4,1>"; return nj_path_bwd_kernel<4, 1>; }
+    *name = "nj_path_bwd_kernel<4,2>"; return nj_path_bwd_kernel<4, 2>;
+}
+
 // flat parameters -> zero-padded image; one block per (net, layer)
 __global__ void nj_pack_kernel(const __grid_constant__ NjCfg cfg, const float* __restrict__ params, float* __restrict__ image) {
     const int n = blockIdx.x / NJODE_MAX_LINEAR, l = blockIdx.x % NJODE_MAX_LINEAR;
@@ -218,6 +243,14 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
         NJ_CUDA(cudaFuncSetAttribute(nj_seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
         nj_seg_fwd_kernel<<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
         nj_set_last_kernel(0, "nj_seg_fwd_kernel");
+    } else if (pl.path.ok) {
+        NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
+        const char* name = "";
+        nj_path_kern_t kern = nj_path_pick(pl.path.rg_f, pl.path.tr_f, false, &name);
+        NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_f_bytes));
+        if (tm) cudaEventRecord(g_ev[0], st);
+        kern<<<pl.path_grid_f, pl.path.nw_f * 32, pl.path_smem_f_bytes, st>>>(pl.fwd, pl.path, a);
+        nj_set_last_kernel(0, name);
     } else {
         nj_set_last_kernel(0, "nj_fwd_kernel");
         auto kern = nj_fwd_kernel;
@@ -262,6 +295,15 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
         kern<<<pl.seg_grid_b, pl.seg.nt_b, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
         nj_set_last_kernel(1, pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : "nj_seg_bwd_kernel");
+    } else if (pl.path.ok) {
+        NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
+        const char* name = "";
+        nj_path_kern_t kern = nj_path_pick(pl.path.rg_b, pl.path.tr_b, true, &name);
+        NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_b_bytes));
+        if (tm) cudaEventRecord(g_ev[2], st);
+        nparts = pl.path_grid_b;
+        kern<<<pl.path_grid_b, pl.path.nt_b, pl.path_smem_b_bytes, st>>>(pl.bwd, pl.path, a);
+        nj_set_last_kernel(1, name);
     } else {
         nj_set_last_kernel(1, "nj_bwd_kernel");
         auto kern = nj_bwd_kernel;

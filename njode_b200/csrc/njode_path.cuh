@@ -1,0 +1,1353 @@
+// njode_path.cuh -- whole-path units (masked model, GRU jump, return_path) on the warp GEMMs of njode_seg.cuh.
+//
+// A whole path carries a true recurrence through its jumps (NJODE/models.py:464-467 masked imputation,
+// 460-461 GRU cell, 483-484 last_X = Y), so it cannot be cut into independent segments.  The generic kernels
+// (njode_core.cuh) march such units CTA-cooperatively with ~12 __syncthreads per Euler step; a PhysioNet-shaped
+// batch (3 700 dependent steps) was bound by barrier latency at 0.2-2.5 % of the FMA roofline.  Here:
+//   * forward: WARP-AUTONOMOUS.  A warp owns R = RG*TR paths from the start encoder to hT: Euler steps, jumps
+//     (readout, imputation, encoder / GRU, readout, loss row), path recording -- only __syncwarp after the
+//     parameter image is in shared memory.  Rows of a warp jump at different steps: the warp marches to the next
+//     step at which any of its rows jumps (kept in a register), runs the jump networks over all R rows and commits
+//     the result for the jumping rows only.
+//   * small batches (the reference's PhysioNet batch is 50): RG < 4 row groups.  The 4/RG lanes that would hold
+//     further rows split the reduction dimension of every layer GEMM instead and meet in two shuffles, so ONE
+//     path per warp (RG = 1) runs a layer in a quarter of the dependent FMA chain.
+//   * backward: a CTA owns P = R*nw rows in lockstep over the batch-global steps, two CTA barriers per Euler step
+//     for the dW phase (thread-owned 4x4 register tiles, helper warps as in njode_seg.cuh).  A jump is reversed
+//     warp-locally by the warps that own jumping rows; its three dW phases (readout, encoder / GRU, readout) run
+//     over the jumping rows only (per-warp row masks).
+// h at every Euler step comes from the forward's h_hist: an O(S*B*H) buffer, 30 MB for the PhysioNet batch -- the
+// segment path (non-masked training) is the one that recomputes from its checkpoints.
+//
+// Same dual-compilation scheme as njode_seg.cuh (-DNJODE_HOST_SIM: sequential host simulation for the CPU tests).
+#pragma once
+#include "njode_seg.cuh"
+
+#define NJP_RS 8                    // row-slot stride of the per-warp scalar arrays (forward: R <= 8)
+enum { NJP_I_PATH = 0, NJP_I_CUR, NJP_I_END, NJP_I_NEXTK, NJP_I_ROW, NJP_I_ACT, NJP_I_RK, NJP_I_COUNT };
+enum { NJP_F_TAU = 0, NJP_F_CA, NJP_F_CB, NJP_F_COUNT };
+#define NJP_NEVER 0x7FFFFFFF
+
+struct NjPath {
+    int ok;
+    int rg_f, tr_f, nw_f;           // forward: a warp owns rg*tr rows, nw warps per CTA
+    int rg_b, tr_b, nw_b, nt_b;     // backward: nw_b row warps of rg*tr rows + helper warps up to nt_b threads
+    int sI, sA, sO, sH, sD, s3, nA;
+    int f_region, f_IN, f_A0, f_A1, f_OUT, f_HS, f_EE, f_LX, f_TX, f_XI, f_YBJ, f_YY, f_MM, f_GI, f_F, f_I;
+    int f_warp0, f_smem_floats, n_tiles_f;
+    int b_IN, b_A, b_G, b_GOUT, b_GZ, b_OUT, b_GH, b_HB, b_EE, b_GE, b_XI, b_LX, b_TX, b_YBJ, b_YY, b_GYBJ, b_GX, b_MM,
+        b_GI, b_GHH, b_F, b_I;
+    int b_smem_floats, P_b, n_tiles_b;
+    int tile_base[NJODE_NUM_NETS][NJODE_MAX_LINEAR];    // first dW tile of (net, layer); order ODE, RO, ENC, GRU_HH, GRU_IH
+    int tiles_total, nt_slots;
+};
+
+// ------------------------------------------------------------------------------------------------
+// warp GEMMs with RG row groups.  lane = (rg, og), rg = lane >> 3, og = lane & 7.  Row of the lane's i-th accumulator
+// row: (rg mod RG) + RG*i; the KSN = 4/RG lanes that share rows split the float4 chunks of the reduction dimension
+// (chunk q belongs to split q mod KSN) and add their partial sums by shuffles (xor 16, then xor 8).  The host
+// simulation has no shuffles: there the split-0 lane evaluates all KSN partial sums itself, in the same order.
+// ------------------------------------------------------------------------------------------------
+template <int RG> struct NjRG {
+    static constexpr int KSN = 4 / RG;
+    NJ_HD static int row(int rg) { return RG == 4 ? rg : (RG == 2 ? (rg & 1) : 0); }
+    NJ_HD static int ks(int rg) { return RG == 4 ? 0 : (RG == 2 ? (rg >> 1) : rg); }
+};
+
+template <int RG>
+NJ_HD float nj_ks_sum(float v) {
+#if !defined(NJODE_HOST_SIM)
+    if (RG <= 2) v += __shfl_xor_sync(0xFFFFFFFFu, v, 16);
+    if (RG == 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+#endif
+    return v;
+}
+// host simulation: combines the KSN partial sums of one accumulator in the order of the device's shuffle tree
+template <int RG>
+NJ_HD float nj_ks_combine(const float* p, int stride) {
+    if (RG == 4) return p[0];
+    if (RG == 2) return p[0] + p[stride];
+    return (p[0] + p[2 * stride]) + (p[stride] + p[3 * stride]);
+}
+
+template <int RG, int TR, int TO>
+NJ_HD void nj_pg_fwd_partial(const NjWL& L, int rr, int og, int ks, float (&acc)[TR][TO]) {
+    constexpr int KSN = 4 / RG;
+#pragma unroll
+    for (int j = 0; j < TO; ++j) {
+        const float b = (L.bias && ks == 0) ? L.bias[L.o_base + og + 8 * j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < TR; ++i) acc[i][j] = b;
+    }
+    nj_sp ap[TR], wp[TO];
+#pragma unroll
+    for (int i = 0; i < TR; ++i) ap[i] = nj_sp_of(L.in + (size_t)(rr + RG * i) * L.in_s);
+#pragma unroll
+    for (int j = 0; j < TO; ++j) wp[j] = nj_sp_of(L.W + (size_t)(L.o_base + og + 8 * j) * L.w_s);
+#pragma unroll 2
+    for (int k4 = ks; k4 < L.K4; k4 += KSN) {
+        nj_f4 a[TR], w[TO];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) a[i] = nj_sp_ld4(NJ_SP_ADD(ap[i], 4 * k4));
+#pragma unroll
+        for (int j = 0; j < TO; ++j) w[j] = nj_sp_ld4(NJ_SP_ADD(wp[j], 4 * k4));
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int j = 0; j < TO; ++j) {
+                acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
+                acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
+                acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
+                acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
+            }
+    }
+}
+
+// out[r][o] = act(b[o] + sum_k in[r][k] W[o][k]) (* dropout); outputs o = o_base + og + 8j
+template <int RG, int TR, int TO>
+NJ_HD void nj_pg_fwd(const NjWL& L, int lane) {
+    const int rg = lane >> 3, og = lane & 7;
+    const int rr = NjRG<RG>::row(rg), ks = NjRG<RG>::ks(rg);
+    float acc[TR][TO];
+#if defined(NJODE_HOST_SIM)
+    if (ks != 0) return;
+    {
+        constexpr int KSN = 4 / RG;
+        float part[KSN][TR][TO];
+        for (int q = 0; q < KSN; ++q) nj_pg_fwd_partial<RG, TR, TO>(L, rr, og, q, part[q]);
+        for (int i = 0; i < TR; ++i)
+            for (int j = 0; j < TO; ++j) acc[i][j] = nj_ks_combine<RG>(&part[0][i][j], TR * TO);
+    }
+#else
+    nj_pg_fwd_partial<RG, TR, TO>(L, rr, og, ks, acc);
+    if (RG < 4) {
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int j = 0; j < TO; ++j) acc[i][j] = nj_ks_sum<RG>(acc[i][j]);
+        if (ks != 0) return;
+    }
+#endif
+    const unsigned obase16 = (unsigned)(L.o_base + og);
+#pragma unroll
+    for (int i = 0; i < TR; ++i) {
+        const int r = rr + RG * i;
+        float* orow = L.out + (size_t)r * L.out_s + L.o_base + og;
+        if (L.drop) {
+            const unsigned lk = nj_layer_key((unsigned)L.rk[r], L.tag);
+#pragma unroll
+            for (int j = 0; j < TO; j += 2) {
+                const unsigned o = obase16 + 8u * j;               // neurons o and o ^ 8 share a hash word (nj_keep)
+                const unsigned word = nj_keep_word(lk, (o & 7u) | ((o >> 4) << 3));
+                const float v0 = nj_act(acc[i][j], L.act) * L.keep_scale;
+                orow[8 * j] = (word & 0xFFFFu) >= L.thr ? v0 : nj_u2f(NJ_DROPPED);
+                if (j + 1 < TO) {
+                    const float v1 = nj_act(acc[i][j + 1], L.act) * L.keep_scale;
+                    orow[8 * j + 8] = (word >> 16) >= L.thr ? v1 : nj_u2f(NJ_DROPPED);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TO; ++j) orow[8 * j] = nj_act(acc[i][j], L.act);
+        }
+    }
+}
+
+template <int RG, int TR>
+NJ_HDN void nj_pg_layer_fwd(NjWL L, int to0, int to_last, int nch) {
+    NJ_ASSUME_SHARED(L.in); NJ_ASSUME_SHARED(L.W); NJ_ASSUME_SHARED(L.out); NJ_ASSUME_SHARED(L.rk);
+    if (L.bias) NJ_ASSUME_SHARED(L.bias);
+    for (int ch = 0; ch < nch; ++ch) {
+        L.o_base = ch * 8 * to0;
+        const int to = ch < nch - 1 ? to0 : to_last;
+        NJ_LANES(lane) {
+            switch (to) {
+                case 1: nj_pg_fwd<RG, TR, 1>(L, lane); break;
+                case 2: nj_pg_fwd<RG, TR, 2>(L, lane); break;
+                case 3: nj_pg_fwd<RG, TR, 3>(L, lane); break;
+                case 4: nj_pg_fwd<RG, TR, 4>(L, lane); break;
+                case 5: nj_pg_fwd<RG, TR, 5>(L, lane); break;
+                case 6: nj_pg_fwd<RG, TR, 6>(L, lane); break;
+                case 7: nj_pg_fwd<RG, TR, 7>(L, lane); break;
+                default: nj_pg_fwd<RG, TR, 8>(L, lane); break;
+            }
+        }
+    }
+}
+
+template <int RG, int TR, int TK>
+NJ_HD void nj_pg_dx_partial(const NjWD& L, int rr, int kq, int ks, float (&acc)[TR][TK][4]) {
+    constexpr int KSN = 4 / RG;
+#pragma unroll
+    for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int jk = 0; jk < TK; ++jk)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][jk][c] = 0.f;
+    nj_sp wp[TK], gp[TR];
+#pragma unroll
+    for (int jk = 0; jk < TK; ++jk) {
+        int kg = L.kg_base + kq + 8 * jk;
+        kg = kg < L.K4in ? kg : L.K4in - 1;          // clamped lanes compute a duplicate, never store
+        wp[jk] = nj_sp_of(L.W + 4 * kg);
+    }
+#pragma unroll
+    for (int i = 0; i < TR; ++i) gp[i] = nj_sp_of(L.g + (size_t)(rr + RG * i) * L.g_s);
+    const int ws = L.w_s;
+    for (int o4 = ks; o4 < L.O4; o4 += KSN) {
+        nj_f4 gv[TR];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) gv[i] = nj_sp_ld4(NJ_SP_ADD(gp[i], 4 * o4));
+#pragma unroll
+        for (int jk = 0; jk < TK; ++jk) {
+            const nj_sp q = NJ_SP_ADD(wp[jk], 4 * o4 * ws);
+            const nj_f4 w0 = nj_sp_ld4(q), w1 = nj_sp_ld4(NJ_SP_ADD(q, ws)), w2 = nj_sp_ld4(NJ_SP_ADD(q, 2 * ws)), w3 = nj_sp_ld4(NJ_SP_ADD(q, 3 * ws));
+#pragma unroll
+            for (int i = 0; i < TR; ++i) {
+                acc[i][jk][0] = fmaf(gv[i].x, w0.x, fmaf(gv[i].y, w1.x, fmaf(gv[i].z, w2.x, fmaf(gv[i].w, w3.x, acc[i][jk][0]))));
+                acc[i][jk][1] = fmaf(gv[i].x, w0.y, fmaf(gv[i].y, w1.y, fmaf(gv[i].z, w2.y, fmaf(gv[i].w, w3.y, acc[i][jk][1]))));
+                acc[i][jk][2] = fmaf(gv[i].x, w0.z, fmaf(gv[i].y, w1.z, fmaf(gv[i].z, w2.z, fmaf(gv[i].w, w3.z, acc[i][jk][2]))));
+                acc[i][jk][3] = fmaf(gv[i].x, w0.w, fmaf(gv[i].y, w1.w, fmaf(gv[i].z, w2.w, fmaf(gv[i].w, w3.w, acc[i][jk][3]))));
+            }
+        }
+    }
+}
+
+// gin[r][k] = (sum_o g[r][o] W[o][k]) * act'(aprev[r][k]) * dropout factor; k-groups (float4) kg = kg_base + kq + 8*jk
+template <int RG, int TR, int TK>
+NJ_HD void nj_pg_dx(const NjWD& L, int lane) {
+    const int rg = lane >> 3, kq = lane & 7;
+    const int rr = NjRG<RG>::row(rg), ks = NjRG<RG>::ks(rg);
+    float acc[TR][TK][4];
+#if defined(NJODE_HOST_SIM)
+    if (ks != 0) return;
+    {
+        constexpr int KSN = 4 / RG;
+        float part[KSN][TR][TK][4];
+        for (int q = 0; q < KSN; ++q) nj_pg_dx_partial<RG, TR, TK>(L, rr, kq, q, part[q]);
+        for (int i = 0; i < TR; ++i)
+            for (int jk = 0; jk < TK; ++jk)
+                for (int c = 0; c < 4; ++c) acc[i][jk][c] = nj_ks_combine<RG>(&part[0][i][jk][c], TR * TK * 4);
+    }
+#else
+    nj_pg_dx_partial<RG, TR, TK>(L, rr, kq, ks, acc);
+    if (RG < 4) {
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int jk = 0; jk < TK; ++jk)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][jk][c] = nj_ks_sum<RG>(acc[i][jk][c]);
+        if (ks != 0) return;
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < TR; ++i) {
+        const int r = rr + RG * i;
+#pragma unroll
+        for (int jk = 0; jk < TK; ++jk) {
+            const int kg = L.kg_base + kq + 8 * jk;
+            if (kg >= L.K4in) continue;
+            float v[4] = {acc[i][jk][0], acc[i][jk][1], acc[i][jk][2], acc[i][jk][3]};
+            if (L.aprev) {
+                const nj_f4 av = nj_sp_ld4(nj_sp_of(L.aprev + (size_t)r * L.a_s + 4 * kg));
+                const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float a = a4[c];
+                    if (L.drop) {
+                        if (nj_f2u(a) == NJ_DROPPED) v[c] = 0.f;
+                        else { a *= L.one_minus_p; v[c] *= L.keep_scale; }
+                    }
+                    if (L.act_prev == NJODE_ACT_TANH) v[c] *= (1.f - a * a);
+                    else if (L.act_prev == NJODE_ACT_RELU) v[c] = a > 0.f ? v[c] : 0.f;
+                }
+            }
+            nj_f4 o; o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3];
+            nj_st4(L.gin + (size_t)r * L.gin_s + 4 * kg, o);
+        }
+    }
+}
+
+template <int RG, int TR>
+NJ_HDN void nj_pg_layer_dx(NjWD D) {
+    NJ_ASSUME_SHARED(D.g); NJ_ASSUME_SHARED(D.W); NJ_ASSUME_SHARED(D.gin);
+    if (D.aprev) NJ_ASSUME_SHARED(D.aprev);
+    for (int kb = 0; kb < D.K4in; kb += 16) {
+        D.kg_base = kb;
+        const bool two = (D.K4in - kb) > 8;
+        NJ_LANES(lane) {
+            if (two) nj_pg_dx<RG, TR, 2>(D, lane); else nj_pg_dx<RG, TR, 1>(D, lane);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-warp view of the MLP buffers
+// ------------------------------------------------------------------------------------------------
+struct NjPW {
+    const NjCfg* c;
+    const float* wimg;
+    float *IN, *A0, *A1, *OUT, *G0, *GOUT, *GZ;
+    int sI, sA, sO;
+    int a_buf_stride, g_buf_stride;
+    int* RK;
+};
+
+template <int RG, int TR>
+NJ_HD void nj_path_mlp_fwd(const NjPW& w, int netid, bool keep_all, bool skip_last) {
+    const NjCfg& c = *w.c;
+    const NjNet& N = c.net[netid];
+    const float* in = w.IN; int in_s = w.sI;
+    for (int l = 0; l < N.n; ++l) {
+        const bool last = (l == N.n - 1);
+        if (last && skip_last) break;
+        NjWL L;
+        L.in = in; L.in_s = in_s; L.K4 = (N.dim[l] + 3) >> 2;
+        L.W = w.wimg + N.w_img[l]; L.w_s = N.ks[l];
+        L.bias = N.b_src[l] >= 0 ? w.wimg + N.b_img[l] : nullptr;
+        if (last) { L.out = w.OUT; L.out_s = w.sO; }
+        else { L.out = keep_all ? w.A0 + (size_t)l * w.a_buf_stride : ((l & 1) ? w.A1 : w.A0); L.out_s = w.sA; }
+        L.act = last ? NJODE_ACT_NONE : N.act[l];
+        L.drop = (!last) && c.has_drop; L.thr = c.thr; L.keep_scale = c.keep_scale;
+        L.rk = w.RK; L.tag = (unsigned)(netid * 16 + l + 1);
+        L.o_base = 0;
+        nj_pg_layer_fwd<RG, TR>(L, N.to[l], N.tol[l], N.nch[l]);
+        NJ_SYNCWARP();
+        in = L.out; in_s = L.out_s;
+    }
+}
+
+template <int RG, int TR>
+NJ_HD void nj_path_mlp_dx(const NjPW& w, int netid, bool need_in_grad) {
+    const NjCfg& c = *w.c;
+    const NjNet& N = c.net[netid];
+    for (int l = N.n - 1; l >= 0; --l) {
+        if (l == 0 && !need_in_grad) break;
+        NjWD D;
+        if (l == N.n - 1) { D.g = w.GOUT; D.g_s = w.sO; } else { D.g = w.G0 + (size_t)l * w.g_buf_stride; D.g_s = w.sA; }
+        D.O4 = (N.dim[l + 1] + 3) >> 2;
+        D.W = w.wimg + N.w_img[l]; D.w_s = N.ks[l];
+        D.K4in = (N.dim[l] + 3) >> 2;
+        if (l > 0) {
+            D.gin = w.G0 + (size_t)(l - 1) * w.g_buf_stride; D.gin_s = w.sA;
+            D.aprev = w.A0 + (size_t)(l - 1) * w.a_buf_stride; D.a_s = w.sA; D.act_prev = N.act[l - 1];
+        } else {
+            D.gin = w.GZ; D.gin_s = w.sI; D.aprev = nullptr; D.a_s = 0; D.act_prev = NJODE_ACT_NONE;
+        }
+        D.drop = c.has_drop; D.keep_scale = c.keep_scale; D.one_minus_p = c.one_minus_p;
+        D.kg_base = 0;
+        nj_pg_layer_dx<RG, TR>(D);
+        NJ_SYNCWARP();
+    }
+}
+
+NJ_HD unsigned nj_path_jump_key(const NjCfg& c, const NjArgs& a, int p, int jump, unsigned which) {
+    return nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), NJ_EVENT_JUMP_BASE + 3u * (unsigned)jump + which);
+}
+
+// ================================================================================================
+// forward: one warp = R = RG*TR whole paths
+// ================================================================================================
+template <int RG, int TR>
+struct NjPathFwd {
+    static constexpr int R = RG * TR;
+    static constexpr int RS = NJP_RS;
+    const NjCfg& c; const NjPath& s; const NjArgs& a;
+    NjPW w;
+    float *HS, *EE, *LX, *TX, *XI, *YBJ, *YY, *MM, *GI, *F;
+    int* I;
+    int d4, H4, inf4, ein4;
+
+    NJ_HD NjPathFwd(const NjCfg& c_, const NjPath& s_, const NjArgs& a_, float* reg, const float* wimg) : c(c_), s(s_), a(a_) {
+        w.c = &c; w.wimg = wimg;
+        w.IN = reg + s.f_IN; w.A0 = reg + s.f_A0; w.A1 = reg + s.f_A1; w.OUT = reg + s.f_OUT;
+        w.G0 = w.GOUT = w.GZ = nullptr; w.a_buf_stride = 0; w.g_buf_stride = 0;
+        w.sI = s.sI; w.sA = s.sA; w.sO = s.sO;
+        HS = reg + s.f_HS; EE = reg + s.f_EE; LX = reg + s.f_LX; TX = reg + s.f_TX; XI = reg + s.f_XI; YBJ = reg + s.f_YBJ; YY = reg + s.f_YY;
+        MM = reg + s.f_MM; GI = reg + s.f_GI; F = reg + s.f_F;
+        I = reinterpret_cast<int*>(reg + s.f_I);
+        w.RK = I + NJP_I_RK * RS;
+        d4 = ((c.d + 3) >> 2) << 2; H4 = ((c.H + 3) >> 2) << 2; inf4 = ((c.inf + 3) >> 2) << 2; ein4 = ((c.enc_in + 3) >> 2) << 2;
+    }
+
+    // cursor -> (next jump row, step count at which it happens)
+    NJ_HD void set_next(int r) {
+        const int cur = I[NJP_I_CUR * RS + r];
+        if (cur < I[NJP_I_END * RS + r]) {
+            const int row = NJ_LDG(a.b.path_rows + cur);
+            I[NJP_I_ROW * RS + r] = row;
+            I[NJP_I_NEXTK * RS + r] = NJ_LDG(a.b.jump_step + NJ_LDG(a.b.row_jump + row));
+        } else { I[NJP_I_ROW * RS + r] = -1; I[NJP_I_NEXTK * RS + r] = NJP_NEVER; }
+    }
+
+    // path_h / path_y record e: h and readout(h) of every row (return_path, NJODE/models.py:440-444, 491-494)
+    NJ_HD void record(int e, unsigned event_key) {
+        const int sI = s.sI, sO = s.sO, sH = s.sH;
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int p = I[NJP_I_PATH * RS + er];
+            for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                const float h = c_ < c.H ? HS[er * sH + c_] : 0.f;
+                if (p >= 0 && c_ < c.H) a.path_h[((size_t)e * a.b.B + p) * c.H + c_] = h;
+                w.IN[(size_t)er * sI + c_] = c_ < c.H ? nj_tanh(h) : 0.f;
+            }
+            if (ec0 == 0) w.RK[er] = p >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), event_key) : 0;
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, false, false);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int p = I[NJP_I_PATH * RS + er];
+            if (p >= 0)
+                for (int c_ = ec0; c_ < c.dout; c_ += LPR) {
+                    float y = w.OUT[er * sO + c_];
+                    if (c.residual) y += nj_resid(HS + er * sH, c.H, c.dout, c_);
+                    a.path_y[((size_t)e * a.b.B + p) * c.dout + c_] = y;
+                }
+        }
+        NJ_SYNCWARP();
+    }
+
+    NJ_HD void euler_step(int k) {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
+        const float tcur = NJ_LDG(a.b.step_t + k), dt = NJ_LDG(a.b.step_dt + k);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int p = I[NJP_I_PATH * RS + er];
+            const float tau = F[NJP_F_TAU * RS + er];
+            float* hh = (p >= 0 && a.h_hist) ? a.h_hist + ((size_t)k * a.b.B + p) * c.H : nullptr;
+            for (int c_ = ec0; c_ < inf4; c_ += LPR) {
+                float v = 0.f;
+                if (c_ < c.d) v = TX[er * sD + c_];
+                else if (c_ < c.d + c.H) {
+                    const float h = HS[er * sH + c_ - c.d];
+                    if (hh) hh[c_ - c.d] = h;
+                    v = nj_tanh(h);
+                } else if (c_ < c.inf) {
+                    if (c_ == c.d + c.H) v = tau;
+                    else if (c_ == c.d + c.H + 1) v = tcur - tau;
+                    else v = tau + (tcur - tau);
+                }
+                w.IN[(size_t)er * sI + c_] = v;
+            }
+            if (ec0 == 0) w.RK[er] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ODE, false, false);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            for (int c_ = ec0; c_ < c.H; c_ += LPR)
+                HS[er * sH + c_] = fmaf(dt, w.OUT[er * sO + c_], HS[er * sH + c_]);
+        }
+        NJ_SYNCWARP();
+    }
+
+    // the jump of NJODE/models.py:449-489 for the rows whose next jump happens after nk Euler steps
+    NJ_HD void jump(int nk) {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD, s3 = s.s3, H = c.H;
+        // (a) Y_bj = readout(h before the jump)
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const bool act = I[NJP_I_NEXTK * RS + er] == nk;
+            const int row = I[NJP_I_ROW * RS + er], p = I[NJP_I_PATH * RS + er];
+            for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                const float h = c_ < H ? HS[er * sH + c_] : 0.f;
+                if (act && c_ < H && a.h_before) a.h_before[(size_t)row * H + c_] = h;
+                w.IN[(size_t)er * sI + c_] = c_ < H ? nj_tanh(h) : 0.f;
+            }
+            if (ec0 == 0) {
+                I[NJP_I_ACT * RS + er] = act ? 1 : 0;
+                w.RK[er] = act ? (int)nj_path_jump_key(c, a, p, NJ_LDG(a.b.row_jump + row), 0u) : 0;
+            }
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, false, false);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            for (int c_ = ec0; c_ < c.dout; c_ += LPR) {
+                float y = w.OUT[er * sO + c_];
+                if (c.residual) y += nj_resid(HS + er * sH, H, c.dout, c_);
+                YBJ[er * sD + c_] = y;
+            }
+        }
+        NJ_SYNCWARP();
+        if (c.use_rnn) {
+            // (b') h[i_obs] = GRUCell(tanh(X_obs), tanh(h[i_obs]))  (NJODE/models.py:202-217, 460-461; gates r, z, n)
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const bool act = I[NJP_I_ACT * RS + er] != 0;
+                const int row = I[NJP_I_ROW * RS + er];
+                for (int c_ = ec0; c_ < d4; c_ += LPR) {
+                    const float x = (act && c_ < c.d) ? NJ_LDG(a.b.X + (size_t)row * c.d + c_) : 0.f;
+                    XI[er * sD + c_] = x;
+                    w.IN[(size_t)er * sI + c_] = c_ < c.d ? nj_tanh(x) : 0.f;
+                }
+            }
+            NJ_SYNCWARP();
+            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_GRU_IH, false, false);
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                for (int c_ = ec0; c_ < 3 * H; c_ += LPR) GI[er * s3 + c_] = w.OUT[er * sO + c_];
+                for (int c_ = ec0; c_ < H4; c_ += LPR) w.IN[(size_t)er * sI + c_] = c_ < H ? nj_tanh(HS[er * sH + c_]) : 0.f;
+            }
+            NJ_SYNCWARP();
+            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_GRU_HH, false, false);
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const bool act = I[NJP_I_ACT * RS + er] != 0;
+                for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                    float e = 0.f;
+                    if (c_ < H) {
+                        const float* gi = GI + er * s3;
+                        const float* o = w.OUT + er * sO;
+                        const float hh = w.IN[(size_t)er * sI + c_];
+                        const float r = nj_sigmoid(gi[c_] + o[c_]);
+                        const float z = nj_sigmoid(gi[H + c_] + o[H + c_]);
+                        const float n = nj_tanh(fmaf(r, o[2 * H + c_], gi[2 * H + c_]));
+                        e = act ? fmaf(z, hh - n, n) : HS[er * sH + c_];
+                    }
+                    if (c_ < H) EE[er * sH + c_] = e;
+                }
+            }
+            NJ_SYNCWARP();
+        } else {
+            // (b) encoder at the (imputed) observation
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const bool act = I[NJP_I_ACT * RS + er] != 0;
+                const int row = I[NJP_I_ROW * RS + er], p = I[NJP_I_PATH * RS + er];
+                for (int c_ = ec0; c_ < ein4; c_ += LPR) {
+                    float v = 0.f;
+                    if (c_ < c.d) {
+                        float x = act ? NJ_LDG(a.b.X + (size_t)row * c.d + c_) : 0.f;
+                        if (c.masked) {
+                            const float m = act ? NJ_LDG(a.b.M + (size_t)row * c.d + c_) : 0.f;
+                            x = x * m + (1.f - m) * YBJ[er * sD + c_];
+                            MM[er * sD + c_] = m;
+                        }
+                        XI[er * sD + c_] = x;
+                        v = nj_tanh(x);
+                    } else if (c.masked && c_ < 2 * c.d) {
+                        v = act ? NJ_LDG(a.b.M + (size_t)row * c.d + c_ - c.d) : 0.f;
+                    }
+                    w.IN[(size_t)er * sI + c_] = v;
+                }
+                if (ec0 == 0) w.RK[er] = act ? (int)nj_path_jump_key(c, a, p, NJ_LDG(a.b.row_jump + row), 1u) : 0;
+            }
+            NJ_SYNCWARP();
+            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, false, false);
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const bool act = I[NJP_I_ACT * RS + er] != 0;
+                for (int c_ = ec0; c_ < H; c_ += LPR) {
+                    float e = w.OUT[er * sO + c_];
+                    if (c.residual) e += nj_resid(XI + er * sD, c.d, H, c_);
+                    EE[er * sH + c_] = act ? e : HS[er * sH + c_];
+                }
+            }
+            NJ_SYNCWARP();
+        }
+        // (c) commit h, Y = readout(h after the jump)
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const bool act = I[NJP_I_ACT * RS + er] != 0;
+            const int row = I[NJP_I_ROW * RS + er], p = I[NJP_I_PATH * RS + er];
+            for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                float e = 0.f;
+                if (c_ < H) { e = EE[er * sH + c_]; HS[er * sH + c_] = e; }
+                w.IN[(size_t)er * sI + c_] = c_ < H ? nj_tanh(e) : 0.f;
+            }
+            if (ec0 == 0) w.RK[er] = act ? (int)nj_path_jump_key(c, a, p, NJ_LDG(a.b.row_jump + row), 2u) : 0;
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, false, false);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const bool act = I[NJP_I_ACT * RS + er] != 0;
+            const int row = I[NJP_I_ROW * RS + er];
+            if (act)
+                for (int c_ = ec0; c_ < c.dout; c_ += LPR) {
+                    float y = w.OUT[er * sO + c_];
+                    if (c.residual) y += nj_resid(HS + er * sH, H, c.dout, c_);
+                    YY[er * sD + c_] = y;
+                    if (a.y_after) a.y_after[(size_t)row * c.dout + c_] = y;
+                    // last_X = Y[i_obs] (masked, differentiable) or X_obs  (NJODE/models.py:481-486)
+                    const float lx = c.masked ? y : NJ_LDG(a.b.X + (size_t)row * c.d + c_);
+                    LX[er * sD + c_] = lx; TX[er * sD + c_] = nj_tanh(lx);
+                }
+        }
+        NJ_SYNCWARP();
+        // (d) loss row, tau, cursor
+        NJ_LANES(lane) {
+            if (lane < R && I[NJP_I_ACT * RS + lane]) {
+                const int r = lane, row = I[NJP_I_ROW * RS + r];
+                if (a.get_loss) {
+                    float sa = 0.f, sb = 0.f;
+                    for (int c_ = 0; c_ < c.dout; ++c_) {
+                        const float x = NJ_LDG(a.b.X + (size_t)row * c.d + c_);
+                        const float m = c.masked ? NJ_LDG(a.b.M + (size_t)row * c.d + c_) : 1.f;
+                        const float y = YY[r * sD + c_], yb = YBJ[r * sD + c_];
+                        const float da = x - y, db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y) : (yb - x);
+                        sa = fmaf(m * da, da, sa); sb = fmaf(m * db, db, sb);
+                    }
+                    const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+                    const float sm = (c.loss_kind == NJODE_LOSS_STANDARD) ? (2.f * c.w * ra + 2.f * (1.f - c.w) * rb)
+                                                                          : (c.w * ra + (1.f - c.w) * rb);
+                    a.row_loss[row] = sm * sm / NJ_LDG(a.b.n_obs_ot + I[NJP_I_PATH * RS + r]);
+                }
+                F[NJP_F_TAU * RS + r] = NJ_LDG(a.b.jump_tau + NJ_LDG(a.b.row_jump + row));
+                I[NJP_I_CUR * RS + r] += 1;
+                set_next(r);
+            }
+        }
+        NJ_SYNCWARP();
+    }
+
+    NJ_HD void run(int u0, int u1) {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
+        const bool rec = a.b.E > 0;
+        NJ_LANES(lane) {
+            if (lane < R) {
+                const int u = u0 + lane;
+                if (u < u1) {
+                    const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                    I[NJP_I_PATH * RS + lane] = dsc[0]; I[NJP_I_CUR * RS + lane] = dsc[3]; I[NJP_I_END * RS + lane] = dsc[4];
+                } else { I[NJP_I_PATH * RS + lane] = -1; I[NJP_I_CUR * RS + lane] = 0; I[NJP_I_END * RS + lane] = 0; }
+                I[NJP_I_ACT * RS + lane] = 0;
+                set_next(lane);
+            }
+        }
+        NJ_SYNCWARP();
+        // ---- start: h = encoder(start_X, mask = 0)  (NJODE/models.py:411-419) ----
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int p = I[NJP_I_PATH * RS + er];
+            for (int c_ = ec0; c_ < ein4; c_ += LPR) {
+                float v = 0.f;
+                if (c_ < c.d) {
+                    const float x = p >= 0 ? NJ_LDG(a.b.start_X + (size_t)p * c.d + c_) : 0.f;
+                    XI[er * sD + c_] = x; LX[er * sD + c_] = x;
+                    v = nj_tanh(x);
+                    TX[er * sD + c_] = v;
+                }
+                w.IN[(size_t)er * sI + c_] = v;
+            }
+            if (ec0 == 0) {
+                F[NJP_F_TAU * RS + er] = 0.f;
+                w.RK[er] = p >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), NJ_EVENT_INIT) : 0;
+            }
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, false, false);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            for (int c_ = ec0; c_ < c.H; c_ += LPR) {
+                float e = w.OUT[er * sO + c_];
+                if (c.residual) e += nj_resid(XI + er * sD, c.d, c.H, c_);
+                HS[er * sH + c_] = e;
+            }
+        }
+        NJ_SYNCWARP();
+        if (rec) record(0, NJ_EVENT_INIT);
+        const int S = a.b.S, K = a.b.K;
+        int k = 0, gi = 0;
+        for (;;) {
+            int nk = NJP_NEVER;
+            if (rec) { if (gi < K) nk = NJ_LDG(a.b.jump_step + gi); }
+            else for (int r = 0; r < R; ++r) nk = I[NJP_I_NEXTK * RS + r] < nk ? I[NJP_I_NEXTK * RS + r] : nk;
+            const int kend = nk < S ? nk : S;
+            for (; k < kend; ++k) {
+                euler_step(k);
+                if (rec) record(NJ_LDG(a.b.step_event + k), NJ_EVENT_PATH_RO_BASE + (unsigned)k);
+            }
+            if (nk > S) break;
+            bool any = false;
+            for (int r = 0; r < R; ++r) any |= (I[NJP_I_NEXTK * RS + r] == nk);
+            if (any) jump(nk);
+            if (rec) { record(NJ_LDG(a.b.jump_event + gi), NJ_EVENT_JUMP_BASE + 3u * (unsigned)gi + 2u); ++gi; }
+        }
+        // ---- hT ----
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int p = I[NJP_I_PATH * RS + er];
+            if (p >= 0)
+                for (int c_ = ec0; c_ < c.H; c_ += LPR) a.hT[(size_t)p * c.H + c_] = HS[er * sH + c_];
+        }
+        NJ_SYNCWARP();
+    }
+};
+
+template <int RG, int TR>
+NJ_HD void nj_path_cta_forward(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem) {
+    float* simg = smem;
+    nj_stage_image(simg, a.image, c.img_floats, s.nw_f * 32);
+    nj_zero(smem + s.f_warp0, s.nw_f * s.f_region, s.nw_f * 32);
+    NJ_SYNC();
+    constexpr int R = RG * TR;
+    NJ_WARPS(wp, s.nw_f) {
+        float* reg = smem + s.f_warp0 + (size_t)wp * s.f_region;
+        int* slot = reinterpret_cast<int*>(reg + s.f_I) + NJP_I_COUNT * NJP_RS;
+        for (;;) {
+            NJ_LANES(lane) { if (lane == 0) *slot = nj_atomic_inc(a.counter); }
+            NJ_SYNCWARP();
+            const int wt = *slot;
+            NJ_SYNCWARP();
+            if (wt >= s.n_tiles_f) break;
+            const int ub = wt * R, ue = ub + R < a.b.n_units ? ub + R : a.b.n_units;
+            NjPathFwd<RG, TR> f(c, s, a, reg, simg);
+            f.run(ub, ue);
+        }
+    }
+}
+
+// ================================================================================================
+// backward: one CTA = P rows (nw_b row warps of R rows + dW helper warps), lockstep over the batch-global steps
+// ================================================================================================
+enum { NJB_I_PATH = 0, NJB_I_CUR, NJB_I_C0, NJB_I_PREVK, NJB_I_ROW, NJB_I_ACT, NJB_I_RK, NJB_I_COUNT };
+
+struct NjPathB {                    // CTA-level views
+    float *IN, *A, *G, *GOUT, *GZ, *OUT, *GH, *HB, *EE, *GE, *XI, *LX, *TX, *YBJ, *YY, *GYBJ, *GX, *MM, *GI, *GHH, *F;
+    int* I;
+    int* MSK;                       // [nw_b] bit i: row i of the warp takes part in the current jump
+};
+
+NJ_HD void nj_pathb_bind(NjPathB& t, const NjPath& s, float* smem) {
+    t.IN = smem + s.b_IN; t.A = smem + s.b_A; t.G = smem + s.b_G; t.GOUT = smem + s.b_GOUT; t.GZ = smem + s.b_GZ;
+    t.OUT = smem + s.b_OUT; t.GH = smem + s.b_GH; t.HB = smem + s.b_HB; t.EE = smem + s.b_EE; t.GE = smem + s.b_GE;
+    t.XI = smem + s.b_XI; t.LX = smem + s.b_LX; t.TX = smem + s.b_TX; t.YBJ = smem + s.b_YBJ; t.YY = smem + s.b_YY;
+    t.GYBJ = smem + s.b_GYBJ; t.GX = smem + s.b_GX; t.MM = smem + s.b_MM; t.GI = smem + s.b_GI; t.GHH = smem + s.b_GHH;
+    t.F = smem + s.b_F; t.I = reinterpret_cast<int*>(smem + s.b_I);
+    t.MSK = t.I + NJB_I_COUNT * s.P_b + 4;
+}
+
+// (net, layer, og, kg) of dW tile T; false when T belongs to another network
+NJ_HD bool nj_path_tile_decode(const NjCfg& c, const NjPath& s, int netid, int T, int& l, int& og, int& kg) {
+    const NjNet& N = c.net[netid];
+    if (N.n == 0 || T < s.tile_base[netid][0]) return false;
+    l = 0;
+    for (int ll = N.n - 1; ll > 0; --ll) if (T >= s.tile_base[netid][ll]) { l = ll; break; }
+    const int K4 = (N.dim[l] + 3) >> 2, O4 = (N.dim[l + 1] + 3) >> 2;
+    const int tl = T - s.tile_base[netid][l];
+    if (tl >= K4 * O4) return false;
+    kg = tl % K4; og = tl / K4;
+    return true;
+}
+
+// q[0..15] += sum_r g[r][4og..] (x) a[r][4kg..], q[16..19] += sum_r g[r][4og..]; rows = all Pt rows (msk == nullptr) or
+// the rows flagged in the per-warp masks, in ascending order (deterministic)
+NJ_HD void nj_path_dw_rows(const NjCfg& c, const NjPath& s, const NjPathB& t, int netid, int l, int og, int kg, int Pt,
+                           const int* msk, int R, float* q) {
+    const NjNet& N = c.net[netid];
+    const int P = s.P_b;
+    const float* g; int g_s;
+    if (l == N.n - 1) { g = t.GOUT; g_s = s.sO; } else { g = t.G + (size_t)l * P * s.sA; g_s = s.sA; }
+    const float* av; int a_s;
+    if (l == 0) { av = t.IN; a_s = s.sI; } else { av = t.A + (size_t)(l - 1) * P * s.sA; a_s = s.sA; }
+    nj_sp gq = nj_sp_of(g + 4 * og), aq = nj_sp_of(av + 4 * kg);
+    float r00 = q[0], r01 = q[1], r02 = q[2], r03 = q[3], r10 = q[4], r11 = q[5], r12 = q[6], r13 = q[7];
+    float r20 = q[8], r21 = q[9], r22 = q[10], r23 = q[11], r30 = q[12], r31 = q[13], r32 = q[14], r33 = q[15];
+    float b0 = q[16], b1 = q[17], b2 = q[18], b3 = q[19];
+#define NJP_DW_ROW(GP, AP)                                                                                          \
+    {                                                                                                               \
+        const nj_f4 gv = nj_sp_ld4(GP);                                                                             \
+        const nj_f4 x = nj_sp_ld4(AP);                                                                              \
+        r00 = fmaf(gv.x, x.x, r00); r01 = fmaf(gv.x, x.y, r01); r02 = fmaf(gv.x, x.z, r02); r03 = fmaf(gv.x, x.w, r03); \
+        r10 = fmaf(gv.y, x.x, r10); r11 = fmaf(gv.y, x.y, r11); r12 = fmaf(gv.y, x.z, r12); r13 = fmaf(gv.y, x.w, r13); \
+        r20 = fmaf(gv.z, x.x, r20); r21 = fmaf(gv.z, x.y, r21); r22 = fmaf(gv.z, x.z, r22); r23 = fmaf(gv.z, x.w, r23); \
+        r30 = fmaf(gv.w, x.x, r30); r31 = fmaf(gv.w, x.y, r31); r32 = fmaf(gv.w, x.z, r32); r33 = fmaf(gv.w, x.w, r33); \
+        b0 += gv.x; b1 += gv.y; b2 += gv.z; b3 += gv.w;                                                             \
+    }
+    if (!msk) {
+#pragma unroll 4
+        for (int r = 0; r < Pt; ++r) {
+            NJP_DW_ROW(gq, aq);
+            gq = NJ_SP_ADD(gq, g_s); aq = NJ_SP_ADD(aq, a_s);
+        }
+    } else {
+        for (int wq = 0, r0 = 0; r0 < Pt; ++wq, r0 += R) {
+            int m = msk[wq];
+            for (int i = 0; m; ++i, m >>= 1)
+                if (m & 1) NJP_DW_ROW(NJ_SP_ADD(gq, (r0 + i) * g_s), NJ_SP_ADD(aq, (r0 + i) * a_s));
+        }
+    }
+#undef NJP_DW_ROW
+    q[0] = r00; q[1] = r01; q[2] = r02; q[3] = r03; q[4] = r10; q[5] = r11; q[6] = r12; q[7] = r13;
+    q[8] = r20; q[9] = r21; q[10] = r22; q[11] = r23; q[12] = r30; q[13] = r31; q[14] = r32; q[15] = r33;
+    q[16] = b0; q[17] = b1; q[18] = b2; q[19] = b3;
+}
+
+// dW phase of one network: thread-owned tiles, the first NJ_SEG_NT_MAX * nt of them in registers for the whole launch,
+// the others accumulated from zero and added into this CTA's partial image (L2 resident) right away
+NJ_HD void nj_path_dw(const NjCfg& c, const NjPath& s, const NjPathB& t, int netid, float* acc, float* gpart,
+                      int tid, int nt, int Pt, const int* msk, int R) {
+#pragma unroll
+    for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
+        if (slot >= s.nt_slots) break;
+        int l, og, kg;
+        if (!nj_path_tile_decode(c, s, netid, slot * nt + tid, l, og, kg)) continue;
+        nj_path_dw_rows(c, s, t, netid, l, og, kg, Pt, msk, R, acc + slot * 20);
+    }
+    for (int T = NJ_SEG_NT_MAX * nt + tid; T < s.tiles_total; T += nt) {
+        int l, og, kg;
+        if (!nj_path_tile_decode(c, s, netid, T, l, og, kg)) continue;
+        float q[20];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) q[i] = 0.f;
+        nj_path_dw_rows(c, s, t, netid, l, og, kg, Pt, msk, R, q);
+        nj_seg_tile_store(c, netid, l, og, kg, q, gpart, true);
+    }
+}
+
+NJ_HD void nj_path_dw_flush(const NjCfg& c, const NjPath& s, const float* acc, float* gpart, int tid, int nt) {
+#pragma unroll
+    for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
+        if (slot >= s.nt_slots) break;
+        const int T = slot * nt + tid;
+        if (T >= s.tiles_total) continue;
+        for (int netid = 0; netid < NJODE_NUM_NETS; ++netid) {
+            int l, og, kg;
+            if (nj_path_tile_decode(c, s, netid, T, l, og, kg)) { nj_seg_tile_store(c, netid, l, og, kg, acc + slot * 20, gpart, false); break; }
+        }
+    }
+}
+
+// CTA-wide: the latest step count at which a row of the tile still has a jump to reverse (-1: none)
+NJ_HD int nj_pathb_next(const NjPathB& t, int P, int Pt) {
+    int m = -1;
+    for (int r = 0; r < Pt; ++r) m = t.I[NJB_I_PREVK * P + r] > m ? t.I[NJB_I_PREVK * P + r] : m;
+    return m;
+}
+
+template <int RG, int TR>
+struct NjPathBwd {
+    static constexpr int R = RG * TR;
+    const NjCfg& c; const NjPath& s; const NjArgs& a; const NjPathB& t;
+    const float* simg;
+    int P, d4, H4, inf4, ein4, do4, wa;
+
+    NJ_HD NjPathBwd(const NjCfg& c_, const NjPath& s_, const NjArgs& a_, const NjPathB& t_, const float* simg_)
+        : c(c_), s(s_), a(a_), t(t_), simg(simg_) {
+        P = s.P_b;
+        d4 = ((c.d + 3) >> 2) << 2; H4 = ((c.H + 3) >> 2) << 2; inf4 = ((c.inf + 3) >> 2) << 2;
+        ein4 = ((c.enc_in + 3) >> 2) << 2; do4 = ((c.dout + 3) >> 2) << 2;
+        wa = P * s.sA;
+    }
+    NJ_HD NjPW view(int r0) const {
+        NjPW w;
+        w.c = &c; w.wimg = simg;
+        w.IN = t.IN + (size_t)r0 * s.sI; w.A0 = t.A + (size_t)r0 * s.sA; w.A1 = nullptr; w.OUT = t.OUT + (size_t)r0 * s.sO;
+        w.G0 = t.G + (size_t)r0 * s.sA; w.GOUT = t.GOUT + (size_t)r0 * s.sO; w.GZ = t.GZ + (size_t)r0 * s.sI;
+        w.sI = s.sI; w.sA = s.sA; w.sO = s.sO;
+        w.a_buf_stride = wa; w.g_buf_stride = wa; w.RK = t.I + NJB_I_RK * P + r0;
+        return w;
+    }
+    NJ_HD void set_key(int r, bool valid, unsigned ev) const {
+        t.I[NJB_I_RK * P + r] = valid ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(t.I[NJB_I_PATH * P + r] + a.b.path_id_offset), ev) : 0;
+    }
+    // cursor -> (row of the latest jump not yet reversed, its step count)
+    NJ_HD void set_prev(int r) const {
+        const int cur = t.I[NJB_I_CUR * P + r];
+        if (cur > t.I[NJB_I_C0 * P + r]) {
+            const int row = NJ_LDG(a.b.path_rows + cur - 1);
+            t.I[NJB_I_ROW * P + r] = row;
+            t.I[NJB_I_PREVK * P + r] = NJ_LDG(a.b.jump_step + NJ_LDG(a.b.row_jump + row));
+        } else { t.I[NJB_I_ROW * P + r] = -1; t.I[NJB_I_PREVK * P + r] = -1; }
+    }
+    // (last_X, tanh(last_X), tau) valid between the jump of row NJB_I_ROW (or the start) and the next jump
+    NJ_HD void load_state(int r0, int lane) const {
+        NJ_ROWMAP(R);
+        const int r = r0 + er, p = t.I[NJB_I_PATH * P + r], prev = t.I[NJB_I_ROW * P + r];
+        for (int c_ = ec0; c_ < d4; c_ += LPR) {
+            float x = 0.f;
+            if (p >= 0 && c_ < c.d) {
+                if (prev < 0) x = NJ_LDG(a.b.start_X + (size_t)p * c.d + c_);
+                else if (c.masked) x = a.y_after[(size_t)prev * c.dout + c_];
+                else x = NJ_LDG(a.b.X + (size_t)prev * c.d + c_);
+            }
+            t.LX[r * s.sD + c_] = x; t.TX[r * s.sD + c_] = c_ < c.d ? nj_tanh(x) : 0.f;
+        }
+        if (ec0 == 0) t.F[NJP_F_TAU * P + r] = (p >= 0 && prev >= 0) ? NJ_LDG(a.b.jump_tau + NJ_LDG(a.b.row_jump + prev)) : 0.f;
+    }
+
+    // ---- reverse of Euler step k, warp-local part (rows r0 .. r0 + R) ----
+    NJ_HD void step_local(int r0, int k) const {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
+        const NjPW w = view(r0);
+        const float tcur = NJ_LDG(a.b.step_t + k), dt = NJ_LDG(a.b.step_dt + k);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er, p = t.I[NJB_I_PATH * P + r];
+            const float tau = t.F[NJP_F_TAU * P + r];
+            const float* hh = p >= 0 ? a.h_hist + ((size_t)k * a.b.B + p) * c.H : nullptr;
+            for (int c_ = ec0; c_ < inf4; c_ += LPR) {
+                float v = 0.f;
+                if (c_ < c.d) v = t.TX[r * sD + c_];
+                else if (c_ < c.d + c.H) v = nj_tanh(hh ? hh[c_ - c.d] : 0.f);
+                else if (c_ < c.inf) {
+                    if (c_ == c.d + c.H) v = tau;
+                    else if (c_ == c.d + c.H + 1) v = tcur - tau;
+                    else v = tau + (tcur - tau);
+                }
+                t.IN[(size_t)r * sI + c_] = v;
+            }
+            for (int c_ = ec0; c_ < H4; c_ += LPR) t.GOUT[(size_t)r * sO + c_] = c_ < c.H ? dt * t.GH[r * sH + c_] : 0.f;
+            if (ec0 == 0) set_key(r, true, (unsigned)k);
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ODE, true, true);
+        nj_path_mlp_dx<RG, TR>(w, NJODE_NET_ODE, true);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er;
+            if (t.I[NJB_I_PATH * P + r] >= 0) {
+                for (int c_ = ec0; c_ < c.H; c_ += LPR) {
+                    const float th = t.IN[(size_t)r * sI + c.d + c_];
+                    t.GH[r * sH + c_] += t.GZ[(size_t)r * sI + c.d + c_] * (1.f - th * th);
+                }
+                if (c.masked)            // last_X = Y[i_obs] is differentiable (NJODE/models.py:483-484)
+                    for (int c_ = ec0; c_ < c.d; c_ += LPR) {
+                        const float tx = t.IN[(size_t)r * sI + c_];
+                        t.GX[r * sD + c_] += t.GZ[(size_t)r * sI + c_] * (1.f - tx * tx);
+                    }
+            }
+        }
+        NJ_SYNCWARP();
+    }
+
+    // ---- jump reversal, phase 1 (warp-local): recompute Y_bj, E, Y; loss gradients; readout backward at E ----
+    NJ_HD void jump_p1(int r0, int wp, int k) const {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD, s3 = s.s3, H = c.H;
+        const NjPW w = view(r0);
+        int msk = 0;
+        for (int i = 0; i < R; ++i) msk |= (t.I[NJB_I_PREVK * P + r0 + i] == k) ? (1 << i) : 0;
+        NJ_LANES(lane) { if (lane == 0) t.MSK[wp] = msk; }
+        if (!msk) { NJ_SYNCWARP(); return; }
+        const float gl = NJ_LDG(a.grad_loss);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
+            const bool act = (msk >> er) & 1;
+            for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                const float h = (act && c_ < H) ? a.h_before[(size_t)row * H + c_] : 0.f;
+                if (c_ < H) t.HB[r * sH + c_] = h;
+                t.IN[(size_t)r * sI + c_] = c_ < H ? nj_tanh(h) : 0.f;
+            }
+            if (ec0 == 0) {
+                t.I[NJB_I_ACT * P + r] = act ? 1 : 0;
+                set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 0u);
+            }
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, true, false);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er;
+            for (int c_ = ec0; c_ < c.dout; c_ += LPR) {
+                float y = t.OUT[r * sO + c_];
+                if (c.residual) y += nj_resid(t.HB + r * sH, H, c.dout, c_);
+                t.YBJ[r * sD + c_] = y;
+            }
+        }
+        NJ_SYNCWARP();
+        if (c.use_rnn) {
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
+                const bool act = (msk >> er) & 1;
+                for (int c_ = ec0; c_ < d4; c_ += LPR) {
+                    const float x = (act && c_ < c.d) ? NJ_LDG(a.b.X + (size_t)row * c.d + c_) : 0.f;
+                    t.XI[r * sD + c_] = x;
+                    t.IN[(size_t)r * sI + c_] = c_ < c.d ? nj_tanh(x) : 0.f;
+                }
+            }
+            NJ_SYNCWARP();
+            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_GRU_IH, true, false);
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er;
+                for (int c_ = ec0; c_ < 3 * H; c_ += LPR) t.GI[r * s3 + c_] = t.OUT[r * sO + c_];
+                for (int c_ = ec0; c_ < H4; c_ += LPR) t.IN[(size_t)r * sI + c_] = c_ < H ? nj_tanh(t.HB[r * sH + c_]) : 0.f;
+            }
+            NJ_SYNCWARP();
+            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_GRU_HH, true, false);
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
+                const bool act = (msk >> er) & 1;
+                for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                    float e = 0.f;
+                    if (c_ < H) {
+                        float* gi = t.GI + r * s3;
+                        float* gh = t.GHH + r * s3;
+                        const float* o = t.OUT + r * sO;
+                        const float hh = t.IN[(size_t)r * sI + c_];
+                        const float rr_ = nj_sigmoid(gi[c_] + o[c_]);
+                        const float z = nj_sigmoid(gi[H + c_] + o[H + c_]);
+                        const float ghn = o[2 * H + c_];
+                        const float n = nj_tanh(fmaf(rr_, ghn, gi[2 * H + c_]));
+                        gi[c_] = rr_; gi[H + c_] = z; gi[2 * H + c_] = n;
+                        gh[c_] = hh; gh[2 * H + c_] = ghn;
+                        e = fmaf(z, hh - n, n);
+                        t.EE[r * sH + c_] = e;
+                    }
+                    t.IN[(size_t)r * sI + c_] = c_ < H ? nj_tanh(e) : 0.f;
+                }
+                if (ec0 == 0) set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 2u);
+            }
+            NJ_SYNCWARP();
+        } else {
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
+                const bool act = (msk >> er) & 1;
+                for (int c_ = ec0; c_ < ein4; c_ += LPR) {
+                    float v = 0.f;
+                    if (c_ < c.d) {
+                        float x = act ? NJ_LDG(a.b.X + (size_t)row * c.d + c_) : 0.f;
+                        if (c.masked) {
+                            const float m = act ? NJ_LDG(a.b.M + (size_t)row * c.d + c_) : 0.f;
+                            x = x * m + (1.f - m) * t.YBJ[r * sD + c_];
+                            t.MM[r * sD + c_] = m;
+                        }
+                        t.XI[r * sD + c_] = x;
+                        v = nj_tanh(x);
+                    } else if (c.masked && c_ < 2 * c.d) v = act ? NJ_LDG(a.b.M + (size_t)row * c.d + c_ - c.d) : 0.f;
+                    t.IN[(size_t)r * sI + c_] = v;
+                }
+                if (ec0 == 0) set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 1u);
+            }
+            NJ_SYNCWARP();
+            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, true, false);
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
+                const bool act = (msk >> er) & 1;
+                for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                    float e = 0.f;
+                    if (c_ < H) {
+                        e = t.OUT[r * sO + c_];
+                        if (c.residual) e += nj_resid(t.XI + r * sD, c.d, H, c_);
+                        t.EE[r * sH + c_] = e;
+                    }
+                    t.IN[(size_t)r * sI + c_] = c_ < H ? nj_tanh(e) : 0.f;
+                }
+                if (ec0 == 0) set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 2u);
+            }
+            NJ_SYNCWARP();
+        }
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, true, false);
+        // loss derivative (compute_loss / compute_loss_2, NJODE/models.py:71-126)
+        NJ_LANES(lane) {
+            if (lane < R) {
+                const int r = r0 + lane, row = t.I[NJB_I_ROW * P + r];
+                float ca = 0.f, cb = 0.f;
+                if ((msk >> lane) & 1) {
+                    float sa = 0.f, sb = 0.f;
+                    for (int c_ = 0; c_ < c.dout; ++c_) {
+                        float y = t.OUT[r * sO + c_];
+                        if (c.residual) y += nj_resid(t.EE + r * sH, H, c.dout, c_);
+                        t.YY[r * sD + c_] = y;
+                        const float x = NJ_LDG(a.b.X + (size_t)row * c.d + c_), yb = t.YBJ[r * sD + c_];
+                        const float m = c.masked ? NJ_LDG(a.b.M + (size_t)row * c.d + c_) : 1.f;
+                        const float da = x - y, db = (c.loss_kind == NJODE_LOSS_STANDARD) ? (yb - y) : (yb - x);
+                        sa = fmaf(m * da, da, sa); sb = fmaf(m * db, db, sb);
+                    }
+                    const float ra = sqrtf(sa + 1e-10f), rb = sqrtf(sb + 1e-10f);
+                    const float wa_ = (c.loss_kind == NJODE_LOSS_STANDARD) ? 2.f * c.w : c.w;
+                    const float wb_ = (c.loss_kind == NJODE_LOSS_STANDARD) ? 2.f * (1.f - c.w) : (1.f - c.w);
+                    const float sm = wa_ * ra + wb_ * rb;
+                    const float nobs = a.b.n_obs_ot ? NJ_LDG(a.b.n_obs_ot + t.I[NJB_I_PATH * P + r]) : 1.f;
+                    const float cf = a.b.n_obs_ot ? gl * 2.f * sm / (nobs * (float)a.b.batch_size_norm) : 0.f;
+                    ca = cf * wa_ / ra; cb = cf * wb_ / rb;
+                }
+                t.F[NJP_F_CA * P + r] = ca; t.F[NJP_F_CB * P + r] = cb;
+            }
+        }
+        NJ_SYNCWARP();
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
+            const bool act = (msk >> er) & 1;
+            for (int c_ = ec0; c_ < do4; c_ += LPR) {
+                float gy = 0.f, gyb = 0.f;
+                if (c_ < c.dout && act) {
+                    const float x = NJ_LDG(a.b.X + (size_t)row * c.d + c_), y = t.YY[r * sD + c_], yb = t.YBJ[r * sD + c_];
+                    const float m = c.masked ? NJ_LDG(a.b.M + (size_t)row * c.d + c_) : 1.f;
+                    const float ca = t.F[NJP_F_CA * P + r], cb = t.F[NJP_F_CB * P + r];
+                    if (c.loss_kind == NJODE_LOSS_STANDARD) { gy = -ca * m * (x - y) - cb * m * (yb - y); gyb = cb * m * (yb - y); }
+                    else { gy = -ca * m * (x - y); gyb = cb * m * (yb - x); }
+                    if (c.masked) gy += t.GX[r * sD + c_];           // last_X = Y[i_obs]
+                }
+                t.GOUT[(size_t)r * sO + c_] = gy;
+                t.GYBJ[r * sD + c_] = gyb;
+            }
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_dx<RG, TR>(w, NJODE_NET_RO, true);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er;
+            const bool act = (msk >> er) & 1;
+            for (int c_ = ec0; c_ < H; c_ += LPR) {
+                const float th = t.IN[(size_t)r * sI + c_];
+                float ge = t.GZ[(size_t)r * sI + c_] * (1.f - th * th);
+                if (c.residual) ge += nj_resid_bwd(t.GOUT + (size_t)r * sO, H, c.dout, c_);
+                t.GE[r * sH + c_] = act ? ge + t.GH[r * sH + c_] : 0.f;
+            }
+        }
+        NJ_SYNCWARP();
+    }
+
+    // ---- phase 2 (warp-local): encoder (or GRU hidden map) at the observation, backward with g = dL/dE ----
+    NJ_HD void jump_p2(int r0, int wp) const {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD, s3 = s.s3, H = c.H;
+        const int msk = t.MSK[wp];
+        if (!msk) return;
+        const NjPW w = view(r0);
+        if (c.use_rnn) {
+            // backward of h' = (1 - z) n + z tanh(h_old), gates from (gi, gh)
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er;
+                const bool act = (msk >> er) & 1;
+                for (int c_ = ec0; c_ < H4; c_ += LPR) {
+                    if (c_ < H) {
+                        float* gi = t.GI + r * s3;
+                        const float* gh = t.GHH + r * s3;
+                        float* go = t.GOUT + (size_t)r * sO;
+                        const float ge = act ? t.GE[r * sH + c_] : 0.f;
+                        const float rr_ = gi[c_], z = gi[H + c_], n = gi[2 * H + c_], hh = gh[c_], ghn = gh[2 * H + c_];
+                        const float dpn = ge * (1.f - z) * (1.f - n * n);
+                        const float dpr = dpn * ghn * rr_ * (1.f - rr_);
+                        const float dpz = ge * (hh - n) * z * (1.f - z);
+                        go[c_] = dpr; go[H + c_] = dpz; go[2 * H + c_] = dpn * rr_;
+                        gi[c_] = dpr; gi[H + c_] = dpz; gi[2 * H + c_] = dpn;
+                        t.EE[r * sH + c_] = ge * z;
+                        t.IN[(size_t)r * sI + c_] = hh;
+                    } else t.IN[(size_t)r * sI + c_] = 0.f;
+                }
+            }
+            NJ_SYNCWARP();
+            nj_path_mlp_dx<RG, TR>(w, NJODE_NET_GRU_HH, true);
+        } else {
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
+                const bool act = (msk >> er) & 1;
+                for (int c_ = ec0; c_ < ein4; c_ += LPR) {
+                    float v = 0.f;
+                    if (c_ < c.d) v = nj_tanh(t.XI[r * sD + c_]);
+                    else if (c.masked && c_ < 2 * c.d) v = t.MM[r * sD + c_ - c.d];
+                    t.IN[(size_t)r * sI + c_] = v;
+                }
+                for (int c_ = ec0; c_ < H4; c_ += LPR) t.GOUT[(size_t)r * sO + c_] = (c_ < H && act) ? t.GE[r * sH + c_] : 0.f;
+                if (ec0 == 0) set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 1u);
+            }
+            NJ_SYNCWARP();
+            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, true, true);
+            nj_path_mlp_dx<RG, TR>(w, NJODE_NET_ENC, c.masked != 0);
+            if (c.masked) {
+                // imputation X*M + (1 - M)*Y_bj: the gradient wrt the encoder input reaches Y_bj where M = 0
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er;
+                    if ((msk >> er) & 1)
+                        for (int c_ = ec0; c_ < c.d; c_ += LPR) {
+                            const float tx = t.IN[(size_t)r * sI + c_];
+                            float gx = t.GZ[(size_t)r * sI + c_] * (1.f - tx * tx);
+                            if (c.residual) gx += nj_resid_bwd(t.GOUT + (size_t)r * sO, c.d, H, c_);
+                            t.GYBJ[r * sD + c_] += (1.f - t.MM[r * sD + c_]) * gx;
+                        }
+                }
+                NJ_SYNCWARP();
+            }
+        }
+    }
+
+    // ---- GRU only, phase 2b (warp-local): operands of the input map's dW ----
+    NJ_HD void jump_p2b(int r0, int wp) const {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD, s3 = s.s3, H = c.H;
+        const int msk = t.MSK[wp];
+        if (!msk) return;
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er;
+            for (int c_ = ec0; c_ < H; c_ += LPR) {
+                const float hh = t.GHH[r * s3 + c_];
+                t.EE[r * sH + c_] = (t.EE[r * sH + c_] + t.GZ[(size_t)r * sI + c_]) * (1.f - hh * hh);
+            }
+        }
+        NJ_SYNCWARP();
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er;
+            for (int c_ = ec0; c_ < 3 * H; c_ += LPR) t.GOUT[(size_t)r * sO + c_] = t.GI[r * s3 + c_];
+            for (int c_ = ec0; c_ < d4; c_ += LPR) t.IN[(size_t)r * sI + c_] = c_ < c.d ? nj_tanh(t.XI[r * sD + c_]) : 0.f;
+        }
+        NJ_SYNCWARP();
+    }
+
+    // ---- phase 3 (warp-local): readout at h_before, backward with g = dL/dY_bj -> adjoint before the jump; cursor ----
+    NJ_HD void jump_p3(int r0, int wp) const {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD, H = c.H;
+        const int msk = t.MSK[wp];
+        if (!msk) return;
+        const NjPW w = view(r0);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
+            const bool act = (msk >> er) & 1;
+            const int zc = c.use_rnn ? 3 * H : H4;        // clears what the previous phase left in GOUT
+            for (int c_ = ec0; c_ < H4; c_ += LPR) t.IN[(size_t)r * sI + c_] = c_ < H ? nj_tanh(t.HB[r * sH + c_]) : 0.f;
+            for (int c_ = ec0; c_ < zc || c_ < do4; c_ += LPR) t.GOUT[(size_t)r * sO + c_] = (c_ < c.dout && act) ? t.GYBJ[r * sD + c_] : 0.f;
+            if (ec0 == 0) set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 0u);
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, true, true);
+        nj_path_mlp_dx<RG, TR>(w, NJODE_NET_RO, true);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er;
+            if ((msk >> er) & 1) {
+                for (int c_ = ec0; c_ < H; c_ += LPR) {
+                    const float th = t.IN[(size_t)r * sI + c_];
+                    float gh = t.GZ[(size_t)r * sI + c_] * (1.f - th * th);
+                    if (c.residual) gh += nj_resid_bwd(t.GOUT + (size_t)r * sO, H, c.dout, c_);
+                    if (c.use_rnn) gh += t.EE[r * sH + c_];
+                    t.GH[r * sH + c_] = gh;
+                }
+                for (int c_ = ec0; c_ < c.d; c_ += LPR) t.GX[r * sD + c_] = 0.f;
+            }
+        }
+        NJ_SYNCWARP();
+        NJ_LANES(lane) {
+            if (lane < R && ((msk >> lane) & 1)) {
+                t.I[NJB_I_CUR * P + r0 + lane] -= 1;
+                set_prev(r0 + lane);
+            }
+        }
+        NJ_SYNCWARP();
+        NJ_LANES(lane) { load_state(r0, lane); }
+        NJ_SYNCWARP();
+    }
+
+    // ---- start encoder reversed (warp-local) ----
+    NJ_HD void start_local(int r0) const {
+        const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
+        const NjPW w = view(r0);
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int r = r0 + er;
+            const bool valid = t.I[NJB_I_PATH * P + r] >= 0;
+            for (int c_ = ec0; c_ < ein4; c_ += LPR) t.IN[(size_t)r * sI + c_] = c_ < c.d ? t.TX[r * sD + c_] : 0.f;
+            for (int c_ = ec0; c_ < H4; c_ += LPR) t.GOUT[(size_t)r * sO + c_] = (c_ < c.H && valid) ? t.GH[r * sH + c_] : 0.f;
+            if (ec0 == 0) set_key(r, valid, NJ_EVENT_INIT);
+        }
+        NJ_SYNCWARP();
+        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, true, true);
+        nj_path_mlp_dx<RG, TR>(w, NJODE_NET_ENC, false);
+    }
+};
+
+// the barrier protocol of one tile, shared by the row warps and the helper warps:
+//   per reversed jump step: p1 | dW RO | p2 | dW ENC or GRU_HH | [GRU: p2b | dW GRU_IH |] p3 | dW RO |
+//   per reversed Euler step: local | dW ODE |;  start encoder: local | dW ENC |       ("|" = CTA barrier)
+template <int RG, int TR, bool ROWS>
+NJ_HD void nj_path_bwd_tile(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem, const NjPathB& t, float* nj_acc_base,
+                            int cta, int u0, int u1) {
+    constexpr int R = RG * TR;
+    const int P = s.P_b, nt = s.nt_b, Pt = R * s.nw_b;
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    const NjPathBwd<RG, TR> B(c, s, a, t, smem);
+    if (ROWS) {
+        NJ_THREADS(tid, nt) {
+            if (tid < Pt) {
+                const int u = u0 + tid;
+                if (u < u1) {
+                    const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                    t.I[NJB_I_PATH * P + tid] = dsc[0]; t.I[NJB_I_C0 * P + tid] = dsc[3]; t.I[NJB_I_CUR * P + tid] = dsc[4];
+                } else { t.I[NJB_I_PATH * P + tid] = -1; t.I[NJB_I_C0 * P + tid] = 0; t.I[NJB_I_CUR * P + tid] = 0; }
+                t.I[NJB_I_ACT * P + tid] = 0;
+                B.set_prev(tid);
+            }
+        }
+    }
+    NJ_SYNC();
+    if (ROWS) {
+        NJ_WARPS(wp, s.nw_b) {
+            const int r0 = wp * R;
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er, p = t.I[NJB_I_PATH * P + r];
+                const float* ght = (p >= 0 && a.grad_hT) ? a.grad_hT + (size_t)p * c.H : nullptr;
+                for (int c_ = ec0; c_ < c.H; c_ += LPR) t.GH[r * s.sH + c_] = ght ? NJ_LDG(ght + c_) : 0.f;
+                for (int c_ = ec0; c_ < c.d; c_ += LPR) t.GX[r * s.sD + c_] = 0.f;
+                B.load_state(r0, lane);
+            }
+            NJ_SYNCWARP();
+        }
+    }
+    int nk = nj_pathb_next(t, P, Pt);
+    for (int k = a.b.S; ; --k) {
+        if (nk == k) {
+            if (ROWS) { NJ_WARPS(wp, s.nw_b) { B.jump_p1(wp * R, wp, k); } }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_path_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), gpart, tid, nt, Pt, t.MSK, R); }
+            NJ_SYNC();
+            if (ROWS) { NJ_WARPS(wp, s.nw_b) { B.jump_p2(wp * R, wp); } }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_path_dw(c, s, t, c.use_rnn ? NJODE_NET_GRU_HH : NJODE_NET_ENC, NJ_ACC(tid), gpart, tid, nt, Pt, t.MSK, R); }
+            NJ_SYNC();
+            if (c.use_rnn) {
+                if (ROWS) { NJ_WARPS(wp, s.nw_b) { B.jump_p2b(wp * R, wp); } }
+                NJ_SYNC();
+                NJ_THREADS(tid, nt) { nj_path_dw(c, s, t, NJODE_NET_GRU_IH, NJ_ACC(tid), gpart, tid, nt, Pt, t.MSK, R); }
+                NJ_SYNC();
+            }
+            if (ROWS) { NJ_WARPS(wp, s.nw_b) { B.jump_p3(wp * R, wp); } }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_path_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), gpart, tid, nt, Pt, t.MSK, R); }
+            NJ_SYNC();
+            nk = nj_pathb_next(t, P, Pt);
+        }
+        if (k == 0) break;
+        if (ROWS) { NJ_WARPS(wp, s.nw_b) { B.step_local(wp * R, k - 1); } }
+        NJ_SYNC();
+        NJ_THREADS(tid, nt) { nj_path_dw(c, s, t, NJODE_NET_ODE, NJ_ACC(tid), gpart, tid, nt, Pt, nullptr, R); }
+        NJ_SYNC();
+    }
+    if (ROWS) { NJ_WARPS(wp, s.nw_b) { B.start_local(wp * R); } }
+    NJ_SYNC();
+    NJ_THREADS(tid, nt) { nj_path_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), gpart, tid, nt, Pt, nullptr, R); }
+    NJ_SYNC();
+}
+
+template <int RG, int TR>
+NJ_HD void nj_path_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem, int cta) {
+    const int nt = s.nt_b;
+    constexpr int R = RG * TR;
+    nj_stage_image(smem, a.image, c.img_floats, nt);
+    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
+    nj_zero(a.partials + (size_t)cta * c.img_floats, c.img_floats, nt);
+    NJ_SYNC();
+    NjPathB t;
+    nj_pathb_bind(t, s, smem);
+    NJ_ACC_DECL(nt);
+    int* ctl = t.I + NJB_I_COUNT * s.P_b;
+    for (;;) {
+        NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int tile = ctl[0];
+        NJ_SYNC();
+        if (tile >= s.n_tiles_b) break;
+        const int rows = R * s.nw_b;
+        const int ub = tile * rows, ue = ub + rows < a.b.n_units ? ub + rows : a.b.n_units;
+#if !defined(NJODE_HOST_SIM)
+        if ((int)(threadIdx.x >> 5) >= s.nw_b) { nj_path_bwd_tile<RG, TR, false>(c, s, a, smem, t, nj_acc_base, cta, ub, ue); continue; }
+#endif
+        nj_path_bwd_tile<RG, TR, true>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
+    }
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    NJ_THREADS(tid, nt) { nj_path_dw_flush(c, s, NJ_ACC(tid), gpart, tid, nt); }
+}

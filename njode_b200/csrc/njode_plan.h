@@ -5,10 +5,14 @@
 #include <algorithm>
 #include "njode_core.cuh"
 #include "njode_seg.cuh"
+#include "njode_path.cuh"
 
 struct NjPlanOut {
     NjCfg fwd, bwd;
     NjSeg seg;                      // seg.ok: the segment fast path (njode_seg.cuh) serves this call
+    NjPath path;                    // path.ok: the warp-GEMM whole-path kernels (njode_path.cuh) serve this call
+    int path_grid_f, path_grid_b;
+    size_t path_smem_f_bytes, path_smem_b_bytes;
     int seg_grid_f, seg_grid_b;
     size_t seg_smem_f_bytes, seg_smem_b_bytes;
     int n_tiles;
@@ -431,14 +435,147 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
     s.ok = 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// whole-path units on the warp GEMMs (njode_path.cuh): eligibility, tile shapes, shared-memory layout
+// ------------------------------------------------------------------------------------------------
+static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_sms, size_t smem_limit, NjPlanOut& out) {
+    NjPath& s = out.path;
+    memset(&s, 0, sizeof(s));
+    const char* off = getenv("NJODE_NO_PATH");
+    if (off && atoi(off)) return;
+    const int n = b.n_units;
+    if (b.unit_kind != 0 || n <= 0 || c.compact) return;
+    int maxhid = 1, maxn = 1, maxlast = 1;
+    const int nnets = c.use_rnn ? NJODE_NUM_NETS : 3;
+    for (int q = 0; q < nnets; ++q) {
+        const NjNet& N = c.net[q];
+        maxn = std::max(maxn, N.n);
+        for (int l = 0; l < N.n - 1; ++l) maxhid = std::max(maxhid, N.rp[l]);
+        maxlast = std::max(maxlast, N.rp[N.n - 1]);
+    }
+    s.sI = nj_stride_act(std::max(std::max(c.inf, c.enc_in), std::max(c.H, c.d)));
+    s.sA = nj_stride_act(maxhid);
+    s.sO = nj_stride_act(maxlast);
+    s.sH = (c.H + 3) & ~3; s.sD = (std::max(c.d, c.dout) + 3) & ~3; s.s3 = (3 * c.H + 3) & ~3;
+    s.nA = std::max(1, maxn - 1);
+    static const int order[NJODE_NUM_NETS] = {NJODE_NET_ODE, NJODE_NET_RO, NJODE_NET_ENC, NJODE_NET_GRU_HH, NJODE_NET_GRU_IH};
+    int tiles = 0;
+    for (int oi = 0; oi < NJODE_NUM_NETS; ++oi) {
+        const NjNet& N = c.net[order[oi]];
+        for (int l = 0; l < NJODE_MAX_LINEAR; ++l) {
+            s.tile_base[order[oi]][l] = tiles;
+            if (l < N.n) tiles += ((N.dim[l] + 3) / 4) * ((N.dim[l + 1] + 3) / 4);
+        }
+    }
+    s.tiles_total = tiles;
+    const char* frw = getenv("NJODE_PATH_R");                 // tests: rows per warp (1, 2, 4, 8)
+    const int force_r = frw ? atoi(frw) : 0;
+    auto shape = [](int R, int& rg, int& tr) { rg = R >= 4 ? 4 : R; tr = R >= 8 ? 2 : 1; };
+    // ---- forward: per-warp regions ----
+    {
+        auto region = [&](int R) {
+            int o = 0;
+            s.f_IN = o; o += R * s.sI;
+            s.f_A0 = o; o += R * s.sA;
+            s.f_A1 = o; o += R * s.sA;
+            s.f_OUT = o; o += R * s.sO;
+            s.f_HS = o; o += R * s.sH;
+            s.f_EE = o; o += R * s.sH;
+            s.f_LX = o; o += R * s.sD;
+            s.f_TX = o; o += R * s.sD;
+            s.f_XI = o; o += R * s.sD;
+            s.f_YBJ = o; o += R * s.sD;
+            s.f_YY = o; o += R * s.sD;
+            s.f_MM = o; o += R * s.sD;
+            s.f_GI = o; if (c.use_rnn) o += R * s.s3;
+            s.f_F = o; o += NJP_F_COUNT * NJP_RS;
+            s.f_I = o; o += NJP_I_COUNT * NJP_RS + 4;
+            return (o + 3) & ~3;
+        };
+        // the smallest tile height whose warps still fit the machine in one wave of 12-warp CTAs: smaller tiles = more
+        // warps to hide the latency of the dependent steps and, below 4 rows, a split reduction dimension
+        int R = 8;
+        for (int cand = 1; cand <= 8; cand *= 2)
+            if ((n + cand - 1) / cand <= num_sms * 12) { R = cand; break; }
+        if (force_r) R = force_r;
+        shape(R, s.rg_f, s.tr_f);
+        s.f_region = region(R);
+        s.f_warp0 = c.img_floats;
+        s.n_tiles_f = (n + R - 1) / R;
+        int nw = 0;
+        for (int cand = 12; cand >= 1; --cand)
+            if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
+        if (!nw) return;
+        nw = std::max(1, std::min(nw, (s.n_tiles_f + num_sms - 1) / num_sms));
+        s.nw_f = nw;
+        s.f_smem_floats = c.img_floats + nw * s.f_region;
+        out.path_grid_f = std::max(1, std::min((s.n_tiles_f + nw - 1) / nw, num_sms));
+        out.path_smem_f_bytes = (size_t)s.f_smem_floats * 4;
+    }
+    // ---- backward: CTA-level arrays of P rows ----
+    {
+        auto layout = [&](int P, int nw) {
+            int o = c.img_floats;
+            s.b_IN = o; o += P * s.sI;
+            s.b_A = o; o += s.nA * P * s.sA;
+            s.b_G = o; o += s.nA * P * s.sA;
+            s.b_GOUT = o; o += P * s.sO;
+            s.b_GZ = o; o += P * s.sI;
+            s.b_OUT = o; o += P * s.sO;
+            s.b_GH = o; o += P * s.sH;
+            s.b_HB = o; o += P * s.sH;
+            s.b_EE = o; o += P * s.sH;
+            s.b_GE = o; o += P * s.sH;
+            s.b_XI = o; o += P * s.sD;
+            s.b_LX = o; o += P * s.sD;
+            s.b_TX = o; o += P * s.sD;
+            s.b_YBJ = o; o += P * s.sD;
+            s.b_YY = o; o += P * s.sD;
+            s.b_GYBJ = o; o += P * s.sD;
+            s.b_GX = o; o += P * s.sD;
+            s.b_MM = o; o += P * s.sD;
+            s.b_GI = o; if (c.use_rnn) o += P * s.s3;
+            s.b_GHH = o; if (c.use_rnn) o += P * s.s3;
+            s.b_F = o; o += NJP_F_COUNT * P;
+            s.b_I = o; o += NJB_I_COUNT * P + 4 + nw + 4;
+            return (o + 3) & ~3;
+        };
+        const int P_want = std::max(1, (n + num_sms - 1) / num_sms);
+        int R = 8;
+        for (int cand = 1; cand <= 8; cand *= 2)
+            if ((P_want + cand - 1) / cand <= 12) { R = cand; break; }
+        if (force_r) R = force_r;
+        int nw = std::max(1, std::min(12, (P_want + R - 1) / R));
+        int fl = 0;
+        for (; nw >= 1; --nw) {
+            fl = layout(R * nw, nw);
+            if ((size_t)fl * 4 <= smem_limit) break;
+        }
+        if (nw < 1) return;
+        shape(R, s.rg_b, s.tr_b);
+        s.nw_b = nw; s.P_b = R * nw; s.b_smem_floats = fl;
+        const int wtot = std::max(nw, std::min(12, (tiles + 32 * NJ_SEG_NT_MAX - 1) / (32 * NJ_SEG_NT_MAX)));
+        s.nt_b = 32 * wtot;
+        s.nt_slots = std::min(NJ_SEG_NT_MAX, (tiles + s.nt_b - 1) / s.nt_b);
+        s.n_tiles_b = (n + s.P_b - 1) / s.P_b;
+        out.path_grid_b = std::max(1, std::min(s.n_tiles_b, num_sms));
+        out.path_smem_b_bytes = (size_t)s.b_smem_floats * 4;
+    }
+    s.ok = 1;
+}
+
 // the whole launch plan of one (model, batch) pair: the segment fast path when it serves the call (padded parameter
 // image), else the generic kernels on the compact image
 static inline bool nj_plan_all(const njode_model_t& m, const njode_batch_t& b, int num_sms, size_t smem_limit, int force_P,
                                NjPlanOut& out, std::string& err) {
+    memset(&out.path, 0, sizeof(out.path));
     if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, false, out, err)) return false;
     nj_make_seg(out.fwd, b, num_sms, smem_limit, out);
     if (out.seg.ok) return true;
+    nj_make_path(out.fwd, b, num_sms, smem_limit, out);
+    if (out.path.ok) return true;
     if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, true, out, err)) return false;
     memset(&out.seg, 0, sizeof(out.seg));
+    memset(&out.path, 0, sizeof(out.path));
     return true;
 }

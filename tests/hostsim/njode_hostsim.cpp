@@ -7,6 +7,7 @@
 // without a CUDA device).
 #define NJODE_HOST_SIM 1
 #include <stdlib.h>
+#include <stdio.h>
 #include <vector>
 #include "../../njode_b200/csrc/njode_plan.h"
 
@@ -21,6 +22,10 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
     std::string err;
     const char* fp = getenv("NJODE_FORCE_TILE");
     if (!nj_plan_all(*m, *b, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
+    if (getenv("NJODE_DEBUG_PLAN"))
+        fprintf(stderr, "[plan] units %d kind %d E %d -> seg %d path %d (fwd rg %d tr %d nw %d | bwd rg %d tr %d nw %d nt %d P %d slots %d tiles %d)\n",
+                b->n_units, b->unit_kind, b->E, out.seg.ok, out.path.ok, out.path.rg_f, out.path.tr_f, out.path.nw_f, out.path.rg_b,
+                out.path.tr_b, out.path.nw_b, out.path.nt_b, out.path.P_b, out.path.nt_slots, out.path.tiles_total);
     const size_t cap = (size_t)kSimSMs * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
     out.ws_bytes = out.ws_partials_off + cap * std::max(out.fwd.img_floats, out.bwd.img_floats) * sizeof(float);
@@ -82,6 +87,16 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
             if (cta == 0) *a.counter = 0;
             nj_seg_cta_forward(pl.fwd, pl.seg, a, smem.data());
         }
+    } else if (pl.path.ok) {
+        std::vector<float> smem(pl.path.f_smem_floats);
+        for (int cta = 0; cta < pl.path_grid_f; ++cta) {
+            std::fill(smem.begin(), smem.end(), NAN);
+            if (cta == 0) *a.counter = 0;
+            if (pl.path.rg_f == 1) nj_path_cta_forward<1, 1>(pl.fwd, pl.path, a, smem.data());
+            else if (pl.path.rg_f == 2) nj_path_cta_forward<2, 1>(pl.fwd, pl.path, a, smem.data());
+            else if (pl.path.tr_f == 1) nj_path_cta_forward<4, 1>(pl.fwd, pl.path, a, smem.data());
+            else nj_path_cta_forward<4, 2>(pl.fwd, pl.path, a, smem.data());
+        }
     } else {
         std::vector<float> smem(pl.fwd.smem_floats_fwd);
         for (int cta = 0; cta < pl.grid_fwd && batch->n_units > 0; ++cta) {
@@ -116,6 +131,17 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
             nj_seg_cta_backward<false>(pl.bwd, pl.seg, a, smem.data(), cta);
         }
         nparts = pl.seg_grid_b;
+    } else if (pl.path.ok) {
+        std::vector<float> smem(pl.path.b_smem_floats);
+        for (int cta = 0; cta < pl.path_grid_b; ++cta) {
+            std::fill(smem.begin(), smem.end(), NAN);
+            if (cta == 0) *a.counter = 0;
+            if (pl.path.rg_b == 1) nj_path_cta_backward<1, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+            else if (pl.path.rg_b == 2) nj_path_cta_backward<2, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+            else if (pl.path.tr_b == 1) nj_path_cta_backward<4, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+            else nj_path_cta_backward<4, 2>(pl.bwd, pl.path, a, smem.data(), cta);
+        }
+        nparts = pl.path_grid_b;
     } else {
         std::vector<float> smem(pl.bwd.smem_floats_bwd);
         for (int cta = 0; cta < pl.grid_bwd && batch->n_units > 0; ++cta) {

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "hostsim", "njode_hostsim.cpp")
 OUT_DIR = os.path.join(ROOT, "tests", "_hostsim")
 OUT = os.path.join(OUT_DIR, "libnjode_hostsim.so")
-DEPS = [SRC] + [os.path.join(ROOT, "njode_b200", "csrc", f) for f in ("njode_core.cuh", "njode_hash.cuh", "njode_seg.cuh", "njode_plan.h")] + \
+DEPS = [SRC] + [os.path.join(ROOT, "njode_b200", "csrc", f) for f in ("njode_core.cuh", "njode_hash.cuh", "njode_seg.cuh", "njode_path.cuh", "njode_plan.h")] + \
        [os.path.join(ROOT, "include", "njode_b200.h")]
 
 _runner = None

@@ -10,7 +10,7 @@ import oracle.njode_oracle as orc
 from njode_b200 import models
 
 RTOL = 1e-4          # BASELINE.json north_star: loss, predictions, parameter gradients (fp32)
-NOISE_MULT = 4.0
+NOISE_MULT = 8.0
 
 
 def rel_err(a, b):
@@ -27,7 +27,10 @@ def noise_floor(ref32, truth64, kern32=None):
     are measured: ``ref32`` (ATen on the CPU, libm tanh) and ``kern32`` = the same oracle with tanh evaluated by the
     kernels' formula 1 - 2 / (exp2(2 x log2 e) + 1) (absolute error ~1e-7, the accuracy class of CUDA's own tanhf, which
     uses that expression above |x| = 0.55): sums that cancel (the gradient of a trained model) see that noise directly.
-    NOISE_MULT covers that a measured maximum is ONE draw of the noise (other summation orders, ex2/rcp.approx)."""
+    NOISE_MULT covers that a measured maximum is ONE draw of the noise, other summation orders, and that the emulation
+    rounds exp2 correctly (<= 1 ulp on the CPU) where the SFU's ex2.approx.ftz has a relative error of up to 2^-22 (4 ulp):
+    measured on the B200, the worst element of the golden cases sits at 5.6x the emulated floor (gru_masked,
+    grad ode_f.f.0.weight, |diff| 2.4e-7 = 5.5e-6 of the tensor's max)."""
     t = np.asarray(truth64, dtype=np.float64)
     f = np.abs(np.asarray(ref32, dtype=np.float64) - t).max()
     if kern32 is not None:

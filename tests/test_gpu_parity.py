@@ -156,3 +156,25 @@ def test_native_library_is_loaded():
     with open("/proc/self/maps") as f:
         assert "libnjode_b200.so" in f.read()
     assert _ext.cuda_lib().dll.njode_abi_version() == 4
+
+
+@pytest.mark.parametrize("width", [50, 200])
+def test_config4_physionet_full_size_against_oracle(width):
+    """BASELINE config 4 at its FULL size: the reference's PhysioNet batch of 50 records
+    (parallel_train.py:656), d = H = 41 masked, ~3 700 dependent Euler steps on the 3000-tick grid with float32 times
+    (physionet_train.py:192-193), 2x50 and 2x200 tanh nets -- where fp32 error has thousands of steps to accumulate.
+    Element-wise rtol 1e-4 + the measured fp32 noise floor (parity_util.noise_floor); the per-output errors go to
+    gpurun_out/parity_physionet_b50_<width>.json."""
+    import json
+    import bench
+    wl = dict(bench.WORKLOADS["physionet_synth_b50"], width=width)
+    batch, dt = bench.synth_batch_physio(wl, 1234, 0, wl["paths"])
+    cfg = dict(bench.model_cfg(wl), dropout_rate=0.0)
+    report = {}
+    try:
+        parity_util.check_against_oracle(cfg, batch, dt, bench.horizon(wl), seed=11, device=DEV, report=report)
+    finally:
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_physionet_b50_%d.json" % width), "w") as f:
+            json.dump(report, f, indent=1)

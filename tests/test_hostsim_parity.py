@@ -29,6 +29,8 @@ def sim_runner():
     os.environ.pop("NJODE_FORCE_DW", None)
     os.environ.pop("NJODE_SEG_HELPERS", None)
     os.environ.pop("NJODE_SEG_LOW", None)
+    os.environ.pop("NJODE_NO_PATH", None)
+    os.environ.pop("NJODE_PATH_R", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -50,6 +52,7 @@ def test_path_call(name):
 @pytest.mark.parametrize("name", ["bs_ckpt1", "masked_small", "curt_nobias_relu", "gru_masked"])
 def test_tile_size_invariance(name, tile):
     os.environ["NJODE_FORCE_TILE"] = str(tile)
+    os.environ["NJODE_NO_PATH"] = "1"            # the generic CTA-cooperative kernels (njode_core.cuh)
     parity_util.check_training_call(name, "cpu", with_hT_grad=True)
     parity_util.check_path_call(name, "cpu")
 
@@ -61,6 +64,7 @@ def test_gradient_image_residency(name, dw):
     partial in global memory (0) -- same gradients"""
     os.environ["NJODE_FORCE_DW"] = str(dw)
     os.environ["NJODE_NO_SEG"] = "1"
+    os.environ["NJODE_NO_PATH"] = "1"
     parity_util.check_training_call(name, "cpu", with_hT_grad=True)
 
 
@@ -70,6 +74,7 @@ def test_small_tiles(name, tile):
     """tile heights the planner picks for small whole-path batches (PhysioNet batch of 50 -> one path per CTA)"""
     os.environ["NJODE_FORCE_TILE"] = str(tile)
     os.environ["NJODE_NO_SEG"] = "1"
+    os.environ["NJODE_NO_PATH"] = "1"
     parity_util.check_training_call(name, "cpu", with_hT_grad=True)
     parity_util.check_path_call(name, "cpu")
 
@@ -237,3 +242,40 @@ def test_backward_after_a_parameter_update_raises():
         next(m.parameters()).mul_(1.5)
     with pytest.raises(RuntimeError, match="modified"):
         loss.backward()
+
+
+# ---- whole-path units on the warp GEMMs (njode_path.cuh): every tile shape the planner can pick ----
+@pytest.mark.parametrize("rows", [1, 2, 4, 8])
+@pytest.mark.parametrize("name", ["masked_small", "gru_demo", "gru_masked", "gru_d3_nores"])
+def test_path_kernels_every_tile_shape(name, rows):
+    """rows per warp 1 / 2 (split reduction dimension, partial sums meet in shuffles), 4 and 8: same loss, hT, gradients
+    (with a gradient flowing into hT) and recorded paths as the reference"""
+    os.environ["NJODE_PATH_R"] = str(rows)
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    parity_util.check_training_call(name, "cpu")
+    parity_util.check_path_call(name, "cpu")
+
+
+@pytest.mark.parametrize("rows", [1, 2, 4, 8])
+@pytest.mark.parametrize("name", ["bs_ckpt1", "curt_nobias_relu", "res_case2", "easy_w07_nores"])
+def test_path_kernels_record_paths_of_the_non_masked_model(name, rows):
+    """return_path / until_T calls of the non-masked model (evaluate, get_pred) are whole-path units too"""
+    os.environ["NJODE_PATH_R"] = str(rows)
+    parity_util.check_path_call(name, "cpu")
+
+
+@pytest.mark.parametrize("rows", [1, 2, 4, 8])
+def test_path_kernels_train_mode_dropout(rows):
+    os.environ["NJODE_PATH_R"] = str(rows)
+    cfg = dict(cases.CONFIGS["masked_small"], dropout_rate=0.25)
+    batch = cases.irregular_batch(11, 5, 10, seed=21, masked=True, times_f32=True)
+    parity_util.check_against_oracle(cfg, batch, 0.05, 1 + 1e-12, seed=3, device="cpu", train=True, grad_hT=True)
+    cfg = cases.demo_cfg(use_rnn=True, dropout_rate=0.2, bias=False, hidden_size=6)
+    batch = cases.grid_batch(13, 1, 16, 0.3, seed=9)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 16, 1.0, seed=4, device="cpu", train=True, grad_hT=True)
+
+
+def test_path_kernels_physionet_shape():
+    """d = H = 41 masked, 2x50 nets, float32 times, several waves of tiles per CTA on the 4-SM simulation"""
+    batch = cases.irregular_batch(70, 41, 30, seed=7, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.2, feat_prob=0.12)
+    parity_util.check_against_oracle(cases.CONFIGS["masked_physio"], batch, 0.01, 1 + 1e-12, seed=3, device="cpu", grad_hT=True)
