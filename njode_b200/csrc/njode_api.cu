@@ -302,6 +302,7 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_b_bytes));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.path_grid_b;
+        if (getenv("NJODE_DEBUG_PLAN")) fprintf(stderr, "[bwd] ws %p partials %p (+%zu) img %d grid %d nt %d ws_bytes %zu\n", workspace, (void*)a.partials, pl.ws_partials_off, pl.bwd.img_floats, pl.path_grid_b, pl.path.nt_b, pl.ws_bytes);
         kern<<<pl.path_grid_b, pl.path.nt_b, pl.path_smem_b_bytes, st>>>(pl.bwd, pl.path, a);
         nj_set_last_kernel(1, name);
     } else {

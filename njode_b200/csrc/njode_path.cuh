@@ -777,17 +777,13 @@ NJ_HD void nj_path_dw_rows(const NjCfg& c, const NjPath& s, const NjPathB& t, in
     q[16] = b0; q[17] = b1; q[18] = b2; q[19] = b3;
 }
 
-// dW phase of one network: thread-owned tiles, the first NJ_SEG_NT_MAX * nt of them in registers for the whole launch,
-// the others accumulated from zero and added into this CTA's partial image (L2 resident) right away
-NJ_HD void nj_path_dw(const NjCfg& c, const NjPath& s, const NjPathB& t, int netid, float* acc, float* gpart,
-                      int tid, int nt, int Pt, const int* msk, int R) {
-#pragma unroll
-    for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
-        if (slot >= s.nt_slots) break;
-        int l, og, kg;
-        if (!nj_path_tile_decode(c, s, netid, slot * nt + tid, l, og, kg)) continue;
-        nj_path_dw_rows(c, s, t, netid, l, og, kg, Pt, msk, R, acc + slot * 20);
-    }
+// tiles beyond the register slots: accumulated from zero and added into this CTA's partial image (L2 resident) right
+// away.  Kept out of line: inlined into the 40-accumulator dW phase, ptxas (12.9, -O3) produced a wrong partial-image
+// address for these tiles on sm_100a (compute-sanitizer: out-of-bounds LDG in the read-modify-write; a printf next to it
+// made the problem disappear), while the same source is correct in the host simulation.
+NJ_HDN void nj_path_dw_overflow(const NjCfg* cp, const NjPath* sp, const NjPathB* tp, int netid, float* gpart, int tid, int nt,
+                                int Pt, const int* msk, int R) {
+    const NjCfg& c = *cp; const NjPath& s = *sp; const NjPathB& t = *tp;
     for (int T = NJ_SEG_NT_MAX * nt + tid; T < s.tiles_total; T += nt) {
         int l, og, kg;
         if (!nj_path_tile_decode(c, s, netid, T, l, og, kg)) continue;
@@ -797,6 +793,19 @@ NJ_HD void nj_path_dw(const NjCfg& c, const NjPath& s, const NjPathB& t, int net
         nj_path_dw_rows(c, s, t, netid, l, og, kg, Pt, msk, R, q);
         nj_seg_tile_store(c, netid, l, og, kg, q, gpart, true);
     }
+}
+
+// dW phase of one network: thread-owned tiles, the first NJ_SEG_NT_MAX * nt of them in registers for the whole launch
+NJ_HD void nj_path_dw(const NjCfg& c, const NjPath& s, const NjPathB& t, int netid, float* acc, float* gpart,
+                      int tid, int nt, int Pt, const int* msk, int R) {
+#pragma unroll
+    for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
+        if (slot >= s.nt_slots) break;
+        int l, og, kg;
+        if (!nj_path_tile_decode(c, s, netid, slot * nt + tid, l, og, kg)) continue;
+        nj_path_dw_rows(c, s, t, netid, l, og, kg, Pt, msk, R, acc + slot * 20);
+    }
+    if (s.tiles_total > NJ_SEG_NT_MAX * nt) nj_path_dw_overflow(&c, &s, &t, netid, gpart, tid, nt, Pt, msk, R);
 }
 
 NJ_HD void nj_path_dw_flush(const NjCfg& c, const NjPath& s, const float* acc, float* gpart, int tid, int nt) {

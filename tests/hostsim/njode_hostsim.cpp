@@ -15,7 +15,9 @@ static thread_local std::string g_err;
 extern "C" const char* njode_last_error(void) { return g_err.c_str(); }
 extern "C" int njode_abi_version(void) { return NJODE_ABI_VERSION; }
 
-static const int kSimSMs = 4;
+// simulated SM count: 4 keeps several tiles per CTA in play; NJODE_SIM_SMS=148 reproduces the launch plans of a B200
+static int sim_sms() { const char* e = getenv("NJODE_SIM_SMS"); return e ? atoi(e) : 4; }
+#define kSimSMs sim_sms()
 static const size_t kSimSmem = 227 * 1024;
 
 static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& out) {
