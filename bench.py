@@ -60,9 +60,11 @@ WORKLOADS = {
                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=200),
     # BASELINE.json configs[4]: scaled BlackScholes, d=16, H=256, 4x256 nets, 1000 Euler steps, paths generated
     # on the device (Philox Euler-Maruyama + device collate), tcgen05 tensor-core kernels (bf16 operands)
+    # The dataset is BASELINE's "1M on-device-generated paths" sharded over 8 GPUs: every rank generates ITS 131 072 paths
+    # (global path ids rank * 131072 ..., 16.8 GB of fp64 paths per GPU) and steps through batches of 8 192 of them.
     "bs_scaled_d16_h256": dict(sde="BlackScholes", paths=8192, steps=1000, d=16, H=256, width=256,
                                layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128,
-                               cpu_sample_steps=100, device_data=True),
+                               cpu_sample_steps=100, device_data=True, dataset_paths=131072),
     "bs_scaled_d16_h256_small": dict(sde="BlackScholes", paths=4096, steps=100, d=16, H=256, width=256,
                                      layers=4, obs_perc=0.1, dropout=0.1, cpu_sample_paths=128, device_data=True),
     # BASELINE.json configs[3]: PhysioNet-shaped synthetic irregular series: 41 masked features,
@@ -186,17 +188,31 @@ def synth_batch_physio(wl, seed, first_path, n_paths):
     return batch, 0.016 / 48
 
 
-def synth_batch_device(wl, seed, first_path, n_paths, dev):
+def device_dataset(wl, seed, first_path, n_paths, dev):
     """paths + observation mask generated on the device (njode_sde_generate, one Philox subsequence per global
-    path id: identical data for any sharding) and collated there (njode_collate)."""
+    path id: identical data for any sharding), kept there; -> (dataset, generation ms by CUDA events, bytes written)"""
     import torch
     from njode_b200 import stock_model
     p = SDE_PARAMS
     hp = dict(drift=p["drift"], volatility=p["volatility"], mean=p["mean"], speed=p["speed"],
               correlation=p["correlation"], S0=[p["S0"]] * wl["d"], nb_paths=n_paths, nb_steps=wl["steps"],
               maturity=p["maturity"], sine_coeff=None, obs_perc=wl["obs_perc"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
     ds = stock_model.DeviceDataset(wl["sde"], hp, seed=seed, first_path=first_path, device=dev)
-    b = ds.collate(torch.arange(n_paths))
+    e1.record()
+    torch.cuda.synchronize()
+    nbytes = ds.paths.numel() * 8 + ds.observed.numel() * 4 + ds.nb_obs.numel() * 4
+    return ds, e0.elapsed_time(e1), nbytes
+
+
+def synth_batch_device(wl, seed, first_path, n_paths, dev, on_device=False):
+    """one batch of a device-generated dataset, collated on the device (njode_collate).  on_device: the index arrays stay
+    device tensors too (the resident arm); otherwise they are host arrays as in the reference's contract."""
+    import torch
+    ds, _, _ = device_dataset(wl, seed, first_path, n_paths, dev)
+    b = ds.collate(torch.arange(n_paths), on_device=on_device)
     return b, ds.dt
 
 
@@ -457,8 +473,17 @@ def measure_b200(ctx, wl_name, wl, steps, warmup, sample_clocks=True):
     B = wl["paths"]                      # per GPU (weak scaling)
     first = rank * B
     dev_data = bool(wl.get("device_data"))
+    generator = None
     if dev_data:
-        batch, dt = synth_batch_device(wl, 1234, first, B, dev)
+        # this rank's shard of the dataset, generated where it is used; batches are collated from it on the device
+        n_ds = int(wl.get("dataset_paths", B))
+        ds, gen_ms, gen_bytes = device_dataset(wl, 1234, rank * n_ds, n_ds, dev)
+        dt = ds.dt
+        batch = ds.collate(torch.arange(B), on_device=True)
+        hbm = float(ctx.peaks.get("hbm_gbs", 6650.0))
+        generator = {"paths_per_gpu": n_ds, "paths_total": n_ds * world, "bytes_written_per_gpu": gen_bytes, "ms": gen_ms,
+                     "gb_per_s": gen_bytes / (gen_ms * 1e-3) / 1e9, "frac_of_hbm_peak": gen_bytes / (gen_ms * 1e-3) / 1e9 / hbm,
+                     "note": "njode_sde_generate: fp64 paths [paths, d, steps+1] + int32 observation mask, CUDA events"}
     else:
         batch, dt = synth_batch(wl, 1234, first, B)
     # the Euler grid is batch-global (NJODE/models.py:430-439): all ranks use the union of times.
@@ -525,10 +550,11 @@ def measure_b200(ctx, wl_name, wl, steps, warmup, sample_clocks=True):
     model.output_device = "cpu"
     nb = 3
     if dev_data:
-        # the e2e arm still hands HOST tensors to the public API (X / start_X are copied to the host here)
+        # the e2e arm still hands HOST tensors to the public API: other batches of the same dataset, copied to the host here
         host_batches = []
         for j in range(nb):
-            hb = synth_batch_device(wl, 4321 + j, first, B, dev)[0]
+            lo = ((j + 1) * B) % max(1, len(ds) - B + 1)
+            hb = ds.collate(torch.arange(lo, lo + B))
             hb["X"], hb["start_X"] = hb["X"].cpu(), hb["start_X"].cpu()
             host_batches.append(hb)
     else:
@@ -609,8 +635,11 @@ def measure_b200(ctx, wl_name, wl, steps, warmup, sample_clocks=True):
                     "kernel_ms": k_ms, "fwd_enc_ms": te.value, "fwd_ode_ms": to.value, "fwd_ro_ms": tr_.value,
                     "bwd_chain_ms": tc_.value, "bwd_dw_ms": td.value, "flops_per_launch": 3.0 * fwd_flops}
     del model, pb, host_batches, batch
+    if dev_data:
+        del ds
     torch.cuda.empty_cache()
-    return {"value": value, "ms_per_step": ms_per_step, "steps": steps, "warmup": max(warmup, 3),
+    res_extra = {"generator": generator} if generator else {}
+    return {**res_extra, "value": value, "ms_per_step": ms_per_step, "steps": steps, "warmup": max(warmup, 3),
             "dtype": "bf16" if tensor_path else "f32",
             "config": config_of(wl_name, wl, euler_steps=S, obs_rows_per_gpu=N_rows, parallelism="dp%d" % world,
                                 l2="flushed between timed steps (256 MiB write)"),

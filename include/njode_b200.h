@@ -244,6 +244,9 @@ long long njode_launch_count(void);
 const char* njode_last_kernel(int which);
 /* fp32 FMA-pipe microbenchmark: dependent chains of FFMA on every SM; *fmas = lane-FMAs issued */
 int njode_fma_peak_launch(float* scratch, int iters, double* fmas, void* stream);
+/* legacy tensor path (mma.sync m16n8k8 tf32) microbenchmark, 8 independent accumulator tiles per warp on every SM;
+ * *macs = multiply-accumulates issued.  Measures whether a 3xTF32 mma.sync dW phase could beat the FFMA pipe. */
+int njode_mma_tf32_peak_launch(float* scratch, int iters, double* macs, void* stream);
 /* writes `bytes` of buf (size it > L2) so the next kernel starts with a cold L2 */
 int njode_l2_flush(void* buf, int64_t bytes, void* stream);
 

@@ -201,12 +201,19 @@ class Runner:
         per-path CSR and the sorted work units are built on the device (schedule.build_index_torch)."""
         sched = _sched.build_schedule(times, delta_t, T, until_T, return_path)
         B = int(start_X.shape[0])
-        tp = np.ascontiguousarray(np.asarray(time_ptr, dtype=np.int64).astype(np.int32))
-        K = len(tp) - 1
-        N = int(tp[-1]) if len(tp) else 0
         n_idx = int(obs_idx.numel()) if torch.is_tensor(obs_idx) else len(obs_idx)
-        if n_idx != N:
-            raise AssertionError("len(obs_idx) != time_ptr[-1]")
+        if torch.is_tensor(time_ptr) and time_ptr.device.type != "cpu":
+            # a batch collated on the device (stock_model.DeviceDataset.collate(..., on_device=True)): time_ptr / obs_idx /
+            # n_obs_ot never visit the host; K comes from len(times) and N from the (already sliced) row arrays
+            tp = time_ptr.detach().to(self.device, torch.int32).contiguous()
+            K = int(tp.numel()) - 1
+            N = n_idx
+        else:
+            tp = np.ascontiguousarray(np.asarray(time_ptr, dtype=np.int64).astype(np.int32))
+            K = len(tp) - 1
+            N = int(tp[-1]) if len(tp) else 0
+            if n_idx != N:
+                raise AssertionError("len(obs_idx) != time_ptr[-1]")
 
         def stage_f32(t, shape):
             if t is None:

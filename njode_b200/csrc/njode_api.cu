@@ -70,7 +70,43 @@ __global__ void __launch_bounds__(384) nj_path_bwd_kernel(const __grid_constant_
                                                           const __grid_constant__ NjArgs args) {
     nj_path_cta_backward<RG, TR>(cfg, path, args, nj_smem, blockIdx.x);
 }
+// the same units with weight-stationary Euler steps (small batches): all warps of a CTA on one tile
+// (13 warps: warps are allocated in groups of 4, so the register file gives a 416-thread CTA 128 registers per thread)
+template <int RG, int TR>
+__global__ void __launch_bounds__(416) nj_stat_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
+                                                          const __grid_constant__ NjArgs args) {
+    nj_stat_cta_forward<RG, TR>(cfg, path, args, nj_smem);
+}
+template <int RG, int TR>
+__global__ void __launch_bounds__(416) nj_stat_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
+                                                          const __grid_constant__ NjArgs args) {
+    nj_stat_cta_backward<RG, TR>(cfg, path, args, nj_smem, blockIdx.x);
+}
+// pipelined backward: dW of the ODE network on helper warps, concurrent with the row warps' next step
+template <int RG, int TR>
+__global__ void __launch_bounds__(384) nj_path_bwd_pipe_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
+                                                               const __grid_constant__ NjArgs args) {
+    nj_path_cta_backward_pipe<RG, TR>(cfg, path, args, nj_smem, blockIdx.x);
+}
 typedef void (*nj_path_kern_t)(const NjCfg, const NjPath, const NjArgs);
+static nj_path_kern_t nj_pipe_pick(int rg, int tr, const char** name) {
+    if (rg == 1) { *name = "nj_path_bwd_pipe_kernel<1,1>"; return nj_path_bwd_pipe_kernel<1, 1>; }
+    if (rg == 2) { *name = "nj_path_bwd_pipe_kernel<2,1>"; return nj_path_bwd_pipe_kernel<2, 1>; }
+    if (tr == 1) { *name = "nj_path_bwd_pipe_kernel<4,1>"; return nj_path_bwd_pipe_kernel<4, 1>; }
+    *name = "nj_path_bwd_pipe_kernel<4,2>"; return nj_path_bwd_pipe_kernel<4, 2>;
+}
+static nj_path_kern_t nj_stat_pick(int rg, int tr, bool bwd, const char** name) {
+    if (!bwd) {
+        if (rg == 1) { *name = "nj_stat_fwd_kernel<1,1>"; return nj_stat_fwd_kernel<1, 1>; }
+        if (rg == 2) { *name = "nj_stat_fwd_kernel<2,1>"; return nj_stat_fwd_kernel<2, 1>; }
+        if (tr == 1) { *name = "nj_stat_fwd_kernel<4,1>"; return nj_stat_fwd_kernel<4, 1>; }
+        *name = "nj_stat_fwd_kernel<4,2>"; return nj_stat_fwd_kernel<4, 2>;
+    }
+    if (rg == 1) { *name = "nj_stat_bwd_kernel<1,1>"; return nj_stat_bwd_kernel<1, 1>; }
+    if (rg == 2) { *name = "nj_stat_bwd_kernel<2,1>"; return nj_stat_bwd_kernel<2, 1>; }
+    if (tr == 1) { *name = "nj_stat_bwd_kernel<4,1>"; return nj_stat_bwd_kernel<4, 1>; }
+    *name = "nj_stat_bwd_kernel<4,2>"; return nj_stat_bwd_kernel<4, 2>;
+}
 static nj_path_kern_t nj_path_pick(int rg, int tr, bool bwd, const char** name) {
     if (!bwd) {
         if (rg == 1) { *name = "nj_path_fwd_kernel<1,1>"; return nj_path_fwd_kernel<1, 1>; }
@@ -246,10 +282,11 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";
-        nj_path_kern_t kern = nj_path_pick(pl.path.rg_f, pl.path.tr_f, false, &name);
+        nj_path_kern_t kern = pl.path.stat ? nj_stat_pick(pl.path.rg_f, pl.path.tr_f, false, &name)
+                                           : nj_path_pick(pl.path.rg_f, pl.path.tr_f, false, &name);
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_f_bytes));
         if (tm) cudaEventRecord(g_ev[0], st);
-        kern<<<pl.path_grid_f, pl.path.nw_f * 32, pl.path_smem_f_bytes, st>>>(pl.fwd, pl.path, a);
+        kern<<<pl.path_grid_f, (pl.path.stat ? pl.path.nw_s : pl.path.nw_f) * 32, pl.path_smem_f_bytes, st>>>(pl.fwd, pl.path, a);
         nj_set_last_kernel(0, name);
     } else {
         nj_set_last_kernel(0, "nj_fwd_kernel");
@@ -298,7 +335,9 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";
-        nj_path_kern_t kern = nj_path_pick(pl.path.rg_b, pl.path.tr_b, true, &name);
+        nj_path_kern_t kern = pl.path.stat ? nj_stat_pick(pl.path.rg_b, pl.path.tr_b, true, &name)
+                              : (pl.path.pipe ? nj_pipe_pick(pl.path.rg_b, pl.path.tr_b, &name)
+                                              : nj_path_pick(pl.path.rg_b, pl.path.tr_b, true, &name));
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_b_bytes));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.path_grid_b;

@@ -40,6 +40,10 @@ struct NjPath {
     int b_smem_floats, P_b, n_tiles_b;
     int tile_base[NJODE_NUM_NETS][NJODE_MAX_LINEAR];    // first dW tile of (net, layer); order ODE, RO, ENC, GRU_HH, GRU_IH
     int tiles_total, nt_slots;
+    // weight-stationary Euler steps (small batches): one CTA of nw_s warps per tile of rg*tr rows, ODE weights in registers
+    int stat, nw_s, b_PART;
+    // pipelined backward: dW of the ODE network on helper warps, operand buffers (IN, A, G, GOUT) twice, b_copy floats apart
+    int pipe, b_copy;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -604,7 +608,8 @@ struct NjPathFwd {
         NJ_SYNCWARP();
     }
 
-    NJ_HD void run(int u0, int u1) {
+    // unit descriptors, start encoder, first record
+    NJ_HD void begin(int u0, int u1) {
         const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
         const bool rec = a.b.E > 0;
         NJ_LANES(lane) {
@@ -650,31 +655,46 @@ struct NjPathFwd {
         }
         NJ_SYNCWARP();
         if (rec) record(0, NJ_EVENT_INIT);
-        const int S = a.b.S, K = a.b.K;
+    }
+    // step count at which the next jump of the tile happens (NJP_NEVER: none left); gi: global jump cursor (return_path)
+    NJ_HD int next_jump(int gi) const {
+        int nk = NJP_NEVER;
+        if (a.b.E > 0) { if (gi < a.b.K) nk = NJ_LDG(a.b.jump_step + gi); }
+        else for (int r = 0; r < R; ++r) nk = I[NJP_I_NEXTK * RS + r] < nk ? I[NJP_I_NEXTK * RS + r] : nk;
+        return nk;
+    }
+    NJ_HD bool any_jumps_at(int nk) const {
+        bool any = false;
+        for (int r = 0; r < R; ++r) any |= (I[NJP_I_NEXTK * RS + r] == nk);
+        return any;
+    }
+    NJ_HD void finish() {
+        NJ_LANES(lane) {
+            NJ_ROWMAP(R);
+            const int p = I[NJP_I_PATH * RS + er];
+            if (p >= 0)
+                for (int c_ = ec0; c_ < c.H; c_ += LPR) a.hT[(size_t)p * c.H + c_] = HS[er * s.sH + c_];
+        }
+        NJ_SYNCWARP();
+    }
+
+    NJ_HD void run(int u0, int u1) {
+        const bool rec = a.b.E > 0;
+        begin(u0, u1);
+        const int S = a.b.S;
         int k = 0, gi = 0;
         for (;;) {
-            int nk = NJP_NEVER;
-            if (rec) { if (gi < K) nk = NJ_LDG(a.b.jump_step + gi); }
-            else for (int r = 0; r < R; ++r) nk = I[NJP_I_NEXTK * RS + r] < nk ? I[NJP_I_NEXTK * RS + r] : nk;
+            const int nk = next_jump(gi);
             const int kend = nk < S ? nk : S;
             for (; k < kend; ++k) {
                 euler_step(k);
                 if (rec) record(NJ_LDG(a.b.step_event + k), NJ_EVENT_PATH_RO_BASE + (unsigned)k);
             }
             if (nk > S) break;
-            bool any = false;
-            for (int r = 0; r < R; ++r) any |= (I[NJP_I_NEXTK * RS + r] == nk);
-            if (any) jump(nk);
+            if (any_jumps_at(nk)) jump(nk);
             if (rec) { record(NJ_LDG(a.b.jump_event + gi), NJ_EVENT_JUMP_BASE + 3u * (unsigned)gi + 2u); ++gi; }
         }
-        // ---- hT ----
-        NJ_LANES(lane) {
-            NJ_ROWMAP(R);
-            const int p = I[NJP_I_PATH * RS + er];
-            if (p >= 0)
-                for (int c_ = ec0; c_ < c.H; c_ += LPR) a.hT[(size_t)p * c.H + c_] = HS[er * sH + c_];
-        }
-        NJ_SYNCWARP();
+        finish();
     }
 };
 
@@ -1332,6 +1352,195 @@ NJ_HD void nj_path_bwd_tile(const NjCfg& c, const NjPath& s, const NjArgs& a, fl
     NJ_SYNC();
 }
 
+// ------------------------------------------------------------------------------------------------
+// pipelined variant: the dW phase of Euler step k runs on the HELPER warps while the row warps already reverse step
+// k - 1.  The operand buffers of a step (IN, A, G, GOUT) exist twice; the ODE network's gradient tiles live in the helper
+// warps' registers only (up to NJP_HSLOTS 4x4 tiles per helper thread), so the row warps never wait for a dW phase: one CTA
+// barrier per Euler step, at which "row warps finished step k into buffer b" meets "helpers finished the dW of step k + 1
+// from buffer 1 - b".  A jump drains the pipeline and runs its (rare) three dW phases through the partial image.
+// (ncu, PhysioNet-shaped batch of 2 000 before this: 9.5 barrier stalls per issued instruction, issue slots 19 % busy --
+// seven row warps and five helpers took turns.)
+// ------------------------------------------------------------------------------------------------
+#define NJP_HSLOTS 5
+#define NJP_HACC (NJP_HSLOTS * 20)
+NJ_HDN void nj_stat_dw(const NjCfg* cp, const NjPath* sp, const NjPathB* tp, int netid, float* gpart, int tid, int nt, int Pt,
+                       const int* msk, int R);          // every dW tile of one network through the partial image (below)
+
+// helper thread `hid` of `nth`: dW of the ODE network for the Pt rows of the step held in the operand buffers of `t`
+NJ_HD void nj_path_dw_helper(const NjCfg& c, const NjPath& s, const NjPathB& t, float* acc, int hid, int nth, int Pt) {
+    const int ode_tiles = s.tile_base[NJODE_NET_RO][0];        // the ODE network's tiles come first
+#pragma unroll
+    for (int slot = 0; slot < NJP_HSLOTS; ++slot) {
+        const int T = slot * nth + hid;
+        if (T >= ode_tiles) break;
+        int l, og, kg;
+        if (!nj_path_tile_decode(c, s, NJODE_NET_ODE, T, l, og, kg)) continue;
+        nj_path_dw_rows(c, s, t, NJODE_NET_ODE, l, og, kg, Pt, nullptr, 1, acc + slot * 20);
+    }
+}
+NJ_HD void nj_path_helper_flush(const NjCfg& c, const NjPath& s, const float* acc, float* gpart, int hid, int nth) {
+    const int ode_tiles = s.tile_base[NJODE_NET_RO][0];
+#pragma unroll
+    for (int slot = 0; slot < NJP_HSLOTS; ++slot) {
+        const int T = slot * nth + hid;
+        if (T >= ode_tiles) break;
+        int l, og, kg;
+        if (nj_path_tile_decode(c, s, NJODE_NET_ODE, T, l, og, kg)) nj_seg_tile_store(c, NJODE_NET_ODE, l, og, kg, acc + slot * 20, gpart, false);
+    }
+}
+
+#if defined(NJODE_HOST_SIM)
+#define NJP_HACC_DECL(nt) std::vector<float> njp_hacc_store((size_t)(nt) * NJP_HACC, 0.f); float* njp_hacc = njp_hacc_store.data()
+#define NJP_HACC_OF(tid) (njp_hacc + (size_t)(tid) * NJP_HACC)
+#else
+#define NJP_HACC_DECL(nt) float njp_hacc_store[NJP_HACC]; _Pragma("unroll") for (int _i = 0; _i < NJP_HACC; ++_i) njp_hacc_store[_i] = 0.f; float* njp_hacc = njp_hacc_store
+#define NJP_HACC_OF(tid) (njp_hacc)
+#endif
+
+// ROWS: the calling warp owns rows (device: warps < nw_b; host simulation: always, the NJ_THREADS loops cover the helper ids)
+template <int RG, int TR, bool ROWS>
+NJ_HD void nj_path_bwd_tile_pipe(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem, const NjPathB& t0, const NjPathB& t1,
+                                 float* njp_hacc, int cta, int u0, int u1) {
+    constexpr int R = RG * TR;
+    const int P = s.P_b, nt = s.nt_b, Pt = R * s.nw_b, nrow = 32 * s.nw_b, nth = nt - nrow;
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    const NjPathBwd<RG, TR> B0(c, s, a, t0, smem), B1(c, s, a, t1, smem);
+    const NjPathB& t = t0;
+#if defined(NJODE_HOST_SIM)
+    const bool helper_here = true;
+#else
+    const bool helper_here = !ROWS;
+#endif
+    if (ROWS) {
+        NJ_THREADS(tid, nt) {
+            if (tid < Pt) {
+                const int u = u0 + tid;
+                if (u < u1) {
+                    const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                    t.I[NJB_I_PATH * P + tid] = dsc[0]; t.I[NJB_I_C0 * P + tid] = dsc[3]; t.I[NJB_I_CUR * P + tid] = dsc[4];
+                } else { t.I[NJB_I_PATH * P + tid] = -1; t.I[NJB_I_C0 * P + tid] = 0; t.I[NJB_I_CUR * P + tid] = 0; }
+                t.I[NJB_I_ACT * P + tid] = 0;
+                B0.set_prev(tid);
+            }
+        }
+    }
+    NJ_SYNC();
+    if (ROWS) {
+        NJ_WARPS(wp, s.nw_b) {
+            const int r0 = wp * R;
+            NJ_LANES(lane) {
+                NJ_ROWMAP(R);
+                const int r = r0 + er, p = t.I[NJB_I_PATH * P + r];
+                const float* ght = (p >= 0 && a.grad_hT) ? a.grad_hT + (size_t)p * c.H : nullptr;
+                for (int c_ = ec0; c_ < c.H; c_ += LPR) t.GH[r * s.sH + c_] = ght ? NJ_LDG(ght + c_) : 0.f;
+                for (int c_ = ec0; c_ < c.d; c_ += LPR) t.GX[r * s.sD + c_] = 0.f;
+                B0.load_state(r0, lane);
+            }
+            NJ_SYNCWARP();
+        }
+    }
+    int nk = nj_pathb_next(t, P, Pt);
+    int par = 0;                 // buffer the row warps write next
+    bool pending = false;        // the helpers still owe the dW of the step in buffer par ^ 1
+    for (int k = a.b.S; ; --k) {
+        if (nk == k) {
+            // drain, then the jump on buffer 0 with its dW phases through the partial image (all threads)
+            if (pending && helper_here) {
+                NJ_THREADS(tid, nt) { if (tid >= nrow) nj_path_dw_helper(c, s, par ? t0 : t1, NJP_HACC_OF(tid), tid - nrow, nth, Pt); }
+            }
+            pending = false;
+            NJ_SYNC();
+            if (ROWS) { NJ_WARPS(wp, s.nw_b) { B0.jump_p1(wp * R, wp, k); } }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t0, NJODE_NET_RO, gpart, tid, nt, Pt, t.MSK, R); }
+            NJ_SYNC();
+            if (ROWS) { NJ_WARPS(wp, s.nw_b) { B0.jump_p2(wp * R, wp); } }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t0, c.use_rnn ? NJODE_NET_GRU_HH : NJODE_NET_ENC, gpart, tid, nt, Pt, t.MSK, R); }
+            NJ_SYNC();
+            if (c.use_rnn) {
+                if (ROWS) { NJ_WARPS(wp, s.nw_b) { B0.jump_p2b(wp * R, wp); } }
+                NJ_SYNC();
+                NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t0, NJODE_NET_GRU_IH, gpart, tid, nt, Pt, t.MSK, R); }
+                NJ_SYNC();
+            }
+            if (ROWS) { NJ_WARPS(wp, s.nw_b) { B0.jump_p3(wp * R, wp); } }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t0, NJODE_NET_RO, gpart, tid, nt, Pt, t.MSK, R); }
+            NJ_SYNC();
+            nk = nj_pathb_next(t, P, Pt);
+        }
+        if (k == 0) break;
+        if (ROWS) { NJ_WARPS(wp, s.nw_b) { if (par) B1.step_local(wp * R, k - 1); else B0.step_local(wp * R, k - 1); } }
+        if (pending && helper_here) {
+            NJ_THREADS(tid, nt) { if (tid >= nrow) nj_path_dw_helper(c, s, par ? t0 : t1, NJP_HACC_OF(tid), tid - nrow, nth, Pt); }
+        }
+        NJ_SYNC();
+        pending = true; par ^= 1;
+    }
+    if (pending && helper_here) {
+        NJ_THREADS(tid, nt) { if (tid >= nrow) nj_path_dw_helper(c, s, par ? t0 : t1, NJP_HACC_OF(tid), tid - nrow, nth, Pt); }
+    }
+    NJ_SYNC();
+    if (ROWS) { NJ_WARPS(wp, s.nw_b) { B0.start_local(wp * R); } }
+    NJ_SYNC();
+    NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t0, NJODE_NET_ENC, gpart, tid, nt, Pt, nullptr, R); }
+    NJ_SYNC();
+}
+
+template <int RG, int TR>
+NJ_HD void nj_path_cta_backward_pipe(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem, int cta) {
+    const int nt = s.nt_b;
+    constexpr int R = RG * TR;
+    nj_stage_image(smem, a.image, c.img_floats, nt);
+    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    nj_zero(gpart, c.img_floats, nt);
+    NJ_SYNC();
+    NjPathB t0, t1;
+    nj_pathb_bind(t0, s, smem);
+    t1 = t0;
+    t1.IN = t0.IN + s.b_copy; t1.A = t0.A + s.b_copy; t1.G = t0.G + s.b_copy; t1.GOUT = t0.GOUT + s.b_copy;
+    int* ctl = t0.I + NJB_I_COUNT * s.P_b;
+    const int nrow = 32 * s.nw_b, rows = R * s.nw_b;
+#if defined(NJODE_HOST_SIM)
+    NJP_HACC_DECL(nt);
+    for (;;) {
+        ctl[0] = nj_atomic_inc(a.counter);
+        const int tile = ctl[0];
+        if (tile >= s.n_tiles_b) break;
+        const int ub = tile * rows, ue = ub + rows < a.b.n_units ? ub + rows : a.b.n_units;
+        nj_path_bwd_tile_pipe<RG, TR, true>(c, s, a, smem, t0, t1, njp_hacc, cta, ub, ue);
+    }
+    NJ_THREADS(tid, nt) { if (tid >= nrow) nj_path_helper_flush(c, s, NJP_HACC_OF(tid), gpart, tid - nrow, nt - nrow); }
+#else
+    // two copies of the tile loop: the helpers' 100 accumulator registers are live in their branch only, so the row
+    // warps' GEMM code does not compete with them for registers
+    if ((int)threadIdx.x >= nrow) {
+        NJP_HACC_DECL(nt);
+        for (;;) {
+            __syncthreads();
+            const int tile = ctl[0];
+            __syncthreads();
+            if (tile >= s.n_tiles_b) break;
+            const int ub = tile * rows, ue = ub + rows < a.b.n_units ? ub + rows : a.b.n_units;
+            nj_path_bwd_tile_pipe<RG, TR, false>(c, s, a, smem, t0, t1, njp_hacc, cta, ub, ue);
+        }
+        nj_path_helper_flush(c, s, njp_hacc, gpart, (int)threadIdx.x - nrow, nt - nrow);
+    } else {
+        for (;;) {
+            if (threadIdx.x == 0) ctl[0] = nj_atomic_inc(a.counter);
+            __syncthreads();
+            const int tile = ctl[0];
+            __syncthreads();
+            if (tile >= s.n_tiles_b) break;
+            const int ub = tile * rows, ue = ub + rows < a.b.n_units ? ub + rows : a.b.n_units;
+            nj_path_bwd_tile_pipe<RG, TR, true>(c, s, a, smem, t0, t1, nullptr, cta, ub, ue);
+        }
+    }
+#endif
+}
+
 template <int RG, int TR>
 NJ_HD void nj_path_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem, int cta) {
     const int nt = s.nt_b;
@@ -1359,4 +1568,545 @@ NJ_HD void nj_path_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a
     }
     float* gpart = a.partials + (size_t)cta * c.img_floats;
     NJ_THREADS(tid, nt) { nj_path_dw_flush(c, s, NJ_ACC(tid), gpart, tid, nt); }
+}
+
+// ================================================================================================
+// weight-stationary Euler steps: small whole-path batches (the reference's PhysioNet batch is 50 records)
+//
+// With at most a handful of paths per SM the warp GEMMs above leave the machine idle: one warp per path exposes every
+// instruction latency of a 3 700-step dependent chain.  Here ONE CTA of NW = ceil(widest layer / 4) warps owns the R <= 8
+// paths of a tile and all of its threads cooperate on every path:
+//   * the ODE network's weights live in REGISTERS for the whole launch: thread (warp w, lane = (oq, ksl)) holds the slice
+//     ksl (of 8) of the weight row of output o = 4 w + oq of every layer -- at most 12 floats per layer;
+//   * a layer of a step = 3 broadcast LDS.128 of the activation slice + 12 FFMA + 3 shuffles (the 8 slices of an output
+//     meet), one CTA barrier; no weight ever moves after the launch has started;
+//   * backward: dW[o][slice] += g[o] * a[slice] is thread-local (the gradient tile of a thread mirrors its weight tile,
+//     also in registers for the whole launch); the input gradient g . W is reduced over the 4 outputs of a warp by
+//     shuffles and over the warps through a partial buffer in shared memory, summed by its consumer after the barrier.
+// Jumps, the start encoder and path records stay with warp 0 on the warp GEMMs above (the other warps wait).
+// ================================================================================================
+#define NJT_MAXL 3                  // Linear layers of the ODE network
+#define NJT_SLICE 12                // floats of one k-slice: 3 float4 chunks, 8 slices -> layer inputs up to 96 wide
+#define NJT_PARTW 96
+
+// layer 0 (input width up to 96): slices of 12 floats; the other layers (hidden widths up to 64): slices of 8
+struct NjStatRegs {
+    float w0[12], w1[8], w2[8];
+    float dw0[12], dw1[8], dw2[8];
+    float b[NJT_MAXL], db[NJT_MAXL];
+};
+template <int L> struct NjStatL { static constexpr int Q = L == 0 ? 3 : 2; };     // float4 chunks per slice
+template <int L> NJ_HD float* nj_stat_w(NjStatRegs& r) { return L == 0 ? r.w0 : (L == 1 ? r.w1 : r.w2); }
+template <int L> NJ_HD const float* nj_stat_w(const NjStatRegs& r) { return L == 0 ? r.w0 : (L == 1 ? r.w1 : r.w2); }
+template <int L> NJ_HD float* nj_stat_dw(NjStatRegs& r) { return L == 0 ? r.dw0 : (L == 1 ? r.dw1 : r.dw2); }
+
+struct NjStatGeo { int n, K4[NJT_MAXL], KS[NJT_MAXL], O[NJT_MAXL]; };
+
+NJ_HD NjStatGeo nj_stat_geo(const NjCfg& c) {
+    NjStatGeo g;
+    const NjNet& N = c.net[NJODE_NET_ODE];
+    g.n = N.n;
+    for (int l = 0; l < NJT_MAXL; ++l) {
+        g.K4[l] = l < N.n ? (N.dim[l] + 3) >> 2 : 0;
+        g.KS[l] = (g.K4[l] + 7) >> 3;                  // <= 3 for layer 0, <= 2 for the others (planner)
+        g.O[l] = l < N.n ? N.dim[l + 1] : 0;
+    }
+    return g;
+}
+
+#if defined(NJODE_HOST_SIM)
+#define NJT_REGS_DECL(nt) std::vector<NjStatRegs> njt_regs_store(nt); NjStatRegs* njt_regs = njt_regs_store.data()
+#define NJT_REGS(tid) (njt_regs[tid])
+#else
+#define NJT_REGS_DECL(nt) NjStatRegs njt_regs_store; NjStatRegs* njt_regs = &njt_regs_store
+#define NJT_REGS(tid) (*njt_regs)
+#endif
+
+// weight slices of this thread from the parameter image in shared memory (rows beyond a layer's outputs: zero)
+template <int L>
+NJ_HD void nj_stat_load_layer(const NjCfg& c, const NjStatGeo& g, const float* simg, int tid, NjStatRegs& R_) {
+    const NjNet& N = c.net[NJODE_NET_ODE];
+    const int o = 4 * (tid >> 5) + ((tid & 31) >> 3), ksl = tid & 7;
+    float* w = nj_stat_w<L>(R_);
+    float* dw = nj_stat_dw<L>(R_);
+#pragma unroll
+    for (int j = 0; j < 4 * NjStatL<L>::Q; ++j) {
+        const int q = j >> 2, c4 = ksl * g.KS[L] + q;
+        float v = 0.f;
+        if (L < g.n && o < g.O[L] && q < g.KS[L] && c4 < g.K4[L]) v = simg[N.w_img[L] + o * N.ks[L] + 4 * c4 + (j & 3)];
+        w[j] = v; dw[j] = 0.f;
+    }
+    R_.b[L] = (L < g.n && o < g.O[L] && N.b_src[L] >= 0) ? simg[N.b_img[L] + o] : 0.f;
+    R_.db[L] = 0.f;
+}
+NJ_HD void nj_stat_load(const NjCfg& c, const NjStatGeo& g, const float* simg, int tid, NjStatRegs& R_) {
+    nj_stat_load_layer<0>(c, g, simg, tid, R_);
+    nj_stat_load_layer<1>(c, g, simg, tid, R_);
+    nj_stat_load_layer<2>(c, g, simg, tid, R_);
+}
+
+// partial dot product of one weight slice with the matching activation slice of a row
+template <int Q>
+NJ_HD float nj_stat_dot(const float* w, const float* in_row, int K4, int KS, int ksl) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int c4 = ksl * KS + q;
+        if (q < KS && c4 < K4) {
+            const nj_f4 a = nj_sp_ld4(nj_sp_of(in_row + 4 * c4));
+            s0 = fmaf(a.x, w[4 * q], s0); s1 = fmaf(a.y, w[4 * q + 1], s1);
+            s2 = fmaf(a.z, w[4 * q + 2], s2); s3 = fmaf(a.w, w[4 * q + 3], s3);
+        }
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// sum over the 8 k-slices of an output (lanes ksl = 0..7 of one oq group); the total is valid in the ksl == 0 lane
+template <int L>
+NJ_HD float nj_stat_sum8(NjStatRegs* regs, int tid, const float* in_row, int K4, int KS) {
+#if defined(NJODE_HOST_SIM)
+    float p[8];
+    for (int sl = 0; sl < 8; ++sl) p[sl] = nj_stat_dot<NjStatL<L>::Q>(nj_stat_w<L>(regs[tid + sl]), in_row, K4, KS, sl);
+    return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+#else
+    (void)tid;
+    float v = nj_stat_dot<NjStatL<L>::Q>(nj_stat_w<L>(*regs), in_row, K4, KS, threadIdx.x & 7);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+    return v;
+#endif
+}
+
+// one layer of the forward step over the R rows of the tile; hidden layers: out = act(. + b) with dropout marks,
+// last layer (hs != nullptr): hs[r][o] += dt * (. + b).  The layer index is a template parameter: the register arrays of
+// NjStatRegs must only ever be indexed with compile-time constants, or they end up in local memory.
+template <int l>
+NJ_HD void nj_stat_layer_fwd(const NjCfg& c, const NjStatGeo& g, NjStatRegs* regs, int tid, int R,
+                             const float* in, int in_s, float* out, int out_s, float* hs, int hs_s, float dt, const int* rk) {
+    const int lane = tid & 31, o = 4 * (tid >> 5) + (lane >> 3), ksl = lane & 7;
+#if defined(NJODE_HOST_SIM)
+    if (ksl != 0) return;
+#endif
+    const NjNet& N = c.net[NJODE_NET_ODE];
+    const bool lead = ksl == 0 && o < g.O[l];
+#if defined(NJODE_HOST_SIM)
+    const float bias = regs[tid].b[l];
+#else
+    const float bias = regs->b[l];
+#endif
+    for (int r = 0; r < R; ++r) {
+        const float sum = nj_stat_sum8<l>(regs, tid, in + (size_t)r * in_s, g.K4[l], g.KS[l]);
+        if (lead) {
+            if (hs) hs[r * hs_s + o] = fmaf(dt, sum + bias, hs[r * hs_s + o]);
+            else {
+                float v = nj_act(sum + bias, N.act[l]);
+                if (c.has_drop) {
+                    const unsigned lk = nj_layer_key((unsigned)rk[r], (unsigned)(NJODE_NET_ODE * 16 + l + 1));
+                    v = nj_keep(lk, (unsigned)o, c.thr) ? v * c.keep_scale : nj_u2f(NJ_DROPPED);
+                }
+                out[(size_t)r * out_s + o] = v;
+            }
+        }
+    }
+}
+
+// the ODE network's input rows of step k for the R rows of the tile: [tanh(last_X), tanh(h), tau, t - tau(, t)]
+// (ODEFunc.forward, NJODE/models.py:188-199); hsrc: h of the step (forward: HS, also written to h_hist; backward: h_hist)
+template <bool BWD>
+NJ_HD void nj_stat_build_in(const NjCfg& c, const NjArgs& a, int tid, int nt, int R, int k, const int* path, const float* TX, int sD,
+                            const float* tau, float* HS, int sH, float* IN, int sI, int* rk, const float* GH, float* GOUT, int sO) {
+    const int inf4 = ((c.inf + 3) >> 2) << 2;
+    const float tcur = NJ_LDG(a.b.step_t + k), dt = NJ_LDG(a.b.step_dt + k);
+    const int c_ = tid & 127, groups = nt >> 7;        // 128 threads per row; a trailing partial group stays idle
+    for (int r = tid >> 7; r < R && (tid >> 7) < groups; r += groups) {
+        const int p = path[r];
+        if (c_ < inf4) {
+            float v = 0.f;
+            if (c_ < c.d) v = TX[r * sD + c_];
+            else if (c_ < c.d + c.H) {
+                float h;
+                float* hh = (p >= 0 && a.h_hist) ? a.h_hist + ((size_t)k * a.b.B + p) * c.H + (c_ - c.d) : nullptr;
+                if (BWD) h = hh ? *hh : 0.f;
+                else { h = HS[r * sH + c_ - c.d]; if (hh) *hh = h; }
+                v = nj_tanh(h);
+            } else if (c_ < c.inf) {
+                const float t_ = tau[r];
+                if (c_ == c.d + c.H) v = t_;
+                else if (c_ == c.d + c.H + 1) v = tcur - t_;
+                else v = t_ + (tcur - t_);
+            }
+            IN[(size_t)r * sI + c_] = v;
+        }
+        if (BWD && c_ < c.H) GOUT[(size_t)r * sO + c_] = dt * GH[r * sH + c_];
+        if (c_ == 127) rk[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
+    }
+}
+
+// forward Euler step k of the tile, all threads of the CTA (n + 1 barriers)
+template <int RG, int TR>
+NJ_HD void nj_stat_fwd_step(const NjCfg& c, const NjPath& s, const NjArgs& a, const NjStatGeo& g, NjStatRegs* njt_regs,
+                            NjPathFwd<RG, TR>& f, int nt, int k) {
+    constexpr int R = RG * TR, RS = NJP_RS;
+    const float dt = NJ_LDG(a.b.step_dt + k);
+    NJ_THREADS(tid, nt) {
+        nj_stat_build_in<false>(c, a, tid, nt, R, k, f.I + NJP_I_PATH * RS, f.TX, s.sD, f.F + NJP_F_TAU * RS, f.HS, s.sH,
+                                f.w.IN, s.sI, f.w.RK, nullptr, nullptr, 0);
+    }
+    NJ_SYNC();
+    const int* rk = f.w.RK;
+    NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, f.w.IN, s.sI, f.w.A0, s.sA, nullptr, 0, 0.f, rk); }
+    NJ_SYNC();
+    if (g.n == 2) {
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, nullptr, 0, f.HS, s.sH, dt, rk); }
+        NJ_SYNC();
+    } else {
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, f.w.A1, s.sA, nullptr, 0, 0.f, rk); }
+        NJ_SYNC();
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<2>(c, g, njt_regs, tid, R, f.w.A1, s.sA, nullptr, 0, f.HS, s.sH, dt, rk); }
+        NJ_SYNC();
+    }
+}
+
+template <int RG, int TR>
+NJ_HD void nj_stat_cta_forward(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem) {
+    constexpr int R = RG * TR;
+    const int nt = 32 * s.nw_s;
+    float* simg = smem;
+    nj_stage_image(simg, a.image, c.img_floats, nt);
+    nj_zero(smem + s.f_warp0, s.f_region, nt);
+    NJ_SYNC();
+    const NjStatGeo g = nj_stat_geo(c);
+    NJT_REGS_DECL(nt);
+    NJ_THREADS(tid, nt) { nj_stat_load(c, g, simg, tid, NJT_REGS(tid)); }
+    float* reg = smem + s.f_warp0;
+    int* slot = reinterpret_cast<int*>(reg + s.f_I) + NJP_I_COUNT * NJP_RS;
+    NjPathFwd<RG, TR> f(c, s, a, reg, simg);
+    const bool rec = a.b.E > 0;
+    const int S = a.b.S;
+    for (;;) {
+        NJ_THREADS(tid, nt) { if (tid == 0) *slot = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int wt = *slot;
+        NJ_SYNC();
+        if (wt >= s.n_tiles_f) break;
+        const int ub = wt * R, ue = ub + R < a.b.n_units ? ub + R : a.b.n_units;
+        NJ_WARPS(wp, 1) { if (wp == 0) f.begin(ub, ue); }
+        NJ_SYNC();
+        int k = 0, gi = 0;
+        for (;;) {
+            const int nk = f.next_jump(gi);
+            const int kend = nk < S ? nk : S;
+            for (; k < kend; ++k) {
+                nj_stat_fwd_step<RG, TR>(c, s, a, g, njt_regs, f, nt, k);
+                if (rec) {
+                    NJ_WARPS(wp, 1) { if (wp == 0) f.record(NJ_LDG(a.b.step_event + k), NJ_EVENT_PATH_RO_BASE + (unsigned)k); }
+                    NJ_SYNC();
+                }
+            }
+            if (nk > S) break;
+            const bool any = f.any_jumps_at(nk);
+            NJ_SYNC();                            // every warp has read the cursors before warp 0 advances them
+            NJ_WARPS(wp, 1) {
+                if (wp == 0) {
+                    if (any) f.jump(nk);
+                    if (rec) f.record(NJ_LDG(a.b.jump_event + gi), NJ_EVENT_JUMP_BASE + 3u * (unsigned)gi + 2u);
+                }
+            }
+            if (rec) ++gi;
+            NJ_SYNC();
+        }
+        NJ_WARPS(wp, 1) { if (wp == 0) f.finish(); }
+        NJ_SYNC();
+    }
+}
+
+// ---- backward ----
+// sum over the 4 outputs of a warp (lanes oq = 0..3 with equal ksl); the total is valid in the oq == 0 lanes
+NJ_HD float nj_stat_sum4(float v) {
+#if !defined(NJODE_HOST_SIM)
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 16);
+#endif
+    return v;
+}
+
+// reverse of layer l for the R rows: with g[r][o] = dL/d(pre-activation output o),
+//   dW[o][slice] += g a[slice], db[o] += g               (thread-local registers)
+//   part[r][warp][k] = sum over the warp's 4 outputs of g[o] W[o][k]   (input-gradient partials, summed by the consumer)
+template <int l>
+NJ_HD void nj_stat_layer_bwd(const NjStatGeo& g, NjStatRegs* regs, int tid, int nw, int R,
+                             const float* gout, int g_s, const float* in, int in_s, float* part) {
+    const int lane = tid & 31, wq = tid >> 5, oq = lane >> 3, ksl = lane & 7, o = 4 * wq + oq;
+    const int KS = g.KS[l], K4 = g.K4[l];
+#if defined(NJODE_HOST_SIM)
+    // sequential lanes: every lane updates its own dW; the oq == 0 lane of a slice sums the four partial products
+    for (int r = 0; r < R; ++r) {
+        const float gv = o < g.O[l] ? gout[(size_t)r * g_s + o] : 0.f;
+        NjStatRegs& me = regs[tid];
+        float* dw = nj_stat_dw<l>(me);
+        for (int q = 0; q < NjStatL<l>::Q; ++q) {
+            const int c4 = ksl * KS + q;
+            if (q < KS && c4 < K4) {
+                const nj_f4 a = nj_ld4(in + (size_t)r * in_s + 4 * c4);
+                dw[4 * q] = fmaf(gv, a.x, dw[4 * q]); dw[4 * q + 1] = fmaf(gv, a.y, dw[4 * q + 1]);
+                dw[4 * q + 2] = fmaf(gv, a.z, dw[4 * q + 2]); dw[4 * q + 3] = fmaf(gv, a.w, dw[4 * q + 3]);
+            }
+        }
+        if (ksl == 0) me.db[l] += gv;
+        if (oq == 0) {
+            for (int q = 0; q < NjStatL<l>::Q; ++q) {
+                const int c4 = ksl * KS + q;
+                if (!(q < KS && c4 < K4)) continue;
+                for (int e = 0; e < 4; ++e) {
+                    float p4[4];
+                    for (int oo = 0; oo < 4; ++oo) {
+                        const int o2 = 4 * wq + oo;
+                        const float g2 = o2 < g.O[l] ? gout[(size_t)r * g_s + o2] : 0.f;
+                        p4[oo] = g2 * nj_stat_w<l>(regs[tid + 8 * oo])[4 * q + e];
+                    }
+                    part[((size_t)r * nw + wq) * NJT_PARTW + 4 * c4 + e] = (p4[0] + p4[1]) + (p4[2] + p4[3]);
+                }
+            }
+        }
+    }
+#else
+    NjStatRegs& me = *regs;
+    float* dw = nj_stat_dw<l>(me);
+    const float* w = nj_stat_w<l>(me);
+    for (int r = 0; r < R; ++r) {
+        const float gv = o < g.O[l] ? gout[(size_t)r * g_s + o] : 0.f;
+#pragma unroll
+        for (int q = 0; q < NjStatL<l>::Q; ++q) {
+            const int c4 = ksl * KS + q;
+            if (q < KS && c4 < K4) {
+                const nj_f4 a = nj_sp_ld4(nj_sp_of(in + (size_t)r * in_s + 4 * c4));
+                dw[4 * q] = fmaf(gv, a.x, dw[4 * q]); dw[4 * q + 1] = fmaf(gv, a.y, dw[4 * q + 1]);
+                dw[4 * q + 2] = fmaf(gv, a.z, dw[4 * q + 2]); dw[4 * q + 3] = fmaf(gv, a.w, dw[4 * q + 3]);
+            }
+        }
+        if (ksl == 0) me.db[l] += gv;
+#pragma unroll
+        for (int q = 0; q < NjStatL<l>::Q; ++q) {
+            if (q < KS) {                     // uniform over the warp: every lane takes part in the shuffles
+                nj_f4 v;
+                v.x = nj_stat_sum4(gv * w[4 * q]); v.y = nj_stat_sum4(gv * w[4 * q + 1]);
+                v.z = nj_stat_sum4(gv * w[4 * q + 2]); v.w = nj_stat_sum4(gv * w[4 * q + 3]);
+                const int c4 = ksl * KS + q;
+                if (oq == 0 && c4 < K4) nj_st4(part + ((size_t)r * nw + wq) * NJT_PARTW + 4 * c4, v);
+            }
+        }
+    }
+#endif
+}
+
+// consumer of the partials of layer l (l >= 1): g_prev[r][o'] = (sum over the warps) * act'(a[r][o']) for the hidden
+// activation a = output of layer l - 1; written by the ksl == 0 lane of output o', read by its 8 lanes after a warp sync
+NJ_HD void nj_stat_consume_hidden(const NjCfg& c, const NjStatGeo& g, int tid, int nw, int l, int R, const float* part,
+                                  const float* act, int a_s, float* gprev, int gp_s) {
+    const int lane = tid & 31, o = 4 * (tid >> 5) + (lane >> 3), ksl = lane & 7;
+    const NjNet& N = c.net[NJODE_NET_ODE];
+    if (ksl != 0 || o >= g.O[l - 1]) return;
+    for (int r = 0; r < R; ++r) {
+        float v = 0.f;
+        for (int wq = 0; wq < nw; ++wq) v += part[((size_t)r * nw + wq) * NJT_PARTW + o];
+        float a_ = act[(size_t)r * a_s + o];
+        if (c.has_drop) {
+            if (nj_f2u(a_) == NJ_DROPPED) v = 0.f;
+            else { a_ *= c.one_minus_p; v *= c.keep_scale; }
+        }
+        if (N.act[l - 1] == NJODE_ACT_TANH) v *= (1.f - a_ * a_);
+        else if (N.act[l - 1] == NJODE_ACT_RELU) v = a_ > 0.f ? v : 0.f;
+        gprev[(size_t)r * gp_s + o] = v;
+    }
+}
+
+// reverse Euler step k of the tile, all threads of the CTA (2n + 2 barriers)
+template <int RG, int TR>
+NJ_HD void nj_stat_bwd_step(const NjCfg& c, const NjPath& s, const NjArgs& a, const NjStatGeo& g, NjStatRegs* njt_regs,
+                            const NjPathB& t, float* part0, float* part1, int nt, int k) {
+    constexpr int R = RG * TR;
+    const int P = s.P_b, nw = s.nw_s, wa = P * s.sA;
+    NJ_THREADS(tid, nt) {
+        nj_stat_build_in<true>(c, a, tid, nt, R, k, t.I + NJB_I_PATH * P, t.TX, s.sD, t.F + NJP_F_TAU * P, nullptr, s.sH,
+                               t.IN, s.sI, t.I + NJB_I_RK * P, t.GH, t.GOUT, s.sO);
+    }
+    NJ_SYNC();
+    // recompute the hidden activations (kept with their dropout marks)
+    int* rk = t.I + NJB_I_RK * P;
+    float* A0 = t.A; float* A1 = t.A + wa; float* G0 = t.G; float* G1 = t.G + wa;
+    NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, t.IN, s.sI, A0, s.sA, nullptr, 0, 0.f, rk); }
+    NJ_SYNC();
+    if (g.n == 3) {
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, A0, s.sA, A1, s.sA, nullptr, 0, 0.f, rk); }
+        NJ_SYNC();
+    }
+    // layers in reverse: dW in registers, input-gradient partials through shared memory (two buffers in turn: a warp may
+    // still sum the previous layer's partials while another one writes the next)
+    float* part;
+    if (g.n == 3) {
+        NJ_THREADS(tid, nt) { nj_stat_layer_bwd<2>(g, njt_regs, tid, nw, R, t.GOUT, s.sO, A1, s.sA, part0); }
+        NJ_SYNC();
+        NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 2, R, part0, A1, s.sA, G1, s.sA); }
+        NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
+        NJ_THREADS(tid, nt) { nj_stat_layer_bwd<1>(g, njt_regs, tid, nw, R, G1, s.sA, A0, s.sA, part1); }
+        NJ_SYNC();
+        NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 1, R, part1, A0, s.sA, G0, s.sA); }
+        NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
+        NJ_THREADS(tid, nt) { nj_stat_layer_bwd<0>(g, njt_regs, tid, nw, R, G0, s.sA, t.IN, s.sI, part0); }
+        NJ_SYNC();
+        part = part1;
+    } else {
+        NJ_THREADS(tid, nt) { nj_stat_layer_bwd<1>(g, njt_regs, tid, nw, R, t.GOUT, s.sO, A0, s.sA, part0); }
+        NJ_SYNC();
+        NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 1, R, part0, A0, s.sA, G0, s.sA); }
+        NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
+        NJ_THREADS(tid, nt) { nj_stat_layer_bwd<0>(g, njt_regs, tid, nw, R, G0, s.sA, t.IN, s.sI, part1); }
+        NJ_SYNC();
+        part = part0;
+    }
+    // the partials of layer 0 -> adjoint of h (and of last_X for the masked model)
+    const float* pl = part == part0 ? part1 : part0;
+    NJ_THREADS(tid, nt) {
+        const int lane = tid & 31, o = 4 * (tid >> 5) + (lane >> 3), ksl = lane & 7;
+        if (ksl == 0) {
+            for (int r = 0; r < R; ++r) {
+                if (t.I[NJB_I_PATH * P + r] < 0) continue;
+                if (o < c.H) {
+                    float v = 0.f;
+                    for (int wq = 0; wq < nw; ++wq) v += pl[((size_t)r * nw + wq) * NJT_PARTW + c.d + o];
+                    const float th = t.IN[(size_t)r * s.sI + c.d + o];
+                    t.GH[r * s.sH + o] += v * (1.f - th * th);
+                }
+                if (c.masked && o < c.d) {
+                    float v = 0.f;
+                    for (int wq = 0; wq < nw; ++wq) v += pl[((size_t)r * nw + wq) * NJT_PARTW + o];
+                    const float tx = t.IN[(size_t)r * s.sI + o];
+                    t.GX[r * s.sD + o] += v * (1.f - tx * tx);
+                }
+            }
+        }
+    }
+    NJ_SYNC();
+}
+
+// the register tiles of the ODE network's gradient -> this CTA's partial image (every element has exactly one owner)
+template <int L>
+NJ_HD void nj_stat_flush_layer(const NjCfg& c, const NjStatGeo& g, NjStatRegs& R_, int tid, float* gpart) {
+    const NjNet& N = c.net[NJODE_NET_ODE];
+    const int o = 4 * (tid >> 5) + ((tid & 31) >> 3), ksl = tid & 7;
+    if (L >= g.n || o >= g.O[L]) return;
+    const float* dw = nj_stat_dw<L>(R_);
+#pragma unroll
+    for (int j = 0; j < 4 * NjStatL<L>::Q; ++j) {
+        const int q = j >> 2, c4 = ksl * g.KS[L] + q;
+        if (q < g.KS[L] && c4 < g.K4[L]) gpart[N.w_img[L] + o * N.ks[L] + 4 * c4 + (j & 3)] = dw[j];
+    }
+    if (ksl == 0 && N.b_src[L] >= 0) gpart[N.b_img[L] + o] = R_.db[L];
+}
+NJ_HD void nj_stat_flush(const NjCfg& c, const NjStatGeo& g, NjStatRegs& R_, int tid, float* gpart) {
+    nj_stat_flush_layer<0>(c, g, R_, tid, gpart);
+    nj_stat_flush_layer<1>(c, g, R_, tid, gpart);
+    nj_stat_flush_layer<2>(c, g, R_, tid, gpart);
+}
+
+// jump-network dW phase of the weight-stationary kernel: every tile goes through the partial image (no register tiles:
+// the registers hold the ODE network; jumps are ~2 % of the steps)
+NJ_HDN void nj_stat_dw(const NjCfg* cp, const NjPath* sp, const NjPathB* tp, int netid, float* gpart, int tid, int nt, int Pt,
+                       const int* msk, int R) {
+    const NjCfg& c = *cp; const NjPath& s = *sp; const NjPathB& t = *tp;
+    for (int T = tid; T < s.tiles_total; T += nt) {
+        int l, og, kg;
+        if (!nj_path_tile_decode(c, s, netid, T, l, og, kg)) continue;
+        float q[20];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) q[i] = 0.f;
+        nj_path_dw_rows(c, s, t, netid, l, og, kg, Pt, msk, R, q);
+        nj_seg_tile_store(c, netid, l, og, kg, q, gpart, true);
+    }
+}
+
+template <int RG, int TR>
+NJ_HD void nj_stat_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem, int cta) {
+    constexpr int R = RG * TR;
+    const int nt = 32 * s.nw_s, P = s.P_b;
+    nj_stage_image(smem, a.image, c.img_floats, nt);
+    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    nj_zero(gpart, c.img_floats, nt);
+    NJ_SYNC();
+    NjPathB t;
+    nj_pathb_bind(t, s, smem);
+    const NjStatGeo g = nj_stat_geo(c);
+    NJT_REGS_DECL(nt);
+    NJ_THREADS(tid, nt) { nj_stat_load(c, g, smem, tid, NJT_REGS(tid)); }
+    float* part0 = smem + s.b_PART;
+    float* part1 = part0 + (size_t)R * s.nw_s * NJT_PARTW;
+    const NjPathBwd<RG, TR> B(c, s, a, t, smem);
+    int* ctl = t.I + NJB_I_COUNT * P;
+    for (;;) {
+        NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int tile = ctl[0];
+        NJ_SYNC();
+        if (tile >= s.n_tiles_b) break;
+        const int ub = tile * R, ue = ub + R < a.b.n_units ? ub + R : a.b.n_units;
+        NJ_THREADS(tid, nt) {
+            if (tid < R) {
+                const int u = ub + tid;
+                if (u < ue) {
+                    const int32_t* dsc = a.b.unit_desc + (size_t)u * 6;
+                    t.I[NJB_I_PATH * P + tid] = dsc[0]; t.I[NJB_I_C0 * P + tid] = dsc[3]; t.I[NJB_I_CUR * P + tid] = dsc[4];
+                } else { t.I[NJB_I_PATH * P + tid] = -1; t.I[NJB_I_C0 * P + tid] = 0; t.I[NJB_I_CUR * P + tid] = 0; }
+                t.I[NJB_I_ACT * P + tid] = 0;
+                B.set_prev(tid);
+            }
+        }
+        NJ_SYNC();
+        NJ_WARPS(wp, 1) {
+            if (wp == 0) {
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int p = t.I[NJB_I_PATH * P + er];
+                    const float* ght = (p >= 0 && a.grad_hT) ? a.grad_hT + (size_t)p * c.H : nullptr;
+                    for (int c_ = ec0; c_ < c.H; c_ += LPR) t.GH[er * s.sH + c_] = ght ? NJ_LDG(ght + c_) : 0.f;
+                    for (int c_ = ec0; c_ < c.d; c_ += LPR) t.GX[er * s.sD + c_] = 0.f;
+                    B.load_state(0, lane);
+                }
+                NJ_SYNCWARP();
+            }
+        }
+        NJ_SYNC();
+        int nk = nj_pathb_next(t, P, R);
+        for (int k = a.b.S; ; --k) {
+            if (nk == k) {
+                NJ_WARPS(wp, 1) { if (wp == 0) B.jump_p1(0, 0, k); }
+                NJ_SYNC();
+                NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_RO, gpart, tid, nt, R, t.MSK, R); }
+                NJ_SYNC();
+                NJ_WARPS(wp, 1) { if (wp == 0) B.jump_p2(0, 0); }
+                NJ_SYNC();
+                NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, c.use_rnn ? NJODE_NET_GRU_HH : NJODE_NET_ENC, gpart, tid, nt, R, t.MSK, R); }
+                NJ_SYNC();
+                if (c.use_rnn) {
+                    NJ_WARPS(wp, 1) { if (wp == 0) B.jump_p2b(0, 0); }
+                    NJ_SYNC();
+                    NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_GRU_IH, gpart, tid, nt, R, t.MSK, R); }
+                    NJ_SYNC();
+                }
+                NJ_WARPS(wp, 1) { if (wp == 0) B.jump_p3(0, 0); }
+                NJ_SYNC();
+                NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_RO, gpart, tid, nt, R, t.MSK, R); }
+                NJ_SYNC();
+                nk = nj_pathb_next(t, P, R);
+            }
+            if (k == 0) break;
+            nj_stat_bwd_step<RG, TR>(c, s, a, g, njt_regs, t, part0, part1, nt, k - 1);
+        }
+        NJ_WARPS(wp, 1) { if (wp == 0) B.start_local(0); }
+        NJ_SYNC();
+        NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_ENC, gpart, tid, nt, R, nullptr, R); }
+        NJ_SYNC();
+    }
+    NJ_THREADS(tid, nt) { nj_stat_flush(c, g, NJT_REGS(tid), tid, gpart); }
 }

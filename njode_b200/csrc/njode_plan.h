@@ -458,19 +458,44 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
     s.sO = nj_stride_act(maxlast);
     s.sH = (c.H + 3) & ~3; s.sD = (std::max(c.d, c.dout) + 3) & ~3; s.s3 = (3 * c.H + 3) & ~3;
     s.nA = std::max(1, maxn - 1);
+    const char* frw = getenv("NJODE_PATH_R");                 // tests: rows per warp (1, 2, 4, 8)
+    const int force_r = frw ? atoi(frw) : 0;
+    auto shape = [](int R, int& rg, int& tr) { rg = R >= 4 ? 4 : R; tr = R >= 8 ? 2 : 1; };
+    // ---- weight-stationary Euler steps: batches of at most 8 paths per SM whose ODE network fits the register tiles ----
+    int stat_R = 0;
+    {
+        const NjNet& O = c.net[NJODE_NET_ODE];
+        const char* ns = getenv("NJODE_NO_STAT");
+        bool ok = !(ns && atoi(ns)) && (O.n == 2 || O.n == 3);
+        int maxo = std::max(c.H, c.masked ? c.d : 0);
+        for (int l = 0; l < O.n && ok; ++l) {
+            if (O.dim[l] > (l == 0 ? 96 : 64)) ok = false;      // register slices: 8 x 12 floats (layer 0), 8 x 8 (the others)
+            maxo = std::max(maxo, O.dim[l + 1]);
+        }
+        const int nw = std::max(4, (maxo + 3) / 4);
+        if (nw > 13) ok = false;                              // launch bounds: 416 threads
+        if (ok) {
+            for (int cand = 1; cand <= 8 && !stat_R; cand *= 2)
+                if ((n + cand - 1) / cand <= num_sms) stat_R = cand;
+            if (force_r) stat_R = force_r;
+            const char* fs = getenv("NJODE_FORCE_STAT");      // tests: take the stationary kernels whatever the batch size
+            if (!stat_R && fs && atoi(fs)) stat_R = 8;
+        }
+        if (stat_R) { s.stat = 1; s.nw_s = nw; }
+    }
+    // dW tiles of the thread-owned 4x4 scheme; the stationary kernels keep the ODE network's gradient in their own
+    // register tiles, so the ODE network has no tiles there
     static const int order[NJODE_NUM_NETS] = {NJODE_NET_ODE, NJODE_NET_RO, NJODE_NET_ENC, NJODE_NET_GRU_HH, NJODE_NET_GRU_IH};
     int tiles = 0;
     for (int oi = 0; oi < NJODE_NUM_NETS; ++oi) {
         const NjNet& N = c.net[order[oi]];
         for (int l = 0; l < NJODE_MAX_LINEAR; ++l) {
+            if (s.stat && order[oi] == NJODE_NET_ODE) { s.tile_base[order[oi]][l] = 0x3FFFFFFF; continue; }
             s.tile_base[order[oi]][l] = tiles;
             if (l < N.n) tiles += ((N.dim[l] + 3) / 4) * ((N.dim[l + 1] + 3) / 4);
         }
     }
     s.tiles_total = tiles;
-    const char* frw = getenv("NJODE_PATH_R");                 // tests: rows per warp (1, 2, 4, 8)
-    const int force_r = frw ? atoi(frw) : 0;
-    auto shape = [](int R, int& rg, int& tr) { rg = R >= 4 ? 4 : R; tr = R >= 8 ? 2 : 1; };
     // ---- forward: per-warp regions ----
     {
         auto region = [&](int R) {
@@ -498,6 +523,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         for (int cand = 1; cand <= 8; cand *= 2)
             if ((n + cand - 1) / cand <= num_sms * 12) { R = cand; break; }
         if (force_r) R = force_r;
+        if (s.stat) R = stat_R;
         shape(R, s.rg_f, s.tr_f);
         s.f_region = region(R);
         s.f_warp0 = c.img_floats;
@@ -507,6 +533,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
         if (!nw) return;
         nw = std::max(1, std::min(nw, (s.n_tiles_f + num_sms - 1) / num_sms));
+        if (s.stat) nw = 1;                                   // one tile per CTA at a time, all warps on it
         s.nw_f = nw;
         s.f_smem_floats = c.img_floats + nw * s.f_region;
         out.path_grid_f = std::max(1, std::min((s.n_tiles_f + nw - 1) / nw, num_sms));
@@ -520,6 +547,8 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             s.b_A = o; o += s.nA * P * s.sA;
             s.b_G = o; o += s.nA * P * s.sA;
             s.b_GOUT = o; o += P * s.sO;
+            s.b_copy = o - s.b_IN;                            // pipelined backward: a second set of the four operand buffers
+            if (s.pipe) o += s.b_copy;
             s.b_GZ = o; o += P * s.sI;
             s.b_OUT = o; o += P * s.sO;
             s.b_GH = o; o += P * s.sH;
@@ -536,6 +565,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             s.b_MM = o; o += P * s.sD;
             s.b_GI = o; if (c.use_rnn) o += P * s.s3;
             s.b_GHH = o; if (c.use_rnn) o += P * s.s3;
+            s.b_PART = o; if (s.stat) o += 2 * P * s.nw_s * NJT_PARTW;
             s.b_F = o; o += NJP_F_COUNT * P;
             s.b_I = o; o += NJB_I_COUNT * P + 4 + nw + 4;
             return (o + 3) & ~3;
@@ -546,6 +576,17 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             if ((P_want + cand - 1) / cand <= 12) { R = cand; break; }
         if (force_r) R = force_r;
         int nw = std::max(1, std::min(12, (P_want + R - 1) / R));
+        if (s.stat) { R = stat_R; nw = 1; }
+        // pipelined dW: enough helper warps to hold the ODE network's tiles in their registers
+        const int ode_tiles = s.tile_base[NJODE_NET_RO][0];
+        const int helpers_min = std::max(3, (ode_tiles + 32 * NJP_HSLOTS - 1) / (32 * NJP_HSLOTS));
+        const char* np_ = getenv("NJODE_NO_PIPE");
+        if (!s.stat && !(np_ && atoi(np_)) && helpers_min <= 8) {
+            // rows per warp so that the row warps leave room for the helpers
+            while ((P_want + R - 1) / R > 12 - helpers_min && R < 8 && !force_r) R *= 2;
+            nw = std::max(1, std::min(12 - helpers_min, (P_want + R - 1) / R));
+            s.pipe = 1;
+        }
         int fl = 0;
         for (; nw >= 1; --nw) {
             fl = layout(R * nw, nw);
@@ -557,6 +598,8 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         const int wtot = std::max(nw, std::min(12, (tiles + 32 * NJ_SEG_NT_MAX - 1) / (32 * NJ_SEG_NT_MAX)));
         s.nt_b = 32 * wtot;
         s.nt_slots = std::min(NJ_SEG_NT_MAX, (tiles + s.nt_b - 1) / s.nt_b);
+        if (s.stat) { s.nt_b = 32 * s.nw_s; s.nt_slots = 0; }
+        if (s.pipe) { s.nt_b = 32 * 12; s.nt_slots = 0; }
         s.n_tiles_b = (n + s.P_b - 1) / s.P_b;
         out.path_grid_b = std::max(1, std::min(s.n_tiles_b, num_sms));
         out.path_smem_b_bytes = (size_t)s.b_smem_floats * 4;

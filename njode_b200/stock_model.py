@@ -415,16 +415,25 @@ class DeviceDataset:
                 cols.append(torch.pow(X.double(), float(name.split("-")[1])).float())
         return torch.cat(cols, dim=1)
 
-    def collate(self, sel, func_names=None):
+    def collate(self, sel, func_names=None, on_device=False):
         """the reference's collate dict (NJODE/data_utils.py:311-315); ``func_names`` = the 'func_appl_X' option of
-        train.py (e.g. ["power-2"]: the model then also learns the conditional second moment)"""
+        train.py (e.g. ["power-2"]: the model then also learns the conditional second moment).
+
+        ``on_device=True``: ``time_ptr`` / ``obs_idx`` / ``n_obs_ot`` stay device tensors (int32) that
+        ``NJODE.forward`` / ``prepare_batch`` take as they are -- the only device->host traffic of the batch is the
+        8-byte (K, N) pair, plus the K grid indices when some grid time has no observation in the batch (``times`` is
+        host data by contract: the Euler schedule is built from it in float64 on the host)."""
         o = self.collate_device(sel)
         o["X"] = self._apply_functions(o["X"], func_names)
         o["start_X"] = self._apply_functions(o["start_X"], func_names)
         K, N = (int(v) for v in o["counts"].cpu())
-        tidx = o["time_idx"][:K].cpu().numpy()
         # current_time += dt once per grid step in float64 (data_utils.py:293-296)
         grid_t = np.cumsum(np.full(self.nb_steps, self.dt, dtype=np.float64))
+        if on_device:
+            times = grid_t if K == self.nb_steps else grid_t[o["time_idx"][:K].cpu().numpy() - 1]
+            return {"times": times, "time_ptr": o["time_ptr"][:K + 1], "obs_idx": o["obs_idx"][:N], "start_X": o["start_X"],
+                    "n_obs_ot": o["n_obs_ot"], "X": o["X"][:N], "true_paths": None, "observed_dates": None}
+        tidx = o["time_idx"][:K].cpu().numpy()
         return {"times": grid_t[tidx - 1], "time_ptr": o["time_ptr"][:K + 1].cpu().numpy().astype(np.int64),
                 "obs_idx": o["obs_idx"][:N].cpu().to(torch.int64), "start_X": o["start_X"],
                 "n_obs_ot": o["n_obs_ot"].cpu().to(torch.int64), "X": o["X"][:N],

@@ -88,7 +88,7 @@ def run(sde="BlackScholes", epochs=20, paths=20000, steps=100, batch=200, seed=0
         order = train_idx[np.random.default_rng(1000 + epoch).permutation(len(train_idx))]
         t0 = time.perf_counter()
         for i in range(0, len(order), batch):
-            b = ds.collate(np.sort(order[i:i + batch]))
+            b = ds.collate(np.sort(order[i:i + batch]), on_device=True)
             opt.zero_grad()
             hT, loss = model(b["times"], b["time_ptr"], b["X"], b["obs_idx"], dt, T, b["start_X"], b["n_obs_ot"])
             loss.backward()
@@ -101,7 +101,7 @@ def run(sde="BlackScholes", epochs=20, paths=20000, steps=100, batch=200, seed=0
             _, vloss = model(vb["times"], vb["time_ptr"], vb["X"], vb["obs_idx"], dt, T, vb["start_X"], vb["n_obs_ot"])
         eval_s = time.perf_counter() - t0
         model.weight_decay_step()
-        rec = {"epoch": epoch, "train_time_s": train_s, "eval_time_s": eval_s, "train_loss": float(loss), "eval_loss": float(vloss),
+        rec = {"epoch": epoch, "train_time_s": train_s, "eval_time_s": eval_s, "train_loss": float(loss.detach()), "eval_loss": float(vloss),
                "optimal_eval_loss": opt_loss, "ratio": float(vloss) / opt_loss, "path": model.last_forward_path}
         if sde == "BlackScholes" and d == 1 and epoch in REF_CURVE:
             rec["reference_eval_loss"], rec["reference_optimal"] = REF_CURVE[epoch]

@@ -25,8 +25,8 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
     const char* fp = getenv("NJODE_FORCE_TILE");
     if (!nj_plan_all(*m, *b, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
     if (getenv("NJODE_DEBUG_PLAN"))
-        fprintf(stderr, "[plan] units %d kind %d E %d -> seg %d path %d (fwd rg %d tr %d nw %d | bwd rg %d tr %d nw %d nt %d P %d slots %d tiles %d)\n",
-                b->n_units, b->unit_kind, b->E, out.seg.ok, out.path.ok, out.path.rg_f, out.path.tr_f, out.path.nw_f, out.path.rg_b,
+        fprintf(stderr, "[plan] units %d kind %d E %d -> seg %d path %d stat %d nw_s %d pipe %d (fwd rg %d tr %d nw %d | bwd rg %d tr %d nw %d nt %d P %d slots %d tiles %d)\n",
+                b->n_units, b->unit_kind, b->E, out.seg.ok, out.path.ok, out.path.stat, out.path.nw_s, out.path.pipe, out.path.rg_f, out.path.tr_f, out.path.nw_f, out.path.rg_b,
                 out.path.tr_b, out.path.nw_b, out.path.nt_b, out.path.P_b, out.path.nt_slots, out.path.tiles_total);
     const size_t cap = (size_t)kSimSMs * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
@@ -94,7 +94,13 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
         for (int cta = 0; cta < pl.path_grid_f; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
             if (cta == 0) *a.counter = 0;
-            if (pl.path.rg_f == 1) nj_path_cta_forward<1, 1>(pl.fwd, pl.path, a, smem.data());
+            if (pl.path.stat) {
+                if (pl.path.rg_f == 1) nj_stat_cta_forward<1, 1>(pl.fwd, pl.path, a, smem.data());
+                else if (pl.path.rg_f == 2) nj_stat_cta_forward<2, 1>(pl.fwd, pl.path, a, smem.data());
+                else if (pl.path.tr_f == 1) nj_stat_cta_forward<4, 1>(pl.fwd, pl.path, a, smem.data());
+                else nj_stat_cta_forward<4, 2>(pl.fwd, pl.path, a, smem.data());
+            }
+            else if (pl.path.rg_f == 1) nj_path_cta_forward<1, 1>(pl.fwd, pl.path, a, smem.data());
             else if (pl.path.rg_f == 2) nj_path_cta_forward<2, 1>(pl.fwd, pl.path, a, smem.data());
             else if (pl.path.tr_f == 1) nj_path_cta_forward<4, 1>(pl.fwd, pl.path, a, smem.data());
             else nj_path_cta_forward<4, 2>(pl.fwd, pl.path, a, smem.data());
@@ -138,7 +144,19 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         for (int cta = 0; cta < pl.path_grid_b; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
             if (cta == 0) *a.counter = 0;
-            if (pl.path.rg_b == 1) nj_path_cta_backward<1, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+            if (pl.path.stat) {
+                if (pl.path.rg_b == 1) nj_stat_cta_backward<1, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+                else if (pl.path.rg_b == 2) nj_stat_cta_backward<2, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+                else if (pl.path.tr_b == 1) nj_stat_cta_backward<4, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+                else nj_stat_cta_backward<4, 2>(pl.bwd, pl.path, a, smem.data(), cta);
+            }
+            else if (pl.path.pipe) {
+                if (pl.path.rg_b == 1) nj_path_cta_backward_pipe<1, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+                else if (pl.path.rg_b == 2) nj_path_cta_backward_pipe<2, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+                else if (pl.path.tr_b == 1) nj_path_cta_backward_pipe<4, 1>(pl.bwd, pl.path, a, smem.data(), cta);
+                else nj_path_cta_backward_pipe<4, 2>(pl.bwd, pl.path, a, smem.data(), cta);
+            }
+            else if (pl.path.rg_b == 1) nj_path_cta_backward<1, 1>(pl.bwd, pl.path, a, smem.data(), cta);
             else if (pl.path.rg_b == 2) nj_path_cta_backward<2, 1>(pl.bwd, pl.path, a, smem.data(), cta);
             else if (pl.path.tr_b == 1) nj_path_cta_backward<4, 1>(pl.bwd, pl.path, a, smem.data(), cta);
             else nj_path_cta_backward<4, 2>(pl.bwd, pl.path, a, smem.data(), cta);

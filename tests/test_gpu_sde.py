@@ -176,3 +176,24 @@ def test_cond_exp_kernel_matches_the_reference_fixture(name):
     got = smodel.compute_cond_exp_device(pb, d).cpu().numpy()
     assert np.array_equal(np.asarray(pb.sched.path_t, dtype=np.float64), g("path_t"))
     np.testing.assert_allclose(got, g("path_y"), rtol=2e-6, atol=1e-7)
+
+
+def test_device_collated_batch_needs_no_host_round_trip():
+    """f1: DeviceDataset.collate(on_device=True) hands device index arrays (time_ptr, obs_idx, n_obs_ot) straight to
+    NJODE.forward; same loss / hT as the host-index route bit for bit, same gradients up to the summation order (the
+    two index builders order units of equal length differently)"""
+    hp = dict(HP, nb_paths=3000, dimension=2, S0=[1.0, 1.5], nb_steps=60, obs_perc=0.1)
+    ds = stock_model.DeviceDataset("BlackScholes", hp, seed=11)
+    sel = np.arange(500, 2500)
+    outs = []
+    for on_device in (False, True):
+        b = ds.collate(sel, on_device=on_device)
+        if on_device:
+            assert all(b[k].device.type == "cuda" for k in ("time_ptr", "obs_idx", "n_obs_ot", "X", "start_X"))
+        torch.manual_seed(0)
+        m = models.NJODE(**cases.demo_cfg(input_size=2, output_size=2)).to("cuda:0").eval()
+        hT, loss = m(b["times"], b["time_ptr"], b["X"], b["obs_idx"], ds.dt, 1.0, b["start_X"], b["n_obs_ot"])
+        loss.backward()
+        outs.append((float(loss.detach()), hT.detach().cpu().numpy(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]).cpu().numpy()))
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-6 * np.abs(outs[1][2]).max())

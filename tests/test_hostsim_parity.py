@@ -31,6 +31,9 @@ def sim_runner():
     os.environ.pop("NJODE_SEG_LOW", None)
     os.environ.pop("NJODE_NO_PATH", None)
     os.environ.pop("NJODE_PATH_R", None)
+    os.environ.pop("NJODE_NO_STAT", None)
+    os.environ.pop("NJODE_NO_PIPE", None)
+    os.environ.pop("NJODE_SIM_SMS", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -245,27 +248,46 @@ def test_backward_after_a_parameter_update_raises():
 
 
 # ---- whole-path units on the warp GEMMs (njode_path.cuh): every tile shape the planner can pick ----
+STAT = pytest.mark.parametrize("stat", ["warp-gemm", "warp-gemm-pipelined", "weight-stationary"])
+
+
+def _pick(stat):
+    """small batches take the weight-stationary Euler steps (ODE weights in registers, all warps of a CTA on one tile);
+    NJODE_NO_STAT keeps them on the warp-GEMM path kernels that serve the larger batches, whose backward runs the ODE
+    network's dW phase on helper warps concurrently with the row warps' next step unless NJODE_NO_PIPE is set"""
+    if stat != "weight-stationary":
+        os.environ["NJODE_NO_STAT"] = "1"
+    if stat == "warp-gemm":
+        os.environ["NJODE_NO_PIPE"] = "1"
+
+
+@STAT
 @pytest.mark.parametrize("rows", [1, 2, 4, 8])
 @pytest.mark.parametrize("name", ["masked_small", "gru_demo", "gru_masked", "gru_d3_nores"])
-def test_path_kernels_every_tile_shape(name, rows):
+def test_path_kernels_every_tile_shape(name, rows, stat):
     """rows per warp 1 / 2 (split reduction dimension, partial sums meet in shuffles), 4 and 8: same loss, hT, gradients
     (with a gradient flowing into hT) and recorded paths as the reference"""
+    _pick(stat)
     os.environ["NJODE_PATH_R"] = str(rows)
     parity_util.check_training_call(name, "cpu", with_hT_grad=True)
     parity_util.check_training_call(name, "cpu")
     parity_util.check_path_call(name, "cpu")
 
 
+@STAT
 @pytest.mark.parametrize("rows", [1, 2, 4, 8])
 @pytest.mark.parametrize("name", ["bs_ckpt1", "curt_nobias_relu", "res_case2", "easy_w07_nores"])
-def test_path_kernels_record_paths_of_the_non_masked_model(name, rows):
+def test_path_kernels_record_paths_of_the_non_masked_model(name, rows, stat):
     """return_path / until_T calls of the non-masked model (evaluate, get_pred) are whole-path units too"""
+    _pick(stat)
     os.environ["NJODE_PATH_R"] = str(rows)
     parity_util.check_path_call(name, "cpu")
 
 
+@STAT
 @pytest.mark.parametrize("rows", [1, 2, 4, 8])
-def test_path_kernels_train_mode_dropout(rows):
+def test_path_kernels_train_mode_dropout(rows, stat):
+    _pick(stat)
     os.environ["NJODE_PATH_R"] = str(rows)
     cfg = dict(cases.CONFIGS["masked_small"], dropout_rate=0.25)
     batch = cases.irregular_batch(11, 5, 10, seed=21, masked=True, times_f32=True)
@@ -279,3 +301,13 @@ def test_path_kernels_physionet_shape():
     """d = H = 41 masked, 2x50 nets, float32 times, several waves of tiles per CTA on the 4-SM simulation"""
     batch = cases.irregular_batch(70, 41, 30, seed=7, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.2, feat_prob=0.12)
     parity_util.check_against_oracle(cases.CONFIGS["masked_physio"], batch, 0.01, 1 + 1e-12, seed=3, device="cpu", grad_hT=True)
+
+
+@pytest.mark.parametrize("B", [50, 300])
+def test_weight_stationary_kernels_physionet_shape_with_the_b200_launch_plan(B):
+    """the reference's PhysioNet batch of 50 records (one path per CTA) and 300 records (tiles of 4 rows... on 148 SMs:
+    2 rows per CTA) with the launch plan of a 148-SM device: d = H = 41 masked, 2x50 nets -> 13 warps per CTA"""
+    os.environ["NJODE_SIM_SMS"] = "148"
+    batch = cases.irregular_batch(B, 41, 12, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
+    cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 12, 1 + 1e-12, seed=5, device="cpu", train=True, grad_hT=True)
