@@ -546,6 +546,31 @@ def measure_b200(ctx, wl_name, wl, steps, warmup, sample_clocks=True):
     kname_f = (lib.njode_last_kernel(0) or b"").decode()
     kname_b = (lib.njode_last_kernel(1) or b"").decode()
 
+    # ---- the same step with the backward in recompute mode (segment kernels): nothing saved by the forward pass -----
+    recompute = None
+    if kname_b.startswith("nj_seg_bwd"):
+        keep_mode = model.recompute
+        model.recompute = "on"
+        for _ in range(3):
+            step_resident()
+        torch.cuda.synchronize()
+        ctx.barrier()
+        n_rc = max(3, min(steps, 10))
+        evr = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_rc)]
+        for i in range(n_rc):
+            ctx.flush()
+            evr[i][0].record()
+            step_resident()
+            evr[i][1].record()
+        torch.cuda.synchronize()
+        rc_ms = ctx.max_over_ranks(float(sum(a.elapsed_time(b_) for a, b_ in evr))) / n_rc
+        recompute = {"ms_per_step": rc_ms, "value": units_per_step / (rc_ms * 1e-3), "saved_bytes_per_step": 0,
+                     "history_bytes_per_step_without": 4 * (S * B * wl["H"] + pb.N * (wl["H"] + wl["d"])),
+                     "note": "NJODE.recompute = 'on': the backward recomputes every segment from its checkpoint at the "
+                             "observation time; default 'auto' keeps the [S, B, H] history up to 256 MiB"}
+        model.recompute = keep_mode
+        step_resident()
+
     # ---- end-to-end arm: public API, host tensors ---------------------------------------------
     model.output_device = "cpu"
     nb = 3
@@ -639,6 +664,8 @@ def measure_b200(ctx, wl_name, wl, steps, warmup, sample_clocks=True):
         del ds
     torch.cuda.empty_cache()
     res_extra = {"generator": generator} if generator else {}
+    if recompute:
+        res_extra["recompute"] = recompute
     return {**res_extra, "value": value, "ms_per_step": ms_per_step, "steps": steps, "warmup": max(warmup, 3),
             "dtype": "bf16" if tensor_path else "f32",
             "config": config_of(wl_name, wl, euler_steps=S, obs_rows_per_gpu=N_rows, parallelism="dp%d" % world,
@@ -714,6 +741,9 @@ def run_b200(args, wl_name, wl):
            "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
            "config": head["config"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
            "roofline": head["roofline"], "wall_s_timed_region": head["wall_s_timed_region"]}
+    for k in ("recompute", "generator"):
+        if k in head:
+            out[k] = head[k]
     if check is not None:
         out["dp_check"] = check
     if ctx.world == 1 and not args.no_cpu_baseline:

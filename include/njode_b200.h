@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define NJODE_ABI_VERSION 4
+#define NJODE_ABI_VERSION 5
 #define NJODE_MAX_LINEAR 8          /* max number of Linear layers per network */
 
 enum { NJODE_ACT_NONE = 0, NJODE_ACT_TANH = 1, NJODE_ACT_RELU = 2 };
@@ -112,11 +112,16 @@ typedef struct njode_plan {
     int64_t smem_fwd_bytes, smem_bwd_bytes;
     int64_t image_floats;      /* padded parameter image (also the per-CTA gradient partial) */
     int64_t workspace_bytes;   /* scratch the caller must provide to forward/backward */
+    int64_t recompute_bytes;   /* > 0: njode_backward can run WITHOUT anything saved by the forward pass (saved members NULL):
+                                  it recomputes the forward of every segment from its checkpoint at the observation time; this
+                                  many bytes of the workspace hold the h chains of the tiles in flight.  0: the backward of this
+                                  (model, batch) needs the history written by njode_forward */
 } njode_plan_t;
 
-/* buffers produced by the forward pass that the backward pass re-reads */
+/* buffers produced by the forward pass that the backward pass re-reads; all NULL when the backward recomputes
+ * (njode_plan_t.recompute_bytes > 0): nothing of size O(S * B) exists then */
 typedef struct njode_saved {
-    float* h_hist;             /* [S, B, hidden]  h at the start of every Euler step, or NULL (no grad) */
+    float* h_hist;             /* [S, B, hidden]  h at the start of every Euler step, or NULL (no grad / recompute) */
     float* h_before;           /* [N, hidden]     h just before the jump of row r, or NULL */
     float* y_after;            /* [N, output]     Y = readout(h after jump) of row r, or NULL */
 } njode_saved_t;

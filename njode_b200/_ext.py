@@ -12,6 +12,7 @@ import torch
 from . import schedule as _sched
 
 MAX_LINEAR = 8
+RECOMPUTE_AUTO_BYTES = 256 << 20      # "auto": keep the [S, B, H] history of the forward pass up to this size
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB_PATH = os.path.join(_HERE, "libnjode_b200.so")
 
@@ -46,7 +47,7 @@ class PlanT(C.Structure):
     _fields_ = [("tile_paths", C.c_int32), ("threads", C.c_int32), ("grid_fwd", C.c_int32),
                 ("grid_bwd", C.c_int32), ("weights_in_smem", C.c_int32), ("grads_in_smem", C.c_int32),
                 ("smem_fwd_bytes", C.c_int64), ("smem_bwd_bytes", C.c_int64),
-                ("image_floats", C.c_int64), ("workspace_bytes", C.c_int64)]
+                ("image_floats", C.c_int64), ("workspace_bytes", C.c_int64), ("recompute_bytes", C.c_int64)]
 
 
 class SavedT(C.Structure):
@@ -91,7 +92,7 @@ class Lib:
                                      C.c_void_p, C.c_void_p]
         for f in (d.njode_plan, d.njode_forward, d.njode_backward):
             f.restype = C.c_int
-        if d.njode_abi_version() != 4:
+        if d.njode_abi_version() != 5:
             raise NjodeError("njode_b200: ABI version mismatch in %s" % path)
         # device index build (absent from the host simulation: the CPU-only tests use schedule.build_index_torch)
         self.has_index = hasattr(d, "njode_build_index")
@@ -417,7 +418,11 @@ class Runner:
         self.lib.check(rc, "njode_wide_backward")
         return grads
 
-    def forward(self, model_t, pb, params, H, dout, get_loss, need_grad):
+    def forward(self, model_t, pb, params, H, dout, get_loss, need_grad, recompute="auto"):
+        """``recompute``: "on" / "off" / "auto" -- when the backward of this (model, batch) can recompute its forward
+        from the checkpoints at the observation times (njode_plan: recompute_bytes > 0; the segment kernels), "on" saves
+        NOTHING for it (no [S, B, H] history: memory independent of the batch size, ~15 % more backward time); "auto"
+        does so when the history would exceed RECOMPUTE_AUTO_BYTES"""
         f32 = dict(dtype=torch.float32, device=self.device)
         pl = self.plan(model_t, pb.fwd)
         ws = self._workspace(pl.workspace_bytes)
@@ -427,7 +432,10 @@ class Runner:
         path_h = torch.empty(E, pb.B, H, **f32) if E else None
         path_y = torch.empty(E, pb.B, dout, **f32) if E else None
         saved_t, saved = SavedT(), None
-        if need_grad:
+        hist_bytes = 4 * max(pb.sched.S, 1) * pb.B * H
+        if need_grad and pl.recompute_bytes > 0 and (recompute == "on" or (recompute == "auto" and hist_bytes > RECOMPUTE_AUTO_BYTES)):
+            saved = ()                       # the backward recomputes: nothing to keep
+        elif need_grad:
             saved = (torch.empty(max(pb.sched.S, 1) * pb.B * H, **f32),
                      torch.empty(max(pb.N, 1) * H, **f32), torch.empty(max(pb.N, 1) * dout, **f32))
             saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved])
@@ -444,7 +452,7 @@ class Runner:
         pl = self.plan(model_t, bt)
         ws = self._workspace(pl.workspace_bytes)
         grads = torch.empty_like(params)
-        saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved])
+        saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved]) if saved else SavedT()
         with self._guard():
             rc = self.lib.dll.njode_backward(C.byref(model_t), C.byref(bt), _ptr(params), C.byref(saved_t),
                                              _ptr(grad_loss), _ptr(grad_hT), _ptr(grads), _ptr(ws),

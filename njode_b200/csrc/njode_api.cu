@@ -226,6 +226,13 @@ static int nj_plan_for(const njode_model_t* model, const njode_batch_t* b, int d
     const size_t cap = (size_t)di.sms * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
     out.ws_bytes = out.ws_partials_off + cap * std::max(out.fwd.img_floats, out.bwd.img_floats) * sizeof(float);
+    // recompute mode of the segment backward: [grid][S][P_b][sH] floats, offered up to 1 GiB
+    out.ws_scratch_off = (out.ws_bytes + 255) & ~(size_t)255;
+    out.scratch_bytes = 0;
+    if (out.seg.ok) {
+        const size_t sb = (size_t)out.seg_grid_b * (size_t)std::max(1, (int)b->S) * out.seg.P_b * out.seg.sH * sizeof(float);
+        if (sb <= ((size_t)1 << 30)) { out.scratch_bytes = sb; out.ws_bytes = out.ws_scratch_off + sb; }
+    }
     return 0;
 }
 
@@ -237,6 +244,7 @@ extern "C" int njode_plan(const njode_model_t* model, const njode_batch_t* batch
     p->weights_in_smem = o.fwd.w_smem; p->grads_in_smem = o.bwd.dw_smem;
     p->smem_fwd_bytes = (int64_t)o.smem_fwd_bytes; p->smem_bwd_bytes = (int64_t)o.smem_bwd_bytes;
     p->image_floats = o.fwd.img_floats; p->workspace_bytes = (int64_t)o.ws_bytes;
+    p->recompute_bytes = (int64_t)o.scratch_bytes;
     return 0;
 }
 
@@ -310,12 +318,17 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     NjPlanOut pl;
     if (int rc = nj_plan_for(model, batch, dev, pl)) return rc;
     if (!workspace || !params || !grads || !grad_loss || !saved) return nj_fail(-1, "null buffer");
-    if (batch->S > 0 && !saved->h_hist) return nj_fail(-1, "backward needs the h history of the forward pass");
-    if (batch->N > 0 && (!saved->h_before || (model->masked && !saved->y_after))) return nj_fail(-1, "backward needs h_before / y_after");
+    // nothing saved by the forward pass: the segment backward recomputes every segment from its checkpoint
+    const bool recompute = !saved->h_hist && !saved->h_before && pl.seg.ok && pl.scratch_bytes > 0;
+    if (!recompute) {
+        if (batch->S > 0 && !saved->h_hist) return nj_fail(-1, "backward needs the h history of the forward pass (njode_plan: recompute_bytes == 0)");
+        if (batch->N > 0 && (!saved->h_before || (model->masked && !saved->y_after))) return nj_fail(-1, "backward needs h_before / y_after");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     NjArgs a;
     nj_fill_args(a, batch, pl, (char*)workspace);
     a.h_hist = saved->h_hist; a.h_before = saved->h_before; a.y_after = saved->y_after;
+    if (recompute) a.scratch = reinterpret_cast<float*>((char*)workspace + pl.ws_scratch_off);
     a.grad_loss = grad_loss; a.grad_hT = grad_hT;
     a.get_loss = 1;
     a.n_tiles = pl.n_tiles;

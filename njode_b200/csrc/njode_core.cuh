@@ -464,6 +464,9 @@ struct NjArgs {
     int* counter;              // tile counter of the segment kernels (zeroed before every launch)
     int n_tiles;
     int get_loss;
+    // segment backward without anything saved by the forward pass ("recompute forward segments from the checkpoints at
+    // the observation times"): per-CTA scratch [S][P_b][sH] for the h chain of the tile being reversed, or NULL
+    float* scratch;
 };
 
 struct NjCta {

@@ -19,6 +19,7 @@ struct NjPlanOut {
     int grid_fwd, grid_bwd;
     size_t smem_fwd_bytes, smem_bwd_bytes;
     size_t ws_image_off, ws_rowloss_off, ws_counter_off, ws_partials_off, ws_bytes;
+    size_t ws_scratch_off, scratch_bytes;      // segment backward in recompute mode: h chains of the tiles in flight
 };
 
 // compact: the generic kernels (njode_core.cuh) only touch rows < 4 * og of a weight block; the 8*to*nch row padding
@@ -583,9 +584,18 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         const char* np_ = getenv("NJODE_NO_PIPE");
         if (!s.stat && !(np_ && atoi(np_)) && helpers_min <= 8) {
             // rows per warp so that the row warps leave room for the helpers
-            while ((P_want + R - 1) / R > 12 - helpers_min && R < 8 && !force_r) R *= 2;
-            nw = std::max(1, std::min(12 - helpers_min, (P_want + R - 1) / R));
-            s.pipe = 1;
+            int Rp = R;
+            while ((P_want + Rp - 1) / Rp > 12 - helpers_min && Rp < 8 && !force_r) Rp *= 2;
+            const int nwp = std::max(1, std::min(12 - helpers_min, (P_want + Rp - 1) / Rp));
+            // worth it when the helpers' dW (16 FFMA per tile and row) is well hidden behind the row warps' step (five
+            // layer passes over Rp rows): measured on B200, PhysioNet nets (ratio 0.3) backward 145 -> 128 ms, demo nets
+            // with the GRU jump at 36 rows per CTA (ratio 0.7) 5.6 -> 6.3 ms
+            double w_ode = 0;
+            for (int l = 0; l < c.net[NJODE_NET_ODE].n; ++l) w_ode += (double)c.net[NJODE_NET_ODE].dim[l] * c.net[NJODE_NET_ODE].dim[l + 1];
+            const double row_ffma = 5.0 * w_ode * Rp / 32.0;
+            const double help_ffma = (double)ode_tiles * 16.0 * (Rp * nwp) / (32.0 * (12 - nwp));
+            const char* fp_ = getenv("NJODE_FORCE_PIPE");
+            if (help_ffma < 0.5 * row_ffma || (fp_ && atoi(fp_))) { s.pipe = 1; R = Rp; nw = nwp; }
         }
         int fl = 0;
         for (; nw >= 1; --nw) {

@@ -682,15 +682,12 @@ NJ_HD void nj_seg_tile_store(const NjCfg& c, int netid, int l, int og, int kg, c
 // phase B: dW[o][k] += sum_r g[r][o] a[r][k] over the Pt rows of the tile.  Tiles are thread-owned: the first
 // NT_MAX * nt of them (the ODE network first) live in registers (`acc`) for the whole launch; the others are
 // accumulated from zero and added into this CTA's partial image in global memory (L2 resident) right away.
-NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, float* acc, float* gpart,
-                     int tid, int nt, int Pt) {
-#pragma unroll
-    for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
-        if (slot >= s.nt_slots) break;
-        int l, og, kg;
-        if (!nj_seg_tile_decode(c, s, netid, slot * nt + tid, l, og, kg)) continue;
-        nj_seg_dw_rows(c, s, t, netid, l, og, kg, Pt, acc + slot * 20);
-    }
+// tiles beyond the register slots.  Out of line on purpose: inlined next to the 40 accumulator registers of the dW phase,
+// ptxas 12.9 (-O3, sm_100a) has produced a wrong partial-image address for this read-modify-write (compute-sanitizer:
+// out-of-bounds LDG; first seen in njode_path.cuh, then here once the recompute phase changed the register allocation of
+// the kernel) while the same source is correct in the host simulation.
+NJ_HDN void nj_seg_dw_overflow(const NjCfg* cp, const NjSeg* sp, const NjSegB* tp, int netid, float* gpart, int tid, int nt, int Pt) {
+    const NjCfg& c = *cp; const NjSeg& s = *sp; const NjSegB& t = *tp;
     for (int T = NJ_SEG_NT_MAX * nt + tid; T < s.tiles_total; T += nt) {
         int l, og, kg;
         if (!nj_seg_tile_decode(c, s, netid, T, l, og, kg)) continue;
@@ -700,6 +697,18 @@ NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid,
         nj_seg_dw_rows(c, s, t, netid, l, og, kg, Pt, q);
         nj_seg_tile_store(c, netid, l, og, kg, q, gpart, true);
     }
+}
+
+NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, float* acc, float* gpart,
+                     int tid, int nt, int Pt) {
+#pragma unroll
+    for (int slot = 0; slot < NJ_SEG_NT_MAX; ++slot) {
+        if (slot >= s.nt_slots) break;
+        int l, og, kg;
+        if (!nj_seg_tile_decode(c, s, netid, slot * nt + tid, l, og, kg)) continue;
+        nj_seg_dw_rows(c, s, t, netid, l, og, kg, Pt, acc + slot * 20);
+    }
+    if (s.tiles_total > NJ_SEG_NT_MAX * nt) nj_seg_dw_overflow(&c, &s, &t, netid, gpart, tid, nt, Pt);
 }
 
 // writes the register tiles into this CTA's partial gradient image (pre-zeroed by the caller)
@@ -791,12 +800,77 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                 if (ec0 == 0) t.F[NJS_F_TAU * P + r] = (p >= 0 && sr >= 0) ? NJ_LDG(a.b.jump_tau + NJ_LDG(a.b.row_jump + sr)) : 0.f;
             }
             NJ_SYNCWARP();
+            if (a.scratch) {
+                // ---- recompute the forward of the tile's segments from their checkpoints: h at the start of a segment is
+                // the encoder of its start observation (nothing saved by the forward pass).  The h chain goes to this CTA's
+                // scratch [step][row][sH] (L2 resident), h at the segment end stays in HB for the jump reversal. ----
+                float* sc = a.scratch + (size_t)cta * a.b.S * P * sH;
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er;
+                    const bool valid = t.I[NJS_I_PATH * P + r] >= 0;
+                    for (int c_ = ec0; c_ < d4; c_ += LPR) {
+                        t.XI[r * sD + c_] = t.LX[r * sD + c_];
+                        t.IN[(size_t)r * sI + c_] = t.TX[r * sD + c_];
+                    }
+                    if (ec0 == 0) { NJ_SEGB_KEY(r, valid, nj_seg_event_of_start(a, t.I[NJS_I_START * P + r])); }
+                }
+                NJ_SYNCWARP();
+                nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, true, false);
+                NJ_LANES(lane) {
+                    NJ_ROWMAP(R);
+                    const int r = r0 + er;
+                    for (int c_ = ec0; c_ < c.H; c_ += LPR) {
+                        float e = t.OUT[r * sO + c_];
+                        if (c.residual) e += nj_resid(t.XI + r * sD, c.d, c.H, c_);
+                        t.HB[r * sH + c_] = e;
+                    }
+                }
+                NJ_SYNCWARP();
+                for (int j = 0; j < maxlen; ++j) {
+                    NJ_LANES(lane) {
+                        NJ_ROWMAP(R);
+                        const int r = r0 + er;
+                        const bool active = j < t.I[NJS_I_LEN * P + r];
+                        const int k = t.I[NJS_I_S0 * P + r] + j;
+                        const float tau = t.F[NJS_F_TAU * P + r];
+                        for (int c_ = ec0; c_ < inf4; c_ += LPR) {
+                            float v = 0.f;
+                            if (c_ < c.d) v = t.TX[r * sD + c_];
+                            else if (c_ < c.d + c.H) {
+                                const float h = t.HB[r * sH + c_ - c.d];
+                                if (active) sc[((size_t)j * P + r) * sH + c_ - c.d] = h;
+                                v = nj_tanh(h);
+                            } else if (c_ < c.inf) {
+                                const float tcur = active ? NJ_LDG(a.b.step_t + k) : 0.f;
+                                if (c_ == c.d + c.H) v = tau;
+                                else if (c_ == c.d + c.H + 1) v = tcur - tau;
+                                else v = tau + (tcur - tau);
+                            }
+                            t.IN[(size_t)r * sI + c_] = v;
+                        }
+                        if (ec0 == 0) { NJ_SEGB_KEY(r, true, (unsigned)k); }
+                    }
+                    NJ_SYNCWARP();
+                    nj_seg_mlp_fwd<TR>(w, NJODE_NET_ODE, true, false);
+                    NJ_LANES(lane) {
+                        NJ_ROWMAP(R);
+                        const int r = r0 + er;
+                        if (j < t.I[NJS_I_LEN * P + r]) {
+                            const float dt = NJ_LDG(a.b.step_dt + t.I[NJS_I_S0 * P + r] + j);
+                            for (int c_ = ec0; c_ < c.H; c_ += LPR)
+                                t.HB[r * sH + c_] = fmaf(dt, t.OUT[r * sO + c_], t.HB[r * sH + c_]);
+                        }
+                    }
+                    NJ_SYNCWARP();
+                }
+            }
             if (any_jump) {
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
                     const int r = r0 + er, row = t.I[NJS_I_ROW * P + r];
                     for (int c_ = ec0; c_ < H4; c_ += LPR) {
-                        const float h = (row >= 0 && c_ < c.H) ? a.h_before[(size_t)row * c.H + c_] : 0.f;
+                        const float h = (row >= 0 && c_ < c.H) ? (a.scratch ? t.HB[r * sH + c_] : a.h_before[(size_t)row * c.H + c_]) : 0.f;
                         if (c_ < c.H) t.HB[r * sH + c_] = h;
                         t.IN[(size_t)r * sI + c_] = c_ < c.H ? nj_tanh(h) : 0.f;
                     }
@@ -957,7 +1031,9 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     const int k = t.I[NJS_I_S0 * P + r] + j;
                     const float tau = t.F[NJS_F_TAU * P + r];
                     const float dt = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
-                    const float* hh = active ? a.h_hist + ((size_t)k * a.b.B + t.I[NJS_I_PATH * P + r]) * c.H : nullptr;
+                    const float* hh = nullptr;
+                    if (active) hh = a.scratch ? a.scratch + ((size_t)cta * a.b.S * P + (size_t)j * P + r) * sH
+                                               : a.h_hist + ((size_t)k * a.b.B + t.I[NJS_I_PATH * P + r]) * c.H;
                     for (int c_ = ec0; c_ < inf4; c_ += LPR) {
                         float v = 0.f;
                         if (c_ < c.d) v = t.TX[r * sD + c_];

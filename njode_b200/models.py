@@ -173,7 +173,8 @@ class _NJODEFunction(torch.autograd.Function):
             hT, loss, path_h, path_y, saved = runner.forward_wide(
                 model_t, pb, flat, H, dout, get_loss, need_grad, fp32_backward=module.tensor_core_backward == "fp32")
         else:
-            hT, loss, path_h, path_y, saved = runner.forward(model_t, pb, flat, H, dout, get_loss, need_grad)
+            hT, loss, path_h, path_y, saved = runner.forward(model_t, pb, flat, H, dout, get_loss, need_grad,
+                                                             recompute=module.recompute)
         ctx.module, ctx.runner, ctx.pb, ctx.model_t, ctx.saved = module, runner, pb, model_t, saved
         # the backward re-reads the parameters: remember which buffer / which in-place versions the forward saw
         ctx.flat_version = module._flat_version
@@ -205,7 +206,7 @@ class _NJODEFunction(torch.autograd.Function):
         g_loss = torch.zeros((), device=dev) if g_loss is None else g_loss.to(dev, torch.float32).contiguous()
         if g_hT is not None:
             g_hT = g_hT.to(dev, torch.float32).contiguous()
-        if isinstance(ctx.saved[0], str):          # ("wide", blob): operand tiles of the tensor-core forward
+        if len(ctx.saved) and isinstance(ctx.saved[0], str):          # ("wide", blob): operand tiles of the tensor-core forward
             grads = runner.backward_wide(ctx.model_t, ctx.pb, flat, ctx.saved[1], g_loss, g_hT)
         else:
             grads = runner.backward(ctx.model_t, ctx.pb, flat, ctx.saved, g_loss, g_hT)
@@ -265,6 +266,10 @@ class NJODE(torch.nn.Module):
         # "fp32" (the FMA backward kernels re-reading h_hist)
         self.tensor_core_backward = os.environ.get("NJODE_TENSOR_CORE_BACKWARD", "tcgen05")
         self.last_forward_path = None
+        # backward of the segment kernels: "off" = re-read the [S, B, H] history the forward pass wrote; "on" = save nothing
+        # and recompute every segment from its checkpoint at the observation time (memory independent of S * B);
+        # "auto" = recompute once the history would exceed _ext.RECOMPUTE_AUTO_BYTES
+        self.recompute = os.environ.get("NJODE_RECOMPUTE", "auto")
 
     def _use_tensor_cores(self, runner, pb, model_t):
         mode = self.tensor_cores

@@ -155,7 +155,7 @@ def test_native_library_is_loaded():
     from njode_b200 import _ext
     with open("/proc/self/maps") as f:
         assert "libnjode_b200.so" in f.read()
-    assert _ext.cuda_lib().dll.njode_abi_version() == 4
+    assert _ext.cuda_lib().dll.njode_abi_version() == 5
 
 
 @pytest.mark.parametrize("width", [50, 200])
@@ -178,3 +178,55 @@ def test_config4_physionet_full_size_against_oracle(width):
         os.makedirs(out, exist_ok=True)
         with open(os.path.join(out, "parity_physionet_b50_%d.json" % width), "w") as f:
             json.dump(report, f, indent=1)
+
+
+# ---- segment backward in recompute mode (north_star: "recomputes forward segments from checkpointed h at observation
+# times rather than storing every step"): nothing is saved by the forward pass ----
+@pytest.fixture
+def recompute_on():
+    os.environ["NJODE_RECOMPUTE"] = "on"
+    yield
+    os.environ.pop("NJODE_RECOMPUTE", None)
+
+
+@pytest.mark.parametrize("name", ["bs_ckpt1", "heston_ckpt2", "ou_ckpt3", "irregular_demo", "curt_nobias_relu", "res_case2", "easy_w07_nores"])
+def test_recompute_mode_golden_cases(name, recompute_on):
+    parity_util.check_training_call(name, DEV, with_hT_grad=True)
+    parity_util.check_training_call(name, DEV)
+
+
+def test_recompute_mode_train_dropout_and_big_nets(recompute_on):
+    cfg = cases.demo_cfg(dropout_rate=0.1)
+    batch = cases.grid_batch(600, 1, 60, 0.12, seed=31)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 60, 1.0, seed=12, device=DEV, train=True, grad_hT=True)
+    nn100 = [[100, "tanh"], [100, "tanh"]]
+    cfg = cases.demo_cfg(ode_nn=nn100, enc_nn=nn100, readout_nn=nn100, dropout_rate=0.1)
+    batch = cases.grid_batch(96, 1, 40, 0.1, seed=21)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 40, 1.0, seed=5, device=DEV, train=True)
+
+
+def test_recompute_mode_allocates_no_history(recompute_on):
+    """20 000 paths x 100 steps: the default mode keeps 80 MB of h history per step of training, recompute mode none"""
+    batch = cases.grid_batch(20000, 1, 100, 0.1, seed=41)
+    peaks = {}
+    for mode in ("off", "on"):
+        torch.manual_seed(0)
+        m = models.NJODE(**cases.demo_cfg()).to(DEV)
+        m.recompute = mode
+        m.output_device = "cuda"
+        pb = m.prepare_batch(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 0.01, 1.0, batch["start_X"], batch["n_obs_ot"])
+        hT, loss = m.forward_prepared(pb)
+        loss.backward()                            # warm-up: workspaces exist
+        torch.cuda.synchronize()
+        for p in m.parameters():
+            p.grad = None
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        hT, loss = m.forward_prepared(pb)
+        held = torch.cuda.memory_allocated() - base           # what the graph keeps alive between forward and backward
+        loss.backward()
+        torch.cuda.synchronize()
+        peaks[mode] = held
+        del hT, loss
+    assert peaks["off"] >= 4 * 100 * 20000 * 10           # [S, B, H] fp32
+    assert peaks["on"] < 2 * 1024 * 1024                  # hT + scalars only

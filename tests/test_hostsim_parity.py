@@ -33,6 +33,7 @@ def sim_runner():
     os.environ.pop("NJODE_PATH_R", None)
     os.environ.pop("NJODE_NO_STAT", None)
     os.environ.pop("NJODE_NO_PIPE", None)
+    os.environ.pop("NJODE_FORCE_PIPE", None)
     os.environ.pop("NJODE_SIM_SMS", None)
 
 
@@ -259,6 +260,8 @@ def _pick(stat):
         os.environ["NJODE_NO_STAT"] = "1"
     if stat == "warp-gemm":
         os.environ["NJODE_NO_PIPE"] = "1"
+    if stat == "warp-gemm-pipelined":
+        os.environ["NJODE_FORCE_PIPE"] = "1"
 
 
 @STAT
@@ -311,3 +314,38 @@ def test_weight_stationary_kernels_physionet_shape_with_the_b200_launch_plan(B):
     batch = cases.irregular_batch(B, 41, 12, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
     cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
     parity_util.check_against_oracle(cfg, batch, 1.0 / 12, 1 + 1e-12, seed=5, device="cpu", train=True, grad_hT=True)
+
+
+# ---- segment backward in recompute mode: nothing saved by the forward pass (north_star: "the backward pass recomputes
+# forward segments from checkpointed h at observation times rather than storing every step") ----
+@pytest.fixture
+def recompute_on():
+    os.environ["NJODE_RECOMPUTE"] = "on"
+    yield
+    os.environ.pop("NJODE_RECOMPUTE", None)
+    os.environ.pop("NJODE_FORCE_TR", None)
+
+
+@pytest.mark.parametrize("name", ["bs_ckpt1", "heston_ckpt2", "ou_ckpt3", "irregular_demo", "curt_nobias_relu", "res_case2", "easy_w07_nores"])
+def test_segment_backward_recomputes_from_checkpoints(name, recompute_on):
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    parity_util.check_training_call(name, "cpu")
+
+
+@pytest.mark.parametrize("tr", [1, 2])
+def test_segment_backward_recompute_train_mode_dropout(tr, recompute_on):
+    """the recomputed forward replays the forward kernel's dropout masks (same counter-based keys)"""
+    os.environ["NJODE_FORCE_TR"] = str(tr)
+    cfg = cases.demo_cfg(dropout_rate=0.15, input_size=2, output_size=2)
+    batch = cases.grid_batch(150, 2, 30, 0.2, seed=12)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 30, 1.0, seed=6, device="cpu", train=True, grad_hT=True)
+
+
+def test_recompute_mode_saves_nothing(recompute_on):
+    from njode_b200 import _ext
+    cfg, meta, sd, batch, outs = cases.load_case("bs_ckpt1")
+    m = parity_util.build_model(cfg, sd, "cpu")
+    assert m.recompute == "on"
+    m.eval()
+    hT, loss = parity_util.call(m, batch, meta, "cpu")
+    assert loss.grad_fn is not None and loss.grad_fn.saved == ()
