@@ -58,6 +58,11 @@ WORKLOADS = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable demo batch
     "bs_demo_200": dict(sde="BlackScholes", paths=200, steps=100, d=1, H=10, width=50, layers=2,
                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=200),
+    # batch sweep around it (BASELINE.json configs[2]: batch in {200 .. 20 000})
+    "bs_demo_1k": dict(sde="BlackScholes", paths=1000, steps=100, d=1, H=10, width=50, layers=2,
+                       obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
+    "bs_demo_5k": dict(sde="BlackScholes", paths=5000, steps=100, d=1, H=10, width=50, layers=2,
+                       obs_perc=0.1, dropout=0.1, cpu_sample_paths=1000),
     # BASELINE.json configs[4]: scaled BlackScholes, d=16, H=256, 4x256 nets, 1000 Euler steps, paths generated
     # on the device (Philox Euler-Maruyama + device collate), tcgen05 tensor-core kernels (bf16 operands)
     # The dataset is BASELINE's "1M on-device-generated paths" sharded over 8 GPUs: every rank generates ITS 131 072 paths

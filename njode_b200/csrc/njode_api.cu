@@ -59,6 +59,18 @@ __global__ void __launch_bounds__(384) nj_seg_bwd_kernel_h(const __grid_constant
     nj_seg_cta_backward<true>(cfg, seg, args, nj_smem, blockIdx.x);
 }
 
+// segment units of small batches on the weight-stationary Euler steps (njode_path.cuh, nj_segstat_*)
+template <int TR>
+__global__ void __launch_bounds__(416) nj_segstat_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+                                                             const __grid_constant__ NjArgs args) {
+    nj_segstat_cta_forward<TR>(cfg, seg, args, nj_smem);
+}
+template <int TR>
+__global__ void __launch_bounds__(416) nj_segstat_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+                                                             const __grid_constant__ NjArgs args) {
+    nj_segstat_cta_backward<TR>(cfg, seg, args, nj_smem, blockIdx.x);
+}
+
 // whole-path units on the warp GEMMs (njode_path.cuh); one kernel per (row groups, rows per group) tile shape
 template <int RG, int TR>
 __global__ void __launch_bounds__(384) nj_path_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
@@ -284,9 +296,16 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     if (pl.seg.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[0], st);
-        NJ_CUDA(cudaFuncSetAttribute(nj_seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
-        nj_seg_fwd_kernel<<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
-        nj_set_last_kernel(0, "nj_seg_fwd_kernel");
+        if (pl.seg.stat) {
+            auto kern = pl.seg.f_tr[0] == 2 ? nj_segstat_fwd_kernel<2> : nj_segstat_fwd_kernel<1>;
+            NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
+            kern<<<pl.seg_grid_f, pl.seg.nw_s * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
+            nj_set_last_kernel(0, pl.seg.f_tr[0] == 2 ? "nj_segstat_fwd_kernel<2>" : "nj_segstat_fwd_kernel<1>");
+        } else {
+            NJ_CUDA(cudaFuncSetAttribute(nj_seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
+            nj_seg_fwd_kernel<<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
+            nj_set_last_kernel(0, "nj_seg_fwd_kernel");
+        }
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";
@@ -341,10 +360,12 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.seg_grid_b;
-        auto kern = pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h : nj_seg_bwd_kernel;
+        auto kern = pl.seg.stat ? (pl.seg.b_tr[0] == 2 ? nj_segstat_bwd_kernel<2> : nj_segstat_bwd_kernel<1>)
+                                : (pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h : nj_seg_bwd_kernel);
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
         kern<<<pl.seg_grid_b, pl.seg.nt_b, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
-        nj_set_last_kernel(1, pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : "nj_seg_bwd_kernel");
+        nj_set_last_kernel(1, pl.seg.stat ? (pl.seg.b_tr[0] == 2 ? "nj_segstat_bwd_kernel<2>" : "nj_segstat_bwd_kernel<1>")
+                                          : (pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : "nj_seg_bwd_kernel"));
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";

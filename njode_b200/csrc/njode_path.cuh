@@ -1683,7 +1683,7 @@ NJ_HD float nj_stat_sum8(NjStatRegs* regs, int tid, const float* in_row, int K4,
 // NjStatRegs must only ever be indexed with compile-time constants, or they end up in local memory.
 template <int l>
 NJ_HD void nj_stat_layer_fwd(const NjCfg& c, const NjStatGeo& g, NjStatRegs* regs, int tid, int R,
-                             const float* in, int in_s, float* out, int out_s, float* hs, int hs_s, float dt, const int* rk) {
+                             const float* in, int in_s, float* out, int out_s, float* hs, int hs_s, const float* dtv, const int* rk) {
     const int lane = tid & 31, o = 4 * (tid >> 5) + (lane >> 3), ksl = lane & 7;
 #if defined(NJODE_HOST_SIM)
     if (ksl != 0) return;
@@ -1698,7 +1698,7 @@ NJ_HD void nj_stat_layer_fwd(const NjCfg& c, const NjStatGeo& g, NjStatRegs* reg
     for (int r = 0; r < R; ++r) {
         const float sum = nj_stat_sum8<l>(regs, tid, in + (size_t)r * in_s, g.K4[l], g.KS[l]);
         if (lead) {
-            if (hs) hs[r * hs_s + o] = fmaf(dt, sum + bias, hs[r * hs_s + o]);
+            if (hs) hs[r * hs_s + o] = fmaf(dtv[r], sum + bias, hs[r * hs_s + o]);     // dtv[r] = 0: the row rests
             else {
                 float v = nj_act(sum + bias, N.act[l]);
                 if (c.has_drop) {
@@ -1715,7 +1715,8 @@ NJ_HD void nj_stat_layer_fwd(const NjCfg& c, const NjStatGeo& g, NjStatRegs* reg
 // (ODEFunc.forward, NJODE/models.py:188-199); hsrc: h of the step (forward: HS, also written to h_hist; backward: h_hist)
 template <bool BWD>
 NJ_HD void nj_stat_build_in(const NjCfg& c, const NjArgs& a, int tid, int nt, int R, int k, const int* path, const float* TX, int sD,
-                            const float* tau, float* HS, int sH, float* IN, int sI, int* rk, const float* GH, float* GOUT, int sO) {
+                            const float* tau, float* HS, int sH, float* IN, int sI, int* rk, const float* GH, float* GOUT, int sO,
+                            float* dtv) {
     const int inf4 = ((c.inf + 3) >> 2) << 2;
     const float tcur = NJ_LDG(a.b.step_t + k), dt = NJ_LDG(a.b.step_dt + k);
     const int c_ = tid & 127, groups = nt >> 7;        // 128 threads per row; a trailing partial group stays idle
@@ -1739,7 +1740,10 @@ NJ_HD void nj_stat_build_in(const NjCfg& c, const NjArgs& a, int tid, int nt, in
             IN[(size_t)r * sI + c_] = v;
         }
         if (BWD && c_ < c.H) GOUT[(size_t)r * sO + c_] = dt * GH[r * sH + c_];
-        if (c_ == 127) rk[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
+        if (c_ == 127) {
+            rk[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
+            if (dtv) dtv[r] = dt;
+        }
     }
 }
 
@@ -1748,22 +1752,22 @@ template <int RG, int TR>
 NJ_HD void nj_stat_fwd_step(const NjCfg& c, const NjPath& s, const NjArgs& a, const NjStatGeo& g, NjStatRegs* njt_regs,
                             NjPathFwd<RG, TR>& f, int nt, int k) {
     constexpr int R = RG * TR, RS = NJP_RS;
-    const float dt = NJ_LDG(a.b.step_dt + k);
+    float* dtv = f.F + NJP_F_CA * RS;              // (the loss-coefficient slots are free in the forward pass)
     NJ_THREADS(tid, nt) {
         nj_stat_build_in<false>(c, a, tid, nt, R, k, f.I + NJP_I_PATH * RS, f.TX, s.sD, f.F + NJP_F_TAU * RS, f.HS, s.sH,
-                                f.w.IN, s.sI, f.w.RK, nullptr, nullptr, 0);
+                                f.w.IN, s.sI, f.w.RK, nullptr, nullptr, 0, dtv);
     }
     NJ_SYNC();
     const int* rk = f.w.RK;
-    NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, f.w.IN, s.sI, f.w.A0, s.sA, nullptr, 0, 0.f, rk); }
+    NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, f.w.IN, s.sI, f.w.A0, s.sA, nullptr, 0, nullptr, rk); }
     NJ_SYNC();
     if (g.n == 2) {
-        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, nullptr, 0, f.HS, s.sH, dt, rk); }
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, nullptr, 0, f.HS, s.sH, dtv, rk); }
         NJ_SYNC();
     } else {
-        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, f.w.A1, s.sA, nullptr, 0, 0.f, rk); }
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, f.w.A1, s.sA, nullptr, 0, nullptr, rk); }
         NJ_SYNC();
-        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<2>(c, g, njt_regs, tid, R, f.w.A1, s.sA, nullptr, 0, f.HS, s.sH, dt, rk); }
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<2>(c, g, njt_regs, tid, R, f.w.A1, s.sA, nullptr, 0, f.HS, s.sH, dtv, rk); }
         NJ_SYNC();
     }
 }
@@ -1929,16 +1933,16 @@ NJ_HD void nj_stat_bwd_step(const NjCfg& c, const NjPath& s, const NjArgs& a, co
     const int P = s.P_b, nw = s.nw_s, wa = P * s.sA;
     NJ_THREADS(tid, nt) {
         nj_stat_build_in<true>(c, a, tid, nt, R, k, t.I + NJB_I_PATH * P, t.TX, s.sD, t.F + NJP_F_TAU * P, nullptr, s.sH,
-                               t.IN, s.sI, t.I + NJB_I_RK * P, t.GH, t.GOUT, s.sO);
+                               t.IN, s.sI, t.I + NJB_I_RK * P, t.GH, t.GOUT, s.sO, nullptr);
     }
     NJ_SYNC();
     // recompute the hidden activations (kept with their dropout marks)
     int* rk = t.I + NJB_I_RK * P;
     float* A0 = t.A; float* A1 = t.A + wa; float* G0 = t.G; float* G1 = t.G + wa;
-    NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, t.IN, s.sI, A0, s.sA, nullptr, 0, 0.f, rk); }
+    NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, t.IN, s.sI, A0, s.sA, nullptr, 0, nullptr, rk); }
     NJ_SYNC();
     if (g.n == 3) {
-        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, A0, s.sA, A1, s.sA, nullptr, 0, 0.f, rk); }
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, A0, s.sA, A1, s.sA, nullptr, 0, nullptr, rk); }
         NJ_SYNC();
     }
     // layers in reverse: dW in registers, input-gradient partials through shared memory (two buffers in turn: a warp may
@@ -2107,6 +2111,197 @@ NJ_HD void nj_stat_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a
         NJ_SYNC();
         NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_ENC, gpart, tid, nt, R, nullptr, R); }
         NJ_SYNC();
+    }
+    NJ_THREADS(tid, nt) { nj_stat_flush(c, g, NJT_REGS(tid), tid, gpart); }
+}
+
+// ================================================================================================
+// weight-stationary Euler steps for SEGMENT units (non-masked training call at small batch sizes: the reference's own
+// batch of 200 paths is ~2 200 segments of ~10 steps -- 15 units per SM, far too few for the 12-warp tiles of
+// njode_seg.cuh, whose kernels then run one latency-bound warp per scheduler).  Same register-resident ODE network as
+// above; a tile = 4*TR units whose rows step through their OWN Euler steps (unit r is at step s0[r] + j, rests once j
+// reaches its length), warp 0 runs the start encoder and the jump that ends the segments (njode_seg.cuh code).
+// ================================================================================================
+template <bool BWD>
+NJ_HD void nj_segstat_build_in(const NjCfg& c, const NjArgs& a, int tid, int nt, int R, int j, const int* I, int istride,
+                               const float* TX, int sD, const float* tau, float* HS, int sH, float* IN, int sI, int* rk,
+                               const float* GH, float* GOUT, int sO, float* dtv, const float* scratch_j, int sc_stride) {
+    const int inf4 = ((c.inf + 3) >> 2) << 2;
+    const int c_ = tid & 127, groups = nt >> 7;
+    for (int r = tid >> 7; r < R && (tid >> 7) < groups; r += groups) {
+        const int p = I[NJS_I_PATH * istride + r];
+        const bool active = j < I[NJS_I_LEN * istride + r];
+        const int k = I[NJS_I_S0 * istride + r] + j;
+        const float dt = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
+        if (c_ < inf4) {
+            float v = 0.f;
+            if (c_ < c.d) v = TX[r * sD + c_];
+            else if (c_ < c.d + c.H) {
+                float h = 0.f;
+                if (BWD) {
+                    if (active) h = scratch_j ? scratch_j[(size_t)r * sc_stride + c_ - c.d]
+                                              : a.h_hist[((size_t)k * a.b.B + p) * c.H + c_ - c.d];
+                } else {
+                    h = HS[r * sH + c_ - c.d];
+                    if (active && a.h_hist) a.h_hist[((size_t)k * a.b.B + p) * c.H + c_ - c.d] = h;
+                }
+                v = nj_tanh(h);
+            } else if (c_ < c.inf) {
+                const float t_ = tau[r], tcur = active ? NJ_LDG(a.b.step_t + k) : 0.f;
+                if (c_ == c.d + c.H) v = t_;
+                else if (c_ == c.d + c.H + 1) v = tcur - t_;
+                else v = t_ + (tcur - t_);
+            }
+            IN[(size_t)r * sI + c_] = v;
+        }
+        if (BWD && c_ < c.H) GOUT[(size_t)r * sO + c_] = dt * GH[r * sH + c_];
+        if (c_ == 127) {
+            rk[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
+            if (dtv) dtv[r] = dt;
+        }
+    }
+}
+
+template <int TR>
+NJ_HD void nj_segstat_cta_forward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
+    constexpr int R = 4 * TR, RS = 16;
+    const int nt = 32 * s.nw_s;
+    float* simg = smem + s.f_img;
+    nj_stage_image(simg, a.image, c.img_floats, nt);
+    nj_zero(smem + s.f_warp0, s.f_region, nt);
+    NJ_SYNC();
+    const NjStatGeo g = nj_stat_geo(c);
+    NJT_REGS_DECL(nt);
+    NJ_THREADS(tid, nt) { nj_stat_load(c, g, simg, tid, NJT_REGS(tid)); }
+    float* reg = smem + s.f_warp0;
+    NjSegFwd<TR> f(c, s, a, reg, simg);
+    int* slot = f.I + NJS_I_COUNT * RS;
+    float* dtv = f.F + NJS_F_DT * RS;
+    for (;;) {
+        NJ_THREADS(tid, nt) { if (tid == 0) *slot = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int wt = *slot;
+        NJ_SYNC();
+        if (wt >= s.n_tiles_f) break;
+        int ub, ue;
+        nj_seg_tile_lookup(s.f_ncls, s.f_t0, s.f_u0, s.f_u1, s.f_tr, 4, wt, ub, ue);
+        NJ_WARPS(wp, 1) { if (wp == 0) f.begin(ub, ue); }
+        NJ_SYNC();
+        int maxlen = 0;
+        for (int r = 0; r < R; ++r) maxlen = f.I[NJS_I_LEN * RS + r] > maxlen ? f.I[NJS_I_LEN * RS + r] : maxlen;
+        for (int j = 0; j < maxlen; ++j) {
+            NJ_THREADS(tid, nt) {
+                nj_segstat_build_in<false>(c, a, tid, nt, R, j, f.I, RS, f.TX, s.sD, f.F + NJS_F_TAU * RS, f.HS, s.sH, f.w.IN, s.sI,
+                                           f.w.RK, nullptr, nullptr, 0, dtv, nullptr, 0);
+            }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, f.w.IN, s.sI, f.w.A0, s.sA, nullptr, 0, nullptr, f.w.RK); }
+            NJ_SYNC();
+            if (g.n == 2) {
+                NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, nullptr, 0, f.HS, s.sH, dtv, f.w.RK); }
+                NJ_SYNC();
+            } else {
+                NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, f.w.A1, s.sA, nullptr, 0, nullptr, f.w.RK); }
+                NJ_SYNC();
+                NJ_THREADS(tid, nt) { nj_stat_layer_fwd<2>(c, g, njt_regs, tid, R, f.w.A1, s.sA, nullptr, 0, f.HS, s.sH, dtv, f.w.RK); }
+                NJ_SYNC();
+            }
+        }
+        NJ_WARPS(wp, 1) { if (wp == 0) { f.maxlen = maxlen; f.finish(); } }
+        NJ_SYNC();
+    }
+}
+
+// the reverse Euler steps of a segment tile on all warps of the CTA (REV functor of nj_seg_bwd_tile)
+template <int TR>
+struct NjSegStatRev {
+    static constexpr bool stat = true;
+    static constexpr int R = 4 * TR;
+    const NjCfg& c; const NjSeg& s; const NjArgs& a; const NjStatGeo& g; NjStatRegs* njt_regs; const NjSegB& t;
+    float* part0; float* part1; int nt, cta;
+
+    NJ_HD void step(int j) const {
+        const int P = s.P_b, nw = s.nw_s, wa = P * s.sA;
+        int* rk = t.I + NJS_I_RK * P;
+        const float* scj = a.scratch ? a.scratch + ((size_t)cta * a.b.S * P + (size_t)j * P) * s.sH : nullptr;
+        NJ_THREADS(tid, nt) {
+            nj_segstat_build_in<true>(c, a, tid, nt, R, j, t.I, P, t.TX, s.sD, t.F + NJS_F_TAU * P, nullptr, s.sH, t.IN, s.sI, rk,
+                                      t.GH, t.GOUT, s.sO, nullptr, scj, s.sH);
+        }
+        NJ_SYNC();
+        float* A0 = t.A; float* A1 = t.A + wa; float* G0 = t.G; float* G1 = t.G + wa;
+        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, t.IN, s.sI, A0, s.sA, nullptr, 0, nullptr, rk); }
+        NJ_SYNC();
+        if (g.n == 3) {
+            NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, A0, s.sA, A1, s.sA, nullptr, 0, nullptr, rk); }
+            NJ_SYNC();
+        }
+        const float* pl;
+        if (g.n == 3) {
+            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<2>(g, njt_regs, tid, nw, R, t.GOUT, s.sO, A1, s.sA, part0); }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 2, R, part0, A1, s.sA, G1, s.sA); }
+            NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
+            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<1>(g, njt_regs, tid, nw, R, G1, s.sA, A0, s.sA, part1); }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 1, R, part1, A0, s.sA, G0, s.sA); }
+            NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
+            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<0>(g, njt_regs, tid, nw, R, G0, s.sA, t.IN, s.sI, part0); }
+            NJ_SYNC();
+            pl = part0;
+        } else {
+            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<1>(g, njt_regs, tid, nw, R, t.GOUT, s.sO, A0, s.sA, part0); }
+            NJ_SYNC();
+            NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 1, R, part0, A0, s.sA, G0, s.sA); }
+            NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
+            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<0>(g, njt_regs, tid, nw, R, G0, s.sA, t.IN, s.sI, part1); }
+            NJ_SYNC();
+            pl = part1;
+        }
+        // the partials of layer 0 -> adjoint of h (resting rows: GOUT was 0, so their partials are 0)
+        NJ_THREADS(tid, nt) {
+            const int lane = tid & 31, o = 4 * (tid >> 5) + (lane >> 3), ksl = lane & 7;
+            if (ksl == 0 && o < c.H) {
+                for (int r = 0; r < R; ++r) {
+                    float v = 0.f;
+                    for (int wq = 0; wq < nw; ++wq) v += pl[((size_t)r * nw + wq) * NJT_PARTW + c.d + o];
+                    const float th = t.IN[(size_t)r * s.sI + c.d + o];
+                    t.GH[r * s.sH + o] += v * (1.f - th * th);
+                }
+            }
+        }
+        NJ_SYNC();
+    }
+};
+
+template <int TR>
+NJ_HD void nj_segstat_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
+    const int nt = s.nt_b;                       // = 32 * nw_s
+    constexpr int R = 4 * TR;
+    float* simg = smem + s.b_img;
+    nj_stage_image(simg, a.image, c.img_floats, nt);
+    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
+    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    nj_zero(gpart, c.img_floats, nt);
+    NJ_SYNC();
+    NjSegB t;
+    nj_segb_bind(t, s, smem);
+    const NjStatGeo g = nj_stat_geo(c);
+    NJT_REGS_DECL(nt);
+    NJ_THREADS(tid, nt) { nj_stat_load(c, g, simg, tid, NJT_REGS(tid)); }
+    float* part0 = smem + s.b_PART;
+    float* part1 = part0 + (size_t)R * s.nw_s * NJT_PARTW;
+    const NjSegStatRev<TR> rev{c, s, a, g, njt_regs, t, part0, part1, nt, cta};
+    int* ctl = t.I + NJS_I_COUNT * s.P_b;
+    for (;;) {
+        NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int tile = ctl[0];
+        NJ_SYNC();
+        if (tile >= s.n_tiles_b) break;
+        int ub, ue;
+        nj_seg_tile_lookup(s.b_ncls, s.b_t0, s.b_u0, s.b_u1, s.b_tr, 4 * s.nw_b, tile, ub, ue);
+        nj_seg_bwd_tile<TR, NjSegStatRev<TR>>(c, s, a, smem, t, nullptr, cta, ub, ue, rev);
     }
     NJ_THREADS(tid, nt) { nj_stat_flush(c, g, NJT_REGS(tid), tid, gpart); }
 }

@@ -259,6 +259,11 @@ static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_u
 // ------------------------------------------------------------------------------------------------
 // segment fast path (njode_seg.cuh): eligibility + shared-memory layout
 // ------------------------------------------------------------------------------------------------
+// segment batches of at most this many units per SM take the weight-stationary kernels (measured on B200)
+#ifndef NJ_SEGSTAT_MAX_UNITS_PER_SM
+#define NJ_SEGSTAT_MAX_UNITS_PER_SM 32
+#endif
+
 static inline int nj_seg_fwd_region(const NjCfg& c, NjSeg& s, int R) {
     (void)c;
     int o = 0;
@@ -355,6 +360,74 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
         }
     }
     s.tiles_total = tiles;
+    // ---- small batches: weight-stationary Euler steps (njode_path.cuh, nj_segstat_*): one tile of 4 or 8 segments per
+    // CTA at a time, all warps of the CTA on its steps, the ODE network and its gradient in registers ----
+    {
+        const NjNet& O = c.net[NJODE_NET_ODE];
+        const char* fs = getenv("NJODE_SEG_STAT");            // 0: never, 1: whatever the batch size (tests)
+        const int want = fs ? atoi(fs) : -1;
+        bool ok = want != 0 && (O.n == 2 || O.n == 3);
+        int maxo = c.H;
+        for (int l = 0; l < O.n && ok; ++l) {
+            if (O.dim[l] > (l == 0 ? 96 : 64)) ok = false;
+            maxo = std::max(maxo, O.dim[l + 1]);
+        }
+        const int nws = std::max(4, (maxo + 3) / 4);
+        if (nws > 13) ok = false;
+        if (ok && want < 0 && n_units > NJ_SEGSTAT_MAX_UNITS_PER_SM * num_sms) ok = false;
+        if (ok) {
+            const char* ftr_ = getenv("NJODE_FORCE_TR");
+            int tr = n_units > 4 * num_sms ? 2 : 1;
+            if (ftr_ && atoi(ftr_)) tr = atoi(ftr_) >= 2 ? 2 : 1;
+            const int R = 4 * tr;
+            s.stat = 1; s.nw_s = nws;
+            // the ODE network has no thread-owned 4x4 tiles here; the jump networks' tiles all go through the partial image
+            tiles = 0;
+            for (int oi = 0; oi < 3; ++oi) {
+                const NjNet& N = c.net[order[oi]];
+                for (int l = 0; l < NJODE_MAX_LINEAR; ++l) {
+                    if (order[oi] == NJODE_NET_ODE) { s.tile_base[order[oi]][l] = 0x3FFFFFFF; continue; }
+                    s.tile_base[order[oi]][l] = tiles;
+                    if (l < N.n) tiles += ((N.dim[l] + 3) / 4) * ((N.dim[l + 1] + 3) / 4);
+                }
+            }
+            s.tiles_total = tiles;
+            const int n_loss_ = std::max(0, std::min(b.n_loss_units, n_units));
+            const int rb[2] = {0, n_loss_}, re[2] = {n_loss_, n_units};
+            const int z1[2] = {0, 0}, z2[2] = {0, 0};
+            const int one[1] = {tr};
+            s.f_region = nj_seg_fwd_region(c, s, R);
+            s.f_img = 0; s.f_warp0 = c.img_floats;
+            s.f_ncls = nj_seg_classes(rb, re, z1, z2, one, 1, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr);
+            s.n_tiles_f = s.f_t0[s.f_ncls];
+            s.nw_f = 1;
+            s.f_smem_floats = c.img_floats + s.f_region;
+            int fl = nj_seg_bwd_layout(c, s, R);
+            s.b_PART = fl; fl += 2 * R * nws * NJT_PARTW;
+            s.b_smem_floats = fl; s.P_b = R; s.nw_b = 1; s.nt_b = 32 * nws; s.nt_slots = 0;
+            s.b_ncls = nj_seg_classes(rb, re, z1, z2, one, 1, 4, s.b_t0, s.b_u0, s.b_u1, s.b_tr);
+            s.n_tiles_b = s.b_t0[s.b_ncls];
+            if ((size_t)s.f_smem_floats * 4 <= smem_limit && (size_t)s.b_smem_floats * 4 <= smem_limit) {
+                out.seg_smem_f_bytes = (size_t)s.f_smem_floats * 4;
+                out.seg_smem_b_bytes = (size_t)s.b_smem_floats * 4;
+                out.seg_grid_f = std::max(1, std::min(s.n_tiles_f, num_sms));
+                out.seg_grid_b = std::max(1, std::min(s.n_tiles_b, num_sms));
+                s.ok = 1;
+                return;
+            }
+            // does not fit: the warp kernels below
+            s.stat = 0; s.nw_s = 0; s.b_PART = 0;
+            tiles = 0;
+            for (int oi = 0; oi < 3; ++oi) {
+                const NjNet& N = c.net[order[oi]];
+                for (int l = 0; l < NJODE_MAX_LINEAR; ++l) {
+                    s.tile_base[order[oi]][l] = tiles;
+                    if (l < N.n) tiles += ((N.dim[l] + 3) / 4) * ((N.dim[l + 1] + 3) / 4);
+                }
+            }
+            s.tiles_total = tiles;
+        }
+    }
     const char* ftr = getenv("NJODE_FORCE_TR");
     const int force_tr = ftr ? atoi(ftr) : 0;
     const char* fnw = getenv("NJODE_FORCE_NW");

@@ -98,6 +98,9 @@ struct NjSeg {
     // [u0, u1) in tiles of 4*tr (forward, per warp) or 4*tr*nw_b (backward, per CTA) rows; t0 = first tile id.
     int f_ncls, f_t0[7], f_u0[6], f_u1[6], f_tr[6];
     int b_ncls, b_t0[7], b_u0[6], b_u1[6], b_tr[6];
+    // weight-stationary Euler steps for small batches (njode_path.cuh): one CTA of nw_s warps per tile of 4*tr units, the
+    // ODE network's weights and gradient in registers; b_PART: input-gradient partials [2][P_b][nw_s][96]
+    int stat, nw_s, b_PART;
 };
 
 // tile id -> (class, first unit, one-past-last unit)
@@ -388,20 +391,34 @@ NJ_HD unsigned nj_seg_event_of_jump(const NjArgs& a, int row, unsigned which) {
 // ------------------------------------------------------------------------------------------------
 // forward: one warp = R = 4*TR units
 // ------------------------------------------------------------------------------------------------
+// forward of one tile of R = 4*TR segment units by one warp, in three parts (the weight-stationary kernels of small
+// batches run begin / finish on warp 0 and replace the Euler steps by CTA-cooperative ones)
 template <int TR>
-NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* reg, const float* wimg, int u0, int u1) {
-    constexpr int R = 4 * TR;
-    constexpr int RS = 16;             // row-slot stride of the per-warp scalar arrays (tallest tile)
+struct NjSegFwd {
+    static constexpr int R = 4 * TR;
+    static constexpr int RS = 16;             // row-slot stride of the per-warp scalar arrays (tallest tile)
+    const NjCfg& c; const NjSeg& s; const NjArgs& a;
     NjSegW w;
-    w.c = &c; w.s = &s; w.wimg = wimg;
-    w.IN = reg + s.f_IN; w.A0 = reg + s.f_A0; w.A1 = reg + s.f_A1; w.OUT = reg + s.f_OUT;
-    w.G0 = w.GOUT = w.GZ = nullptr; w.a_buf_stride = 0; w.g_buf_stride = 0;
-    float* HS = reg + s.f_HS; float* LX = reg + s.f_LX; float* TX = reg + s.f_TX; float* XI = reg + s.f_XI;
-    float* YBJ = reg + s.f_YBJ; float* F = reg + s.f_F;
-    int* I = reinterpret_cast<int*>(reg + s.f_I);
-    w.RK = I + NJS_I_RK * RS;
-    const int d4 = ((c.d + 3) >> 2) << 2, H4 = ((c.H + 3) >> 2) << 2, inf4 = ((c.inf + 3) >> 2) << 2;
-    const int sI = s.sI, sO = s.sO, sH = s.sH, sD = s.sD;
+    float *HS, *LX, *TX, *XI, *YBJ, *F;
+    int* I;
+    int d4, H4, inf4, sI, sO, sH, sD;
+    int maxlen, any_jump;
+
+    NJ_HD NjSegFwd(const NjCfg& c_, const NjSeg& s_, const NjArgs& a_, float* reg, const float* wimg) : c(c_), s(s_), a(a_) {
+        w.c = &c; w.s = &s; w.wimg = wimg;
+        w.IN = reg + s.f_IN; w.A0 = reg + s.f_A0; w.A1 = reg + s.f_A1; w.OUT = reg + s.f_OUT;
+        w.G0 = w.GOUT = w.GZ = nullptr; w.a_buf_stride = 0; w.g_buf_stride = 0;
+        HS = reg + s.f_HS; LX = reg + s.f_LX; TX = reg + s.f_TX; XI = reg + s.f_XI;
+        YBJ = reg + s.f_YBJ; F = reg + s.f_F;
+        I = reinterpret_cast<int*>(reg + s.f_I);
+        w.RK = I + NJS_I_RK * RS;
+        d4 = ((c.d + 3) >> 2) << 2; H4 = ((c.H + 3) >> 2) << 2; inf4 = ((c.inf + 3) >> 2) << 2;
+        sI = s.sI; sO = s.sO; sH = s.sH; sD = s.sD;
+        maxlen = 0; any_jump = 0;
+    }
+
+    // unit descriptors, h = encoder(start value)
+    NJ_HD void begin(int u0, int u1) {
     // ---- unit descriptors ----
     NJ_LANES(lane) {
         if (lane < R) {
@@ -420,7 +437,7 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
         }
     }
     NJ_SYNCWARP();
-    int maxlen = 0, any_jump = 0;
+    maxlen = 0; any_jump = 0;
     for (int r = 0; r < R; ++r) {
         maxlen = I[NJS_I_LEN * RS + r] > maxlen ? I[NJS_I_LEN * RS + r] : maxlen;
         any_jump |= (I[NJS_I_ROW * RS + r] >= 0);
@@ -452,8 +469,11 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
         }
     }
     NJ_SYNCWARP();
-    // ---- Euler steps ----
-    for (int j = 0; j < maxlen; ++j) {
+    }
+
+    // Euler step j of the tile (units shorter than j + 1 steps rest)
+    NJ_HD void step(int j) {
+
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             const bool active = j < I[NJS_I_LEN * RS + er];
@@ -492,7 +512,10 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
             }
         }
         NJ_SYNCWARP();
-    }
+        }
+
+    // hT of the units that end their path, then the jump that ends the segment
+    NJ_HD void finish() {
     // ---- hT of the units that end their path ----
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
@@ -578,6 +601,15 @@ NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
         }
     }
     NJ_SYNCWARP();
+    }
+};
+
+template <int TR>
+NJ_HD void nj_seg_forward_warp(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* reg, const float* wimg, int u0, int u1) {
+    NjSegFwd<TR> f(c, s, a, reg, wimg);
+    f.begin(u0, u1);
+    for (int j = 0; j < f.maxlen; ++j) f.step(j);
+    f.finish();
 }
 
 NJ_HD void nj_seg_cta_forward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
@@ -688,7 +720,7 @@ NJ_HD void nj_seg_tile_store(const NjCfg& c, int netid, int l, int og, int kg, c
 // the kernel) while the same source is correct in the host simulation.
 NJ_HDN void nj_seg_dw_overflow(const NjCfg* cp, const NjSeg* sp, const NjSegB* tp, int netid, float* gpart, int tid, int nt, int Pt) {
     const NjCfg& c = *cp; const NjSeg& s = *sp; const NjSegB& t = *tp;
-    for (int T = NJ_SEG_NT_MAX * nt + tid; T < s.tiles_total; T += nt) {
+    for (int T = s.nt_slots * nt + tid; T < s.tiles_total; T += nt) {
         int l, og, kg;
         if (!nj_seg_tile_decode(c, s, netid, T, l, og, kg)) continue;
         float q[20];
@@ -708,7 +740,7 @@ NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid,
         if (!nj_seg_tile_decode(c, s, netid, slot * nt + tid, l, og, kg)) continue;
         nj_seg_dw_rows(c, s, t, netid, l, og, kg, Pt, acc + slot * 20);
     }
-    if (s.tiles_total > NJ_SEG_NT_MAX * nt) nj_seg_dw_overflow(&c, &s, &t, netid, gpart, tid, nt, Pt);
+    if (s.tiles_total > s.nt_slots * nt) nj_seg_dw_overflow(&c, &s, &t, netid, gpart, tid, nt, Pt);
 }
 
 // writes the register tiles into this CTA's partial gradient image (pre-zeroed by the caller)
@@ -747,9 +779,14 @@ NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, flo
     t.I[NJS_I_RK * P + (r)] = (valid) ? (int)nj_row_key(c.seed_lo, c.seed_hi,                                      \
         (unsigned)(t.I[NJS_I_PATH * P + (r)] + a.b.path_id_offset), (ev)) : 0
 
-template <int TR>
+// REV: how the Euler steps are reversed.  The default (NjSegWarpRev) is the warp-local recompute + dx below followed by the
+// CTA-wide dW phase; the weight-stationary kernels of small batches (njode_path.cuh) pass a functor whose step(j) runs
+// on all warps of the CTA, and then only warp 0 executes the warp-local sections of this function.
+struct NjSegWarpRev { static constexpr bool stat = false; NJ_HD void step(int) const {} };
+
+template <int TR, class REV = NjSegWarpRev>
 NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, const NjSegB& t, float* nj_acc_base,
-                           int cta, int u0, int u1) {
+                           int cta, int u0, int u1, const REV& rev = REV()) {
     constexpr int R = 4 * TR;
     const int P = s.P_b, nt = s.nt_b, Pt = R * s.nw_b;
     float* simg = smem + s.b_img;
@@ -784,6 +821,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
         // ================= the jump at the end of the segment, reversed =================
         // J1-J4 (warp-local): Y_bj = ro(h_before), E = enc(X_obs), Y = ro(E); loss gradients; ro backward at E
         NJ_WARPS(wp, s.nw_b) {
+                if (REV::stat && wp != 0) continue;
             NJ_SEGB_WARP_VIEW();
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
@@ -973,6 +1011,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
             NJ_SYNC();
             // J5: encoder at X_obs, backward with g = dL/dE (from Y only)
             NJ_WARPS(wp, s.nw_b) {
+                if (REV::stat && wp != 0) continue;
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -990,6 +1029,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
             NJ_SYNC();
             // J6: readout at h_before, backward with g = dL/dY_bj -> gradient wrt h at the segment end
             NJ_WARPS(wp, s.nw_b) {
+                if (REV::stat && wp != 0) continue;
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -1021,8 +1061,11 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
             NJ_SYNC();
         }
         // ================= Euler steps, reversed =================
+        if (REV::stat) { NJ_SYNC(); }              // GH / TX / tau of warp 0's prelude and jump reversal are visible to every warp
         for (int j = maxlen - 1; j >= 0; --j) {
+            if (REV::stat) { rev.step(j); continue; }
             NJ_WARPS(wp, s.nw_b) {
+                if (REV::stat && wp != 0) continue;
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -1069,6 +1112,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
         }
         // ================= the start encoder, reversed =================
         NJ_WARPS(wp, s.nw_b) {
+                if (REV::stat && wp != 0) continue;
             NJ_SEGB_WARP_VIEW();
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);

@@ -49,3 +49,13 @@ def uninstall():
     if _saved:
         _ext.cuda_runner = _saved[0]
         del _saved[:]
+
+
+def plan_kind(model, pb, which="fwd"):
+    """kernel family the planner picks: set of {"seg", "segstat", "path", "pathstat", "pipe"} (see njode_hostsim_plan_kind)"""
+    import ctypes as C
+    dll = runner().lib.dll
+    mt = model._model_struct(0)
+    bits = dll.njode_hostsim_plan_kind(C.byref(mt), C.byref(getattr(pb, which)))
+    assert bits >= 0, bits
+    return {n for i, n in enumerate(("seg", "segstat", "path", "pathstat", "pipe")) if bits >> i & 1}

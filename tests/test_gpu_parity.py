@@ -23,6 +23,8 @@ def no_test_runner():
     hostsim_util.uninstall()
     yield
     os.environ.pop("NJODE_FORCE_TILE", None)
+    os.environ.pop("NJODE_SEG_STAT", None)
+    os.environ.pop("NJODE_FORCE_TR", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -218,6 +220,7 @@ def test_recompute_mode_allocates_no_history(recompute_on):
         hT, loss = m.forward_prepared(pb)
         loss.backward()                            # warm-up: workspaces exist
         torch.cuda.synchronize()
+        del hT, loss                               # the warm-up graph (and what it kept) is gone before the baseline is read
         for p in m.parameters():
             p.grad = None
         torch.cuda.reset_peak_memory_stats()
@@ -228,5 +231,43 @@ def test_recompute_mode_allocates_no_history(recompute_on):
         torch.cuda.synchronize()
         peaks[mode] = held
         del hT, loss
-    assert peaks["off"] >= 4 * 100 * 20000 * 10           # [S, B, H] fp32
-    assert peaks["on"] < 2 * 1024 * 1024                  # hT + scalars only
+    assert peaks["off"] >= 4 * 100 * 20000 * 10, peaks    # [S, B, H] fp32
+    assert peaks["on"] < 2 * 1024 * 1024, peaks           # hT + scalars only
+
+
+# ---- small segment batches: the planner gives them to the weight-stationary kernels (nj_segstat_*); the 12-warp tile
+# kernels of big batches are kept covered on the same small cases (NJODE_SEG_STAT=0) ----
+SEG_NAMES = [n for n in NAMES if "masked" not in n and "gru" not in n]
+
+
+@pytest.mark.parametrize("stat", ["0", "1"])
+@pytest.mark.parametrize("name", SEG_NAMES)
+def test_segment_units_both_kernel_families(name, stat):
+    os.environ["NJODE_SEG_STAT"] = stat
+    parity_util.check_training_call(name, DEV, with_hT_grad=True)
+    parity_util.check_training_call(name, DEV)
+
+
+@pytest.mark.parametrize("tr", ["1", "2"])
+@pytest.mark.parametrize("B", [40, 200, 1500])
+def test_segment_stationary_kernels_train_mode(B, tr):
+    """the reference's batch of 200 (and a smaller / larger one) in train mode, both tile heights, with and without a
+    gradient into hT; 3-Linear ODE network at B = 40"""
+    os.environ["NJODE_SEG_STAT"] = "1"
+    os.environ["NJODE_FORCE_TR"] = tr
+    cfg = cases.demo_cfg(dropout_rate=0.1, ode_nn=[[50, "tanh"]] * (1 if B == 40 else 2))
+    batch = cases.grid_batch(B, 1, 100, 0.1, seed=27)
+    parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=8, device=DEV, train=True, grad_hT=True)
+    parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=8, device=DEV, train=True)
+    import ctypes as C
+    from njode_b200 import _ext
+    dll = _ext.cuda_lib().dll
+    dll.njode_last_kernel.argtypes, dll.njode_last_kernel.restype = [C.c_int], C.c_char_p
+    assert b"segstat" in dll.njode_last_kernel(0) and b"segstat" in dll.njode_last_kernel(1)
+
+
+def test_segment_stationary_kernels_recompute(recompute_on):
+    os.environ["NJODE_SEG_STAT"] = "1"
+    cfg = cases.demo_cfg(dropout_rate=0.1)
+    batch = cases.grid_batch(300, 1, 100, 0.1, seed=28)
+    parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=9, device=DEV, train=True, grad_hT=True)

@@ -19,7 +19,11 @@ NAMES = cases.golden_names()
 @pytest.fixture(autouse=True)
 def sim_runner():
     hostsim_util.install()
+    # the golden cases are tiny: left alone the planner would give every segment batch to the weight-stationary kernels
+    # of small batches; the tests below choose (NJODE_SEG_STAT = 1 / unset) where those are the subject
+    os.environ["NJODE_SEG_STAT"] = "0"
     yield
+    os.environ.pop("NJODE_SEG_STAT", None)
     hostsim_util.uninstall()
     os.environ.pop("NJODE_FORCE_TILE", None)
     os.environ.pop("NJODE_FORCE_TR", None)
@@ -349,3 +353,48 @@ def test_recompute_mode_saves_nothing(recompute_on):
     m.eval()
     hT, loss = parity_util.call(m, batch, meta, "cpu")
     assert loss.grad_fn is not None and loss.grad_fn.saved == ()
+
+
+# ---- segment units of small batches on the weight-stationary Euler steps (njode_path.cuh, nj_segstat_*) ----
+@pytest.mark.parametrize("tr", [1, 2])
+@pytest.mark.parametrize("name", SEG_NAMES)
+def test_segment_stationary_kernels(name, tr):
+    os.environ["NJODE_SEG_STAT"] = "1"
+    os.environ["NJODE_FORCE_TR"] = str(tr)
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    parity_util.check_training_call(name, "cpu")
+
+
+@pytest.mark.parametrize("tr", [1, 2])
+@pytest.mark.parametrize("layers", [1, 2])
+def test_segment_stationary_kernels_train_mode_dropout(tr, layers):
+    """2- and 3-Linear ODE networks (the register tiles hold up to three layers), several CTAs, dropout masks replayed"""
+    os.environ["NJODE_SEG_STAT"] = "1"
+    os.environ["NJODE_FORCE_TR"] = str(tr)
+    cfg = cases.demo_cfg(dropout_rate=0.2, input_size=2, output_size=2, ode_nn=[[50, "tanh"]] * layers)
+    batch = cases.grid_batch(40, 2, 25, 0.2, seed=16)
+    parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
+    parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=False)
+
+
+def test_segment_stationary_kernels_recompute(recompute_on):
+    os.environ["NJODE_SEG_STAT"] = "1"
+    cfg = cases.demo_cfg(dropout_rate=0.15)
+    batch = cases.grid_batch(60, 1, 30, 0.2, seed=12)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 30, 1.0, seed=6, device="cpu", train=True, grad_hT=True)
+
+
+def test_planner_gives_the_reference_batch_to_the_stationary_kernels():
+    """B200 launch plan (148 SMs): the reference's own batch of 200 paths x 100 steps (~2 200 segments) takes the
+    weight-stationary kernels, a batch of 20 000 paths the 12-warp tile kernels; ODE networks wider than the register
+    tiles (2 x 100) never do"""
+    os.environ.pop("NJODE_SEG_STAT", None)
+    os.environ["NJODE_SIM_SMS"] = "148"
+    for B, layers, want in ((200, [[50, "tanh"]] * 2, True), (20000, [[50, "tanh"]] * 2, False), (200, [[100, "tanh"]] * 2, False)):
+        cfg = cases.demo_cfg(ode_nn=layers)
+        m = models.NJODE(**cfg)
+        batch = cases.grid_batch(B, 1, 100, 0.1, seed=3)
+        pb = m.prepare_batch(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 0.01, 1.0, batch["start_X"], batch["n_obs_ot"])
+        for which in ("fwd", "bwd_all", "bwd_loss"):
+            kind = hostsim_util.plan_kind(m, pb, which)
+            assert "seg" in kind and ("segstat" in kind) == want, (B, layers, which, kind)
