@@ -100,7 +100,34 @@ __global__ void __launch_bounds__(384) nj_path_bwd_pipe_kernel(const __grid_cons
                                                                const __grid_constant__ NjArgs args) {
     nj_path_cta_backward_pipe<RG, TR>(cfg, path, args, nj_smem, blockIdx.x);
 }
+// thread-per-neuron kernels of small whole-path batches (njode_tpn.cuh): F / T / D warps around a glue warp
+typedef NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 1> NjTpnA1;
+typedef NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 4> NjTpnA4;
+typedef NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 1> NjTpnB1;
+typedef NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 4> NjTpnB4;
+template <class D>
+__global__ void __launch_bounds__(NJN_NT_FWD) nj_tpn_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
+                                                                const __grid_constant__ NjArgs args) {
+    nj_tpn_cta_forward<D>(cfg, path, args, nj_smem);
+}
+template <class D>
+__global__ void __launch_bounds__(NJN_NT_BWD) nj_tpn_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
+                                                                const __grid_constant__ NjArgs args) {
+    nj_tpn_cta_backward<D>(cfg, path, args, nj_smem, blockIdx.x);
+}
 typedef void (*nj_path_kern_t)(const NjCfg, const NjPath, const NjArgs);
+static nj_path_kern_t nj_tpn_pick(int cls, int R, bool bwd, const char** name) {
+    if (!bwd) {
+        if (cls == 1 && R == 1) { *name = "nj_tpn_fwd_kernel<A,1>"; return nj_tpn_fwd_kernel<NjTpnA1>; }
+        if (cls == 1) { *name = "nj_tpn_fwd_kernel<A,4>"; return nj_tpn_fwd_kernel<NjTpnA4>; }
+        if (R == 1) { *name = "nj_tpn_fwd_kernel<B,1>"; return nj_tpn_fwd_kernel<NjTpnB1>; }
+        *name = "nj_tpn_fwd_kernel<B,4>"; return nj_tpn_fwd_kernel<NjTpnB4>;
+    }
+    if (cls == 1 && R == 1) { *name = "nj_tpn_bwd_kernel<A,1>"; return nj_tpn_bwd_kernel<NjTpnA1>; }
+    if (cls == 1) { *name = "nj_tpn_bwd_kernel<A,4>"; return nj_tpn_bwd_kernel<NjTpnA4>; }
+    if (R == 1) { *name = "nj_tpn_bwd_kernel<B,1>"; return nj_tpn_bwd_kernel<NjTpnB1>; }
+    *name = "nj_tpn_bwd_kernel<B,4>"; return nj_tpn_bwd_kernel<NjTpnB4>;
+}
 static nj_path_kern_t nj_pipe_pick(int rg, int tr, const char** name) {
     if (rg == 1) { *name = "nj_path_bwd_pipe_kernel<1,1>"; return nj_path_bwd_pipe_kernel<1, 1>; }
     if (rg == 2) { *name = "nj_path_bwd_pipe_kernel<2,1>"; return nj_path_bwd_pipe_kernel<2, 1>; }
@@ -309,11 +336,12 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";
-        nj_path_kern_t kern = pl.path.stat ? nj_stat_pick(pl.path.rg_f, pl.path.tr_f, false, &name)
-                                           : nj_path_pick(pl.path.rg_f, pl.path.tr_f, false, &name);
+        nj_path_kern_t kern = pl.path.tpn ? nj_tpn_pick(pl.path.tpn, pl.path.rg_f * pl.path.tr_f, false, &name)
+                              : (pl.path.stat ? nj_stat_pick(pl.path.rg_f, pl.path.tr_f, false, &name)
+                                              : nj_path_pick(pl.path.rg_f, pl.path.tr_f, false, &name));
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_f_bytes));
         if (tm) cudaEventRecord(g_ev[0], st);
-        kern<<<pl.path_grid_f, (pl.path.stat ? pl.path.nw_s : pl.path.nw_f) * 32, pl.path_smem_f_bytes, st>>>(pl.fwd, pl.path, a);
+        kern<<<pl.path_grid_f, pl.path.tpn ? NJN_NT_FWD : (pl.path.stat ? pl.path.nw_s : pl.path.nw_f) * 32, pl.path_smem_f_bytes, st>>>(pl.fwd, pl.path, a);
         nj_set_last_kernel(0, name);
     } else {
         nj_set_last_kernel(0, "nj_fwd_kernel");
@@ -369,7 +397,8 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";
-        nj_path_kern_t kern = pl.path.stat ? nj_stat_pick(pl.path.rg_b, pl.path.tr_b, true, &name)
+        nj_path_kern_t kern = pl.path.tpn ? nj_tpn_pick(pl.path.tpn, pl.path.rg_b * pl.path.tr_b, true, &name)
+                              : pl.path.stat ? nj_stat_pick(pl.path.rg_b, pl.path.tr_b, true, &name)
                               : (pl.path.pipe ? nj_pipe_pick(pl.path.rg_b, pl.path.tr_b, &name)
                                               : nj_path_pick(pl.path.rg_b, pl.path.tr_b, true, &name));
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_b_bytes));

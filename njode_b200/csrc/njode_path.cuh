@@ -44,6 +44,9 @@ struct NjPath {
     int stat, nw_s, b_PART;
     // pipelined backward: dW of the ODE network on helper warps, operand buffers (IN, A, G, GOUT) twice, b_copy floats apart
     int pipe, b_copy;
+    // thread-per-neuron kernels of small batches (njode_tpn.cuh): dimension class (1: demo networks, 2: PhysioNet-shaped),
+    // operand buffers three times
+    int tpn;
 };
 
 // ------------------------------------------------------------------------------------------------

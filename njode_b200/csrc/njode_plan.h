@@ -5,7 +5,7 @@
 #include <algorithm>
 #include "njode_core.cuh"
 #include "njode_seg.cuh"
-#include "njode_path.cuh"
+#include "njode_tpn.cuh"
 
 struct NjPlanOut {
     NjCfg fwd, bwd;
@@ -557,6 +557,32 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         }
         if (stat_R) { s.stat = 1; s.nw_s = nw; }
     }
+    // ---- thread-per-neuron kernels (njode_tpn.cuh): tiles of 1 or 4 paths, one per SM, ODE network of a known dimension class ----
+    int tpn_R = 0;
+    {
+        const NjNet& O = c.net[NJODE_NET_ODE];
+        const char* nt_ = getenv("NJODE_NO_TPN");
+        const char* ft_ = getenv("NJODE_FORCE_TPN");           // tests: whatever the batch size
+        auto fits = [&](int kc0, int kch, int hc) {
+            return O.dim[0] <= 4 * kc0 && O.dim[1] <= 4 * kch && O.dim[2] <= 4 * kch && O.dim[3] <= 4 * hc && c.H <= 4 * hc &&
+                   c.d + 4 * hc <= NJN_T && O.dim[0] <= NJN_T && c.inf <= 2 * NJN_F;
+        };
+        int cls = 0;
+        if (!(nt_ && atoi(nt_)) && O.n == 3) cls = fits(NJN_A_KC0, NJN_A_KCH, NJN_A_HC) ? 1 : (fits(NJN_B_KC0, NJN_B_KCH, NJN_B_HC) ? 2 : 0);
+        if (cls) {
+            if (n <= num_sms) tpn_R = 1;
+            else if ((n + 3) / 4 <= num_sms || (ft_ && atoi(ft_))) tpn_R = 4;
+            if (force_r) tpn_R = (force_r == 1 || force_r == 4) ? force_r : 0;
+        }
+        if (tpn_R) {
+            s.tpn = cls; s.stat = 0; s.nw_s = 0; stat_R = 0;
+            const int kc0 = cls == 1 ? NJN_A_KC0 : NJN_B_KC0, kch = cls == 1 ? NJN_A_KCH : NJN_B_KCH, hc = cls == 1 ? NJN_A_HC : NJN_B_HC;
+            // the register tiles read whole classes of columns: rows at least that wide (the padding stays zero)
+            s.sI = std::max(s.sI, nj_stride_act(4 * kc0));
+            s.sA = std::max(s.sA, nj_stride_act(4 * kch));
+            s.sO = std::max(s.sO, nj_stride_act(4 * hc));
+        }
+    }
     // dW tiles of the thread-owned 4x4 scheme; the stationary kernels keep the ODE network's gradient in their own
     // register tiles, so the ODE network has no tiles there
     static const int order[NJODE_NUM_NETS] = {NJODE_NET_ODE, NJODE_NET_RO, NJODE_NET_ENC, NJODE_NET_GRU_HH, NJODE_NET_GRU_IH};
@@ -598,6 +624,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             if ((n + cand - 1) / cand <= num_sms * 12) { R = cand; break; }
         if (force_r) R = force_r;
         if (s.stat) R = stat_R;
+        if (s.tpn) R = tpn_R;
         shape(R, s.rg_f, s.tr_f);
         s.f_region = region(R);
         s.f_warp0 = c.img_floats;
@@ -607,7 +634,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
         if (!nw) return;
         nw = std::max(1, std::min(nw, (s.n_tiles_f + num_sms - 1) / num_sms));
-        if (s.stat) nw = 1;                                   // one tile per CTA at a time, all warps on it
+        if (s.stat || s.tpn) nw = 1;                          // one tile per CTA at a time, all warps on it
         s.nw_f = nw;
         s.f_smem_floats = c.img_floats + nw * s.f_region;
         out.path_grid_f = std::max(1, std::min((s.n_tiles_f + nw - 1) / nw, num_sms));
@@ -623,6 +650,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             s.b_GOUT = o; o += P * s.sO;
             s.b_copy = o - s.b_IN;                            // pipelined backward: a second set of the four operand buffers
             if (s.pipe) o += s.b_copy;
+            if (s.tpn) o += 2 * s.b_copy;                     // thread-per-neuron backward: three sets
             s.b_GZ = o; o += P * s.sI;
             s.b_OUT = o; o += P * s.sO;
             s.b_GH = o; o += P * s.sH;
@@ -651,11 +679,12 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         if (force_r) R = force_r;
         int nw = std::max(1, std::min(12, (P_want + R - 1) / R));
         if (s.stat) { R = stat_R; nw = 1; }
+        if (s.tpn) { R = tpn_R; nw = 1; }
         // pipelined dW: enough helper warps to hold the ODE network's tiles in their registers
         const int ode_tiles = s.tile_base[NJODE_NET_RO][0];
         const int helpers_min = std::max(3, (ode_tiles + 32 * NJP_HSLOTS - 1) / (32 * NJP_HSLOTS));
         const char* np_ = getenv("NJODE_NO_PIPE");
-        if (!s.stat && !(np_ && atoi(np_)) && helpers_min <= 8) {
+        if (!s.stat && !s.tpn && !(np_ && atoi(np_)) && helpers_min <= 8) {
             // rows per warp so that the row warps leave room for the helpers
             int Rp = R;
             while ((P_want + Rp - 1) / Rp > 12 - helpers_min && Rp < 8 && !force_r) Rp *= 2;
@@ -683,6 +712,10 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         s.nt_slots = std::min(NJ_SEG_NT_MAX, (tiles + s.nt_b - 1) / s.nt_b);
         if (s.stat) { s.nt_b = 32 * s.nw_s; s.nt_slots = 0; }
         if (s.pipe) { s.nt_b = 32 * 12; s.nt_slots = 0; }
+        if (s.tpn) {
+            s.nt_b = NJN_NT_BWD; s.nt_slots = 0;
+            if (ode_tiles > NJN_D * NJN_DSLOTS) return;
+        }
         s.n_tiles_b = (n + s.P_b - 1) / s.P_b;
         out.path_grid_b = std::max(1, std::min(s.n_tiles_b, num_sms));
         out.path_smem_b_bytes = (size_t)s.b_smem_floats * 4;

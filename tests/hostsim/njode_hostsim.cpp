@@ -25,8 +25,8 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
     const char* fp = getenv("NJODE_FORCE_TILE");
     if (!nj_plan_all(*m, *b, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
     if (getenv("NJODE_DEBUG_PLAN"))
-        fprintf(stderr, "[plan] units %d kind %d E %d -> seg %d (stat %d) path %d stat %d nw_s %d pipe %d (fwd rg %d tr %d nw %d | bwd rg %d tr %d nw %d nt %d P %d slots %d tiles %d)\n",
-                b->n_units, b->unit_kind, b->E, out.seg.ok, out.seg.stat, out.path.ok, out.path.stat, out.path.nw_s, out.path.pipe, out.path.rg_f, out.path.tr_f, out.path.nw_f, out.path.rg_b,
+        fprintf(stderr, "[plan] units %d kind %d E %d -> seg %d (stat %d) path %d stat %d tpn %d nw_s %d pipe %d (fwd rg %d tr %d nw %d | bwd rg %d tr %d nw %d nt %d P %d slots %d tiles %d)\n",
+                b->n_units, b->unit_kind, b->E, out.seg.ok, out.seg.stat, out.path.ok, out.path.stat, out.path.tpn, out.path.nw_s, out.path.pipe, out.path.rg_f, out.path.tr_f, out.path.nw_f, out.path.rg_b,
                 out.path.tr_b, out.path.nw_b, out.path.nt_b, out.path.P_b, out.path.nt_slots, out.path.tiles_total);
     const size_t cap = (size_t)kSimSMs * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
@@ -48,7 +48,7 @@ extern "C" int njode_hostsim_plan_kind(const njode_model_t* model, const njode_b
     NjPlanOut o;
     if (int rc = plan_for(model, bs, o)) return rc;
     return (o.seg.ok ? 1 : 0) | (o.seg.ok && o.seg.stat ? 2 : 0) | (o.path.ok ? 4 : 0) | (o.path.ok && o.path.stat ? 8 : 0) |
-           (o.path.ok && o.path.pipe ? 16 : 0);
+           (o.path.ok && o.path.pipe ? 16 : 0) | (o.path.ok && o.path.tpn ? 32 : 0);
 }
 
 extern "C" int njode_plan(const njode_model_t* model, const njode_batch_t* bs, int, njode_plan_t* p) {
@@ -115,7 +115,13 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
         for (int cta = 0; cta < pl.path_grid_f; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
             if (cta == 0) *a.counter = 0;
-            if (pl.path.stat) {
+            if (pl.path.tpn) {
+                const int R = pl.path.rg_f * pl.path.tr_f;
+                if (pl.path.tpn == 1 && R == 1) nj_tpn_cta_forward<NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 1>>(pl.fwd, pl.path, a, smem.data());
+                else if (pl.path.tpn == 1) nj_tpn_cta_forward<NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 4>>(pl.fwd, pl.path, a, smem.data());
+                else if (R == 1) nj_tpn_cta_forward<NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 1>>(pl.fwd, pl.path, a, smem.data());
+                else nj_tpn_cta_forward<NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 4>>(pl.fwd, pl.path, a, smem.data());
+            } else if (pl.path.stat) {
                 if (pl.path.rg_f == 1) nj_stat_cta_forward<1, 1>(pl.fwd, pl.path, a, smem.data());
                 else if (pl.path.rg_f == 2) nj_stat_cta_forward<2, 1>(pl.fwd, pl.path, a, smem.data());
                 else if (pl.path.tr_f == 1) nj_stat_cta_forward<4, 1>(pl.fwd, pl.path, a, smem.data());
@@ -172,7 +178,13 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         for (int cta = 0; cta < pl.path_grid_b; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
             if (cta == 0) *a.counter = 0;
-            if (pl.path.stat) {
+            if (pl.path.tpn) {
+                const int R = pl.path.rg_b * pl.path.tr_b;
+                if (pl.path.tpn == 1 && R == 1) nj_tpn_cta_backward<NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 1>>(pl.bwd, pl.path, a, smem.data(), cta);
+                else if (pl.path.tpn == 1) nj_tpn_cta_backward<NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 4>>(pl.bwd, pl.path, a, smem.data(), cta);
+                else if (R == 1) nj_tpn_cta_backward<NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 1>>(pl.bwd, pl.path, a, smem.data(), cta);
+                else nj_tpn_cta_backward<NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 4>>(pl.bwd, pl.path, a, smem.data(), cta);
+            } else if (pl.path.stat) {
                 if (pl.path.rg_b == 1) nj_stat_cta_backward<1, 1>(pl.bwd, pl.path, a, smem.data(), cta);
                 else if (pl.path.rg_b == 2) nj_stat_cta_backward<2, 1>(pl.bwd, pl.path, a, smem.data(), cta);
                 else if (pl.path.tr_b == 1) nj_stat_cta_backward<4, 1>(pl.bwd, pl.path, a, smem.data(), cta);

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "hostsim", "njode_hostsim.cpp")
 OUT_DIR = os.path.join(ROOT, "tests", "_hostsim")
 OUT = os.path.join(OUT_DIR, "libnjode_hostsim.so")
-DEPS = [SRC] + [os.path.join(ROOT, "njode_b200", "csrc", f) for f in ("njode_core.cuh", "njode_hash.cuh", "njode_seg.cuh", "njode_path.cuh", "njode_plan.h")] + \
+DEPS = [SRC] + [os.path.join(ROOT, "njode_b200", "csrc", f) for f in ("njode_core.cuh", "njode_hash.cuh", "njode_seg.cuh", "njode_path.cuh", "njode_tpn.cuh", "njode_plan.h")] + \
        [os.path.join(ROOT, "include", "njode_b200.h")]
 
 _runner = None
@@ -58,4 +58,4 @@ def plan_kind(model, pb, which="fwd"):
     mt = model._model_struct(0)
     bits = dll.njode_hostsim_plan_kind(C.byref(mt), C.byref(getattr(pb, which)))
     assert bits >= 0, bits
-    return {n for i, n in enumerate(("seg", "segstat", "path", "pathstat", "pipe")) if bits >> i & 1}
+    return {n for i, n in enumerate(("seg", "segstat", "path", "pathstat", "pipe", "tpn")) if bits >> i & 1}

@@ -25,6 +25,8 @@ def no_test_runner():
     os.environ.pop("NJODE_FORCE_TILE", None)
     os.environ.pop("NJODE_SEG_STAT", None)
     os.environ.pop("NJODE_FORCE_TR", None)
+    os.environ.pop("NJODE_NO_TPN", None)
+    os.environ.pop("NJODE_NO_STAT", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -271,3 +273,46 @@ def test_segment_stationary_kernels_recompute(recompute_on):
     cfg = cases.demo_cfg(dropout_rate=0.1)
     batch = cases.grid_batch(300, 1, 100, 0.1, seed=28)
     parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=9, device=DEV, train=True, grad_hT=True)
+
+
+# ---- small whole-path batches: thread-per-neuron kernels (njode_tpn.cuh), next to the kernels they replace ----
+def _last_kernels():
+    import ctypes as C
+    from njode_b200 import _ext
+    dll = _ext.cuda_lib().dll
+    dll.njode_last_kernel.argtypes, dll.njode_last_kernel.restype = [C.c_int], C.c_char_p
+    return dll.njode_last_kernel(0).decode(), dll.njode_last_kernel(1).decode()
+
+
+@pytest.mark.parametrize("family", ["tpn", "stat", "warp"])
+@pytest.mark.parametrize("B", [50, 300])
+def test_small_physionet_batches_every_kernel_family(B, family):
+    """the reference's PhysioNet batch (50 records; 300: tiles of 4) in train mode, d = H = 41 masked, 2x50 nets, dropout
+    0.2, gradient into hT: thread-per-neuron (the planner's choice), K-split weight-stationary, warp GEMMs"""
+    if family != "tpn":
+        os.environ["NJODE_NO_TPN"] = "1"
+    if family == "warp":
+        os.environ["NJODE_NO_STAT"] = "1"
+    batch = cases.irregular_batch(B, 41, 60, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.2, feat_prob=0.12)
+    cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 60, 1 + 1e-12, seed=5, device=DEV, train=True, grad_hT=True)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 60, 1 + 1e-12, seed=5, device=DEV, train=True)
+    kf, kb = _last_kernels()
+    want = {"tpn": "nj_tpn_", "stat": "nj_stat_", "warp": "nj_path_"}[family]
+    assert want in kf and want in kb, (kf, kb)
+
+
+@pytest.mark.parametrize("B", [60, 400])
+def test_thread_per_neuron_kernels_demo_nets_gru_jump(B):
+    """dimension class A (d = 1, H = 10, 2x50 nets) on whole-path units: the GRU-jump variant of the demo model"""
+    cfg = cases.demo_cfg(use_rnn=True, dropout_rate=0.1)
+    batch = cases.grid_batch(B, 1, 100, 0.1, seed=31)
+    parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=6, device=DEV, train=True, grad_hT=True)
+    kf, kb = _last_kernels()
+    assert "nj_tpn_" in kf and "nj_tpn_" in kb, (kf, kb)
+
+
+def test_thread_per_neuron_kernels_record_paths():
+    """return_path call (evaluation / plotting) of the non-masked demo model: a readout record after every step"""
+    for name in ("bs_ckpt1", "masked_small"):
+        parity_util.check_path_call(name, DEV)

@@ -36,6 +36,8 @@ def sim_runner():
     os.environ.pop("NJODE_NO_PATH", None)
     os.environ.pop("NJODE_PATH_R", None)
     os.environ.pop("NJODE_NO_STAT", None)
+    os.environ.pop("NJODE_NO_TPN", None)
+    os.environ.pop("NJODE_FORCE_TPN", None)
     os.environ.pop("NJODE_NO_PIPE", None)
     os.environ.pop("NJODE_FORCE_PIPE", None)
     os.environ.pop("NJODE_SIM_SMS", None)
@@ -253,13 +255,20 @@ def test_backward_after_a_parameter_update_raises():
 
 
 # ---- whole-path units on the warp GEMMs (njode_path.cuh): every tile shape the planner can pick ----
-STAT = pytest.mark.parametrize("stat", ["warp-gemm", "warp-gemm-pipelined", "weight-stationary"])
+STAT = pytest.mark.parametrize("stat", ["warp-gemm", "warp-gemm-pipelined", "weight-stationary", "thread-per-neuron"])
 
 
 def _pick(stat):
     """small batches take the weight-stationary Euler steps (ODE weights in registers, all warps of a CTA on one tile);
     NJODE_NO_STAT keeps them on the warp-GEMM path kernels that serve the larger batches, whose backward runs the ODE
     network's dW phase on helper warps concurrently with the row warps' next step unless NJODE_NO_PIPE is set"""
+    if stat == "thread-per-neuron":
+        # (njode_tpn.cuh: tiles of 1 or 4 paths; networks outside its dimension classes fall to the kernels below)
+        os.environ["NJODE_FORCE_TPN"] = "1"
+        if os.environ.get("NJODE_PATH_R") in ("2", "8"):
+            pytest.skip("thread-per-neuron tiles have 1 or 4 rows")
+        return
+    os.environ["NJODE_NO_TPN"] = "1"
     if stat != "weight-stationary":
         os.environ["NJODE_NO_STAT"] = "1"
     if stat == "warp-gemm":
@@ -274,8 +283,8 @@ def _pick(stat):
 def test_path_kernels_every_tile_shape(name, rows, stat):
     """rows per warp 1 / 2 (split reduction dimension, partial sums meet in shuffles), 4 and 8: same loss, hT, gradients
     (with a gradient flowing into hT) and recorded paths as the reference"""
-    _pick(stat)
     os.environ["NJODE_PATH_R"] = str(rows)
+    _pick(stat)
     parity_util.check_training_call(name, "cpu", with_hT_grad=True)
     parity_util.check_training_call(name, "cpu")
     parity_util.check_path_call(name, "cpu")
@@ -286,16 +295,16 @@ def test_path_kernels_every_tile_shape(name, rows, stat):
 @pytest.mark.parametrize("name", ["bs_ckpt1", "curt_nobias_relu", "res_case2", "easy_w07_nores"])
 def test_path_kernels_record_paths_of_the_non_masked_model(name, rows, stat):
     """return_path / until_T calls of the non-masked model (evaluate, get_pred) are whole-path units too"""
-    _pick(stat)
     os.environ["NJODE_PATH_R"] = str(rows)
+    _pick(stat)
     parity_util.check_path_call(name, "cpu")
 
 
 @STAT
 @pytest.mark.parametrize("rows", [1, 2, 4, 8])
 def test_path_kernels_train_mode_dropout(rows, stat):
-    _pick(stat)
     os.environ["NJODE_PATH_R"] = str(rows)
+    _pick(stat)
     cfg = dict(cases.CONFIGS["masked_small"], dropout_rate=0.25)
     batch = cases.irregular_batch(11, 5, 10, seed=21, masked=True, times_f32=True)
     parity_util.check_against_oracle(cfg, batch, 0.05, 1 + 1e-12, seed=3, device="cpu", train=True, grad_hT=True)
@@ -311,10 +320,25 @@ def test_path_kernels_physionet_shape():
 
 
 @pytest.mark.parametrize("B", [50, 300])
+def test_thread_per_neuron_kernels_physionet_shape_with_the_b200_launch_plan(B):
+    """the reference's PhysioNet batch of 50 records (one path per CTA) and 300 records (tiles of 4) with the launch plan
+    of a 148-SM device: dimension class B (84 / 52 / 44), dropout on, gradient into hT"""
+    os.environ["NJODE_SIM_SMS"] = "148"
+    batch = cases.irregular_batch(B, 41, 12, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
+    cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
+    m = models.NJODE(**cfg)
+    pb = m.prepare_batch(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 1.0 / 12, 1 + 1e-12, batch["start_X"], batch["n_obs_ot"], M=batch["M"])
+    assert "tpn" in hostsim_util.plan_kind(m, pb, "fwd") and "tpn" in hostsim_util.plan_kind(m, pb, "bwd_all")
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 12, 1 + 1e-12, seed=5, device="cpu", train=True, grad_hT=True)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 12, 1 + 1e-12, seed=5, device="cpu", train=True)
+
+
+@pytest.mark.parametrize("B", [50, 300])
 def test_weight_stationary_kernels_physionet_shape_with_the_b200_launch_plan(B):
     """the reference's PhysioNet batch of 50 records (one path per CTA) and 300 records (tiles of 4 rows... on 148 SMs:
     2 rows per CTA) with the launch plan of a 148-SM device: d = H = 41 masked, 2x50 nets -> 13 warps per CTA"""
     os.environ["NJODE_SIM_SMS"] = "148"
+    os.environ["NJODE_NO_TPN"] = "1"
     batch = cases.irregular_batch(B, 41, 12, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
     cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
     parity_util.check_against_oracle(cfg, batch, 1.0 / 12, 1 + 1e-12, seed=5, device="cpu", train=True, grad_hT=True)
