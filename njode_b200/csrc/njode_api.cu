@@ -59,18 +59,6 @@ __global__ void __launch_bounds__(384) nj_seg_bwd_kernel_h(const __grid_constant
     nj_seg_cta_backward<true>(cfg, seg, args, nj_smem, blockIdx.x);
 }
 
-// segment units of small batches on the weight-stationary Euler steps (njode_path.cuh, nj_segstat_*)
-template <int TR>
-__global__ void __launch_bounds__(416) nj_segstat_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
-                                                             const __grid_constant__ NjArgs args) {
-    nj_segstat_cta_forward<TR>(cfg, seg, args, nj_smem);
-}
-template <int TR>
-__global__ void __launch_bounds__(416) nj_segstat_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
-                                                             const __grid_constant__ NjArgs args) {
-    nj_segstat_cta_backward<TR>(cfg, seg, args, nj_smem, blockIdx.x);
-}
-
 // whole-path units on the warp GEMMs (njode_path.cuh); one kernel per (row groups, rows per group) tile shape
 template <int RG, int TR>
 __global__ void __launch_bounds__(384) nj_path_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
@@ -114,6 +102,17 @@ template <class D>
 __global__ void __launch_bounds__(NJN_NT_BWD) nj_tpn_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
                                                                 const __grid_constant__ NjArgs args) {
     nj_tpn_cta_backward<D>(cfg, path, args, nj_smem, blockIdx.x);
+}
+// segment units of small batches on the same roles (nj_segtpn_*, tiles of 4 segments)
+template <class D>
+__global__ void __launch_bounds__(NJN_NT_FWD) nj_segtpn_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+                                                                   const __grid_constant__ NjArgs args) {
+    nj_segtpn_cta_forward<D>(cfg, seg, args, nj_smem);
+}
+template <class D>
+__global__ void __launch_bounds__(NJN_NT_BWD) nj_segtpn_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+                                                                   const __grid_constant__ NjArgs args) {
+    nj_segtpn_cta_backward<D>(cfg, seg, args, nj_smem, blockIdx.x);
 }
 typedef void (*nj_path_kern_t)(const NjCfg, const NjPath, const NjArgs);
 static nj_path_kern_t nj_tpn_pick(int cls, int R, bool bwd, const char** name) {
@@ -323,11 +322,11 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     if (pl.seg.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[0], st);
-        if (pl.seg.stat) {
-            auto kern = pl.seg.f_tr[0] == 2 ? nj_segstat_fwd_kernel<2> : nj_segstat_fwd_kernel<1>;
+        if (pl.seg.tpn) {
+            auto kern = pl.seg.tpn == 1 ? nj_segtpn_fwd_kernel<NjTpnA4> : nj_segtpn_fwd_kernel<NjTpnB4>;
             NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
-            kern<<<pl.seg_grid_f, pl.seg.nw_s * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
-            nj_set_last_kernel(0, pl.seg.f_tr[0] == 2 ? "nj_segstat_fwd_kernel<2>" : "nj_segstat_fwd_kernel<1>");
+            kern<<<pl.seg_grid_f, NJN_NT_FWD, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
+            nj_set_last_kernel(0, pl.seg.tpn == 1 ? "nj_segtpn_fwd_kernel<A>" : "nj_segtpn_fwd_kernel<B>");
         } else {
             NJ_CUDA(cudaFuncSetAttribute(nj_seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
             nj_seg_fwd_kernel<<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
@@ -388,12 +387,12 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.seg_grid_b;
-        auto kern = pl.seg.stat ? (pl.seg.b_tr[0] == 2 ? nj_segstat_bwd_kernel<2> : nj_segstat_bwd_kernel<1>)
-                                : (pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h : nj_seg_bwd_kernel);
+        auto kern = pl.seg.tpn ? (pl.seg.tpn == 1 ? nj_segtpn_bwd_kernel<NjTpnA4> : nj_segtpn_bwd_kernel<NjTpnB4>)
+                               : (pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h : nj_seg_bwd_kernel);
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
         kern<<<pl.seg_grid_b, pl.seg.nt_b, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
-        nj_set_last_kernel(1, pl.seg.stat ? (pl.seg.b_tr[0] == 2 ? "nj_segstat_bwd_kernel<2>" : "nj_segstat_bwd_kernel<1>")
-                                          : (pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : "nj_seg_bwd_kernel"));
+        nj_set_last_kernel(1, pl.seg.tpn ? (pl.seg.tpn == 1 ? "nj_segtpn_bwd_kernel<A>" : "nj_segtpn_bwd_kernel<B>")
+                                         : (pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : "nj_seg_bwd_kernel"));
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";

@@ -46,7 +46,7 @@ struct NjPath {
     int pipe, b_copy;
     // thread-per-neuron kernels of small batches (njode_tpn.cuh): dimension class (1: demo networks, 2: PhysioNet-shaped),
     // operand buffers three times
-    int tpn;
+    int tpn, b_TD, b_PRE, f_MB, b_MB, b_GIMG;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -299,9 +299,14 @@ struct NjPW {
     int sI, sA, sO;
     int a_buf_stride, g_buf_stride;
     int* RK;
+    void* coop;                     // mailbox of the cooperative layer service (njode_tpn.cuh) or null: the warp's own GEMM
 };
 
-template <int RG, int TR>
+// cooperative evaluation of one layer by the F threads of a thread-per-neuron CTA, posted by the glue warp (njode_tpn.cuh)
+NJ_HD void nj_coop_post_fwd(void* mailbox, const NjWL& L, int o_store);
+NJ_HD void nj_coop_post_dx(void* mailbox, const NjWD& D);
+
+template <int RG, int TR, bool COOP = false>
 NJ_HD void nj_path_mlp_fwd(const NjPW& w, int netid, bool keep_all, bool skip_last) {
     const NjCfg& c = *w.c;
     const NjNet& N = c.net[netid];
@@ -319,13 +324,14 @@ NJ_HD void nj_path_mlp_fwd(const NjPW& w, int netid, bool keep_all, bool skip_la
         L.drop = (!last) && c.has_drop; L.thr = c.thr; L.keep_scale = c.keep_scale;
         L.rk = w.RK; L.tag = (unsigned)(netid * 16 + l + 1);
         L.o_base = 0;
-        nj_pg_layer_fwd<RG, TR>(L, N.to[l], N.tol[l], N.nch[l]);
+        if (COOP) nj_coop_post_fwd(w.coop, L, 8 * (N.to[l] * (N.nch[l] - 1) + N.tol[l]));
+        else nj_pg_layer_fwd<RG, TR>(L, N.to[l], N.tol[l], N.nch[l]);
         NJ_SYNCWARP();
         in = L.out; in_s = L.out_s;
     }
 }
 
-template <int RG, int TR>
+template <int RG, int TR, bool COOP = false>
 NJ_HD void nj_path_mlp_dx(const NjPW& w, int netid, bool need_in_grad) {
     const NjCfg& c = *w.c;
     const NjNet& N = c.net[netid];
@@ -344,7 +350,8 @@ NJ_HD void nj_path_mlp_dx(const NjPW& w, int netid, bool need_in_grad) {
         }
         D.drop = c.has_drop; D.keep_scale = c.keep_scale; D.one_minus_p = c.one_minus_p;
         D.kg_base = 0;
-        nj_pg_layer_dx<RG, TR>(D);
+        if (COOP) nj_coop_post_dx(w.coop, D);
+        else nj_pg_layer_dx<RG, TR>(D);
         NJ_SYNCWARP();
     }
 }
@@ -356,7 +363,7 @@ NJ_HD unsigned nj_path_jump_key(const NjCfg& c, const NjArgs& a, int p, int jump
 // ================================================================================================
 // forward: one warp = R = RG*TR whole paths
 // ================================================================================================
-template <int RG, int TR>
+template <int RG, int TR, bool COOP = false>
 struct NjPathFwd {
     static constexpr int R = RG * TR;
     static constexpr int RS = NJP_RS;
@@ -370,7 +377,7 @@ struct NjPathFwd {
         w.c = &c; w.wimg = wimg;
         w.IN = reg + s.f_IN; w.A0 = reg + s.f_A0; w.A1 = reg + s.f_A1; w.OUT = reg + s.f_OUT;
         w.G0 = w.GOUT = w.GZ = nullptr; w.a_buf_stride = 0; w.g_buf_stride = 0;
-        w.sI = s.sI; w.sA = s.sA; w.sO = s.sO;
+        w.sI = s.sI; w.sA = s.sA; w.sO = s.sO; w.coop = nullptr;
         HS = reg + s.f_HS; EE = reg + s.f_EE; LX = reg + s.f_LX; TX = reg + s.f_TX; XI = reg + s.f_XI; YBJ = reg + s.f_YBJ; YY = reg + s.f_YY;
         MM = reg + s.f_MM; GI = reg + s.f_GI; F = reg + s.f_F;
         I = reinterpret_cast<int*>(reg + s.f_I);
@@ -402,7 +409,7 @@ struct NjPathFwd {
             if (ec0 == 0) w.RK[er] = p >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), event_key) : 0;
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, false, false);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_RO, false, false);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             const int p = I[NJP_I_PATH * RS + er];
@@ -441,7 +448,7 @@ struct NjPathFwd {
             if (ec0 == 0) w.RK[er] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ODE, false, false);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_ODE, false, false);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             for (int c_ = ec0; c_ < c.H; c_ += LPR)
@@ -469,7 +476,7 @@ struct NjPathFwd {
             }
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, false, false);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_RO, false, false);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             for (int c_ = ec0; c_ < c.dout; c_ += LPR) {
@@ -492,14 +499,14 @@ struct NjPathFwd {
                 }
             }
             NJ_SYNCWARP();
-            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_GRU_IH, false, false);
+            nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_GRU_IH, false, false);
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
                 for (int c_ = ec0; c_ < 3 * H; c_ += LPR) GI[er * s3 + c_] = w.OUT[er * sO + c_];
                 for (int c_ = ec0; c_ < H4; c_ += LPR) w.IN[(size_t)er * sI + c_] = c_ < H ? nj_tanh(HS[er * sH + c_]) : 0.f;
             }
             NJ_SYNCWARP();
-            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_GRU_HH, false, false);
+            nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_GRU_HH, false, false);
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
                 const bool act = I[NJP_I_ACT * RS + er] != 0;
@@ -543,7 +550,7 @@ struct NjPathFwd {
                 if (ec0 == 0) w.RK[er] = act ? (int)nj_path_jump_key(c, a, p, NJ_LDG(a.b.row_jump + row), 1u) : 0;
             }
             NJ_SYNCWARP();
-            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, false, false);
+            nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_ENC, false, false);
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
                 const bool act = I[NJP_I_ACT * RS + er] != 0;
@@ -568,7 +575,7 @@ struct NjPathFwd {
             if (ec0 == 0) w.RK[er] = act ? (int)nj_path_jump_key(c, a, p, NJ_LDG(a.b.row_jump + row), 2u) : 0;
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, false, false);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_RO, false, false);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             const bool act = I[NJP_I_ACT * RS + er] != 0;
@@ -647,7 +654,7 @@ struct NjPathFwd {
             }
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, false, false);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_ENC, false, false);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             for (int c_ = ec0; c_ < c.H; c_ += LPR) {
@@ -851,12 +858,13 @@ NJ_HD int nj_pathb_next(const NjPathB& t, int P, int Pt) {
     return m;
 }
 
-template <int RG, int TR>
+template <int RG, int TR, bool COOP = false>
 struct NjPathBwd {
     static constexpr int R = RG * TR;
     const NjCfg& c; const NjPath& s; const NjArgs& a; const NjPathB& t;
     const float* simg;
     int P, d4, H4, inf4, ein4, do4, wa;
+    void* coop = nullptr;
 
     NJ_HD NjPathBwd(const NjCfg& c_, const NjPath& s_, const NjArgs& a_, const NjPathB& t_, const float* simg_)
         : c(c_), s(s_), a(a_), t(t_), simg(simg_) {
@@ -871,7 +879,7 @@ struct NjPathBwd {
         w.IN = t.IN + (size_t)r0 * s.sI; w.A0 = t.A + (size_t)r0 * s.sA; w.A1 = nullptr; w.OUT = t.OUT + (size_t)r0 * s.sO;
         w.G0 = t.G + (size_t)r0 * s.sA; w.GOUT = t.GOUT + (size_t)r0 * s.sO; w.GZ = t.GZ + (size_t)r0 * s.sI;
         w.sI = s.sI; w.sA = s.sA; w.sO = s.sO;
-        w.a_buf_stride = wa; w.g_buf_stride = wa; w.RK = t.I + NJB_I_RK * P + r0;
+        w.a_buf_stride = wa; w.g_buf_stride = wa; w.RK = t.I + NJB_I_RK * P + r0; w.coop = coop;
         return w;
     }
     NJ_HD void set_key(int r, bool valid, unsigned ev) const {
@@ -927,8 +935,8 @@ struct NjPathBwd {
             if (ec0 == 0) set_key(r, true, (unsigned)k);
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ODE, true, true);
-        nj_path_mlp_dx<RG, TR>(w, NJODE_NET_ODE, true);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_ODE, true, true);
+        nj_path_mlp_dx<RG, TR, COOP>(w, NJODE_NET_ODE, true);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             const int r = r0 + er;
@@ -971,7 +979,7 @@ struct NjPathBwd {
             }
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, true, false);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_RO, true, false);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             const int r = r0 + er;
@@ -994,7 +1002,7 @@ struct NjPathBwd {
                 }
             }
             NJ_SYNCWARP();
-            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_GRU_IH, true, false);
+            nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_GRU_IH, true, false);
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
                 const int r = r0 + er;
@@ -1002,7 +1010,7 @@ struct NjPathBwd {
                 for (int c_ = ec0; c_ < H4; c_ += LPR) t.IN[(size_t)r * sI + c_] = c_ < H ? nj_tanh(t.HB[r * sH + c_]) : 0.f;
             }
             NJ_SYNCWARP();
-            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_GRU_HH, true, false);
+            nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_GRU_HH, true, false);
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
                 const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
@@ -1050,7 +1058,7 @@ struct NjPathBwd {
                 if (ec0 == 0) set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 1u);
             }
             NJ_SYNCWARP();
-            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, true, false);
+            nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_ENC, true, false);
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
                 const int r = r0 + er, row = t.I[NJB_I_ROW * P + r];
@@ -1068,7 +1076,7 @@ struct NjPathBwd {
             }
             NJ_SYNCWARP();
         }
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, true, false);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_RO, true, false);
         // loss derivative (compute_loss / compute_loss_2, NJODE/models.py:71-126)
         NJ_LANES(lane) {
             if (lane < R) {
@@ -1116,7 +1124,7 @@ struct NjPathBwd {
             }
         }
         NJ_SYNCWARP();
-        nj_path_mlp_dx<RG, TR>(w, NJODE_NET_RO, true);
+        nj_path_mlp_dx<RG, TR, COOP>(w, NJODE_NET_RO, true);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             const int r = r0 + er;
@@ -1161,7 +1169,7 @@ struct NjPathBwd {
                 }
             }
             NJ_SYNCWARP();
-            nj_path_mlp_dx<RG, TR>(w, NJODE_NET_GRU_HH, true);
+            nj_path_mlp_dx<RG, TR, COOP>(w, NJODE_NET_GRU_HH, true);
         } else {
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
@@ -1177,8 +1185,8 @@ struct NjPathBwd {
                 if (ec0 == 0) set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 1u);
             }
             NJ_SYNCWARP();
-            nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, true, true);
-            nj_path_mlp_dx<RG, TR>(w, NJODE_NET_ENC, c.masked != 0);
+            nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_ENC, true, true);
+            nj_path_mlp_dx<RG, TR, COOP>(w, NJODE_NET_ENC, c.masked != 0);
             if (c.masked) {
                 // imputation X*M + (1 - M)*Y_bj: the gradient wrt the encoder input reaches Y_bj where M = 0
                 NJ_LANES(lane) {
@@ -1236,8 +1244,8 @@ struct NjPathBwd {
             if (ec0 == 0) set_key(r, act, NJ_EVENT_JUMP_BASE + 3u * (unsigned)(act ? NJ_LDG(a.b.row_jump + row) : 0) + 0u);
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_RO, true, true);
-        nj_path_mlp_dx<RG, TR>(w, NJODE_NET_RO, true);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_RO, true, true);
+        nj_path_mlp_dx<RG, TR, COOP>(w, NJODE_NET_RO, true);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             const int r = r0 + er;
@@ -1277,8 +1285,8 @@ struct NjPathBwd {
             if (ec0 == 0) set_key(r, valid, NJ_EVENT_INIT);
         }
         NJ_SYNCWARP();
-        nj_path_mlp_fwd<RG, TR>(w, NJODE_NET_ENC, true, true);
-        nj_path_mlp_dx<RG, TR>(w, NJODE_NET_ENC, false);
+        nj_path_mlp_fwd<RG, TR, COOP>(w, NJODE_NET_ENC, true, true);
+        nj_path_mlp_dx<RG, TR, COOP>(w, NJODE_NET_ENC, false);
     }
 };
 
@@ -2118,193 +2126,3 @@ NJ_HD void nj_stat_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a
     NJ_THREADS(tid, nt) { nj_stat_flush(c, g, NJT_REGS(tid), tid, gpart); }
 }
 
-// ================================================================================================
-// weight-stationary Euler steps for SEGMENT units (non-masked training call at small batch sizes: the reference's own
-// batch of 200 paths is ~2 200 segments of ~10 steps -- 15 units per SM, far too few for the 12-warp tiles of
-// njode_seg.cuh, whose kernels then run one latency-bound warp per scheduler).  Same register-resident ODE network as
-// above; a tile = 4*TR units whose rows step through their OWN Euler steps (unit r is at step s0[r] + j, rests once j
-// reaches its length), warp 0 runs the start encoder and the jump that ends the segments (njode_seg.cuh code).
-// ================================================================================================
-template <bool BWD>
-NJ_HD void nj_segstat_build_in(const NjCfg& c, const NjArgs& a, int tid, int nt, int R, int j, const int* I, int istride,
-                               const float* TX, int sD, const float* tau, float* HS, int sH, float* IN, int sI, int* rk,
-                               const float* GH, float* GOUT, int sO, float* dtv, const float* scratch_j, int sc_stride) {
-    const int inf4 = ((c.inf + 3) >> 2) << 2;
-    const int c_ = tid & 127, groups = nt >> 7;
-    for (int r = tid >> 7; r < R && (tid >> 7) < groups; r += groups) {
-        const int p = I[NJS_I_PATH * istride + r];
-        const bool active = j < I[NJS_I_LEN * istride + r];
-        const int k = I[NJS_I_S0 * istride + r] + j;
-        const float dt = active ? NJ_LDG(a.b.step_dt + k) : 0.f;
-        if (c_ < inf4) {
-            float v = 0.f;
-            if (c_ < c.d) v = TX[r * sD + c_];
-            else if (c_ < c.d + c.H) {
-                float h = 0.f;
-                if (BWD) {
-                    if (active) h = scratch_j ? scratch_j[(size_t)r * sc_stride + c_ - c.d]
-                                              : a.h_hist[((size_t)k * a.b.B + p) * c.H + c_ - c.d];
-                } else {
-                    h = HS[r * sH + c_ - c.d];
-                    if (active && a.h_hist) a.h_hist[((size_t)k * a.b.B + p) * c.H + c_ - c.d] = h;
-                }
-                v = nj_tanh(h);
-            } else if (c_ < c.inf) {
-                const float t_ = tau[r], tcur = active ? NJ_LDG(a.b.step_t + k) : 0.f;
-                if (c_ == c.d + c.H) v = t_;
-                else if (c_ == c.d + c.H + 1) v = tcur - t_;
-                else v = t_ + (tcur - t_);
-            }
-            IN[(size_t)r * sI + c_] = v;
-        }
-        if (BWD && c_ < c.H) GOUT[(size_t)r * sO + c_] = dt * GH[r * sH + c_];
-        if (c_ == 127) {
-            rk[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), (unsigned)k);
-            if (dtv) dtv[r] = dt;
-        }
-    }
-}
-
-template <int TR>
-NJ_HD void nj_segstat_cta_forward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
-    constexpr int R = 4 * TR, RS = 16;
-    const int nt = 32 * s.nw_s;
-    float* simg = smem + s.f_img;
-    nj_stage_image(simg, a.image, c.img_floats, nt);
-    nj_zero(smem + s.f_warp0, s.f_region, nt);
-    NJ_SYNC();
-    const NjStatGeo g = nj_stat_geo(c);
-    NJT_REGS_DECL(nt);
-    NJ_THREADS(tid, nt) { nj_stat_load(c, g, simg, tid, NJT_REGS(tid)); }
-    float* reg = smem + s.f_warp0;
-    NjSegFwd<TR> f(c, s, a, reg, simg);
-    int* slot = f.I + NJS_I_COUNT * RS;
-    float* dtv = f.F + NJS_F_DT * RS;
-    for (;;) {
-        NJ_THREADS(tid, nt) { if (tid == 0) *slot = nj_atomic_inc(a.counter); }
-        NJ_SYNC();
-        const int wt = *slot;
-        NJ_SYNC();
-        if (wt >= s.n_tiles_f) break;
-        int ub, ue;
-        nj_seg_tile_lookup(s.f_ncls, s.f_t0, s.f_u0, s.f_u1, s.f_tr, 4, wt, ub, ue);
-        NJ_WARPS(wp, 1) { if (wp == 0) f.begin(ub, ue); }
-        NJ_SYNC();
-        int maxlen = 0;
-        for (int r = 0; r < R; ++r) maxlen = f.I[NJS_I_LEN * RS + r] > maxlen ? f.I[NJS_I_LEN * RS + r] : maxlen;
-        for (int j = 0; j < maxlen; ++j) {
-            NJ_THREADS(tid, nt) {
-                nj_segstat_build_in<false>(c, a, tid, nt, R, j, f.I, RS, f.TX, s.sD, f.F + NJS_F_TAU * RS, f.HS, s.sH, f.w.IN, s.sI,
-                                           f.w.RK, nullptr, nullptr, 0, dtv, nullptr, 0);
-            }
-            NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, f.w.IN, s.sI, f.w.A0, s.sA, nullptr, 0, nullptr, f.w.RK); }
-            NJ_SYNC();
-            if (g.n == 2) {
-                NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, nullptr, 0, f.HS, s.sH, dtv, f.w.RK); }
-                NJ_SYNC();
-            } else {
-                NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, f.w.A0, s.sA, f.w.A1, s.sA, nullptr, 0, nullptr, f.w.RK); }
-                NJ_SYNC();
-                NJ_THREADS(tid, nt) { nj_stat_layer_fwd<2>(c, g, njt_regs, tid, R, f.w.A1, s.sA, nullptr, 0, f.HS, s.sH, dtv, f.w.RK); }
-                NJ_SYNC();
-            }
-        }
-        NJ_WARPS(wp, 1) { if (wp == 0) { f.maxlen = maxlen; f.finish(); } }
-        NJ_SYNC();
-    }
-}
-
-// the reverse Euler steps of a segment tile on all warps of the CTA (REV functor of nj_seg_bwd_tile)
-template <int TR>
-struct NjSegStatRev {
-    static constexpr bool stat = true;
-    static constexpr int R = 4 * TR;
-    const NjCfg& c; const NjSeg& s; const NjArgs& a; const NjStatGeo& g; NjStatRegs* njt_regs; const NjSegB& t;
-    float* part0; float* part1; int nt, cta;
-
-    NJ_HD void step(int j) const {
-        const int P = s.P_b, nw = s.nw_s, wa = P * s.sA;
-        int* rk = t.I + NJS_I_RK * P;
-        const float* scj = a.scratch ? a.scratch + ((size_t)cta * a.b.S * P + (size_t)j * P) * s.sH : nullptr;
-        NJ_THREADS(tid, nt) {
-            nj_segstat_build_in<true>(c, a, tid, nt, R, j, t.I, P, t.TX, s.sD, t.F + NJS_F_TAU * P, nullptr, s.sH, t.IN, s.sI, rk,
-                                      t.GH, t.GOUT, s.sO, nullptr, scj, s.sH);
-        }
-        NJ_SYNC();
-        float* A0 = t.A; float* A1 = t.A + wa; float* G0 = t.G; float* G1 = t.G + wa;
-        NJ_THREADS(tid, nt) { nj_stat_layer_fwd<0>(c, g, njt_regs, tid, R, t.IN, s.sI, A0, s.sA, nullptr, 0, nullptr, rk); }
-        NJ_SYNC();
-        if (g.n == 3) {
-            NJ_THREADS(tid, nt) { nj_stat_layer_fwd<1>(c, g, njt_regs, tid, R, A0, s.sA, A1, s.sA, nullptr, 0, nullptr, rk); }
-            NJ_SYNC();
-        }
-        const float* pl;
-        if (g.n == 3) {
-            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<2>(g, njt_regs, tid, nw, R, t.GOUT, s.sO, A1, s.sA, part0); }
-            NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 2, R, part0, A1, s.sA, G1, s.sA); }
-            NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
-            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<1>(g, njt_regs, tid, nw, R, G1, s.sA, A0, s.sA, part1); }
-            NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 1, R, part1, A0, s.sA, G0, s.sA); }
-            NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
-            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<0>(g, njt_regs, tid, nw, R, G0, s.sA, t.IN, s.sI, part0); }
-            NJ_SYNC();
-            pl = part0;
-        } else {
-            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<1>(g, njt_regs, tid, nw, R, t.GOUT, s.sO, A0, s.sA, part0); }
-            NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_stat_consume_hidden(c, g, tid, nw, 1, R, part0, A0, s.sA, G0, s.sA); }
-            NJ_THREADS(tid, nt) { NJ_SYNCWARP(); }
-            NJ_THREADS(tid, nt) { nj_stat_layer_bwd<0>(g, njt_regs, tid, nw, R, G0, s.sA, t.IN, s.sI, part1); }
-            NJ_SYNC();
-            pl = part1;
-        }
-        // the partials of layer 0 -> adjoint of h (resting rows: GOUT was 0, so their partials are 0)
-        NJ_THREADS(tid, nt) {
-            const int lane = tid & 31, o = 4 * (tid >> 5) + (lane >> 3), ksl = lane & 7;
-            if (ksl == 0 && o < c.H) {
-                for (int r = 0; r < R; ++r) {
-                    float v = 0.f;
-                    for (int wq = 0; wq < nw; ++wq) v += pl[((size_t)r * nw + wq) * NJT_PARTW + c.d + o];
-                    const float th = t.IN[(size_t)r * s.sI + c.d + o];
-                    t.GH[r * s.sH + o] += v * (1.f - th * th);
-                }
-            }
-        }
-        NJ_SYNC();
-    }
-};
-
-template <int TR>
-NJ_HD void nj_segstat_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
-    const int nt = s.nt_b;                       // = 32 * nw_s
-    constexpr int R = 4 * TR;
-    float* simg = smem + s.b_img;
-    nj_stage_image(simg, a.image, c.img_floats, nt);
-    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
-    float* gpart = a.partials + (size_t)cta * c.img_floats;
-    nj_zero(gpart, c.img_floats, nt);
-    NJ_SYNC();
-    NjSegB t;
-    nj_segb_bind(t, s, smem);
-    const NjStatGeo g = nj_stat_geo(c);
-    NJT_REGS_DECL(nt);
-    NJ_THREADS(tid, nt) { nj_stat_load(c, g, simg, tid, NJT_REGS(tid)); }
-    float* part0 = smem + s.b_PART;
-    float* part1 = part0 + (size_t)R * s.nw_s * NJT_PARTW;
-    const NjSegStatRev<TR> rev{c, s, a, g, njt_regs, t, part0, part1, nt, cta};
-    int* ctl = t.I + NJS_I_COUNT * s.P_b;
-    for (;;) {
-        NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
-        NJ_SYNC();
-        const int tile = ctl[0];
-        NJ_SYNC();
-        if (tile >= s.n_tiles_b) break;
-        int ub, ue;
-        nj_seg_tile_lookup(s.b_ncls, s.b_t0, s.b_u0, s.b_u1, s.b_tr, 4 * s.nw_b, tile, ub, ue);
-        nj_seg_bwd_tile<TR, NjSegStatRev<TR>>(c, s, a, smem, t, nullptr, cta, ub, ue, rev);
-    }
-    NJ_THREADS(tid, nt) { nj_stat_flush(c, g, NJT_REGS(tid), tid, gpart); }
-}

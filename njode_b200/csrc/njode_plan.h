@@ -259,9 +259,9 @@ static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_u
 // ------------------------------------------------------------------------------------------------
 // segment fast path (njode_seg.cuh): eligibility + shared-memory layout
 // ------------------------------------------------------------------------------------------------
-// segment batches of at most this many units per SM take the weight-stationary kernels (measured on B200)
-#ifndef NJ_SEGSTAT_MAX_UNITS_PER_SM
-#define NJ_SEGSTAT_MAX_UNITS_PER_SM 32
+// segment batches of at most this many units per SM take the thread-per-neuron kernels (measured on B200)
+#ifndef NJ_SEGTPN_MAX_UNITS_PER_SM
+#define NJ_SEGTPN_MAX_UNITS_PER_SM 32
 #endif
 
 static inline int nj_seg_fwd_region(const NjCfg& c, NjSeg& s, int R) {
@@ -282,13 +282,14 @@ static inline int nj_seg_fwd_region(const NjCfg& c, NjSeg& s, int R) {
     return (o + 3) & ~3;
 }
 
-static inline int nj_seg_bwd_layout(const NjCfg& c, NjSeg& s, int P) {
+static inline int nj_seg_bwd_layout(const NjCfg& c, NjSeg& s, int P, int sets = 1) {
     int o = c.img_floats;
     s.b_img = 0;
     s.b_IN = o; o += P * s.sI;
     s.b_A = o; o += s.nA * P * s.sA;
     s.b_G = o; o += s.nA * P * s.sA;
     s.b_GOUT = o; o += P * s.sO;
+    s.b_copy = o - s.b_IN; o += (sets - 1) * s.b_copy;       // thread-per-neuron backward: the operand buffers three times
     s.b_GZ = o; o += P * s.sI;
     s.b_OUT = o; o += P * s.sO;
     s.b_GH = o; o += P * s.sH;
@@ -360,72 +361,54 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
         }
     }
     s.tiles_total = tiles;
-    // ---- small batches: weight-stationary Euler steps (njode_path.cuh, nj_segstat_*): one tile of 4 or 8 segments per
-    // CTA at a time, all warps of the CTA on its steps, the ODE network and its gradient in registers ----
+    // ---- small batches: thread-per-neuron kernels (njode_tpn.cuh, nj_segtpn_*): tiles of 4 segments, one per CTA at a time ----
     {
         const NjNet& O = c.net[NJODE_NET_ODE];
-        const char* fs = getenv("NJODE_SEG_STAT");            // 0: never, 1: whatever the batch size (tests)
+        const char* fs = getenv("NJODE_SEG_TPN");             // 0: never, 1: whatever the batch size (tests)
         const int want = fs ? atoi(fs) : -1;
-        bool ok = want != 0 && (O.n == 2 || O.n == 3);
-        int maxo = c.H;
-        for (int l = 0; l < O.n && ok; ++l) {
-            if (O.dim[l] > (l == 0 ? 96 : 64)) ok = false;
-            maxo = std::max(maxo, O.dim[l + 1]);
-        }
-        const int nws = std::max(4, (maxo + 3) / 4);
-        if (nws > 13) ok = false;
-        if (ok && want < 0 && n_units > NJ_SEGSTAT_MAX_UNITS_PER_SM * num_sms) ok = false;
-        if (ok) {
-            const char* ftr_ = getenv("NJODE_FORCE_TR");
-            int tr = n_units > 4 * num_sms ? 2 : 1;
-            if (ftr_ && atoi(ftr_)) tr = atoi(ftr_) >= 2 ? 2 : 1;
-            const int R = 4 * tr;
-            s.stat = 1; s.nw_s = nws;
-            // the ODE network has no thread-owned 4x4 tiles here; the jump networks' tiles all go through the partial image
-            tiles = 0;
-            for (int oi = 0; oi < 3; ++oi) {
-                const NjNet& N = c.net[order[oi]];
-                for (int l = 0; l < NJODE_MAX_LINEAR; ++l) {
-                    if (order[oi] == NJODE_NET_ODE) { s.tile_base[order[oi]][l] = 0x3FFFFFFF; continue; }
-                    s.tile_base[order[oi]][l] = tiles;
-                    if (l < N.n) tiles += ((N.dim[l] + 3) / 4) * ((N.dim[l + 1] + 3) / 4);
-                }
-            }
-            s.tiles_total = tiles;
+        auto fits = [&](int kc0, int kch, int hc) {
+            return O.dim[0] <= 4 * kc0 && O.dim[1] <= 4 * kch && O.dim[2] <= 4 * kch && O.dim[3] <= 4 * hc && c.H <= 4 * hc &&
+                   c.d + 4 * hc <= NJN_T && O.dim[0] <= NJN_T && c.inf <= 2 * NJN_F;
+        };
+        int cls = 0;
+        if (want != 0 && O.n == 3) cls = fits(NJN_A_KC0, NJN_A_KCH, NJN_A_HC) ? 1 : (fits(NJN_B_KC0, NJN_B_KCH, NJN_B_HC) ? 2 : 0);
+        if (cls && want < 0 && n_units > NJ_SEGTPN_MAX_UNITS_PER_SM * num_sms) cls = 0;
+        if (cls && tiles - s.tile_base[NJODE_NET_RO][0] >= 0 && s.tile_base[NJODE_NET_RO][0] > NJN_D * NJN_DSLOTS) cls = 0;
+        if (cls) {
+            NjSeg keep = s;
+            const int kc0 = cls == 1 ? NJN_A_KC0 : NJN_B_KC0, kch = cls == 1 ? NJN_A_KCH : NJN_B_KCH, hc = cls == 1 ? NJN_A_HC : NJN_B_HC;
+            s.tpn = cls;
+            s.sI = std::max(s.sI, nj_stride_act(4 * kc0));
+            s.sA = std::max(s.sA, nj_stride_act(4 * kch));
+            s.sO = std::max(s.sO, nj_stride_act(4 * hc));
             const int n_loss_ = std::max(0, std::min(b.n_loss_units, n_units));
             const int rb[2] = {0, n_loss_}, re[2] = {n_loss_, n_units};
             const int z1[2] = {0, 0}, z2[2] = {0, 0};
-            const int one[1] = {tr};
-            s.f_region = nj_seg_fwd_region(c, s, R);
+            const int one[1] = {1};
+            s.f_region = nj_seg_fwd_region(c, s, NJN_SEG_R);
             s.f_img = 0; s.f_warp0 = c.img_floats;
             s.f_ncls = nj_seg_classes(rb, re, z1, z2, one, 1, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr);
             s.n_tiles_f = s.f_t0[s.f_ncls];
             s.nw_f = 1;
             s.f_smem_floats = c.img_floats + s.f_region;
-            int fl = nj_seg_bwd_layout(c, s, R);
-            s.b_PART = fl; fl += 2 * R * nws * NJT_PARTW;
-            s.b_smem_floats = fl; s.P_b = R; s.nw_b = 1; s.nt_b = 32 * nws; s.nt_slots = 0;
+            int fl = nj_seg_bwd_layout(c, s, NJN_SEG_R, 3);
+            s.b_TD = fl; fl += 2 * NJN_DSLOTS * NJN_D;
+            s.b_PRE = fl; fl += 16 + 2 * NJN_SEG_R * s.sH;
+            fl = (fl + 3) & ~3;
+            s.b_GIMG = fl; fl += c.img_floats - c.net[NJODE_NET_ENC].w_img[0];
+            s.b_smem_floats = (fl + 3) & ~3; s.P_b = NJN_SEG_R; s.nw_b = 1; s.nt_b = NJN_NT_BWD; s.nt_slots = 0;
             s.b_ncls = nj_seg_classes(rb, re, z1, z2, one, 1, 4, s.b_t0, s.b_u0, s.b_u1, s.b_tr);
             s.n_tiles_b = s.b_t0[s.b_ncls];
             if ((size_t)s.f_smem_floats * 4 <= smem_limit && (size_t)s.b_smem_floats * 4 <= smem_limit) {
                 out.seg_smem_f_bytes = (size_t)s.f_smem_floats * 4;
                 out.seg_smem_b_bytes = (size_t)s.b_smem_floats * 4;
-                out.seg_grid_f = std::max(1, std::min(s.n_tiles_f, num_sms));
+                // forward CTAs are 3 warps with up to 255 registers: several per SM, tiles handed out by an atomic counter
+                out.seg_grid_f = std::max(1, std::min(s.n_tiles_f, 2 * num_sms));
                 out.seg_grid_b = std::max(1, std::min(s.n_tiles_b, num_sms));
                 s.ok = 1;
                 return;
             }
-            // does not fit: the warp kernels below
-            s.stat = 0; s.nw_s = 0; s.b_PART = 0;
-            tiles = 0;
-            for (int oi = 0; oi < 3; ++oi) {
-                const NjNet& N = c.net[order[oi]];
-                for (int l = 0; l < NJODE_MAX_LINEAR; ++l) {
-                    s.tile_base[order[oi]][l] = tiles;
-                    if (l < N.n) tiles += ((N.dim[l] + 3) / 4) * ((N.dim[l + 1] + 3) / 4);
-                }
-            }
-            s.tiles_total = tiles;
+            s = keep;                                         // does not fit: the warp kernels below
         }
     }
     const char* ftr = getenv("NJODE_FORCE_TR");
@@ -615,6 +598,8 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             s.f_GI = o; if (c.use_rnn) o += R * s.s3;
             s.f_F = o; o += NJP_F_COUNT * NJP_RS;
             s.f_I = o; o += NJP_I_COUNT * NJP_RS + 4;
+            o = (o + 3) & ~3;
+            s.f_MB = o; if (s.tpn) o += (int)((sizeof(NjCoopMB) + 15) / 16) * 4;    // mailbox of the cooperative jump layers
             return (o + 3) & ~3;
         };
         // the smallest tile height whose warps still fit the machine in one wave of 12-warp CTAs: smaller tiles = more
@@ -668,6 +653,13 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             s.b_GI = o; if (c.use_rnn) o += P * s.s3;
             s.b_GHH = o; if (c.use_rnn) o += P * s.s3;
             s.b_PART = o; if (s.stat) o += 2 * P * s.nw_s * NJT_PARTW;
+            // thread-per-neuron backward: dW tile table [slots * owners][2], prefetch slots (time, step size, h) of the next step
+            s.b_TD = o; if (s.tpn) o += 2 * NJN_DSLOTS * NJN_D;
+            s.b_PRE = o; if (s.tpn) o += 4 + 2 * P * s.sH;
+            o = (o + 3) & ~3;
+            s.b_MB = o; if (s.tpn) o += (int)((sizeof(NjCoopMB) + 15) / 16) * 4;
+            // gradient image of the jump networks (everything behind the ODE network; zeroed with the other buffers)
+            s.b_GIMG = o; if (s.tpn) o += c.img_floats - c.net[NJODE_NET_ENC].w_img[0];
             s.b_F = o; o += NJP_F_COUNT * P;
             s.b_I = o; o += NJB_I_COUNT * P + 4 + nw + 4;
             return (o + 3) & ~3;

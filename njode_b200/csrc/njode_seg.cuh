@@ -98,9 +98,9 @@ struct NjSeg {
     // [u0, u1) in tiles of 4*tr (forward, per warp) or 4*tr*nw_b (backward, per CTA) rows; t0 = first tile id.
     int f_ncls, f_t0[7], f_u0[6], f_u1[6], f_tr[6];
     int b_ncls, b_t0[7], b_u0[6], b_u1[6], b_tr[6];
-    // weight-stationary Euler steps for small batches (njode_path.cuh): one CTA of nw_s warps per tile of 4*tr units, the
-    // ODE network's weights and gradient in registers; b_PART: input-gradient partials [2][P_b][nw_s][96]
-    int stat, nw_s, b_PART;
+    // thread-per-neuron kernels of small batches (njode_tpn.cuh): dimension class, operand buffers three times (b_copy apart),
+    // dW tile table, prefetch slots, gradient image of the jump networks in shared memory
+    int tpn, b_copy, b_TD, b_PRE, b_GIMG;
 };
 
 // tile id -> (class, first unit, one-past-last unit)
@@ -782,7 +782,12 @@ NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, flo
 // REV: how the Euler steps are reversed.  The default (NjSegWarpRev) is the warp-local recompute + dx below followed by the
 // CTA-wide dW phase; the weight-stationary kernels of small batches (njode_path.cuh) pass a functor whose step(j) runs
 // on all warps of the CTA, and then only warp 0 executes the warp-local sections of this function.
-struct NjSegWarpRev { static constexpr bool stat = false; NJ_HD void step(int) const {} };
+struct NjSegWarpRev {
+    static constexpr bool stat = false;
+    static constexpr bool glue = true;             // this instantiation contains the warp-local sections
+    NJ_HD void run(int) const {}
+    NJ_HD float* gpart(float* global_partial) const { return global_partial; }
+};
 
 template <int TR, class REV = NjSegWarpRev>
 NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, const NjSegB& t, float* nj_acc_base,
@@ -790,7 +795,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
     constexpr int R = 4 * TR;
     const int P = s.P_b, nt = s.nt_b, Pt = R * s.nw_b;
     float* simg = smem + s.b_img;
-    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    float* gpart = rev.gpart(a.partials + (size_t)cta * c.img_floats);
     const float gl = NJ_LDG(a.grad_loss);
     const int d4 = ((c.d + 3) >> 2) << 2, H4 = ((c.H + 3) >> 2) << 2, inf4 = ((c.inf + 3) >> 2) << 2, do4 = ((c.dout + 3) >> 2) << 2;
     const int wa = P * s.sA;
@@ -821,7 +826,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
         // ================= the jump at the end of the segment, reversed =================
         // J1-J4 (warp-local): Y_bj = ro(h_before), E = enc(X_obs), Y = ro(E); loss gradients; ro backward at E
         NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && wp != 0) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) continue;
             NJ_SEGB_WARP_VIEW();
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
@@ -1011,7 +1016,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
             NJ_SYNC();
             // J5: encoder at X_obs, backward with g = dL/dE (from Y only)
             NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && wp != 0) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) continue;
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -1029,7 +1034,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
             NJ_SYNC();
             // J6: readout at h_before, backward with g = dL/dY_bj -> gradient wrt h at the segment end
             NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && wp != 0) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) continue;
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -1061,11 +1066,10 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
             NJ_SYNC();
         }
         // ================= Euler steps, reversed =================
-        if (REV::stat) { NJ_SYNC(); }              // GH / TX / tau of warp 0's prelude and jump reversal are visible to every warp
-        for (int j = maxlen - 1; j >= 0; --j) {
-            if (REV::stat) { rev.step(j); continue; }
+        if (REV::stat) { NJ_SYNC(); rev.run(maxlen); }   // (GH / TX / tau of warp 0's prelude and jump reversal are visible to every warp)
+        for (int j = REV::stat ? -1 : maxlen - 1; j >= 0; --j) {
             NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && wp != 0) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) continue;
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -1112,7 +1116,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
         }
         // ================= the start encoder, reversed =================
         NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && wp != 0) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) continue;
             NJ_SEGB_WARP_VIEW();
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);

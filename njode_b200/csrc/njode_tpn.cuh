@@ -54,11 +54,21 @@ template <int KC0_, int KCH_, int HC_, int R_> struct NjTpnDims {
 #define NJN_SYNC_FT() do { if (ROLE == NJN_ROLE_F || ROLE == NJN_ROLE_T) asm volatile("bar.sync 1, 160;" ::: "memory"); } while (0)
 #endif
 
+// 4-byte asynchronous copy global -> shared (prefetch of next step's h / time / step size: a register prefetch shares its
+// scoreboard with the loads of the current step and stalled their first use -- ncu source page, profiles/r2l_*)
+#if defined(NJODE_HOST_SIM)
+NJ_HD void nj_cp_async4(float* dst, const float* src) { *dst = *src; }
+NJ_HD void nj_cp_wait() {}
+#else
+__device__ __forceinline__ void nj_cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void nj_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
 template <class D> struct NjTpnF {
     float w0[4 * D::KC0], w1[4 * D::KCH], w2[4 * D::KCH];
     float b0, b1, b2;
-    float hpre[2 * D::R];            // h of the NEXT step to rebuild (backward), loaded one pipeline iteration ahead
-    float tpre, dpre;                // time / step size of the next step
 };
 template <class D> struct NjTpnT {
     float c2[4 * D::HC], c1[4 * D::KCH], c0[4 * D::KCH];
@@ -76,9 +86,6 @@ NJ_HD void nj_tpn_f_load(const NjCfg& c, const float* simg, int o, NjTpnF<D>& f)
     f.b0 = (o < N.dim[1] && N.b_src[0] >= 0) ? simg[N.b_img[0] + o] : 0.f;
     f.b1 = (o < N.dim[2] && N.b_src[1] >= 0) ? simg[N.b_img[1] + o] : 0.f;
     f.b2 = (o < N.dim[3] && N.b_src[2] >= 0) ? simg[N.b_img[2] + o] : 0.f;
-#pragma unroll
-    for (int j = 0; j < 2 * D::R; ++j) f.hpre[j] = 0.f;
-    f.tpre = 0.f; f.dpre = 0.f;
 }
 
 template <class D>
@@ -140,11 +147,156 @@ NJ_HD float nj_tpn_time_col(const NjCfg& c, int c_, float tau, float tcur) {
 }
 
 // ================================================================================================
+// cooperative layers for the glue warp: the jump networks (readout, encoder, GRU) live in the shared-memory parameter image;
+// a lone warp needs ~2 us per layer for them (K-split lanes, shuffles), which made the ~75 jumps of a PhysioNet record
+// 45 % of the forward and a third of the backward kernel (ncu source page, profiles/r2l_*).  The glue warp keeps its
+// bookkeeping code; wherever it evaluates a layer it posts the layer descriptor to a mailbox and the 64 F threads -- idle
+// during a jump -- compute it, one output (forward) or one float4 group of inputs (input gradient) per thread.
+// ================================================================================================
+struct NjCoopMB { int op, o_store, R, pad; NjWL L; NjWD D; };       // op: 0 done, 1 forward layer, 2 input gradient
+
+template <int R>
+NJ_HD void nj_coop_fwd_rows(const NjWL& L, int o_store, int o) {
+    for (int oo = o; oo < o_store; oo += NJN_F) {
+        float p[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { p[r][0] = 0.f; p[r][1] = 0.f; p[r][2] = 0.f; p[r][3] = 0.f; }
+        const nj_sp wp = nj_sp_of(L.W + (size_t)oo * L.w_s), ap = nj_sp_of(L.in);
+#pragma unroll 4
+        for (int k4 = 0; k4 < L.K4; ++k4) {
+            const nj_f4 w = nj_sp_ld4(NJ_SP_ADD(wp, 4 * k4));
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const nj_f4 v = nj_sp_ld4(NJ_SP_ADD(ap, r * L.in_s + 4 * k4));
+                p[r][0] = fmaf(w.x, v.x, p[r][0]); p[r][1] = fmaf(w.y, v.y, p[r][1]);
+                p[r][2] = fmaf(w.z, v.z, p[r][2]); p[r][3] = fmaf(w.w, v.w, p[r][3]);
+            }
+        }
+        const float bias = L.bias ? L.bias[oo] : 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float v = nj_act(((p[r][0] + p[r][1]) + (p[r][2] + p[r][3])) + bias, L.act);
+            if (L.drop) v = nj_keep(nj_layer_key((unsigned)L.rk[r], L.tag), (unsigned)oo, L.thr) ? v * L.keep_scale : nj_u2f(NJ_DROPPED);
+            L.out[(size_t)r * L.out_s + oo] = v;
+        }
+    }
+}
+
+// gin[r][4kg..] = (sum_o g[r][o] W[o][4kg..]) * act'(aprev) * dropout factor  (nj_pg_dx, njode_path.cuh, without the K split)
+template <int R>
+NJ_HD void nj_coop_dx_rows(const NjWD& L, int o) {
+    for (int kg = o; kg < L.K4in; kg += NJN_F) {
+        float acc[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+        const nj_sp wp = nj_sp_of(L.W + 4 * kg), gp = nj_sp_of(L.g);
+        const int ws = L.w_s;
+        for (int o4 = 0; o4 < L.O4; ++o4) {
+            const nj_sp q = NJ_SP_ADD(wp, 4 * o4 * ws);
+            const nj_f4 w0 = nj_sp_ld4(q), w1 = nj_sp_ld4(NJ_SP_ADD(q, ws)), w2 = nj_sp_ld4(NJ_SP_ADD(q, 2 * ws)), w3 = nj_sp_ld4(NJ_SP_ADD(q, 3 * ws));
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const nj_f4 gv = nj_sp_ld4(NJ_SP_ADD(gp, r * L.g_s + 4 * o4));
+                acc[r][0] = fmaf(gv.x, w0.x, fmaf(gv.y, w1.x, fmaf(gv.z, w2.x, fmaf(gv.w, w3.x, acc[r][0]))));
+                acc[r][1] = fmaf(gv.x, w0.y, fmaf(gv.y, w1.y, fmaf(gv.z, w2.y, fmaf(gv.w, w3.y, acc[r][1]))));
+                acc[r][2] = fmaf(gv.x, w0.z, fmaf(gv.y, w1.z, fmaf(gv.z, w2.z, fmaf(gv.w, w3.z, acc[r][2]))));
+                acc[r][3] = fmaf(gv.x, w0.w, fmaf(gv.y, w1.w, fmaf(gv.z, w2.w, fmaf(gv.w, w3.w, acc[r][3]))));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float v[4] = {acc[r][0], acc[r][1], acc[r][2], acc[r][3]};
+            if (L.aprev) {
+                const nj_f4 av = nj_sp_ld4(nj_sp_of(L.aprev + (size_t)r * L.a_s + 4 * kg));
+                const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float a_ = a4[c];
+                    if (L.drop) {
+                        if (nj_f2u(a_) == NJ_DROPPED) v[c] = 0.f;
+                        else { a_ *= L.one_minus_p; v[c] *= L.keep_scale; }
+                    }
+                    if (L.act_prev == NJODE_ACT_TANH) v[c] *= (1.f - a_ * a_);
+                    else if (L.act_prev == NJODE_ACT_RELU) v[c] = a_ > 0.f ? v[c] : 0.f;
+                }
+            }
+            nj_f4 ov; ov.x = v[0]; ov.y = v[1]; ov.z = v[2]; ov.w = v[3];
+            nj_st4(L.gin + (size_t)r * L.gin_s + 4 * kg, ov);
+        }
+    }
+}
+
+NJ_HD void nj_coop_run(const NjCoopMB* mb, int op, int o) {
+    if (op == 1) { if (mb->R == 1) nj_coop_fwd_rows<1>(mb->L, mb->o_store, o); else nj_coop_fwd_rows<4>(mb->L, mb->o_store, o); }
+    else { if (mb->R == 1) nj_coop_dx_rows<1>(mb->D, o); else nj_coop_dx_rows<4>(mb->D, o); }
+}
+
+#if defined(NJODE_HOST_SIM)
+NJ_HD void nj_coop_post_fwd(void* mailbox, const NjWL& L, int o_store) {
+    NjCoopMB* mb = static_cast<NjCoopMB*>(mailbox);
+    mb->L = L; mb->o_store = o_store;
+    for (int o = 0; o < NJN_F; ++o) nj_coop_run(mb, 1, o);
+}
+NJ_HD void nj_coop_post_dx(void* mailbox, const NjWD& D) {
+    NjCoopMB* mb = static_cast<NjCoopMB*>(mailbox);
+    mb->D = D;
+    for (int o = 0; o < NJN_F; ++o) nj_coop_run(mb, 2, o);
+}
+#define NJN_COOP_DONE(mb) ((void)0)
+#define NJN_COOP_SERVE(mb, o) ((void)0)
+#else
+// glue warp + F threads = 96 threads on named barrier 2
+#define NJN_COOP_BAR() asm volatile("bar.sync 2, 96;" ::: "memory")
+NJ_HD void nj_coop_post_fwd(void* mailbox, const NjWL& L, int o_store) {
+    NjCoopMB* mb = static_cast<NjCoopMB*>(mailbox);
+    if ((threadIdx.x & 31) == 0) { mb->L = L; mb->o_store = o_store; mb->op = 1; }
+    __syncwarp();
+    NJN_COOP_BAR();
+    NJN_COOP_BAR();
+}
+NJ_HD void nj_coop_post_dx(void* mailbox, const NjWD& D) {
+    NjCoopMB* mb = static_cast<NjCoopMB*>(mailbox);
+    if ((threadIdx.x & 31) == 0) { mb->D = D; mb->op = 2; }
+    __syncwarp();
+    NJN_COOP_BAR();
+    NJN_COOP_BAR();
+}
+__device__ __forceinline__ void nj_coop_done(NjCoopMB* mb) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mb->op = 0;
+    __syncwarp();
+    NJN_COOP_BAR();
+}
+__device__ __forceinline__ void nj_coop_serve(const NjCoopMB* mb, int o) {
+    for (;;) {
+        NJN_COOP_BAR();
+        const int op = *reinterpret_cast<const volatile int*>(&mb->op);
+        if (!op) break;
+        nj_coop_run(mb, op, o);
+        NJN_COOP_BAR();
+    }
+}
+#define NJN_COOP_DONE(mb) nj_coop_done(mb)
+#define NJN_COOP_SERVE(mb, o) nj_coop_serve(mb, o)
+#endif
+
+// a section of glue code (warp 0) whose layers the F threads serve
+#if defined(NJODE_HOST_SIM)
+#define NJN_GLUE(mb, stmt) do { stmt; } while (0)
+#else
+#define NJN_GLUE(mb, stmt)                                                                        \
+    do {                                                                                          \
+        if (ROLE == NJN_ROLE_G) { stmt; NJN_COOP_DONE(mb); }                                      \
+        else if (ROLE == NJN_ROLE_F) NJN_COOP_SERVE(mb, (int)threadIdx.x - NJN_F0);               \
+    } while (0)
+#endif
+
+// ================================================================================================
 // forward
 // ================================================================================================
 // F thread o: the whole input rows of step k from the state (first step after a jump / the start / a record)
 template <class D>
-NJ_HD void nj_tpn_fwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1>& f, int o, int k) {
+NJ_HD void nj_tpn_fwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, int o, int k) {
     constexpr int R = D::R, RS = NJP_RS;
     const int inf4 = ((c.inf + 3) >> 2) << 2;
     const float tcur = NJ_LDG(a.b.step_t + k), dt = NJ_LDG(a.b.step_dt + k);
@@ -174,17 +326,20 @@ NJ_HD void nj_tpn_fwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, Nj
 // the three phases of Euler step k for F thread o.  next: step k + 1 follows without a jump in between -- phase 3 then
 // also writes what changes in the input rows (tanh(h), the time columns), the history and the dropout keys of step k + 1
 template <class D>
-NJ_HD void nj_tpn_fwd_p1(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1>& f, NjTpnF<D>& q, int o,
+NJ_HD void nj_tpn_fwd_p1(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, NjTpnF<D>& q, int o,
                          int k, bool next) {
-    if (next && o == NJN_F - 1) { q.tpre = NJ_LDG(a.b.step_t + k + 1); q.dpre = NJ_LDG(a.b.step_dt + k + 1); }
+    if (next && o == NJN_F - 1) {                 // time and step size of step k + 1, consumed in phase 3
+        nj_cp_async4(f.F + NJP_F_CB * NJP_RS + ((k + 1) & 1), a.b.step_t + k + 1);
+        nj_cp_async4(f.F + NJP_F_CB * NJP_RS + 2 + ((k + 1) & 1), a.b.step_dt + k + 1);
+    }
     nj_tpn_hidden<D::KC0, D::R>(c, 0, q.w0, q.b0, o, f.w.IN, s.sI, f.w.A0, s.sA, f.w.RK);
 }
 template <class D>
-NJ_HD void nj_tpn_fwd_p2(const NjCfg& c, const NjPath& s, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1>& f, NjTpnF<D>& q, int o) {
+NJ_HD void nj_tpn_fwd_p2(const NjCfg& c, const NjPath& s, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, NjTpnF<D>& q, int o) {
     nj_tpn_hidden<D::KCH, D::R>(c, 1, q.w1, q.b1, o, f.w.A0, s.sA, f.w.A1, s.sA, f.w.RK);
 }
 template <class D>
-NJ_HD void nj_tpn_fwd_p3(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1>& f, NjTpnF<D>& q, int o,
+NJ_HD void nj_tpn_fwd_p3(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, NjTpnF<D>& q, int o,
                          int k, bool next) {
     constexpr int R = D::R, RS = NJP_RS;
     float acc[R];
@@ -202,12 +357,14 @@ NJ_HD void nj_tpn_fwd_p3(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPat
         }
     }
     if (next && o == NJN_F - 1) {
+        nj_cp_wait();
+        const float tnext = f.F[NJP_F_CB * RS + ((k + 1) & 1)], dnext = f.F[NJP_F_CB * RS + 2 + ((k + 1) & 1)];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float tau = f.F[NJP_F_TAU * RS + r];
-            for (int c_ = c.d + c.H + 1; c_ < c.inf; ++c_) f.w.IN[(size_t)r * s.sI + c_] = nj_tpn_time_col(c, c_, tau, q.tpre);
+            for (int c_ = c.d + c.H + 1; c_ < c.inf; ++c_) f.w.IN[(size_t)r * s.sI + c_] = nj_tpn_time_col(c, c_, tau, tnext);
             f.w.RK[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(f.I[NJP_I_PATH * RS + r] + a.b.path_id_offset), (unsigned)(k + 1));
-            f.F[NJP_F_CA * RS + ((k + 1) & 1) * 4 + r] = q.dpre;
+            f.F[NJP_F_CA * RS + ((k + 1) & 1) * 4 + r] = dnext;
         }
     }
 }
@@ -234,7 +391,10 @@ NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
     const float* simg = smem;
     float* reg = smem + s.f_warp0;
     int* slot = reinterpret_cast<int*>(reg + s.f_I) + NJP_I_COUNT * NJP_RS;
-    NjPathFwd<RG, 1> f(c, s, a, reg, simg);
+    NjPathFwd<RG, 1, true> f(c, s, a, reg, simg);
+    NjCoopMB* mb = reinterpret_cast<NjCoopMB*>(reg + s.f_MB);
+    NJ_THREADS(tid, NJN_NT_FWD) { if (tid == 0) { mb->R = R; mb->op = 0; } }
+    f.w.coop = mb;
     NJN_FREGS_DECL(D);
     NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_f_load<D>(c, simg, o, NJN_FREGS(o)); }
     const bool rec = a.b.E > 0;
@@ -246,7 +406,7 @@ NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
         NJ_SYNC();
         if (wt >= s.n_tiles_f) break;
         const int ub = wt * R, ue = ub + R < a.b.n_units ? ub + R : a.b.n_units;
-        if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) { NJ_WARPS(wp, 1) { if (wp == 0) f.begin(ub, ue); } }
+        NJN_GLUE(mb, f.begin(ub, ue));
         NJ_SYNC();
         int k = 0, gi = 0;
         for (;;) {
@@ -262,9 +422,7 @@ NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
                     NJN_SYNC_F();
                     NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p3<D>(c, s, a, f, NJN_FREGS(o), o, k, false); }
                     NJ_SYNC();
-                    if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) {
-                        NJ_WARPS(wp, 1) { if (wp == 0) f.record(NJ_LDG(a.b.step_event + k), NJ_EVENT_PATH_RO_BASE + (unsigned)k); }
-                    }
+                    NJN_GLUE(mb, f.record(NJ_LDG(a.b.step_event + k), NJ_EVENT_PATH_RO_BASE + (unsigned)k));
                     NJ_SYNC();
                 }
             } else if (k < kend) {
@@ -284,14 +442,7 @@ NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
             if (nk > S) break;
             const bool any = f.any_jumps_at(nk);
             NJ_SYNC();                            // every thread has read the cursors before the glue warp advances them
-            if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) {
-                NJ_WARPS(wp, 1) {
-                    if (wp == 0) {
-                        if (any) f.jump(nk);
-                        if (rec) f.record(NJ_LDG(a.b.jump_event + gi), NJ_EVENT_JUMP_BASE + 3u * (unsigned)gi + 2u);
-                    }
-                }
-            }
+            NJN_GLUE(mb, { if (any) f.jump(nk); if (rec) f.record(NJ_LDG(a.b.jump_event + gi), NJ_EVENT_JUMP_BASE + 3u * (unsigned)gi + 2u); });
             if (rec) ++gi;
             NJ_SYNC();
         }
@@ -321,16 +472,20 @@ NJ_HD void nj_tpn_set(NjPathB& t, int off) { t.IN += off; t.A += off; t.G += off
 // F, phase 1: the input rows of step e into its operand set (h from the history; the value was loaded one iteration ahead
 // when `have`), then the load for step e - 1 is issued (`pre`)
 template <class D>
-NJ_HD void nj_tpn_bwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, const NjPathB& t0, const NjPathB& te, NjTpnF<D>& q, int o,
+NJ_HD void nj_tpn_bwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem, const NjPathB& t0, const NjPathB& te, int o,
                             int e, bool have, bool pre) {
     constexpr int R = D::R;
     const int P = s.P_b, inf4 = ((c.inf + 3) >> 2) << 2;
-    // (every thread keeps the time of the step: the time columns belong to whichever threads their indices fall on)
-    float tcur = q.tpre;
-    if (!have) tcur = NJ_LDG(a.b.step_t + e);
-    if (pre) q.tpre = NJ_LDG(a.b.step_t + e - 1);
+    float* pre_f = smem + s.b_PRE;               // [0..1] time, [2..3] step size of the step (by parity), then h [2][P][sH]
+    float* HP = pre_f + 4;
+    if (have) nj_cp_wait();                      // this thread's copies of the previous iteration (h of step e)
+    const float tcur = have ? pre_f[e & 1] : NJ_LDG(a.b.step_t + e);
+    if (o == 0) {
+        if (!have) pre_f[2 + (e & 1)] = NJ_LDG(a.b.step_dt + e);
+        if (pre) { nj_cp_async4(pre_f + ((e - 1) & 1), a.b.step_t + e - 1); nj_cp_async4(pre_f + 2 + ((e - 1) & 1), a.b.step_dt + e - 1); }
+    }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {                // (the planner admits at most 2 * NJN_F input columns; constant indices into hpre)
+    for (int i = 0; i < 2; ++i) {                // (the planner admits at most 2 * NJN_F input columns)
         const int c_ = o + NJN_F * i;
         if (c_ >= inf4) break;
 #pragma unroll
@@ -342,8 +497,8 @@ NJ_HD void nj_tpn_bwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, co
                 float h = 0.f;
                 if (p >= 0) {
                     const float* hh = a.h_hist + ((size_t)e * a.b.B + p) * c.H + c_ - c.d;
-                    h = have ? q.hpre[2 * r + i] : NJ_LDG(hh);
-                    if (pre) q.hpre[2 * r + i] = NJ_LDG(hh - (size_t)a.b.B * c.H);
+                    h = have ? HP[((e & 1) * P + r) * s.sH + c_ - c.d] : NJ_LDG(hh);
+                    if (pre) nj_cp_async4(HP + (((e - 1) & 1) * P + r) * s.sH + c_ - c.d, hh - (size_t)a.b.B * c.H);
                 }
                 v = nj_tanh(h);
             } else if (c_ < c.inf) v = nj_tpn_time_col(c, c_, t0.F[NJP_F_TAU * P + r], tcur);
@@ -369,8 +524,8 @@ NJ_HD float nj_tpn_hidden_grad(const NjCfg& c, int l, float v, float a_) {
     return v;
 }
 
-template <class D>
-NJ_HD void nj_tpn_bwd_t1(const NjCfg& c, const NjPath& s, const NjPathB& te, const NjTpnT<D>& q, int k) {
+template <class D, class S, class TB>
+NJ_HD void nj_tpn_bwd_t1(const NjCfg& c, const S& s, const TB& te, const NjTpnT<D>& q, int k) {
     constexpr int R = D::R;
     const int wa = s.P_b * s.sA;
     float acc[R];
@@ -380,8 +535,8 @@ NJ_HD void nj_tpn_bwd_t1(const NjCfg& c, const NjPath& s, const NjPathB& te, con
 #pragma unroll
     for (int r = 0; r < R; ++r) te.G[wa + (size_t)r * s.sA + k] = k < O ? nj_tpn_hidden_grad(c, 1, acc[r], te.A[wa + (size_t)r * s.sA + k]) : 0.f;
 }
-template <class D>
-NJ_HD void nj_tpn_bwd_t2(const NjCfg& c, const NjPath& s, const NjPathB& te, const NjTpnT<D>& q, int k) {
+template <class D, class S, class TB>
+NJ_HD void nj_tpn_bwd_t2(const NjCfg& c, const S& s, const TB& te, const NjTpnT<D>& q, int k) {
     constexpr int R = D::R;
     const int wa = s.P_b * s.sA;
     float acc[R];
@@ -419,26 +574,63 @@ NJ_HD void nj_tpn_bwd_t3(const NjCfg& c, const NjPath& s, const NjPathB& t0, con
     }
 }
 
-// D thread x: dW of the ODE network for the rows of the step held in operand set `te`
-NJ_HD void nj_tpn_dw(const NjCfg& c, const NjPath& s, const NjPathB& te, float* acc, int x, int Pt) {
+// D thread x owns the tiles T = slot * NJN_D + x of the ODE network.  Their operand addresses are decoded once per launch
+// into a table in shared memory: [T][0] offset of g (floats from the operand set's IN buffer), [T][1] offset of a | layer << 24
+// (-1: no such tile) -- decoding per step cost the D warps 1 100 instructions per step and made them the critical path
+NJ_HD bool nj_tpn_ode_tile(const NjCfg& c, const NjPath& s, int T, int& l, int& og, int& kg) { return nj_path_tile_decode(c, s, NJODE_NET_ODE, T, l, og, kg); }
+NJ_HD bool nj_tpn_ode_tile(const NjCfg& c, const NjSeg& s, int T, int& l, int& og, int& kg) { return nj_seg_tile_decode(c, s, NJODE_NET_ODE, T, l, og, kg); }
+
+template <class S>
+NJ_HD void nj_tpn_dw_table(const NjCfg& c, const S& s, float* smem, int x) {
     const int ode_tiles = s.tile_base[NJODE_NET_RO][0];        // the ODE network's tiles come first
+    const NjNet& N = c.net[NJODE_NET_ODE];
+    int* td = reinterpret_cast<int*>(smem + s.b_TD);
+    const int P = s.P_b;
+    for (int slot = 0; slot < NJN_DSLOTS; ++slot) {
+        const int T = slot * NJN_D + x;
+        int l, og, kg, e0 = -1, e1 = 0;
+        if (T < ode_tiles && nj_tpn_ode_tile(c, s, T, l, og, kg)) {
+            e0 = (l == N.n - 1 ? s.b_GOUT : s.b_G + l * P * s.sA) - s.b_IN + 4 * og;
+            e1 = ((l == 0 ? s.b_IN : s.b_A + (l - 1) * P * s.sA) - s.b_IN + 4 * kg) | (l << 24);
+        }
+        td[2 * T] = e0; td[2 * T + 1] = e1;
+    }
+}
+
+template <int R, class S>
+NJ_HD void nj_tpn_dw(const NjCfg& c, const S& s, const float* smem, const float* set_in, float* acc, int x) {
+    const int* td = reinterpret_cast<const int*>(smem + s.b_TD);
+    const int last = c.net[NJODE_NET_ODE].n - 1;
 #pragma unroll
     for (int slot = 0; slot < NJN_DSLOTS; ++slot) {
         const int T = slot * NJN_D + x;
-        if (T >= ode_tiles) break;
-        int l, og, kg;
-        if (!nj_path_tile_decode(c, s, NJODE_NET_ODE, T, l, og, kg)) continue;
-        nj_path_dw_rows(c, s, te, NJODE_NET_ODE, l, og, kg, Pt, nullptr, 1, acc + slot * 20);
+        const int e0 = td[2 * T], e1 = td[2 * T + 1];
+        if (e0 < 0) continue;
+        const int l = e1 >> 24;
+        const int g_s = l == last ? s.sO : s.sA, a_s = l == 0 ? s.sI : s.sA;
+        const nj_sp gq = nj_sp_of(set_in + e0), aq = nj_sp_of(set_in + (e1 & 0xFFFFFF));
+        float* q = acc + slot * 20;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const nj_f4 gv = nj_sp_ld4(NJ_SP_ADD(gq, r * g_s));
+            const nj_f4 v = nj_sp_ld4(NJ_SP_ADD(aq, r * a_s));
+            q[0] = fmaf(gv.x, v.x, q[0]); q[1] = fmaf(gv.x, v.y, q[1]); q[2] = fmaf(gv.x, v.z, q[2]); q[3] = fmaf(gv.x, v.w, q[3]);
+            q[4] = fmaf(gv.y, v.x, q[4]); q[5] = fmaf(gv.y, v.y, q[5]); q[6] = fmaf(gv.y, v.z, q[6]); q[7] = fmaf(gv.y, v.w, q[7]);
+            q[8] = fmaf(gv.z, v.x, q[8]); q[9] = fmaf(gv.z, v.y, q[9]); q[10] = fmaf(gv.z, v.z, q[10]); q[11] = fmaf(gv.z, v.w, q[11]);
+            q[12] = fmaf(gv.w, v.x, q[12]); q[13] = fmaf(gv.w, v.y, q[13]); q[14] = fmaf(gv.w, v.z, q[14]); q[15] = fmaf(gv.w, v.w, q[15]);
+            q[16] += gv.x; q[17] += gv.y; q[18] += gv.z; q[19] += gv.w;
+        }
     }
 }
-NJ_HD void nj_tpn_dw_flush(const NjCfg& c, const NjPath& s, const float* acc, float* gpart, int x) {
+template <class S>
+NJ_HD void nj_tpn_dw_flush(const NjCfg& c, const S& s, const float* acc, float* gpart, int x) {
     const int ode_tiles = s.tile_base[NJODE_NET_RO][0];
 #pragma unroll
     for (int slot = 0; slot < NJN_DSLOTS; ++slot) {
         const int T = slot * NJN_D + x;
         if (T >= ode_tiles) break;
         int l, og, kg;
-        if (nj_path_tile_decode(c, s, NJODE_NET_ODE, T, l, og, kg)) nj_seg_tile_store(c, NJODE_NET_ODE, l, og, kg, acc + slot * 20, gpart, false);
+        if (nj_tpn_ode_tile(c, s, T, l, og, kg)) nj_seg_tile_store(c, NJODE_NET_ODE, l, og, kg, acc + slot * 20, gpart, false);
     }
 }
 
@@ -447,15 +639,24 @@ NJ_HD void nj_tpn_bwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
     constexpr int R = D::R, RG = (R >= 4 ? 4 : R);
     const int nt = NJN_NT_BWD, P = s.P_b;
     const bool G = ROLE == NJN_ALL || ROLE == NJN_ROLE_G;
-    float* gpart = a.partials + (size_t)cta * c.img_floats;
+    // the jump networks' dW tiles are read-modify-written at every jump: into a gradient image in SHARED memory (the
+    // global partial image cost ~3 us of L2 round trips per dW phase, four or five phases per jump), copied out once
+    // (the ODE network comes first in the image and has its own accumulators: the shared copy starts behind it)
+    const int ode_floats = c.net[NJODE_NET_ENC].w_img[0];
+    float* gout = a.partials + (size_t)cta * c.img_floats;
+    float* gpart = smem + s.b_GIMG - ode_floats;
     NjPathB t;
     nj_pathb_bind(t, s, smem);
-    const NjPathBwd<RG, 1> B(c, s, a, t, smem);
+    NjPathBwd<RG, 1, true> B(c, s, a, t, smem);
+    NjCoopMB* mb = reinterpret_cast<NjCoopMB*>(smem + s.b_MB);
+    NJ_THREADS(tid, nt) { if (tid == 0) { mb->R = R; mb->op = 0; } }
+    B.coop = mb;
     NJN_FREGS_DECL(D);
     NJN_TREGS_DECL(D);
     NJN_DACC_DECL();
     NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_f_load<D>(c, smem, o, NJN_FREGS(o)); }
     NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, k) { nj_tpn_t_load<D>(c, smem, k, NJN_TREGS(k)); }
+    NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { nj_tpn_dw_table(c, s, smem, x); }      // (read by its writer only)
     int* ctl = t.I + NJB_I_COUNT * P;
     for (;;) {
         NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
@@ -496,21 +697,21 @@ NJ_HD void nj_tpn_bwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
         for (int k = a.b.S; ; ) {
             if (nk == k) {
                 // (the pipeline is empty between runs: the jump works on operand set 0, its dW phases go through the partial image)
-                if (G) { NJ_WARPS(wp, 1) { if (wp == 0) B.jump_p1(0, 0, k); } }
+                NJN_GLUE(mb, B.jump_p1(0, 0, k));
                 NJ_SYNC();
                 NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_RO, gpart, tid, nt, R, t.MSK, R); }
                 NJ_SYNC();
-                if (G) { NJ_WARPS(wp, 1) { if (wp == 0) B.jump_p2(0, 0); } }
+                NJN_GLUE(mb, B.jump_p2(0, 0));
                 NJ_SYNC();
                 NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, c.use_rnn ? NJODE_NET_GRU_HH : NJODE_NET_ENC, gpart, tid, nt, R, t.MSK, R); }
                 NJ_SYNC();
                 if (c.use_rnn) {
-                    if (G) { NJ_WARPS(wp, 1) { if (wp == 0) B.jump_p2b(0, 0); } }
+                    NJN_GLUE(mb, B.jump_p2b(0, 0));
                     NJ_SYNC();
                     NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_GRU_IH, gpart, tid, nt, R, t.MSK, R); }
                     NJ_SYNC();
                 }
-                if (G) { NJ_WARPS(wp, 1) { if (wp == 0) B.jump_p3(0, 0); } }
+                NJN_GLUE(mb, B.jump_p3(0, 0));
                 NJ_SYNC();
                 NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_RO, gpart, tid, nt, R, t.MSK, R); }
                 NJ_SYNC();
@@ -525,16 +726,10 @@ NJ_HD void nj_tpn_bwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
                 // operand set of step e: e mod 3 (views built here: an indexed array of views would live in local memory)
                 NjPathB tF = t, tT = t, tD = t;
                 nj_tpn_set(tF, ((eF + 3) % 3) * s.b_copy); nj_tpn_set(tT, ((eT + 3) % 3) * s.b_copy); nj_tpn_set(tD, ((eD + 3) % 3) * s.b_copy);
-                float dtn = 0.f;
                 // phase 1
-                NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { if (vF) nj_tpn_bwd_build<D>(c, s, a, t, tF, NJN_FREGS(o), o, eF, j > 0, j + 1 < n); }
-#if !defined(NJODE_HOST_SIM)
-                if (ROLE == NJN_ROLE_T && vF) dtn = NJ_LDG(a.b.step_dt + eF);      // used in phase 3
-#else
-                if (vF) dtn = a.b.step_dt[eF];
-#endif
+                NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { if (vF) nj_tpn_bwd_build<D>(c, s, a, smem, t, tF, o, eF, j > 0, j + 1 < n); }
                 NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) { if (vT) nj_tpn_bwd_t1<D>(c, s, tT, NJN_TREGS(x), x); }
-                NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { if (vD) nj_tpn_dw(c, s, tD, NJN_DACC_OF(x), x, R); }
+                NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { if (vD) nj_tpn_dw<R>(c, s, smem, tD.IN, NJN_DACC_OF(x), x); }
                 NJN_SYNC_FT();
                 // phase 2
                 NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) {
@@ -545,20 +740,22 @@ NJ_HD void nj_tpn_bwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
                 // phase 3
                 NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) {
                     if (vF) nj_tpn_hidden<D::KCH, R>(c, 1, NJN_FREGS(o).w1, NJN_FREGS(o).b1, o, tF.A, s.sA, tF.A + P * s.sA, s.sA, t.I + NJB_I_RK * P);
+                    if (o == 0) nj_cp_wait();            // time / step size of the next step: visible to everyone after the barrier
                 }
                 NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) {
-                    if (vT || vF) nj_tpn_bwd_t3<D>(c, s, t, vT ? &tT : nullptr, vF ? &tF : nullptr, dtn, NJN_TREGS(x), x);
+                    if (vT || vF) nj_tpn_bwd_t3<D>(c, s, t, vT ? &tT : nullptr, vF ? &tF : nullptr, smem[s.b_PRE + 2 + (eF & 1)], NJN_TREGS(x), x);
                 }
                 NJ_SYNC();
             }
             k = lo;
         }
-        if (G) { NJ_WARPS(wp, 1) { if (wp == 0) B.start_local(0); } }
+        NJN_GLUE(mb, B.start_local(0));
         NJ_SYNC();
         NJ_THREADS(tid, nt) { nj_stat_dw(&c, &s, &t, NJODE_NET_ENC, gpart, tid, nt, R, nullptr, R); }
         NJ_SYNC();
     }
-    NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { nj_tpn_dw_flush(c, s, NJN_DACC_OF(x), gpart, x); }
+    NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { nj_tpn_dw_flush(c, s, NJN_DACC_OF(x), gout, x); }
+    NJ_THREADS(tid, nt) { for (int i = ode_floats + tid; i < c.img_floats; i += nt) gout[i] = gpart[i]; }
 }
 
 template <class D>
@@ -566,7 +763,7 @@ NJ_HD void nj_tpn_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a,
     const int nt = NJN_NT_BWD;
     nj_stage_image(smem, a.image, c.img_floats, nt);
     nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
-    nj_zero(a.partials + (size_t)cta * c.img_floats, c.img_floats, nt);
+    nj_zero(a.partials + (size_t)cta * c.img_floats, c.net[NJODE_NET_ENC].w_img[0], nt);     // (rows no dW tile covers stay 0)
     NJ_SYNC();
 #if defined(NJODE_HOST_SIM)
     nj_tpn_bwd_body<D, NJN_ALL>(c, s, a, smem, cta);
@@ -575,5 +772,318 @@ NJ_HD void nj_tpn_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a,
     else if (threadIdx.x < NJN_T0) nj_tpn_bwd_body<D, NJN_ROLE_F>(c, s, a, smem, cta);
     else if (threadIdx.x < NJN_D0) nj_tpn_bwd_body<D, NJN_ROLE_T>(c, s, a, smem, cta);
     else nj_tpn_bwd_body<D, NJN_ROLE_D>(c, s, a, smem, cta);
+#endif
+}
+
+// ================================================================================================
+// SEGMENT units (non-masked training call) of small batches: the reference's own batch of 200 paths is ~2 200 segments of
+// ~10 Euler steps, 15 per SM -- the 12-warp tiles of njode_seg.cuh then run one latency-bound warp per scheduler and the
+// launch lasts as long as its longest segment (~70 steps).  Same roles as above on tiles of 4 segments whose rows step
+// through their OWN Euler steps (row r is at step s0[r] + j and rests once j reaches its length); the start encoder and the
+// jump that ends the segments stay with the glue warp (njode_seg.cuh code).
+// ================================================================================================
+#define NJN_SEG_R 4
+
+NJ_HD void nj_tpn_set(NjSegB& t, int off) { t.IN += off; t.A += off; t.G += off; t.GOUT += off; }
+
+// forward per-row scalars in the F slots of the region: step size by parity (the DT slot), prefetched time / step size (CA slot)
+#define NJN_SEG_DTV(f, par, r) (f).F[NJS_F_DT * 16 + (par) * 4 + (r)]
+#define NJN_SEG_TS(f, par, r) (f).F[NJS_F_CA * 16 + (par) * 4 + (r)]
+#define NJN_SEG_DS(f, par, r) (f).F[NJS_F_CA * 16 + 8 + (par) * 4 + (r)]
+
+template <class D>
+NJ_HD void nj_segtpn_fwd_build(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1>& f, int o, int j) {
+    constexpr int R = NJN_SEG_R, RS = 16;
+    const int inf4 = ((c.inf + 3) >> 2) << 2;
+    for (int c_ = o; c_ < inf4; c_ += NJN_F) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = f.I[NJS_I_PATH * RS + r], k = f.I[NJS_I_S0 * RS + r] + j;
+            const bool active = j < f.I[NJS_I_LEN * RS + r];
+            float v = 0.f;
+            if (c_ < c.d) v = f.TX[r * s.sD + c_];
+            else if (c_ < c.d + c.H) {
+                const float h = f.HS[r * s.sH + c_ - c.d];
+                if (active && a.h_hist) a.h_hist[((size_t)k * a.b.B + p) * c.H + c_ - c.d] = h;
+                v = nj_tanh(h);
+            } else if (c_ < c.inf) v = nj_tpn_time_col(c, c_, f.F[NJS_F_TAU * RS + r], active ? NJ_LDG(a.b.step_t + k) : 0.f);
+            f.w.IN[(size_t)r * s.sI + c_] = v;
+        }
+    }
+    if (o == NJN_F - 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = f.I[NJS_I_S0 * RS + r] + j;
+            f.w.RK[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(f.I[NJS_I_PATH * RS + r] + a.b.path_id_offset), (unsigned)k);
+            NJN_SEG_DTV(f, j & 1, r) = j < f.I[NJS_I_LEN * RS + r] ? NJ_LDG(a.b.step_dt + k) : 0.f;
+        }
+    }
+}
+template <class D>
+NJ_HD void nj_segtpn_fwd_p1(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1>& f, NjTpnF<D>& q, int o, int j, bool next) {
+    constexpr int R = NJN_SEG_R, RS = 16;
+    if (next && o == NJN_F - 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (j + 1 < f.I[NJS_I_LEN * RS + r]) {
+                const int k1 = f.I[NJS_I_S0 * RS + r] + j + 1;
+                nj_cp_async4(&NJN_SEG_TS(f, (j + 1) & 1, r), a.b.step_t + k1);
+                nj_cp_async4(&NJN_SEG_DS(f, (j + 1) & 1, r), a.b.step_dt + k1);
+            }
+        }
+    }
+    nj_tpn_hidden<D::KC0, R>(c, 0, q.w0, q.b0, o, f.w.IN, s.sI, f.w.A0, s.sA, f.w.RK);
+}
+template <class D>
+NJ_HD void nj_segtpn_fwd_p2(const NjCfg& c, const NjSeg& s, NjSegFwd<1>& f, NjTpnF<D>& q, int o) {
+    nj_tpn_hidden<D::KCH, NJN_SEG_R>(c, 1, q.w1, q.b1, o, f.w.A0, s.sA, f.w.A1, s.sA, f.w.RK);
+}
+template <class D>
+NJ_HD void nj_segtpn_fwd_p3(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1>& f, NjTpnF<D>& q, int o, int j, bool next) {
+    constexpr int R = NJN_SEG_R, RS = 16;
+    float acc[R];
+    nj_tpn_dot<D::KCH, R>(q.w2, f.w.A1, s.sA, acc);
+    if (o < c.H) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float h = fmaf(NJN_SEG_DTV(f, j & 1, r), acc[r] + q.b2, f.HS[r * s.sH + o]);
+            f.HS[r * s.sH + o] = h;
+            if (next) {
+                if (j + 1 < f.I[NJS_I_LEN * RS + r] && a.h_hist)
+                    a.h_hist[((size_t)(f.I[NJS_I_S0 * RS + r] + j + 1) * a.b.B + f.I[NJS_I_PATH * RS + r]) * c.H + o] = h;
+                f.w.IN[(size_t)r * s.sI + c.d + o] = nj_tanh(h);
+            }
+        }
+    }
+    if (next && o == NJN_F - 1) {
+        nj_cp_wait();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool an = j + 1 < f.I[NJS_I_LEN * RS + r];
+            const int k1 = f.I[NJS_I_S0 * RS + r] + j + 1;
+            const float tau = f.F[NJS_F_TAU * RS + r], tnext = an ? NJN_SEG_TS(f, (j + 1) & 1, r) : 0.f;
+            for (int c_ = c.d + c.H + 1; c_ < c.inf; ++c_) f.w.IN[(size_t)r * s.sI + c_] = nj_tpn_time_col(c, c_, tau, tnext);
+            f.w.RK[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(f.I[NJS_I_PATH * RS + r] + a.b.path_id_offset), (unsigned)k1);
+            NJN_SEG_DTV(f, (j + 1) & 1, r) = an ? NJN_SEG_DS(f, (j + 1) & 1, r) : 0.f;
+        }
+    }
+}
+
+template <class D, int ROLE>
+NJ_HD void nj_segtpn_fwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
+    constexpr int R = NJN_SEG_R, RS = 16;
+    float* simg = smem + s.f_img;
+    float* reg = smem + s.f_warp0;
+    NjSegFwd<1> f(c, s, a, reg, simg);
+    int* slot = f.I + NJS_I_COUNT * RS;
+    NJN_FREGS_DECL(D);
+    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_f_load<D>(c, simg, o, NJN_FREGS(o)); }
+    for (;;) {
+        NJ_THREADS(tid, NJN_NT_FWD) { if (tid == 0) *slot = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int wt = *slot;
+        NJ_SYNC();
+        if (wt >= s.n_tiles_f) break;
+        int ub, ue;
+        nj_seg_tile_lookup(s.f_ncls, s.f_t0, s.f_u0, s.f_u1, s.f_tr, 4, wt, ub, ue);
+        if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) { NJ_WARPS(wp, 1) { if (wp == 0) f.begin(ub, ue); } }
+        NJ_SYNC();
+        int maxlen = 0;
+        for (int r = 0; r < R; ++r) maxlen = f.I[NJS_I_LEN * RS + r] > maxlen ? f.I[NJS_I_LEN * RS + r] : maxlen;
+        if (maxlen > 0) {
+            NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_segtpn_fwd_build<D>(c, s, a, f, o, 0); }
+            NJN_SYNC_F();
+            for (int j = 0; j < maxlen; ++j) {
+                const bool next = j + 1 < maxlen;
+                NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_segtpn_fwd_p1<D>(c, s, a, f, NJN_FREGS(o), o, j, next); }
+                NJN_SYNC_F();
+                NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_segtpn_fwd_p2<D>(c, s, f, NJN_FREGS(o), o); }
+                NJN_SYNC_F();
+                NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_segtpn_fwd_p3<D>(c, s, a, f, NJN_FREGS(o), o, j, next); }
+                NJN_SYNC_F();
+            }
+        }
+        NJ_SYNC();
+        if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) { NJ_WARPS(wp, 1) { if (wp == 0) { f.maxlen = maxlen; f.finish(); } } }
+        NJ_SYNC();
+    }
+}
+
+template <class D>
+NJ_HD void nj_segtpn_cta_forward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem) {
+    nj_stage_image(smem + s.f_img, a.image, c.img_floats, NJN_NT_FWD);
+    nj_zero(smem + s.f_warp0, s.f_region, NJN_NT_FWD);
+    NJ_SYNC();
+#if defined(NJODE_HOST_SIM)
+    nj_segtpn_fwd_body<D, NJN_ALL>(c, s, a, smem);
+#else
+    if (threadIdx.x < NJN_F0) nj_segtpn_fwd_body<D, NJN_ROLE_G>(c, s, a, smem);
+    else nj_segtpn_fwd_body<D, NJN_ROLE_F>(c, s, a, smem);
+#endif
+}
+
+// ---- backward: the reversed Euler steps of a tile as the REV functor of nj_seg_bwd_tile ----
+// prefetch slots (s.b_PRE): time [2][4], step size [2][4], then h [2][P][sH]
+template <class D>
+NJ_HD void nj_segtpn_bwd_build(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, const NjSegB& t0, const NjSegB& te, int o,
+                               int e, bool have, bool pre, int cta) {
+    constexpr int R = NJN_SEG_R;
+    const int P = s.P_b, inf4 = ((c.inf + 3) >> 2) << 2;
+    float* pre_f = smem + s.b_PRE;
+    float* HP = pre_f + 16;
+    if (have) nj_cp_wait();
+    if (o == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int len = t0.I[NJS_I_LEN * P + r], k = t0.I[NJS_I_S0 * P + r] + e;
+            if (!have) pre_f[8 + (e & 1) * 4 + r] = e < len ? NJ_LDG(a.b.step_dt + k) : 0.f;
+            if (pre) {
+                if (e - 1 < len) {
+                    nj_cp_async4(pre_f + ((e - 1) & 1) * 4 + r, a.b.step_t + k - 1);
+                    nj_cp_async4(pre_f + 8 + ((e - 1) & 1) * 4 + r, a.b.step_dt + k - 1);
+                } else pre_f[8 + ((e - 1) & 1) * 4 + r] = 0.f;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int c_ = o + NJN_F * i;
+        if (c_ >= inf4) break;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = t0.I[NJS_I_PATH * P + r], len = t0.I[NJS_I_LEN * P + r], k = t0.I[NJS_I_S0 * P + r] + e;
+            const bool active = e < len;
+            float v = 0.f;
+            if (c_ < c.d) v = t0.TX[r * s.sD + c_];
+            else if (c_ < c.d + c.H) {
+                const int cc = c_ - c.d;
+                // h before step e: the history of the forward pass, or the recomputed chain of this CTA (recompute mode)
+                const float* hh = a.scratch ? a.scratch + ((size_t)cta * a.b.S * P + (size_t)e * P + r) * s.sH + cc
+                                            : a.h_hist + ((size_t)k * a.b.B + p) * c.H + cc;
+                float h = 0.f;
+                if (active) h = have ? HP[((e & 1) * P + r) * s.sH + cc] : NJ_LDG(hh);
+                if (pre && e - 1 < len)
+                    nj_cp_async4(HP + (((e - 1) & 1) * P + r) * s.sH + cc, a.scratch ? hh - (size_t)P * s.sH : hh - (size_t)a.b.B * c.H);
+                v = nj_tanh(h);
+            } else if (c_ < c.inf) {
+                const float tcur = active ? (have ? pre_f[(e & 1) * 4 + r] : NJ_LDG(a.b.step_t + k)) : 0.f;
+                v = nj_tpn_time_col(c, c_, t0.F[NJS_F_TAU * P + r], tcur);
+            }
+            te.IN[(size_t)r * s.sI + c_] = v;
+        }
+    }
+    if (o == NJN_F - 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            t0.I[NJS_I_RK * P + r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(t0.I[NJS_I_PATH * P + r] + a.b.path_id_offset),
+                                                     (unsigned)(t0.I[NJS_I_S0 * P + r] + e));
+    }
+}
+
+template <class D>
+NJ_HD void nj_segtpn_bwd_t3(const NjCfg& c, const NjSeg& s, const float* smem, const NjSegB& t0, const NjSegB* te, const NjSegB* tn, int eT, int eF,
+                            const NjTpnT<D>& q, int k) {
+    constexpr int R = NJN_SEG_R;
+    const int P = s.P_b;
+    float acc[R];
+    if (te) nj_tpn_dot<D::KCH, R>(q.c0, te->G, s.sA, acc);
+    const bool hcol = k >= c.d && k < c.d + c.H;
+    const int H4 = ((c.H + 3) >> 2) << 2;
+    const float* ds = smem + s.b_PRE + 8 + (eF & 1) * 4;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (te && hcol && eT < t0.I[NJS_I_LEN * P + r]) {
+            const float th = te->IN[(size_t)r * s.sI + k];
+            t0.GH[r * s.sH + k - c.d] += acc[r] * (1.f - th * th);
+        }
+        if (tn && hcol) tn->GOUT[(size_t)r * s.sO + k - c.d] = ds[r] * t0.GH[r * s.sH + k - c.d];      // (step size 0: the row rests)
+        else if (tn && k >= c.d + c.H && k < c.d + H4) tn->GOUT[(size_t)r * s.sO + k - c.d] = 0.f;
+    }
+}
+
+template <class D, int ROLE>
+struct NjSegTpnRev {
+    static constexpr bool stat = true;
+    static constexpr bool glue = (ROLE == NJN_ALL || ROLE == NJN_ROLE_G);
+    const NjCfg& c; const NjSeg& s; const NjArgs& a; float* smem; const NjSegB& t;
+    NjTpnF<D>* njn_f; NjTpnT<D>* njn_t; float* njn_d; int cta; float* gimg;
+
+    NJ_HD float* gpart(float*) const { return gimg; }
+
+    // steps n - 1 ... 0 of the tile, n + 2 pipeline iterations
+    NJ_HD void run(int n) const {
+        constexpr int R = NJN_SEG_R;
+        const int P = s.P_b;
+        for (int it = 0; it <= n + 1; ++it) {
+            const int eF = n - 1 - it, eT = eF + 1, eD = eF + 2;
+            const bool vF = it < n, vT = it >= 1 && it <= n, vD = it >= 2;
+            NjSegB tF = t, tT = t, tD = t;
+            nj_tpn_set(tF, ((eF + 3) % 3) * s.b_copy); nj_tpn_set(tT, ((eT + 3) % 3) * s.b_copy); nj_tpn_set(tD, ((eD + 3) % 3) * s.b_copy);
+            NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { if (vF) nj_segtpn_bwd_build<D>(c, s, a, smem, t, tF, o, eF, it > 0, it + 1 < n, cta); }
+            NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) { if (vT) nj_tpn_bwd_t1<D>(c, s, tT, NJN_TREGS(x), x); }
+            NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { if (vD) nj_tpn_dw<R>(c, s, smem, tD.IN, NJN_DACC_OF(x), x); }
+            NJN_SYNC_FT();
+            NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) {
+                if (vF) nj_tpn_hidden<D::KC0, R>(c, 0, NJN_FREGS(o).w0, NJN_FREGS(o).b0, o, tF.IN, s.sI, tF.A, s.sA, t.I + NJS_I_RK * P);
+            }
+            NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) { if (vT) nj_tpn_bwd_t2<D>(c, s, tT, NJN_TREGS(x), x); }
+            NJN_SYNC_FT();
+            NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) {
+                if (vF) nj_tpn_hidden<D::KCH, R>(c, 1, NJN_FREGS(o).w1, NJN_FREGS(o).b1, o, tF.A, s.sA, tF.A + P * s.sA, s.sA, t.I + NJS_I_RK * P);
+                if (o == 0) nj_cp_wait();
+            }
+            NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) {
+                if (vT || vF) nj_segtpn_bwd_t3<D>(c, s, smem, t, vT ? &tT : nullptr, vF ? &tF : nullptr, eT, eF, NJN_TREGS(x), x);
+            }
+            NJ_SYNC();
+        }
+    }
+};
+
+template <class D, int ROLE>
+NJ_HD void nj_segtpn_bwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
+    const int nt = NJN_NT_BWD;
+    const int ode_floats = c.net[NJODE_NET_ENC].w_img[0];
+    float* gout = a.partials + (size_t)cta * c.img_floats;
+    NjSegB t;
+    nj_segb_bind(t, s, smem);
+    NJN_FREGS_DECL(D);
+    NJN_TREGS_DECL(D);
+    NJN_DACC_DECL();
+    float* simg = smem + s.b_img;
+    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_f_load<D>(c, simg, o, NJN_FREGS(o)); }
+    NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, k) { nj_tpn_t_load<D>(c, simg, k, NJN_TREGS(k)); }
+    NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { nj_tpn_dw_table(c, s, smem, x); }
+    const NjSegTpnRev<D, ROLE> rev{c, s, a, smem, t, njn_f, njn_t, njn_d, cta, smem + s.b_GIMG - ode_floats};
+    int* ctl = t.I + NJS_I_COUNT * s.P_b;
+    for (;;) {
+        NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
+        NJ_SYNC();
+        const int tile = ctl[0];
+        NJ_SYNC();
+        if (tile >= s.n_tiles_b) break;
+        int ub, ue;
+        nj_seg_tile_lookup(s.b_ncls, s.b_t0, s.b_u0, s.b_u1, s.b_tr, 4 * s.nw_b, tile, ub, ue);
+        nj_seg_bwd_tile<1, NjSegTpnRev<D, ROLE>>(c, s, a, smem, t, nullptr, cta, ub, ue, rev);
+    }
+    NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { nj_tpn_dw_flush(c, s, NJN_DACC_OF(x), gout, x); }
+    const float* gimg = smem + s.b_GIMG - ode_floats;
+    NJ_THREADS(tid, nt) { for (int i = ode_floats + tid; i < c.img_floats; i += nt) gout[i] = gimg[i]; }
+}
+
+template <class D>
+NJ_HD void nj_segtpn_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
+    const int nt = NJN_NT_BWD;
+    nj_stage_image(smem + s.b_img, a.image, c.img_floats, nt);
+    nj_zero(smem + s.b_IN, s.b_smem_floats - s.b_IN, nt);
+    nj_zero(a.partials + (size_t)cta * c.img_floats, c.net[NJODE_NET_ENC].w_img[0], nt);
+    NJ_SYNC();
+#if defined(NJODE_HOST_SIM)
+    nj_segtpn_bwd_body<D, NJN_ALL>(c, s, a, smem, cta);
+#else
+    if (threadIdx.x < NJN_F0) nj_segtpn_bwd_body<D, NJN_ROLE_G>(c, s, a, smem, cta);
+    else if (threadIdx.x < NJN_T0) nj_segtpn_bwd_body<D, NJN_ROLE_F>(c, s, a, smem, cta);
+    else if (threadIdx.x < NJN_D0) nj_segtpn_bwd_body<D, NJN_ROLE_T>(c, s, a, smem, cta);
+    else nj_segtpn_bwd_body<D, NJN_ROLE_D>(c, s, a, smem, cta);
 #endif
 }

@@ -26,7 +26,7 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
     if (!nj_plan_all(*m, *b, kSimSMs, kSimSmem, fp ? atoi(fp) : 0, out, err)) { g_err = err; return -3; }
     if (getenv("NJODE_DEBUG_PLAN"))
         fprintf(stderr, "[plan] units %d kind %d E %d -> seg %d (stat %d) path %d stat %d tpn %d nw_s %d pipe %d (fwd rg %d tr %d nw %d | bwd rg %d tr %d nw %d nt %d P %d slots %d tiles %d)\n",
-                b->n_units, b->unit_kind, b->E, out.seg.ok, out.seg.stat, out.path.ok, out.path.stat, out.path.tpn, out.path.nw_s, out.path.pipe, out.path.rg_f, out.path.tr_f, out.path.nw_f, out.path.rg_b,
+                b->n_units, b->unit_kind, b->E, out.seg.ok, out.seg.tpn, out.path.ok, out.path.stat, out.path.tpn, out.path.nw_s, out.path.pipe, out.path.rg_f, out.path.tr_f, out.path.nw_f, out.path.rg_b,
                 out.path.tr_b, out.path.nw_b, out.path.nt_b, out.path.P_b, out.path.nt_slots, out.path.tiles_total);
     const size_t cap = (size_t)kSimSMs * 2;
     out.grid_bwd = (int)std::min<size_t>(out.grid_bwd, cap);
@@ -47,7 +47,7 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
 extern "C" int njode_hostsim_plan_kind(const njode_model_t* model, const njode_batch_t* bs) {
     NjPlanOut o;
     if (int rc = plan_for(model, bs, o)) return rc;
-    return (o.seg.ok ? 1 : 0) | (o.seg.ok && o.seg.stat ? 2 : 0) | (o.path.ok ? 4 : 0) | (o.path.ok && o.path.stat ? 8 : 0) |
+    return (o.seg.ok ? 1 : 0) | (o.seg.ok && o.seg.tpn ? 2 : 0) | (o.path.ok ? 4 : 0) | (o.path.ok && o.path.stat ? 8 : 0) |
            (o.path.ok && o.path.pipe ? 16 : 0) | (o.path.ok && o.path.tpn ? 32 : 0);
 }
 
@@ -105,10 +105,9 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
         for (int cta = 0; cta < pl.seg_grid_f; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
             if (cta == 0) *a.counter = 0;
-            if (pl.seg.stat) {
-                if (pl.seg.f_tr[0] == 2) nj_segstat_cta_forward<2>(pl.fwd, pl.seg, a, smem.data());
-                else nj_segstat_cta_forward<1>(pl.fwd, pl.seg, a, smem.data());
-            } else nj_seg_cta_forward(pl.fwd, pl.seg, a, smem.data());
+            if (pl.seg.tpn == 1) nj_segtpn_cta_forward<NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 4>>(pl.fwd, pl.seg, a, smem.data());
+            else if (pl.seg.tpn == 2) nj_segtpn_cta_forward<NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 4>>(pl.fwd, pl.seg, a, smem.data());
+            else nj_seg_cta_forward(pl.fwd, pl.seg, a, smem.data());
         }
     } else if (pl.path.ok) {
         std::vector<float> smem(pl.path.f_smem_floats);
@@ -167,10 +166,9 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         for (int cta = 0; cta < pl.seg_grid_b; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
             if (cta == 0) *a.counter = 0;
-            if (pl.seg.stat) {
-                if (pl.seg.b_tr[0] == 2) nj_segstat_cta_backward<2>(pl.bwd, pl.seg, a, smem.data(), cta);
-                else nj_segstat_cta_backward<1>(pl.bwd, pl.seg, a, smem.data(), cta);
-            } else nj_seg_cta_backward<false>(pl.bwd, pl.seg, a, smem.data(), cta);
+            if (pl.seg.tpn == 1) nj_segtpn_cta_backward<NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 4>>(pl.bwd, pl.seg, a, smem.data(), cta);
+            else if (pl.seg.tpn == 2) nj_segtpn_cta_backward<NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 4>>(pl.bwd, pl.seg, a, smem.data(), cta);
+            else nj_seg_cta_backward<false>(pl.bwd, pl.seg, a, smem.data(), cta);
         }
         nparts = pl.seg_grid_b;
     } else if (pl.path.ok) {

@@ -23,7 +23,7 @@ def no_test_runner():
     hostsim_util.uninstall()
     yield
     os.environ.pop("NJODE_FORCE_TILE", None)
-    os.environ.pop("NJODE_SEG_STAT", None)
+    os.environ.pop("NJODE_SEG_TPN", None)
     os.environ.pop("NJODE_FORCE_TR", None)
     os.environ.pop("NJODE_NO_TPN", None)
     os.environ.pop("NJODE_NO_STAT", None)
@@ -50,6 +50,14 @@ def test_tile_size_invariance(name, tile):
     os.environ["NJODE_FORCE_TILE"] = str(tile)
     parity_util.check_training_call(name, DEV, with_hT_grad=True)
     parity_util.check_path_call(name, DEV)
+
+
+def _last_kernels():
+    import ctypes as C
+    from njode_b200 import _ext
+    dll = _ext.cuda_lib().dll
+    dll.njode_last_kernel.argtypes, dll.njode_last_kernel.restype = [C.c_int], C.c_char_p
+    return dll.njode_last_kernel(0).decode(), dll.njode_last_kernel(1).decode()
 
 
 def _oracle_vs_cuda(cfg, batch, dt, T, seed, train=False, rtol=1e-4):
@@ -237,53 +245,42 @@ def test_recompute_mode_allocates_no_history(recompute_on):
     assert peaks["on"] < 2 * 1024 * 1024, peaks           # hT + scalars only
 
 
-# ---- small segment batches: the planner gives them to the weight-stationary kernels (nj_segstat_*); the 12-warp tile
-# kernels of big batches are kept covered on the same small cases (NJODE_SEG_STAT=0) ----
+# ---- small segment batches: the planner gives them to the thread-per-neuron kernels (nj_segtpn_*); the 12-warp tile
+# kernels of big batches are kept covered on the same small cases (NJODE_SEG_TPN=0) ----
 SEG_NAMES = [n for n in NAMES if "masked" not in n and "gru" not in n]
 
 
-@pytest.mark.parametrize("stat", ["0", "1"])
+@pytest.mark.parametrize("tpn", ["0", "1"])
 @pytest.mark.parametrize("name", SEG_NAMES)
-def test_segment_units_both_kernel_families(name, stat):
-    os.environ["NJODE_SEG_STAT"] = stat
+def test_segment_units_both_kernel_families(name, tpn):
+    os.environ["NJODE_SEG_TPN"] = tpn
     parity_util.check_training_call(name, DEV, with_hT_grad=True)
     parity_util.check_training_call(name, DEV)
 
 
-@pytest.mark.parametrize("tr", ["1", "2"])
 @pytest.mark.parametrize("B", [40, 200, 1500])
-def test_segment_stationary_kernels_train_mode(B, tr):
-    """the reference's batch of 200 (and a smaller / larger one) in train mode, both tile heights, with and without a
-    gradient into hT; 3-Linear ODE network at B = 40"""
-    os.environ["NJODE_SEG_STAT"] = "1"
-    os.environ["NJODE_FORCE_TR"] = tr
-    cfg = cases.demo_cfg(dropout_rate=0.1, ode_nn=[[50, "tanh"]] * (1 if B == 40 else 2))
+def test_segment_thread_per_neuron_kernels_train_mode(B):
+    """the reference's batch of 200 (and a smaller / larger one) in train mode, with and without a gradient into hT"""
+    os.environ["NJODE_SEG_TPN"] = "1"
+    cfg = cases.demo_cfg(dropout_rate=0.1)
     batch = cases.grid_batch(B, 1, 100, 0.1, seed=27)
     parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=8, device=DEV, train=True, grad_hT=True)
     parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=8, device=DEV, train=True)
-    import ctypes as C
-    from njode_b200 import _ext
-    dll = _ext.cuda_lib().dll
-    dll.njode_last_kernel.argtypes, dll.njode_last_kernel.restype = [C.c_int], C.c_char_p
-    assert b"segstat" in dll.njode_last_kernel(0) and b"segstat" in dll.njode_last_kernel(1)
+    kf, kb = _last_kernels()
+    assert "segtpn" in kf and "segtpn" in kb, (kf, kb)
 
 
-def test_segment_stationary_kernels_recompute(recompute_on):
-    os.environ["NJODE_SEG_STAT"] = "1"
+def test_segment_thread_per_neuron_kernels_class_b_and_recompute(recompute_on):
+    os.environ["NJODE_SEG_TPN"] = "1"
+    cfg = cases.demo_cfg(dropout_rate=0.1, input_size=20, output_size=20, hidden_size=40)
+    batch = cases.grid_batch(64, 20, 40, 0.2, seed=28)
+    parity_util.check_against_oracle(cfg, batch, 0.025, 1.0, seed=9, device=DEV, train=True, grad_hT=True)
     cfg = cases.demo_cfg(dropout_rate=0.1)
     batch = cases.grid_batch(300, 1, 100, 0.1, seed=28)
     parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=9, device=DEV, train=True, grad_hT=True)
 
 
 # ---- small whole-path batches: thread-per-neuron kernels (njode_tpn.cuh), next to the kernels they replace ----
-def _last_kernels():
-    import ctypes as C
-    from njode_b200 import _ext
-    dll = _ext.cuda_lib().dll
-    dll.njode_last_kernel.argtypes, dll.njode_last_kernel.restype = [C.c_int], C.c_char_p
-    return dll.njode_last_kernel(0).decode(), dll.njode_last_kernel(1).decode()
-
-
 @pytest.mark.parametrize("family", ["tpn", "stat", "warp"])
 @pytest.mark.parametrize("B", [50, 300])
 def test_small_physionet_batches_every_kernel_family(B, family):

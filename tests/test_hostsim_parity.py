@@ -19,11 +19,11 @@ NAMES = cases.golden_names()
 @pytest.fixture(autouse=True)
 def sim_runner():
     hostsim_util.install()
-    # the golden cases are tiny: left alone the planner would give every segment batch to the weight-stationary kernels
-    # of small batches; the tests below choose (NJODE_SEG_STAT = 1 / unset) where those are the subject
-    os.environ["NJODE_SEG_STAT"] = "0"
+    # the golden cases are tiny: left alone the planner would give every segment batch to the thread-per-neuron kernels
+    # of small batches; the tests below choose (NJODE_SEG_TPN = 1 / unset) where those are the subject
+    os.environ["NJODE_SEG_TPN"] = "0"
     yield
-    os.environ.pop("NJODE_SEG_STAT", None)
+    os.environ.pop("NJODE_SEG_TPN", None)
     hostsim_util.uninstall()
     os.environ.pop("NJODE_FORCE_TILE", None)
     os.environ.pop("NJODE_FORCE_TR", None)
@@ -379,40 +379,51 @@ def test_recompute_mode_saves_nothing(recompute_on):
     assert loss.grad_fn is not None and loss.grad_fn.saved == ()
 
 
-# ---- segment units of small batches on the weight-stationary Euler steps (njode_path.cuh, nj_segstat_*) ----
-@pytest.mark.parametrize("tr", [1, 2])
+# ---- segment units of small batches on the thread-per-neuron kernels (njode_tpn.cuh, nj_segtpn_*) ----
+SEG_TPN_NAMES = ["bs_ckpt1", "heston_ckpt2", "ou_ckpt3", "irregular_demo", "res_case2", "easy_w07_nores"]
+
+
 @pytest.mark.parametrize("name", SEG_NAMES)
-def test_segment_stationary_kernels(name, tr):
-    os.environ["NJODE_SEG_STAT"] = "1"
-    os.environ["NJODE_FORCE_TR"] = str(tr)
+def test_segment_thread_per_neuron_kernels(name):
+    """every non-masked golden case whose ODE network fits a dimension class (the others keep the warp kernels)"""
+    os.environ["NJODE_SEG_TPN"] = "1"
     parity_util.check_training_call(name, "cpu", with_hT_grad=True)
     parity_util.check_training_call(name, "cpu")
 
 
-@pytest.mark.parametrize("tr", [1, 2])
-@pytest.mark.parametrize("layers", [1, 2])
-def test_segment_stationary_kernels_train_mode_dropout(tr, layers):
-    """2- and 3-Linear ODE networks (the register tiles hold up to three layers), several CTAs, dropout masks replayed"""
-    os.environ["NJODE_SEG_STAT"] = "1"
-    os.environ["NJODE_FORCE_TR"] = str(tr)
-    cfg = cases.demo_cfg(dropout_rate=0.2, input_size=2, output_size=2, ode_nn=[[50, "tanh"]] * layers)
-    batch = cases.grid_batch(40, 2, 25, 0.2, seed=16)
+@pytest.mark.parametrize("d", [1, 2])
+def test_segment_thread_per_neuron_kernels_train_mode_dropout(d):
+    """the demo networks (class A), several CTAs, dropout masks replayed; with and without a gradient into hT"""
+    os.environ["NJODE_SEG_TPN"] = "1"
+    cfg = cases.demo_cfg(dropout_rate=0.2, input_size=d, output_size=d)
+    batch = cases.grid_batch(40, d, 25, 0.2, seed=16)
+    m = models.NJODE(**cfg)
+    pb = m.prepare_batch(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 0.04, 1.0, batch["start_X"], batch["n_obs_ot"])
+    assert "segstat" in hostsim_util.plan_kind(m, pb, "fwd") and "segstat" in hostsim_util.plan_kind(m, pb, "bwd_loss")
     parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
     parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=False)
 
 
-def test_segment_stationary_kernels_recompute(recompute_on):
-    os.environ["NJODE_SEG_STAT"] = "1"
+def test_segment_thread_per_neuron_kernels_class_b():
+    """d = 20, H = 40 non-masked: the wider dimension class (84 / 52 / 44)"""
+    os.environ["NJODE_SEG_TPN"] = "1"
+    cfg = cases.demo_cfg(dropout_rate=0.1, input_size=20, output_size=20, hidden_size=40)
+    batch = cases.grid_batch(30, 20, 12, 0.3, seed=19)
+    parity_util.check_against_oracle(cfg, batch, 1.0 / 12, 1.0, seed=13, device="cpu", train=True, grad_hT=True)
+
+
+def test_segment_thread_per_neuron_kernels_recompute(recompute_on):
+    os.environ["NJODE_SEG_TPN"] = "1"
     cfg = cases.demo_cfg(dropout_rate=0.15)
     batch = cases.grid_batch(60, 1, 30, 0.2, seed=12)
     parity_util.check_against_oracle(cfg, batch, 1.0 / 30, 1.0, seed=6, device="cpu", train=True, grad_hT=True)
 
 
-def test_planner_gives_the_reference_batch_to_the_stationary_kernels():
+def test_planner_gives_the_reference_batch_to_the_thread_per_neuron_kernels():
     """B200 launch plan (148 SMs): the reference's own batch of 200 paths x 100 steps (~2 200 segments) takes the
-    weight-stationary kernels, a batch of 20 000 paths the 12-warp tile kernels; ODE networks wider than the register
-    tiles (2 x 100) never do"""
-    os.environ.pop("NJODE_SEG_STAT", None)
+    thread-per-neuron kernels, a batch of 20 000 paths the 12-warp tile kernels; ODE networks outside the dimension
+    classes (2 x 100) never do"""
+    os.environ.pop("NJODE_SEG_TPN", None)
     os.environ["NJODE_SIM_SMS"] = "148"
     for B, layers, want in ((200, [[50, "tanh"]] * 2, True), (20000, [[50, "tanh"]] * 2, False), (200, [[100, "tanh"]] * 2, False)):
         cfg = cases.demo_cfg(ode_nn=layers)
