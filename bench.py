@@ -412,6 +412,9 @@ class Ctx:
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # (the driver reads ONE JSON line from stdout: keep NCCL's own version banner out of it)
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"
             dist.init_process_group("nccl", device_id=self.dev)
         lib = self.lib = _ext.cuda_lib().dll
         lib.njode_launch_count.restype = C.c_longlong

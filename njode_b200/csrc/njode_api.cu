@@ -53,6 +53,12 @@ __global__ void __launch_bounds__(384) nj_seg_bwd_kernel(const __grid_constant__
     nj_seg_cta_backward<false>(cfg, seg, args, nj_smem, blockIdx.x);
 }
 
+// ... and for launches whose dW tiles all fit the register slots (no out-of-line overflow code: see nj_seg_dw)
+__global__ void __launch_bounds__(384) nj_seg_bwd_kernel_r(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
+                                                           const __grid_constant__ NjArgs args) {
+    nj_seg_cta_backward<false, false>(cfg, seg, args, nj_smem, blockIdx.x);
+}
+
 // the same kernel for launches with dW helper warps (seg.nt_b > 32 * seg.nw_b), see nj_seg_cta_backward
 __global__ void __launch_bounds__(384) nj_seg_bwd_kernel_h(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
                                                            const __grid_constant__ NjArgs args) {
@@ -387,12 +393,14 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.seg_grid_b;
+        const bool seg_in_regs = pl.seg.tiles_total <= pl.seg.nt_slots * pl.seg.nt_b;
         auto kern = pl.seg.tpn ? (pl.seg.tpn == 1 ? nj_segtpn_bwd_kernel<NjTpnA4> : nj_segtpn_bwd_kernel<NjTpnB4>)
-                               : (pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h : nj_seg_bwd_kernel);
+                               : (pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h
+                                  : (seg_in_regs ? nj_seg_bwd_kernel_r : nj_seg_bwd_kernel));
         NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
         kern<<<pl.seg_grid_b, pl.seg.nt_b, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
         nj_set_last_kernel(1, pl.seg.tpn ? (pl.seg.tpn == 1 ? "nj_segtpn_bwd_kernel<A>" : "nj_segtpn_bwd_kernel<B>")
-                                         : (pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : "nj_seg_bwd_kernel"));
+                                         : (pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : (seg_in_regs ? "nj_seg_bwd_kernel_r" : "nj_seg_bwd_kernel")));
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";

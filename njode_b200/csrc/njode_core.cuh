@@ -24,6 +24,7 @@
 #if defined(NJODE_HOST_SIM)
 #define NJ_HD inline
 #define NJ_HDN inline
+#define NJ_UNROLL4
 #define NJ_THREADS(tid, nt) for (int tid = 0; tid < (nt); ++tid)
 #define NJ_SYNC() ((void)0)
 #define NJ_LDG(p) (*(p))
@@ -33,6 +34,7 @@ static inline void nj_st4(float* p, const nj_f4& v) { memcpy(p, &v, 16); }
 #else
 #define NJ_HD __device__ __forceinline__
 #define NJ_HDN __device__ __noinline__
+#define NJ_UNROLL4 _Pragma("unroll 4")
 #define NJ_THREADS(tid, nt) for (int tid = threadIdx.x, _nj_e = threadIdx.x + 1; tid < _nj_e; ++tid)
 #define NJ_SYNC() __syncthreads()
 #define NJ_LDG(p) __ldg(p)

@@ -302,10 +302,6 @@ struct NjPW {
     void* coop;                     // mailbox of the cooperative layer service (njode_tpn.cuh) or null: the warp's own GEMM
 };
 
-// cooperative evaluation of one layer by the F threads of a thread-per-neuron CTA, posted by the glue warp (njode_tpn.cuh)
-NJ_HD void nj_coop_post_fwd(void* mailbox, const NjWL& L, int o_store);
-NJ_HD void nj_coop_post_dx(void* mailbox, const NjWD& D);
-
 template <int RG, int TR, bool COOP = false>
 NJ_HD void nj_path_mlp_fwd(const NjPW& w, int netid, bool keep_all, bool skip_last) {
     const NjCfg& c = *w.c;
@@ -598,7 +594,8 @@ struct NjPathFwd {
                 const int r = lane, row = I[NJP_I_ROW * RS + r];
                 if (a.get_loss) {
                     float sa = 0.f, sb = 0.f;
-                    for (int c_ = 0; c_ < c.dout; ++c_) {
+                    NJ_UNROLL4
+                    for (int c_ = 0; c_ < c.dout; ++c_) {      // (unrolled: the independent loads of four features go out together)
                         const float x = NJ_LDG(a.b.X + (size_t)row * c.d + c_);
                         const float m = c.masked ? NJ_LDG(a.b.M + (size_t)row * c.d + c_) : 1.f;
                         const float y = YY[r * sD + c_], yb = YBJ[r * sD + c_];
@@ -1084,7 +1081,8 @@ struct NjPathBwd {
                 float ca = 0.f, cb = 0.f;
                 if ((msk >> lane) & 1) {
                     float sa = 0.f, sb = 0.f;
-                    for (int c_ = 0; c_ < c.dout; ++c_) {
+                    NJ_UNROLL4
+                    for (int c_ = 0; c_ < c.dout; ++c_) {      // (unrolled: the independent loads of four features go out together)
                         float y = t.OUT[r * sO + c_];
                         if (c.residual) y += nj_resid(t.EE + r * sH, H, c.dout, c_);
                         t.YY[r * sD + c_] = y;

@@ -386,6 +386,7 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
             const int z1[2] = {0, 0}, z2[2] = {0, 0};
             const int one[1] = {1};
             s.f_region = nj_seg_fwd_region(c, s, NJN_SEG_R);
+            s.f_MB = s.f_region; s.f_region += (int)((sizeof(NjCoopMB) + 15) / 16) * 4;       // mailbox of the cooperative layers
             s.f_img = 0; s.f_warp0 = c.img_floats;
             s.f_ncls = nj_seg_classes(rb, re, z1, z2, one, 1, 4, s.f_t0, s.f_u0, s.f_u1, s.f_tr);
             s.n_tiles_f = s.f_t0[s.f_ncls];
@@ -396,6 +397,8 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
             s.b_PRE = fl; fl += 16 + 2 * NJN_SEG_R * s.sH;
             fl = (fl + 3) & ~3;
             s.b_GIMG = fl; fl += c.img_floats - c.net[NJODE_NET_ENC].w_img[0];
+            fl = (fl + 3) & ~3;
+            s.b_MB = fl; fl += (int)((sizeof(NjCoopMB) + 15) / 16) * 4;
             s.b_smem_floats = (fl + 3) & ~3; s.P_b = NJN_SEG_R; s.nw_b = 1; s.nt_b = NJN_NT_BWD; s.nt_slots = 0;
             s.b_ncls = nj_seg_classes(rb, re, z1, z2, one, 1, 4, s.b_t0, s.b_u0, s.b_u1, s.b_tr);
             s.n_tiles_b = s.b_t0[s.b_ncls];

@@ -100,7 +100,7 @@ struct NjSeg {
     int b_ncls, b_t0[7], b_u0[6], b_u1[6], b_tr[6];
     // thread-per-neuron kernels of small batches (njode_tpn.cuh): dimension class, operand buffers three times (b_copy apart),
     // dW tile table, prefetch slots, gradient image of the jump networks in shared memory
-    int tpn, b_copy, b_TD, b_PRE, b_GIMG;
+    int tpn, b_copy, b_TD, b_PRE, b_GIMG, f_MB, b_MB;
 };
 
 // tile id -> (class, first unit, one-past-last unit)
@@ -320,11 +320,16 @@ struct NjSegW {
     float *G0, *GOUT, *GZ;              // backward only
     int a_buf_stride, g_buf_stride;     // distance (floats) between consecutive hidden buffers
     int* RK;                            // dropout row keys of this warp's rows
+    void* coop;                         // mailbox of the cooperative layer service (njode_tpn.cuh) or null
 };
+
+// cooperative evaluation of one layer by the F threads of a thread-per-neuron CTA, posted by the glue warp (njode_tpn.cuh)
+NJ_HD void nj_coop_post_fwd(void* mailbox, const NjWL& L, int o_store);
+NJ_HD void nj_coop_post_dx(void* mailbox, const NjWD& D);
 
 // MLP forward over the warp's rows.  keep_all: hidden activations of layer l go to A0 + l*a_buf_stride
 // (backward); otherwise they ping-pong between A0 and A1.  skip_last: stop after the hidden layers.
-template <int TR>
+template <int TR, bool COOP = false>
 NJ_HD void nj_seg_mlp_fwd(const NjSegW& w, int netid, bool keep_all, bool skip_last) {
     const NjCfg& c = *w.c;
     const NjNet& N = c.net[netid];
@@ -342,7 +347,8 @@ NJ_HD void nj_seg_mlp_fwd(const NjSegW& w, int netid, bool keep_all, bool skip_l
         L.drop = (!last) && c.has_drop; L.thr = c.thr; L.keep_scale = c.keep_scale;
         L.rk = w.RK; L.tag = (unsigned)(netid * 16 + l + 1);
         L.o_base = 0;
-        nj_seg_layer_fwd<TR>(L, N.to[l], N.tol[l], N.nch[l]);
+        if (COOP) nj_coop_post_fwd(w.coop, L, 8 * (N.to[l] * (N.nch[l] - 1) + N.tol[l]));
+        else nj_seg_layer_fwd<TR>(L, N.to[l], N.tol[l], N.nch[l]);
         NJ_SYNCWARP();
         in = L.out; in_s = L.out_s;
     }
@@ -351,7 +357,7 @@ NJ_HD void nj_seg_mlp_fwd(const NjSegW& w, int netid, bool keep_all, bool skip_l
 // MLP backward (input gradients only; dW is phase B).  g wrt the raw output is in GOUT; hidden
 // activations in A0 + l*a_buf_stride; g wrt hidden pre-activation l goes to G0 + l*g_buf_stride;
 // the gradient wrt the network input goes to GZ when need_in_grad.
-template <int TR>
+template <int TR, bool COOP = false>
 NJ_HD void nj_seg_mlp_dx(const NjSegW& w, int netid, bool need_in_grad) {
     const NjCfg& c = *w.c;
     const NjNet& N = c.net[netid];
@@ -370,7 +376,8 @@ NJ_HD void nj_seg_mlp_dx(const NjSegW& w, int netid, bool need_in_grad) {
         }
         D.drop = c.has_drop; D.keep_scale = c.keep_scale; D.one_minus_p = c.one_minus_p;
         D.kg_base = 0;
-        nj_seg_layer_dx<TR>(D);
+        if (COOP) nj_coop_post_dx(w.coop, D);
+        else nj_seg_layer_dx<TR>(D);
         NJ_SYNCWARP();
     }
 }
@@ -393,7 +400,7 @@ NJ_HD unsigned nj_seg_event_of_jump(const NjArgs& a, int row, unsigned which) {
 // ------------------------------------------------------------------------------------------------
 // forward of one tile of R = 4*TR segment units by one warp, in three parts (the weight-stationary kernels of small
 // batches run begin / finish on warp 0 and replace the Euler steps by CTA-cooperative ones)
-template <int TR>
+template <int TR, bool COOP = false>
 struct NjSegFwd {
     static constexpr int R = 4 * TR;
     static constexpr int RS = 16;             // row-slot stride of the per-warp scalar arrays (tallest tile)
@@ -407,7 +414,7 @@ struct NjSegFwd {
     NJ_HD NjSegFwd(const NjCfg& c_, const NjSeg& s_, const NjArgs& a_, float* reg, const float* wimg) : c(c_), s(s_), a(a_) {
         w.c = &c; w.s = &s; w.wimg = wimg;
         w.IN = reg + s.f_IN; w.A0 = reg + s.f_A0; w.A1 = reg + s.f_A1; w.OUT = reg + s.f_OUT;
-        w.G0 = w.GOUT = w.GZ = nullptr; w.a_buf_stride = 0; w.g_buf_stride = 0;
+        w.G0 = w.GOUT = w.GZ = nullptr; w.a_buf_stride = 0; w.g_buf_stride = 0; w.coop = nullptr;
         HS = reg + s.f_HS; LX = reg + s.f_LX; TX = reg + s.f_TX; XI = reg + s.f_XI;
         YBJ = reg + s.f_YBJ; F = reg + s.f_F;
         I = reinterpret_cast<int*>(reg + s.f_I);
@@ -459,7 +466,7 @@ struct NjSegFwd {
         }
     }
     NJ_SYNCWARP();
-    nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, false, false);
+    nj_seg_mlp_fwd<TR, COOP>(w, NJODE_NET_ENC, false, false);
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
         for (int c_ = ec0; c_ < c.H; c_ += LPR) {
@@ -502,7 +509,7 @@ struct NjSegFwd {
             }
         }
         NJ_SYNCWARP();
-        nj_seg_mlp_fwd<TR>(w, NJODE_NET_ODE, false, false);
+        nj_seg_mlp_fwd<TR, COOP>(w, NJODE_NET_ODE, false, false);
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             if (j < I[NJS_I_LEN * RS + er]) {
@@ -541,7 +548,7 @@ struct NjSegFwd {
             w.RK[er] = row >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), nj_seg_event_of_jump(a, row, 0u)) : 0;
     }
     NJ_SYNCWARP();
-    nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, false, false);
+    nj_seg_mlp_fwd<TR, COOP>(w, NJODE_NET_RO, false, false);
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
         const int row = I[NJS_I_ROW * RS + er], p = I[NJS_I_PATH * RS + er];
@@ -560,7 +567,7 @@ struct NjSegFwd {
             w.RK[er] = row >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), nj_seg_event_of_jump(a, row, 1u)) : 0;
     }
     NJ_SYNCWARP();
-    nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, false, false);
+    nj_seg_mlp_fwd<TR, COOP>(w, NJODE_NET_ENC, false, false);
     NJ_LANES(lane) {
         NJ_ROWMAP(R);
         const int row = I[NJS_I_ROW * RS + er], p = I[NJS_I_PATH * RS + er];
@@ -577,13 +584,14 @@ struct NjSegFwd {
             w.RK[er] = row >= 0 ? (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(p + a.b.path_id_offset), nj_seg_event_of_jump(a, row, 2u)) : 0;
     }
     NJ_SYNCWARP();
-    nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, false, false);
+    nj_seg_mlp_fwd<TR, COOP>(w, NJODE_NET_RO, false, false);
     NJ_LANES(lane) {
         if (lane < R) {
             const int r = lane, row = I[NJS_I_ROW * RS + r];
             if (row >= 0) {
                 float sa = 0.f, sb = 0.f;
-                for (int c_ = 0; c_ < c.dout; ++c_) {
+                NJ_UNROLL4
+                    for (int c_ = 0; c_ < c.dout; ++c_) {      // (unrolled: the independent loads of four features go out together)
                     float y = w.OUT[r * sO + c_];
                     if (c.residual) y += nj_resid(HS + r * sH, c.H, c.dout, c_);
                     if (a.y_after) a.y_after[(size_t)row * c.dout + c_] = y;
@@ -731,6 +739,7 @@ NJ_HDN void nj_seg_dw_overflow(const NjCfg* cp, const NjSeg* sp, const NjSegB* t
     }
 }
 
+template <bool OVF = true>
 NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid, float* acc, float* gpart,
                      int tid, int nt, int Pt) {
 #pragma unroll
@@ -740,7 +749,9 @@ NJ_HD void nj_seg_dw(const NjCfg& c, const NjSeg& s, const NjSegB& t, int netid,
         if (!nj_seg_tile_decode(c, s, netid, slot * nt + tid, l, og, kg)) continue;
         nj_seg_dw_rows(c, s, t, netid, l, og, kg, Pt, acc + slot * 20);
     }
-    if (s.tiles_total > s.nt_slots * nt) nj_seg_dw_overflow(&c, &s, &t, netid, gpart, tid, nt, Pt);
+    // OVF = false: an instantiation for launches whose tiles all fit the register slots -- the mere presence of the
+    // out-of-line call cost the backward of the 20 000-path demo batch 10 % (B200: 4.08 -> 4.55 ms)
+    if (OVF && s.tiles_total > s.nt_slots * nt) nj_seg_dw_overflow(&c, &s, &t, netid, gpart, tid, nt, Pt);
 }
 
 // writes the register tiles into this CTA's partial gradient image (pre-zeroed by the caller)
@@ -773,7 +784,7 @@ NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, flo
     w.c = &c; w.s = &s; w.wimg = simg;                                                                             \
     w.IN = t.IN + (size_t)r0 * sI; w.A0 = t.A + (size_t)r0 * s.sA; w.A1 = nullptr; w.OUT = t.OUT + (size_t)r0 * sO; \
     w.G0 = t.G + (size_t)r0 * s.sA; w.GOUT = t.GOUT + (size_t)r0 * sO; w.GZ = t.GZ + (size_t)r0 * sI;             \
-    w.a_buf_stride = wa; w.g_buf_stride = wa; w.RK = t.I + NJS_I_RK * P + r0
+    w.a_buf_stride = wa; w.g_buf_stride = wa; w.RK = t.I + NJS_I_RK * P + r0; w.coop = rev.mailbox()
 
 #define NJ_SEGB_KEY(r, valid, ev)                                                                                  \
     t.I[NJS_I_RK * P + (r)] = (valid) ? (int)nj_row_key(c.seed_lo, c.seed_hi,                                      \
@@ -782,12 +793,20 @@ NJ_HD void nj_seg_dw_flush(const NjCfg& c, const NjSeg& s, const float* acc, flo
 // REV: how the Euler steps are reversed.  The default (NjSegWarpRev) is the warp-local recompute + dx below followed by the
 // CTA-wide dW phase; the weight-stationary kernels of small batches (njode_path.cuh) pass a functor whose step(j) runs
 // on all warps of the CTA, and then only warp 0 executes the warp-local sections of this function.
-struct NjSegWarpRev {
+template <bool OVF>
+struct NjSegWarpRevT {
     static constexpr bool stat = false;
     static constexpr bool glue = true;             // this instantiation contains the warp-local sections
+    static constexpr bool ovf = OVF;               // dW tiles beyond the register slots exist (nj_seg_dw)
+    static constexpr bool coop = false;            // layers of the warp-local sections: the warp's own GEMMs
     NJ_HD void run(int) const {}
     NJ_HD float* gpart(float* global_partial) const { return global_partial; }
+    NJ_HD void* mailbox() const { return nullptr; }
+    NJ_HD void serve(int) const {}
+    NJ_HD void glue_done() const {}
 };
+
+typedef NjSegWarpRevT<true> NjSegWarpRev;
 
 template <int TR, class REV = NjSegWarpRev>
 NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, const NjSegB& t, float* nj_acc_base,
@@ -826,7 +845,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
         // ================= the jump at the end of the segment, reversed =================
         // J1-J4 (warp-local): Y_bj = ro(h_before), E = enc(X_obs), Y = ro(E); loss gradients; ro backward at E
         NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && (!REV::glue || wp != 0)) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) { rev.serve(wp); continue; }
             NJ_SEGB_WARP_VIEW();
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
@@ -859,7 +878,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     if (ec0 == 0) { NJ_SEGB_KEY(r, valid, nj_seg_event_of_start(a, t.I[NJS_I_START * P + r])); }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, true, false);
+                nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_ENC, true, false);
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
                     const int r = r0 + er;
@@ -895,7 +914,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                         if (ec0 == 0) { NJ_SEGB_KEY(r, true, (unsigned)k); }
                     }
                     NJ_SYNCWARP();
-                    nj_seg_mlp_fwd<TR>(w, NJODE_NET_ODE, true, false);
+                    nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_ODE, true, false);
                     NJ_LANES(lane) {
                         NJ_ROWMAP(R);
                         const int r = r0 + er;
@@ -920,7 +939,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 0u)); }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, true, false);
+                nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_RO, true, false);
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
                     const int r = r0 + er, row = t.I[NJS_I_ROW * P + r];
@@ -937,7 +956,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 1u)); }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, true, false);
+                nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_ENC, true, false);
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
                     const int r = r0 + er, row = t.I[NJS_I_ROW * P + r];
@@ -953,7 +972,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 2u)); }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, true, false);
+                nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_RO, true, false);
                 // loss derivative (compute_loss / compute_loss_2, NJODE/models.py:71-126)
                 NJ_LANES(lane) {
                     if (lane < R) {
@@ -961,7 +980,8 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                         float ca = 0.f, cb = 0.f;
                         if (row >= 0) {
                             float sa = 0.f, sb = 0.f;
-                            for (int c_ = 0; c_ < c.dout; ++c_) {
+                            NJ_UNROLL4
+                    for (int c_ = 0; c_ < c.dout; ++c_) {      // (unrolled: the independent loads of four features go out together)
                                 float y = t.OUT[r * sO + c_];
                                 if (c.residual) y += nj_resid(t.EE + r * sH, c.H, c.dout, c_);
                                 t.YY[r * sD + c_] = y;
@@ -997,7 +1017,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_dx<TR>(w, NJODE_NET_RO, true);
+                nj_seg_mlp_dx<TR, REV::coop>(w, NJODE_NET_RO, true);
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
                     const int r = r0 + er;
@@ -1009,14 +1029,15 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     }
                 }
             }
+            rev.glue_done();
         }
         if (any_jump) {
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), gpart, tid, nt, Pt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw<REV::ovf>(c, s, t, NJODE_NET_RO, NJ_ACC(tid), gpart, tid, nt, Pt); }
             NJ_SYNC();
             // J5: encoder at X_obs, backward with g = dL/dE (from Y only)
             NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && (!REV::glue || wp != 0)) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) { rev.serve(wp); continue; }
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -1026,15 +1047,16 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 1u)); }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, true, true);
-                nj_seg_mlp_dx<TR>(w, NJODE_NET_ENC, false);
+                nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_ENC, true, true);
+                nj_seg_mlp_dx<TR, REV::coop>(w, NJODE_NET_ENC, false);
+                rev.glue_done();
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), gpart, tid, nt, Pt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw<REV::ovf>(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), gpart, tid, nt, Pt); }
             NJ_SYNC();
             // J6: readout at h_before, backward with g = dL/dY_bj -> gradient wrt h at the segment end
             NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && (!REV::glue || wp != 0)) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) { rev.serve(wp); continue; }
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -1046,8 +1068,8 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     if (ec0 == 0) { NJ_SEGB_KEY(r, row >= 0, nj_seg_event_of_jump(a, row >= 0 ? row : 0, 0u)); }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_fwd<TR>(w, NJODE_NET_RO, true, true);
-                nj_seg_mlp_dx<TR>(w, NJODE_NET_RO, true);
+                nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_RO, true, true);
+                nj_seg_mlp_dx<TR, REV::coop>(w, NJODE_NET_RO, true);
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
                     const int r = r0 + er;
@@ -1060,16 +1082,17 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                         }
                     }
                 }
+                rev.glue_done();
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_RO, NJ_ACC(tid), gpart, tid, nt, Pt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw<REV::ovf>(c, s, t, NJODE_NET_RO, NJ_ACC(tid), gpart, tid, nt, Pt); }
             NJ_SYNC();
         }
         // ================= Euler steps, reversed =================
         if (REV::stat) { NJ_SYNC(); rev.run(maxlen); }   // (GH / TX / tau of warp 0's prelude and jump reversal are visible to every warp)
         for (int j = REV::stat ? -1 : maxlen - 1; j >= 0; --j) {
             NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && (!REV::glue || wp != 0)) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) { rev.serve(wp); continue; }
                 NJ_SEGB_WARP_VIEW();
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
@@ -1097,8 +1120,8 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     if (ec0 == 0) { NJ_SEGB_KEY(r, true, (unsigned)k); }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_fwd<TR>(w, NJODE_NET_ODE, true, true);
-                nj_seg_mlp_dx<TR>(w, NJODE_NET_ODE, true);
+                nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_ODE, true, true);
+                nj_seg_mlp_dx<TR, REV::coop>(w, NJODE_NET_ODE, true);
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);
                     const int r = r0 + er;
@@ -1109,14 +1132,15 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                         }
                     }
                 }
+                rev.glue_done();
             }
             NJ_SYNC();
-            NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ODE, NJ_ACC(tid), gpart, tid, nt, Pt); }
+            NJ_THREADS(tid, nt) { nj_seg_dw<REV::ovf>(c, s, t, NJODE_NET_ODE, NJ_ACC(tid), gpart, tid, nt, Pt); }
             NJ_SYNC();
         }
         // ================= the start encoder, reversed =================
         NJ_WARPS(wp, s.nw_b) {
-                if (REV::stat && (!REV::glue || wp != 0)) continue;
+                if (REV::stat && (!REV::glue || wp != 0)) { rev.serve(wp); continue; }
             NJ_SEGB_WARP_VIEW();
             NJ_LANES(lane) {
                 NJ_ROWMAP(R);
@@ -1127,11 +1151,12 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                 if (ec0 == 0) { NJ_SEGB_KEY(r, valid, nj_seg_event_of_start(a, t.I[NJS_I_START * P + r])); }
             }
             NJ_SYNCWARP();
-            nj_seg_mlp_fwd<TR>(w, NJODE_NET_ENC, true, true);
-            nj_seg_mlp_dx<TR>(w, NJODE_NET_ENC, false);
+            nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_ENC, true, true);
+            nj_seg_mlp_dx<TR, REV::coop>(w, NJODE_NET_ENC, false);
+            rev.glue_done();
         }
         NJ_SYNC();
-        NJ_THREADS(tid, nt) { nj_seg_dw(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), gpart, tid, nt, Pt); }
+        NJ_THREADS(tid, nt) { nj_seg_dw<REV::ovf>(c, s, t, NJODE_NET_ENC, NJ_ACC(tid), gpart, tid, nt, Pt); }
         NJ_SYNC();
     }
 }
@@ -1141,7 +1166,7 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
 // of nj_seg_bwd_tile and only mirror its barriers and its CTA-wide dW phases.  (On the host simulation the NJ_THREADS
 // loops of nj_seg_bwd_tile already run the helper thread ids.)  Kept out of nj_seg_bwd_tile so that the row warps run
 // exactly the code they ran without helpers.
-template <int TR>
+template <int TR, bool OVF>
 __device__ __forceinline__ void nj_seg_bwd_tile_helper(const NjCfg& c, const NjSeg& s, const NjArgs& a, const NjSegB& t,
                                                        float* acc, int cta) {
     constexpr int R = 4 * TR;
@@ -1154,20 +1179,20 @@ __device__ __forceinline__ void nj_seg_bwd_tile_helper(const NjCfg& c, const NjS
         any_jump |= (t.I[NJS_I_ROW * P + r] >= 0);
     }
     if (any_jump) {
-        NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_RO, acc, gpart, tid, nt, Pt); NJ_SYNC();
-        NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_ENC, acc, gpart, tid, nt, Pt); NJ_SYNC();
-        NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_RO, acc, gpart, tid, nt, Pt); NJ_SYNC();
+        NJ_SYNC(); nj_seg_dw<OVF>(c, s, t, NJODE_NET_RO, acc, gpart, tid, nt, Pt); NJ_SYNC();
+        NJ_SYNC(); nj_seg_dw<OVF>(c, s, t, NJODE_NET_ENC, acc, gpart, tid, nt, Pt); NJ_SYNC();
+        NJ_SYNC(); nj_seg_dw<OVF>(c, s, t, NJODE_NET_RO, acc, gpart, tid, nt, Pt); NJ_SYNC();
     }
     for (int j = maxlen - 1; j >= 0; --j) {
-        NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_ODE, acc, gpart, tid, nt, Pt); NJ_SYNC();
+        NJ_SYNC(); nj_seg_dw<OVF>(c, s, t, NJODE_NET_ODE, acc, gpart, tid, nt, Pt); NJ_SYNC();
     }
-    NJ_SYNC(); nj_seg_dw(c, s, t, NJODE_NET_ENC, acc, gpart, tid, nt, Pt); NJ_SYNC();
+    NJ_SYNC(); nj_seg_dw<OVF>(c, s, t, NJODE_NET_ENC, acc, gpart, tid, nt, Pt); NJ_SYNC();
 }
 #endif
 
 // HELP: the launch has dW helper warps (a second instantiation of the kernel, so that launches without helpers run
 // exactly the code -- and the register allocation -- they had before helpers existed)
-template <bool HELP>
+template <bool HELP, bool OVF = true>
 NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, float* smem, int cta) {
     const int nt = s.nt_b;
     float* simg = smem + s.b_img;
@@ -1189,13 +1214,13 @@ NJ_HD void nj_seg_cta_backward(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
         const int tr = nj_seg_tile_lookup(s.b_ncls, s.b_t0, s.b_u0, s.b_u1, s.b_tr, 4 * s.nw_b, tile, ub, ue);
 #if !defined(NJODE_HOST_SIM)
         if (HELP && (int)(threadIdx.x >> 5) >= s.nw_b) {
-            if (tr == 2) nj_seg_bwd_tile_helper<2>(c, s, a, t, nj_acc_base, cta);
-            else nj_seg_bwd_tile_helper<1>(c, s, a, t, nj_acc_base, cta);
+            if (tr == 2) nj_seg_bwd_tile_helper<2, OVF>(c, s, a, t, nj_acc_base, cta);
+            else nj_seg_bwd_tile_helper<1, OVF>(c, s, a, t, nj_acc_base, cta);
             continue;
         }
 #endif
-        if (tr == 2) nj_seg_bwd_tile<2>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
-        else nj_seg_bwd_tile<1>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
+        if (tr == 2) nj_seg_bwd_tile<2, NjSegWarpRevT<OVF>>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
+        else nj_seg_bwd_tile<1, NjSegWarpRevT<OVF>>(c, s, a, smem, t, nj_acc_base, cta, ub, ue);
     }
     float* gpart = a.partials + (size_t)cta * c.img_floats;
     NJ_THREADS(tid, nt) { nj_seg_dw_flush(c, s, NJ_ACC(tid), gpart, tid, nt); }

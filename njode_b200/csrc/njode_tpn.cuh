@@ -99,24 +99,32 @@ NJ_HD void nj_tpn_t_load(const NjCfg& c, const float* simg, int k, NjTpnT<D>& t)
     for (int o = 0; o < 4 * D::KCH; ++o) t.c0[o] = (o < N.dim[1] && k < N.dim[0]) ? simg[N.w_img[0] + o * N.ks[0] + k] : 0.f;
 }
 
-// acc[r] = sum_j w[j] * x[r][j] over KC float4 chunks; four partial sums per row (the chain of dependent FFMA is KC long)
+// acc[r] = sum_j w[j] * x[r][j] over KC float4 chunks.  Four partial sums per row, eight for single-row tiles (even / odd
+// chunks): one thread alone on its scheduler slot needs that many independent FFMA chains to cover the FFMA latency
 template <int KC, int R>
 NJ_HD void nj_tpn_dot(const float* w, const float* x, int x_s, float* acc) {
-    float p[R][4];
+    constexpr int NP = R == 1 ? 8 : 4;
+    float p[R][NP];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { p[r][0] = 0.f; p[r][1] = 0.f; p[r][2] = 0.f; p[r][3] = 0.f; }
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) p[r][i] = 0.f;
     const nj_sp xp = nj_sp_of(x);
 #pragma unroll
     for (int q = 0; q < KC; ++q) {
+        const int b = NP == 8 ? 4 * (q & 1) : 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const nj_f4 v = nj_sp_ld4(NJ_SP_ADD(xp, r * x_s + 4 * q));
-            p[r][0] = fmaf(w[4 * q], v.x, p[r][0]); p[r][1] = fmaf(w[4 * q + 1], v.y, p[r][1]);
-            p[r][2] = fmaf(w[4 * q + 2], v.z, p[r][2]); p[r][3] = fmaf(w[4 * q + 3], v.w, p[r][3]);
+            p[r][b] = fmaf(w[4 * q], v.x, p[r][b]); p[r][b + 1] = fmaf(w[4 * q + 1], v.y, p[r][b + 1]);
+            p[r][b + 2] = fmaf(w[4 * q + 2], v.z, p[r][b + 2]); p[r][b + 3] = fmaf(w[4 * q + 3], v.w, p[r][b + 3]);
         }
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = (p[r][0] + p[r][1]) + (p[r][2] + p[r][3]);
+    for (int r = 0; r < R; ++r) {
+        if (NP == 8) acc[r] = ((p[r][0] + p[r][4]) + (p[r][1] + p[r][5])) + ((p[r][2] + p[r][6]) + (p[r][3] + p[r][7]));
+        else acc[r] = (p[r][0] + p[r][1]) + (p[r][2] + p[r][3]);
+    }
 }
 
 // hidden layer l of the ODE network, output o, all rows: out[r][o] = dropout(act(w . in[r] + b))
@@ -792,7 +800,7 @@ NJ_HD void nj_tpn_set(NjSegB& t, int off) { t.IN += off; t.A += off; t.G += off;
 #define NJN_SEG_DS(f, par, r) (f).F[NJS_F_CA * 16 + 8 + (par) * 4 + (r)]
 
 template <class D>
-NJ_HD void nj_segtpn_fwd_build(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1>& f, int o, int j) {
+NJ_HD void nj_segtpn_fwd_build(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, true>& f, int o, int j) {
     constexpr int R = NJN_SEG_R, RS = 16;
     const int inf4 = ((c.inf + 3) >> 2) << 2;
     for (int c_ = o; c_ < inf4; c_ += NJN_F) {
@@ -820,7 +828,7 @@ NJ_HD void nj_segtpn_fwd_build(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     }
 }
 template <class D>
-NJ_HD void nj_segtpn_fwd_p1(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1>& f, NjTpnF<D>& q, int o, int j, bool next) {
+NJ_HD void nj_segtpn_fwd_p1(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, true>& f, NjTpnF<D>& q, int o, int j, bool next) {
     constexpr int R = NJN_SEG_R, RS = 16;
     if (next && o == NJN_F - 1) {
 #pragma unroll
@@ -835,11 +843,11 @@ NJ_HD void nj_segtpn_fwd_p1(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjS
     nj_tpn_hidden<D::KC0, R>(c, 0, q.w0, q.b0, o, f.w.IN, s.sI, f.w.A0, s.sA, f.w.RK);
 }
 template <class D>
-NJ_HD void nj_segtpn_fwd_p2(const NjCfg& c, const NjSeg& s, NjSegFwd<1>& f, NjTpnF<D>& q, int o) {
+NJ_HD void nj_segtpn_fwd_p2(const NjCfg& c, const NjSeg& s, NjSegFwd<1, true>& f, NjTpnF<D>& q, int o) {
     nj_tpn_hidden<D::KCH, NJN_SEG_R>(c, 1, q.w1, q.b1, o, f.w.A0, s.sA, f.w.A1, s.sA, f.w.RK);
 }
 template <class D>
-NJ_HD void nj_segtpn_fwd_p3(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1>& f, NjTpnF<D>& q, int o, int j, bool next) {
+NJ_HD void nj_segtpn_fwd_p3(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, true>& f, NjTpnF<D>& q, int o, int j, bool next) {
     constexpr int R = NJN_SEG_R, RS = 16;
     float acc[R];
     nj_tpn_dot<D::KCH, R>(q.w2, f.w.A1, s.sA, acc);
@@ -874,7 +882,10 @@ NJ_HD void nj_segtpn_fwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, f
     constexpr int R = NJN_SEG_R, RS = 16;
     float* simg = smem + s.f_img;
     float* reg = smem + s.f_warp0;
-    NjSegFwd<1> f(c, s, a, reg, simg);
+    NjSegFwd<1, true> f(c, s, a, reg, simg);
+    NjCoopMB* mb = reinterpret_cast<NjCoopMB*>(reg + s.f_MB);
+    NJ_THREADS(tid, NJN_NT_FWD) { if (tid == 0) { mb->R = NJN_SEG_R; mb->op = 0; } }
+    f.w.coop = mb;
     int* slot = f.I + NJS_I_COUNT * RS;
     NJN_FREGS_DECL(D);
     NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_f_load<D>(c, simg, o, NJN_FREGS(o)); }
@@ -886,7 +897,7 @@ NJ_HD void nj_segtpn_fwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, f
         if (wt >= s.n_tiles_f) break;
         int ub, ue;
         nj_seg_tile_lookup(s.f_ncls, s.f_t0, s.f_u0, s.f_u1, s.f_tr, 4, wt, ub, ue);
-        if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) { NJ_WARPS(wp, 1) { if (wp == 0) f.begin(ub, ue); } }
+        NJN_GLUE(mb, f.begin(ub, ue));
         NJ_SYNC();
         int maxlen = 0;
         for (int r = 0; r < R; ++r) maxlen = f.I[NJS_I_LEN * RS + r] > maxlen ? f.I[NJS_I_LEN * RS + r] : maxlen;
@@ -904,7 +915,7 @@ NJ_HD void nj_segtpn_fwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, f
             }
         }
         NJ_SYNC();
-        if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) { NJ_WARPS(wp, 1) { if (wp == 0) { f.maxlen = maxlen; f.finish(); } } }
+        NJN_GLUE(mb, { f.maxlen = maxlen; f.finish(); });
         NJ_SYNC();
     }
 }
@@ -1005,10 +1016,24 @@ template <class D, int ROLE>
 struct NjSegTpnRev {
     static constexpr bool stat = true;
     static constexpr bool glue = (ROLE == NJN_ALL || ROLE == NJN_ROLE_G);
+    static constexpr bool ovf = true;              // every jump-network dW tile goes through the gradient image
+    static constexpr bool coop = true;             // the layers of the glue sections are served by the F threads
     const NjCfg& c; const NjSeg& s; const NjArgs& a; float* smem; const NjSegB& t;
-    NjTpnF<D>* njn_f; NjTpnT<D>* njn_t; float* njn_d; int cta; float* gimg;
+    NjTpnF<D>* njn_f; NjTpnT<D>* njn_t; float* njn_d; int cta; float* gimg; NjCoopMB* mb;
 
     NJ_HD float* gpart(float*) const { return gimg; }
+    NJ_HD void* mailbox() const { return mb; }
+    // a warp-local section of nj_seg_bwd_tile: the glue warp runs it and releases the servers, the F warps serve its layers
+    NJ_HD void serve(int) const {
+#if !defined(NJODE_HOST_SIM)
+        if (ROLE == NJN_ROLE_F) NJN_COOP_SERVE(mb, (int)threadIdx.x - NJN_F0);
+#endif
+    }
+    NJ_HD void glue_done() const {
+#if !defined(NJODE_HOST_SIM)
+        if (ROLE == NJN_ROLE_G) NJN_COOP_DONE(mb);
+#endif
+    }
 
     // steps n - 1 ... 0 of the tile, n + 2 pipeline iterations
     NJ_HD void run(int n) const {
@@ -1054,7 +1079,9 @@ NJ_HD void nj_segtpn_bwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, f
     NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_f_load<D>(c, simg, o, NJN_FREGS(o)); }
     NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, k) { nj_tpn_t_load<D>(c, simg, k, NJN_TREGS(k)); }
     NJN_ROLE(NJN_ROLE_D, NJN_D0, NJN_D, x) { nj_tpn_dw_table(c, s, smem, x); }
-    const NjSegTpnRev<D, ROLE> rev{c, s, a, smem, t, njn_f, njn_t, njn_d, cta, smem + s.b_GIMG - ode_floats};
+    NjCoopMB* mb = reinterpret_cast<NjCoopMB*>(smem + s.b_MB);
+    NJ_THREADS(tid, nt) { if (tid == 0) { mb->R = NJN_SEG_R; mb->op = 0; } }
+    const NjSegTpnRev<D, ROLE> rev{c, s, a, smem, t, njn_f, njn_t, njn_d, cta, smem + s.b_GIMG - ode_floats, mb};
     int* ctl = t.I + NJS_I_COUNT * s.P_b;
     for (;;) {
         NJ_THREADS(tid, nt) { if (tid == 0) ctl[0] = nj_atomic_inc(a.counter); }
