@@ -405,8 +405,8 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
             if ((size_t)s.f_smem_floats * 4 <= smem_limit && (size_t)s.b_smem_floats * 4 <= smem_limit) {
                 out.seg_smem_f_bytes = (size_t)s.f_smem_floats * 4;
                 out.seg_smem_b_bytes = (size_t)s.b_smem_floats * 4;
-                // forward CTAs are 3 warps with up to 255 registers: several per SM, tiles handed out by an atomic counter
-                out.seg_grid_f = std::max(1, std::min(s.n_tiles_f, 2 * num_sms));
+                // forward CTAs are 3 warps with ~215 registers: three per SM, tiles handed out by an atomic counter
+                out.seg_grid_f = std::max(1, std::min(s.n_tiles_f, 3 * num_sms));
                 out.seg_grid_b = std::max(1, std::min(s.n_tiles_b, num_sms));
                 s.ok = 1;
                 return;

@@ -791,6 +791,10 @@ NJ_HD void nj_tpn_cta_backward(const NjCfg& c, const NjPath& s, const NjArgs& a,
 // jump that ends the segments stay with the glue warp (njode_seg.cuh code).
 // ================================================================================================
 #define NJN_SEG_R 4
+// cooperative layers for the glue sections of segment tiles: measured neutral to slightly slower on B200 (bs_demo_200: forward
+// 0.21 -> 0.22 ms, backward 0.41 -> 0.44 ms) -- with 4 rows the glue warp's own warp GEMM has seven independent accumulators
+// per lane and is as fast as 64 threads with one dot product each plus two named barriers per layer.  Kept switchable.
+#define NJN_SEG_COOP false
 
 NJ_HD void nj_tpn_set(NjSegB& t, int off) { t.IN += off; t.A += off; t.G += off; t.GOUT += off; }
 
@@ -800,7 +804,7 @@ NJ_HD void nj_tpn_set(NjSegB& t, int off) { t.IN += off; t.A += off; t.G += off;
 #define NJN_SEG_DS(f, par, r) (f).F[NJS_F_CA * 16 + 8 + (par) * 4 + (r)]
 
 template <class D>
-NJ_HD void nj_segtpn_fwd_build(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, true>& f, int o, int j) {
+NJ_HD void nj_segtpn_fwd_build(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, NJN_SEG_COOP>& f, int o, int j) {
     constexpr int R = NJN_SEG_R, RS = 16;
     const int inf4 = ((c.inf + 3) >> 2) << 2;
     for (int c_ = o; c_ < inf4; c_ += NJN_F) {
@@ -828,7 +832,7 @@ NJ_HD void nj_segtpn_fwd_build(const NjCfg& c, const NjSeg& s, const NjArgs& a, 
     }
 }
 template <class D>
-NJ_HD void nj_segtpn_fwd_p1(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, true>& f, NjTpnF<D>& q, int o, int j, bool next) {
+NJ_HD void nj_segtpn_fwd_p1(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, NJN_SEG_COOP>& f, NjTpnF<D>& q, int o, int j, bool next) {
     constexpr int R = NJN_SEG_R, RS = 16;
     if (next && o == NJN_F - 1) {
 #pragma unroll
@@ -843,11 +847,11 @@ NJ_HD void nj_segtpn_fwd_p1(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjS
     nj_tpn_hidden<D::KC0, R>(c, 0, q.w0, q.b0, o, f.w.IN, s.sI, f.w.A0, s.sA, f.w.RK);
 }
 template <class D>
-NJ_HD void nj_segtpn_fwd_p2(const NjCfg& c, const NjSeg& s, NjSegFwd<1, true>& f, NjTpnF<D>& q, int o) {
+NJ_HD void nj_segtpn_fwd_p2(const NjCfg& c, const NjSeg& s, NjSegFwd<1, NJN_SEG_COOP>& f, NjTpnF<D>& q, int o) {
     nj_tpn_hidden<D::KCH, NJN_SEG_R>(c, 1, q.w1, q.b1, o, f.w.A0, s.sA, f.w.A1, s.sA, f.w.RK);
 }
 template <class D>
-NJ_HD void nj_segtpn_fwd_p3(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, true>& f, NjTpnF<D>& q, int o, int j, bool next) {
+NJ_HD void nj_segtpn_fwd_p3(const NjCfg& c, const NjSeg& s, const NjArgs& a, NjSegFwd<1, NJN_SEG_COOP>& f, NjTpnF<D>& q, int o, int j, bool next) {
     constexpr int R = NJN_SEG_R, RS = 16;
     float acc[R];
     nj_tpn_dot<D::KCH, R>(q.w2, f.w.A1, s.sA, acc);
@@ -882,7 +886,7 @@ NJ_HD void nj_segtpn_fwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, f
     constexpr int R = NJN_SEG_R, RS = 16;
     float* simg = smem + s.f_img;
     float* reg = smem + s.f_warp0;
-    NjSegFwd<1, true> f(c, s, a, reg, simg);
+    NjSegFwd<1, NJN_SEG_COOP> f(c, s, a, reg, simg);
     NjCoopMB* mb = reinterpret_cast<NjCoopMB*>(reg + s.f_MB);
     NJ_THREADS(tid, NJN_NT_FWD) { if (tid == 0) { mb->R = NJN_SEG_R; mb->op = 0; } }
     f.w.coop = mb;
@@ -897,7 +901,8 @@ NJ_HD void nj_segtpn_fwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, f
         if (wt >= s.n_tiles_f) break;
         int ub, ue;
         nj_seg_tile_lookup(s.f_ncls, s.f_t0, s.f_u0, s.f_u1, s.f_tr, 4, wt, ub, ue);
-        NJN_GLUE(mb, f.begin(ub, ue));
+        if (NJN_SEG_COOP) NJN_GLUE(mb, f.begin(ub, ue));
+        else if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) { NJ_WARPS(wp, 1) { if (wp == 0) f.begin(ub, ue); } }
         NJ_SYNC();
         int maxlen = 0;
         for (int r = 0; r < R; ++r) maxlen = f.I[NJS_I_LEN * RS + r] > maxlen ? f.I[NJS_I_LEN * RS + r] : maxlen;
@@ -915,7 +920,8 @@ NJ_HD void nj_segtpn_fwd_body(const NjCfg& c, const NjSeg& s, const NjArgs& a, f
             }
         }
         NJ_SYNC();
-        NJN_GLUE(mb, { f.maxlen = maxlen; f.finish(); });
+        if (NJN_SEG_COOP) NJN_GLUE(mb, { f.maxlen = maxlen; f.finish(); });
+        else if (ROLE == NJN_ALL || ROLE == NJN_ROLE_G) { NJ_WARPS(wp, 1) { if (wp == 0) { f.maxlen = maxlen; f.finish(); } } }
         NJ_SYNC();
     }
 }
@@ -1017,7 +1023,7 @@ struct NjSegTpnRev {
     static constexpr bool stat = true;
     static constexpr bool glue = (ROLE == NJN_ALL || ROLE == NJN_ROLE_G);
     static constexpr bool ovf = true;              // every jump-network dW tile goes through the gradient image
-    static constexpr bool coop = true;             // the layers of the glue sections are served by the F threads
+    static constexpr bool coop = NJN_SEG_COOP;     // the layers of the glue sections: served by the F threads / the glue warp's own GEMMs
     const NjCfg& c; const NjSeg& s; const NjArgs& a; float* smem; const NjSegB& t;
     NjTpnF<D>* njn_f; NjTpnT<D>* njn_t; float* njn_d; int cta; float* gimg; NjCoopMB* mb;
 
@@ -1026,12 +1032,12 @@ struct NjSegTpnRev {
     // a warp-local section of nj_seg_bwd_tile: the glue warp runs it and releases the servers, the F warps serve its layers
     NJ_HD void serve(int) const {
 #if !defined(NJODE_HOST_SIM)
-        if (ROLE == NJN_ROLE_F) NJN_COOP_SERVE(mb, (int)threadIdx.x - NJN_F0);
+        if (coop && ROLE == NJN_ROLE_F) NJN_COOP_SERVE(mb, (int)threadIdx.x - NJN_F0);
 #endif
     }
     NJ_HD void glue_done() const {
 #if !defined(NJODE_HOST_SIM)
-        if (ROLE == NJN_ROLE_G) NJN_COOP_DONE(mb);
+        if (coop && ROLE == NJN_ROLE_G) NJN_COOP_DONE(mb);
 #endif
     }
 
