@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define NJODE_ABI_VERSION 5
+#define NJODE_ABI_VERSION 6
 #define NJODE_MAX_LINEAR 8          /* max number of Linear layers per network */
 
 enum { NJODE_ACT_NONE = 0, NJODE_ACT_TANH = 1, NJODE_ACT_RELU = 2 };
@@ -116,6 +116,9 @@ typedef struct njode_plan {
                                   it recomputes the forward of every segment from its checkpoint at the observation time; this
                                   many bytes of the workspace hold the h chains of the tiles in flight.  0: the backward of this
                                   (model, batch) needs the history written by njode_forward */
+    int64_t act_bytes;         /* > 0: the kernels of this (model, batch) can keep the ODE network's hidden activations of every
+                                  Euler step (njode_saved_t.act_hist, this many bytes): the backward then reads them instead
+                                  of recomputing the hidden layers (optional: trade HBM for backward time) */
 } njode_plan_t;
 
 /* buffers produced by the forward pass that the backward pass re-reads; all NULL when the backward recomputes
@@ -124,6 +127,8 @@ typedef struct njode_saved {
     float* h_hist;             /* [S, B, hidden]  h at the start of every Euler step, or NULL (no grad / recompute) */
     float* h_before;           /* [N, hidden]     h just before the jump of row r, or NULL */
     float* y_after;            /* [N, output]     Y = readout(h after jump) of row r, or NULL */
+    float* act_hist;           /* njode_plan_t.act_bytes bytes or NULL: hidden activations of the ODE network per Euler step
+                                  (the same pointer, or NULL, in njode_forward and njode_backward) */
 } njode_saved_t;
 
 const char* njode_last_error(void);

@@ -13,6 +13,12 @@ from . import schedule as _sched
 
 MAX_LINEAR = 8
 RECOMPUTE_AUTO_BYTES = 256 << 20      # "auto": keep the [S, B, H] history of the forward pass up to this size
+# saved hidden activations of the ODE network (njode_plan_t.act_bytes: the segment backward reads them instead of
+# recomputing two layers per Euler step).  Measured on B200 (profiles/r2w_*): a gain while the records are a few hundred
+# MB (5 000 demo paths x 100 steps = 208 MB: step 2.38 -> 2.23 ms; 1 000 paths: 1.79 -> 1.63; 2x100 nets, 5 000 paths:
+# 7.77 -> 7.53), a loss at 832 MB (20 000 paths: the forward pays 0.25 ms for the stores, the backward gains 0.08 ms), so
+# they are kept up to this budget; NJODE_SAVE_ACTIVATIONS=0 turns them off
+SAVE_ACTIVATIONS_MAX_BYTES = int(os.environ.get("NJODE_SAVE_ACTIVATIONS_MAX_MB", "512")) << 20
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB_PATH = os.path.join(_HERE, "libnjode_b200.so")
 
@@ -47,11 +53,11 @@ class PlanT(C.Structure):
     _fields_ = [("tile_paths", C.c_int32), ("threads", C.c_int32), ("grid_fwd", C.c_int32),
                 ("grid_bwd", C.c_int32), ("weights_in_smem", C.c_int32), ("grads_in_smem", C.c_int32),
                 ("smem_fwd_bytes", C.c_int64), ("smem_bwd_bytes", C.c_int64),
-                ("image_floats", C.c_int64), ("workspace_bytes", C.c_int64), ("recompute_bytes", C.c_int64)]
+                ("image_floats", C.c_int64), ("workspace_bytes", C.c_int64), ("recompute_bytes", C.c_int64), ("act_bytes", C.c_int64)]
 
 
 class SavedT(C.Structure):
-    _fields_ = [("h_hist", C.c_void_p), ("h_before", C.c_void_p), ("y_after", C.c_void_p)]
+    _fields_ = [("h_hist", C.c_void_p), ("h_before", C.c_void_p), ("y_after", C.c_void_p), ("act_hist", C.c_void_p)]
 
 
 class SdeT(C.Structure):
@@ -92,7 +98,7 @@ class Lib:
                                      C.c_void_p, C.c_void_p]
         for f in (d.njode_plan, d.njode_forward, d.njode_backward):
             f.restype = C.c_int
-        if d.njode_abi_version() != 5:
+        if d.njode_abi_version() != 6:
             raise NjodeError("njode_b200: ABI version mismatch in %s" % path)
         # device index build (absent from the host simulation: the CPU-only tests use schedule.build_index_torch)
         self.has_index = hasattr(d, "njode_build_index")
@@ -438,6 +444,8 @@ class Runner:
         elif need_grad:
             saved = (torch.empty(max(pb.sched.S, 1) * pb.B * H, **f32),
                      torch.empty(max(pb.N, 1) * H, **f32), torch.empty(max(pb.N, 1) * dout, **f32))
+            if 0 < pl.act_bytes <= SAVE_ACTIVATIONS_MAX_BYTES and os.environ.get("NJODE_SAVE_ACTIVATIONS", "1") != "0":
+                saved = saved + (torch.empty(pl.act_bytes // 4, **f32),)
             saved_t = SavedT(*[C.c_void_p(t.data_ptr()) for t in saved])
         with self._guard():
             rc = self.lib.dll.njode_forward(C.byref(model_t), C.byref(pb.fwd), _ptr(params), _ptr(hT),

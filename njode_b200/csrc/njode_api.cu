@@ -289,6 +289,7 @@ extern "C" int njode_plan(const njode_model_t* model, const njode_batch_t* batch
     p->smem_fwd_bytes = (int64_t)o.smem_fwd_bytes; p->smem_bwd_bytes = (int64_t)o.smem_bwd_bytes;
     p->image_floats = o.fwd.img_floats; p->workspace_bytes = (int64_t)o.ws_bytes;
     p->recompute_bytes = (int64_t)o.scratch_bytes;
+    p->act_bytes = (int64_t)o.act_bytes;
     return 0;
 }
 
@@ -319,6 +320,7 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
     a.h_hist = saved ? saved->h_hist : nullptr;
     a.h_before = saved ? saved->h_before : nullptr;
     a.y_after = saved ? saved->y_after : nullptr;
+    a.act_hist = (saved && pl.act_bytes > 0) ? saved->act_hist : nullptr; a.act_nh = pl.act_nh; a.act_wp = pl.act_wp;
     a.get_loss = loss ? 1 : 0;
     a.n_tiles = pl.n_tiles;
     nj_pack_kernel<<<NJODE_NUM_NETS * NJODE_MAX_LINEAR, 256, 0, st>>>(pl.fwd, params, const_cast<float*>(a.image));
@@ -380,6 +382,7 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
     NjArgs a;
     nj_fill_args(a, batch, pl, (char*)workspace);
     a.h_hist = saved->h_hist; a.h_before = saved->h_before; a.y_after = saved->y_after;
+    a.act_hist = pl.act_bytes > 0 ? saved->act_hist : nullptr; a.act_nh = pl.act_nh; a.act_wp = pl.act_wp;
     if (recompute) a.scratch = reinterpret_cast<float*>((char*)workspace + pl.ws_scratch_off);
     a.grad_loss = grad_loss; a.grad_hT = grad_hT;
     a.get_loss = 1;

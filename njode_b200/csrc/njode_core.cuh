@@ -469,6 +469,10 @@ struct NjArgs {
     // segment backward without anything saved by the forward pass ("recompute forward segments from the checkpoints at
     // the observation times"): per-CTA scratch [S][P_b][sH] for the h chain of the tile being reversed, or NULL
     float* scratch;
+    // hidden activations of the ODE network at every Euler step, [S][B][act_nh][act_wp] (dropped units as -0.0f), or NULL:
+    // written by the segment forward, read by the segment backward instead of recomputing the two hidden layers
+    float* act_hist;
+    int act_nh, act_wp;
 };
 
 struct NjCta {

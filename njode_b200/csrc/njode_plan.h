@@ -19,6 +19,7 @@ struct NjPlanOut {
     int grid_fwd, grid_bwd;
     size_t smem_fwd_bytes, smem_bwd_bytes;
     size_t ws_image_off, ws_rowloss_off, ws_counter_off, ws_partials_off, ws_bytes;
+    size_t act_bytes; int act_nh, act_wp;      // saved hidden activations of the ODE network (segment warp kernels), see NjArgs
     size_t ws_scratch_off, scratch_bytes;      // segment backward in recompute mode: h chains of the tiles in flight
 };
 
@@ -724,8 +725,18 @@ static inline bool nj_plan_all(const njode_model_t& m, const njode_batch_t& b, i
                                NjPlanOut& out, std::string& err) {
     memset(&out.path, 0, sizeof(out.path));
     if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, false, out, err)) return false;
+    out.act_bytes = 0; out.act_nh = 0; out.act_wp = 0;
     nj_make_seg(out.fwd, b, num_sms, smem_limit, out);
-    if (out.seg.ok) return true;
+    if (out.seg.ok) {
+        const NjNet& O = out.fwd.net[NJODE_NET_ODE];
+        if (!out.seg.tpn && O.n >= 2 && O.n <= 3 && b.S > 0) {
+            int wmax = 0;
+            for (int l = 1; l < O.n; ++l) wmax = std::max(wmax, O.dim[l]);
+            out.act_nh = O.n - 1; out.act_wp = ((wmax + 3) / 4) * 4;
+            out.act_bytes = (size_t)b.S * (size_t)b.B * out.act_nh * out.act_wp * sizeof(float);
+        }
+        return true;
+    }
     nj_make_path(out.fwd, b, num_sms, smem_limit, out);
     if (out.path.ok) return true;
     if (!nj_make_plan(m, b.n_units, b.n_units, b.N, num_sms, smem_limit, force_P, true, out, err)) return false;

@@ -398,6 +398,33 @@ NJ_HD unsigned nj_seg_event_of_jump(const NjArgs& a, int row, unsigned which) {
 // ------------------------------------------------------------------------------------------------
 // forward: one warp = R = 4*TR units
 // ------------------------------------------------------------------------------------------------
+// saved hidden activations (NjArgs::act_hist): rows of one warp <-> [k][p][layer][act_wp] records, float4 per lane,
+// consecutive lanes on consecutive 16 bytes of a row.  kp[r] = step index of row r or -1 (row rests), pp[r] = its path.
+template <int R>
+NJ_HD void nj_seg_act_store(const NjArgs& a, int l, const float* buf, int buf_s, const int* kp, int kstride, const int* pp, int j) {
+    const int w4 = a.act_wp >> 2;
+    NJ_LANES(lane) {
+        for (int idx = lane; idx < R * w4; idx += 32) {
+            const int r = idx / w4, q = idx - r * w4;
+            if (j >= kp[NJS_I_LEN * kstride + r]) continue;
+            const size_t rec = ((size_t)(kp[NJS_I_S0 * kstride + r] + j) * a.b.B + pp[r]) * a.act_nh + l;
+            nj_st4(a.act_hist + rec * a.act_wp + 4 * q, nj_ld4(buf + (size_t)r * buf_s + 4 * q));
+        }
+    }
+}
+template <int R>
+NJ_HD void nj_seg_act_load(const NjArgs& a, int l, float* buf, int buf_s, const int* kp, int kstride, const int* pp, int j) {
+    const int w4 = a.act_wp >> 2;
+    NJ_LANES(lane) {
+        for (int idx = lane; idx < R * w4; idx += 32) {
+            const int r = idx / w4, q = idx - r * w4;
+            if (j >= kp[NJS_I_LEN * kstride + r]) continue;
+            const size_t rec = ((size_t)(kp[NJS_I_S0 * kstride + r] + j) * a.b.B + pp[r]) * a.act_nh + l;
+            nj_st4(buf + (size_t)r * buf_s + 4 * q, nj_ld4(a.act_hist + rec * a.act_wp + 4 * q));
+        }
+    }
+}
+
 // forward of one tile of R = 4*TR segment units by one warp, in three parts (the weight-stationary kernels of small
 // batches run begin / finish on warp 0 and replace the Euler steps by CTA-cooperative ones)
 template <int TR, bool COOP = false>
@@ -480,6 +507,7 @@ struct NjSegFwd {
 
     // Euler step j of the tile (units shorter than j + 1 steps rest)
     NJ_HD void step(int j) {
+        const int sA_ = s.sA;
 
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
@@ -510,6 +538,10 @@ struct NjSegFwd {
         }
         NJ_SYNCWARP();
         nj_seg_mlp_fwd<TR, COOP>(w, NJODE_NET_ODE, false, false);
+        if (a.act_hist) {                       // (the planner offers the buffer for ODE networks with <= 2 hidden layers: A0, A1)
+            nj_seg_act_store<R>(a, 0, w.A0, sA_, I, RS, I + NJS_I_PATH * RS, j);
+            if (a.act_nh > 1) nj_seg_act_store<R>(a, 1, w.A1, sA_, I, RS, I + NJS_I_PATH * RS, j);
+        }
         NJ_LANES(lane) {
             NJ_ROWMAP(R);
             if (j < I[NJS_I_LEN * RS + er]) {
@@ -1120,7 +1152,12 @@ NJ_HD void nj_seg_bwd_tile(const NjCfg& c, const NjSeg& s, const NjArgs& a, floa
                     if (ec0 == 0) { NJ_SEGB_KEY(r, true, (unsigned)k); }
                 }
                 NJ_SYNCWARP();
-                nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_ODE, true, true);
+                if (a.act_hist) {
+                    // the forward pass saved the hidden activations of this step: read them instead of recomputing two layers
+                    nj_seg_act_load<R>(a, 0, w.A0, s.sA, t.I + r0, P, t.I + NJS_I_PATH * P + r0, j);
+                    if (a.act_nh > 1) nj_seg_act_load<R>(a, 1, w.A0 + wa, s.sA, t.I + r0, P, t.I + NJS_I_PATH * P + r0, j);
+                    NJ_SYNCWARP();
+                } else nj_seg_mlp_fwd<TR, REV::coop>(w, NJODE_NET_ODE, true, true);
                 nj_seg_mlp_dx<TR, REV::coop>(w, NJODE_NET_ODE, true);
                 NJ_LANES(lane) {
                     NJ_ROWMAP(R);

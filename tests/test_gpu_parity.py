@@ -167,7 +167,7 @@ def test_native_library_is_loaded():
     from njode_b200 import _ext
     with open("/proc/self/maps") as f:
         assert "libnjode_b200.so" in f.read()
-    assert _ext.cuda_lib().dll.njode_abi_version() == 5
+    assert _ext.cuda_lib().dll.njode_abi_version() == 6
 
 
 @pytest.mark.parametrize("width", [50, 200])

@@ -38,6 +38,7 @@ def sim_runner():
     os.environ.pop("NJODE_NO_STAT", None)
     os.environ.pop("NJODE_NO_TPN", None)
     os.environ.pop("NJODE_FORCE_TPN", None)
+    os.environ.pop("NJODE_SAVE_ACTIVATIONS", None)
     os.environ.pop("NJODE_NO_PIPE", None)
     os.environ.pop("NJODE_FORCE_PIPE", None)
     os.environ.pop("NJODE_SIM_SMS", None)
@@ -433,3 +434,24 @@ def test_planner_gives_the_reference_batch_to_the_thread_per_neuron_kernels():
         for which in ("fwd", "bwd_all", "bwd_loss"):
             kind = hostsim_util.plan_kind(m, pb, which)
             assert "seg" in kind and ("segstat" in kind) == want, (B, layers, which, kind)
+
+
+# ---- saved hidden activations (njode_plan_t.act_bytes / njode_saved_t.act_hist): the default; without them the segment
+# backward recomputes the hidden layers of every step ----
+@pytest.mark.parametrize("tr", [1, 2])
+@pytest.mark.parametrize("name", ["bs_ckpt1", "heston_ckpt2", "curt_nobias_relu", "easy_w07_nores"])
+def test_segment_backward_recomputes_hidden_layers_without_saved_activations(name, tr):
+    os.environ["NJODE_SAVE_ACTIVATIONS"] = "0"
+    os.environ["NJODE_FORCE_TR"] = str(tr)
+    parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+    parity_util.check_training_call(name, "cpu")
+
+
+def test_saved_activations_train_mode_dropout_marks_survive():
+    """the saved records carry the dropout marks (-0.0f) the backward needs; one- and two-hidden-layer ODE networks"""
+    for layers in (1, 2):
+        cfg = cases.demo_cfg(dropout_rate=0.25, input_size=2, output_size=2, ode_nn=[[50, "tanh"]] * layers)
+        batch = cases.grid_batch(40, 2, 25, 0.2, seed=16)
+        for save in ("1", "0"):
+            os.environ["NJODE_SAVE_ACTIVATIONS"] = save
+            parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)

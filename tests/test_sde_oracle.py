@@ -98,4 +98,4 @@ def test_shared_library_exports_every_declared_symbol():
     for n in sorted(names):
         assert hasattr(lib, n), "libnjode_b200.so does not export " + n
     lib.njode_abi_version.restype = ctypes.c_int
-    assert lib.njode_abi_version() == 5
+    assert lib.njode_abi_version() == 6
