@@ -412,10 +412,19 @@ class Ctx:
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            # (the driver reads ONE JSON line from stdout: keep NCCL's own version banner out of it)
-            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-                os.environ["NCCL_DEBUG"] = "WARN"
-            dist.init_process_group("nccl", device_id=self.dev)
+            # the driver reads ONE JSON line from stdout, and NCCL prints its version banner (NCCL_DEBUG >= VERSION) to
+            # stdout when the first communicator comes up: point fd 1 at stderr until that has happened
+            sys.stdout.flush()
+            keep = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(keep, 1)
+                os.close(keep)
         lib = self.lib = _ext.cuda_lib().dll
         lib.njode_launch_count.restype = C.c_longlong
         lib.njode_get_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
