@@ -536,11 +536,16 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         const int nw = std::max(4, (maxo + 3) / 4);
         if (nw > 13) ok = false;                              // launch bounds: 416 threads
         if (ok) {
-            for (int cand = 1; cand <= 8 && !stat_R; cand *= 2)
-                if ((n + cand - 1) / cand <= num_sms) stat_R = cand;
-            if (force_r) stat_R = force_r;
+            // one path per CTA only: with several rows per tile the 12-warp pipelined kernels are faster (B200, PhysioNet
+            // nets: 300 records 136 ms here against 67 ms there, 600 records 342 against 85; profiles/r2z2_*)
+            if (n <= num_sms) stat_R = 1;
             const char* fs = getenv("NJODE_FORCE_STAT");      // tests: take the stationary kernels whatever the batch size
-            if (!stat_R && fs && atoi(fs)) stat_R = 8;
+            if (fs && atoi(fs)) {
+                for (int cand = 1; cand <= 8 && !stat_R; cand *= 2)
+                    if ((n + cand - 1) / cand <= num_sms) stat_R = cand;
+                if (!stat_R) stat_R = 8;
+            }
+            if (force_r && (stat_R || (fs && atoi(fs)))) stat_R = force_r;
         }
         if (stat_R) { s.stat = 1; s.nw_s = nw; }
     }
@@ -557,9 +562,11 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         int cls = 0;
         if (!(nt_ && atoi(nt_)) && O.n == 3) cls = fits(NJN_A_KC0, NJN_A_KCH, NJN_A_HC) ? 1 : (fits(NJN_B_KC0, NJN_B_KCH, NJN_B_HC) ? 2 : 0);
         if (cls) {
+            // tiles of 4 paths exist (tests, NJODE_FORCE_TPN) but lose to the pipelined warp kernels on B200 (300 PhysioNet
+            // records: 80 against 67 ms; 500 demo paths with the GRU jump: 3.9 against 3.0 ms): one path per CTA only
             if (n <= num_sms) tpn_R = 1;
-            else if ((n + 3) / 4 <= num_sms || (ft_ && atoi(ft_))) tpn_R = 4;
-            if (force_r) tpn_R = (force_r == 1 || force_r == 4) ? force_r : 0;
+            else if (ft_ && atoi(ft_)) tpn_R = 4;
+            if (force_r && (tpn_R || (ft_ && atoi(ft_)))) tpn_R = (force_r == 1 || force_r == 4) ? force_r : 0;
         }
         if (tpn_R) {
             s.tpn = cls; s.stat = 0; s.nw_s = 0; stat_R = 0;

@@ -27,6 +27,8 @@ def no_test_runner():
     os.environ.pop("NJODE_FORCE_TR", None)
     os.environ.pop("NJODE_NO_TPN", None)
     os.environ.pop("NJODE_NO_STAT", None)
+    os.environ.pop("NJODE_FORCE_TPN", None)
+    os.environ.pop("NJODE_FORCE_STAT", None)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -290,6 +292,8 @@ def test_small_physionet_batches_every_kernel_family(B, family):
         os.environ["NJODE_NO_TPN"] = "1"
     if family == "warp":
         os.environ["NJODE_NO_STAT"] = "1"
+    if B > 148:                        # (more than one path per SM: the planner's own choice is the pipelined warp kernels)
+        os.environ["NJODE_FORCE_TPN" if family == "tpn" else "NJODE_FORCE_STAT"] = "1"
     batch = cases.irregular_batch(B, 41, 60, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.2, feat_prob=0.12)
     cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
     parity_util.check_against_oracle(cfg, batch, 1.0 / 60, 1 + 1e-12, seed=5, device=DEV, train=True, grad_hT=True)
@@ -302,6 +306,8 @@ def test_small_physionet_batches_every_kernel_family(B, family):
 @pytest.mark.parametrize("B", [60, 400])
 def test_thread_per_neuron_kernels_demo_nets_gru_jump(B):
     """dimension class A (d = 1, H = 10, 2x50 nets) on whole-path units: the GRU-jump variant of the demo model"""
+    if B > 148:
+        os.environ["NJODE_FORCE_TPN"] = "1"
     cfg = cases.demo_cfg(use_rnn=True, dropout_rate=0.1)
     batch = cases.grid_batch(B, 1, 100, 0.1, seed=31)
     parity_util.check_against_oracle(cfg, batch, 0.01, 1.0, seed=6, device=DEV, train=True, grad_hT=True)

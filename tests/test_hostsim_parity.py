@@ -38,6 +38,7 @@ def sim_runner():
     os.environ.pop("NJODE_NO_STAT", None)
     os.environ.pop("NJODE_NO_TPN", None)
     os.environ.pop("NJODE_FORCE_TPN", None)
+    os.environ.pop("NJODE_FORCE_STAT", None)
     os.environ.pop("NJODE_SAVE_ACTIVATIONS", None)
     os.environ.pop("NJODE_NO_PIPE", None)
     os.environ.pop("NJODE_FORCE_PIPE", None)
@@ -270,7 +271,9 @@ def _pick(stat):
             pytest.skip("thread-per-neuron tiles have 1 or 4 rows")
         return
     os.environ["NJODE_NO_TPN"] = "1"
-    if stat != "weight-stationary":
+    if stat == "weight-stationary":
+        os.environ["NJODE_FORCE_STAT"] = "1"      # (the planner itself takes them for one path per CTA only)
+    else:
         os.environ["NJODE_NO_STAT"] = "1"
     if stat == "warp-gemm":
         os.environ["NJODE_NO_PIPE"] = "1"
@@ -322,9 +325,12 @@ def test_path_kernels_physionet_shape():
 
 @pytest.mark.parametrize("B", [50, 300])
 def test_thread_per_neuron_kernels_physionet_shape_with_the_b200_launch_plan(B):
-    """the reference's PhysioNet batch of 50 records (one path per CTA) and 300 records (tiles of 4) with the launch plan
-    of a 148-SM device: dimension class B (84 / 52 / 44), dropout on, gradient into hT"""
+    """the reference's PhysioNet batch of 50 records (one path per CTA: the planner's own choice) and 300 records (tiles of
+    4, forced: the planner gives such batches to the pipelined warp kernels) with the launch plan of a 148-SM device:
+    dimension class B (84 / 52 / 44), dropout on, gradient into hT"""
     os.environ["NJODE_SIM_SMS"] = "148"
+    if B > 148:
+        os.environ["NJODE_FORCE_TPN"] = "1"
     batch = cases.irregular_batch(B, 41, 12, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
     cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
     m = models.NJODE(**cfg)
@@ -340,6 +346,7 @@ def test_weight_stationary_kernels_physionet_shape_with_the_b200_launch_plan(B):
     2 rows per CTA) with the launch plan of a 148-SM device: d = H = 41 masked, 2x50 nets -> 13 warps per CTA"""
     os.environ["NJODE_SIM_SMS"] = "148"
     os.environ["NJODE_NO_TPN"] = "1"
+    os.environ["NJODE_FORCE_STAT"] = "1"
     batch = cases.irregular_batch(B, 41, 12, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
     cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
     parity_util.check_against_oracle(cfg, batch, 1.0 / 12, 1 + 1e-12, seed=5, device="cpu", train=True, grad_hT=True)
@@ -455,3 +462,19 @@ def test_saved_activations_train_mode_dropout_marks_survive():
         for save in ("1", "0"):
             os.environ["NJODE_SAVE_ACTIVATIONS"] = save
             parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
+
+
+def test_planner_kernel_families_for_whole_path_batches():
+    """B200 launch plan: up to one path per SM -> thread per neuron (K-split stationary kernels for ODE networks outside
+    the dimension classes); more -> the pipelined warp kernels (measured: profiles/r2z2_*)"""
+    os.environ["NJODE_SIM_SMS"] = "148"
+    for B, layers, want in ((50, 2, "tpn"), (148, 2, "tpn"), (300, 2, "pipe"), (600, 2, "pipe"), (50, 1, "pathstat")):
+        cfg = dict(cases.CONFIGS["masked_physio"], ode_nn=[[50, "tanh"]] * layers)
+        m = models.NJODE(**cfg)
+        batch = cases.irregular_batch(B, 41, 6, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
+        pb = m.prepare_batch(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 1.0 / 6, 1 + 1e-12, batch["start_X"],
+                             batch["n_obs_ot"], M=batch["M"])
+        for which in ("fwd", "bwd_all"):
+            kind = hostsim_util.plan_kind(m, pb, which)
+            assert "path" in kind and (want in kind or which == "fwd" and want == "pipe"), (B, layers, which, kind)
+            assert not ({"tpn", "pathstat"} - {want}) & kind, (B, layers, which, kind)
