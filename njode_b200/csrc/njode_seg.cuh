@@ -760,7 +760,14 @@ NJ_HD void nj_seg_tile_store(const NjCfg& c, int netid, int l, int og, int kg, c
 // the kernel) while the same source is correct in the host simulation.
 NJ_HDN void nj_seg_dw_overflow(const NjCfg* cp, const NjSeg* sp, const NjSegB* tp, int netid, float* gpart, int tid, int nt, int Pt) {
     const NjCfg& c = *cp; const NjSeg& s = *sp; const NjSegB& t = *tp;
-    for (int T = s.nt_slots * nt + tid; T < s.tiles_total; T += nt) {
+    // the tiles of one network are a contiguous range of the tile numbering: walk the part of it beyond the register slots
+    int lo = s.tile_base[netid][0], hi = s.tiles_total;
+    for (int q = 0; q < 3; ++q) {
+        const int b = s.tile_base[q][0];
+        if (b > lo && b < hi) hi = b;
+    }
+    if (lo < s.nt_slots * nt) lo = s.nt_slots * nt;
+    for (int T = lo + tid; T < hi; T += nt) {
         int l, og, kg;
         if (!nj_seg_tile_decode(c, s, netid, T, l, og, kg)) continue;
         float q[20];
