@@ -41,5 +41,7 @@ def text(f, l):
         except Exception: srcs[f] = []
     return srcs[f][l - 1].strip()[:90] if 0 < l <= len(srcs[f]) else ""
 print("total warp instr %d, samples %d" % (tot, ts))
-for key, n in cnt.most_common(top):
+order = smp.most_common(top) if len(sys.argv) > 5 and sys.argv[5] == "stall" else cnt.most_common(top)
+for key, _n in order:
+    n = cnt[key]
     print("%5.2f%% instr %5.2f%% stall  %s:%d  %s" % (100.0 * n / tot, 100.0 * smp[key] / max(ts, 1), key[0], key[1], text(*key)))
