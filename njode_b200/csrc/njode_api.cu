@@ -43,126 +43,13 @@ __global__ void __launch_bounds__(256) nj_bwd_kernel(const __grid_constant__ NjC
     nj_cta_backward(cfg, args, nj_smem, blockIdx.x, gridDim.x);
 }
 
-__global__ void __launch_bounds__(384) nj_seg_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
-                                                         const __grid_constant__ NjArgs args) {
-    nj_seg_cta_forward(cfg, seg, args, nj_smem);
-}
+// the segment kernels (njode_seg.cuh) live in njode_api_seg.cu, compiled concurrently with this file
+cudaError_t nj_launch_seg(const NjPlanOut& pl, const NjArgs& a, bool bwd, cudaStream_t st, const char** name);
 
-__global__ void __launch_bounds__(384) nj_seg_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
-                                                         const __grid_constant__ NjArgs args) {
-    nj_seg_cta_backward<false>(cfg, seg, args, nj_smem, blockIdx.x);
-}
-
-// ... and for launches whose dW tiles all fit the register slots (no out-of-line overflow code: see nj_seg_dw)
-__global__ void __launch_bounds__(384) nj_seg_bwd_kernel_r(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
-                                                           const __grid_constant__ NjArgs args) {
-    nj_seg_cta_backward<false, false>(cfg, seg, args, nj_smem, blockIdx.x);
-}
-
-// the same kernel for launches with dW helper warps (seg.nt_b > 32 * seg.nw_b), see nj_seg_cta_backward
-__global__ void __launch_bounds__(384) nj_seg_bwd_kernel_h(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
-                                                           const __grid_constant__ NjArgs args) {
-    nj_seg_cta_backward<true>(cfg, seg, args, nj_smem, blockIdx.x);
-}
-
-// whole-path units on the warp GEMMs (njode_path.cuh); one kernel per (row groups, rows per group) tile shape
-template <int RG, int TR>
-__global__ void __launch_bounds__(384) nj_path_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
-                                                          const __grid_constant__ NjArgs args) {
-    nj_path_cta_forward<RG, TR>(cfg, path, args, nj_smem);
-}
-template <int RG, int TR>
-__global__ void __launch_bounds__(384) nj_path_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
-                                                          const __grid_constant__ NjArgs args) {
-    nj_path_cta_backward<RG, TR>(cfg, path, args, nj_smem, blockIdx.x);
-}
-// the same units with weight-stationary Euler steps (small batches): all warps of a CTA on one tile
-// (13 warps: warps are allocated in groups of 4, so the register file gives a 416-thread CTA 128 registers per thread)
-template <int RG, int TR>
-__global__ void __launch_bounds__(416) nj_stat_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
-                                                          const __grid_constant__ NjArgs args) {
-    nj_stat_cta_forward<RG, TR>(cfg, path, args, nj_smem);
-}
-template <int RG, int TR>
-__global__ void __launch_bounds__(416) nj_stat_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
-                                                          const __grid_constant__ NjArgs args) {
-    nj_stat_cta_backward<RG, TR>(cfg, path, args, nj_smem, blockIdx.x);
-}
-// pipelined backward: dW of the ODE network on helper warps, concurrent with the row warps' next step
-template <int RG, int TR>
-__global__ void __launch_bounds__(384) nj_path_bwd_pipe_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
-                                                               const __grid_constant__ NjArgs args) {
-    nj_path_cta_backward_pipe<RG, TR>(cfg, path, args, nj_smem, blockIdx.x);
-}
-// thread-per-neuron kernels of small whole-path batches (njode_tpn.cuh): F / T / D warps around a glue warp
-typedef NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 1> NjTpnA1;
-typedef NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 4> NjTpnA4;
-typedef NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 1> NjTpnB1;
-typedef NjTpnDims<NJN_B_KC0, NJN_B_KCH, NJN_B_HC, 4> NjTpnB4;
-template <class D>
-__global__ void __launch_bounds__(NJN_NT_FWD) nj_tpn_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
-                                                                const __grid_constant__ NjArgs args) {
-    nj_tpn_cta_forward<D>(cfg, path, args, nj_smem);
-}
-template <class D>
-__global__ void __launch_bounds__(NJN_NT_BWD) nj_tpn_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjPath path,
-                                                                const __grid_constant__ NjArgs args) {
-    nj_tpn_cta_backward<D>(cfg, path, args, nj_smem, blockIdx.x);
-}
-// segment units of small batches on the same roles (nj_segtpn_*, tiles of 4 segments)
-template <class D>
-__global__ void __launch_bounds__(NJN_NT_FWD) nj_segtpn_fwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
-                                                                   const __grid_constant__ NjArgs args) {
-    nj_segtpn_cta_forward<D>(cfg, seg, args, nj_smem);
-}
-template <class D>
-__global__ void __launch_bounds__(NJN_NT_BWD) nj_segtpn_bwd_kernel(const __grid_constant__ NjCfg cfg, const __grid_constant__ NjSeg seg,
-                                                                   const __grid_constant__ NjArgs args) {
-    nj_segtpn_cta_backward<D>(cfg, seg, args, nj_smem, blockIdx.x);
-}
-typedef void (*nj_path_kern_t)(const NjCfg, const NjPath, const NjArgs);
-static nj_path_kern_t nj_tpn_pick(int cls, int R, bool bwd, const char** name) {
-    if (!bwd) {
-        if (cls == 1 && R == 1) { *name = "nj_tpn_fwd_kernel<A,1>"; return nj_tpn_fwd_kernel<NjTpnA1>; }
-        if (cls == 1) { *name = "nj_tpn_fwd_kernel<A,4>"; return nj_tpn_fwd_kernel<NjTpnA4>; }
-        if (R == 1) { *name = "nj_tpn_fwd_kernel<B,1>"; return nj_tpn_fwd_kernel<NjTpnB1>; }
-        *name = "nj_tpn_fwd_kernel<B,4>"; return nj_tpn_fwd_kernel<NjTpnB4>;
-    }
-    if (cls == 1 && R == 1) { *name = "nj_tpn_bwd_kernel<A,1>"; return nj_tpn_bwd_kernel<NjTpnA1>; }
-    if (cls == 1) { *name = "nj_tpn_bwd_kernel<A,4>"; return nj_tpn_bwd_kernel<NjTpnA4>; }
-    if (R == 1) { *name = "nj_tpn_bwd_kernel<B,1>"; return nj_tpn_bwd_kernel<NjTpnB1>; }
-    *name = "nj_tpn_bwd_kernel<B,4>"; return nj_tpn_bwd_kernel<NjTpnB4>;
-}
-static nj_path_kern_t nj_pipe_pick(int rg, int tr, const char** name) {
-    if (rg == 1) { *name = "nj_path_bwd_pipe_kernel<1,1>"; return nj_path_bwd_pipe_kernel<1, 1>; }
-    if (rg == 2) { *name = "nj_path_bwd_pipe_kernel<2,1>"; return nj_path_bwd_pipe_kernel<2, 1>; }
-    if (tr == 1) { *name = "nj_path_bwd_pipe_kernel<4,1>"; return nj_path_bwd_pipe_kernel<4, 1>; }
-    *name = "nj_path_bwd_pipe_kernel<4,2>"; return nj_path_bwd_pipe_kernel<4, 2>;
-}
-static nj_path_kern_t nj_stat_pick(int rg, int tr, bool bwd, const char** name) {
-    if (!bwd) {
-        if (rg == 1) { *name = "nj_stat_fwd_kernel<1,1>"; return nj_stat_fwd_kernel<1, 1>; }
-        if (rg == 2) { *name = "nj_stat_fwd_kernel<2,1>"; return nj_stat_fwd_kernel<2, 1>; }
-        if (tr == 1) { *name = "nj_stat_fwd_kernel<4,1>"; return nj_stat_fwd_kernel<4, 1>; }
-        *name = "nj_stat_fwd_kernel<4,2>"; return nj_stat_fwd_kernel<4, 2>;
-    }
-    if (rg == 1) { *name = "nj_stat_bwd_kernel<1,1>"; return nj_stat_bwd_kernel<1, 1>; }
-    if (rg == 2) { *name = "nj_stat_bwd_kernel<2,1>"; return nj_stat_bwd_kernel<2, 1>; }
-    if (tr == 1) { *name = "nj_stat_bwd_kernel<4,1>"; return nj_stat_bwd_kernel<4, 1>; }
-    *name = "nj_stat_bwd_kernel<4,2>"; return nj_stat_bwd_kernel<4, 2>;
-}
-static nj_path_kern_t nj_path_pick(int rg, int tr, bool bwd, const char** name) {
-    if (!bwd) {
-        if (rg == 1) { *name = "nj_path_fwd_kernel<1,1>"; return nj_path_fwd_kernel<1, 1>; }
-        if (rg == 2) { *name = "nj_path_fwd_kernel<2,1>"; return nj_path_fwd_kernel<2, 1>; }
-        if (tr == 1) { *name = "nj_path_fwd_kernel<4,1>"; return nj_path_fwd_kernel<4, 1>; }
-        *name = "nj_path_fwd_kernel<4,2>"; return nj_path_fwd_kernel<4, 2>;
-    }
-    if (rg == 1) { *name = "nj_path_bwd_kernel<1,1>"; return nj_path_bwd_kernel<1, 1>; }
-    if (rg == 2) { *name = "nj_path_bwd_kernel<2,1>"; return nj_path_bwd_kernel<2, 1>; }
-    if (tr == 1) { *name = "nj_path_bwd_kernel<4,1>"; return nj_path_bwd_kernel<4, 1>; }
-    *name = "nj_path_bwd_kernel<4,2>"; return nj_path_bwd_kernel<4, 2>;
-}
+// the kernels of whole-path units and of small batches (njode_path.cuh, njode_tpn.cuh) live in their own translation unit,
+// njode_api_path.cu, compiled concurrently with this one
+cudaError_t nj_launch_path(const NjPlanOut& pl, const NjArgs& a, bool bwd, cudaStream_t st, const char** name);
+cudaError_t nj_launch_segtpn(const NjPlanOut& pl, const NjArgs& a, bool bwd, cudaStream_t st, const char** name);
 
 // flat parameters -> zero-padded image; one block per (net, layer)
 __global__ void nj_pack_kernel(const __grid_constant__ NjCfg cfg, const float* __restrict__ params, float* __restrict__ image) {
@@ -331,24 +218,19 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[0], st);
         if (pl.seg.tpn) {
-            auto kern = pl.seg.tpn == 1 ? nj_segtpn_fwd_kernel<NjTpnA4> : nj_segtpn_fwd_kernel<NjTpnB4>;
-            NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
-            kern<<<pl.seg_grid_f, NJN_NT_FWD, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
-            nj_set_last_kernel(0, pl.seg.tpn == 1 ? "nj_segtpn_fwd_kernel<A>" : "nj_segtpn_fwd_kernel<B>");
+            const char* name = "";
+            NJ_CUDA(nj_launch_segtpn(pl, a, false, st, &name));
+            nj_set_last_kernel(0, name);
         } else {
-            NJ_CUDA(cudaFuncSetAttribute(nj_seg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_f_bytes));
-            nj_seg_fwd_kernel<<<pl.seg_grid_f, pl.seg.nw_f * 32, pl.seg_smem_f_bytes, st>>>(pl.fwd, pl.seg, a);
-            nj_set_last_kernel(0, "nj_seg_fwd_kernel");
+            const char* name = "";
+            NJ_CUDA(nj_launch_seg(pl, a, false, st, &name));
+            nj_set_last_kernel(0, name);
         }
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";
-        nj_path_kern_t kern = pl.path.tpn ? nj_tpn_pick(pl.path.tpn, pl.path.rg_f * pl.path.tr_f, false, &name)
-                              : (pl.path.stat ? nj_stat_pick(pl.path.rg_f, pl.path.tr_f, false, &name)
-                                              : nj_path_pick(pl.path.rg_f, pl.path.tr_f, false, &name));
-        NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_f_bytes));
         if (tm) cudaEventRecord(g_ev[0], st);
-        kern<<<pl.path_grid_f, pl.path.tpn ? NJN_NT_FWD : (pl.path.stat ? pl.path.nw_s : pl.path.nw_f) * 32, pl.path_smem_f_bytes, st>>>(pl.fwd, pl.path, a);
+        NJ_CUDA(nj_launch_path(pl, a, false, st, &name));
         nj_set_last_kernel(0, name);
     } else {
         nj_set_last_kernel(0, "nj_fwd_kernel");
@@ -396,26 +278,21 @@ extern "C" int njode_backward(const njode_model_t* model, const njode_batch_t* b
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.seg_grid_b;
-        const bool seg_in_regs = pl.seg.tiles_total <= pl.seg.nt_slots * pl.seg.nt_b;
-        auto kern = pl.seg.tpn ? (pl.seg.tpn == 1 ? nj_segtpn_bwd_kernel<NjTpnA4> : nj_segtpn_bwd_kernel<NjTpnB4>)
-                               : (pl.seg.nt_b > 32 * pl.seg.nw_b ? nj_seg_bwd_kernel_h
-                                  : (seg_in_regs ? nj_seg_bwd_kernel_r : nj_seg_bwd_kernel));
-        NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.seg_smem_b_bytes));
-        kern<<<pl.seg_grid_b, pl.seg.nt_b, pl.seg_smem_b_bytes, st>>>(pl.bwd, pl.seg, a);
-        nj_set_last_kernel(1, pl.seg.tpn ? (pl.seg.tpn == 1 ? "nj_segtpn_bwd_kernel<A>" : "nj_segtpn_bwd_kernel<B>")
-                                         : (pl.seg.nt_b > 32 * pl.seg.nw_b ? "nj_seg_bwd_kernel_h" : (seg_in_regs ? "nj_seg_bwd_kernel_r" : "nj_seg_bwd_kernel")));
+        if (pl.seg.tpn) {
+            const char* name = "";
+            NJ_CUDA(nj_launch_segtpn(pl, a, true, st, &name));
+            nj_set_last_kernel(1, name);
+        } else {
+            const char* name = "";
+            NJ_CUDA(nj_launch_seg(pl, a, true, st, &name));
+            nj_set_last_kernel(1, name);
+        }
     } else if (pl.path.ok) {
         NJ_CUDA(cudaMemsetAsync(a.counter, 0, 4, st));
         const char* name = "";
-        nj_path_kern_t kern = pl.path.tpn ? nj_tpn_pick(pl.path.tpn, pl.path.rg_b * pl.path.tr_b, true, &name)
-                              : pl.path.stat ? nj_stat_pick(pl.path.rg_b, pl.path.tr_b, true, &name)
-                              : (pl.path.pipe ? nj_pipe_pick(pl.path.rg_b, pl.path.tr_b, &name)
-                                              : nj_path_pick(pl.path.rg_b, pl.path.tr_b, true, &name));
-        NJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.path_smem_b_bytes));
         if (tm) cudaEventRecord(g_ev[2], st);
         nparts = pl.path_grid_b;
-        if (getenv("NJODE_DEBUG_PLAN")) fprintf(stderr, "[bwd] ws %p partials %p (+%zu) img %d grid %d nt %d ws_bytes %zu\n", workspace, (void*)a.partials, pl.ws_partials_off, pl.bwd.img_floats, pl.path_grid_b, pl.path.nt_b, pl.ws_bytes);
-        kern<<<pl.path_grid_b, pl.path.nt_b, pl.path_smem_b_bytes, st>>>(pl.bwd, pl.path, a);
+        NJ_CUDA(nj_launch_path(pl, a, true, st, &name));
         nj_set_last_kernel(1, name);
     } else {
         nj_set_last_kernel(1, "nj_bwd_kernel");

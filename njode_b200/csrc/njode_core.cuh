@@ -33,7 +33,7 @@ static inline nj_f4 nj_ld4(const float* p) { nj_f4 v; memcpy(&v, p, 16); return 
 static inline void nj_st4(float* p, const nj_f4& v) { memcpy(p, &v, 16); }
 #else
 #define NJ_HD __device__ __forceinline__
-#define NJ_HDN __device__ __noinline__
+#define NJ_HDN static __device__ __noinline__
 #define NJ_UNROLL4 _Pragma("unroll 4")
 #define NJ_THREADS(tid, nt) for (int tid = threadIdx.x, _nj_e = threadIdx.x + 1; tid < _nj_e; ++tid)
 #define NJ_SYNC() __syncthreads()
