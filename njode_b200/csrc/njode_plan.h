@@ -611,6 +611,8 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             s.f_I = o; o += NJP_I_COUNT * NJP_RS + 4;
             o = (o + 3) & ~3;
             s.f_MB = o; if (s.tpn) o += (int)((sizeof(NjCoopMB) + 15) / 16) * 4;    // mailbox of the cooperative jump layers
+            s.f_IN2 = o; if (s.tpn) o += R * s.sI;                                // input rows of the other step parity
+            s.f_AUX = o; if (s.tpn) o += 16;                                      // dropout layer keys [parity][layer][4]
             return (o + 3) & ~3;
         };
         // the smallest tile height whose warps still fit the machine in one wave of 12-warp CTAs: smaller tiles = more
@@ -666,7 +668,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             s.b_PART = o; if (s.stat) o += 2 * P * s.nw_s * NJT_PARTW;
             // thread-per-neuron backward: dW tile table [slots * owners][2], prefetch slots (time, step size, h) of the next step
             s.b_TD = o; if (s.tpn) o += 2 * NJN_DSLOTS * NJN_D;
-            s.b_PRE = o; if (s.tpn) o += 4 + 2 * P * s.sH;
+            s.b_PRE = o; if (s.tpn) o += NJN_PRE_HDR + 2 * P * s.sH;
             o = (o + 3) & ~3;
             s.b_MB = o; if (s.tpn) o += (int)((sizeof(NjCoopMB) + 15) / 16) * 4;
             // gradient image of the jump networks (everything behind the ODE network; zeroed with the other buffers)

@@ -47,10 +47,13 @@ template <int KC0_, int KCH_, int HC_, int R_> struct NjTpnDims {
 #if defined(NJODE_HOST_SIM)
 #define NJN_ROLE(ROLEID, lo, n, IDX) for (int IDX = 0; IDX < (n); ++IDX)
 #define NJN_SYNC_F() ((void)0)
+#define NJN_SYNC_STEP() ((void)0)
 #define NJN_SYNC_FT() ((void)0)
 #else
 #define NJN_ROLE(ROLEID, lo, n, IDX) if (ROLE == ROLEID) for (int IDX = (int)threadIdx.x - (lo), _nj_xe = IDX + 1; IDX < _nj_xe; ++IDX)
 #define NJN_SYNC_F() do { if (ROLE == NJN_ROLE_F) asm volatile("bar.sync 1, 64;" ::: "memory"); } while (0)
+// end of a forward step: the F warps and the glue warp (which prepared the next step's scalars meanwhile)
+#define NJN_SYNC_STEP() do { if (ROLE == NJN_ROLE_F || ROLE == NJN_ROLE_G) asm volatile("bar.sync 3, 96;" ::: "memory"); } while (0)
 #define NJN_SYNC_FT() do { if (ROLE == NJN_ROLE_F || ROLE == NJN_ROLE_T) asm volatile("bar.sync 1, 160;" ::: "memory"); } while (0)
 #endif
 
@@ -130,7 +133,7 @@ NJ_HD void nj_tpn_dot(const float* w, const float* x, int x_s, float* acc) {
 // hidden layer l of the ODE network, output o, all rows: out[r][o] = dropout(act(w . in[r] + b))
 template <int KC, int R>
 NJ_HD void nj_tpn_hidden(const NjCfg& c, int l, const float* w, float bias, int o, const float* in, int in_s, float* out, int out_s,
-                         const int* rk) {
+                         const int* rk, const int* lkeys = nullptr) {
     const NjNet& N = c.net[NJODE_NET_ODE];
     float acc[R];
     nj_tpn_dot<KC, R>(w, in, in_s, acc);
@@ -140,7 +143,8 @@ NJ_HD void nj_tpn_hidden(const NjCfg& c, int l, const float* w, float bias, int 
     for (int r = 0; r < R; ++r) {
         float v = nj_act(acc[r] + bias, N.act[l]);
         if (c.has_drop) {
-            const unsigned lk = nj_layer_key((unsigned)rk[r], (unsigned)(NJODE_NET_ODE * 16 + l + 1));
+            // (lkeys: the layer keys of the rows, hashed ahead of time by the glue warp -- the same for every output)
+            const unsigned lk = lkeys ? (unsigned)lkeys[r] : nj_layer_key((unsigned)rk[r], (unsigned)(NJODE_NET_ODE * 16 + l + 1));
             v = nj_keep(lk, (unsigned)o, c.thr) ? v * c.keep_scale : nj_u2f(NJ_DROPPED);
         }
         out[(size_t)r * out_s + o] = pad ? 0.f : v;
@@ -302,12 +306,20 @@ __device__ __forceinline__ void nj_coop_serve(const NjCoopMB* mb, int o) {
 // ================================================================================================
 // forward
 // ================================================================================================
+// Forward, per-step state in the region of the tile: the input rows exist twice (step parity: phase 3 and the glue warp fill
+// the rows of step k + 1 while nobody reads them), so do the step sizes (F slot CA) and the dropout layer keys of the two
+// hidden layers (region AUX: [parity][layer][4 rows]).
+#define NJN_FWD_IN(f, s, par) ((f).w.IN + ((par) ? (s).f_IN2 - (s).f_IN : 0))
+#define NJN_FWD_LK(reg, s, par, l) (reinterpret_cast<int*>((reg) + (s).f_AUX) + ((par) * 2 + (l)) * 4)
+
 // F thread o: the whole input rows of step k from the state (first step after a jump / the start / a record)
 template <class D>
-NJ_HD void nj_tpn_fwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, int o, int k) {
+NJ_HD void nj_tpn_fwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, float* reg, int o, int k) {
     constexpr int R = D::R, RS = NJP_RS;
     const int inf4 = ((c.inf + 3) >> 2) << 2;
     const float tcur = NJ_LDG(a.b.step_t + k), dt = NJ_LDG(a.b.step_dt + k);
+    float* in0 = NJN_FWD_IN(f, s, k & 1);
+    float* in1 = NJN_FWD_IN(f, s, (k + 1) & 1);
     for (int c_ = o; c_ < inf4; c_ += NJN_F) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -319,32 +331,47 @@ NJ_HD void nj_tpn_fwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, Nj
                 if (p >= 0 && a.h_hist) a.h_hist[((size_t)k * a.b.B + p) * c.H + c_ - c.d] = h;
                 v = nj_tanh(h);
             } else if (c_ < c.inf) v = nj_tpn_time_col(c, c_, f.F[NJP_F_TAU * RS + r], tcur);
-            f.w.IN[(size_t)r * s.sI + c_] = v;
+            in0[(size_t)r * s.sI + c_] = v;
+            // what stays the same until the next jump (tanh(last_X), tau) also goes into the rows of the other parity
+            if (c_ < c.d || c_ == c.d + c.H || c_ >= c.inf) in1[(size_t)r * s.sI + c_] = v;
         }
     }
     if (o == NJN_F - 1) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            f.w.RK[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(f.I[NJP_I_PATH * RS + r] + a.b.path_id_offset), (unsigned)k);
+            const unsigned rk = nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(f.I[NJP_I_PATH * RS + r] + a.b.path_id_offset), (unsigned)k);
+            NJN_FWD_LK(reg, s, k & 1, 0)[r] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 1));
+            NJN_FWD_LK(reg, s, k & 1, 1)[r] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 2));
             f.F[NJP_F_CA * RS + (k & 1) * 4 + r] = dt;            // (the loss-coefficient slots are free in the forward pass)
         }
     }
 }
 
-// the three phases of Euler step k for F thread o.  next: step k + 1 follows without a jump in between -- phase 3 then
-// also writes what changes in the input rows (tanh(h), the time columns), the history and the dropout keys of step k + 1
+// glue warp, while the F warps run step k: what step k + 1 needs besides tanh(h) -- time columns, step size, layer keys
 template <class D>
-NJ_HD void nj_tpn_fwd_p1(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, NjTpnF<D>& q, int o,
-                         int k, bool next) {
-    if (next && o == NJN_F - 1) {                 // time and step size of step k + 1, consumed in phase 3
-        nj_cp_async4(f.F + NJP_F_CB * NJP_RS + ((k + 1) & 1), a.b.step_t + k + 1);
-        nj_cp_async4(f.F + NJP_F_CB * NJP_RS + 2 + ((k + 1) & 1), a.b.step_dt + k + 1);
-    }
-    nj_tpn_hidden<D::KC0, D::R>(c, 0, q.w0, q.b0, o, f.w.IN, s.sI, f.w.A0, s.sA, f.w.RK);
+NJ_HD void nj_tpn_fwd_aux(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, float* reg, int lane, int k1) {
+    constexpr int R = D::R, RS = NJP_RS;
+    if (lane >= R) return;
+    const int r = lane;
+    const float tnext = NJ_LDG(a.b.step_t + k1), dnext = NJ_LDG(a.b.step_dt + k1);
+    const unsigned rk = nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(f.I[NJP_I_PATH * RS + r] + a.b.path_id_offset), (unsigned)k1);
+    NJN_FWD_LK(reg, s, k1 & 1, 0)[r] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 1));
+    NJN_FWD_LK(reg, s, k1 & 1, 1)[r] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 2));
+    f.F[NJP_F_CA * RS + (k1 & 1) * 4 + r] = dnext;
+    float* in1 = NJN_FWD_IN(f, s, k1 & 1);
+    const float tau = f.F[NJP_F_TAU * RS + r];
+    for (int c_ = c.d + c.H + 1; c_ < c.inf; ++c_) in1[(size_t)r * s.sI + c_] = nj_tpn_time_col(c, c_, tau, tnext);
+}
+
+// the three phases of Euler step k for F thread o.  next: step k + 1 follows without a jump in between -- phase 3 then
+// also writes tanh(h) into the input rows of step k + 1 and h into the history
+template <class D>
+NJ_HD void nj_tpn_fwd_p1(const NjCfg& c, const NjPath& s, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, float* reg, NjTpnF<D>& q, int o, int k) {
+    nj_tpn_hidden<D::KC0, D::R>(c, 0, q.w0, q.b0, o, NJN_FWD_IN(f, s, k & 1), s.sI, f.w.A0, s.sA, nullptr, NJN_FWD_LK(reg, s, k & 1, 0));
 }
 template <class D>
-NJ_HD void nj_tpn_fwd_p2(const NjCfg& c, const NjPath& s, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, NjTpnF<D>& q, int o) {
-    nj_tpn_hidden<D::KCH, D::R>(c, 1, q.w1, q.b1, o, f.w.A0, s.sA, f.w.A1, s.sA, f.w.RK);
+NJ_HD void nj_tpn_fwd_p2(const NjCfg& c, const NjPath& s, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, float* reg, NjTpnF<D>& q, int o, int k) {
+    nj_tpn_hidden<D::KCH, D::R>(c, 1, q.w1, q.b1, o, f.w.A0, s.sA, f.w.A1, s.sA, nullptr, NJN_FWD_LK(reg, s, k & 1, 1));
 }
 template <class D>
 NJ_HD void nj_tpn_fwd_p3(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPathFwd<(D::R >= 4 ? 4 : D::R), 1, true>& f, NjTpnF<D>& q, int o,
@@ -353,6 +380,7 @@ NJ_HD void nj_tpn_fwd_p3(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPat
     float acc[R];
     nj_tpn_dot<D::KCH, R>(q.w2, f.w.A1, s.sA, acc);
     if (o < c.H) {
+        float* in1 = NJN_FWD_IN(f, s, (k + 1) & 1);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float h = fmaf(f.F[NJP_F_CA * RS + (k & 1) * 4 + r], acc[r] + q.b2, f.HS[r * s.sH + o]);
@@ -360,19 +388,8 @@ NJ_HD void nj_tpn_fwd_p3(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPat
             if (next) {
                 const int p = f.I[NJP_I_PATH * RS + r];
                 if (p >= 0 && a.h_hist) a.h_hist[((size_t)(k + 1) * a.b.B + p) * c.H + o] = h;
-                f.w.IN[(size_t)r * s.sI + c.d + o] = nj_tanh(h);
+                in1[(size_t)r * s.sI + c.d + o] = nj_tanh(h);
             }
-        }
-    }
-    if (next && o == NJN_F - 1) {
-        nj_cp_wait();
-        const float tnext = f.F[NJP_F_CB * RS + ((k + 1) & 1)], dnext = f.F[NJP_F_CB * RS + 2 + ((k + 1) & 1)];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float tau = f.F[NJP_F_TAU * RS + r];
-            for (int c_ = c.d + c.H + 1; c_ < c.inf; ++c_) f.w.IN[(size_t)r * s.sI + c_] = nj_tpn_time_col(c, c_, tau, tnext);
-            f.w.RK[r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(f.I[NJP_I_PATH * RS + r] + a.b.path_id_offset), (unsigned)(k + 1));
-            f.F[NJP_F_CA * RS + ((k + 1) & 1) * 4 + r] = dnext;
         }
     }
 }
@@ -422,11 +439,11 @@ NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
             const int kend = nk < S ? nk : S;
             if (rec) {
                 for (; k < kend; ++k) {
-                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_build<D>(c, s, a, f, o, k); }
+                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_build<D>(c, s, a, f, reg, o, k); }
                     NJN_SYNC_F();
-                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p1<D>(c, s, a, f, NJN_FREGS(o), o, k, false); }
+                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p1<D>(c, s, f, reg, NJN_FREGS(o), o, k); }
                     NJN_SYNC_F();
-                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p2<D>(c, s, f, NJN_FREGS(o), o); }
+                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p2<D>(c, s, f, reg, NJN_FREGS(o), o, k); }
                     NJN_SYNC_F();
                     NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p3<D>(c, s, a, f, NJN_FREGS(o), o, k, false); }
                     NJ_SYNC();
@@ -434,16 +451,19 @@ NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
                     NJ_SYNC();
                 }
             } else if (k < kend) {
-                NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_build<D>(c, s, a, f, o, k); }
+                NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_build<D>(c, s, a, f, reg, o, k); }
                 NJN_SYNC_F();
                 for (; k < kend; ++k) {
                     const bool next = k + 1 < kend;
-                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p1<D>(c, s, a, f, NJN_FREGS(o), o, k, next); }
+                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p1<D>(c, s, f, reg, NJN_FREGS(o), o, k); }
                     NJN_SYNC_F();
-                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p2<D>(c, s, f, NJN_FREGS(o), o); }
+                    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p2<D>(c, s, f, reg, NJN_FREGS(o), o, k); }
                     NJN_SYNC_F();
                     NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_fwd_p3<D>(c, s, a, f, NJN_FREGS(o), o, k, next); }
-                    NJN_SYNC_F();
+                    if (next && (ROLE == NJN_ALL || ROLE == NJN_ROLE_G)) {
+                        NJ_WARPS(wp, 1) { if (wp == 0) { NJ_LANES(lane) { nj_tpn_fwd_aux<D>(c, s, a, f, reg, lane, k + 1); } } }
+                    }
+                    NJN_SYNC_STEP();
                 }
             }
             NJ_SYNC();                            // the state after the run is visible to the glue warp
@@ -476,6 +496,15 @@ NJ_HD void nj_tpn_cta_forward(const NjCfg& c, const NjPath& s, const NjArgs& a, 
 // backward
 // ================================================================================================
 NJ_HD void nj_tpn_set(NjPathB& t, int off) { t.IN += off; t.A += off; t.G += off; t.GOUT += off; }
+#define NJN_PRE_HDR 24
+// backward: the glue warp prepares the next step's scalars and dropout layer keys (1) or the F threads 0 and 63 do (0).
+// Measured on B200 (PhysioNet batch of 50): precomputed layer keys make the backward SLOWER (9.86 -> 10.4 ms, with the glue
+// warp or with thread 63 hashing them: three serial hashes in front of the phase instead of one per thread in parallel in its
+// epilogue), while the three-warp forward gains 21 % from the glue warp's help (4.92 -> 3.90 ms).
+#ifndef NJN_BWD_AUX
+#define NJN_BWD_AUX 0
+#endif
+#define NJN_BWD_LK(smem, s, par, l) (reinterpret_cast<int*>((smem) + (s).b_PRE + 4) + ((par) * 2 + (l)) * 4)
 
 // F, phase 1: the input rows of step e into its operand set (h from the history; the value was loaded one iteration ahead
 // when `have`), then the load for step e - 1 is issued (`pre`)
@@ -484,13 +513,16 @@ NJ_HD void nj_tpn_bwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, fl
                             int e, bool have, bool pre) {
     constexpr int R = D::R;
     const int P = s.P_b, inf4 = ((c.inf + 3) >> 2) << 2;
-    float* pre_f = smem + s.b_PRE;               // [0..1] time, [2..3] step size of the step (by parity), then h [2][P][sH]
-    float* HP = pre_f + 4;
+    // prefetch region: [0..1] time, [2..3] step size of the step (by parity), [4..19] dropout layer keys [parity][layer][4],
+    // then h [2][P][sH].  The scalars and keys of step e were written by the glue warp during the previous pipeline
+    // iteration (`have`), else (first step of a run) by this function.
+    float* pre_f = smem + s.b_PRE;
+    float* HP = pre_f + NJN_PRE_HDR;
     if (have) nj_cp_wait();                      // this thread's copies of the previous iteration (h of step e)
     const float tcur = have ? pre_f[e & 1] : NJ_LDG(a.b.step_t + e);
-    if (o == 0) {
-        if (!have) pre_f[2 + (e & 1)] = NJ_LDG(a.b.step_dt + e);
-        if (pre) { nj_cp_async4(pre_f + ((e - 1) & 1), a.b.step_t + e - 1); nj_cp_async4(pre_f + 2 + ((e - 1) & 1), a.b.step_dt + e - 1); }
+    if (o == 0 && !have) pre_f[2 + (e & 1)] = NJ_LDG(a.b.step_dt + e);
+    if (!NJN_BWD_AUX && o == 0 && pre) {         // (without the glue warp's help: thread 0 fetches the scalars of step e - 1)
+        nj_cp_async4(pre_f + ((e - 1) & 1), a.b.step_t + e - 1); nj_cp_async4(pre_f + 2 + ((e - 1) & 1), a.b.step_dt + e - 1);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {                // (the planner admits at most 2 * NJN_F input columns)
@@ -513,10 +545,37 @@ NJ_HD void nj_tpn_bwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, fl
             te.IN[(size_t)r * s.sI + c_] = v;
         }
     }
-    if (o == NJN_F - 1) {
+    if (o == NJN_F - 1 && (!have || !NJN_BWD_AUX)) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-            t0.I[NJB_I_RK * P + r] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(t0.I[NJB_I_PATH * P + r] + a.b.path_id_offset), (unsigned)e);
+        for (int r = 0; r < R; ++r) {
+            const unsigned rk = nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(t0.I[NJB_I_PATH * P + r] + a.b.path_id_offset), (unsigned)e);
+            if (NJN_BWD_AUX) {
+                NJN_BWD_LK(smem, s, e & 1, 0)[r] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 1));
+                NJN_BWD_LK(smem, s, e & 1, 1)[r] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 2));
+            } else t0.I[NJB_I_RK * P + r] = (int)rk;     // (every F thread derives the layer keys itself, in parallel)
+        }
+    }
+}
+
+// glue warp, while F rebuilds step e: time, step size and dropout layer keys of step e - 1 (the next one F rebuilds)
+template <class D>
+NJ_HD void nj_tpn_bwd_aux(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem, const NjPathB& t0, int lane, int e1,
+                          bool staged, bool more) {
+    constexpr int R = D::R;
+    const int P = s.P_b;
+    float* pre_f = smem + s.b_PRE;
+    if (lane == 0) {
+        // the two scalars travel through a staging pair ([20..21] of the region) filled by cp.async one iteration ahead
+        float tv, dv;
+        if (staged) { nj_cp_wait(); tv = pre_f[20]; dv = pre_f[21]; }
+        else { tv = NJ_LDG(a.b.step_t + e1); dv = NJ_LDG(a.b.step_dt + e1); }
+        pre_f[e1 & 1] = tv; pre_f[2 + (e1 & 1)] = dv;
+        if (more) { nj_cp_async4(pre_f + 20, a.b.step_t + e1 - 1); nj_cp_async4(pre_f + 21, a.b.step_dt + e1 - 1); }
+    }
+    if (lane < R) {
+        const unsigned rk = nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(t0.I[NJB_I_PATH * P + lane] + a.b.path_id_offset), (unsigned)e1);
+        NJN_BWD_LK(smem, s, e1 & 1, 0)[lane] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 1));
+        NJN_BWD_LK(smem, s, e1 & 1, 1)[lane] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 2));
     }
 }
 
@@ -741,18 +800,20 @@ NJ_HD void nj_tpn_bwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
                 NJN_SYNC_FT();
                 // phase 2
                 NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) {
-                    if (vF) nj_tpn_hidden<D::KC0, R>(c, 0, NJN_FREGS(o).w0, NJN_FREGS(o).b0, o, tF.IN, s.sI, tF.A, s.sA, t.I + NJB_I_RK * P);
+                    if (vF) nj_tpn_hidden<D::KC0, R>(c, 0, NJN_FREGS(o).w0, NJN_FREGS(o).b0, o, tF.IN, s.sI, tF.A, s.sA, t.I + NJB_I_RK * P, NJN_BWD_AUX ? NJN_BWD_LK(smem, s, eF & 1, 0) : nullptr);
                 }
                 NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) { if (vT) nj_tpn_bwd_t2<D>(c, s, tT, NJN_TREGS(x), x); }
                 NJN_SYNC_FT();
                 // phase 3
                 NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) {
-                    if (vF) nj_tpn_hidden<D::KCH, R>(c, 1, NJN_FREGS(o).w1, NJN_FREGS(o).b1, o, tF.A, s.sA, tF.A + P * s.sA, s.sA, t.I + NJB_I_RK * P);
-                    if (o == 0) nj_cp_wait();            // time / step size of the next step: visible to everyone after the barrier
+                    if (vF) nj_tpn_hidden<D::KCH, R>(c, 1, NJN_FREGS(o).w1, NJN_FREGS(o).b1, o, tF.A, s.sA, tF.A + P * s.sA, s.sA, t.I + NJB_I_RK * P, NJN_BWD_AUX ? NJN_BWD_LK(smem, s, eF & 1, 1) : nullptr);
+                    if (!NJN_BWD_AUX && o == 0) nj_cp_wait();          // scalars of the next step: visible to everyone after the barrier
                 }
                 NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) {
                     if (vT || vF) nj_tpn_bwd_t3<D>(c, s, t, vT ? &tT : nullptr, vF ? &tF : nullptr, smem[s.b_PRE + 2 + (eF & 1)], NJN_TREGS(x), x);
                 }
+                // the glue warp, idle during a run: scalars and dropout keys of the step F rebuilds next
+                if (NJN_BWD_AUX && j + 1 < n && G) { NJ_WARPS(wp, 1) { if (wp == 0) { NJ_LANES(lane) { nj_tpn_bwd_aux<D>(c, s, a, smem, t, lane, eF - 1, j > 0, j + 2 < n); } } } }
                 NJ_SYNC();
             }
             k = lo;
