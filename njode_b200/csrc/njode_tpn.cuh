@@ -497,10 +497,10 @@ NJ_HD void nj_tpn_cta_forward(const NjCfg& c, const NjPath& s, const NjArgs& a, 
 // ================================================================================================
 NJ_HD void nj_tpn_set(NjPathB& t, int off) { t.IN += off; t.A += off; t.G += off; t.GOUT += off; }
 #define NJN_PRE_HDR 24
-// backward: the glue warp prepares the next step's scalars and dropout layer keys (1) or the F threads 0 and 63 do (0).
-// Measured on B200 (PhysioNet batch of 50): precomputed layer keys make the backward SLOWER (9.86 -> 10.4 ms, with the glue
-// warp or with thread 63 hashing them: three serial hashes in front of the phase instead of one per thread in parallel in its
-// epilogue), while the three-warp forward gains 21 % from the glue warp's help (4.92 -> 3.90 ms).
+// backward: the glue warp fetches the next step's scalars and hashes its row keys (1) or the F threads 0 and 63 do (0).
+// Measured on B200 (PhysioNet batch of 50, backward kernel): 9.57 ms without the glue warp's help, 10.30 ms with it (and
+// 10.4 ms when it also precomputes the layer keys): the backward's eight warps share four schedulers, a busy glue warp
+// competes with a T warp.  The three-warp forward gains 21 % from the same move (4.92 -> 3.90 ms).
 #ifndef NJN_BWD_AUX
 #define NJN_BWD_AUX 0
 #endif
@@ -549,10 +549,8 @@ NJ_HD void nj_tpn_bwd_build(const NjCfg& c, const NjPath& s, const NjArgs& a, fl
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const unsigned rk = nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(t0.I[NJB_I_PATH * P + r] + a.b.path_id_offset), (unsigned)e);
-            if (NJN_BWD_AUX) {
-                NJN_BWD_LK(smem, s, e & 1, 0)[r] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 1));
-                NJN_BWD_LK(smem, s, e & 1, 1)[r] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 2));
-            } else t0.I[NJB_I_RK * P + r] = (int)rk;     // (every F thread derives the layer keys itself, in parallel)
+            if (NJN_BWD_AUX) NJN_BWD_LK(smem, s, e & 1, 0)[r] = (int)rk;
+            else t0.I[NJB_I_RK * P + r] = (int)rk;       // (every F thread derives the layer keys itself, in parallel)
         }
     }
 }
@@ -572,11 +570,9 @@ NJ_HD void nj_tpn_bwd_aux(const NjCfg& c, const NjPath& s, const NjArgs& a, floa
         pre_f[e1 & 1] = tv; pre_f[2 + (e1 & 1)] = dv;
         if (more) { nj_cp_async4(pre_f + 20, a.b.step_t + e1 - 1); nj_cp_async4(pre_f + 21, a.b.step_dt + e1 - 1); }
     }
-    if (lane < R) {
-        const unsigned rk = nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(t0.I[NJB_I_PATH * P + lane] + a.b.path_id_offset), (unsigned)e1);
-        NJN_BWD_LK(smem, s, e1 & 1, 0)[lane] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 1));
-        NJN_BWD_LK(smem, s, e1 & 1, 1)[lane] = (int)nj_layer_key(rk, (unsigned)(NJODE_NET_ODE * 16 + 2));
-    }
+    // row keys of step e1, by parity (the F threads derive their layer keys from them in their epilogues)
+    if (lane < R)
+        NJN_BWD_LK(smem, s, e1 & 1, 0)[lane] = (int)nj_row_key(c.seed_lo, c.seed_hi, (unsigned)(t0.I[NJB_I_PATH * P + lane] + a.b.path_id_offset), (unsigned)e1);
 }
 
 // T: gradient of hidden layer l's pre-activation from the partial sum over the next layer's outputs
@@ -800,13 +796,13 @@ NJ_HD void nj_tpn_bwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
                 NJN_SYNC_FT();
                 // phase 2
                 NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) {
-                    if (vF) nj_tpn_hidden<D::KC0, R>(c, 0, NJN_FREGS(o).w0, NJN_FREGS(o).b0, o, tF.IN, s.sI, tF.A, s.sA, t.I + NJB_I_RK * P, NJN_BWD_AUX ? NJN_BWD_LK(smem, s, eF & 1, 0) : nullptr);
+                    if (vF) nj_tpn_hidden<D::KC0, R>(c, 0, NJN_FREGS(o).w0, NJN_FREGS(o).b0, o, tF.IN, s.sI, tF.A, s.sA, NJN_BWD_AUX ? NJN_BWD_LK(smem, s, eF & 1, 0) : t.I + NJB_I_RK * P);
                 }
                 NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) { if (vT) nj_tpn_bwd_t2<D>(c, s, tT, NJN_TREGS(x), x); }
                 NJN_SYNC_FT();
                 // phase 3
                 NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) {
-                    if (vF) nj_tpn_hidden<D::KCH, R>(c, 1, NJN_FREGS(o).w1, NJN_FREGS(o).b1, o, tF.A, s.sA, tF.A + P * s.sA, s.sA, t.I + NJB_I_RK * P, NJN_BWD_AUX ? NJN_BWD_LK(smem, s, eF & 1, 1) : nullptr);
+                    if (vF) nj_tpn_hidden<D::KCH, R>(c, 1, NJN_FREGS(o).w1, NJN_FREGS(o).b1, o, tF.A, s.sA, tF.A + P * s.sA, s.sA, NJN_BWD_AUX ? NJN_BWD_LK(smem, s, eF & 1, 0) : t.I + NJB_I_RK * P);
                     if (!NJN_BWD_AUX && o == 0) nj_cp_wait();          // scalars of the next step: visible to everyone after the barrier
                 }
                 NJN_ROLE(NJN_ROLE_T, NJN_T0, NJN_T, x) {
