@@ -71,7 +71,7 @@ cudaError_t nj_launch_tpn(const NjPlanOut& pl, const NjArgs& a, bool bwd, cudaSt
 
 cudaError_t nj_launch_path(const NjPlanOut& pl, const NjArgs& a, bool bwd, cudaStream_t st, const char** name) {
     const NjPath& p = pl.path;
-    if (p.tpn) return nj_launch_tpn(pl, a, bwd, st, name);
+    if (p.tpn && (bwd || p.tpn_fwd)) return nj_launch_tpn(pl, a, bwd, st, name);
     nj_path_kern_t kern;
     if (!bwd) kern = p.stat ? nj_stat_pick(p.rg_f, p.tr_f, false, name) : nj_path_pick(p.rg_f, p.tr_f, false, name);
     else kern = p.stat ? nj_stat_pick(p.rg_b, p.tr_b, true, name)

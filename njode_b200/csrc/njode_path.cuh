@@ -46,7 +46,7 @@ struct NjPath {
     int pipe, b_copy;
     // thread-per-neuron kernels of small batches (njode_tpn.cuh): dimension class (1: demo networks, 2: PhysioNet-shaped),
     // operand buffers three times
-    int tpn, b_TD, b_PRE, f_MB, b_MB, b_GIMG, f_IN2, f_AUX;
+    int tpn, tpn_fwd, b_TD, b_PRE, f_MB, b_MB, b_GIMG, f_IN2, f_AUX;      // tpn_fwd: the forward takes them too (else warp kernels)
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -260,6 +260,15 @@ static inline bool nj_make_plan(const njode_model_t& m, int n_units_fwd, int n_u
 // ------------------------------------------------------------------------------------------------
 // segment fast path (njode_seg.cuh): eligibility + shared-memory layout
 // ------------------------------------------------------------------------------------------------
+// whole-path batches of at most this many paths per SM take the thread-per-neuron kernels, one path per tile (measured on B200)
+// (B200, PhysioNet nets, ms per pass: thread per neuron 0.025 / 0.058 per path forward / backward, pipelined warps
+// 17 + 0.0048 / 36 + 0.044 per path: the forward crosses over at ~5.7 paths per SM, the backward at ~17; profiles/r2af_*)
+#ifndef NJ_TPN_MAX_WAVES
+#define NJ_TPN_MAX_WAVES 16
+#endif
+#ifndef NJ_TPN_MAX_WAVES_FWD
+#define NJ_TPN_MAX_WAVES_FWD 5
+#endif
 // segment batches of at most this many units per SM take the thread-per-neuron kernels (measured on B200)
 #ifndef NJ_SEGTPN_MAX_UNITS_PER_SM
 #define NJ_SEGTPN_MAX_UNITS_PER_SM 32
@@ -551,6 +560,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
     }
     // ---- thread-per-neuron kernels (njode_tpn.cuh): tiles of 1 or 4 paths, one per SM, ODE network of a known dimension class ----
     int tpn_R = 0;
+    bool tpn_fwd = true;
     {
         const NjNet& O = c.net[NJODE_NET_ODE];
         const char* nt_ = getenv("NJODE_NO_TPN");
@@ -564,12 +574,20 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         if (cls) {
             // tiles of 4 paths exist (tests, NJODE_FORCE_TPN) but lose to the pipelined warp kernels on B200 (300 PhysioNet
             // records: 80 against 67 ms; 500 demo paths with the GRU jump: 3.9 against 3.0 ms): one path per CTA only
-            if (n <= num_sms) tpn_R = 1;
+            // Several paths per SM are served as several one-path tiles per CTA in sequence (atomic tile counter), up to
+            // NJ_TPN_MAX_WAVES tiles per CTA (env NJODE_TPN_WAVES): beyond that the 12-warp pipelined kernels win.
+            const char* tw_ = getenv("NJODE_TPN_WAVES");
+            const char* twf_ = getenv("NJODE_TPN_WAVES_FWD");
+            // (the demo networks (class A) cross over at ~5 paths per SM in both passes: GRU jump, 500 paths 2.28 against
+            // 3.02 ms, extrapolated crossover at ~730 paths)
+            const int waves = tw_ ? atoi(tw_) : (cls == 1 ? NJ_TPN_MAX_WAVES_FWD : NJ_TPN_MAX_WAVES);
+            const int waves_f = twf_ ? atoi(twf_) : (tw_ ? atoi(tw_) : NJ_TPN_MAX_WAVES_FWD);
+            if (n <= std::max(1, waves) * num_sms) { tpn_R = 1; tpn_fwd = n <= std::max(1, waves_f) * num_sms; }
             else if (ft_ && atoi(ft_)) tpn_R = 4;
             if (force_r && (tpn_R || (ft_ && atoi(ft_)))) tpn_R = (force_r == 1 || force_r == 4) ? force_r : 0;
         }
         if (tpn_R) {
-            s.tpn = cls; s.stat = 0; s.nw_s = 0; stat_R = 0;
+            s.tpn = cls; s.tpn_fwd = tpn_fwd ? 1 : 0; s.stat = 0; s.nw_s = 0; stat_R = 0;
             const int kc0 = cls == 1 ? NJN_A_KC0 : NJN_B_KC0, kch = cls == 1 ? NJN_A_KCH : NJN_B_KCH, hc = cls == 1 ? NJN_A_HC : NJN_B_HC;
             // the register tiles read whole classes of columns: rows at least that wide (the padding stays zero)
             s.sI = std::max(s.sI, nj_stride_act(4 * kc0));
@@ -610,9 +628,9 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             s.f_F = o; o += NJP_F_COUNT * NJP_RS;
             s.f_I = o; o += NJP_I_COUNT * NJP_RS + 4;
             o = (o + 3) & ~3;
-            s.f_MB = o; if (s.tpn) o += (int)((sizeof(NjCoopMB) + 15) / 16) * 4;    // mailbox of the cooperative jump layers
-            s.f_IN2 = o; if (s.tpn) o += R * s.sI;                                // input rows of the other step parity
-            s.f_AUX = o; if (s.tpn) o += 16;                                      // dropout layer keys [parity][layer][4]
+            s.f_MB = o; if (s.tpn && s.tpn_fwd) o += (int)((sizeof(NjCoopMB) + 15) / 16) * 4;    // mailbox of the cooperative jump layers
+            s.f_IN2 = o; if (s.tpn && s.tpn_fwd) o += R * s.sI;                                // input rows of the other step parity
+            s.f_AUX = o; if (s.tpn && s.tpn_fwd) o += 16;                                      // dropout layer keys [parity][layer][4]
             return (o + 3) & ~3;
         };
         // the smallest tile height whose warps still fit the machine in one wave of 12-warp CTAs: smaller tiles = more
@@ -622,7 +640,7 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             if ((n + cand - 1) / cand <= num_sms * 12) { R = cand; break; }
         if (force_r) R = force_r;
         if (s.stat) R = stat_R;
-        if (s.tpn) R = tpn_R;
+        if (s.tpn && s.tpn_fwd) R = tpn_R;
         shape(R, s.rg_f, s.tr_f);
         s.f_region = region(R);
         s.f_warp0 = c.img_floats;
@@ -632,10 +650,12 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             if ((size_t)(c.img_floats + cand * s.f_region) * 4 <= smem_limit) { nw = cand; break; }
         if (!nw) return;
         nw = std::max(1, std::min(nw, (s.n_tiles_f + num_sms - 1) / num_sms));
-        if (s.stat || s.tpn) nw = 1;                          // one tile per CTA at a time, all warps on it
+        if (s.stat || (s.tpn && s.tpn_fwd)) nw = 1;           // one tile per CTA at a time, all warps on it
         s.nw_f = nw;
         s.f_smem_floats = c.img_floats + nw * s.f_region;
         out.path_grid_f = std::max(1, std::min((s.n_tiles_f + nw - 1) / nw, num_sms));
+        // thread-per-neuron forward CTAs are 3 warps with up to 255 registers: two fit an SM
+        if (s.tpn && s.tpn_fwd) out.path_grid_f = std::max(1, std::min(s.n_tiles_f, 2 * num_sms));
         out.path_smem_f_bytes = (size_t)s.f_smem_floats * 4;
     }
     // ---- backward: CTA-level arrays of P rows ----

@@ -43,12 +43,12 @@ static int plan_for(const njode_model_t* m, const njode_batch_t* b, NjPlanOut& o
 
 // test hook (host simulation only): which kernel family the planner picks for (model, batch) --
 // bit 0 segment units, 1 their weight-stationary kernels, 2 whole-path warp kernels, 3 their weight-stationary kernels,
-// 4 pipelined path backward
+// 4 pipelined path backward, 5 thread-per-neuron backward, 6 thread-per-neuron forward too
 extern "C" int njode_hostsim_plan_kind(const njode_model_t* model, const njode_batch_t* bs) {
     NjPlanOut o;
     if (int rc = plan_for(model, bs, o)) return rc;
     return (o.seg.ok ? 1 : 0) | (o.seg.ok && o.seg.tpn ? 2 : 0) | (o.path.ok ? 4 : 0) | (o.path.ok && o.path.stat ? 8 : 0) |
-           (o.path.ok && o.path.pipe ? 16 : 0) | (o.path.ok && o.path.tpn ? 32 : 0);
+           (o.path.ok && o.path.pipe ? 16 : 0) | (o.path.ok && o.path.tpn ? 32 : 0) | (o.path.ok && o.path.tpn && o.path.tpn_fwd ? 64 : 0);
 }
 
 extern "C" int njode_plan(const njode_model_t* model, const njode_batch_t* bs, int, njode_plan_t* p) {
@@ -116,7 +116,7 @@ extern "C" int njode_forward(const njode_model_t* model, const njode_batch_t* ba
         for (int cta = 0; cta < pl.path_grid_f; ++cta) {
             std::fill(smem.begin(), smem.end(), NAN);
             if (cta == 0) *a.counter = 0;
-            if (pl.path.tpn) {
+            if (pl.path.tpn && pl.path.tpn_fwd) {
                 const int R = pl.path.rg_f * pl.path.tr_f;
                 if (pl.path.tpn == 1 && R == 1) nj_tpn_cta_forward<NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 1>>(pl.fwd, pl.path, a, smem.data());
                 else if (pl.path.tpn == 1) nj_tpn_cta_forward<NjTpnDims<NJN_A_KC0, NJN_A_KCH, NJN_A_HC, 4>>(pl.fwd, pl.path, a, smem.data());

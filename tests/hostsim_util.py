@@ -58,4 +58,4 @@ def plan_kind(model, pb, which="fwd"):
     mt = model._model_struct(0)
     bits = dll.njode_hostsim_plan_kind(C.byref(mt), C.byref(getattr(pb, which)))
     assert bits >= 0, bits
-    return {n for i, n in enumerate(("seg", "segstat", "path", "pathstat", "pipe", "tpn")) if bits >> i & 1}
+    return {n for i, n in enumerate(("seg", "segstat", "path", "pathstat", "pipe", "tpn", "tpn_fwd")) if bits >> i & 1}

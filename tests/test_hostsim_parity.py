@@ -465,16 +465,32 @@ def test_saved_activations_train_mode_dropout_marks_survive():
 
 
 def test_planner_kernel_families_for_whole_path_batches():
-    """B200 launch plan: up to one path per SM -> thread per neuron (K-split stationary kernels for ODE networks outside
-    the dimension classes); more -> the pipelined warp kernels (measured: profiles/r2z2_*)"""
+    """B200 launch plan (measured thresholds, profiles/r2af_*): up to 5 paths per SM -> thread per neuron, one path per tile,
+    forward and backward; up to 16 -> thread per neuron backward, warp-GEMM forward; more -> the pipelined warp kernels;
+    ODE networks outside the dimension classes: K-split stationary kernels up to one path per SM"""
     os.environ["NJODE_SIM_SMS"] = "148"
-    for B, layers, want in ((50, 2, "tpn"), (148, 2, "tpn"), (300, 2, "pipe"), (600, 2, "pipe"), (50, 1, "pathstat")):
+    for B, layers, want in ((50, 2, {"tpn", "tpn_fwd"}), (600, 2, {"tpn", "tpn_fwd"}), (2000, 2, {"tpn"}), (3000, 2, {"pipe"}),
+                            (50, 1, {"pathstat"})):
         cfg = dict(cases.CONFIGS["masked_physio"], ode_nn=[[50, "tanh"]] * layers)
         m = models.NJODE(**cfg)
         batch = cases.irregular_batch(B, 41, 6, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
         pb = m.prepare_batch(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 1.0 / 6, 1 + 1e-12, batch["start_X"],
                              batch["n_obs_ot"], M=batch["M"])
-        for which in ("fwd", "bwd_all"):
-            kind = hostsim_util.plan_kind(m, pb, which)
-            assert "path" in kind and (want in kind or which == "fwd" and want == "pipe"), (B, layers, which, kind)
-            assert not ({"tpn", "pathstat"} - {want}) & kind, (B, layers, which, kind)
+        kind = hostsim_util.plan_kind(m, pb, "bwd_all")
+        assert "path" in kind and kind & {"tpn", "tpn_fwd", "pipe", "pathstat"} == want, (B, layers, kind)
+
+
+def test_thread_per_neuron_backward_after_a_warp_gemm_forward():
+    """mid-size batches: the forward runs on the warp kernels, the backward on the thread-per-neuron kernels (same saved
+    history); several one-path tiles per CTA"""
+    os.environ["NJODE_TPN_WAVES_FWD"] = "0"
+    os.environ["NJODE_TPN_WAVES"] = "16"
+    try:
+        for name in ("masked_small", "gru_demo"):
+            parity_util.check_training_call(name, "cpu", with_hT_grad=True)
+        cfg = dict(cases.CONFIGS["masked_physio"], dropout_rate=0.2)
+        batch = cases.irregular_batch(30, 41, 12, seed=17, masked=True, times_f32=True, obs_at_zero=True, row_prob=0.25, feat_prob=0.12)
+        parity_util.check_against_oracle(cfg, batch, 1.0 / 12, 1 + 1e-12, seed=5, device="cpu", train=True, grad_hT=True)
+    finally:
+        os.environ.pop("NJODE_TPN_WAVES_FWD", None)
+        os.environ.pop("NJODE_TPN_WAVES", None)
