@@ -463,6 +463,7 @@ static inline void nj_make_seg(const NjCfg& c, const njode_batch_t& b, int num_s
         if (force_nw) nw = std::max(2, std::min(12, force_nw));
         s.nw_f = nw;
         s.f_smem_floats = c.img_floats + nw * s.f_region;
+
     }
     // ---- backward: CTA-level arrays of P = 8 * nw rows (tallest tile) ----
     {
@@ -581,7 +582,8 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             // (the demo networks (class A) cross over at ~5 paths per SM in both passes: GRU jump, 500 paths 2.28 against
             // 3.02 ms, extrapolated crossover at ~730 paths)
             const int waves = tw_ ? atoi(tw_) : (cls == 1 ? NJ_TPN_MAX_WAVES_FWD : NJ_TPN_MAX_WAVES);
-            const int waves_f = twf_ ? atoi(twf_) : (tw_ ? atoi(tw_) : NJ_TPN_MAX_WAVES_FWD);
+            // (class B forward, two CTAs per SM since only the jump networks' image is staged: 0.0185 ms per path, crossover at ~8)
+            const int waves_f = twf_ ? atoi(twf_) : (tw_ ? atoi(tw_) : (cls == 1 ? NJ_TPN_MAX_WAVES_FWD : 8));
             if (n <= std::max(1, waves) * num_sms) { tpn_R = 1; tpn_fwd = n <= std::max(1, waves_f) * num_sms; }
             else if (ft_ && atoi(ft_)) tpn_R = 4;
             if (force_r && (tpn_R || (ft_ && atoi(ft_)))) tpn_R = (force_r == 1 || force_r == 4) ? force_r : 0;
@@ -653,6 +655,12 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
         if (s.stat || (s.tpn && s.tpn_fwd)) nw = 1;           // one tile per CTA at a time, all warps on it
         s.nw_f = nw;
         s.f_smem_floats = c.img_floats + nw * s.f_region;
+        if (s.tpn && s.tpn_fwd) {
+            // the thread-per-neuron forward holds the ODE network in registers: only the jump networks' part of the image is
+            // staged in shared memory (PhysioNet nets: 112 -> 72 KB, so two of its 3-warp CTAs fit an SM)
+            s.f_warp0 = c.img_floats - c.net[NJODE_NET_ENC].w_img[0];
+            s.f_smem_floats = s.f_warp0 + s.f_region;
+        }
         out.path_grid_f = std::max(1, std::min((s.n_tiles_f + nw - 1) / nw, num_sms));
         // thread-per-neuron forward CTAs are 3 warps with up to 255 registers: two fit an SM
         if (s.tpn && s.tpn_fwd) out.path_grid_f = std::max(1, std::min(s.n_tiles_f, 2 * num_sms));

@@ -413,7 +413,7 @@ NJ_HD void nj_tpn_fwd_p3(const NjCfg& c, const NjPath& s, const NjArgs& a, NjPat
 template <class D, int ROLE>
 NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem) {
     constexpr int R = D::R, RG = (R >= 4 ? 4 : R);
-    const float* simg = smem;
+    const float* simg = smem - c.net[NJODE_NET_ENC].w_img[0];      // image offsets of the jump networks land in the staged part
     float* reg = smem + s.f_warp0;
     int* slot = reinterpret_cast<int*>(reg + s.f_I) + NJP_I_COUNT * NJP_RS;
     NjPathFwd<RG, 1, true> f(c, s, a, reg, simg);
@@ -421,7 +421,7 @@ NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
     NJ_THREADS(tid, NJN_NT_FWD) { if (tid == 0) { mb->R = R; mb->op = 0; } }
     f.w.coop = mb;
     NJN_FREGS_DECL(D);
-    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_f_load<D>(c, simg, o, NJN_FREGS(o)); }
+    NJN_ROLE(NJN_ROLE_F, NJN_F0, NJN_F, o) { nj_tpn_f_load<D>(c, a.image, o, NJN_FREGS(o)); }
     const bool rec = a.b.E > 0;
     const int S = a.b.S;
     for (;;) {
@@ -481,7 +481,9 @@ NJ_HD void nj_tpn_fwd_body(const NjCfg& c, const NjPath& s, const NjArgs& a, flo
 
 template <class D>
 NJ_HD void nj_tpn_cta_forward(const NjCfg& c, const NjPath& s, const NjArgs& a, float* smem) {
-    nj_stage_image(smem, a.image, c.img_floats, NJN_NT_FWD);
+    // (only the jump networks' part of the parameter image: the ODE network goes from global memory straight into registers)
+    const int ode_floats = c.net[NJODE_NET_ENC].w_img[0];
+    nj_stage_image(smem, a.image + ode_floats, c.img_floats - ode_floats, NJN_NT_FWD);
     nj_zero(smem + s.f_warp0, s.f_region, NJN_NT_FWD);
     NJ_SYNC();
 #if defined(NJODE_HOST_SIM)
