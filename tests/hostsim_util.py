@@ -52,10 +52,10 @@ def uninstall():
 
 
 def plan_kind(model, pb, which="fwd"):
-    """kernel family the planner picks: set of {"seg", "segstat", "path", "pathstat", "pipe"} (see njode_hostsim_plan_kind)"""
+    """kernel family the planner picks: set of {"seg", "segtpn", "path", "pathstat", "pipe", "tpn", "tpn_fwd"} (see njode_hostsim_plan_kind)"""
     import ctypes as C
     dll = runner().lib.dll
     mt = model._model_struct(0)
     bits = dll.njode_hostsim_plan_kind(C.byref(mt), C.byref(getattr(pb, which)))
     assert bits >= 0, bits
-    return {n for i, n in enumerate(("seg", "segstat", "path", "pathstat", "pipe", "tpn", "tpn_fwd")) if bits >> i & 1}
+    return {n for i, n in enumerate(("seg", "segtpn", "path", "pathstat", "pipe", "tpn", "tpn_fwd")) if bits >> i & 1}

@@ -407,7 +407,7 @@ def test_segment_thread_per_neuron_kernels_train_mode_dropout(d):
     batch = cases.grid_batch(40, d, 25, 0.2, seed=16)
     m = models.NJODE(**cfg)
     pb = m.prepare_batch(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 0.04, 1.0, batch["start_X"], batch["n_obs_ot"])
-    assert "segstat" in hostsim_util.plan_kind(m, pb, "fwd") and "segstat" in hostsim_util.plan_kind(m, pb, "bwd_loss")
+    assert "segtpn" in hostsim_util.plan_kind(m, pb, "fwd") and "segtpn" in hostsim_util.plan_kind(m, pb, "bwd_loss")
     parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=True)
     parity_util.check_against_oracle(cfg, batch, 0.04, 1.0, seed=12, device="cpu", train=True, grad_hT=False)
 
@@ -440,7 +440,7 @@ def test_planner_gives_the_reference_batch_to_the_thread_per_neuron_kernels():
         pb = m.prepare_batch(batch["times"], batch["time_ptr"], batch["X"], batch["obs_idx"], 0.01, 1.0, batch["start_X"], batch["n_obs_ot"])
         for which in ("fwd", "bwd_all", "bwd_loss"):
             kind = hostsim_util.plan_kind(m, pb, which)
-            assert "seg" in kind and ("segstat" in kind) == want, (B, layers, which, kind)
+            assert "seg" in kind and ("segtpn" in kind) == want, (B, layers, which, kind)
 
 
 # ---- saved hidden activations (njode_plan_t.act_bytes / njode_saved_t.act_hist): the default; without them the segment
