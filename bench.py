@@ -88,6 +88,8 @@ WORKLOADS = {
                             obs_perc=0.1, dropout=0.1, use_rnn=True, cpu_sample_paths=500),
     "bs_demo_gru_1k": dict(sde="BlackScholes", paths=1000, steps=100, d=1, H=10, width=50, layers=2,
                            obs_perc=0.1, dropout=0.1, use_rnn=True, cpu_sample_paths=500),
+    "bs_demo_600": dict(sde="BlackScholes", paths=600, steps=100, d=1, H=10, width=50, layers=2,
+                        obs_perc=0.1, dropout=0.1, cpu_sample_paths=600),
     "bs_demo_400": dict(sde="BlackScholes", paths=400, steps=100, d=1, H=10, width=50, layers=2,
                         obs_perc=0.1, dropout=0.1, cpu_sample_paths=400),
     "physionet_synth_b2000": dict(sde="physionet_synth", paths=2000, steps=3000, d=41, H=41, width=50, layers=2,
