@@ -584,7 +584,10 @@ static inline void nj_make_path(const NjCfg& c, const njode_batch_t& b, int num_
             const int waves = tw_ ? atoi(tw_) : (cls == 1 ? NJ_TPN_MAX_WAVES_FWD : NJ_TPN_MAX_WAVES);
             // (class B forward, two CTAs per SM since only the jump networks' image is staged: 0.0185 ms per path, crossover at ~8)
             const int waves_f = twf_ ? atoi(twf_) : (tw_ ? atoi(tw_) : (cls == 1 ? NJ_TPN_MAX_WAVES_FWD : 8));
-            if (n <= std::max(1, waves) * num_sms) { tpn_R = 1; tpn_fwd = n <= std::max(1, waves_f) * num_sms; }
+            // (calls that record the path -- evaluation, E > 0 -- run a readout on the glue warp after every step: there the
+            // warp kernels win beyond one path per SM: 500 demo paths 1.87 against 1.43 ms, 100 paths 1.02 against 1.36)
+            const int w_b = b.E > 0 ? 1 : std::max(1, waves), w_f = b.E > 0 ? 1 : std::max(1, waves_f);
+            if (n <= w_b * num_sms) { tpn_R = 1; tpn_fwd = n <= w_f * num_sms; }
             else if (ft_ && atoi(ft_)) tpn_R = 4;
             if (force_r && (tpn_R || (ft_ && atoi(ft_)))) tpn_R = (force_r == 1 || force_r == 4) ? force_r : 0;
         }
